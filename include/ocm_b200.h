@@ -1,0 +1,169 @@
+/*
+ * ocm_b200.h — C ABI of the B200-native coarse-grained MD engine.
+ *
+ * This is the drop-in boundary.  In the reference (yutakasi634/OpenCafeMol) the
+ * per-step hot path sits behind the OpenMM C++ API: every
+ * `*ForceFieldGenerator::generate()` emits an `OpenMM::Force`, `SystemGenerator::generate()`
+ * an `OpenMM::System`, `Simulator` owns an `OpenMM::Context` and calls
+ * `integrator->step(save_step)` / `context.getState(...)`.  Each entry point below names the
+ * reference interface it replaces (file:line under the reference's `src/`).
+ *
+ * Conventions
+ *   - units are OpenMM's: nm, ps, amu, kJ/mol, rad, K, elementary charge;
+ *   - every function returns 0 on success, non-zero on failure; the message is then readable
+ *     with ocm_last_error() (thread-local);
+ *   - handles are opaque, owned by the library, released with the matching *_destroy;
+ *   - all arrays are caller-owned host memory, copied during the call;
+ *   - `group` is the force-group id (0..31) whose energy getState reports separately
+ *     (SystemGenerator.cpp:4-32, Observer.cpp:324-346);
+ *   - `periodic` != 0 applies the orthorhombic minimum image (setUsesPeriodicBoundaryConditions /
+ *     CutoffPeriodic); it requires a box at ocm_system_create.
+ *   - index arrays are int32, flattened row-major (ij: 2 per term, ijk: 3, ijkl: 4).
+ */
+#ifndef OCM_B200_H
+#define OCM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ocm_system  ocm_system;
+typedef struct ocm_context ocm_context;
+
+/* Exclusions and interaction groups of one pair ("CustomNonbondedForce"-like) term.
+ * Replaces CustomNonbondedForce::addExclusion / addInteractionGroup as used by e.g.
+ * forcefield/ExcludedVolumeForceFieldGenerator.cpp:62-90 and forcefield/InteractionGroup.hpp:19-101.
+ * n_igroups == 0 means "every bead with a parameter interacts with every other".
+ * Group g couples set1 (members set1[set1_off[g] .. set1_off[g+1])) with set2 likewise; a pair
+ * interacts if one bead is in set1 and the other in set2 of some group. */
+typedef struct ocm_pair_topology {
+    int64_t        n_excl;     /* number of excluded pairs                              */
+    const int32_t* excl_ij;    /* 2*n_excl bead indices                                 */
+    int32_t        n_igroups;  /* number of interaction groups (0 = none)               */
+    const int64_t* set1_off;   /* n_igroups+1 offsets into set1                         */
+    const int32_t* set1;
+    const int64_t* set2_off;   /* n_igroups+1 offsets into set2                         */
+    const int32_t* set2;
+    int32_t        periodic;   /* CutoffPeriodic (1) or CutoffNonPeriodic (0)           */
+} ocm_pair_topology;
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* ocm_last_error(void);
+const char* ocm_version(void);
+/* number of visible CUDA devices (0 when there is none); never fails */
+int ocm_device_count(void);
+
+/* ---- system (replaces OpenMM::System as built by SystemGenerator.cpp:34-111) -------------- */
+/* mass_amu[n]; box_nm = {Lx,Ly,Lz} or NULL for an unlimited boundary */
+int  ocm_system_create(int32_t n, const double* mass_amu, const double* box_nm, ocm_system** out);
+void ocm_system_destroy(ocm_system* sys);
+int  ocm_system_num_particles(const ocm_system* sys);
+
+/* ---- bonded terms -------------------------------------------------------------------------- */
+/* E = 1/2 k (r-r0)^2                      HarmonicBondForceFieldGenerator.cpp:3-14 */
+int ocm_system_add_harmonic_bond(ocm_system*, int group, int periodic, int64_t n,
+                                 const int32_t* ij, const double* r0, const double* k);
+/* E = k exp(-(r-r0)^2/(2 sigma^2))        GaussianBondForceFieldGenerator.cpp:3-23 */
+int ocm_system_add_gaussian_bond(ocm_system*, int group, int periodic, int64_t n,
+                                 const int32_t* ij, const double* k, const double* r0,
+                                 const double* sigma);
+/* E = k (5 (r0/r)^12 - 6 (r0/r)^10)       GoContactForceFieldGenerator.cpp:3-20 */
+int ocm_system_add_go_contact(ocm_system*, int group, int periodic, int64_t n,
+                              const int32_t* ij, const double* k, const double* r0);
+/* E = k2 (r-r0)^2 + k4 (r-r0)^4           ThreeSPN2BondForceFieldGenerator.cpp:3-25
+ * (the reference passes k4 = 100*k_4th; give the final coefficient here) */
+int ocm_system_add_3spn2_bond(ocm_system*, int group, int periodic, int64_t n,
+                              const int32_t* ij, const double* k2, const double* k4,
+                              const double* r0);
+/* E = 1/2 k (theta-theta0)^2              HarmonicAngleForceFieldGenerator.cpp:3-15 */
+int ocm_system_add_harmonic_angle(ocm_system*, int group, int periodic, int64_t n,
+                                  const int32_t* ijk, const double* theta0, const double* k);
+/* E = k (spline(theta) - e_min + walls)   FlexibleLocalAngleForceFieldGenerator.cpp:3-45
+ * y[10]: spline knots on [theta_min, theta_max] (natural cubic spline, 0 outside the range,
+ * OpenMM Continuous1DFunction); linear walls of slope 30 outside the range. */
+int ocm_system_add_flexible_local_angle(ocm_system*, int group, int periodic, int64_t n,
+                                        const int32_t* ijk, const double* k, const double* y10,
+                                        double theta_min, double theta_max, double e_min);
+/* E = k exp(-d^2/(2 sigma^2)), d = wrap(phi-phi0)   GaussianDihedralForceFieldGenerator.cpp:3-28 */
+int ocm_system_add_gaussian_dihedral(ocm_system*, int group, int periodic, int64_t n,
+                                     const int32_t* ijkl, const double* k, const double* phi0,
+                                     const double* sigma);
+/* E = k (1 - cos(nper (phi - t0)))        CosineDihedralForceFieldGenerator.cpp:5-43 */
+int ocm_system_add_cosine_dihedral(ocm_system*, int group, int periodic, int64_t n,
+                                   const int32_t* ijkl, const double* k, const double* t0,
+                                   const int32_t* nper);
+/* E = k (c - e_min + sum_m a_m cos m phi + b_m sin m phi), coef7 = {c,a1,b1,a2,b2,a3,b3}
+ *                                         FlexibleLocalDihedralForceFieldGenerator.cpp:5-63 */
+int ocm_system_add_flexible_local_dihedral(ocm_system*, int group, int periodic, int64_t n,
+                                           const int32_t* ijkl, const double* k,
+                                           const double* coef7, double e_min);
+
+/* ---- pair terms (per-bead parameter arrays have length N; NaN = bead does not take part) --- */
+/* E = eps (s_i+s_j)^12 (r^-12 - rc^-12), r < rc     ExcludedVolumeForceFieldGenerator.cpp:23-92 */
+int ocm_system_add_excluded_volume(ocm_system*, int group, double eps, double rc,
+                                   const double* radius, const ocm_pair_topology* topo);
+/* E = q_i q_j K (exp(-r/debye)/r - cc), r < rc      DebyeHuckelForceFieldGenerator.cpp:52-109 */
+int ocm_system_add_debye_huckel(ocm_system*, int group, double K, double debye_nm, double rc,
+                                double cutoff_correction, const double* charge,
+                                const ocm_pair_topology* topo);
+/* E = step(2^(1/6) s - r) e (4((s/r)^12-(s/r)^6) + 1), s,e arithmetic means
+ *                                         LennardJonesRepulsiveForceFieldGenerator.cpp:33-115 */
+int ocm_system_add_lj_repulsive(ocm_system*, int group, double rc, const double* eps,
+                                const double* sigma, const ocm_pair_topology* topo);
+/* E = e (step(r - 2^(1/6) s) 4((s/r)^12-(s/r)^6) - step(2^(1/6) s - r)), OpenMM switching
+ * function on [r_switch, rc]             LennardJonesAttractiveForceFieldGenerator.cpp:38-123 */
+int ocm_system_add_lj_attractive(ocm_system*, int group, double rc, double r_switch,
+                                 const double* eps, const double* sigma,
+                                 const ocm_pair_topology* topo);
+/* E = step(s-r) (e ((s/r)^12 - 2 (s/r)^6) + e), e geometric, s arithmetic mean
+ *                                         ThreeSPN2ExcludedVolumeForceFieldGenerator.cpp:19-91 */
+int ocm_system_add_3spn2_excluded_volume(ocm_system*, int group, double rc, const double* eps,
+                                         const double* sigma, const ocm_pair_topology* topo);
+
+/* ---- context (replaces OpenMM::Context + LangevinIntegrator) -------------------------------
+ * Simulator.cpp:14-17 (Context), IntegratorGenerator.cpp:5-14 (LangevinIntegrator(T, gamma, dt),
+ * setRandomNumberSeed).  The system is compiled into device-resident term tables; the system
+ * handle may be destroyed afterwards.  device_index: CUDA ordinal. */
+int  ocm_context_create(const ocm_system* sys, double temperature_K, double friction_inv_ps,
+                        double dt_ps, uint64_t seed, int device_index, ocm_context** out);
+void ocm_context_destroy(ocm_context* ctx);
+
+/* tunables: "skin_nm" (Verlet buffer), "nstlist" (0 = adaptive), "threads_per_bead" */
+int ocm_context_set_option(ocm_context*, const char* key, double value);
+int ocm_context_get_option(ocm_context*, const char* key, double* value);
+
+/* Context::setPositions / setVelocities / setVelocitiesToTemperature
+ * (Simulator.cpp:41, Simulator.hpp:49-65); xyz arrays are 3*N doubles */
+int ocm_set_positions(ocm_context*, const double* xyz_nm);
+int ocm_set_velocities(ocm_context*, const double* xyz_nm_per_ps);
+int ocm_set_velocities_to_temperature(ocm_context*, double temperature_K, uint64_t seed);
+
+/* LangevinIntegrator::step(n) (Simulator.cpp:60) */
+int ocm_step(ocm_context*, int64_t nsteps);
+int64_t ocm_current_step(const ocm_context*);
+
+/* Context::getState (Observer.cpp:34,107,113,340,344).  Any output pointer may be NULL.
+ * pos/vel/force: 3*N doubles; epot: sum over groups in group_mask; ekin: leap-frog kinetic
+ * energy shifted by dt/2 as OpenMM reports it; epot_by_group: 32 doubles (all groups). */
+int ocm_get_state(ocm_context*, uint32_t group_mask, double* pos, double* vel, double* force,
+                  double* epot, double* ekin, double* epot_by_group);
+
+/* ---- introspection used by the bit-exact set tests ---------------------------------------- */
+int ocm_num_pair_terms(const ocm_context*);
+/* unordered pairs (i<j, sorted) of pair term `term` (index in order of the add_* calls) that
+ * are inside its interaction cutoff at the current positions, not excluded, and allowed by its
+ * interaction groups.  First call with ij == NULL to get the count. */
+int ocm_get_neighbor_pairs(ocm_context*, int term, int32_t* ij, int64_t capacity, int64_t* n_pairs);
+/* cell index of every participant of the pair list serving `term` (-1 for non-participants),
+ * and the grid dimensions */
+int ocm_get_cell_ids(ocm_context*, int term, int32_t* cell_of_bead, int32_t dims[3]);
+/* counters: "pair_evals_per_step" (neighbor-list entries walked), "rebuilds", "rollbacks",
+ * "kernel_launches", "nstlist", "max_neighbors" */
+int ocm_get_counter(ocm_context*, const char* key, double* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCM_B200_H */

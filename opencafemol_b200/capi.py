@@ -1,0 +1,421 @@
+"""ctypes binding of the C ABI declared in include/ocm_b200.h.
+
+The binder is generic over (shared library path, symbol prefix): the product library
+``opencafemol_b200/lib/libocm_b200.so`` exports ``ocm_*``.  Tests bind the CPU oracle
+(``oracle/libocm_oracle.so``, prefix ``oracle_``) through the same class so that both sides are fed by
+identical term tables; nothing in this package ever loads the oracle.
+
+This mirrors how the reference drives OpenMM: build a System from force-field generators
+(src/SystemGenerator.cpp:34-111), create a Context with a LangevinIntegrator (src/Simulator.cpp:14-17),
+set positions / velocities (src/Simulator.cpp:41, src/Simulator.hpp:49-65), ``step`` (src/Simulator.cpp:60)
+and ``getState`` (src/Observer.cpp:34,107,113,340,344).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIB = os.path.join(_PKG_DIR, "lib", "libocm_b200.so")
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+
+
+class OcmError(RuntimeError):
+    pass
+
+
+class PairTopologyStruct(C.Structure):
+    _fields_ = [
+        ("n_excl", C.c_int64),
+        ("excl_ij", _i32p),
+        ("n_igroups", C.c_int32),
+        ("set1_off", _i64p),
+        ("set1", _i32p),
+        ("set2_off", _i64p),
+        ("set2", _i32p),
+        ("periodic", C.c_int32),
+    ]
+
+
+@dataclass
+class PairTopology:
+    """Exclusions + interaction groups of one pair term (see ocm_pair_topology)."""
+
+    excl: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), np.int32))
+    igroups: list = field(default_factory=list)  # list of (set1, set2) index arrays
+    periodic: bool = False
+
+    def to_struct(self):
+        keep = []
+        excl = np.ascontiguousarray(np.asarray(self.excl, np.int32).reshape(-1, 2))
+        keep.append(excl)
+        s = PairTopologyStruct()
+        s.n_excl = excl.shape[0]
+        s.excl_ij = excl.ctypes.data_as(_i32p)
+        ng = len(self.igroups)
+        s.n_igroups = ng
+        off1 = np.zeros(ng + 1, np.int64)
+        off2 = np.zeros(ng + 1, np.int64)
+        m1, m2 = [], []
+        for g, (a, b) in enumerate(self.igroups):
+            a = np.asarray(sorted(a), np.int32)
+            b = np.asarray(sorted(b), np.int32)
+            m1.append(a)
+            m2.append(b)
+            off1[g + 1] = off1[g] + a.size
+            off2[g + 1] = off2[g] + b.size
+        set1 = np.ascontiguousarray(np.concatenate(m1) if m1 else np.zeros(0, np.int32), np.int32)
+        set2 = np.ascontiguousarray(np.concatenate(m2) if m2 else np.zeros(0, np.int32), np.int32)
+        keep += [off1, off2, set1, set2]
+        s.set1_off = off1.ctypes.data_as(_i64p)
+        s.set2_off = off2.ctypes.data_as(_i64p)
+        s.set1 = set1.ctypes.data_as(_i32p)
+        s.set2 = set2.ctypes.data_as(_i32p)
+        s.periodic = 1 if self.periodic else 0
+        return s, keep
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, np.float64))
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a, np.int32))
+
+
+class Library:
+    """A loaded engine library (product or oracle) with typed entry points."""
+
+    # name -> (restype, argtypes); every symbol include/ocm_b200.h declares
+    SIGNATURES = {
+        "last_error": (C.c_char_p, []),
+        "version": (C.c_char_p, []),
+        "device_count": (C.c_int, []),
+        "system_create": (C.c_int, [C.c_int32, _f64p, _f64p, C.POINTER(C.c_void_p)]),
+        "system_destroy": (None, [C.c_void_p]),
+        "system_num_particles": (C.c_int, [C.c_void_p]),
+        "system_add_harmonic_bond": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p]),
+        "system_add_gaussian_bond": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p, _f64p]),
+        "system_add_go_contact": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p]),
+        "system_add_3spn2_bond": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p, _f64p]),
+        "system_add_harmonic_angle": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p]),
+        "system_add_flexible_local_angle": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p, C.c_double, C.c_double, C.c_double],
+        ),
+        "system_add_gaussian_dihedral": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p, _f64p]),
+        "system_add_cosine_dihedral": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p, _i32p]),
+        "system_add_flexible_local_dihedral": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p, C.c_double],
+        ),
+        "system_add_excluded_volume": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.c_double, C.c_double, _f64p, C.POINTER(PairTopologyStruct)],
+        ),
+        "system_add_debye_huckel": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _f64p, C.POINTER(PairTopologyStruct)],
+        ),
+        "system_add_lj_repulsive": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _f64p, _f64p, C.POINTER(PairTopologyStruct)]),
+        "system_add_lj_attractive": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.c_double, C.c_double, _f64p, _f64p, C.POINTER(PairTopologyStruct)],
+        ),
+        "system_add_3spn2_excluded_volume": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.c_double, _f64p, _f64p, C.POINTER(PairTopologyStruct)],
+        ),
+        "context_create": (
+            C.c_int,
+            [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)],
+        ),
+        "context_destroy": (None, [C.c_void_p]),
+        "context_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
+        "context_get_option": (C.c_int, [C.c_void_p, C.c_char_p, _f64p]),
+        "set_positions": (C.c_int, [C.c_void_p, _f64p]),
+        "set_velocities": (C.c_int, [C.c_void_p, _f64p]),
+        "set_velocities_to_temperature": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64]),
+        "step": (C.c_int, [C.c_void_p, C.c_int64]),
+        "current_step": (C.c_int64, [C.c_void_p]),
+        "get_state": (C.c_int, [C.c_void_p, C.c_uint32, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]),
+        "num_pair_terms": (C.c_int, [C.c_void_p]),
+        "get_neighbor_pairs": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int64, _i64p]),
+        "get_cell_ids": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p]),
+        "get_counter": (C.c_int, [C.c_void_p, C.c_char_p, _f64p]),
+    }
+
+    def __init__(self, path: str = PRODUCT_LIB, prefix: str = "ocm_"):
+        if not os.path.exists(path):
+            raise OcmError(
+                f"engine library not found: {path} — build it first (python -c 'import __graft_entry__ as g; g.build()')"
+            )
+        self.path = path
+        self.prefix = prefix
+        self.dll = C.CDLL(path)
+        self.fn = {}
+        for name, (res, args) in self.SIGNATURES.items():
+            f = getattr(self.dll, prefix + name)
+            f.restype = res
+            f.argtypes = args
+            self.fn[name] = f
+
+    def check(self, status: int):
+        if status != 0:
+            raise OcmError(self.fn["last_error"]().decode("utf-8", "replace"))
+
+    def version(self) -> str:
+        return self.fn["version"]().decode()
+
+    def device_count(self) -> int:
+        return int(self.fn["device_count"]())
+
+
+_product = None
+
+
+def product_library() -> Library:
+    """The CUDA engine.  Fails loudly when the extension has not been built."""
+    global _product
+    if _product is None:
+        _product = Library(PRODUCT_LIB, "ocm_")
+    return _product
+
+
+def _p(a, typ):
+    return a.ctypes.data_as(typ) if a is not None else None
+
+
+class System:
+    """Term-table builder (OpenMM::System + Force objects in the reference)."""
+
+    def __init__(self, lib: Library, mass, box=None):
+        self.lib = lib
+        mass = _f64(mass)
+        self.n = int(mass.size)
+        self.box = None if box is None else _f64(box)
+        h = C.c_void_p()
+        lib.check(lib.fn["system_create"](self.n, _p(mass, _f64p), _p(self.box, _f64p), C.byref(h)))
+        self.handle = h
+        self.pair_terms = []  # names, in order of addition (term index for introspection)
+
+    def close(self):
+        if self.handle:
+            self.lib.fn["system_destroy"](self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- bonded -----------------------------------------------------------------------------
+    def _bonded(self, name, group, periodic, idx, width, *cols, extra=()):
+        idx = _i32(idx).reshape(-1, width)
+        n = idx.shape[0]
+        arrs = []
+        for c in cols:
+            if c.dtype == np.int32:
+                assert c.size == n
+                arrs.append(_p(c, _i32p))
+            else:
+                assert c.size == n, f"{name}: parameter column length {c.size} != {n}"
+                arrs.append(_p(c, _f64p))
+        self.lib.check(self.lib.fn[name](self.handle, int(group), int(bool(periodic)), n, _p(idx, _i32p), *arrs, *extra))
+
+    def add_harmonic_bond(self, group, ij, r0, k, periodic=False):
+        self._bonded("system_add_harmonic_bond", group, periodic, ij, 2, _f64(r0), _f64(k))
+
+    def add_gaussian_bond(self, group, ij, k, r0, sigma, periodic=False):
+        self._bonded("system_add_gaussian_bond", group, periodic, ij, 2, _f64(k), _f64(r0), _f64(sigma))
+
+    def add_go_contact(self, group, ij, k, r0, periodic=False):
+        self._bonded("system_add_go_contact", group, periodic, ij, 2, _f64(k), _f64(r0))
+
+    def add_3spn2_bond(self, group, ij, k2, k4, r0, periodic=False):
+        self._bonded("system_add_3spn2_bond", group, periodic, ij, 2, _f64(k2), _f64(k4), _f64(r0))
+
+    def add_harmonic_angle(self, group, ijk, theta0, k, periodic=False):
+        self._bonded("system_add_harmonic_angle", group, periodic, ijk, 3, _f64(theta0), _f64(k))
+
+    def add_flexible_local_angle(self, group, ijk, k, y10, theta_min, theta_max, e_min, periodic=False):
+        y10 = _f64(y10)
+        assert y10.size == 10
+        idx = _i32(ijk).reshape(-1, 3)
+        k = _f64(k)
+        self.lib.check(
+            self.lib.fn["system_add_flexible_local_angle"](
+                self.handle, int(group), int(bool(periodic)), idx.shape[0], _p(idx, _i32p), _p(k, _f64p),
+                _p(y10, _f64p), float(theta_min), float(theta_max), float(e_min),
+            )
+        )
+
+    def add_gaussian_dihedral(self, group, ijkl, k, phi0, sigma, periodic=False):
+        self._bonded("system_add_gaussian_dihedral", group, periodic, ijkl, 4, _f64(k), _f64(phi0), _f64(sigma))
+
+    def add_cosine_dihedral(self, group, ijkl, k, t0, nper, periodic=False):
+        self._bonded("system_add_cosine_dihedral", group, periodic, ijkl, 4, _f64(k), _f64(t0), _i32(nper))
+
+    def add_flexible_local_dihedral(self, group, ijkl, k, coef7, e_min, periodic=False):
+        coef7 = _f64(coef7)
+        assert coef7.size == 7
+        idx = _i32(ijkl).reshape(-1, 4)
+        k = _f64(k)
+        self.lib.check(
+            self.lib.fn["system_add_flexible_local_dihedral"](
+                self.handle, int(group), int(bool(periodic)), idx.shape[0], _p(idx, _i32p), _p(k, _f64p),
+                _p(coef7, _f64p), float(e_min),
+            )
+        )
+
+    # ---- pair -------------------------------------------------------------------------------
+    def _per_bead(self, a):
+        a = _f64(a)
+        assert a.size == self.n, "per-bead parameter arrays must have one entry per particle (NaN = none)"
+        return a
+
+    def add_excluded_volume(self, group, eps, rc, radius, topo: PairTopology):
+        s, keep = topo.to_struct()
+        r = self._per_bead(radius)
+        self.lib.check(self.lib.fn["system_add_excluded_volume"](self.handle, int(group), float(eps), float(rc), _p(r, _f64p), C.byref(s)))
+        self.pair_terms.append("ExcludedVolume")
+
+    def add_debye_huckel(self, group, K, debye, rc, cutoff_correction, charge, topo: PairTopology):
+        s, keep = topo.to_struct()
+        q = self._per_bead(charge)
+        self.lib.check(
+            self.lib.fn["system_add_debye_huckel"](
+                self.handle, int(group), float(K), float(debye), float(rc), float(cutoff_correction), _p(q, _f64p), C.byref(s)
+            )
+        )
+        self.pair_terms.append("DebyeHuckel")
+
+    def add_lj_repulsive(self, group, rc, eps, sigma, topo: PairTopology):
+        s, keep = topo.to_struct()
+        e, sg = self._per_bead(eps), self._per_bead(sigma)
+        self.lib.check(self.lib.fn["system_add_lj_repulsive"](self.handle, int(group), float(rc), _p(e, _f64p), _p(sg, _f64p), C.byref(s)))
+        self.pair_terms.append("LennardJonesRepulsive")
+
+    def add_lj_attractive(self, group, rc, r_switch, eps, sigma, topo: PairTopology):
+        s, keep = topo.to_struct()
+        e, sg = self._per_bead(eps), self._per_bead(sigma)
+        self.lib.check(
+            self.lib.fn["system_add_lj_attractive"](
+                self.handle, int(group), float(rc), float(r_switch), _p(e, _f64p), _p(sg, _f64p), C.byref(s)
+            )
+        )
+        self.pair_terms.append("LennardJonesAttractive")
+
+    def add_3spn2_excluded_volume(self, group, rc, eps, sigma, topo: PairTopology):
+        s, keep = topo.to_struct()
+        e, sg = self._per_bead(eps), self._per_bead(sigma)
+        self.lib.check(
+            self.lib.fn["system_add_3spn2_excluded_volume"](self.handle, int(group), float(rc), _p(e, _f64p), _p(sg, _f64p), C.byref(s))
+        )
+        self.pair_terms.append("3SPN2ExcludedVolume")
+
+
+class Context:
+    """OpenMM::Context + LangevinIntegrator equivalent."""
+
+    def __init__(self, system: System, temperature, friction, dt, seed=0, device=0):
+        self.lib = system.lib
+        self.n = system.n
+        h = C.c_void_p()
+        self.lib.check(
+            self.lib.fn["context_create"](system.handle, float(temperature), float(friction), float(dt), int(seed), int(device), C.byref(h))
+        )
+        self.handle = h
+        self.pair_terms = list(system.pair_terms)
+
+    def close(self):
+        if self.handle:
+            self.lib.fn["context_destroy"](self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key, value):
+        self.lib.check(self.lib.fn["context_set_option"](self.handle, key.encode(), float(value)))
+
+    def get_option(self, key):
+        v = C.c_double()
+        self.lib.check(self.lib.fn["context_get_option"](self.handle, key.encode(), C.byref(v)))
+        return v.value
+
+    def set_positions(self, xyz):
+        a = _f64(xyz).reshape(-1)
+        assert a.size == 3 * self.n
+        self.lib.check(self.lib.fn["set_positions"](self.handle, _p(a, _f64p)))
+
+    def set_velocities(self, xyz):
+        a = _f64(xyz).reshape(-1)
+        assert a.size == 3 * self.n
+        self.lib.check(self.lib.fn["set_velocities"](self.handle, _p(a, _f64p)))
+
+    def set_velocities_to_temperature(self, temperature, seed):
+        self.lib.check(self.lib.fn["set_velocities_to_temperature"](self.handle, float(temperature), int(seed)))
+
+    def step(self, nsteps):
+        self.lib.check(self.lib.fn["step"](self.handle, int(nsteps)))
+
+    @property
+    def current_step(self):
+        return int(self.lib.fn["current_step"](self.handle))
+
+    def get_state(self, positions=False, velocities=False, forces=False, energy=False, groups=0xFFFFFFFF):
+        out = {}
+        pos = np.empty((self.n, 3)) if positions else None
+        vel = np.empty((self.n, 3)) if velocities else None
+        frc = np.empty((self.n, 3)) if forces else None
+        ep, ek = C.c_double(), C.c_double()
+        ebg = np.zeros(32) if energy else None
+        self.lib.check(
+            self.lib.fn["get_state"](
+                self.handle, int(groups) & 0xFFFFFFFF, _p(pos, _f64p), _p(vel, _f64p), _p(frc, _f64p),
+                C.byref(ep) if energy else None, C.byref(ek) if energy else None, _p(ebg, _f64p),
+            )
+        )
+        if positions:
+            out["positions"] = pos
+        if velocities:
+            out["velocities"] = vel
+        if forces:
+            out["forces"] = frc
+        if energy:
+            out["potential_energy"] = ep.value
+            out["kinetic_energy"] = ek.value
+            out["energy_by_group"] = ebg
+        return out
+
+    def num_pair_terms(self):
+        return int(self.lib.fn["num_pair_terms"](self.handle))
+
+    def neighbor_pairs(self, term):
+        n = C.c_int64()
+        self.lib.check(self.lib.fn["get_neighbor_pairs"](self.handle, int(term), None, 0, C.byref(n)))
+        ij = np.zeros((max(n.value, 1), 2), np.int32)
+        self.lib.check(self.lib.fn["get_neighbor_pairs"](self.handle, int(term), _p(ij, _i32p), ij.shape[0], C.byref(n)))
+        return ij[: n.value]
+
+    def cell_ids(self, term):
+        ids = np.zeros(self.n, np.int32)
+        dims = np.zeros(3, np.int32)
+        self.lib.check(self.lib.fn["get_cell_ids"](self.handle, int(term), _p(ids, _i32p), _p(dims, _i32p)))
+        return ids, dims
+
+    def counter(self, key):
+        v = C.c_double()
+        self.lib.check(self.lib.fn["get_counter"](self.handle, key.encode(), C.byref(v)))
+        return v.value

@@ -1,0 +1,634 @@
+"""TOML (Mjolnir-style) input -> typed term tables in OpenMM units.
+
+Python mirror of the reference's reader layer, used by the Python front end, the tests and the
+benchmark: ``read_toml_system`` (src/input/ReadTOMLInput.cpp:21-875), the per-potential
+``read_toml_*_ff_generator`` functions (src/input/ReadTOMLForceFieldGenerator.cpp), ``Topology``
+(src/Topology.cpp), ``extract_interaction_group`` (src/forcefield/InteractionGroup.hpp:19-101) and the
+force-group bookkeeping of ``SystemGenerator::add_ff_generator`` (src/SystemGenerator.cpp:4-32).
+
+Where the reference hands OpenMM an expression string plus parameters, this module emits a ``Term`` with
+the same parameters (same unit conversions) that ``build_system`` feeds to the C ABI.
+"""
+from __future__ import annotations
+
+import math
+import os
+import tomllib
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import tables
+from .capi import Context, Library, PairTopology, System
+
+NM_PER_ANGSTROM = 0.1
+ANGSTROM_PER_NM = 10.0
+KJ_PER_KCAL = 4.184
+CAFETIME = math.sqrt(1.0 / KJ_PER_KCAL) * 0.1  # ps, src/util/Constants.hpp:23
+
+
+# ------------------------------------------------------------------------------------------------
+class Topology:
+    """Bond graph with typed edges (src/Topology.hpp, src/Topology.cpp).
+
+    The depth-limited DFS with a shared visited list is reproduced verbatim in behaviour
+    (SURVEY.md Appendix C4): in cyclic graphs it can miss nodes a BFS would find.
+    """
+
+    def __init__(self, n):
+        self.nodes = [[] for _ in range(n)]  # (neighbour, edge_type) in insertion order
+        self.molecules = None
+
+    def size(self):
+        return len(self.nodes)
+
+    def add_edges(self, index_sets, edge_type):
+        for ids in index_sets:
+            ids = list(ids)
+            for a in range(len(ids) - 1):
+                for b in range(a + 1, len(ids)):
+                    self.nodes[ids[a]].append((ids[b], edge_type))
+                    self.nodes[ids[b]].append((ids[a], edge_type))
+        self.molecules = None
+
+    def make_molecule(self, edge_type):
+        n = len(self.nodes)
+        seen = [False] * n
+        mols = []
+        for start in range(n):
+            if seen[start]:
+                continue
+            stack = [start]
+            mol = []
+            while stack:
+                s = stack.pop()
+                mol.append(s)  # duplicates possible exactly as in the reference
+                seen[s] = True
+                for nb, et in self.nodes[s]:
+                    if et == edge_type and not seen[nb]:
+                        stack.append(nb)
+            mols.append(mol)
+        self.molecules = mols
+
+    def ignore_list_within_molecule(self):
+        assert self.molecules is not None
+        out = set()
+        for mol in self.molecules:
+            for a in range(len(mol) - 1):
+                for b in range(a + 1, len(mol)):
+                    out.add((mol[a], mol[b]))
+        return out
+
+    def _adjacent_within(self, node, dist, edge_type, acc):
+        acc.append(node)
+        if dist == 0:
+            return
+        for nb, et in self.nodes[node]:
+            if et == edge_type and nb not in acc:
+                self._adjacent_within(nb, dist - 1, edge_type, acc)
+
+    def ignore_list_within_edge(self, dist, edge_type):
+        out = set()
+        for i in range(len(self.nodes)):
+            if not any(et == edge_type for _, et in self.nodes[i]):
+                continue
+            acc = []
+            self._adjacent_within(i, dist, edge_type, acc)
+            for j in acc:
+                if j != i:
+                    out.add((min(i, j), max(i, j)))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Term:
+    kind: str  # C-ABI adder suffix, e.g. "harmonic_bond"
+    name: str  # reference generator name() -> .ene column / force group
+    args: dict
+    group: int = -1
+
+
+@dataclass
+class SystemSpec:
+    mass: np.ndarray
+    box: np.ndarray | None
+    positions: np.ndarray  # nm
+    velocities: np.ndarray | None  # nm/ps
+    names: list
+    groups: list
+    terms: list = field(default_factory=list)
+    group_ids: dict = field(default_factory=dict)  # name -> force group
+    temperature: float = 300.0
+    friction: float = 0.01 / CAFETIME
+    dt: float = 0.0
+    seed: int = 0
+    vel_seed: int = 0
+    total_step: int = 0
+    save_step: int = 1
+    delta_t_raw: float = 0.0
+    energy_minimization: bool = False
+    periodic: bool = False
+    output: dict = field(default_factory=dict)
+    platform: dict = field(default_factory=dict)
+
+    def add_term(self, term: Term):
+        """SystemGenerator::add_ff_generator group rule (src/SystemGenerator.cpp:4-32): the group id is
+        the map size at first insertion of the name; all FlexibleLocalAngle (XXX) share one group,
+        likewise FlexibleLocalDihedral; duplicate names share the first id."""
+        key = term.name
+        if "FlexibleLocalAngle" in key:
+            key = "FlexibleLocalAngle"
+        elif "FlexibleLocalDihedral" in key:
+            key = "FlexibleLocalDihedral"
+        if key not in self.group_ids:
+            self.group_ids[key] = len(self.group_ids)
+        term.group = self.group_ids[key]
+        self.terms.append(term)
+
+
+def _either(tab, k1, k2):
+    if k1 in tab and k2 in tab:
+        raise ValueError(f"key duplicates: {k1} and {k2}")
+    if k1 in tab:
+        return tab[k1]
+    if k2 in tab:
+        return tab[k2]
+    raise KeyError(f"both keys, {k1!r} and {k2!r}, are not found")
+
+
+def _param(p, env, key, default=None):
+    """Utility::find_parameter(_or): string values are looked up in `env` (src/util/Utility.hpp:47-158)."""
+    if key not in p:
+        if default is None:
+            raise KeyError(f"value {key} does not exists")
+        return default
+    v = p[key]
+    if isinstance(v, str):
+        if env is None or v not in env:
+            if default is not None:
+                return default
+            raise KeyError(f'named variable "{v}" does not exists')
+        return env[v]
+    return v
+
+
+def _param_either(p, env, k1, k2):
+    if k1 in p and k2 in p:
+        raise ValueError("key duplicates")
+    if k1 in p:
+        return _param(p, env, k1)
+    return _param(p, env, k2)
+
+
+def _indices(p, env, n, who, nsys):
+    idx = list(_param(p, env, "indices"))
+    off = _param(p, env, "offset", 0)
+    if isinstance(off, (list, tuple)):  # add_offset, src/input/Utility.cpp:82-131
+        idx = [a + b for a, b in zip(idx, off)]
+    else:
+        idx = [a + off for a in idx]
+    assert len(idx) == n
+    for a in idx:
+        if a >= nsys:
+            raise RuntimeError(f"[error] {who} : index {a} exceeds the system's largest index {nsys - 1}.")
+    return idx
+
+
+def _index(p, env, who, nsys):
+    i = _param(p, env, "index") + _param(p, env, "offset", 0)
+    if i >= nsys:
+        raise RuntimeError(f"[error] {who} : index {i} exceeds the system's largest index {nsys - 1}.")
+    return i
+
+
+def expand_include(tab, base_dir):
+    """`include = "file"` / `include = [..]` expansion at any table (src/input/Utility.cpp:41-80)."""
+    if isinstance(tab, dict):
+        if "include" in tab:
+            inc = tab.pop("include")
+            files = [inc] if isinstance(inc, str) else list(inc)
+            for f in files:
+                with open(os.path.join(base_dir, f), "rb") as fh:
+                    sub = tomllib.load(fh)
+                for k, v in sub.items():  # merge_toml_tables: existing keys win
+                    if k not in tab:
+                        tab[k] = v
+        for v in tab.values():
+            expand_include(v, base_dir)
+    elif isinstance(tab, list):
+        for v in tab:
+            expand_include(v, base_dir)
+    return tab
+
+
+# ------------------------------------------------------------------------------------------------
+def _read_ignore(ff, topo: Topology):
+    """read_ignore_molecule_and_particles_within + read_ignore_group
+    (src/input/ReadTOMLForceFieldGenerator.cpp:963-1051)."""
+    excl = set()
+    gpairs = []
+    ign = ff.get("ignore")
+    if ign is None:
+        return np.zeros((0, 2), np.int32), gpairs
+    if "molecule" in ign:
+        name = ign["molecule"]
+        if name in ("Intra", "Self"):
+            excl |= {(min(a, b), max(a, b)) if a != b else (a, b) for a, b in topo.ignore_list_within_molecule()}
+        elif name in ("Others", "Inter"):
+            raise RuntimeError('[error] ignore molecule do not support "Others" or "Inter".')
+    if "particles_within" in ign:
+        for etype, dist in ign["particles_within"].items():
+            excl |= topo.ignore_list_within_edge(int(dist), etype)
+    if "group" in ign:
+        g = ign["group"]
+        for a, b in g.get("inter", []):
+            gpairs.append((a, b))
+        for a in g.get("intra", []):
+            gpairs.append((a, a))
+    arr = np.array(sorted(excl), np.int32).reshape(-1, 2)
+    return arr, gpairs
+
+
+def extract_interaction_group(has_param, ignore_group_pairs, group_vec):
+    """src/forcefield/InteractionGroup.hpp:19-101 — returns [(set1, set2), ...] or [] when every
+    particle takes part and no group rule applies."""
+    n = len(has_param)
+    if not ignore_group_pairs:
+        if not all(has_param):
+            part = [i for i in range(n) if has_param[i]]
+            return [(part, part)]
+        return []
+    related = sorted({g for pr in ignore_group_pairs for g in pr})
+    gmap = {g: [] for g in related}
+    others = []
+    for i in range(n):
+        if has_param[i]:
+            if group_vec[i] is not None and group_vec[i] in gmap:
+                gmap[group_vec[i]].append(i)
+            else:
+                others.append(i)
+
+    def ignored(a, b):
+        return any((p == a and q == b) or (p == b and q == a) for p, q in ignore_group_pairs)
+
+    out = [(others, others)]
+    for ia, a in enumerate(related):
+        out.append((gmap[a], others))
+        for b in related[ia:]:
+            if not ignored(a, b):
+                out.append((gmap[a], gmap[b]))
+    return out
+
+
+def _two_largest(vals, strict):
+    """The reference's max / second-max trackers (ExcludedVolume uses '<', LJ uses '<=';
+    SURVEY.md Appendix C12)."""
+    mx = sm = np.finfo(np.float64).tiny
+    for v in vals:
+        if (mx < v) if strict else (mx <= v):
+            sm, mx = mx, v
+        elif (sm < v) if strict else (sm <= v):
+            sm = v
+    return mx, sm
+
+
+# ------------------------------------------------------------------------------------------------
+def fla_min_energy(aa):
+    """E_min scan of FlexibleLocalAngleForceFieldGenerator::generate (…cpp:11-19) with the
+    reference's own tabulated-second-derivative spline (…cpp:47-68)."""
+    y = tables.FLA_SPLINE[aa]
+    y2 = tables.FLA_SPLINE_D2[aa]
+    thetas = tables.FLA_THETAS
+    tmin, tmax = tables.FLA_MIN_THETA, tables.FLA_MAX_THETA
+    dth = (tmax - tmin) / 9.0
+    rd = 1.0 / dth
+    emin = y[0]
+    th = tmin
+    while th < tmax:
+        n = min(8, int(math.floor((th - tmin) * rd)))
+        if thetas[n + 1] < th:
+            n += 1
+        elif th < thetas[n]:
+            n -= 1
+        a = (thetas[n + 1] - th) * rd
+        b = (th - thetas[n]) * rd
+        e = a * y[n] + b * y[n + 1] + ((a * a * a - a) * y2[n] + (b * b * b - b) * y2[n + 1]) * dth * dth / 6.0
+        emin = min(emin, e)
+        th += 1e-4
+    return emin
+
+
+def fld_min_energy(c):
+    """E_min scan of FlexibleLocalDihedralForceFieldGenerator::generate (…cpp:7-26)."""
+    n = int(math.ceil(2 * math.pi / 1e-4)) + 2
+    # reproduce the accumulating loop phi += 1e-4 exactly
+    phi = np.empty(n)
+    p = -math.pi
+    k = 0
+    while p < math.pi:
+        phi[k] = p
+        p += 1e-4
+        k += 1
+    phi = phi[:k]
+    s1, c1 = np.sin(phi), np.cos(phi)
+    ssq, csq = s1 * s1, c1 * c1
+    s2, c2 = 2 * s1 * c1, csq - ssq
+    s3, c3 = s1 * (3 - 4 * ssq), c1 * (4 * csq - 3)
+    e = c[1] * c1 + c[2] * s1 + c[3] * c2 + c[4] * s2 + c[5] * c3 + c[6] * s3 + c[0]
+    return float(e.min())
+
+
+_fla_cache = {}
+_fld_cache = {}
+
+
+# ------------------------------------------------------------------------------------------------
+def read_toml(path_or_dict, base_dir=None) -> SystemSpec:
+    if isinstance(path_or_dict, dict):
+        data = path_or_dict
+        base_dir = base_dir or "."
+    else:
+        with open(path_or_dict, "rb") as fh:
+            data = tomllib.load(fh)
+        base_dir = os.path.dirname(os.path.abspath(path_or_dict))
+    expand_include(data, base_dir)
+
+    systems = data["systems"]
+    particles = systems[0]["particles"]
+    n = len(particles)
+    mass = np.array([float(_either(p, "m", "mass")) for p in particles])
+    groups = [p.get("group") for p in particles]
+    names = [p.get("name", "") for p in particles]
+    pos = np.array([_either(p, "pos", "position") for p in particles], float) * NM_PER_ANGSTROM
+    vel = None
+    if "vel" in particles[0] or "velocity" in particles[0]:
+        for p in particles:
+            if "vel" not in p and "velocity" not in p:
+                raise RuntimeError("[error] All particle need to have velocity, because first particle in system has velocity.")
+        vel = np.array([_either(p, "vel", "velocity") for p in particles], float) * NM_PER_ANGSTROM / CAFETIME
+
+    sim = data["simulator"]
+    btype = sim["boundary_type"]
+    periodic = btype in ("Periodic", "PeriodicCuboid")
+    box = None
+    if periodic:
+        shape = systems[0]["boundary_shape"]
+        lo, up = np.array(shape["lower"], float), np.array(shape["upper"], float)
+        box = (up - lo) * NM_PER_ANGSTROM
+    attr = systems[0]["attributes"]
+    if "ensemble" in attr and attr["ensemble"].get("type", "NVT") != "NVT":
+        raise NotImplementedError("only the NVT ensemble is in scope (barostats: SURVEY.md §2.2 out of scope)")
+    temperature = float(attr["temperature"])
+
+    spec = SystemSpec(mass=mass, box=box, positions=pos, velocities=vel, names=names, groups=groups)
+    spec.periodic = periodic
+    spec.temperature = temperature
+    spec.delta_t_raw = float(sim["delta_t"])
+    spec.dt = spec.delta_t_raw * CAFETIME
+    spec.friction = float(sim.get("gamma_t", 0.01)) / CAFETIME
+    spec.seed = int(sim.get("seed", 0))
+    spec.vel_seed = int(systems[0].get("vel_seed", 0)) if isinstance(systems[0], dict) else 0
+    spec.total_step = int(sim["total_step"])
+    spec.save_step = int(sim["save_step"])
+    spec.energy_minimization = bool(sim.get("energy_minimization", False))
+    spec.output = dict(data.get("files", {}).get("output", {}))
+    spec.platform = dict(data.get("platform", {}))
+
+    topo = Topology(n)
+    ff = data["forcefields"][0]
+    for lf in ff.get("local", []):
+        _read_local(spec, lf, topo, periodic)
+    topo.make_molecule("bond")
+    for gf in ff.get("global", []):
+        _read_global(spec, gf, topo, periodic, attr)
+    spec.topology = topo
+    return spec
+
+
+def _read_local(spec, lf, topo, periodic):
+    inter, pot = lf["interaction"], lf["potential"]
+    env = lf.get("env")
+    params = lf["parameters"]
+    n = topo.size()
+    topo_name = lf.get("topology")
+
+    def add_topology(idx_list):
+        if "topology" in lf:
+            topo.add_edges(idx_list, topo_name)
+
+    if inter == "BondLength" and pot == "Harmonic":
+        idx = [_indices(p, env, 2, "read_toml_harmonic_bond_ff_generator", n) for p in params]
+        r0 = [_param(p, env, "v0") * NM_PER_ANGSTROM for p in params]
+        k = [_param(p, env, "k") * KJ_PER_KCAL * ANGSTROM_PER_NM * ANGSTROM_PER_NM * 2.0 for p in params]
+        add_topology(idx)
+        spec.add_term(Term("harmonic_bond", "HarmonicBond", dict(ij=idx, r0=r0, k=k, periodic=periodic)))
+    elif inter == "BondLength" and pot == "Gaussian":
+        idx = [_indices(p, env, 2, "read_toml_gaussian_bond_ff_generator", n) for p in params]
+        k = [_param(p, env, "k") * KJ_PER_KCAL for p in params]
+        r0 = [_param(p, env, "v0") * NM_PER_ANGSTROM for p in params]
+        sg = [_param_either(p, env, "sigma", "σ") * NM_PER_ANGSTROM for p in params]
+        add_topology(idx)
+        spec.add_term(Term("gaussian_bond", "GaussianBond", dict(ij=idx, k=k, r0=r0, sigma=sg, periodic=periodic)))
+    elif inter == "BondLength" and pot == "GoContact":
+        idx = [_indices(p, env, 2, "read_toml_go_contact_ff_generator", n) for p in params]
+        k = [_param(p, env, "k") * KJ_PER_KCAL for p in params]
+        r0 = [_param(p, env, "v0") * NM_PER_ANGSTROM for p in params]
+        add_topology(idx)
+        spec.add_term(Term("go_contact", "GoContact", dict(ij=idx, k=k, r0=r0, periodic=periodic)))
+    elif inter == "BondLength" and pot == "3SPN2Bond":
+        idx = [_indices(p, env, 2, "read_toml_3spn2_bond_ff_generator", n) for p in params]
+        r0 = [_param(p, env, "v0") * NM_PER_ANGSTROM for p in params]
+        k2 = [_param(p, env, "k") * KJ_PER_KCAL * 100.0 for p in params]
+        # the reference's expression multiplies its k4 (= k * 4.184e4) by a further 100
+        k4 = [100.0 * _param(p, env, "k") * KJ_PER_KCAL * 1.0e4 for p in params]
+        add_topology(idx)
+        spec.add_term(Term("3spn2_bond", "3SPN2Bond", dict(ij=idx, k2=k2, k4=k4, r0=r0, periodic=periodic)))
+    elif inter == "BondAngle" and pot == "Harmonic":
+        idx = [_indices(p, env, 3, "read_toml_harmonic_angle_ff_generator", n) for p in params]
+        th0 = []
+        for p in params:
+            v0 = _param(p, env, "v0")
+            if v0 < 0 or 2 * math.pi < v0:
+                raise RuntimeError("[error] read_toml_harmonic_angle_ff_generator: v0 must be between 0 and 2pi")
+            if math.pi < v0:
+                v0 = 2.0 * math.pi - v0
+            th0.append(v0)
+        k = [_param(p, env, "k") * KJ_PER_KCAL * 2.0 for p in params]
+        add_topology(idx)
+        spec.add_term(Term("harmonic_angle", "HarmonicAngle", dict(ijk=idx, theta0=th0, k=k, periodic=periodic)))
+    elif inter == "BondAngle" and pot == "FlexibleLocalAngle":
+        # one Force per residue type, alphabetical std::map order (ReadTOMLInput.cpp:237-246)
+        for aa in sorted(tables.FLA_SPLINE):
+            sel = [p for p in params if p["y"][3:6] == aa]
+            idx = [_indices(p, env, 3, "read_toml_flexible_local_angle_ff_generator", n) for p in sel]
+            k = [_param(p, env, "k") * KJ_PER_KCAL for p in sel]
+            add_topology(idx)
+            if aa not in _fla_cache:
+                _fla_cache[aa] = fla_min_energy(aa)
+            spec.add_term(
+                Term(
+                    "flexible_local_angle", f"FlexibleLocalAngle ({aa})",
+                    dict(ijk=idx, k=k, y10=tables.FLA_SPLINE[aa], theta_min=tables.FLA_MIN_THETA,
+                         theta_max=tables.FLA_MAX_THETA, e_min=_fla_cache[aa], periodic=periodic),
+                )
+            )
+    elif inter == "DihedralAngle" and pot == "Gaussian":
+        _gaussian_dihedral(spec, params, env, topo, lf, periodic)
+    elif inter == "DihedralAngle" and pot == "Cosine":
+        _cosine_dihedral(spec, params, env, topo, lf, periodic)
+    elif inter == "DihedralAngle" and pot in ("Gaussian+Cosine", "Cosine+Gaussian"):
+        a1, a2 = [], []
+        for e in params:
+            v1, v2 = dict(e["Gaussian"]), dict(e["Cosine"])
+            v1["indices"] = e["indices"]
+            v2["indices"] = e["indices"]
+            a1.append(v1)
+            a2.append(v2)
+        # the synthesised tables carry only "parameters": no topology edges, no env (ReadTOMLInput.cpp:262-290)
+        _gaussian_dihedral(spec, a1, None, topo, {}, periodic)
+        _cosine_dihedral(spec, a2, None, topo, {}, periodic)
+    elif inter == "DihedralAngle" and pot == "FlexibleLocalDihedral":
+        for key in sorted(tables.FLD_FOURIER):  # std::map<pair<string,string>> order
+            first, second = key
+            sel = []
+            for p in params:
+                coef = p["coef"]
+                if second == "GLY":
+                    ok = coef[4:7] == "GLY"
+                elif second == "PRO":
+                    # NB: the R2-PRO branch also captures "GLY-PRO" entries (reference behaviour,
+                    # ReadTOMLForceFieldGenerator.cpp:696-717), which are then counted by both Forces
+                    ok = (coef == "GLY-PRO") if first == "GLY" else (coef[4:7] == "PRO")
+                else:
+                    ok = coef[4:7] not in ("GLY", "PRO") and coef[0:3] == first
+                if ok:
+                    sel.append(p)
+            idx = [_indices(p, env, 4, "read_toml_flexible_local_dihedral_ff_generator", n) for p in sel]
+            k = [_param(p, env, "k") * KJ_PER_KCAL for p in sel]
+            add_topology(idx)
+            if key not in _fld_cache:
+                _fld_cache[key] = fld_min_energy(tables.FLD_FOURIER[key])
+            spec.add_term(
+                Term(
+                    "flexible_local_dihedral", f"FlexibleLocalDihedral ({first}-{second})",
+                    dict(ijkl=idx, k=k, coef7=tables.FLD_FOURIER[key], e_min=_fld_cache[key], periodic=periodic),
+                )
+            )
+    else:
+        raise NotImplementedError(f"local force field {inter}/{pot} is not in scope yet")
+
+
+def _gaussian_dihedral(spec, params, env, topo, lf, periodic):
+    n = topo.size()
+    idx = [_indices(p, env, 4, "read_toml_gaussian_dihedral_ff_generator", n) for p in params]
+    k = [_param(p, env, "k") * KJ_PER_KCAL for p in params]
+    phi0 = [_param(p, env, "v0") for p in params]
+    sg = [_param_either(p, env, "sigma", "σ") for p in params]
+    if "topology" in lf:
+        topo.add_edges(idx, lf["topology"])
+    spec.add_term(Term("gaussian_dihedral", "GaussianDihedral", dict(ijkl=idx, k=k, phi0=phi0, sigma=sg, periodic=periodic)))
+
+
+def _cosine_dihedral(spec, params, env, topo, lf, periodic):
+    n = topo.size()
+    idx = [_indices(p, env, 4, "read_toml_cosine_dihedral_ff_generator", n) for p in params]
+    k = [_param(p, env, "k") * KJ_PER_KCAL for p in params]
+    t0 = [_param(p, env, "v0") + math.pi for p in params]
+    nper = [int(_param(p, env, "n")) for p in params]
+    if "topology" in lf:
+        topo.add_edges(idx, lf["topology"])
+    spec.add_term(Term("cosine_dihedral", "CosineDihedral", dict(ijkl=idx, k=k, t0=t0, nper=nper, periodic=periodic)))
+
+
+def debye_huckel_constants(temperature, ionic_strength, cutoff_ratio):
+    """DebyeHuckelForceFieldGenerator ctor (…cpp:10-50) and calc_dielectric_water (…hpp:36-41)."""
+    Na, kB = 6.02214076e23, 1.380649e-23
+    eps0_c = 8.854187817e-12 * 1.0e3 * 1.0e-9 / Na
+    echarge = 1.6021766208e-19
+    T, Cs = temperature, ionic_strength
+    epsk = (249.4 - 0.788 * T + 7.2e-4 * T * T) * (1.0 - 2.551e-1 * Cs + 5.151e-2 * Cs * Cs - 6.889e-3 * Cs * Cs * Cs)
+    eps0 = eps0_c / echarge / echarge
+    K = 1.0 / (4.0 * 3.1415926535897932385 * eps0 * epsk)
+    if not Cs > 0:
+        raise RuntimeError("[error] ionic strength must be larger than zero")
+    ion = Cs * 1.0e-24
+    debye = math.sqrt((eps0 * epsk * kB * 1.0e-3 * T) / (2.0 * ion))
+    rc = debye * cutoff_ratio
+    cc = math.exp(-cutoff_ratio) / rc
+    return K, debye, rc, cc
+
+
+def _read_global(spec, gf, topo, periodic, attr):
+    pot = gf["potential"]
+    env = gf.get("env")
+    n = topo.size()
+    params = gf.get("parameters", [])
+    groups = spec.groups
+
+    def topo_for(has):
+        excl, gpairs = _read_ignore(gf, topo)
+        ig = extract_interaction_group(has, gpairs, groups)
+        return PairTopology(excl=excl, igroups=ig, periodic=periodic)
+
+    if pot == "ExcludedVolume":
+        eps = float(gf["epsilon"]) * KJ_PER_KCAL
+        cutoff = float(gf.get("cutoff", 2.0))
+        rad = np.full(n, np.nan)
+        for p in params:
+            rad[_index(p, env, "read_toml_excluded_volume_ff_generator", n)] = _param(p, env, "radius") * NM_PER_ANGSTROM
+        has = ~np.isnan(rad)
+        mx, sm = _two_largest(rad[has], strict=True)
+        rc = (mx + sm) * cutoff
+        spec.add_term(Term("excluded_volume", "ExcludedVolume", dict(eps=eps, rc=rc, radius=rad, topo=topo_for(has))))
+    elif pot == "DebyeHuckel":
+        ratio = float(gf.get("cutoff", 5.5))
+        q = np.full(n, np.nan)
+        for p in params:
+            q[_index(p, env, "read_toml_debye_huckel_ff_generator", n)] = _param(p, env, "charge")
+        K, debye, rc, cc = debye_huckel_constants(spec.temperature, float(attr["ionic_strength"]), ratio)
+        spec.add_term(
+            Term("debye_huckel", "DebyeHuckel",
+                 dict(K=K, debye=debye, rc=rc, cutoff_correction=cc, charge=q, topo=topo_for(~np.isnan(q))))
+        )
+    elif pot in ("LennardJonesRepulsive", "LennardJonesAttractive"):
+        if "table" in gf:
+            raise NotImplementedError("UniformLennardJonesAttractive is not in scope yet")
+        ratio = float(_param(gf, env, "cutoff", 2.5))
+        eps = np.full(n, np.nan)
+        sig = np.full(n, np.nan)
+        for p in params:
+            i = _param(p, env, "index") + _param(p, env, "offset", 0)
+            sig[i] = _param(p, env, "sigma") * NM_PER_ANGSTROM
+            eps[i] = _param(p, env, "epsilon") * KJ_PER_KCAL
+        has = ~np.isnan(sig)
+        mx, sm = _two_largest(sig[has], strict=False)
+        rc = (mx + sm) * 0.5 * ratio
+        if pot == "LennardJonesRepulsive":
+            spec.add_term(Term("lj_repulsive", pot, dict(rc=rc, eps=eps, sigma=sig, topo=topo_for(has))))
+        else:
+            spec.add_term(Term("lj_attractive", pot, dict(rc=rc, r_switch=0.9 * rc, eps=eps, sigma=sig, topo=topo_for(has))))
+    else:
+        raise NotImplementedError(f"global force field {pot} is not in scope yet")
+
+
+# ------------------------------------------------------------------------------------------------
+def build_system(lib: Library, spec: SystemSpec) -> System:
+    """SystemGenerator::generate (src/SystemGenerator.cpp:34-111): masses, box, forces with groups."""
+    sysm = System(lib, spec.mass, spec.box)
+    for t in spec.terms:
+        getattr(sysm, "add_" + t.kind)(t.group, **t.args)
+    return sysm
+
+
+def make_context(lib: Library, spec: SystemSpec, device=0, seed=None) -> Context:
+    """Simulator ctor + initialize + set_velocity (src/Simulator.cpp:4-47, ReadTOMLInput.cpp:1094-1121)."""
+    sysm = build_system(lib, spec)
+    ctx = Context(sysm, spec.temperature, spec.friction, spec.dt, spec.seed if seed is None else seed, device)
+    ctx.set_positions(spec.positions)
+    if spec.velocities is not None:
+        ctx.set_velocities(spec.velocities)
+    else:
+        ctx.set_velocities_to_temperature(spec.temperature, spec.vel_seed)
+    ctx.group_ids = dict(spec.group_ids)
+    return ctx

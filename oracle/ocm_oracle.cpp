@@ -1,0 +1,968 @@
+// ocm_oracle.cpp — CPU ORACLE.  TEST INFRASTRUCTURE ONLY, NOT PRODUCT CODE.
+//
+// A double-precision CPU restatement of the per-step hot path of yutakasi634/OpenCafeMol, i.e.
+// of the OpenMM 8.0.0 semantics that the reference's force-field generators rely on (SURVEY.md
+// Appendix A/B).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs may load this library; the product (libocm_b200.so) never does.
+//
+// PARITY STATUS: "parity unpinned" by the reference's own tests — test/test_read_toml_ff_generator.cpp
+// holds no numeric assertion and OpenMM (where the arithmetic lives, pinned 8.0.0 by
+// .github/workflows/main.yml:25) is absent from /root/reference and cannot be built offline.
+// The oracle is instead pinned by (i) the closed-form known answers of the reference's own sample
+// inputs (tests/test_oracle_kat.py) and (ii) finite differences F = -dE/dx.
+//
+// It exports the same C ABI as include/ocm_b200.h with the prefix `oracle_` instead of `ocm_`.
+// Each potential cites the reference file:line whose expression string it restates.
+//
+// Build: make -C oracle   (g++ -O2 -fopenmp -ffp-contract=off)
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/ocm_b200.h"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return 1; }
+
+const double kBoltz = 8.31446261815324e-3;  // kJ/mol/K  (OpenMM BOLTZ)
+
+struct Vec3 {
+    double x, y, z;
+};
+inline Vec3 operator-(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline Vec3 operator+(Vec3 a, Vec3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline Vec3 operator*(Vec3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+inline double dot(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline Vec3 cross(Vec3 a, Vec3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+enum BondedKind {
+    B_HARMONIC_BOND, B_GAUSSIAN_BOND, B_GO_CONTACT, B_3SPN2_BOND,
+    B_HARMONIC_ANGLE, B_FLEX_ANGLE, B_GAUSSIAN_DIHEDRAL, B_COSINE_DIHEDRAL, B_FLEX_DIHEDRAL
+};
+
+struct BondedTerm {
+    BondedKind kind;
+    int group, periodic;
+    int nbody;                 // 2, 3 or 4
+    std::vector<int32_t> idx;  // nbody * n
+    std::vector<double> p;     // npar * n
+    int npar;
+    // FLA: natural-spline knots + second derivatives, range, e_min.  FLD: coef7 + e_min
+    double tab[24];
+    int64_t n() const { return (int64_t)idx.size() / nbody; }
+};
+
+enum PairKind { P_EXV, P_DH, P_LJREP, P_LJATT, P_3SPN2EXV };
+
+struct PairTerm {
+    PairKind kind;
+    int group, periodic;
+    double rc, rsw;
+    double g0, g1, g2;            // global parameters (meaning depends on kind)
+    std::vector<double> p0, p1;   // per-bead parameters (NaN = not a participant)
+    std::vector<int32_t> part;    // participants, ascending
+    std::vector<std::vector<int32_t>> excl;  // per bead, sorted partner list
+    std::vector<int32_t> cls;     // interaction class per bead (-1 none)
+    std::vector<uint8_t> allow;   // ncls x ncls
+    int ncls;
+};
+
+}  // namespace
+
+struct ocm_system {
+    int n;
+    std::vector<double> mass;
+    bool has_box;
+    double box[3];
+    std::vector<BondedTerm> bonded;
+    std::vector<PairTerm> pairs;
+};
+
+struct ocm_context {
+    ocm_system sys;
+    double T, gamma, dt;
+    uint64_t seed;
+    int64_t step;
+    std::vector<Vec3> x, v;
+    bool force_brute;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// geometry helpers
+inline Vec3 min_image(Vec3 d, const double* box) {
+    d.x -= box[0] * std::nearbyint(d.x / box[0]);
+    d.y -= box[1] * std::nearbyint(d.y / box[1]);
+    d.z -= box[2] * std::nearbyint(d.z / box[2]);
+    return d;
+}
+
+// natural cubic spline second derivatives on equally spaced knots (OpenMM SplineFitter::
+// createNaturalSpline as used by Continuous1DFunction)
+void natural_spline_y2(const double* y, int n, double h, double* y2) {
+    std::vector<double> a(n), b(n), c(n), r(n);
+    y2[0] = y2[n - 1] = 0.0;
+    if (n < 3) return;
+    // tridiagonal system for interior points
+    int m = n - 2;
+    std::vector<double> diag(m), rhs(m), sup(m), sub(m);
+    for (int i = 0; i < m; i++) {
+        sub[i] = h; diag[i] = 4.0 * h; sup[i] = h;
+        rhs[i] = 6.0 * ((y[i + 2] - y[i + 1]) / h - (y[i + 1] - y[i]) / h);
+    }
+    for (int i = 1; i < m; i++) {
+        double w = sub[i] / diag[i - 1];
+        diag[i] -= w * sup[i - 1];
+        rhs[i] -= w * rhs[i - 1];
+    }
+    std::vector<double> sol(m);
+    sol[m - 1] = rhs[m - 1] / diag[m - 1];
+    for (int i = m - 2; i >= 0; i--) sol[i] = (rhs[i] - sup[i] * sol[i + 1]) / diag[i];
+    for (int i = 0; i < m; i++) y2[i + 1] = sol[i];
+}
+
+// value and derivative of the spline at t in [tmin,tmax]
+inline void spline_eval(const double* y, const double* y2, int n, double tmin, double tmax,
+                        double t, double* val, double* der) {
+    double h = (tmax - tmin) / (n - 1);
+    int k = (int)std::floor((t - tmin) / h);
+    if (k < 0) k = 0;
+    if (k > n - 2) k = n - 2;
+    double a = (tmin + (k + 1) * h - t) / h;
+    double b = 1.0 - a;
+    *val = a * y[k] + b * y[k + 1] + ((a * a * a - a) * y2[k] + (b * b * b - b) * y2[k + 1]) * h * h / 6.0;
+    *der = (y[k + 1] - y[k]) / h + ((1.0 - 3.0 * a * a) * y2[k] + (3.0 * b * b - 1.0) * y2[k + 1]) * h / 6.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bonded energies: E and dE/d(coordinate) for each kind
+inline void bond_like(const BondedTerm& t, int64_t m, double r, double* E, double* dEdr) {
+    const double* p = &t.p[m * t.npar];
+    switch (t.kind) {
+        case B_HARMONIC_BOND: {  // p = r0, k     HarmonicBondForceFieldGenerator.cpp:3-14
+            double d = r - p[0];
+            *E = 0.5 * p[1] * d * d; *dEdr = p[1] * d;
+        } break;
+        case B_GAUSSIAN_BOND: {  // p = k, r0, sigma   GaussianBondForceFieldGenerator.cpp:5-9
+            double d = r - p[1];
+            double e = p[0] * std::exp(-d * d / (2.0 * p[2] * p[2]));
+            *E = e; *dEdr = -e * d / (p[2] * p[2]);
+        } break;
+        case B_GO_CONTACT: {  // p = k, r0     GoContactForceFieldGenerator.cpp:5-7
+            double s = p[1] / r, s2 = s * s, s10 = s2 * s2 * s2 * s2 * s2, s12 = s10 * s2;
+            *E = p[0] * (5.0 * s12 - 6.0 * s10);
+            *dEdr = p[0] * 60.0 * (s10 - s12) / r;
+        } break;
+        case B_3SPN2_BOND: {  // p = k2, k4, r0  ThreeSPN2BondForceFieldGenerator.cpp:5-10
+            double d = r - p[2], d2 = d * d;
+            *E = p[0] * d2 + p[1] * d2 * d2; *dEdr = 2.0 * p[0] * d + 4.0 * p[1] * d2 * d;
+        } break;
+        default: *E = 0; *dEdr = 0;
+    }
+}
+
+inline void angle_like(const BondedTerm& t, int64_t m, double th, double* E, double* dEdth) {
+    const double* p = &t.p[m * t.npar];
+    if (t.kind == B_HARMONIC_ANGLE) {  // p = theta0, k   HarmonicAngleForceFieldGenerator.cpp:5-12
+        double d = th - p[0];
+        *E = 0.5 * p[1] * d * d; *dEdth = p[1] * d;
+    } else {  // B_FLEX_ANGLE, p = k.   FlexibleLocalAngleForceFieldGenerator.cpp:21-25
+        const double* y = t.tab; const double* y2 = t.tab + 10;
+        double tmin = t.tab[20], tmax = t.tab[21], emin = t.tab[22];
+        double val = 0, der = 0;
+        if (th >= tmin && th <= tmax) spline_eval(y, y2, 10, tmin, tmax, th, &val, &der);
+        double e = val - emin, de = der;
+        if (tmin - th >= 0.0) { e += 30.0 * (tmin - th) + y[0]; de += -30.0; }  // step(x)=1 for x>=0
+        if (th - tmax >= 0.0) { e += 30.0 * (th - tmax) + y[9]; de += 30.0; }
+        *E = p[0] * e; *dEdth = p[0] * de;
+    }
+}
+
+inline void dihedral_like(const BondedTerm& t, int64_t m, double phi, double* E, double* dEdphi) {
+    const double* p = &t.p[m * t.npar];
+    const double PI = 3.14159265358979323846;
+    switch (t.kind) {
+        case B_GAUSSIAN_DIHEDRAL: {  // p = k, phi0, sigma  GaussianDihedralForceFieldGenerator.cpp:5-12
+            double dt = phi - p[1];
+            double d = dt - std::floor((dt + PI) / (2.0 * PI)) * 2.0 * PI;
+            double e = p[0] * std::exp(-d * d / (2.0 * p[2] * p[2]));
+            *E = e; *dEdphi = -e * d / (p[2] * p[2]);
+        } break;
+        case B_COSINE_DIHEDRAL: {  // p = k, t0, n     CosineDihedralForceFieldGenerator.cpp:7-12
+            double a = p[2] * (phi - p[1]);
+            *E = p[0] * (1.0 - std::cos(a)); *dEdphi = p[0] * p[2] * std::sin(a);
+        } break;
+        case B_FLEX_DIHEDRAL: {  // p = k   FlexibleLocalDihedralForceFieldGenerator.cpp:28-37
+            const double* c = t.tab; double emin = t.tab[7];
+            double e = c[0] - emin, de = 0;
+            for (int h = 1; h <= 3; h++) {
+                double cs = std::cos(h * phi), sn = std::sin(h * phi);
+                e += c[2 * h - 1] * cs + c[2 * h] * sn;
+                de += h * (-c[2 * h - 1] * sn + c[2 * h] * cs);
+            }
+            *E = p[0] * e; *dEdphi = p[0] * de;
+        } break;
+        default: *E = 0; *dEdphi = 0;
+    }
+}
+
+void eval_bonded(const ocm_context& c, const BondedTerm& t, std::vector<Vec3>* F, double* Egroup) {
+    const double* box = c.sys.box;
+    double Esum = 0;
+    for (int64_t m = 0; m < t.n(); m++) {
+        const int32_t* id = &t.idx[m * t.nbody];
+        if (t.nbody == 2) {
+            Vec3 d = c.x[id[0]] - c.x[id[1]];
+            if (t.periodic) d = min_image(d, box);
+            double r = std::sqrt(dot(d, d)), E, dE;
+            bond_like(t, m, r, &E, &dE);
+            Esum += E;
+            if (F) {
+                Vec3 f = d * (-dE / r);
+                (*F)[id[0]] = (*F)[id[0]] + f;
+                (*F)[id[1]] = (*F)[id[1]] - f;
+            }
+        } else if (t.nbody == 3) {
+            // angle at the middle particle (OpenMM angle(p1,p2,p3))
+            Vec3 a = c.x[id[0]] - c.x[id[1]], b = c.x[id[2]] - c.x[id[1]];
+            if (t.periodic) { a = min_image(a, box); b = min_image(b, box); }
+            double la = std::sqrt(dot(a, a)), lb = std::sqrt(dot(b, b));
+            double cs = dot(a, b) / (la * lb);
+            cs = std::max(-1.0, std::min(1.0, cs));
+            double th = std::acos(cs), E, dE;
+            angle_like(t, m, th, &E, &dE);
+            Esum += E;
+            if (F) {
+                double sn = std::sqrt(std::max(1.0 - cs * cs, 1e-24));
+                Vec3 ah = a * (1.0 / la), bh = b * (1.0 / lb);
+                Vec3 fi = (bh - ah * cs) * (dE / (sn * la));
+                Vec3 fk = (ah - bh * cs) * (dE / (sn * lb));
+                (*F)[id[0]] = (*F)[id[0]] + fi;
+                (*F)[id[2]] = (*F)[id[2]] + fk;
+                (*F)[id[1]] = (*F)[id[1]] - fi - fk;
+            }
+        } else {
+            // dihedral(p1,p2,p3,p4) with OpenMM's sign rule
+            Vec3 Fv = c.x[id[0]] - c.x[id[1]], G = c.x[id[1]] - c.x[id[2]], H = c.x[id[3]] - c.x[id[2]];
+            if (t.periodic) { Fv = min_image(Fv, box); G = min_image(G, box); H = min_image(H, box); }
+            Vec3 A = cross(Fv, G), B = cross(H, G);
+            double A2 = dot(A, A), B2 = dot(B, B), lG = std::sqrt(dot(G, G));
+            double cs = dot(A, B) / std::sqrt(A2 * B2);
+            cs = std::max(-1.0, std::min(1.0, cs));
+            double phi = std::acos(cs);
+            // sign: d0 = p1-p2 = Fv, c1 = d1 x d2 = (p3-p2) x (p3-p4) = (-G) x (-H) = G x H = -B
+            if (dot(Fv, B) > 0.0) phi = -phi;   // d0.c1 < 0  <=>  Fv.B > 0
+            double E, dE;
+            dihedral_like(t, m, phi, &E, &dE);
+            Esum += E;
+            if (F) {
+                double FG = dot(Fv, G), HG = dot(H, G);
+                Vec3 dp1 = A * (-lG / A2);
+                Vec3 dp4 = B * (lG / B2);
+                Vec3 dp2 = A * (lG / A2) + A * (FG / (A2 * lG)) - B * (HG / (B2 * lG));
+                Vec3 dp3 = B * (-lG / B2) - A * (FG / (A2 * lG)) + B * (HG / (B2 * lG));
+                (*F)[id[0]] = (*F)[id[0]] - dp1 * dE;
+                (*F)[id[1]] = (*F)[id[1]] - dp2 * dE;
+                (*F)[id[2]] = (*F)[id[2]] - dp3 * dE;
+                (*F)[id[3]] = (*F)[id[3]] - dp4 * dE;
+            }
+        }
+    }
+    if (Egroup) Egroup[t.group] += Esum;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair potentials: E(r) and dE/dr for one pair of term t (r < rc, not excluded, groups allowed)
+inline void pair_energy(const PairTerm& t, int i, int j, double r, double* E, double* dEdr) {
+    switch (t.kind) {
+        case P_EXV: {  // ExcludedVolumeForceFieldGenerator.cpp:25-27; g0 = eps, g1 = rc^-12
+            double s = t.p0[i] + t.p0[j];
+            double s12 = std::pow(s, 12), ir = 1.0 / r, ir12 = std::pow(ir, 12);
+            *E = t.g0 * s12 * (ir12 - t.g1);
+            *dEdr = -12.0 * t.g0 * s12 * ir12 * ir;
+        } break;
+        case P_DH: {  // DebyeHuckelForceFieldGenerator.cpp:54-57; g0 = K, g1 = debye, g2 = cc
+            double qq = t.p0[i] * t.p0[j] * t.g0;
+            double ex = std::exp(-r / t.g1);
+            *E = qq * (ex / r - t.g2);
+            *dEdr = -qq * ex * (1.0 / (r * r) + 1.0 / (t.g1 * r));
+        } break;
+        case P_LJREP: {  // LennardJonesRepulsiveForceFieldGenerator.cpp:35-43; p0 = eps, p1 = sigma
+            double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = 0.5 * (t.p0[i] + t.p0[j]);
+            double th = sg * std::pow(2.0, 1.0 / 6.0);
+            if (th - r >= 0.0) {
+                double sr = sg / r, s6 = std::pow(sr, 6), s12 = s6 * s6;
+                *E = ep * (4.0 * (s12 - s6) + 1.0);
+                *dEdr = ep * 4.0 * (-12.0 * s12 + 6.0 * s6) / r;
+            } else { *E = 0; *dEdr = 0; }
+        } break;
+        case P_LJATT: {  // LennardJonesAttractiveForceFieldGenerator.cpp:40-50 (+ switch :113-115)
+            double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = 0.5 * (t.p0[i] + t.p0[j]);
+            double th = sg * std::pow(2.0, 1.0 / 6.0);
+            double e = 0, de = 0;
+            if (r - th >= 0.0) {
+                double sr = sg / r, s6 = std::pow(sr, 6), s12 = s6 * s6;
+                e += ep * 4.0 * (s12 - s6);
+                de += ep * 4.0 * (-12.0 * s12 + 6.0 * s6) / r;
+            }
+            if (th - r >= 0.0) e -= ep;
+            // OpenMM switching function
+            if (r > t.rsw) {
+                double w = t.rc - t.rsw, x = (r - t.rsw) / w;
+                double S = 1.0 + x * x * x * (-10.0 + x * (15.0 - 6.0 * x));
+                double dS = x * x * (-30.0 + x * (60.0 - 30.0 * x)) / w;
+                de = S * de + e * dS;
+                e = e * S;
+            }
+            *E = e; *dEdr = de;
+        } break;
+        case P_3SPN2EXV: {  // ThreeSPN2ExcludedVolumeForceFieldGenerator.cpp:21-26
+            double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = std::sqrt(t.p0[i] * t.p0[j]);
+            if (sg - r >= 0.0) {
+                double sr = sg / r, s6 = std::pow(sr, 6), s12 = s6 * s6;
+                *E = ep * (s12 - 2.0 * s6) + ep;
+                *dEdr = ep * (-12.0 * s12 + 12.0 * s6) / r;
+            } else { *E = 0; *dEdr = 0; }
+        } break;
+    }
+}
+
+inline bool pair_allowed(const PairTerm& t, int i, int j) {
+    if (t.ncls > 0) {
+        int ci = t.cls[i], cj = t.cls[j];
+        if (ci < 0 || cj < 0 || !t.allow[ci * t.ncls + cj]) return false;
+    }
+    const auto& e = t.excl[i];
+    return !std::binary_search(e.begin(), e.end(), j);
+}
+
+// --- canonical FP32 / fixed-point predicate shared (bit-exactly) with the CUDA engine ---------
+// Periodic boxes: positions are quantised to 32-bit fixed-point box fractions; the wrapped
+// integer difference IS the minimum image.  Unlimited boundary: FP32 positions.
+struct Canon {
+    bool periodic;
+    std::vector<uint32_t> fx, fy, fz;  // periodic
+    std::vector<float> px, py, pz;     // non-periodic
+    float sx, sy, sz;                  // box / 2^32
+};
+
+Canon canonicalise(const ocm_context& c) {
+    Canon q;
+    int n = c.sys.n;
+    q.periodic = c.sys.has_box;
+    if (q.periodic) {
+        q.fx.resize(n); q.fy.resize(n); q.fz.resize(n);
+        double inv[3] = {1.0 / c.sys.box[0], 1.0 / c.sys.box[1], 1.0 / c.sys.box[2]};
+        for (int i = 0; i < n; i++) {
+            double u[3] = {c.x[i].x * inv[0], c.x[i].y * inv[1], c.x[i].z * inv[2]};
+            uint32_t f[3];
+            for (int k = 0; k < 3; k++) {
+                double w = u[k] - std::floor(u[k]);
+                f[k] = (uint32_t)(uint64_t)(w * 4294967296.0);
+            }
+            q.fx[i] = f[0]; q.fy[i] = f[1]; q.fz[i] = f[2];
+        }
+        q.sx = (float)(c.sys.box[0] / 4294967296.0);
+        q.sy = (float)(c.sys.box[1] / 4294967296.0);
+        q.sz = (float)(c.sys.box[2] / 4294967296.0);
+    } else {
+        q.px.resize(n); q.py.resize(n); q.pz.resize(n);
+        for (int i = 0; i < n; i++) {
+            q.px[i] = (float)c.x[i].x; q.py[i] = (float)c.x[i].y; q.pz[i] = (float)c.x[i].z;
+        }
+    }
+    return q;
+}
+
+inline float canon_r2(const Canon& q, int i, int j) {
+    float dx, dy, dz;
+    if (q.periodic) {
+        dx = (float)(int32_t)(q.fx[i] - q.fx[j]) * q.sx;
+        dy = (float)(int32_t)(q.fy[i] - q.fy[j]) * q.sy;
+        dz = (float)(int32_t)(q.fz[i] - q.fz[j]) * q.sz;
+    } else {
+        dx = q.px[i] - q.px[j]; dy = q.py[i] - q.py[j]; dz = q.pz[i] - q.pz[j];
+    }
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+// effective interaction cutoff of a term (pairs beyond contribute exactly zero)
+double effective_rc(const PairTerm& t) {
+    double rc = t.rc;
+    if (t.kind == P_LJREP || t.kind == P_3SPN2EXV) {
+        // zero beyond max over pairs of the zone boundary
+        double m1 = 0, m2 = 0;  // two largest sigma
+        for (int i : t.part) {
+            double s = t.p1[i];
+            if (s >= m1) { m2 = m1; m1 = s; } else if (s > m2) m2 = s;
+        }
+        if (t.part.size() < 2) m2 = m1;
+        double smax = 0.5 * (m1 + m2);
+        double zone = (t.kind == P_LJREP) ? smax * std::pow(2.0, 1.0 / 6.0) : smax;
+        zone *= (1.0 + 1e-6);
+        rc = std::min(rc, zone);
+    }
+    return rc;
+}
+
+// cell-list enumeration of candidate pairs (double precision positions), calling fn(i, j, d, r)
+// for every unordered participant pair with r < rc.  Brute force for small systems.
+template <class Fn>
+void for_each_pair(const ocm_context& c, const PairTerm& t, double rc, bool parallel, Fn fn) {
+    const int np = (int)t.part.size();
+    const double* box = c.sys.box;
+    const bool per = t.periodic != 0;
+    const double rc2 = rc * rc;
+    bool brute = c.force_brute || np < 1500;
+    int nc[3] = {1, 1, 1};
+    double lo[3] = {0, 0, 0}, w[3] = {1, 1, 1};
+    if (!brute) {
+        if (per) {
+            for (int k = 0; k < 3; k++) {
+                nc[k] = (int)std::floor(box[k] / rc);
+                if (nc[k] < 3) { brute = true; }
+                w[k] = box[k] / std::max(nc[k], 1);
+            }
+        } else {
+            double hi[3] = {-1e300, -1e300, -1e300};
+            lo[0] = lo[1] = lo[2] = 1e300;
+            for (int i : t.part) {
+                const double* xi = &c.x[i].x;
+                for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], xi[k]); hi[k] = std::max(hi[k], xi[k]); }
+            }
+            for (int k = 0; k < 3; k++) {
+                nc[k] = std::max(1, std::min(256, (int)std::floor((hi[k] - lo[k]) / rc) + 1));
+                w[k] = std::max(rc, (hi[k] - lo[k]) / nc[k] * (1 + 1e-12));
+            }
+        }
+    }
+    if (brute) {
+#pragma omp parallel for schedule(dynamic, 8) if (parallel)
+        for (int a = 0; a < np; a++) {
+            int i = t.part[a];
+            for (int b = a + 1; b < np; b++) {
+                int j = t.part[b];
+                Vec3 d = c.x[i] - c.x[j];
+                if (per) d = min_image(d, box);
+                double r2 = dot(d, d);
+                if (r2 < rc2) fn(i, j, d, std::sqrt(r2));
+            }
+        }
+        return;
+    }
+    // bin
+    int64_t ncell = (int64_t)nc[0] * nc[1] * nc[2];
+    std::vector<int> cell_of(np), count(ncell + 1, 0), order(np);
+    for (int a = 0; a < np; a++) {
+        const double* xi = &c.x[t.part[a]].x;
+        int ci[3];
+        for (int k = 0; k < 3; k++) {
+            double u = per ? (xi[k] - box[k] * std::floor(xi[k] / box[k])) : (xi[k] - lo[k]);
+            ci[k] = std::max(0, std::min(nc[k] - 1, (int)std::floor(u / w[k])));
+        }
+        cell_of[a] = (ci[2] * nc[1] + ci[1]) * nc[0] + ci[0];
+        count[cell_of[a] + 1]++;
+    }
+    for (int64_t k = 0; k < ncell; k++) count[k + 1] += count[k];
+    std::vector<int> cursor(count.begin(), count.end() - 1);
+    for (int a = 0; a < np; a++) order[cursor[cell_of[a]]++] = a;
+#pragma omp parallel for schedule(dynamic, 4) if (parallel)
+    for (int64_t cidx = 0; cidx < ncell; cidx++) {
+        int cx = cidx % nc[0], cy = (cidx / nc[0]) % nc[1], cz = cidx / ((int64_t)nc[0] * nc[1]);
+        for (int dz = -1; dz <= 1; dz++)
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    int ox = cx + dx, oy = cy + dy, oz = cz + dz;
+                    if (per) {
+                        ox = (ox + nc[0]) % nc[0]; oy = (oy + nc[1]) % nc[1]; oz = (oz + nc[2]) % nc[2];
+                    } else if (ox < 0 || oy < 0 || oz < 0 || ox >= nc[0] || oy >= nc[1] || oz >= nc[2]) continue;
+                    int64_t oidx = ((int64_t)oz * nc[1] + oy) * nc[0] + ox;
+                    if (oidx < cidx) continue;  // each unordered cell pair once (nc>=3 => no aliasing)
+                    for (int ua = count[cidx]; ua < count[cidx + 1]; ua++) {
+                        int a = order[ua], i = t.part[a];
+                        int vb0 = (oidx == cidx) ? ua + 1 : count[oidx];
+                        for (int vb = vb0; vb < count[oidx + 1]; vb++) {
+                            int b = order[vb], j = t.part[b];
+                            Vec3 d = c.x[i] - c.x[j];
+                            if (per) d = min_image(d, box);
+                            double r2 = dot(d, d);
+                            if (r2 < rc2) {
+                                if (i < j) fn(i, j, d, std::sqrt(r2));
+                                else fn(j, i, d * -1.0, std::sqrt(r2));
+                            }
+                        }
+                    }
+                }
+    }
+}
+
+void eval_pair(const ocm_context& c, const PairTerm& t, std::vector<Vec3>* F, double* Egroup) {
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    const int n = c.sys.n;
+    std::vector<std::vector<Vec3>> Fl;
+    if (F) Fl.assign(nthreads, std::vector<Vec3>(n, Vec3{0, 0, 0}));
+    std::vector<double> El(nthreads * 8, 0.0);
+    for_each_pair(c, t, t.rc, true, [&](int i, int j, Vec3 d, double r) {
+        if (!pair_allowed(t, i, j)) return;
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        double E, dE;
+        pair_energy(t, i, j, r, &E, &dE);
+        El[tid * 8] += E;
+        if (F) {
+            Vec3 f = d * (-dE / r);
+            Fl[tid][i] = Fl[tid][i] + f;
+            Fl[tid][j] = Fl[tid][j] - f;
+        }
+    });
+    double E = 0;
+    for (int k = 0; k < nthreads; k++) E += El[k * 8];
+    if (Egroup) Egroup[t.group] += E;
+    if (F)
+        for (int k = 0; k < nthreads; k++)
+            for (int i = 0; i < n; i++) (*F)[i] = (*F)[i] + Fl[k][i];
+}
+
+void compute(const ocm_context& c, std::vector<Vec3>* F, double* Egroup, uint32_t mask) {
+    if (F) F->assign(c.sys.n, Vec3{0, 0, 0});
+    if (Egroup) std::fill(Egroup, Egroup + 32, 0.0);
+    for (const auto& t : c.sys.bonded)
+        if (mask >> t.group & 1) eval_bonded(c, t, F, Egroup);
+    for (const auto& t : c.sys.pairs)
+        if (mask >> t.group & 1) eval_pair(c, t, F, Egroup);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), the documented noise source shared with the CUDA engine:
+// key = (seed_lo, seed_hi), counter = (bead, step_lo, step_hi, stream).
+inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                          uint32_t out[4]) {
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+inline void normals3(uint64_t seed, uint32_t bead, uint64_t step, uint32_t stream, double g[3]) {
+    uint32_t o[4];
+    philox4x32_10(bead, (uint32_t)step, (uint32_t)(step >> 32), stream, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    const double TWO_PI = 6.283185307179586476925;
+    double u0 = (o[0] + 0.5) * (1.0 / 4294967296.0), u1 = (o[1] + 0.5) * (1.0 / 4294967296.0);
+    double u2 = (o[2] + 0.5) * (1.0 / 4294967296.0), u3 = (o[3] + 0.5) * (1.0 / 4294967296.0);
+    double r0 = std::sqrt(-2.0 * std::log(u0)), r1 = std::sqrt(-2.0 * std::log(u2));
+    g[0] = r0 * std::cos(TWO_PI * u1);
+    g[1] = r0 * std::sin(TWO_PI * u1);
+    g[2] = r1 * std::cos(TWO_PI * u3);
+}
+
+int check_idx(const ocm_system* s, const int32_t* idx, int64_t cnt, const char* what) {
+    for (int64_t k = 0; k < cnt; k++)
+        if (idx[k] < 0 || idx[k] >= s->n) return fail(std::string(what) + ": particle index out of range");
+    return 0;
+}
+
+int add_bonded(ocm_system* s, BondedKind kind, int group, int periodic, int nbody, int64_t n,
+               const int32_t* idx, int npar, std::vector<const double*> cols, const char* what) {
+    if (!s) return fail("null system");
+    if (group < 0 || group > 31) return fail("force group must be in 0..31");
+    if (periodic && !s->has_box) return fail(std::string(what) + ": periodic term without a box");
+    if (check_idx(s, idx, n * nbody, what)) return 1;
+    BondedTerm t;
+    t.kind = kind; t.group = group; t.periodic = periodic; t.nbody = nbody; t.npar = npar;
+    t.idx.assign(idx, idx + n * nbody);
+    t.p.resize(n * npar);
+    for (int64_t m = 0; m < n; m++)
+        for (int q = 0; q < npar; q++) t.p[m * npar + q] = cols[q][m];
+    std::fill(t.tab, t.tab + 24, 0.0);
+    s->bonded.push_back(std::move(t));
+    return 0;
+}
+
+int add_pair(ocm_system* s, PairKind kind, int group, double rc, double rsw, double g0, double g1, double g2,
+             const double* p0, const double* p1, const ocm_pair_topology* topo, const char* what) {
+    if (!s) return fail("null system");
+    if (group < 0 || group > 31) return fail("force group must be in 0..31");
+    if (!topo) return fail("null topology");
+    if (topo->periodic && !s->has_box) return fail(std::string(what) + ": periodic term without a box");
+    if (topo->periodic)
+        for (int k = 0; k < 3; k++)
+            if (rc > 0.5 * s->box[k]) return fail(std::string(what) + ": cutoff exceeds half the box");
+    PairTerm t;
+    t.kind = kind; t.group = group; t.periodic = topo->periodic; t.rc = rc; t.rsw = rsw;
+    t.g0 = g0; t.g1 = g1; t.g2 = g2;
+    int n = s->n;
+    t.p0.assign(p0, p0 + n);
+    if (p1) t.p1.assign(p1, p1 + n); else t.p1 = t.p0;  // single-parameter kinds
+    for (int i = 0; i < n; i++) {
+        bool has0 = !std::isnan(t.p0[i]), has1 = !std::isnan(t.p1[i]);
+        if (has0 != has1) return fail(std::string(what) + ": incomplete parameter set for a particle");
+    }
+    t.excl.assign(n, {});
+    if (check_idx(s, topo->excl_ij, topo->n_excl * 2, what)) return 1;
+    for (int64_t e = 0; e < topo->n_excl; e++) {
+        int a = topo->excl_ij[2 * e], b = topo->excl_ij[2 * e + 1];
+        if (a == b) continue;
+        t.excl[a].push_back(b); t.excl[b].push_back(a);
+    }
+    for (auto& v : t.excl) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+    t.ncls = 0;
+    t.cls.assign(n, -1);
+    if (topo->n_igroups > 0) {
+        // class = membership signature over all sets
+        int ng = topo->n_igroups;
+        std::vector<std::vector<uint8_t>> sig(n, std::vector<uint8_t>(2 * ng, 0));
+        for (int g = 0; g < ng; g++) {
+            for (int64_t k = topo->set1_off[g]; k < topo->set1_off[g + 1]; k++) {
+                int b = topo->set1[k];
+                if (b < 0 || b >= n) return fail(std::string(what) + ": interaction-group index out of range");
+                sig[b][2 * g] = 1;
+            }
+            for (int64_t k = topo->set2_off[g]; k < topo->set2_off[g + 1]; k++) {
+                int b = topo->set2[k];
+                if (b < 0 || b >= n) return fail(std::string(what) + ": interaction-group index out of range");
+                sig[b][2 * g + 1] = 1;
+            }
+        }
+        std::map<std::vector<uint8_t>, int> ids;
+        std::vector<std::vector<uint8_t>> reps;
+        for (int i = 0; i < n; i++) {
+            bool any = false;
+            for (auto v : sig[i]) any |= v;
+            if (!any) continue;
+            if (std::isnan(t.p0[i])) return fail(std::string(what) + ": interaction group member without parameters");
+            auto it = ids.find(sig[i]);
+            if (it == ids.end()) { it = ids.emplace(sig[i], (int)reps.size()).first; reps.push_back(sig[i]); }
+            t.cls[i] = it->second;
+        }
+        t.ncls = (int)reps.size();
+        t.allow.assign(t.ncls * t.ncls, 0);
+        for (int a = 0; a < t.ncls; a++)
+            for (int b = 0; b < t.ncls; b++) {
+                int cnt = 0;
+                for (int g = 0; g < ng; g++)
+                    if ((reps[a][2 * g] && reps[b][2 * g + 1]) || (reps[a][2 * g + 1] && reps[b][2 * g])) cnt++;
+                if (cnt > 1) return fail(std::string(what) + ": overlapping interaction groups (a pair would be counted twice) are not supported");
+                t.allow[a * t.ncls + b] = (uint8_t)cnt;
+            }
+        for (int i = 0; i < n; i++) if (t.cls[i] >= 0) t.part.push_back(i);
+    } else {
+        for (int i = 0; i < n; i++) {
+            if (std::isnan(t.p0[i])) return fail(std::string(what) + ": a particle has no parameter but no interaction group was given");
+            t.part.push_back(i);
+        }
+    }
+    s->pairs.push_back(std::move(t));
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* oracle_last_error(void) { return g_err.c_str(); }
+const char* oracle_version(void) { return "ocm-oracle 0.1 (CPU double precision; test infrastructure)"; }
+int oracle_device_count(void) { return 0; }
+
+int oracle_system_create(int32_t n, const double* mass, const double* box, ocm_system** out) {
+    if (n <= 0 || !mass || !out) return fail("system_create: bad arguments");
+    auto* s = new ocm_system();
+    s->n = n; s->mass.assign(mass, mass + n);
+    s->has_box = box != nullptr;
+    for (int k = 0; k < 3; k++) s->box[k] = box ? box[k] : 0.0;
+    if (box) for (int k = 0; k < 3; k++) if (!(box[k] > 0)) { delete s; return fail("system_create: box edge must be positive"); }
+    *out = s;
+    return 0;
+}
+void oracle_system_destroy(ocm_system* s) { delete s; }
+int oracle_system_num_particles(const ocm_system* s) { return s ? s->n : -1; }
+
+int oracle_system_add_harmonic_bond(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* r0, const double* k) {
+    return add_bonded(s, B_HARMONIC_BOND, g, per, 2, n, ij, 2, {r0, k}, "harmonic_bond");
+}
+int oracle_system_add_gaussian_bond(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* k, const double* r0, const double* sigma) {
+    return add_bonded(s, B_GAUSSIAN_BOND, g, per, 2, n, ij, 3, {k, r0, sigma}, "gaussian_bond");
+}
+int oracle_system_add_go_contact(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* k, const double* r0) {
+    return add_bonded(s, B_GO_CONTACT, g, per, 2, n, ij, 2, {k, r0}, "go_contact");
+}
+int oracle_system_add_3spn2_bond(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* k2, const double* k4, const double* r0) {
+    return add_bonded(s, B_3SPN2_BOND, g, per, 2, n, ij, 3, {k2, k4, r0}, "3spn2_bond");
+}
+int oracle_system_add_harmonic_angle(ocm_system* s, int g, int per, int64_t n, const int32_t* ijk, const double* th0, const double* k) {
+    return add_bonded(s, B_HARMONIC_ANGLE, g, per, 3, n, ijk, 2, {th0, k}, "harmonic_angle");
+}
+int oracle_system_add_flexible_local_angle(ocm_system* s, int g, int per, int64_t n, const int32_t* ijk, const double* k,
+                                           const double* y10, double tmin, double tmax, double emin) {
+    if (add_bonded(s, B_FLEX_ANGLE, g, per, 3, n, ijk, 1, {k}, "flexible_local_angle")) return 1;
+    BondedTerm& t = s->bonded.back();
+    for (int q = 0; q < 10; q++) t.tab[q] = y10[q];
+    natural_spline_y2(y10, 10, (tmax - tmin) / 9.0, t.tab + 10);
+    t.tab[20] = tmin; t.tab[21] = tmax; t.tab[22] = emin;
+    return 0;
+}
+int oracle_system_add_gaussian_dihedral(ocm_system* s, int g, int per, int64_t n, const int32_t* ijkl, const double* k, const double* phi0, const double* sigma) {
+    return add_bonded(s, B_GAUSSIAN_DIHEDRAL, g, per, 4, n, ijkl, 3, {k, phi0, sigma}, "gaussian_dihedral");
+}
+int oracle_system_add_cosine_dihedral(ocm_system* s, int g, int per, int64_t n, const int32_t* ijkl, const double* k, const double* t0, const int32_t* nper) {
+    std::vector<double> nn(n);
+    for (int64_t m = 0; m < n; m++) nn[m] = nper[m];
+    return add_bonded(s, B_COSINE_DIHEDRAL, g, per, 4, n, ijkl, 3, {k, t0, nn.data()}, "cosine_dihedral");
+}
+int oracle_system_add_flexible_local_dihedral(ocm_system* s, int g, int per, int64_t n, const int32_t* ijkl, const double* k, const double* coef7, double emin) {
+    if (add_bonded(s, B_FLEX_DIHEDRAL, g, per, 4, n, ijkl, 1, {k}, "flexible_local_dihedral")) return 1;
+    BondedTerm& t = s->bonded.back();
+    for (int q = 0; q < 7; q++) t.tab[q] = coef7[q];
+    t.tab[7] = emin;
+    return 0;
+}
+
+int oracle_system_add_excluded_volume(ocm_system* s, int g, double eps, double rc, const double* radius, const ocm_pair_topology* topo) {
+    return add_pair(s, P_EXV, g, rc, rc, eps, std::pow(1.0 / rc, 12), 0, radius, nullptr, topo, "excluded_volume");
+}
+int oracle_system_add_debye_huckel(ocm_system* s, int g, double K, double debye, double rc, double cc, const double* charge, const ocm_pair_topology* topo) {
+    return add_pair(s, P_DH, g, rc, rc, K, debye, cc, charge, nullptr, topo, "debye_huckel");
+}
+int oracle_system_add_lj_repulsive(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
+    return add_pair(s, P_LJREP, g, rc, rc, 0, 0, 0, eps, sigma, topo, "lj_repulsive");
+}
+int oracle_system_add_lj_attractive(ocm_system* s, int g, double rc, double rsw, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
+    if (!(rsw < rc)) return fail("lj_attractive: r_switch must be below rc");
+    return add_pair(s, P_LJATT, g, rc, rsw, 0, 0, 0, eps, sigma, topo, "lj_attractive");
+}
+int oracle_system_add_3spn2_excluded_volume(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
+    return add_pair(s, P_3SPN2EXV, g, rc, rc, 0, 0, 0, eps, sigma, topo, "3spn2_excluded_volume");
+}
+
+int oracle_context_create(const ocm_system* sys, double T, double gamma, double dt, uint64_t seed, int device, ocm_context** out) {
+    (void)device;
+    if (!sys || !out) return fail("context_create: bad arguments");
+    auto* c = new ocm_context();
+    c->sys = *sys; c->T = T; c->gamma = gamma; c->dt = dt; c->seed = seed; c->step = 0;
+    c->x.assign(sys->n, Vec3{0, 0, 0}); c->v.assign(sys->n, Vec3{0, 0, 0});
+    c->force_brute = false;
+    *out = c;
+    return 0;
+}
+void oracle_context_destroy(ocm_context* c) { delete c; }
+
+int oracle_context_set_option(ocm_context* c, const char* key, double v) {
+    if (!c) return fail("null context");
+    if (!strcmp(key, "brute_force")) { c->force_brute = v != 0; return 0; }
+    if (!strcmp(key, "threads")) {
+#ifdef _OPENMP
+        omp_set_num_threads((int)v);
+#endif
+        return 0;
+    }
+    return 0;  // engine tunables are meaningless for the oracle
+}
+int oracle_context_get_option(ocm_context* c, const char* key, double* v) {
+    if (!c || !v) return fail("null argument");
+    if (!strcmp(key, "threads")) {
+#ifdef _OPENMP
+        *v = omp_get_max_threads();
+#else
+        *v = 1;
+#endif
+        return 0;
+    }
+    *v = 0; return 0;
+}
+
+int oracle_set_positions(ocm_context* c, const double* xyz) {
+    if (!c || !xyz) return fail("null argument");
+    for (int i = 0; i < c->sys.n; i++) c->x[i] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+    return 0;
+}
+int oracle_set_velocities(ocm_context* c, const double* xyz) {
+    if (!c || !xyz) return fail("null argument");
+    for (int i = 0; i < c->sys.n; i++) c->v[i] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+    return 0;
+}
+// v = sqrt(kT/m) N(0,1), no COM removal.  Noise stream 1 of the shared Philox.
+int oracle_set_velocities_to_temperature(ocm_context* c, double T, uint64_t seed) {
+    if (!c) return fail("null context");
+    for (int i = 0; i < c->sys.n; i++) {
+        double g[3];
+        normals3(seed, (uint32_t)i, 0, 1, g);
+        double m = c->sys.mass[i];
+        double s = m > 0 ? std::sqrt(kBoltz * T / m) : 0.0;
+        c->v[i] = {s * g[0], s * g[1], s * g[2]};
+    }
+    return 0;
+}
+
+// SURVEY.md B.1 (OpenMM LangevinIntegrator, leap-frog)
+int oracle_step(ocm_context* c, int64_t nsteps) {
+    if (!c) return fail("null context");
+    const double a = std::exp(-c->gamma * c->dt);
+    const double b = c->gamma == 0 ? c->dt : (1.0 - a) / c->gamma;
+    const double cc = std::sqrt(kBoltz * c->T * (1.0 - a * a));
+    std::vector<Vec3> F;
+    for (int64_t s = 0; s < nsteps; s++) {
+        compute(*c, &F, nullptr, 0xFFFFFFFFu);
+        for (int i = 0; i < c->sys.n; i++) {
+            double m = c->sys.mass[i];
+            if (!(m > 0)) continue;
+            double g[3];
+            normals3(c->seed, (uint32_t)i, (uint64_t)c->step, 0, g);
+            double im = 1.0 / m, sq = std::sqrt(im);
+            Vec3& v = c->v[i];
+            v.x = a * v.x + b * F[i].x * im + cc * sq * g[0];
+            v.y = a * v.y + b * F[i].y * im + cc * sq * g[1];
+            v.z = a * v.z + b * F[i].z * im + cc * sq * g[2];
+            c->x[i] = c->x[i] + v * c->dt;
+        }
+        c->step++;
+    }
+    return 0;
+}
+int64_t oracle_current_step(const ocm_context* c) { return c ? c->step : -1; }
+
+int oracle_get_state(ocm_context* c, uint32_t mask, double* pos, double* vel, double* force, double* epot, double* ekin, double* ebg) {
+    if (!c) return fail("null context");
+    int n = c->sys.n;
+    if (pos) for (int i = 0; i < n; i++) { pos[3 * i] = c->x[i].x; pos[3 * i + 1] = c->x[i].y; pos[3 * i + 2] = c->x[i].z; }
+    if (vel) for (int i = 0; i < n; i++) { vel[3 * i] = c->v[i].x; vel[3 * i + 1] = c->v[i].y; vel[3 * i + 2] = c->v[i].z; }
+    if (force || epot || ebg) {
+        std::vector<Vec3> F; double Eg[32];
+        compute(*c, force ? &F : nullptr, Eg, mask);
+        if (force) for (int i = 0; i < n; i++) { force[3 * i] = F[i].x; force[3 * i + 1] = F[i].y; force[3 * i + 2] = F[i].z; }
+        if (epot) { double e = 0; for (int g = 0; g < 32; g++) e += Eg[g]; *epot = e; }
+        if (ebg) std::copy(Eg, Eg + 32, ebg);
+    }
+    if (ekin) {
+        // leap-frog KE shifted by dt/2 with the current (all-group) forces, SURVEY.md B.1
+        std::vector<Vec3> F;
+        compute(*c, &F, nullptr, 0xFFFFFFFFu);
+        double ke = 0;
+        for (int i = 0; i < n; i++) {
+            double m = c->sys.mass[i];
+            if (!(m > 0)) continue;
+            Vec3 vs = c->v[i] + F[i] * (0.5 * c->dt / m);
+            ke += 0.5 * m * dot(vs, vs);
+        }
+        *ekin = ke;
+    }
+    return 0;
+}
+
+int oracle_num_pair_terms(const ocm_context* c) { return c ? (int)c->sys.pairs.size() : -1; }
+
+// pair set with the canonical FP32 / fixed-point predicate (bit-exact contract with the engine)
+int oracle_get_neighbor_pairs(ocm_context* c, int term, int32_t* ij, int64_t cap, int64_t* npairs) {
+    if (!c || !npairs) return fail("null argument");
+    if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");
+    const PairTerm& t = c->sys.pairs[term];
+    Canon q = canonicalise(*c);
+    double rce = effective_rc(t);
+    float rc2 = (float)(rce * rce);
+    std::vector<std::pair<int, int>> out;
+    // candidates from a double-precision search with a margin, decided by the canonical predicate
+    std::vector<std::vector<std::pair<int, int>>> loc(1);
+#ifdef _OPENMP
+    loc.resize(omp_get_max_threads());
+#endif
+    for_each_pair(*c, t, rce * 1.001 + 1e-4, true, [&](int i, int j, Vec3, double) {
+        if (!pair_allowed(t, i, j)) return;
+        if (canon_r2(q, i, j) < rc2) {
+            int tid = 0;
+#ifdef _OPENMP
+            tid = omp_get_thread_num();
+#endif
+            loc[tid].push_back({i, j});
+        }
+    });
+    for (auto& v : loc) out.insert(out.end(), v.begin(), v.end());
+    std::sort(out.begin(), out.end());
+    *npairs = (int64_t)out.size();
+    if (ij) {
+        if (cap < (int64_t)out.size()) return fail("get_neighbor_pairs: capacity too small");
+        for (size_t k = 0; k < out.size(); k++) { ij[2 * k] = out[k].first; ij[2 * k + 1] = out[k].second; }
+    }
+    return 0;
+}
+
+// Canonical cell assignment, shared bit-exactly with the engine: the grid is derived from the
+// term's list cutoff (effective rc + skin); see DESIGN.md "cell grid".
+static double g_skin = 0.3;
+int oracle_set_skin(double skin) { g_skin = skin; return 0; }
+
+int oracle_get_cell_ids(ocm_context* c, int term, int32_t* cell_of_bead, int32_t dims[3]) {
+    if (!c || !cell_of_bead || !dims) return fail("null argument");
+    if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");
+    const PairTerm& t = c->sys.pairs[term];
+    Canon q = canonicalise(*c);
+    int n = c->sys.n;
+    float rl = (float)(effective_rc(t) + g_skin);
+    float wmin = rl * 0.5f;
+    for (int i = 0; i < n; i++) cell_of_bead[i] = -1;
+    if (q.periodic) {
+        int nc[3];
+        for (int k = 0; k < 3; k++) {
+            nc[k] = (int)floorf((float)c->sys.box[k] / wmin);
+            nc[k] = std::max(1, std::min(nc[k], 1024));
+            dims[k] = nc[k];
+        }
+        for (int i : t.part) {
+            uint32_t cx = (uint32_t)(((uint64_t)q.fx[i] * (uint64_t)nc[0]) >> 32);
+            uint32_t cy = (uint32_t)(((uint64_t)q.fy[i] * (uint64_t)nc[1]) >> 32);
+            uint32_t cz = (uint32_t)(((uint64_t)q.fz[i] * (uint64_t)nc[2]) >> 32);
+            cell_of_bead[i] = (int32_t)((cz * nc[1] + cy) * nc[0] + cx);
+        }
+    } else {
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i : t.part) {
+            float p[3] = {q.px[i], q.py[i], q.pz[i]};
+            for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], p[k]); hi[k] = fmaxf(hi[k], p[k]); }
+        }
+        int nc[3]; float inv[3];
+        for (int k = 0; k < 3; k++) {
+            float ext = hi[k] - lo[k];
+            nc[k] = (int)floorf(ext / wmin) + 1;
+            nc[k] = std::max(1, std::min(nc[k], 1024));
+            dims[k] = nc[k];
+            inv[k] = 1.0f / wmin;
+        }
+        for (int i : t.part) {
+            float p[3] = {q.px[i], q.py[i], q.pz[i]};
+            int ci[3];
+            for (int k = 0; k < 3; k++) {
+                int v = (int)floorf((p[k] - lo[k]) * inv[k]);
+                ci[k] = std::max(0, std::min(nc[k] - 1, v));
+            }
+            cell_of_bead[i] = (ci[2] * nc[1] + ci[1]) * nc[0] + ci[0];
+        }
+    }
+    return 0;
+}
+
+int oracle_get_counter(ocm_context*, const char*, double* v) { if (v) *v = 0; return 0; }
+
+}  // extern "C"

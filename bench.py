@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — ns/day of the per-step coarse-grained MD hot path on the HPS IDR condensate slab
+(BASELINE.json configs[1]: 100 x 163-bead FUS-LC chains = 16 300 beads, Ashbaugh-Hatch + Debye-Hueckel).
+
+One bench "step" = one observer interval of the reference's run loop, i.e. ``integrator->step(save_step)``
+with save_step = 1000 MD steps (src/Simulator.cpp:49-76); ns/day = MD steps/s x dt[ps] x 86.4e-3... see
+`ns_per_day`.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # the engine (this repo)
+    python bench.py --impl reference --steps 2 --warmup 1      # CPU arm: the oracle port of the reference path
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N   # N independent replicas
+
+The line printed by rank 0 follows the driver's contract (metric/value/unit/..., e2e, roofline,
+cpu_baseline, clocks, gpu_launches).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MD_STEPS_PER_STEP = 1000  # save_step of the reference's FUS sample
+FLOP_PER_AH_PAIR = 50.0   # algorithmic FP32 flop per in-cutoff pair, Newton-3 applied
+FLOP_PER_DH_PAIR = 40.0
+BYTES_PER_BEAD_INTEGRATE = 80.0
+
+
+def ns_per_day(md_steps, dt_ps, seconds):
+    return md_steps * dt_ps * 1e-3 / seconds * 86400.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def cpu_port_run(spec, md_steps, threads=None):
+    """Times the CPU oracle (OpenMM-equivalent CPU restatement of the reference path; OpenMM itself is
+    not installable offline) on `md_steps` MD steps of the same workload."""
+    import __graft_entry__ as g
+    from opencafemol_b200 import toml_input
+    from opencafemol_b200.capi import Library
+
+    g.build_oracle()
+    lib = Library(g.ORACLE_SO, "oracle_")
+    ctx = toml_input.make_context(lib, spec)
+    if threads:
+        ctx.set_option("threads", threads)
+    cores = int(ctx.get_option("threads"))
+    ctx.step(1)
+    t0 = time.perf_counter()
+    ctx.step(md_steps)
+    dt = time.perf_counter() - t0
+    return ns_per_day(md_steps, spec.dt, dt), cores, dt
+
+
+def workload():
+    from opencafemol_b200 import synth
+
+    return synth.hps_slab(n_chains=100)
+
+
+def config_dict(spec, extra=None):
+    c = {"workload": "C2 HPS IDR condensate slab: 100 x FUS-LC(163) = 16300 beads, Ashbaugh-Hatch (rc 3.999 nm) + "
+                     "Debye-Hueckel (I=0.1 M) + harmonic bonds, Langevin 300 K, dt 0.00489 ps",
+         "beads": int(spec.mass.size), "md_steps_per_step": MD_STEPS_PER_STEP, "dt_ps": spec.dt,
+         "l2": "working set (< 40 MB) is L2-resident by construction in a real run; every MD step rewrites positions and "
+               "forces, no flush between bench steps", "parallelism": "1 replica per GPU"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec = workload()
+    sample_steps = 20
+    for _ in range(args.warmup):
+        cpu_port_run(spec, 2)
+    vals, cores = [], 1
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, cores, dt = cpu_port_run(spec, sample_steps)
+        vals.append(v); t_all += dt
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "ns/day", "value": value, "unit": "ns/day", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_all / args.steps * 1e3 * (MD_STEPS_PER_STEP / sample_steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(spec),
+        "cpu_baseline": {"value": value, "unit": "ns/day", "cores": cores, "kind": "port",
+                         "sample": f"{sample_steps} MD steps of the C2 workload per bench step (a bench step is extrapolated "
+                                   f"to {MD_STEPS_PER_STEP}); OpenMM-equivalent CPU restatement, OpenMM not installable offline"},
+        "e2e": {"value": value, "unit": "ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+
+    from opencafemol_b200 import toml_input
+    from opencafemol_b200.capi import product_library
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+
+    lib = product_library()  # raises if the CUDA extension is missing: no CPU fallback
+    spec = workload()
+    spec.seed += rank  # independent replicas
+    ctx = toml_input.make_context(lib, spec, device=local)
+    n = spec.mass.size
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up: also equilibrates the serpentine start and settles the adaptive rebuild interval
+    launches0 = None
+    for _ in range(max(args.warmup, 3)):
+        ctx.step(MD_STEPS_PER_STEP)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = ctx.counter("kernel_launches")
+    t_dev = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.step(MD_STEPS_PER_STEP)
+        t_dev += ctx.counter("last_step_ms") * 1e-3
+    barrier()
+    t_wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = ctx.counter("kernel_launches") - launches0
+    nst = ctx.counter("nstlist")
+
+    # e2e: the same metric through the C ABI with HOST buffers: per bench step upload positions and
+    # velocities, step, download positions, velocities and the energies (what Simulator::run + observers do)
+    st = ctx.get_state(positions=True, velocities=True)
+    pos, vel = st["positions"], st["velocities"]
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.set_positions(pos)
+        ctx.set_velocities(vel)
+        ctx.step(MD_STEPS_PER_STEP)
+        st = ctx.get_state(positions=True, velocities=True, energy=True)
+        pos, vel = st["positions"], st["velocities"]
+    barrier()
+    t_e2e = time.perf_counter() - te0
+    h2d = 2 * n * 3 * 8
+    d2h = 2 * n * 3 * 8 + 33 * 8
+
+    times = torch.tensor([t_dev, t_e2e, t_wall], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e, t_wall = times.tolist()
+
+    if rank == 0:
+        md = args.steps * MD_STEPS_PER_STEP
+        value = world * ns_per_day(md, spec.dt, t_dev)
+        e2e = world * ns_per_day(md, spec.dt, t_e2e)
+        # roofline of the dominant kernel (fused force launch): algorithmic FP32 flop / measured launch time
+        n_ah = len(ctx.neighbor_pairs(1))
+        n_dh = len(ctx.neighbor_pairs(2))
+        flop = n_ah * FLOP_PER_AH_PAIR + n_dh * FLOP_PER_DH_PAIR
+        ms_force = ctx.profile_kernel("force", 200)
+        ms_int = ctx.profile_kernel("integrate", 200)
+        ms_reb = ctx.profile_kernel("rebuild", 50)
+        peak = lib.measure_fp32_peak(local)
+        peaks, how = measured_peaks()
+        achieved = flop / (ms_force * 1e-3) / 1e12
+        hbm_int = n * BYTES_PER_BEAD_INTEGRATE / (ms_int * 1e-3) / 1e9
+        line = {
+            "metric": "ns/day", "value": value, "unit": "ns/day", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(spec, {"nstlist": nst, "skin_nm": ctx.get_option("skin_nm")}),
+            "md_steps_per_s": md / t_dev, "pair_interactions_per_s": (n_ah + n_dh) * md / t_dev * world,
+            "wall_ms_per_step": t_wall / args.steps * 1e3,
+            "e2e": {"value": e2e, "unit": "ns/day", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "fp32", "kernel": "force_kernel (fused pair lists + bonded)", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "peak_source": "register-resident FMA microbenchmark on this GPU (SURVEY.md 8d); no tensor-core work on this path",
+                         "algorithmic_flop_per_launch": flop, "ms_per_launch": ms_force,
+                         "in_cutoff_pairs": {"ashbaugh_hatch": n_ah, "debye_huckel": n_dh}},
+            "roofline_hbm": {"bound": "hbm", "kernel": "integrate_kernel", "achieved": hbm_int, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                             "frac": hbm_int / peaks.get("hbm_gbs", 1.0), "peak_source": how, "ms_per_launch": ms_int,
+                             "note": "16 300 beads = 1.3 MB per launch: latency-bound, L2-resident"},
+            "kernel_ms": {"force": ms_force, "integrate": ms_int, "rebuild_all_lists": ms_reb},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sample = 20
+            v, cores, dt = cpu_port_run(spec, sample)
+            line["cpu_baseline"] = {"value": v, "unit": "ns/day", "cores": cores, "kind": "port",
+                                    "sample": f"{sample} MD steps of the same C2 workload ({dt:.1f} s); OpenMM-equivalent CPU restatement "
+                                              "(oracle), OpenMM not installable offline"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    import __graft_entry__ as g
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        g.build()
+    run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

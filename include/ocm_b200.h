@@ -160,8 +160,17 @@ int ocm_get_neighbor_pairs(ocm_context*, int term, int32_t* ij, int64_t capacity
  * and the grid dimensions */
 int ocm_get_cell_ids(ocm_context*, int term, int32_t* cell_of_bead, int32_t dims[3]);
 /* counters: "pair_evals_per_step" (neighbor-list entries walked), "rebuilds", "rollbacks",
- * "kernel_launches", "nstlist", "max_neighbors" */
+ * "kernel_launches", "nstlist", "max_neighbors", "num_pair_lists", "last_step_ms" (device time of the
+ * last ocm_step, CUDA events on the engine's stream), "list_cutoff_nm.<term>", "threads_per_bead.<term>" */
 int ocm_get_counter(ocm_context*, const char* key, double* value);
+
+/* ---- measurement hooks (bench.py; CUDA events on the engine's own stream) ------------------- */
+/* average device time (ms) of `reps` back-to-back launches of one kernel at the current state:
+ * "force" (the fused per-step force launch), "integrate", "rebuild" (whole list rebuild sequence) */
+int ocm_profile_kernel(ocm_context*, const char* which, int reps, double* avg_ms);
+/* register-resident FP32 FMA microbenchmark: the attainable CUDA-core rate (TFLOP/s) that the pair
+ * kernel's roofline is quoted against */
+int ocm_measure_fp32_peak(int device_index, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -149,6 +149,8 @@ class Library:
         "get_neighbor_pairs": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int64, _i64p]),
         "get_cell_ids": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p]),
         "get_counter": (C.c_int, [C.c_void_p, C.c_char_p, _f64p]),
+        "profile_kernel": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, _f64p]),
+        "measure_fp32_peak": (C.c_int, [C.c_int, _f64p]),
     }
 
     def __init__(self, path: str = PRODUCT_LIB, prefix: str = "ocm_"):
@@ -175,6 +177,11 @@ class Library:
 
     def device_count(self) -> int:
         return int(self.fn["device_count"]())
+
+    def measure_fp32_peak(self, device=0) -> float:
+        v = C.c_double()
+        self.check(self.fn["measure_fp32_peak"](int(device), C.byref(v)))
+        return v.value
 
 
 _product = None
@@ -418,4 +425,10 @@ class Context:
     def counter(self, key):
         v = C.c_double()
         self.lib.check(self.lib.fn["get_counter"](self.handle, key.encode(), C.byref(v)))
+        return v.value
+
+    def profile_kernel(self, which, reps=50):
+        """average device milliseconds of one launch of `which` ("force", "integrate", "rebuild")"""
+        v = C.c_double()
+        self.lib.check(self.lib.fn["profile_kernel"](self.handle, which.encode(), int(reps), C.byref(v)))
         return v.value

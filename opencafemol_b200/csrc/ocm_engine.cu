@@ -1,0 +1,1102 @@
+// ocm_engine.cu — host orchestration + C ABI (include/ocm_b200.h) of the B200 engine.
+//
+// Host side of what OpenMM's Context/Integrator/Platform layer is to the reference
+// (src/Simulator.cpp:14-17,41,60; src/Observer.cpp:34,107,113,340,344): it compiles the term tables of
+// an ocm_system into device-resident tables, plans the pair lists (fusing compatible pair terms),
+// builds Verlet lists, and drives the per-step kernels through CUDA graphs.
+//
+// Stepping model: a "window" = [rebuild every pair list] + nst x [force_kernel, integrate_kernel],
+// captured once per window length as a CUDA graph.  The integrate kernel flags any bead that leaves
+// the Verlet buffer (displacement > skin/2) before the window's last step; on a flag the engine rolls
+// back to the backup taken at the start of the batch and replays with a shorter window.  Noise is
+// counter-based (Philox keyed by seed, counter = bead/step), so a replay reproduces the trajectory.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "host_system.hpp"
+#include "kernels.cuh"
+
+namespace ocm {
+thread_local std::string g_err;
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + \
+                                     __FILE__ + ":" + std::to_string(__LINE__) + " (" #expr ")");   \
+        }                                                                                           \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) CUDA_TRY(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void zero(cudaStream_t s = 0) { if (n) CUDA_TRY(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void upload(const std::vector<T>& h) {
+        alloc(h.size());
+        if (n) CUDA_TRY(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+    }
+};
+
+const double kBoltz = 8.31446261815324e-3;  // kJ/mol/K
+
+struct PairListHost {
+    std::vector<int> terms;  // member pair terms (indices into sys.pairs)
+    int form = 0;            // SEG_PAIR_TZ / SEG_PAIR_DH
+    int np = 0, ntypes = 0, stride = 0, tpb = 8;
+    double rc_list = 0;      // largest effective cutoff of the members
+    std::vector<double> rc_eff;  // per member
+    // device storage
+    DevBuf<int> part, excl_off, excl_idx, cell_of_slot, cell_count, cell_start, cell_cursor, sorted_slots, nbr_count;
+    DevBuf<unsigned char> type;
+    DevBuf<signed char> cls;
+    DevBuf<unsigned int> nbr;
+    DevBuf<GridDev> grid;
+    DevBuf<float4> tabF;
+    DevBuf<float> tabA2, tabQ;
+    DevBuf<float4> memE[kMaxMembers];
+    PairListDev dev{};       // host mirror of the device descriptor
+    int max_cells = 0;
+};
+
+}  // namespace ocm
+
+using namespace ocm;
+
+struct ocm_context {
+    ocm_system sys;  // host copy of the term tables
+    int n = 0;
+    bool periodic = false;
+    double T = 0, gamma = 0, dt = 0;
+    uint64_t seed = 0;
+    int64_t step = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    StepParams P{};
+
+    DevBuf<double> x, xref, xbak;
+    DevBuf<float4> v, vbak;
+    DevBuf<uint4> posq;
+    DevBuf<unsigned long long> fbuf;
+    DevBuf<int> flags;
+    DevBuf<unsigned long long> step_base;
+    DevBuf<double> egroup;  // 32 group energies + [32] kinetic
+    DevBuf<unsigned long long> pair_counter;
+
+    std::vector<std::unique_ptr<PairListHost>> lists;
+    std::vector<int> term_list, term_member;  // pair term -> (list, member)
+    DevBuf<PairListDev> d_lists;
+    BondedDev bonded_h[B_NUM_KINDS]{};
+    DevBuf<int> b_idx[B_NUM_KINDS], b_meta[B_NUM_KINDS];
+    DevBuf<double> b_par[B_NUM_KINDS], b_tabs;
+    DevBuf<BondedDev> d_bonded;
+    std::vector<WorkSeg> segs;
+    DevBuf<WorkSeg> d_segs;
+    int total_blocks = 0;
+    size_t smem_bytes = 0;
+
+    // options
+    double skin = 0.3;
+    int nstlist_fixed = 0;   // 0 = adaptive
+    int nst = 10;
+    int tpb_opt = 0;         // 0 = auto
+    bool lists_ready = false, positions_set = false, lists_current = false;
+    std::map<int, cudaGraphExec_t> graphs;
+    // counters
+    double n_rebuilds = 0, n_rollbacks = 0, n_launches = 0, n_windows = 0, last_step_ms = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    ~ocm_context() {
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace ocm {
+
+static const int kNstChoices[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 56, 64, 80, 100};
+
+static void drop_graphs(ocm_context* c) {
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    c->graphs.clear();
+}
+
+// ---- two-zone 12-6 coefficient sets ------------------------------------------------------------
+struct TZ { double c12i, c6i, c0i, a2, c12o, c6o, c0o; };
+
+static TZ tz_coeffs(const PairTerm& t, int i, int j) {
+    TZ z{0, 0, 0, INFINITY, 0, 0, 0};
+    switch (t.kind) {
+        case P_EXV: {  // eps (s_i+s_j)^12 (r^-12 - rc^-12)
+            double A = t.g0 * std::pow(t.p0[i] + t.p0[j], 12);
+            z.c12i = A; z.c0i = -A * t.g1;
+        } break;
+        case P_LJREP: {
+            double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = 0.5 * (t.p0[i] + t.p0[j]);
+            double th = sg * std::pow(2.0, 1.0 / 6.0);
+            z.c12i = 4 * ep * std::pow(sg, 12); z.c6i = 4 * ep * std::pow(sg, 6); z.c0i = ep; z.a2 = th * th;
+        } break;
+        case P_LJATT: {
+            double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = 0.5 * (t.p0[i] + t.p0[j]);
+            double th = sg * std::pow(2.0, 1.0 / 6.0);
+            z.c0i = -ep; z.a2 = th * th;
+            z.c12o = 4 * ep * std::pow(sg, 12); z.c6o = 4 * ep * std::pow(sg, 6);
+        } break;
+        case P_3SPN2EXV: {
+            double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = std::sqrt(t.p0[i] * t.p0[j]);
+            z.c12i = ep * std::pow(sg, 12); z.c6i = 2 * ep * std::pow(sg, 6); z.c0i = ep; z.a2 = sg * sg;
+        } break;
+        default: break;
+    }
+    return z;
+}
+
+static bool same_topology(const PairTerm& a, const PairTerm& b) {
+    return a.periodic == b.periodic && a.part == b.part && a.excl == b.excl && a.cls == b.cls && a.allow == b.allow;
+}
+
+// ---- list planning: which pair terms share one Verlet list ------------------------------------
+static void plan_lists(ocm_context* c) {
+    const auto& pairs = c->sys.pairs;
+    c->term_list.assign(pairs.size(), -1);
+    c->term_member.assign(pairs.size(), -1);
+    for (size_t t = 0; t < pairs.size(); t++) {
+        const PairTerm& pt = pairs[t];
+        int target = -1;
+        if (pt.kind == P_LJREP || pt.kind == P_LJATT) {
+            // Ashbaugh-Hatch: LJ-repulsive + LJ-attractive with identical sigma (same zone boundary)
+            for (size_t l = 0; l < c->lists.size() && target < 0; l++) {
+                auto& L = *c->lists[l];
+                if (L.form != SEG_PAIR_TZ || L.terms.size() != 1) continue;
+                const PairTerm& o = pairs[L.terms[0]];
+                bool partner = (o.kind == P_LJREP && pt.kind == P_LJATT) || (o.kind == P_LJATT && pt.kind == P_LJREP);
+                if (!partner || !same_topology(o, pt)) continue;
+                bool same_sigma = true;
+                for (int i : pt.part) if (o.p1[i] != pt.p1[i]) { same_sigma = false; break; }
+                const PairTerm& rep = (o.kind == P_LJREP) ? o : pt;
+                const PairTerm& att = (o.kind == P_LJREP) ? pt : o;
+                // the repulsive term must be zero beyond its zone inside both cutoffs, and the switch
+                // must start outside the zone
+                double zone = effective_rc(rep);
+                if (same_sigma && zone <= rep.rc && zone <= att.rsw) target = (int)l;
+            }
+        }
+        if (target < 0) {
+            c->lists.emplace_back(new PairListHost());
+            target = (int)c->lists.size() - 1;
+            c->lists[target]->form = (pt.kind == P_DH) ? SEG_PAIR_DH : SEG_PAIR_TZ;
+        }
+        c->term_list[t] = target;
+        c->term_member[t] = (int)c->lists[target]->terms.size();
+        c->lists[target]->terms.push_back((int)t);
+    }
+}
+
+static void compile_list(ocm_context* c, PairListHost& L) {
+    const auto& pairs = c->sys.pairs;
+    const PairTerm& t0 = pairs[L.terms[0]];
+    L.np = (int)t0.part.size();
+    const int nm = (int)L.terms.size();
+    // types: unique tuples of the members' per-bead parameters
+    std::map<std::vector<double>, int> ids;
+    std::vector<int> rep_bead;
+    std::vector<unsigned char> type(L.np);
+    for (int a = 0; a < L.np; a++) {
+        int i = t0.part[a];
+        std::vector<double> key;
+        for (int m = 0; m < nm; m++) { key.push_back(pairs[L.terms[m]].p0[i]); key.push_back(pairs[L.terms[m]].p1[i]); }
+        auto it = ids.find(key);
+        if (it == ids.end()) {
+            if (ids.size() >= 255) throw std::runtime_error("pair term with more than 255 distinct per-bead parameter sets is not supported");
+            it = ids.emplace(key, (int)ids.size()).first;
+            rep_bead.push_back(i);
+        }
+        type[a] = (unsigned char)it->second;
+    }
+    L.ntypes = std::max<int>(1, (int)ids.size());
+    const int nt = L.ntypes, nt2 = nt * nt;
+    L.type.upload(type);
+    L.part.upload(std::vector<int>(t0.part.begin(), t0.part.end()));
+    // exclusions CSR per slot
+    {
+        std::vector<int> slot_of(c->n, -1);
+        for (int a = 0; a < L.np; a++) slot_of[t0.part[a]] = a;
+        std::vector<std::vector<int>> ex(L.np);
+        for (auto& e : t0.excl) {
+            int a = slot_of[e.first], b = slot_of[e.second];
+            if (a < 0 || b < 0) continue;
+            ex[a].push_back(e.second); ex[b].push_back(e.first);
+        }
+        std::vector<int> off(L.np + 1, 0), idx;
+        for (int a = 0; a < L.np; a++) {
+            std::sort(ex[a].begin(), ex[a].end());
+            off[a + 1] = off[a] + (int)ex[a].size();
+            idx.insert(idx.end(), ex[a].begin(), ex[a].end());
+        }
+        if (idx.empty()) idx.push_back(0);
+        L.excl_off.upload(off); L.excl_idx.upload(idx);
+    }
+    if (t0.ncls > 0) {
+        std::vector<signed char> cl(L.np);
+        for (int a = 0; a < L.np; a++) cl[a] = (signed char)t0.cls[t0.part[a]];
+        L.cls.upload(cl);
+    }
+    // cutoffs
+    L.rc_eff.clear();
+    L.rc_list = 0;
+    for (int m = 0; m < nm; m++) { L.rc_eff.push_back(effective_rc(pairs[L.terms[m]])); L.rc_list = std::max(L.rc_list, L.rc_eff.back()); }
+    PairListDev& D = L.dev;
+    std::memset(&D, 0, sizeof(D));
+    D.np = L.np; D.ntypes = nt; D.ncls = t0.ncls; D.form = L.form; D.nmem = nm;
+    for (int k = 0; k < t0.ncls && k < 32; k++) D.allow[k] = t0.allow[k];
+    D.rc2 = (float)(L.rc_list * L.rc_list);
+    D.rsw = (float)L.rc_list; D.inv_sw = 0.f; D.has_switch = 0;
+    if (L.form == SEG_PAIR_DH) {
+        std::vector<float> tq(nt2);
+        for (int a = 0; a < nt; a++)
+            for (int b = 0; b < nt; b++) tq[a * nt + b] = (float)(t0.p0[rep_bead[a]] * t0.p0[rep_bead[b]] * t0.g0);
+        if (rep_bead.empty()) tq.assign(1, 0.f);
+        L.tabQ.upload(tq);
+        D.inv_debye = (float)(1.0 / t0.g1); D.dh_cc = (float)t0.g2;
+        D.mem_group[0] = t0.group; D.mem_rc2[0] = D.rc2;
+    } else {
+        std::vector<float4> tf(nt2, make_float4(0, 0, 0, 0));
+        std::vector<float> ta(nt2, INFINITY);
+        for (int m = 0; m < nm; m++) {
+            const PairTerm& t = pairs[L.terms[m]];
+            std::vector<float4> te(2 * nt2, make_float4(0, 0, 0, 0));
+            for (int a = 0; a < nt && !rep_bead.empty(); a++)
+                for (int b = 0; b < nt; b++) {
+                    TZ z = tz_coeffs(t, rep_bead[a], rep_bead[b]);
+                    int k = a * nt + b;
+                    tf[k].x += (float)z.c12i; tf[k].y += (float)z.c6i; tf[k].z += (float)z.c12o; tf[k].w += (float)z.c6o;
+                    if (std::isfinite(z.a2)) ta[k] = (float)z.a2;
+                    te[2 * k] = make_float4((float)z.c12i, (float)z.c6i, (float)z.c0i, (float)z.a2);
+                    te[2 * k + 1] = make_float4((float)z.c12o, (float)z.c6o, (float)z.c0o, 0.f);
+                }
+            L.memE[m].upload(te);
+            D.memE[m] = L.memE[m].p;
+            D.mem_group[m] = t.group;
+            D.mem_rc2[m] = (float)(t.rc * t.rc);
+            D.mem_switch[m] = (t.kind == P_LJATT) ? 1 : 0;
+            if (t.kind == P_LJATT) {
+                D.has_switch = 1; D.rsw = (float)t.rsw; D.inv_sw = (float)(1.0 / (t.rc - t.rsw));
+            }
+        }
+        L.tabF.upload(tf); L.tabA2.upload(ta);
+    }
+    D.part = L.part.p; D.type = L.type.p; D.cls = L.cls.p;
+    D.excl_off = L.excl_off.p; D.excl_idx = L.excl_idx.p;
+    D.tabF = L.tabF.p; D.tabA2 = L.tabA2.p; D.tabQ = L.tabQ.p;
+    D.smem_tab = (L.form == SEG_PAIR_TZ && nt <= 64) ? 1 : 0;
+    L.cell_of_slot.alloc(std::max(L.np, 1)); L.sorted_slots.alloc(std::max(L.np, 1)); L.nbr_count.alloc(std::max(L.np, 1));
+    L.nbr_count.zero();
+    D.cell_of_slot = L.cell_of_slot.p; D.sorted_slots = L.sorted_slots.p; D.nbr_count = L.nbr_count.p;
+}
+
+// (re)derive everything that depends on the skin: list radius, cell grid
+static void configure_grid(ocm_context* c, PairListHost& L) {
+    PairListDev& D = L.dev;
+    const double rlist = L.rc_list + c->skin;
+    D.rlist2 = (float)(rlist * rlist);
+    D.wmin = 0.5f * (float)rlist;
+    GridDev g{};
+    for (int k = 0; k < 3; k++) { g.bmin[k] = 0x7FFFFFFF; g.bmax[k] = (int)0x80000000; g.lo[k] = 0.f; }
+    if (c->periodic) {
+        long long tot = 1;
+        for (int k = 0; k < 3; k++) {
+            int nc = (int)floorf((float)c->sys.box[k] / D.wmin);
+            g.nc[k] = std::max(1, std::min(nc, 1024));
+            tot *= g.nc[k];
+        }
+        if (tot > (1ll << 26)) throw std::runtime_error("cell grid too large");
+        g.ncell = (int)tot;
+        g.inv_w = 1.0f / D.wmin;
+        L.max_cells = g.ncell;
+    } else {
+        g.nc[0] = g.nc[1] = g.nc[2] = 1; g.ncell = 1; g.inv_w = 1.0f / D.wmin;
+        L.max_cells = std::max(4096, std::min(1 << 21, 8 * L.np + 64));
+    }
+    L.grid.upload(std::vector<GridDev>(1, g));
+    L.cell_count.alloc(L.max_cells + 1); L.cell_count.zero();
+    L.cell_start.alloc(L.max_cells + 1); L.cell_start.zero();
+    L.cell_cursor.alloc(L.max_cells);
+    D.grid = L.grid.p; D.max_cells = L.max_cells;
+    D.cell_count = L.cell_count.p; D.cell_start = L.cell_start.p; D.cell_cursor = L.cell_cursor.p;
+}
+
+static void upload_lists(ocm_context* c) {
+    std::vector<PairListDev> h;
+    for (auto& L : c->lists) h.push_back(L->dev);
+    if (h.empty()) h.emplace_back();
+    c->d_lists.upload(h);
+}
+
+static int pick_tpb(const ocm_context* c, const PairListHost& L) {
+    if (c->tpb_opt == 4 || c->tpb_opt == 8 || c->tpb_opt == 16 || c->tpb_opt == 32) return c->tpb_opt;
+    // enough warps to fill 148 SMs x 16 resident warps, but not more lanes per bead than useful
+    const double lanes_wanted = 148.0 * 16 * 32;
+    int t = 32;
+    while (t > 4 && (double)L.np * t > 4.0 * lanes_wanted) t >>= 1;
+    if (L.stride > 0) while (t > 4 && L.stride < 4 * t) t >>= 1;
+    return t;
+}
+
+static void build_segments(ocm_context* c) {
+    c->segs.clear();
+    int blk = 0;
+    size_t smem = 0;
+    for (size_t l = 0; l < c->lists.size(); l++) {
+        auto& L = *c->lists[l];
+        if (L.np == 0) continue;
+        L.tpb = pick_tpb(c, L);
+        int bpb = kBlock / L.tpb;
+        int nb = (L.np + bpb - 1) / bpb;
+        c->segs.push_back({blk, nb, L.form, (int)l, L.tpb});
+        blk += nb;
+        if (L.dev.smem_tab) smem = std::max(smem, (size_t)L.ntypes * L.ntypes * 20);
+    }
+    for (int k = 0; k < B_NUM_KINDS; k++) {
+        if (c->bonded_h[k].n == 0) continue;
+        int nb = (c->bonded_h[k].n + kBlock - 1) / kBlock;
+        c->segs.push_back({blk, nb, SEG_BONDED, k, 0});
+        blk += nb;
+    }
+    c->total_blocks = blk;
+    c->smem_bytes = smem;
+    if (c->segs.empty()) c->segs.push_back({0, 0, SEG_BONDED, 0, 0});
+    c->d_segs.upload(c->segs);
+    if (smem > 48 * 1024) {
+        CUDA_TRY(cudaFuncSetAttribute(force_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(force_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    drop_graphs(c);
+}
+
+static void compile_bonded(ocm_context* c) {
+    std::vector<double> tabs(24, 0.0);  // table 0 = dummy
+    for (int k = 0; k < B_NUM_KINDS; k++) {
+        std::vector<int> idx, meta;
+        std::vector<double> par;
+        int npar = 0, nbody = bonded_nbody(k);
+        for (const auto& t : c->sys.bonded) {
+            if (t.kind != k) continue;
+            npar = t.npar;
+            int tab_id = 0;
+            if (k == B_FLEX_ANGLE || k == B_FLEX_DIHEDRAL) {
+                tab_id = (int)(tabs.size() / 24);
+                if (tab_id >= 32768) throw std::runtime_error("too many flexible-local tables");
+                tabs.insert(tabs.end(), t.tab, t.tab + 24);
+            }
+            idx.insert(idx.end(), t.idx.begin(), t.idx.end());
+            par.insert(par.end(), t.p.begin(), t.p.end());
+            for (int64_t m = 0; m < t.n(); m++) meta.push_back(t.group | (t.periodic << 8) | (tab_id << 16));
+        }
+        BondedDev& B = c->bonded_h[k];
+        B.n = (int)(idx.size() / nbody); B.npar = npar;
+        if (B.n) {
+            c->b_idx[k].upload(idx); c->b_par[k].upload(par); c->b_meta[k].upload(meta);
+            B.idx = c->b_idx[k].p; B.par = c->b_par[k].p; B.meta = c->b_meta[k].p;
+        }
+    }
+    c->b_tabs.upload(tabs);
+    for (int k = 0; k < B_NUM_KINDS; k++) c->bonded_h[k].tabs = c->b_tabs.p;
+    c->d_bonded.upload(std::vector<BondedDev>(c->bonded_h, c->bonded_h + B_NUM_KINDS));
+}
+
+static void update_params(ocm_context* c) {
+    StepParams& P = c->P;
+    P.n = c->n; P.periodic = c->periodic ? 1 : 0;
+    for (int k = 0; k < 3; k++) {
+        P.box[k] = c->periodic ? c->sys.box[k] : 1.0;
+        P.inv_box[k] = 1.0 / P.box[k];
+        P.fscale[k] = (float)(P.box[k] / 4294967296.0);
+    }
+    P.dt = c->dt;
+    const double a = std::exp(-c->gamma * c->dt);
+    P.a = (float)a;
+    P.b = (float)(c->gamma == 0 ? c->dt : (1.0 - a) / c->gamma);
+    P.c = (float)std::sqrt(kBoltz * c->T * (1.0 - a * a));
+    P.seed_lo = (unsigned int)c->seed; P.seed_hi = (unsigned int)(c->seed >> 32);
+    P.half_skin2 = (float)(0.25 * c->skin * c->skin);
+}
+
+// ---- enqueue helpers ----------------------------------------------------------------------------
+static inline int nblk(int n, int b) { return std::max(1, (n + b - 1) / b); }
+
+static void enqueue_rebuild(ocm_context* c, cudaStream_t s, bool count_only) {
+    const int n = c->n;
+    if (!count_only) save_ref_kernel<<<nblk(3 * n, 256), 256, 0, s>>>(n, c->x.p, c->xref.p);
+    for (size_t l = 0; l < c->lists.size(); l++) {
+        auto& L = *c->lists[l];
+        if (L.np == 0) continue;
+        const int li = (int)l;
+        if (c->periodic) {
+            bin_kernel<true><<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
+        } else {
+            bbox_kernel<<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
+            grid_kernel<<<1, 1, 0, s>>>(c->d_lists.p, li);
+            bin_kernel<false><<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
+        }
+        scan_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li);
+        scatter_kernel<<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li);
+        sortcell_kernel<<<std::min(nblk(L.max_cells, 128), 2048), 128, 0, s>>>(c->d_lists.p, li);
+        if (c->periodic)
+            build_list_kernel<true><<<nblk(L.np * 32, 256), 256, 0, s>>>(c->d_lists.p, li, c->P, c->posq.p, c->flags.p, count_only ? 1 : 0);
+        else
+            build_list_kernel<false><<<nblk(L.np * 32, 256), 256, 0, s>>>(c->d_lists.p, li, c->P, c->posq.p, c->flags.p, count_only ? 1 : 0);
+        c->n_launches += c->periodic ? 5 : 7;
+    }
+    if (!count_only) { c->n_launches += 1; c->n_rebuilds += 1; }
+}
+
+static void enqueue_forces(ocm_context* c, cudaStream_t s) {
+    if (c->total_blocks == 0) return;
+    if (c->periodic)
+        force_kernel<true><<<c->total_blocks, kBlock, c->smem_bytes, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->P, c->posq.p, c->x.p, c->fbuf.p);
+    else
+        force_kernel<false><<<c->total_blocks, kBlock, c->smem_bytes, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->P, c->posq.p, c->x.p, c->fbuf.p);
+    c->n_launches += 1;
+}
+
+// size (or re-size) the Verlet rows from a counting pass at the current positions
+static void size_lists(ocm_context* c, double growth) {
+    cudaStream_t s = c->stream;
+    for (auto& L : c->lists) configure_grid(c, *L);
+    upload_lists(c);
+    std::vector<int> fl(FLAG_COUNT, 0);
+    // one counting pass per list: FLAG_MAXDISP+1 receives the largest neighbour count of that list
+    for (size_t l = 0; l < c->lists.size(); l++) {
+        auto& L = *c->lists[l];
+        if (L.np == 0) continue;
+        CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, FLAG_COUNT * sizeof(int), s));
+        const int li = (int)l;
+        if (c->periodic) bin_kernel<true><<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
+        else {
+            bbox_kernel<<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
+            grid_kernel<<<1, 1, 0, s>>>(c->d_lists.p, li);
+            bin_kernel<false><<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
+        }
+        scan_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li);
+        scatter_kernel<<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li);
+        sortcell_kernel<<<std::min(nblk(L.max_cells, 128), 2048), 128, 0, s>>>(c->d_lists.p, li);
+        if (c->periodic) build_list_kernel<true><<<nblk(L.np * 32, 256), 256, 0, s>>>(c->d_lists.p, li, c->P, c->posq.p, c->flags.p, 1);
+        else build_list_kernel<false><<<nblk(L.np * 32, 256), 256, 0, s>>>(c->d_lists.p, li, c->P, c->posq.p, c->flags.p, 1);
+        CUDA_TRY(cudaMemcpyAsync(fl.data(), c->flags.p, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        int maxn = fl[FLAG_MAXDISP + 1];
+        int want = (int)(maxn * growth) + 16;
+        want = (want + 31) / 32 * 32;
+        if (want > L.stride) {
+            L.stride = want;
+            L.nbr.alloc((size_t)std::max(L.np, 1) * L.stride);
+        }
+        L.dev.stride = L.stride; L.dev.nbr = L.nbr.p;
+    }
+    CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, FLAG_COUNT * sizeof(int), s));
+    upload_lists(c);
+    build_segments(c);
+    c->lists_ready = true;
+    c->lists_current = false;
+}
+
+static void ensure_lists_current(ocm_context* c) {
+    if (!c->positions_set) throw std::runtime_error("positions have not been set");
+    if (!c->lists_ready) size_lists(c, 1.25);
+    if (c->lists_current) return;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        enqueue_rebuild(c, c->stream, false);
+        int fl[FLAG_COUNT];
+        CUDA_TRY(cudaMemcpyAsync(fl, c->flags.p, sizeof(fl), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (!fl[FLAG_OVERFLOW]) { c->lists_current = true; return; }
+        size_lists(c, 1.5);
+    }
+    throw std::runtime_error("neighbour list keeps overflowing");
+}
+
+static cudaGraphExec_t window_graph(ocm_context* c, int nst) {
+    auto it = c->graphs.find(nst);
+    if (it != c->graphs.end()) return it->second;
+    cudaStream_t s = c->stream;
+    cudaGraph_t g;
+    double launches_before = c->n_launches, rebuilds_before = c->n_rebuilds;
+    CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    enqueue_rebuild(c, s, false);
+    for (int k = 0; k < nst; k++) {
+        enqueue_forces(c, s);
+        integrate_kernel<<<nblk(c->n, 128), 128, 0, s>>>(c->P, c->x.p, c->v.p, c->fbuf.p, c->posq.p, c->xref.p,
+                                                         c->step_base.p, k, nst, k == nst - 1 ? 1 : 0, c->flags.p);
+    }
+    CUDA_TRY(cudaStreamEndCapture(s, &g));
+    c->n_launches = launches_before; c->n_rebuilds = rebuilds_before;  // counted per launch of the graph instead
+    cudaGraphExec_t ge;
+    CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
+    CUDA_TRY(cudaGraphDestroy(g));
+    c->graphs[nst] = ge;
+    return ge;
+}
+
+static double launches_per_window(const ocm_context* c, int nst) {
+    double per_rebuild = 1;
+    for (auto& L : c->lists) if (L->np) per_rebuild += c->periodic ? 5 : 7;
+    return per_rebuild + nst * (1.0 + (c->total_blocks > 0 ? 1.0 : 0.0));
+}
+
+static int quantise_nst(double want) {
+    int best = 1;
+    for (int v : kNstChoices) if (v <= want) best = v;
+    return best;
+}
+
+static int initial_nst(const ocm_context* c) {
+    // ballistic bound: fastest bead ~ 5 sigma_v, lightest mass
+    double mmin = 1e300;
+    for (double m : c->sys.mass) if (m > 0) mmin = std::min(mmin, m);
+    if (!(mmin < 1e300)) return 1;
+    double vmax = 5.0 * std::sqrt(kBoltz * std::max(c->T, 1.0) / mmin);
+    double n = 0.5 * c->skin / (vmax * c->dt);
+    return quantise_nst(std::max(1.0, std::min(100.0, n)));
+}
+
+static void do_steps(ocm_context* c, int64_t nsteps) {
+    if (nsteps <= 0) return;
+    if (!c->positions_set) throw std::runtime_error("positions have not been set");
+    if (!c->lists_ready) size_lists(c, 1.25);
+    cudaStream_t s = c->stream;
+    const size_t xb = (size_t)3 * c->n * sizeof(double), vb = (size_t)c->n * sizeof(float4);
+    int64_t done = 0;
+    if (c->nstlist_fixed > 0) c->nst = c->nstlist_fixed;
+    CUDA_TRY(cudaEventRecord(c->ev0, s));
+    while (done < nsteps) {
+        // one batch = up to 16 windows between host synchronisations
+        CUDA_TRY(cudaMemcpyAsync(c->xbak.p, c->x.p, xb, cudaMemcpyDeviceToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->vbak.p, c->v.p, vb, cudaMemcpyDeviceToDevice, s));
+        const int64_t step0 = c->step + done;
+        unsigned long long sb = (unsigned long long)step0;
+        CUDA_TRY(cudaMemcpyAsync(c->step_base.p, &sb, sizeof(sb), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, FLAG_COUNT * sizeof(int), s));
+        int64_t batch = 0;
+        int windows = 0;
+        double launches = 0;
+        const int nst = c->nst;
+        while (done + batch < nsteps && windows < 16) {
+            int w = (int)std::min<int64_t>(nst, nsteps - done - batch);
+            CUDA_TRY(cudaGraphLaunch(window_graph(c, w), s));
+            launches += launches_per_window(c, w);
+            batch += w; windows++;
+        }
+        int fl[FLAG_COUNT];
+        CUDA_TRY(cudaMemcpyAsync(fl, c->flags.p, sizeof(fl), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (fl[FLAG_NAN]) throw std::runtime_error("particle coordinate or force is NaN");
+        if (fl[FLAG_VIOLATION] || fl[FLAG_OVERFLOW]) {
+            // roll back and replay the batch with a safer configuration
+            CUDA_TRY(cudaMemcpyAsync(c->x.p, c->xbak.p, xb, cudaMemcpyDeviceToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(c->v.p, c->vbak.p, vb, cudaMemcpyDeviceToDevice, s));
+            CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, (size_t)3 * c->n * sizeof(unsigned long long), s));
+            canon_kernel<<<nblk(c->n, 256), 256, 0, s>>>(c->P, c->x.p, c->posq.p);
+            c->n_rollbacks += 1;
+            if (fl[FLAG_OVERFLOW]) size_lists(c, 1.5);
+            if (fl[FLAG_VIOLATION]) {
+                if (c->nst <= 1) throw std::runtime_error("a particle crosses the Verlet buffer within one step; increase skin_nm or reduce the time step");
+                c->nst = quantise_nst(std::max(1.0, c->nst * 0.6));
+            }
+            continue;
+        }
+        c->n_launches += launches; c->n_windows += windows; c->n_rebuilds += windows;
+        done += batch;
+        // adapt the rebuild interval from the largest end-of-window displacement (only full windows count)
+        if (c->nstlist_fixed <= 0 && batch >= nst) {
+            float d2;
+            std::memcpy(&d2, &fl[FLAG_MAXDISP], sizeof(float));
+            double disp = std::sqrt((double)d2), half = 0.5 * c->skin;
+            if (disp > 0) {
+                double ratio = 0.70 * half / disp;  // aim the last step at 70 % of the buffer
+                double want = c->nst * std::min(1.5, std::max(0.6, ratio));
+                int q = quantise_nst(std::max(1.0, want));
+                if (q < c->nst || ratio > 1.25) c->nst = q;
+            }
+        }
+    }
+    CUDA_TRY(cudaEventRecord(c->ev1, s));
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_step_ms = ms;
+    c->step += nsteps;
+    c->lists_current = false;
+}
+
+static void compute_forces_into_fbuf(ocm_context* c) {
+    ensure_lists_current(c);
+    CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, (size_t)3 * c->n * sizeof(unsigned long long), c->stream));
+    enqueue_forces(c, c->stream);
+}
+
+}  // namespace ocm
+
+// ================================================================================================
+#define OCM_GUARD_BEGIN try {
+#define OCM_GUARD_END                                             \
+    }                                                             \
+    catch (const std::exception& e) { return ocm::fail(e.what()); } \
+    catch (...) { return ocm::fail("unknown error"); }
+
+extern "C" {
+
+const char* ocm_last_error(void) { return g_err.c_str(); }
+const char* ocm_version(void) { return "ocm-b200 0.1 (sm_100a)"; }
+int ocm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ocm_system_create(int32_t n, const double* mass, const double* box, ocm_system** out) {
+    if (n <= 0 || !mass || !out) return fail("system_create: bad arguments");
+    if (n >= (1 << 24)) return fail("system_create: at most 16,777,215 particles are supported");
+    if (box) for (int k = 0; k < 3; k++) if (!(box[k] > 0)) return fail("system_create: box edge must be positive");
+    auto* s = new ocm_system();
+    s->n = n; s->mass.assign(mass, mass + n); s->has_box = box != nullptr;
+    for (int k = 0; k < 3; k++) s->box[k] = box ? box[k] : 0.0;
+    *out = s;
+    return 0;
+}
+void ocm_system_destroy(ocm_system* s) { delete s; }
+int ocm_system_num_particles(const ocm_system* s) { return s ? s->n : -1; }
+
+int ocm_system_add_harmonic_bond(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* r0, const double* k) {
+    return add_bonded(s, B_HARMONIC_BOND, g, per, n, ij, {r0, k}, "harmonic_bond");
+}
+int ocm_system_add_gaussian_bond(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* k, const double* r0, const double* sigma) {
+    return add_bonded(s, B_GAUSSIAN_BOND, g, per, n, ij, {k, r0, sigma}, "gaussian_bond");
+}
+int ocm_system_add_go_contact(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* k, const double* r0) {
+    return add_bonded(s, B_GO_CONTACT, g, per, n, ij, {k, r0}, "go_contact");
+}
+int ocm_system_add_3spn2_bond(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* k2, const double* k4, const double* r0) {
+    return add_bonded(s, B_3SPN2_BOND, g, per, n, ij, {k2, k4, r0}, "3spn2_bond");
+}
+int ocm_system_add_harmonic_angle(ocm_system* s, int g, int per, int64_t n, const int32_t* ijk, const double* th0, const double* k) {
+    return add_bonded(s, B_HARMONIC_ANGLE, g, per, n, ijk, {th0, k}, "harmonic_angle");
+}
+int ocm_system_add_flexible_local_angle(ocm_system* s, int g, int per, int64_t n, const int32_t* ijk, const double* k,
+                                        const double* y10, double tmin, double tmax, double emin) {
+    if (!y10 || !(tmax > tmin)) return fail("flexible_local_angle: bad table");
+    if (add_bonded(s, B_FLEX_ANGLE, g, per, n, ijk, {k}, "flexible_local_angle")) return 1;
+    BondedTerm& t = s->bonded.back();
+    for (int q = 0; q < 10; q++) t.tab[q] = y10[q];
+    natural_spline_second_derivatives(y10, 10, (tmax - tmin) / 9.0, t.tab + 10);
+    t.tab[20] = tmin; t.tab[21] = tmax; t.tab[22] = emin;
+    return 0;
+}
+int ocm_system_add_gaussian_dihedral(ocm_system* s, int g, int per, int64_t n, const int32_t* ijkl, const double* k, const double* phi0, const double* sigma) {
+    return add_bonded(s, B_GAUSSIAN_DIHEDRAL, g, per, n, ijkl, {k, phi0, sigma}, "gaussian_dihedral");
+}
+int ocm_system_add_cosine_dihedral(ocm_system* s, int g, int per, int64_t n, const int32_t* ijkl, const double* k, const double* t0, const int32_t* nper) {
+    if (n > 0 && !nper) return fail("cosine_dihedral: null periodicity array");
+    std::vector<double> nn((size_t)std::max<int64_t>(n, 0));
+    for (int64_t m = 0; m < n; m++) nn[m] = nper[m];
+    return add_bonded(s, B_COSINE_DIHEDRAL, g, per, n, ijkl, {k, t0, nn.data()}, "cosine_dihedral");
+}
+int ocm_system_add_flexible_local_dihedral(ocm_system* s, int g, int per, int64_t n, const int32_t* ijkl, const double* k, const double* coef7, double emin) {
+    if (!coef7) return fail("flexible_local_dihedral: null coefficient table");
+    if (add_bonded(s, B_FLEX_DIHEDRAL, g, per, n, ijkl, {k}, "flexible_local_dihedral")) return 1;
+    BondedTerm& t = s->bonded.back();
+    for (int q = 0; q < 7; q++) t.tab[q] = coef7[q];
+    t.tab[7] = emin;
+    return 0;
+}
+
+int ocm_system_add_excluded_volume(ocm_system* s, int g, double eps, double rc, const double* radius, const ocm_pair_topology* topo) {
+    return add_pair(s, P_EXV, g, rc, rc, eps, std::pow(1.0 / rc, 12), 0, radius, nullptr, topo, "excluded_volume");
+}
+int ocm_system_add_debye_huckel(ocm_system* s, int g, double K, double debye, double rc, double cc, const double* charge, const ocm_pair_topology* topo) {
+    if (!(debye > 0)) return fail("debye_huckel: debye length must be positive");
+    return add_pair(s, P_DH, g, rc, rc, K, debye, cc, charge, nullptr, topo, "debye_huckel");
+}
+int ocm_system_add_lj_repulsive(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
+    if (!sigma) return fail("lj_repulsive: null sigma");
+    return add_pair(s, P_LJREP, g, rc, rc, 0, 0, 0, eps, sigma, topo, "lj_repulsive");
+}
+int ocm_system_add_lj_attractive(ocm_system* s, int g, double rc, double rsw, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
+    if (!sigma) return fail("lj_attractive: null sigma");
+    if (!(rsw < rc)) return fail("lj_attractive: r_switch must be below rc");
+    return add_pair(s, P_LJATT, g, rc, rsw, 0, 0, 0, eps, sigma, topo, "lj_attractive");
+}
+int ocm_system_add_3spn2_excluded_volume(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
+    if (!sigma) return fail("3spn2_excluded_volume: null sigma");
+    return add_pair(s, P_3SPN2EXV, g, rc, rc, 0, 0, 0, eps, sigma, topo, "3spn2_excluded_volume");
+}
+
+int ocm_context_create(const ocm_system* sys, double T, double gamma, double dt, uint64_t seed, int device, ocm_context** out) {
+    if (!sys || !out) return fail("context_create: bad arguments");
+    if (!(dt > 0)) return fail("context_create: time step must be positive");
+    int ndev = ocm_device_count();
+    if (ndev <= 0) return fail("context_create: no CUDA device available (this engine has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("context_create: device index out of range");
+    ocm_context* c = nullptr;
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(device));
+    c = new ocm_context();
+    c->sys = *sys; c->n = sys->n; c->periodic = sys->has_box;
+    c->T = T; c->gamma = gamma; c->dt = dt; c->seed = seed; c->device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+    const int n = c->n;
+    c->x.alloc(3 * (size_t)n); c->xref.alloc(3 * (size_t)n); c->xbak.alloc(3 * (size_t)n);
+    c->v.alloc(n); c->vbak.alloc(n); c->posq.alloc(n); c->fbuf.alloc(3 * (size_t)n);
+    c->flags.alloc(FLAG_COUNT); c->step_base.alloc(1); c->egroup.alloc(40); c->pair_counter.alloc(1);
+    c->x.zero(); c->xref.zero(); c->fbuf.zero(); c->flags.zero(); c->step_base.zero(); c->posq.zero();
+    std::vector<float4> v0(n);
+    for (int i = 0; i < n; i++) v0[i] = make_float4(0, 0, 0, sys->mass[i] > 0 ? (float)(1.0 / sys->mass[i]) : 0.f);
+    CUDA_TRY(cudaMemcpy(c->v.p, v0.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    // default skin: 8 % of the largest cutoff, within [0.1, 0.4] nm
+    plan_lists(c);
+    double rcmax = 0;
+    for (auto& L : c->lists) { compile_list(c, *L); rcmax = std::max(rcmax, L->rc_list); }
+    c->skin = std::min(0.4, std::max(0.1, 0.08 * rcmax));
+    if (c->periodic)
+        for (auto& L : c->lists)
+            for (int k = 0; k < 3; k++)
+                if (L->rc_list + c->skin > 0.5 * sys->box[k]) c->skin = std::max(0.0, 0.5 * sys->box[k] - L->rc_list) * 0.999;
+    compile_bonded(c);
+    update_params(c);
+    c->nst = initial_nst(c);
+    CUDA_TRY(cudaDeviceSynchronize());
+    *out = c;
+    return 0;
+    }
+    catch (const std::exception& e) { delete c; return ocm::fail(e.what()); }
+    catch (...) { delete c; return ocm::fail("unknown error"); }
+}
+void ocm_context_destroy(ocm_context* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    delete c;
+}
+
+int ocm_context_set_option(ocm_context* c, const char* key, double value) {
+    if (!c || !key) return fail("null argument");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::string k(key);
+    if (k == "skin_nm") {
+        if (!(value > 0)) return fail("skin_nm must be positive");
+        if (c->periodic)
+            for (auto& L : c->lists)
+                for (int d = 0; d < 3; d++)
+                    if (L->rc_list + value > 0.5 * c->sys.box[d]) return fail("skin_nm: cutoff + skin exceeds half the box");
+        c->skin = value;
+        update_params(c);
+        c->lists_ready = false; c->lists_current = false;
+        for (auto& L : c->lists) L->stride = 0;
+        drop_graphs(c);
+        if (c->nstlist_fixed <= 0) c->nst = initial_nst(c);
+    } else if (k == "nstlist") {
+        c->nstlist_fixed = (int)value;
+        if (c->nstlist_fixed > 0) c->nst = c->nstlist_fixed; else c->nst = initial_nst(c);
+    } else if (k == "threads_per_bead") {
+        int t = (int)value;
+        if (!(t == 0 || t == 4 || t == 8 || t == 16 || t == 32)) return fail("threads_per_bead must be 0 (auto), 4, 8, 16 or 32");
+        c->tpb_opt = t;
+        if (c->lists_ready) build_segments(c);
+    } else {
+        return fail("unknown option: " + k);
+    }
+    return 0;
+    OCM_GUARD_END
+}
+int ocm_context_get_option(ocm_context* c, const char* key, double* value) {
+    if (!c || !key || !value) return fail("null argument");
+    std::string k(key);
+    if (k == "skin_nm") *value = c->skin;
+    else if (k == "nstlist") *value = c->nstlist_fixed;
+    else if (k == "threads_per_bead") *value = c->tpb_opt;
+    else return fail("unknown option: " + k);
+    return 0;
+}
+
+int ocm_set_positions(ocm_context* c, const double* xyz) {
+    if (!c || !xyz) return fail("null argument");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(c->x.p, xyz, (size_t)3 * c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    canon_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->P, c->x.p, c->posq.p);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->positions_set = true; c->lists_current = false;
+    return 0;
+    OCM_GUARD_END
+}
+int ocm_set_velocities(ocm_context* c, const double* xyz) {
+    if (!c || !xyz) return fail("null argument");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::vector<float4> v(c->n);
+    for (int i = 0; i < c->n; i++) {
+        double m = c->sys.mass[i];
+        v[i] = make_float4((float)xyz[3 * i], (float)xyz[3 * i + 1], (float)xyz[3 * i + 2], m > 0 ? (float)(1.0 / m) : 0.f);
+    }
+    CUDA_TRY(cudaMemcpy(c->v.p, v.data(), c->n * sizeof(float4), cudaMemcpyHostToDevice));
+    return 0;
+    OCM_GUARD_END
+}
+int ocm_set_velocities_to_temperature(ocm_context* c, double T, uint64_t seed) {
+    if (!c) return fail("null context");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    init_velocity_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->n, (float)(kBoltz * T), (unsigned int)seed, (unsigned int)(seed >> 32), c->v.p);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+    OCM_GUARD_END
+}
+
+int ocm_step(ocm_context* c, int64_t nsteps) {
+    if (!c) return fail("null context");
+    if (nsteps < 0) return fail("step: negative step count");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    do_steps(c, nsteps);
+    return 0;
+    OCM_GUARD_END
+}
+int64_t ocm_current_step(const ocm_context* c) { return c ? c->step : -1; }
+
+int ocm_get_state(ocm_context* c, uint32_t mask, double* pos, double* vel, double* force, double* epot, double* ekin, double* ebg) {
+    if (!c) return fail("null context");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int n = c->n;
+    if (pos) CUDA_TRY(cudaMemcpyAsync(pos, c->x.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    std::vector<float4> hv;
+    if (vel) { hv.resize(n); CUDA_TRY(cudaMemcpyAsync(hv.data(), c->v.p, n * sizeof(float4), cudaMemcpyDeviceToHost, s)); }
+    std::vector<unsigned long long> hf;
+    double he[40];
+    if (force || epot || ekin || ebg) {
+        ensure_lists_current(c);
+        if (force && mask != 0xFFFFFFFFu) {
+            // forces restricted to a group mask: only at the granularity of whole force segments
+            for (auto& L : c->lists) {
+                int in = 0, tot = 0;
+                for (int t : L->terms) { tot++; in += (mask >> c->sys.pairs[t].group) & 1; }
+                if (in != 0 && in != tot) return fail("get_state: the force-group mask splits a fused pair list");
+            }
+            return fail("get_state: forces restricted to a force-group mask are not supported; request all groups");
+        }
+        CUDA_TRY(cudaMemsetAsync(c->egroup.p, 0, 40 * sizeof(double), s));
+        if (epot || ebg) {
+            if (c->total_blocks > 0) {
+                if (c->periodic) energy_kernel<true><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->P, c->posq.p, c->x.p, c->egroup.p);
+                else energy_kernel<false><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->P, c->posq.p, c->x.p, c->egroup.p);
+            }
+        }
+        if (force || ekin) {
+            compute_forces_into_fbuf(c);
+            if (ekin) kinetic_kernel<<<nblk(n, kBlock), kBlock, 0, s>>>(c->P, c->v.p, c->fbuf.p, c->egroup.p + 32);
+            if (force) { hf.resize((size_t)3 * n); CUDA_TRY(cudaMemcpyAsync(hf.data(), c->fbuf.p, hf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s)); }
+            CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, (size_t)3 * n * sizeof(unsigned long long), s));
+        }
+        CUDA_TRY(cudaMemcpyAsync(he, c->egroup.p, 40 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (vel) for (int i = 0; i < n; i++) { vel[3 * i] = hv[i].x; vel[3 * i + 1] = hv[i].y; vel[3 * i + 2] = hv[i].z; }
+    if (force) for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) force[3 * i + k] = (double)(long long)hf[(size_t)k * n + i] / kFixScale;
+    if (epot) { double e = 0; for (int g = 0; g < 32; g++) if (mask >> g & 1) e += he[g]; *epot = e; }
+    if (ebg) std::copy(he, he + 32, ebg);
+    if (ekin) *ekin = he[32];
+    return 0;
+    OCM_GUARD_END
+}
+
+int ocm_num_pair_terms(const ocm_context* c) { return c ? (int)c->sys.pairs.size() : -1; }
+
+int ocm_get_neighbor_pairs(ocm_context* c, int term, int32_t* ij, int64_t capacity, int64_t* n_pairs) {
+    if (!c || !n_pairs) return fail("null argument");
+    if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    ensure_lists_current(c);
+    cudaStream_t s = c->stream;
+    const int li = c->term_list[term];
+    PairListHost& L = *c->lists[li];
+    const double rce = effective_rc(c->sys.pairs[term]);
+    const float rc2 = (float)(rce * rce);
+    DevBuf<int> out;
+    if (ij && capacity > 0) out.alloc((size_t)2 * capacity);
+    CUDA_TRY(cudaMemsetAsync(c->pair_counter.p, 0, sizeof(unsigned long long), s));
+    if (L.np > 0) {
+        if (c->periodic) extract_pairs_kernel<true><<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->P, c->posq.p, rc2, out.p, capacity, c->pair_counter.p);
+        else extract_pairs_kernel<false><<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->P, c->posq.p, rc2, out.p, capacity, c->pair_counter.p);
+    }
+    unsigned long long cnt = 0;
+    CUDA_TRY(cudaMemcpyAsync(&cnt, c->pair_counter.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *n_pairs = (int64_t)cnt;
+    if (ij) {
+        if ((int64_t)cnt > capacity) return fail("get_neighbor_pairs: capacity too small");
+        std::vector<std::pair<int, int>> pr(cnt);
+        std::vector<int> raw((size_t)2 * cnt);
+        if (cnt) CUDA_TRY(cudaMemcpy(raw.data(), out.p, raw.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < cnt; k++) pr[k] = {raw[2 * k], raw[2 * k + 1]};
+        std::sort(pr.begin(), pr.end());
+        for (size_t k = 0; k < cnt; k++) { ij[2 * k] = pr[k].first; ij[2 * k + 1] = pr[k].second; }
+    }
+    return 0;
+    OCM_GUARD_END
+}
+
+int ocm_get_cell_ids(ocm_context* c, int term, int32_t* cell_of_bead, int32_t dims[3]) {
+    if (!c || !cell_of_bead || !dims) return fail("null argument");
+    if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    ensure_lists_current(c);
+    PairListHost& L = *c->lists[c->term_list[term]];
+    std::vector<int> cs(std::max(L.np, 1));
+    GridDev g;
+    CUDA_TRY(cudaMemcpy(cs.data(), L.cell_of_slot.p, cs.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&g, L.grid.p, sizeof(g), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < c->n; i++) cell_of_bead[i] = -1;
+    const auto& part = c->sys.pairs[L.terms[0]].part;
+    for (int a = 0; a < L.np; a++) cell_of_bead[part[a]] = cs[a];
+    for (int k = 0; k < 3; k++) dims[k] = g.nc[k];
+    return 0;
+    OCM_GUARD_END
+}
+
+int ocm_get_counter(ocm_context* c, const char* key, double* value) {
+    if (!c || !key || !value) return fail("null argument");
+    OCM_GUARD_BEGIN
+    std::string k(key);
+    if (k == "rebuilds") *value = c->n_rebuilds;
+    else if (k == "rollbacks") *value = c->n_rollbacks;
+    else if (k == "kernel_launches") *value = c->n_launches;
+    else if (k == "nstlist") *value = c->nst;
+    else if (k == "last_step_ms") *value = c->last_step_ms;
+    else if (k == "num_pair_lists") *value = (double)c->lists.size();
+    else if (k == "max_neighbors") { int m = 0; for (auto& L : c->lists) m = std::max(m, L->stride); *value = m; }
+    else if (k == "pair_evals_per_step") {
+        CUDA_TRY(cudaSetDevice(c->device));
+        ensure_lists_current(c);
+        double tot = 0;
+        for (auto& L : c->lists) {
+            if (!L->np) continue;
+            std::vector<int> cnt(L->np);
+            CUDA_TRY(cudaMemcpy(cnt.data(), L->nbr_count.p, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            for (int v : cnt) tot += v;
+        }
+        *value = tot;
+    } else if (k.rfind("list_cutoff_nm.", 0) == 0) {
+        int term = std::atoi(k.c_str() + 15);
+        if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");
+        *value = c->lists[c->term_list[term]]->rc_list + c->skin;
+    } else if (k.rfind("threads_per_bead.", 0) == 0) {
+        int term = std::atoi(k.c_str() + 17);
+        if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");
+        *value = c->lists[c->term_list[term]]->tpb;
+    } else return fail("unknown counter: " + k);
+    return 0;
+    OCM_GUARD_END
+}
+
+int ocm_profile_kernel(ocm_context* c, const char* which, int reps, double* avg_ms) {
+    if (!c || !which || !avg_ms || reps <= 0) return fail("profile_kernel: bad arguments");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    ensure_lists_current(c);
+    cudaStream_t s = c->stream;
+    std::string w(which);
+    const size_t fb = (size_t)3 * c->n * sizeof(unsigned long long);
+    double launches = c->n_launches, rebuilds = c->n_rebuilds;
+    auto run = [&](int count) {
+        for (int r = 0; r < count; r++) {
+            if (w == "force") enqueue_forces(c, s);
+            else if (w == "rebuild") enqueue_rebuild(c, s, false);
+            else if (w == "integrate") {
+                // dt = 0 copy of the parameters would change the physics; instead integrate a scratch copy
+                integrate_kernel<<<nblk(c->n, 128), 128, 0, s>>>(c->P, c->xbak.p, c->vbak.p, c->fbuf.p, c->posq.p, c->xref.p,
+                                                                 c->step_base.p, 0, 1, 0, c->flags.p);
+            } else throw std::runtime_error("profile_kernel: unknown kernel " + w);
+        }
+    };
+    if (w == "integrate") {
+        CUDA_TRY(cudaMemcpyAsync(c->xbak.p, c->x.p, (size_t)3 * c->n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(c->vbak.p, c->v.p, (size_t)c->n * sizeof(float4), cudaMemcpyDeviceToDevice, s));
+    }
+    run(3);
+    CUDA_TRY(cudaEventRecord(c->ev0, s));
+    run(reps);
+    CUDA_TRY(cudaEventRecord(c->ev1, s));
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *avg_ms = ms / reps;
+    // leave the state as it was: clear the accumulator and flags, restore the pair-kernel positions
+    CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, fb, s));
+    CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, FLAG_COUNT * sizeof(int), s));
+    canon_kernel<<<nblk(c->n, 256), 256, 0, s>>>(c->P, c->x.p, c->posq.p);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    c->n_launches = launches; c->n_rebuilds = rebuilds;
+    c->lists_current = false;
+    return 0;
+    OCM_GUARD_END
+}
+
+int ocm_measure_fp32_peak(int device, double* tflops) {
+    if (!tflops) return fail("null argument");
+    OCM_GUARD_BEGIN
+    int ndev = ocm_device_count();
+    if (device < 0 || device >= ndev) return fail("measure_fp32_peak: device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    DevBuf<float> out;
+    out.alloc((size_t)blocks * threads);
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        fma_peak_kernel<<<blocks, threads>>>(out.p, iters, 0.999f, 1e-3f);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double flop = (double)blocks * threads * iters * 16.0 * 8.0 * 2.0;
+        if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = best;
+    return 0;
+    OCM_GUARD_END
+}
+
+}  // extern "C"

@@ -632,3 +632,53 @@ def make_context(lib: Library, spec: SystemSpec, device=0, seed=None) -> Context
         ctx.set_velocities_to_temperature(spec.temperature, spec.vel_seed)
     ctx.group_ids = dict(spec.group_ids)
     return ctx
+
+
+# ------------------------------------------------------------------------------------------------
+# SystemSpec <-> plain dict (JSON-able): golden fixtures travel to machines without the reference tree
+def spec_to_dict(spec: SystemSpec) -> dict:
+    def conv(v):
+        if isinstance(v, PairTopology):
+            return {"__topo__": True, "excl": np.asarray(v.excl).tolist(),
+                    "igroups": [[list(map(int, a)), list(map(int, b))] for a, b in v.igroups], "periodic": bool(v.periodic)}
+        if isinstance(v, np.ndarray):
+            return {"__nd__": True, "v": [None if (isinstance(x, float) and math.isnan(x)) else x for x in v.reshape(-1).tolist()],
+                    "shape": list(v.shape)}
+        if isinstance(v, (list, tuple)):
+            return [conv(x) for x in v]
+        if isinstance(v, (np.floating, np.integer)):
+            return v.item()
+        return v
+
+    return {
+        "mass": spec.mass.tolist(), "box": None if spec.box is None else spec.box.tolist(),
+        "positions": spec.positions.tolist(), "velocities": None if spec.velocities is None else spec.velocities.tolist(),
+        "names": spec.names, "groups": spec.groups, "group_ids": spec.group_ids,
+        "temperature": spec.temperature, "friction": spec.friction, "dt": spec.dt, "seed": spec.seed,
+        "vel_seed": spec.vel_seed, "total_step": spec.total_step, "save_step": spec.save_step,
+        "delta_t_raw": spec.delta_t_raw, "energy_minimization": spec.energy_minimization, "periodic": spec.periodic,
+        "terms": [{"kind": t.kind, "name": t.name, "group": t.group, "args": {k: conv(v) for k, v in t.args.items()}}
+                  for t in spec.terms],
+    }
+
+
+def spec_from_dict(d: dict) -> SystemSpec:
+    def conv(v):
+        if isinstance(v, dict) and v.get("__topo__"):
+            return PairTopology(excl=np.array(v["excl"], np.int32).reshape(-1, 2),
+                                igroups=[(a, b) for a, b in v["igroups"]], periodic=v["periodic"])
+        if isinstance(v, dict) and v.get("__nd__"):
+            return np.array([np.nan if x is None else x for x in v["v"]], float).reshape(v["shape"])
+        return v
+
+    spec = SystemSpec(mass=np.array(d["mass"], float), box=None if d["box"] is None else np.array(d["box"], float),
+                      positions=np.array(d["positions"], float),
+                      velocities=None if d["velocities"] is None else np.array(d["velocities"], float),
+                      names=d["names"], groups=d["groups"])
+    for k in ("temperature", "friction", "dt", "seed", "vel_seed", "total_step", "save_step", "delta_t_raw",
+              "energy_minimization", "periodic"):
+        setattr(spec, k, d[k])
+    spec.group_ids = dict(d["group_ids"])
+    for t in d["terms"]:
+        spec.terms.append(Term(t["kind"], t["name"], {k: conv(v) for k, v in t["args"].items()}, t["group"]))
+    return spec

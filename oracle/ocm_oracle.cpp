@@ -911,17 +911,15 @@ int oracle_get_neighbor_pairs(ocm_context* c, int term, int32_t* ij, int64_t cap
 
 // Canonical cell assignment, shared bit-exactly with the engine: the grid is derived from the
 // term's list cutoff (effective rc + skin); see DESIGN.md "cell grid".
-static double g_skin = 0.3;
-int oracle_set_skin(double skin) { g_skin = skin; return 0; }
-
-int oracle_get_cell_ids(ocm_context* c, int term, int32_t* cell_of_bead, int32_t dims[3]) {
+// rlist = list cutoff (interaction cutoff of the list serving the term + skin), reported by the engine
+// through ocm_get_counter("list_cutoff_nm.<term>").
+int oracle_get_cell_ids_rlist(ocm_context* c, int term, double rlist, int32_t* cell_of_bead, int32_t dims[3]) {
     if (!c || !cell_of_bead || !dims) return fail("null argument");
     if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");
     const PairTerm& t = c->sys.pairs[term];
     Canon q = canonicalise(*c);
     int n = c->sys.n;
-    float rl = (float)(effective_rc(t) + g_skin);
-    float wmin = rl * 0.5f;
+    float wmin = 0.5f * (float)rlist;
     for (int i = 0; i < n; i++) cell_of_bead[i] = -1;
     if (q.periodic) {
         int nc[3];
@@ -963,6 +961,15 @@ int oracle_get_cell_ids(ocm_context* c, int term, int32_t* cell_of_bead, int32_t
     return 0;
 }
 
+int oracle_get_cell_ids(ocm_context* c, int term, int32_t* cell_of_bead, int32_t dims[3]) {
+    if (!c) return fail("null argument");
+    if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");
+    return oracle_get_cell_ids_rlist(c, term, effective_rc(c->sys.pairs[term]) + 0.3, cell_of_bead, dims);
+}
+
 int oracle_get_counter(ocm_context*, const char*, double* v) { if (v) *v = 0; return 0; }
+
+int oracle_profile_kernel(ocm_context*, const char*, int, double* v) { if (v) *v = 0; return fail("the oracle has no kernels"); }
+int oracle_measure_fp32_peak(int, double* v) { if (v) *v = 0; return fail("the oracle has no device"); }
 
 }  // extern "C"

@@ -1,0 +1,253 @@
+"""Parity of the CUDA engine (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): neighbour pairs and cell assignment bit-exact as integer sets;
+per-particle forces and per-term energies within 1e-5 relative (FP32 pair arithmetic against the
+double-precision oracle; bonded terms are evaluated in double on the device)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden_spec, load_golden_values
+from opencafemol_b200 import synth, toml_input as ti
+from opencafemol_b200.capi import Context, PairTopology, System
+
+pytestmark = pytest.mark.gpu
+FORCE_TOL = 1e-5
+ENERGY_TOL = 1e-5
+
+
+def force_error(f, fref):
+    """norm-relative per-particle error with the rms force as floor."""
+    frms = np.sqrt((fref ** 2).sum(1).mean())
+    return np.linalg.norm(f - fref, axis=1) / np.maximum(np.linalg.norm(fref, axis=1), frms)
+
+
+def check_state(ctx, ora, spec, ftol=FORCE_TOL, etol=ENERGY_TOL):
+    a = ctx.get_state(forces=True, energy=True)
+    b = ora.get_state(forces=True, energy=True)
+    err = force_error(a["forces"], b["forces"])
+    assert err.max() < ftol, f"force error {err.max():.3e}"
+    escale = max(np.abs(b["energy_by_group"]).max(), 1.0)
+    for name, g in spec.group_ids.items():
+        ea, eb = a["energy_by_group"][g], b["energy_by_group"][g]
+        assert abs(ea - eb) <= etol * max(abs(eb), 1e-3 * escale), (name, ea, eb)
+    assert a["kinetic_energy"] == pytest.approx(b["kinetic_energy"], rel=1e-5)
+    return a, b
+
+
+def check_sets(ctx, ora):
+    for t in range(ctx.num_pair_terms()):
+        pa, pb = ctx.neighbor_pairs(t), ora.neighbor_pairs(t)
+        assert pa.shape == pb.shape and np.array_equal(pa, pb), f"pair set of term {t} differs"
+
+
+def test_sh3_golden(engine, oracle):
+    spec = load_golden_spec("sh3")
+    gold = load_golden_values("sh3")
+    ctx, ora = ti.make_context(engine, spec), ti.make_context(oracle, spec)
+    a, _ = check_state(ctx, ora, spec)
+    check_sets(ctx, ora)
+    for k, gid in spec.group_ids.items():
+        ref = gold["energy_by_group_kj"][k]
+        assert abs(a["energy_by_group"][gid] - ref) <= ENERGY_TOL * max(abs(ref), 0.1)
+    assert force_error(a["forces"], np.array(gold["forces"])).max() < FORCE_TOL
+    for t in range(ctx.num_pair_terms()):
+        assert ctx.neighbor_pairs(t).tolist() == gold["pairs"][str(t)]
+
+
+@pytest.mark.parametrize("n_chains", [3, 12])
+def test_hps_slab_small(engine, oracle, n_chains):
+    spec = synth.hps_slab(n_chains=n_chains)
+    ctx, ora = ti.make_context(engine, spec), ti.make_context(oracle, spec)
+    check_state(ctx, ora, spec)
+    check_sets(ctx, ora)
+
+
+def test_hps_c2_full_size(engine, oracle):
+    """BASELINE config C2 (16 300 beads): forces, energies, and the 2.5 M-pair set bit-exact."""
+    spec = synth.hps_slab(n_chains=100)
+    ctx, ora = ti.make_context(engine, spec), ti.make_context(oracle, spec)
+    check_state(ctx, ora, spec)
+    check_sets(ctx, ora)
+    # Newton's third law on the fixed-point accumulator: total force is zero to rounding
+    f = ctx.get_state(forces=True)["forces"]
+    assert np.abs(f.sum(0)).max() < 1e-3 * np.abs(f).max()
+
+
+def test_cell_assignment_bit_exact(engine, oracle):
+    import ctypes as C
+    for spec in (synth.hps_slab(n_chains=12), load_golden_spec("sh3")):
+        ctx, ora = ti.make_context(engine, spec), ti.make_context(oracle, spec)
+        for t in range(ctx.num_pair_terms()):
+            rlist = ctx.counter(f"list_cutoff_nm.{t}")
+            ids, dims = ctx.cell_ids(t)
+            oid = np.zeros(spec.mass.size, np.int32)
+            od = np.zeros(3, np.int32)
+            fn = oracle.dll.oracle_get_cell_ids_rlist
+            fn.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+            assert fn(ora.handle, t, rlist, oid.ctypes.data_as(C.POINTER(C.c_int32)), od.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+            assert np.array_equal(dims, od), (dims, od)
+            assert np.array_equal(ids, oid)
+
+
+def test_positions_across_periodic_boundary(engine, oracle):
+    """Unwrapped coordinates many box lengths away give the same forces (fixed-point box fractions)."""
+    spec = synth.hps_slab(n_chains=6)
+    rng = np.random.default_rng(3)
+    shift = rng.integers(-3, 4, size=(spec.mass.size, 3)) * spec.box
+    chain = np.repeat(np.arange(6), 163)
+    spec.positions = spec.positions + shift[chain * 163]  # whole chains moved by lattice vectors
+    ctx, ora = ti.make_context(engine, spec), ti.make_context(oracle, spec)
+    check_state(ctx, ora, spec)
+    check_sets(ctx, ora)
+
+
+def test_trajectory_tracks_oracle(engine, oracle):
+    """Same Philox noise on both sides: a short Langevin trajectory stays together."""
+    spec = synth.hps_slab(n_chains=3)
+    ctx, ora = ti.make_context(engine, spec), ti.make_context(oracle, spec)
+    ctx.step(25); ora.step(25)
+    a = ctx.get_state(positions=True, velocities=True)
+    b = ora.get_state(positions=True, velocities=True)
+    assert np.abs(a["positions"] - b["positions"]).max() < 2e-5
+    assert np.abs(a["velocities"] - b["velocities"]).max() < 2e-3
+    assert ctx.current_step == 25
+
+
+def test_sh3_trajectory_and_split_steps(engine, oracle):
+    spec = load_golden_spec("sh3")
+    ctx, ora = ti.make_context(engine, spec), ti.make_context(oracle, spec)
+    ctx.step(7); ctx.step(13); ora.step(20)
+    a = ctx.get_state(positions=True); b = ora.get_state(positions=True)
+    assert np.abs(a["positions"] - b["positions"]).max() < 2e-5
+    check_state(ctx, ora, spec, ftol=5e-3, etol=5e-3)  # states differ by the accumulated FP32 drift
+
+
+def test_velocity_initialisation(engine, oracle):
+    spec = synth.hps_slab(n_chains=3)
+    ctx, ora = ti.make_context(engine, spec), ti.make_context(oracle, spec)
+    ctx.set_velocities_to_temperature(300.0, 99); ora.set_velocities_to_temperature(300.0, 99)
+    va = ctx.get_state(velocities=True)["velocities"]; vb = ora.get_state(velocities=True)["velocities"]
+    assert np.abs(va - vb).max() < 1e-5
+    kT = 8.31446261815324e-3 * 300
+    assert (spec.mass[:, None] * vb ** 2).mean() == pytest.approx(kT, rel=0.1)
+
+
+def test_nve_limit_energy_conservation(engine):
+    """gamma = 0 turns the Langevin step into leap-frog: total energy is conserved (drift matched to the
+    integrator's O(dt^2) fluctuation, no secular loss through the Verlet buffer or rollbacks)."""
+    spec = synth.hps_slab(n_chains=12)
+    spec.friction = 0.0
+    ctx = ti.make_context(engine, spec)
+    ctx.step(200)
+    e = []
+    for _ in range(10):
+        ctx.step(100)
+        st = ctx.get_state(energy=True)
+        e.append(st["potential_energy"] + st["kinetic_energy"])
+    e = np.array(e)
+    ke = st["kinetic_energy"]
+    assert np.abs(e - e.mean()).max() < 5e-3 * ke
+    assert abs(e[-1] - e[0]) < 5e-3 * ke
+
+
+def test_rebuild_interval_independence(engine):
+    """Forced list rebuild cadence changes only the FP32 summation order."""
+    spec = synth.hps_slab(n_chains=6)
+    out = []
+    for nst in (1, 5, 0):
+        ctx = ti.make_context(engine, spec)
+        ctx.set_option("nstlist", nst)
+        ctx.step(60)
+        out.append(ctx.get_state(positions=True)["positions"])
+    assert np.abs(out[0] - out[1]).max() < 1e-4
+    assert np.abs(out[0] - out[2]).max() < 1e-4
+
+
+def test_run_to_run_determinism(engine):
+    spec = synth.hps_slab(n_chains=6)
+    res = []
+    for _ in range(2):
+        ctx = ti.make_context(engine, spec)
+        ctx.set_option("nstlist", 10)
+        ctx.step(100)
+        res.append(ctx.get_state(positions=True, velocities=True))
+    assert np.array_equal(res[0]["positions"], res[1]["positions"])
+    assert np.array_equal(res[0]["velocities"], res[1]["velocities"])
+
+
+def test_equipartition_long_langevin(engine):
+    spec = synth.hps_slab(n_chains=12)
+    ctx = ti.make_context(engine, spec)
+    ctx.step(3000)
+    kes = []
+    for _ in range(10):
+        ctx.step(200)
+        kes.append(ctx.get_state(energy=True)["kinetic_energy"])
+    kT = 8.31446261815324e-3 * spec.temperature
+    assert np.mean(kes) == pytest.approx(1.5 * spec.mass.size * kT, rel=0.03)
+
+
+def test_options_and_counters(engine):
+    spec = synth.hps_slab(n_chains=3)
+    ctx = ti.make_context(engine, spec)
+    ctx.set_option("skin_nm", 0.25)
+    assert ctx.get_option("skin_nm") == pytest.approx(0.25)
+    for tpb in (4, 8, 16, 32):
+        ctx.set_option("threads_per_bead", tpb)
+        f = ctx.get_state(forces=True)["forces"]
+        if tpb == 4:
+            f0 = f
+        assert np.abs(f - f0).max() < 1e-3
+    ctx.step(30)
+    assert ctx.counter("kernel_launches") > 60
+    assert ctx.counter("rebuilds") >= 1
+    assert ctx.counter("pair_evals_per_step") > 0
+    assert ctx.counter("num_pair_lists") == 2  # LJ-rep + LJ-att fused into one Ashbaugh-Hatch list, + DH
+    with pytest.raises(Exception):
+        ctx.set_option("no_such_option", 1)
+
+
+def test_every_bonded_kind_and_interaction_groups(engine, oracle):
+    """Random small system exercising all nine bonded kinds, EXV with interaction groups, 3SPN.2 EXV."""
+    from opencafemol_b200 import tables
+    rng = np.random.default_rng(5)
+    n = 40
+    pos = np.zeros((n, 3))
+    for i in range(1, n):
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        pos[i] = pos[i - 1] + 0.45 * d
+    ij = np.array([[i, i + 1] for i in range(n - 1)])
+    ijk = np.array([[i, i + 1, i + 2] for i in range(n - 2)])
+    ijkl = np.array([[i, i + 1, i + 2, i + 3] for i in range(n - 3)])
+    m2, m3, m4 = len(ij), len(ijk), len(ijkl)
+    radius = rng.uniform(0.15, 0.25, n)
+    radius[::7] = np.nan
+    has = ~np.isnan(radius)
+    grp = ["A" if i < 20 else "B" for i in range(n)]
+    ig = ti.extract_interaction_group(has, [("A", "A")], grp)
+    excl = np.array([[i, i + d] for d in (1, 2) for i in range(n - d)])
+    ctxs = []
+    for lib in (engine, oracle):
+        s = System(lib, rng.uniform(50, 150, n) * 0 + 100.0)
+        s.add_harmonic_bond(0, ij, np.full(m2, 0.45), np.full(m2, 5000.0))
+        s.add_gaussian_bond(1, ijk[:, [0, 2]], -np.full(m3, 2.0), np.full(m3, 0.7), np.full(m3, 0.1))
+        s.add_go_contact(2, ijkl[:, [0, 3]], np.full(m4, 1.3), np.full(m4, 0.9))
+        s.add_3spn2_bond(3, ij, np.full(m2, 200.0), np.full(m2, 2e4), np.full(m2, 0.45))
+        s.add_harmonic_angle(4, ijk, np.full(m3, 2.0), np.full(m3, 40.0))
+        s.add_flexible_local_angle(5, ijk, np.full(m3, 4.184), tables.FLA_SPLINE["GLY"], tables.FLA_MIN_THETA,
+                                   tables.FLA_MAX_THETA, 0.5)
+        s.add_gaussian_dihedral(6, ijkl, -np.full(m4, 1.8), np.linspace(-3, 3, m4), np.full(m4, 0.3))
+        s.add_cosine_dihedral(7, ijkl, np.full(m4, 2.0), np.linspace(-3, 3, m4), (np.arange(m4) % 3 + 1).astype(np.int32))
+        s.add_flexible_local_dihedral(8, ijkl, np.full(m4, 4.184), tables.FLD_FOURIER[("ALA", "R3")], 1.2)
+        s.add_excluded_volume(9, 2.5, 0.9, radius, PairTopology(excl=excl, igroups=ig))
+        s.add_3spn2_excluded_volume(10, 1.4, np.full(n, 1.0), rng.uniform(0.45, 0.7, n) * 0 + np.linspace(0.45, 0.7, n),
+                                    PairTopology(excl=excl))
+        c = Context(s, 300.0, 0.2, 0.002, seed=11)
+        c.set_positions(pos)
+        ctxs.append(c)
+    ctx, ora = ctxs
+
+    class Spec:
+        group_ids = {str(g): g for g in range(11)}
+    check_state(ctx, ora, Spec)
+    check_sets(ctx, ora)

@@ -1,0 +1,182 @@
+"""Pins the CPU oracle: closed-form known answers of the reference's own SH3 sample (SURVEY.md
+Appendix D), the committed golden fixture, finite differences F = -dE/dx for every term kind, and the
+cell-list / brute-force agreement.  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import load_golden_spec, load_golden_values
+from opencafemol_b200 import synth, toml_input as ti
+from opencafemol_b200.capi import Context, PairTopology, System
+
+KCAL = 4.184
+
+
+def test_sh3_known_answers(oracle):
+    spec = load_golden_spec("sh3")
+    ctx = ti.make_context(oracle, spec)
+    e = ctx.get_state(energy=True)["energy_by_group"]
+    g = spec.group_ids
+    # sample is at its parameter minima: sum of k's (kcal/mol)
+    assert abs(e[g["GoContact"]] / KCAL - (-112.5303)) < 1e-6
+    assert abs(e[g["GaussianBond"]] / KCAL - (-140.674)) < 1e-5
+    assert abs(e[g["GaussianDihedral"]] / KCAL - (-40.7812)) < 1e-5  # pins the dihedral sign convention
+    assert abs(e[g["HarmonicBond"]] / KCAL) < 1e-8
+
+
+def test_sh3_matches_golden(oracle):
+    spec = load_golden_spec("sh3")
+    gold = load_golden_values("sh3")
+    ctx = ti.make_context(oracle, spec)
+    st = ctx.get_state(forces=True, energy=True)
+    for k, gid in spec.group_ids.items():
+        assert st["energy_by_group"][gid] == pytest.approx(gold["energy_by_group_kj"][k], rel=1e-10, abs=1e-10)
+    assert np.allclose(st["forces"], np.array(gold["forces"]), atol=1e-7)
+    assert st["kinetic_energy"] == pytest.approx(gold["kinetic_energy_kj"], rel=1e-10)
+    for t in range(ctx.num_pair_terms()):
+        assert ctx.neighbor_pairs(t).tolist() == gold["pairs"][str(t)]
+
+
+def test_sh3_exclusion_counts():
+    spec = load_golden_spec("sh3")
+    exv = [t for t in spec.terms if t.kind == "excluded_volume"][0]
+    # bond<=3 (162 pairs) U contact<=1 (215 pairs), disjoint
+    assert len(exv.args["topo"].excl) == 377
+    assert exv.args["rc"] == pytest.approx((0.2348 + 0.2265) * 2.0, abs=1e-9)
+
+
+def _fd_check(lib, build, n, box=None, seed=0, h=1e-6, tol=2e-6):
+    rng = np.random.default_rng(seed)
+    sysm = System(lib, np.full(n, 50.0), box)
+    pos = build(sysm, rng)
+    ctx = Context(sysm, 300.0, 0.2, 0.001, 1)
+    ctx.set_positions(pos)
+    f = ctx.get_state(forces=True)["forces"]
+    fd = np.zeros_like(f)
+    for i in range(n):
+        for k in range(3):
+            p = pos.copy(); p[i, k] += h; ctx.set_positions(p)
+            ep = ctx.get_state(energy=True)["potential_energy"]
+            p[i, k] -= 2 * h; ctx.set_positions(p)
+            em = ctx.get_state(energy=True)["potential_energy"]
+            fd[i, k] = -(ep - em) / (2 * h)
+    scale = max(np.abs(f).max(), 1.0)
+    assert np.abs(f - fd).max() / scale < tol, (np.abs(f - fd).max(), scale)
+
+
+def _chain(n, rng, bond=0.38):
+    p = np.zeros((n, 3))
+    for i in range(1, n):
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        p[i] = p[i - 1] + bond * d
+    return p + 3.0
+
+
+BONDED = ["harmonic_bond", "gaussian_bond", "go_contact", "3spn2_bond", "harmonic_angle", "flexible_local_angle",
+          "gaussian_dihedral", "cosine_dihedral", "flexible_local_dihedral"]
+
+
+@pytest.mark.parametrize("kind", BONDED)
+@pytest.mark.parametrize("periodic", [False, True])
+def test_bonded_finite_difference(oracle, kind, periodic):
+    from opencafemol_b200 import tables
+    n = 6
+    box = np.array([2.5, 2.2, 2.0]) if periodic else None  # smaller than the chain: bonds cross the boundary
+
+    def build(s, rng):
+        ij = np.array([[i, i + 1] for i in range(n - 1)])
+        ijk = np.array([[i, i + 1, i + 2] for i in range(n - 2)])
+        ijkl = np.array([[i, i + 1, i + 2, i + 3] for i in range(n - 3)])
+        m2, m3, m4 = len(ij), len(ijk), len(ijkl)
+        if kind == "harmonic_bond":
+            s.add_harmonic_bond(0, ij, rng.uniform(0.3, 0.4, m2), rng.uniform(100, 1000, m2), periodic)
+        elif kind == "gaussian_bond":
+            s.add_gaussian_bond(0, ij, -rng.uniform(1, 5, m2), rng.uniform(0.3, 0.5, m2), rng.uniform(0.05, 0.2, m2), periodic)
+        elif kind == "go_contact":
+            s.add_go_contact(0, ij, rng.uniform(0.5, 2, m2), rng.uniform(0.3, 0.45, m2), periodic)
+        elif kind == "3spn2_bond":
+            s.add_3spn2_bond(0, ij, rng.uniform(100, 300, m2), rng.uniform(1e4, 3e4, m2), rng.uniform(0.3, 0.45, m2), periodic)
+        elif kind == "harmonic_angle":
+            s.add_harmonic_angle(0, ijk, rng.uniform(1.5, 2.5, m3), rng.uniform(10, 100, m3), periodic)
+        elif kind == "flexible_local_angle":
+            s.add_flexible_local_angle(0, ijk, rng.uniform(2, 5, m3), tables.FLA_SPLINE["PRO"], tables.FLA_MIN_THETA,
+                                       tables.FLA_MAX_THETA, 0.6, periodic)
+        elif kind == "gaussian_dihedral":
+            s.add_gaussian_dihedral(0, ijkl, -rng.uniform(1, 3, m4), rng.uniform(-3, 3, m4), rng.uniform(0.15, 0.6, m4), periodic)
+        elif kind == "cosine_dihedral":
+            s.add_cosine_dihedral(0, ijkl, rng.uniform(1, 3, m4), rng.uniform(-3, 3, m4), rng.integers(1, 4, m4), periodic)
+        else:
+            s.add_flexible_local_dihedral(0, ijkl, rng.uniform(2, 5, m4), tables.FLD_FOURIER[("GLY", "PRO")], 1.0, periodic)
+        return _chain(n, rng)
+
+    _fd_check(oracle, build, n, box, seed=BONDED.index(kind))
+
+
+PAIRS = ["excluded_volume", "debye_huckel", "lj_repulsive", "lj_attractive", "3spn2_excluded_volume"]
+
+
+@pytest.mark.parametrize("kind", PAIRS)
+@pytest.mark.parametrize("periodic", [False, True])
+def test_pair_finite_difference(oracle, kind, periodic):
+    n = 24
+    box = np.array([2.6, 2.4, 2.8]) if periodic else None
+
+    def build(s, rng):
+        topo = PairTopology(excl=np.array([[0, 1], [2, 5]]), periodic=periodic)
+        if kind == "excluded_volume":
+            s.add_excluded_volume(0, 2.5, 1.0, rng.uniform(0.15, 0.25, n), topo)
+        elif kind == "debye_huckel":
+            s.add_debye_huckel(0, 1.83, 0.3, 1.1, np.exp(-1.1 / 0.3) / 1.1, rng.choice([-1.0, 1.0, 0.5], n), topo)
+        elif kind == "lj_repulsive":
+            s.add_lj_repulsive(0, 1.2, rng.uniform(0.5, 1.0, n), rng.uniform(0.4, 0.6, n), topo)
+        elif kind == "lj_attractive":
+            s.add_lj_attractive(0, 1.2, 1.08, rng.uniform(0.5, 1.0, n), rng.uniform(0.4, 0.6, n), topo)
+        else:
+            s.add_3spn2_excluded_volume(0, 1.2, rng.uniform(0.8, 1.2, n), rng.uniform(0.4, 0.7, n), topo)
+        # jittered lattice: no overlaps, many pairs in every zone
+        g = np.stack(np.meshgrid(np.arange(2), np.arange(3), np.arange(4), indexing="ij"), -1).reshape(-1, 3)
+        return g * 0.62 + rng.uniform(-0.06, 0.06, (n, 3)) + 0.3
+
+    _fd_check(oracle, build, n, box, seed=10 + PAIRS.index(kind), tol=5e-6)
+
+
+def test_cell_list_matches_brute_force(oracle):
+    spec = synth.hps_slab(n_chains=14)  # > 1500 beads: cell-list path
+    ctx = ti.make_context(oracle, spec)
+    a = ctx.get_state(forces=True, energy=True)
+    ctx.set_option("brute_force", 1)
+    b = ctx.get_state(forces=True, energy=True)
+    assert np.abs(a["forces"] - b["forces"]).max() < 1e-8
+    assert np.allclose(a["energy_by_group"], b["energy_by_group"], rtol=1e-11, atol=1e-9)
+    ctx.set_option("brute_force", 0)
+    p1 = ctx.neighbor_pairs(1)
+    ctx.set_option("brute_force", 1)
+    assert np.array_equal(p1, ctx.neighbor_pairs(1))
+
+
+def test_interaction_groups_and_errors(oracle):
+    n = 8
+    s = System(oracle, np.full(n, 10.0))
+    q = np.array([1.0, np.nan, -1.0, np.nan, 1.0, np.nan, np.nan, -1.0])
+    charged = [0, 2, 4, 7]
+    s.add_debye_huckel(0, 1.8, 0.9, 5.0, 0.0, q, PairTopology(igroups=[(charged, charged)]))
+    ctx = Context(s, 300, 0.2, 0.001)
+    ctx.set_positions(np.arange(3 * n).reshape(n, 3) * 0.1)
+    pairs = ctx.neighbor_pairs(0)
+    assert sorted(map(tuple, pairs.tolist())) == [(a, b) for i, a in enumerate(charged) for b in charged[i + 1:]]
+    # NaN parameter without an interaction group is an error
+    s2 = System(oracle, np.full(n, 10.0))
+    with pytest.raises(Exception):
+        s2.add_debye_huckel(0, 1.8, 0.9, 5.0, 0.0, q, PairTopology())
+
+
+def test_langevin_equipartition(oracle):
+    """Free particles under the Langevin step reach kT per degree of freedom (B.1 coefficients)."""
+    n = 2000
+    s = System(oracle, np.full(n, 80.0))
+    s.add_harmonic_bond(0, np.zeros((0, 2), np.int32), [], [])
+    ctx = Context(s, 300.0, 5.0, 0.05, seed=7)
+    ctx.set_positions(np.zeros((n, 3)))
+    ctx.step(60)
+    v = ctx.get_state(velocities=True)["velocities"]
+    kT = 8.31446261815324e-3 * 300
+    assert (80.0 * (v ** 2).mean()) == pytest.approx(kT, rel=0.05)

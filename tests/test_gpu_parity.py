@@ -212,10 +212,16 @@ def test_every_bonded_kind_and_interaction_groups(engine, oracle):
     from opencafemol_b200 import tables
     rng = np.random.default_rng(5)
     n = 40
+    # self-avoiding walk: no unphysical overlaps (forces stay inside the fixed-point accumulator's
+    # +-2^31 kJ/mol/nm range, the same limit OpenMM's CUDA platform has)
     pos = np.zeros((n, 3))
-    for i in range(1, n):
+    i = 1
+    while i < n:
         d = rng.normal(size=3); d /= np.linalg.norm(d)
-        pos[i] = pos[i - 1] + 0.45 * d
+        cand = pos[i - 1] + 0.45 * d
+        if i < 2 or np.linalg.norm(pos[:i - 1] - cand, axis=1).min() > 0.5:
+            pos[i] = cand
+            i += 1
     ij = np.array([[i, i + 1] for i in range(n - 1)])
     ijk = np.array([[i, i + 1, i + 2] for i in range(n - 2)])
     ijkl = np.array([[i, i + 1, i + 2, i + 3] for i in range(n - 3)])

@@ -100,6 +100,61 @@ int ocm_system_add_flexible_local_dihedral(ocm_system*, int group, int periodic,
                                            const int32_t* ijkl, const double* k,
                                            const double* coef7, double e_min);
 
+/* 3SPN.2 base stacking on (p1 = sugar 5', p2 = base 5', p3 = base 3'):
+ *   E = rep + f(K_BS (angle(p1,p2,p3) - theta0)) attr,  dr = |p2-p3| - r0,
+ *   rep = eps (1-exp(-alpha dr))^2 [dr <= 0],  attr = eps (1-exp(-alpha dr))^2 [dr >= 0] - eps,
+ *   f(x) = 1 (|x| <= pi/2), sin^2 x (|x| <= pi), 0 otherwise
+ *                                         ThreeSPN2BaseStackingForceFieldGenerator.cpp:3-50 */
+int ocm_system_add_3spn2_base_stacking(ocm_system*, int group, int periodic, int64_t n,
+                                       const int32_t* ijk, const double* eps, const double* r0,
+                                       const double* theta0, double alpha, double K_BS);
+
+/* ---- donor x acceptor terms ("CustomHbondForce"-like) ------------------------
+ * donors: 3 bead indices (d1,d2,d3) per donor, acceptors: 3 (a1,a2,a3) per acceptor, -1 = unused.
+ * Every donor x acceptor combination is evaluated iff it is not excluded and |d1 - a1| < cutoff
+ * (no switching; the energy is discontinuous at the cutoff, as in OpenMM).  Exclusions are
+ * (donor index, acceptor index) pairs, as CustomHbondForce::addExclusion takes them. */
+typedef struct ocm_da_topology {
+    int64_t        n_donors;
+    const int32_t* donors;      /* 3*n_donors    */
+    int64_t        n_acceptors;
+    const int32_t* acceptors;   /* 3*n_acceptors */
+    int64_t        n_excl;
+    const int32_t* excl_da;     /* 2*n_excl: donor index, acceptor index */
+    double         cutoff;      /* nm */
+    int32_t        periodic;
+} ocm_da_topology;
+
+/* 3SPN.2 base pairing, donor (d1 = base, d2 = sugar), acceptor (a1 = base, a2 = sugar):
+ *   E = rep + 1/2 (1 + cos(dihedral(d2,d1,a1,a2) - phi0)) f(K (angle(d2,d1,a1) - theta0_1))
+ *             f(K (angle(a2,a1,d1) - theta0_2)) attr,   dr = |d1-a1| - r0
+ * per-donor parameter arrays of length n_donors    ThreeSPN2BasePairForceFieldGenerator.cpp:5-100 */
+int ocm_system_add_3spn2_base_pair(ocm_system*, int group, const ocm_da_topology* topo,
+                                   const double* eps, const double* r0, const double* theta0_1,
+                                   const double* theta0_2, const double* phi0, double alpha,
+                                   double K_BP);
+/* 3SPN.2 cross stacking, donor (d1 = base, d2 = sugar, d3 unused by the expression), acceptor
+ * (a1 = paired base, a2 = sugar, a3 = cross base):
+ *   E = f(K_BP (t3 - theta0_3)) f(K_CS (angle(d2,d1,a3) - theta0_CS)) attr / 2,  dr = |d1-a3| - r0,
+ *   t3 = acos(clamp(sin t1 sin t2 cos phi - cos t1 cos t2, +-0.99)), t1 = angle(d2,d1,a1),
+ *   t2 = angle(d1,a1,a2), phi = dihedral(d2,d1,a1,a2)
+ * per-acceptor parameter arrays of length n_acceptors
+ *                                         ThreeSPN2CrossStackingForceFieldGenerator.cpp:5-104 */
+int ocm_system_add_3spn2_cross_stacking(ocm_system*, int group, const ocm_da_topology* topo,
+                                        const double* eps, const double* r0, const double* theta0_3,
+                                        const double* theta0_CS, double K_BP, double K_CS,
+                                        double alpha);
+/* protein-DNA non-specific hydrogen bond, donor (d1 = CA of the N-side neighbour, d2 = CA,
+ * d3 = CA of the C-side neighbour), acceptor (a1 = phosphate, a2 = 3' sugar):
+ *   E = -k exp(-dr^2 / 2 sigma^2) f(K (theta - theta0)) f(K (phi - phi0)),  K = pi / (2 delta),
+ *   dr = |d2-a1| - r0, phi = angle(d2,a1,a2), theta = acos(clamp(sin t1 sin t2 cos p - cos t1 cos t2,
+ *   +-0.99999)), t1 = angle(d1,d3,a1), t2 = angle(d3,a1,d2), p = dihedral(d1,d3,a1,d2)
+ * per-donor parameter arrays of length n_donors; the cutoff applies to |d1 - a1| (OpenMM's rule)
+ *                                         ProteinDNANonSpecificForceFieldGenerator.cpp:38-141 */
+int ocm_system_add_pdns(ocm_system*, int group, const ocm_da_topology* topo, const double* k,
+                        const double* r0, const double* theta0, const double* phi0, double sigma,
+                        double delta);
+
 /* ---- pair terms (per-bead parameter arrays have length N; NaN = bead does not take part) --- */
 /* E = eps (s_i+s_j)^12 (r^-12 - rc^-12), r < rc     ExcludedVolumeForceFieldGenerator.cpp:23-92 */
 int ocm_system_add_excluded_volume(ocm_system*, int group, double eps, double rc,
@@ -159,6 +214,11 @@ int ocm_get_neighbor_pairs(ocm_context*, int term, int32_t* ij, int64_t capacity
 /* cell index of every participant of the pair list serving `term` (-1 for non-participants),
  * and the grid dimensions */
 int ocm_get_cell_ids(ocm_context*, int term, int32_t* cell_of_bead, int32_t dims[3]);
+/* donor-acceptor terms: number of terms, and the (donor index, acceptor index) combinations of term `term`
+ * that are evaluated at the current positions (not excluded, |d1 - a1| < cutoff), sorted.  First call with
+ * da == NULL to get the count. */
+int ocm_num_da_terms(const ocm_context*);
+int ocm_get_da_pairs(ocm_context*, int term, int32_t* da, int64_t capacity, int64_t* n_pairs);
 /* counters: "pair_evals_per_step" (neighbor-list entries walked), "rebuilds", "rollbacks",
  * "kernel_launches", "nstlist", "max_neighbors", "num_pair_lists", "last_step_ms" (device time of the
  * last ocm_step, CUDA events on the engine's stream), "list_cutoff_nm.<term>", "threads_per_bead.<term>" */

@@ -30,6 +30,19 @@ class OcmError(RuntimeError):
     pass
 
 
+class DATopologyStruct(C.Structure):
+    _fields_ = [
+        ("n_donors", C.c_int64),
+        ("donors", C.POINTER(C.c_int32)),
+        ("n_acceptors", C.c_int64),
+        ("acceptors", C.POINTER(C.c_int32)),
+        ("n_excl", C.c_int64),
+        ("excl_da", C.POINTER(C.c_int32)),
+        ("cutoff", C.c_double),
+        ("periodic", C.c_int32),
+    ]
+
+
 class PairTopologyStruct(C.Structure):
     _fields_ = [
         ("n_excl", C.c_int64),
@@ -79,6 +92,29 @@ class PairTopology:
         s.set2 = set2.ctypes.data_as(_i32p)
         s.periodic = 1 if self.periodic else 0
         return s, keep
+
+
+@dataclass
+class DATopology:
+    """Donors, acceptors, exclusions and cutoff of one donor x acceptor term (see ocm_da_topology)."""
+
+    donors: np.ndarray      # (nd, 3) bead indices, -1 = unused
+    acceptors: np.ndarray   # (na, 3)
+    cutoff: float
+    excl: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), np.int32))  # (donor index, acceptor index)
+    periodic: bool = False
+
+    def to_struct(self):
+        d = np.ascontiguousarray(np.asarray(self.donors, np.int32).reshape(-1, 3))
+        a = np.ascontiguousarray(np.asarray(self.acceptors, np.int32).reshape(-1, 3))
+        e = np.ascontiguousarray(np.asarray(self.excl, np.int32).reshape(-1, 2))
+        s = DATopologyStruct()
+        s.n_donors, s.donors = d.shape[0], d.ctypes.data_as(_i32p)
+        s.n_acceptors, s.acceptors = a.shape[0], a.ctypes.data_as(_i32p)
+        s.n_excl, s.excl_da = e.shape[0], e.ctypes.data_as(_i32p)
+        s.cutoff = float(self.cutoff)
+        s.periodic = 1 if self.periodic else 0
+        return s, [d, a, e]
 
 
 def _f64(a):
@@ -132,6 +168,24 @@ class Library:
             C.c_int,
             [C.c_void_p, C.c_int, C.c_double, _f64p, _f64p, C.POINTER(PairTopologyStruct)],
         ),
+        "system_add_3spn2_base_stacking": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p, _f64p, C.c_double, C.c_double],
+        ),
+        "system_add_3spn2_base_pair": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.POINTER(DATopologyStruct), _f64p, _f64p, _f64p, _f64p, _f64p, C.c_double, C.c_double],
+        ),
+        "system_add_3spn2_cross_stacking": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.POINTER(DATopologyStruct), _f64p, _f64p, _f64p, _f64p, C.c_double, C.c_double, C.c_double],
+        ),
+        "system_add_pdns": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.POINTER(DATopologyStruct), _f64p, _f64p, _f64p, _f64p, C.c_double, C.c_double],
+        ),
+        "num_da_terms": (C.c_int, [C.c_void_p]),
+        "get_da_pairs": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int64, _i64p]),
         "context_create": (
             C.c_int,
             [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)],
@@ -282,6 +336,33 @@ class System:
             )
         )
 
+    def add_3spn2_base_stacking(self, group, ijk, eps, r0, theta0, alpha, K_BS, periodic=False):
+        self._bonded("system_add_3spn2_base_stacking", group, periodic, ijk, 3, _f64(eps), _f64(r0), _f64(theta0),
+                     extra=(float(alpha), float(K_BS)))
+
+    # ---- donor x acceptor -------------------------------------------------------------------
+    def _da(self, name, group, topo: DATopology, cols, count, scalars):
+        s, keep = topo.to_struct()
+        arrs = []
+        for c in cols:
+            c = _f64(c)
+            assert c.size == count, f"{name}: parameter column length {c.size} != {count}"
+            keep.append(c)
+            arrs.append(_p(c, _f64p))
+        self.lib.check(self.lib.fn[name](self.handle, int(group), C.byref(s), *arrs, *[float(x) for x in scalars]))
+
+    def add_3spn2_base_pair(self, group, topo, eps, r0, theta0_1, theta0_2, phi0, alpha, K_BP):
+        nd = np.asarray(topo.donors).reshape(-1, 3).shape[0]
+        self._da("system_add_3spn2_base_pair", group, topo, [eps, r0, theta0_1, theta0_2, phi0], nd, (alpha, K_BP))
+
+    def add_3spn2_cross_stacking(self, group, topo, eps, r0, theta0_3, theta0_CS, K_BP, K_CS, alpha):
+        na = np.asarray(topo.acceptors).reshape(-1, 3).shape[0]
+        self._da("system_add_3spn2_cross_stacking", group, topo, [eps, r0, theta0_3, theta0_CS], na, (K_BP, K_CS, alpha))
+
+    def add_pdns(self, group, topo, k, r0, theta0, phi0, sigma, delta):
+        nd = np.asarray(topo.donors).reshape(-1, 3).shape[0]
+        self._da("system_add_pdns", group, topo, [k, r0, theta0, phi0], nd, (sigma, delta))
+
     # ---- pair -------------------------------------------------------------------------------
     def _per_bead(self, a):
         a = _f64(a)
@@ -415,6 +496,16 @@ class Context:
         ij = np.zeros((max(n.value, 1), 2), np.int32)
         self.lib.check(self.lib.fn["get_neighbor_pairs"](self.handle, int(term), _p(ij, _i32p), ij.shape[0], C.byref(n)))
         return ij[: n.value]
+
+    def num_da_terms(self):
+        return int(self.lib.fn["num_da_terms"](self.handle))
+
+    def da_pairs(self, term):
+        n = C.c_int64()
+        self.lib.check(self.lib.fn["get_da_pairs"](self.handle, int(term), None, 0, C.byref(n)))
+        da = np.zeros((max(n.value, 1), 2), np.int32)
+        self.lib.check(self.lib.fn["get_da_pairs"](self.handle, int(term), _p(da, _i32p), da.shape[0], C.byref(n)))
+        return da[: n.value]
 
     def cell_ids(self, term):
         ids = np.zeros(self.n, np.int32)

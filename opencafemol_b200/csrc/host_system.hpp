@@ -17,13 +17,13 @@ namespace ocm {
 
 enum BondedKind : int {
     B_HARMONIC_BOND = 0, B_GAUSSIAN_BOND, B_GO_CONTACT, B_3SPN2_BOND,
-    B_HARMONIC_ANGLE, B_FLEX_ANGLE, B_GAUSSIAN_DIHEDRAL, B_COSINE_DIHEDRAL, B_FLEX_DIHEDRAL,
+    B_HARMONIC_ANGLE, B_FLEX_ANGLE, B_GAUSSIAN_DIHEDRAL, B_COSINE_DIHEDRAL, B_FLEX_DIHEDRAL, B_3SPN2_STACK,
     B_NUM_KINDS
 };
 
 inline int bonded_nbody(int kind) {
     if (kind <= B_3SPN2_BOND) return 2;
-    if (kind <= B_FLEX_ANGLE) return 3;
+    if (kind <= B_FLEX_ANGLE || kind == B_3SPN2_STACK) return 3;
     return 4;
 }
 
@@ -49,6 +49,20 @@ struct PairTerm {
     int ncls;
 };
 
+// donor x acceptor ("CustomHbondForce"-like) term
+enum DAKind : int { DA_BASE_PAIR = 0, DA_CROSS_STACK = 1, DA_PDNS = 2 };
+
+struct DATerm {
+    int kind, group, periodic, npar;
+    double cutoff;
+    double g0, g1, g2;                  // BP: alpha, K_BP; CS: K_BP, K_CS, alpha; PDNS: sigma, delta
+    std::vector<int32_t> donors, acceptors;  // 3 per entry, -1 = unused
+    std::vector<double> p;              // npar per donor (BP, PDNS) or per acceptor (CS)
+    std::vector<uint64_t> excl;         // sorted keys donor * n_acceptors + acceptor
+    int64_t nd() const { return (int64_t)donors.size() / 3; }
+    int64_t na() const { return (int64_t)acceptors.size() / 3; }
+};
+
 }  // namespace ocm
 
 struct ocm_system {
@@ -58,6 +72,7 @@ struct ocm_system {
     double box[3] = {0, 0, 0};
     std::vector<ocm::BondedTerm> bonded;
     std::vector<ocm::PairTerm> pairs;
+    std::vector<ocm::DATerm> das;
 };
 
 namespace ocm {
@@ -193,6 +208,55 @@ inline int add_pair(ocm_system* s, int kind, int group, double rc, double rsw, d
         }
     }
     s->pairs.push_back(std::move(t));
+    return 0;
+}
+
+inline int add_da(ocm_system* s, int kind, int group, const ocm_da_topology* topo, bool per_donor,
+                  std::vector<const double*> cols, double g0, double g1, double g2, const char* what) {
+    if (!s || !topo) return fail(std::string(what) + ": null argument");
+    if (group < 0 || group > 31) return fail("force group must be in 0..31");
+    if (topo->periodic && !s->has_box) return fail(std::string(what) + ": periodic term without a box");
+    if (!topo->periodic && s->has_box) return fail(std::string(what) + ": non-periodic donor-acceptor term in a periodic system is not supported");
+    if (!(topo->cutoff > 0)) return fail(std::string(what) + ": cutoff must be positive");
+    if (topo->periodic)
+        for (int k = 0; k < 3; k++)
+            if (topo->cutoff > 0.5 * s->box[k]) return fail(std::string(what) + ": cutoff exceeds half the box");
+    if (topo->n_donors < 0 || topo->n_acceptors < 0 || topo->n_excl < 0) return fail(std::string(what) + ": negative count");
+    if ((topo->n_donors > 0 && !topo->donors) || (topo->n_acceptors > 0 && !topo->acceptors) || (topo->n_excl > 0 && !topo->excl_da))
+        return fail(std::string(what) + ": null index array");
+    if (topo->n_donors >= (1 << 24) || topo->n_acceptors >= (1 << 24)) return fail(std::string(what) + ": too many donors or acceptors");
+    DATerm t;
+    t.kind = kind; t.group = group; t.periodic = topo->periodic ? 1 : 0; t.cutoff = topo->cutoff;
+    t.npar = (int)cols.size(); t.g0 = g0; t.g1 = g1; t.g2 = g2;
+    t.donors.assign(topo->donors, topo->donors + 3 * topo->n_donors);
+    t.acceptors.assign(topo->acceptors, topo->acceptors + 3 * topo->n_acceptors);
+    // which slots the expression of each kind reads (d1,d2,d3 / a1,a2,a3); d1 and a1 always (cutoff)
+    static const bool need_d[3][3] = {{true, true, false}, {true, true, false}, {true, true, true}};
+    static const bool need_a[3][3] = {{true, true, false}, {true, true, true}, {true, true, false}};
+    for (int64_t d = 0; d < topo->n_donors; d++)
+        for (int q = 0; q < 3; q++) {
+            int32_t v = t.donors[3 * d + q];
+            if (v >= s->n || v < -1 || (v < 0 && need_d[kind][q])) return fail(std::string(what) + ": donor particle index out of range");
+        }
+    for (int64_t a = 0; a < topo->n_acceptors; a++)
+        for (int q = 0; q < 3; q++) {
+            int32_t v = t.acceptors[3 * a + q];
+            if (v >= s->n || v < -1 || (v < 0 && need_a[kind][q])) return fail(std::string(what) + ": acceptor particle index out of range");
+        }
+    for (int64_t e = 0; e < topo->n_excl; e++) {
+        int64_t d = topo->excl_da[2 * e], a = topo->excl_da[2 * e + 1];
+        if (d < 0 || d >= topo->n_donors || a < 0 || a >= topo->n_acceptors) return fail(std::string(what) + ": exclusion index out of range");
+        t.excl.push_back((uint64_t)d * (uint64_t)topo->n_acceptors + (uint64_t)a);
+    }
+    std::sort(t.excl.begin(), t.excl.end());
+    t.excl.erase(std::unique(t.excl.begin(), t.excl.end()), t.excl.end());
+    const int64_t cnt = per_donor ? topo->n_donors : topo->n_acceptors;
+    t.p.resize((size_t)cnt * t.npar);
+    for (int q = 0; q < t.npar; q++) {
+        if (cnt > 0 && !cols[q]) return fail(std::string(what) + ": null parameter array");
+        for (int64_t m = 0; m < cnt; m++) t.p[(size_t)m * t.npar + q] = cols[q][m];
+    }
+    s->das.push_back(std::move(t));
     return 0;
 }
 

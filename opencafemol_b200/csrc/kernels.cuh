@@ -17,11 +17,14 @@
 namespace ocm {
 
 constexpr int kBlock = 128;            // threads per block of the force kernel
+#ifndef OCM_FORCE_MINBLOCKS
+#define OCM_FORCE_MINBLOCKS 8            // resident blocks per SM the force kernel is compiled for (register cap 64)
+#endif
 constexpr double kFixScale = 4294967296.0;  // force accumulator: 64-bit fixed point, 2^32 per kJ/mol/nm
 constexpr int kMaxMembers = 4;
 
-enum SegKind : int { SEG_PAIR_TZ = 0, SEG_PAIR_DH = 1, SEG_BONDED = 2 };
-enum FlagSlot : int { FLAG_VIOLATION = 0, FLAG_OVERFLOW = 1, FLAG_TICKET = 2, FLAG_NAN = 3, FLAG_MAXDISP = 4, FLAG_COUNT = 8 };
+enum SegKind : int { SEG_PAIR_TZ = 0, SEG_PAIR_DH = 1, SEG_BONDED = 2, SEG_DA = 3 };
+enum FlagSlot : int { FLAG_VIOLATION = 0, FLAG_OVERFLOW = 1, FLAG_TICKET = 2, FLAG_NAN = 3, FLAG_MAXDISP = 4, FLAG_DA_OVERFLOW = 6, FLAG_COUNT = 8 };
 
 struct GridDev {
     int nc[3];
@@ -46,15 +49,22 @@ struct PairListDev {
     int* cell_count;            // [max_cells+1]
     int* cell_start;            // [max_cells+1]
     int* cell_cursor;           // [max_cells]
-    int* sorted_slots;          // [np]
-    int* nbr_count;             // [np]
-    unsigned int* nbr;          // [np*stride]  bead | type<<24
+    int* tmp_slots;             // [np] cell-grouped slots, arbitrary order inside a cell (scatter output)
+    int* sorted_slots;          // [np] rank k -> slot; cells in grid order, ascending slot inside a cell
+    int* rank_of_bead;          // [N]  bead -> rank k in this list's cell-sorted order, -1 = non participant
+    uint4* spos;                // [np] cell-sorted pair-kernel positions; w = bead | type<<24 (two-zone lists) or the
+                                //      bits of the scaled charge q sqrt(K) (screened-Coulomb lists)
+    int* bead_of_rank;          // [np] rank k -> bead
+    const float* qscaled;       // [np] per slot q sqrt(K) (screened-Coulomb lists)
+    int* nbr_count;             // [np] row length of rank k
+    int* nbr_inner;             // [np] leading entries of the row that are guaranteed inside the inner zone (see zone_a2)
+    float zone_a2, zone_b2, zone_c2;  // build-time distance zones: rows are ordered [A | A' | B | C]
+    unsigned int* nbr;          // [np*stride]  row of rank k: partner rank | partner type<<24
     float rlist2, rc2, rsw, inv_sw;
     // two-zone 12-6 family: E = c12/r^12 - c6/r^6 + c0 inside a2, outer coefficients beyond
-    const float4* tabF;         // [nt*nt] {c12_in, c6_in, c12_out, c6_out} summed over members
-    const float* tabA2;         // [nt*nt] zone boundary squared
-    // screened Coulomb: E = qq (exp(-r/debye)/r - cc)
-    const float* tabQ;          // [nt*nt]
+    const float4* tabF;         // [nt*nt] {12 c12, 6 c6, a2, w}: -dE/dr / r = zone * (12 c12/r^12 - 6 c6/r^6)/r^2
+    float k_in;                 // zone factor = r^2 < a2 ? k_in : w
+    // screened Coulomb: E = q_i q_j K (exp(-r/debye)/r - cc); the charges ride in spos.w
     float inv_debye, dh_cc;
     // per-member energy tables (observer side)
     int mem_group[kMaxMembers];
@@ -71,8 +81,30 @@ struct BondedDev {
     const double* tabs;   // 24 doubles per table
 };
 
+// donor x acceptor terms (3SPN.2 base pairing / cross stacking, PDNS): per-term tables + one Verlet list of
+// (term, donor, acceptor) combinations inside cutoff + skin, rebuilt together with the pair lists
+struct DATermDev {
+    int kind, group, periodic, npar;
+    int nd, na, nexcl, pad;
+    long long cand_begin;              // offset of the term in the flattened donor x acceptor candidate space
+    double rc2, rlist2;                // cutoff^2, (cutoff + skin)^2
+    double g0, g1, g2;
+    const int* donors;                 // 3 * nd
+    const int* acceptors;              // 3 * na
+    const double* par;                 // npar per donor (base pair, PDNS) or per acceptor (cross stacking)
+    const unsigned long long* excl;    // sorted keys donor * na + acceptor
+};
+struct DAListDev {
+    int nterms, capacity;
+    long long ncand;
+    const DATermDev* terms;
+    unsigned int* count;               // entries in use
+    uint2* entries;                    // x = term << 24 | donor, y = acceptor
+};
+
 struct WorkSeg {
-    int block_begin, nblocks, kind, id, tpb;  // tpb: threads per bead (pair segments)
+    int block_begin, nblocks, kind, id, tpb, chunk;  // pair segments: tpb threads per bead, chunk beads per block
+    int staged;                                       // rows staged in shared memory by bulk async copies (tpb == 32)
 };
 
 struct StepParams {
@@ -108,6 +140,42 @@ __device__ __forceinline__ void delta(const uint4& pi, const uint4& pj, const fl
 // canonical squared distance: same operation order as the oracle's canon_r2 (bit-exact pair sets)
 __device__ __forceinline__ float norm2(float dx, float dy, float dz) {
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // <= 1 ulp
+    return y;
+}
+
+__device__ __forceinline__ float fast_rsqrt(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP): a whole Verlet row global -> shared -------
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    unsigned int done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
 }
 
 __device__ __forceinline__ int enc_float(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
@@ -261,46 +329,67 @@ __global__ void scatter_kernel(const PairListDev* lists, int li) {
     int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= L.np) return;
     int pos = atomicAdd(&L.cell_cursor[L.cell_of_slot[a]], 1);
-    L.sorted_slots[pos] = a;
+    L.tmp_slots[pos] = a;
 }
 
-// order the members of every cell by slot (= ascending bead index) so that list order, and with
-// it the FP32 summation order of the force kernel, is reproducible run to run
-__global__ void sortcell_kernel(const PairListDev* lists, int li) {
+// Deterministic cell-sorted order: inside a cell, members are ranked by slot (= ascending bead index), so the
+// list order, and with it the FP32 summation order of the force kernel, is reproducible run to run.  Also
+// fills the list's cell-sorted position array (w = bead | type<<24) and the bead -> rank map.
+__global__ void rank_fill_kernel(const PairListDev* lists, int li, const uint4* __restrict__ posq) {
     const PairListDev& L = lists[li];
-    const int ncell = L.grid->ncell;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x) {
-        int s = L.cell_start[c], e = L.cell_start[c + 1];
-        for (int i = s + 1; i < e; i++) {
-            int v = L.sorted_slots[i], j = i - 1;
-            while (j >= s && L.sorted_slots[j] > v) { L.sorted_slots[j + 1] = L.sorted_slots[j]; j--; }
-            L.sorted_slots[j + 1] = v;
-        }
-    }
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= L.np) return;
+    const int a = L.tmp_slots[p];
+    const int c = L.cell_of_slot[a];
+    const int s = L.cell_start[c], e = L.cell_start[c + 1];
+    int r = 0;
+    for (int q = s; q < e; q++) r += (L.tmp_slots[q] < a) ? 1 : 0;
+    const int k = s + r;
+    const int bead = L.part[a];
+    L.sorted_slots[k] = a;
+    L.rank_of_bead[bead] = k;
+    L.bead_of_rank[k] = bead;
+    uint4 q4 = posq[bead];
+    q4.w = (L.form == SEG_PAIR_DH) ? __float_as_uint(L.qscaled[a]) : ((unsigned int)bead | ((unsigned int)L.type[a] << 24));
+    L.spos[k] = q4;
 }
 
-// one warp per participant: walk the 5x5 rows of neighbouring cells (x-runs are contiguous in the
-// cell-sorted order), test the canonical distance, exclusions and interaction classes, compact with
-// ballots.  count_only: just record the neighbour count (used to size the list).
+// one warp per participant (in cell-sorted order): walk the 5x5 rows of neighbouring cells -- x-runs are
+// contiguous in the cell-sorted position array, so candidates stream in with coalesced 16-byte loads -- test
+// the canonical distance, exclusions and interaction classes, compact with ballots.
+// The row is assembled in shared memory and written out ordered by build-time distance zone [A | A' | B | C]
+// (scan order inside a zone, so it stays deterministic):
+//   A : r^2 < zone_a2 = (min(r_switch, rc) - skin)^2  -> inside the cutoff and below the switch until the next
+//       rebuild (beads move at most skin/2 each): the force kernel evaluates these with no tests (nbr_inner)
+//   A': r^2 < zone_b2   probably still below the switching distance  (warp-uniform vote skips the switch)
+//   B : r^2 < zone_c2   switching region / cutoff shell
+//   C : the rest of the skin                                      (warp-uniform vote skips everything)
+// count_only: just record the neighbour count (used to size the list).  zoned == 0: no shared memory, one zone.
 template <bool PER>
-__global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P, const uint4* __restrict__ posq,
-                                  int* __restrict__ flags, int count_only) {
+__global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P, int* __restrict__ flags, int count_only, int zoned) {
+    extern __shared__ __align__(16) unsigned int bl_smem[];
     const PairListDev& L = lists[li];
     const int lane = threadIdx.x & 31;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= L.np) return;
     const GridDev& g = *L.grid;
+    const uint4* __restrict__ spos = L.spos;
+    const bool dh = L.form == SEG_PAIR_DH;
     const int a = L.sorted_slots[w];
-    const int i = L.part[a];
-    const uint4 pi = posq[i];
+    const uint4 pi = spos[w];
     const int ci = L.cell_of_slot[a];
     const int ncx = g.nc[0], ncy = g.nc[1], ncz = g.nc[2];
     const int cx = ci % ncx, cy = (ci / ncx) % ncy, cz = ci / (ncx * ncy);
     const int e0 = L.excl_off[a], e1 = L.excl_off[a + 1];
     const unsigned int my_allow = L.cls ? L.allow[(int)L.cls[a]] : 0xffffffffu;
-    const float rl2 = L.rlist2;
-    unsigned int* row = L.nbr + (size_t)a * L.stride;
-    int count = 0;
+    const float rl2 = L.rlist2, za2 = L.zone_a2, zb2 = L.zone_b2, zc2 = L.zone_c2;
+    const int stride = L.stride;
+    unsigned int* row = L.nbr + (size_t)w * stride;
+    const bool stage = zoned && !count_only;
+    const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    unsigned int* s_row = bl_smem + (size_t)wib * stride;
+    unsigned char* s_zone = reinterpret_cast<unsigned char*>(bl_smem + (size_t)wpb * stride) + (size_t)wib * stride;
+    int count = 0, cz0 = 0, cz1 = 0, cz2 = 0;
 
     int nz, ny, z0, y0;
     if (PER) { nz = min(5, ncz); z0 = (ncz >= 5) ? cz - 2 : 0; ny = min(5, ncy); y0 = (ncy >= 5) ? cy - 2 : 0; }
@@ -330,37 +419,73 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
                     const int k = k0 + lane;
                     bool ok = false;
                     unsigned int entry = 0;
-                    if (k < ke) {
-                        const int b = L.sorted_slots[k];
-                        const int j = L.part[b];
-                        if (j != i) {
-                            float dx, dy, dz;
-                            delta<PER>(pi, posq[j], P.fscale, dx, dy, dz);
-                            if (norm2(dx, dy, dz) < rl2) {
-                                ok = true;
-                                if (L.cls) ok = (my_allow >> (int)L.cls[b]) & 1u;
-                                for (int e = e0; ok && e < e1; e++) ok = L.excl_idx[e] != j;
-                                entry = (unsigned int)j | ((unsigned int)L.type[b] << 24);
-                            }
+                    int zone = 3;
+                    if (k < ke && k != w) {
+                        const uint4 pj = spos[k];
+                        float dx, dy, dz;
+                        delta<PER>(pi, pj, P.fscale, dx, dy, dz);
+                        const float r2 = norm2(dx, dy, dz);
+                        if (r2 < rl2) {
+                            ok = true;
+                            if (L.cls) ok = (my_allow >> (int)L.cls[L.sorted_slots[k]]) & 1u;
+                            const int j = dh ? L.bead_of_rank[k] : (int)(pj.w & 0xFFFFFFu);
+                            for (int e = e0; ok && e < e1; e++) ok = L.excl_idx[e] != j;
+                            entry = dh ? (unsigned int)k : ((unsigned int)k | (pj.w & 0xFF000000u));
+                            zone = (r2 < za2) ? 0 : (r2 < zb2) ? 1 : (r2 < zc2) ? 2 : 3;
                         }
                     }
                     const unsigned int m = __ballot_sync(0xffffffffu, ok);
-                    if (ok && !count_only) {
+                    if (m == 0u) continue;
+                    if (!count_only) {
                         const int pos = count + __popc(m & ((1u << lane) - 1u));
-                        if (pos < L.stride) row[pos] = entry;
+                        if (ok && pos < stride) {
+                            if (stage) { s_row[pos] = entry; s_zone[pos] = (unsigned char)zone; }
+                            else row[pos] = entry;
+                        }
+                        if (stage) {
+                            cz0 += __popc(__ballot_sync(0xffffffffu, ok && zone == 0));
+                            cz1 += __popc(__ballot_sync(0xffffffffu, ok && zone == 1));
+                            cz2 += __popc(__ballot_sync(0xffffffffu, ok && zone == 2));
+                        }
                     }
                     count += __popc(m);
                 }
             }
         }
     }
-    if (lane == 0) {
-        if (count_only) { L.nbr_count[a] = count; atomicMax(&flags[FLAG_MAXDISP + 1], count); }
-        else {
-            if (count > L.stride) { flags[FLAG_OVERFLOW] = 1; count = L.stride; }
-            L.nbr_count[a] = count;
+    if (count_only) {
+        if (lane == 0) { L.nbr_count[w] = count; atomicMax(&flags[FLAG_MAXDISP + 1], count); }
+        return;
+    }
+    int n_inner = 0;
+    if (count > stride) {
+        if (lane == 0) flags[FLAG_OVERFLOW] = 1;  // the engine re-sizes the rows and rebuilds
+        count = stride;
+        if (stage) for (int t = lane; t < count; t += 32) row[t] = s_row[t];
+    } else if (stage) {
+        __syncwarp();
+        int off0 = 0, off1 = cz0, off2 = cz0 + cz1, off3 = cz0 + cz1 + cz2;
+        n_inner = cz0;
+        for (int t0 = 0; t0 < count; t0 += 32) {
+            const int t = t0 + lane;
+            const bool live = t < count;
+            const unsigned int e = live ? s_row[t] : 0u;
+            const int z = live ? (int)s_zone[t] : -1;
+            const unsigned int lt = (1u << lane) - 1u;
+            const unsigned int m0 = __ballot_sync(0xffffffffu, z == 0), m1 = __ballot_sync(0xffffffffu, z == 1);
+            const unsigned int m2 = __ballot_sync(0xffffffffu, z == 2), m3 = __ballot_sync(0xffffffffu, z == 3);
+            if (z == 0) row[off0 + __popc(m0 & lt)] = e;
+            else if (z == 1) row[off1 + __popc(m1 & lt)] = e;
+            else if (z == 2) row[off2 + __popc(m2 & lt)] = e;
+            else if (z == 3) row[off3 + __popc(m3 & lt)] = e;
+            off0 += __popc(m0); off1 += __popc(m1); off2 += __popc(m2); off3 += __popc(m3);
         }
     }
+    // pad the row to a multiple of 32 with the self entry (distance 0, never interacts): the T = 32 force paths
+    // read whole 32-entry groups
+    const int pad = count + lane;
+    if (pad < ((count + 31) & ~31) && pad < stride) row[pad] = dh ? (unsigned int)w : ((unsigned int)w | (pi.w & 0xFF000000u));
+    if (lane == 0) { L.nbr_count[w] = count; L.nbr_inner[w] = n_inner; }
 }
 
 __global__ void save_ref_kernel(int n, const double* __restrict__ x, double* __restrict__ xref) {
@@ -369,112 +494,352 @@ __global__ void save_ref_kernel(int n, const double* __restrict__ x, double* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// pair forces.  T threads walk one participant's Verlet row (coalesced 4-byte entries), gather the
-// 16-byte partner position, and reduce the FP32 force with shuffles; one fixed-point atomic triple
-// per bead merges the result with the other lists and the bonded terms.
-template <bool PER, int T, bool SMEM>
-__device__ __forceinline__ void pair_tz_block(const PairListDev& L, int blk, const StepParams& P,
-                                              const uint4* __restrict__ posq, unsigned long long* __restrict__ fbuf,
-                                              float* smem) {
-    const int nt = L.ntypes, nt2 = nt * nt;
-    const float4* tabF;
-    const float* tabA2;
-    if (SMEM) {
-        float4* sF = reinterpret_cast<float4*>(smem);
-        float* sA = smem + 4 * nt2;
-        for (int k = threadIdx.x; k < nt2; k += kBlock) { sF[k] = L.tabF[k]; sA[k] = L.tabA2[k]; }
-        __syncthreads();
-        tabF = sF; tabA2 = sA;
-    } else { tabF = L.tabF; tabA2 = L.tabA2; }
-    constexpr int BPB = kBlock / T;
-    const int a = blk * BPB + threadIdx.x / T, s = threadIdx.x % T;
-    float fx = 0.f, fy = 0.f, fz = 0.f;
-    int i = 0;
-    const bool active = a < L.np;
-    if (active) {
-        i = L.part[a];
-        const uint4 pi = posq[i];
-        const int trow = (int)L.type[a] * nt;
-        const int n = L.nbr_count[a];
-        const unsigned int* __restrict__ row = L.nbr + (size_t)a * L.stride;
-        const float rc2 = L.rc2, rsw = L.rsw, inv_sw = L.inv_sw;
-        const float rsw2 = rsw * rsw;
-        const bool sw = L.has_switch != 0;
+// pair forces.  T lanes walk the Verlet row of one participant (coalesced 4-byte entries), gather 16-byte
+// partner positions from the list's cell-sorted array (neighbouring entries are neighbouring addresses, so a
+// warp-wide gather touches few cache lines), and reduce the FP32 force with shuffles; one fixed-point atomic
+// triple per bead merges the result with the other lists and the bonded terms.  A block owns the contiguous
+// rank range [blk*chunk, (blk+1)*chunk): beads that are close in space, so rows overlap in L1.
+//
+// Two-zone 12-6 family: per type pair one float4 {12 c12, 6 c6, a2, w};
+//   -dE/dr / r = zone * (12 c12 / r^12 - 6 c6 / r^6) / r^2,  zone = r^2 < a2 ? k_in : k_out + k_w * w
+template <bool PER, int T, bool SW>
+__device__ __forceinline__ void pair_tz_rows(const PairListDev& L, int k_lo, int k_hi, const StepParams& P,
+                                             unsigned long long* __restrict__ fbuf, const float4* __restrict__ tab) {
+    constexpr int G = kBlock / T;
+    const int g = threadIdx.x / T, s = threadIdx.x % T;
+    const uint4* __restrict__ spos = L.spos;
+    const int nt = L.ntypes;
+    const float rc2 = L.rc2, rsw = L.rsw, inv_sw = L.inv_sw, rsw2 = rsw * rsw;
+    const float kin = L.k_in;
+    for (int base = k_lo; base < k_hi; base += G) {
+        const int k = base + g;
+        const bool active = k < k_hi;
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        unsigned int wi = 0;
+        if (active) {
+            const uint4 pi = spos[k];
+            wi = pi.w;
+            const int trow = (int)(wi >> 24) * nt;
+            const int n = L.nbr_count[k];
+            const unsigned int* __restrict__ row = L.nbr + (size_t)k * L.stride;
 #pragma unroll 4
-        for (int k = s; k < n; k += T) {
-            const unsigned int e = __ldg(&row[k]);
-            const uint4 pj = __ldg(&posq[e & 0xFFFFFFu]);
-            float dx, dy, dz;
-            delta<PER>(pi, pj, P.fscale, dx, dy, dz);
-            const float r2 = norm2(dx, dy, dz);
-            if (r2 < rc2) {
-                const int ti = trow + (int)(e >> 24);
-                const float4 c = tabF[ti];
-                const bool inner = r2 < tabA2[ti];
-                const float c12 = inner ? c.x : c.z, c6 = inner ? c.y : c.w;
-                const float ir2 = __frcp_rn(r2);
+            for (int t = s; t < n; t += T) {
+                const unsigned int e = __ldg(&row[t]);
+                const uint4 pj = __ldg(&spos[(int)(e & 0xFFFFFFu)]);
+                float dx, dy, dz;
+                delta<PER>(pi, pj, P.fscale, dx, dy, dz);
+                const float r2 = norm2(dx, dy, dz);
+                const float4 c = tab[trow + (int)(e >> 24)];
+                const float ir2 = fast_rcp(r2);
                 const float ir6 = ir2 * ir2 * ir2;
-                float fr = (12.f * c12 * ir6 - 6.f * c6) * ir6 * ir2;  // -dE/dr / r
-                if (sw && r2 > rsw2) {
-                    const float r = sqrtf(r2);
-                    const float t = (r - rsw) * inv_sw;
-                    const float S = 1.f + t * t * t * (-10.f + t * (15.f - 6.f * t));
-                    const float dS = t * t * (-30.f + t * (60.f - 30.f * t)) * inv_sw;
-                    const float E = (c12 * ir6 - c6) * ir6;
-                    fr = S * fr - E * dS / r;
+                const float zone = (r2 < c.z) ? kin : c.w;
+                const float a12 = c.x * ir6;
+                float fr = zone * (a12 - c.y) * ir6 * ir2;
+                if (SW) {
+                    if (r2 > rsw2) {
+                        // OpenMM switching function on [rsw, rc]: S = (1-t)^3 (1 + 3t + 6t^2), S' = -30 t^2 (1-t)^2 / (rc-rsw)
+                        const float ir = fast_rsqrt(r2);
+                        const float tt = __saturatef((r2 * ir - rsw) * inv_sw), u = 1.f - tt;
+                        const float S = u * u * u * fmaf(tt, fmaf(tt, 6.f, 3.f), 1.f);
+                        const float tu = tt * u;
+                        const float dS = -30.f * inv_sw * tu * tu;
+                        const float E = zone * (a12 * (1.f / 12.f) - c.y * (1.f / 6.f)) * ir6;
+                        fr = S * fr - E * dS * ir;
+                    }
                 }
+                fr = (r2 < rc2) ? fr : 0.f;
                 fx = fmaf(fr, dx, fx); fy = fmaf(fr, dy, fy); fz = fmaf(fr, dz, fz);
             }
         }
-    }
 #pragma unroll
-    for (int o = T / 2; o > 0; o >>= 1) {
-        fx += __shfl_xor_sync(0xffffffffu, fx, o);
-        fy += __shfl_xor_sync(0xffffffffu, fy, o);
-        fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        for (int o = T / 2; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        if (active && s == 0) add_force_fixed(fbuf, P.n, (int)(wi & 0xFFFFFFu), fx, fy, fz);
     }
-    if (active && s == 0) add_force_fixed(fbuf, P.n, i, fx, fy, fz);
+}
+
+// one pair evaluation of the two-zone 12-6 family; `in` = inside the cutoff (false for padding lanes).
+// Branches are warp-uniform votes: rows are ordered near -> far at build time (zones A' | B | C), so most warp
+// iterations of A' skip the switching function and most of C (the outer skin) skip everything.
+template <bool SW>
+__device__ __forceinline__ void tz_pair(const float4 c, float r2, bool in, float dx, float dy, float dz, float kin,
+                                        float rsw, float rsw2, float inv_sw, float& fx, float& fy, float& fz) {
+    if (!__any_sync(0xffffffffu, in)) return;
+    const float ir2 = fast_rcp(r2);
+    const float ir6 = ir2 * ir2 * ir2;
+    const float zone = (r2 < c.z) ? kin : c.w;
+    const float a12 = c.x * ir6;
+    float fr = zone * (a12 - c.y) * ir6 * ir2;
+    if (SW) {
+        if (__any_sync(0xffffffffu, in && r2 > rsw2)) {
+            // OpenMM switching function on [rsw, rc]: S = (1-t)^3 (1 + 3t + 6t^2), S' = -30 t^2 (1-t)^2 / (rc-rsw)
+            const float ir = fast_rsqrt(r2);
+            const float tt = __saturatef((r2 * ir - rsw) * inv_sw), u = 1.f - tt;
+            const float S = u * u * u * fmaf(tt, fmaf(tt, 6.f, 3.f), 1.f);
+            const float tu = tt * u;
+            const float dS = -30.f * inv_sw * tu * tu;
+            const float E = zone * (a12 * (1.f / 12.f) - c.y * (1.f / 6.f)) * ir6;
+            fr = S * fr - E * dS * ir;
+        }
+    }
+    fr = in ? fr : 0.f;
+    fx = fmaf(fr, dx, fx); fy = fmaf(fr, dy, fy); fz = fmaf(fr, dz, fz);
+}
+// zone A of a row: the pair was closer than (r_switch or rc) - skin when the list was built, so it is inside
+// the cutoff and below the switching distance for the whole life of the list: no tests at all
+__device__ __forceinline__ void tz_pair_inner(const float4 c, float r2, float dx, float dy, float dz, float kin,
+                                              float& fx, float& fy, float& fz) {
+    const float ir2 = fast_rcp(r2);
+    const float ir6 = ir2 * ir2 * ir2;
+    const float zone = (r2 < c.z) ? kin : c.w;
+    const float fr = zone * (c.x * ir6 - c.y) * ir6 * ir2;
+    fx = fmaf(fr, dx, fx); fy = fmaf(fr, dy, fy); fz = fmaf(fr, dz, fz);
+}
+
+// T = 32 path with the row staged in shared memory: one lane issues a 1-D bulk async copy (TMA engine) of the
+// NEXT bead's whole row while the warp works on the current one, so the L2 latency of the row stream never
+// sits on the critical path; inside a row, four gathers + four table look-ups are in flight per lane.
+template <bool PER, bool SW>
+__device__ __forceinline__ void pair_tz_rows_staged(const PairListDev& L, int k_lo, int k_hi, const StepParams& P,
+                                                    unsigned long long* __restrict__ fbuf, const float4* tab,
+                                                    unsigned int* rowbuf, unsigned long long* bars) {
+    constexpr int G = kBlock / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint4* __restrict__ spos = L.spos;
+    const int nt = L.ntypes, stride = L.stride;
+    const float rc2 = L.rc2, rsw = L.rsw, inv_sw = L.inv_sw, rsw2 = rsw * rsw;
+    const float kin = L.k_in;
+    unsigned int* buf = rowbuf + (size_t)warp * 2 * stride;
+    unsigned long long* bar = bars + warp * 2;
+    int k = k_lo + warp;
+    if (k >= k_hi) return;
+    int n_cur = L.nbr_count[k];
+    int n_next = (k + G < k_hi) ? L.nbr_count[k + G] : 0;
+    if (lane == 0) {
+        const unsigned int bytes = (unsigned int)((n_cur + 31) & ~31) << 2;
+        if (bytes) { mbar_expect_tx(&bar[0], bytes); bulk_copy_g2s(buf, L.nbr + (size_t)k * stride, bytes, &bar[0]); }
+    }
+    for (int it = 0; k < k_hi; k += G, it++) {
+        const int b = it & 1;
+        const int n = n_cur;
+        __syncwarp();  // every lane is done reading buffer b^1 (previous bead)
+        if (lane == 0 && k + G < k_hi) {
+            const unsigned int bytes = (unsigned int)((n_next + 31) & ~31) << 2;
+            if (bytes) { mbar_expect_tx(&bar[b ^ 1], bytes); bulk_copy_g2s(buf + (size_t)(b ^ 1) * stride, L.nbr + (size_t)(k + G) * stride, bytes, &bar[b ^ 1]); }
+        }
+        n_cur = n_next;
+        n_next = (k + 2 * G < k_hi) ? L.nbr_count[k + 2 * G] : 0;
+        const uint4 pi = spos[k];
+        const int trow = (int)(pi.w >> 24) * nt;
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        if (n > 0) {
+            // buffer b completes its (it>>1)-th phase
+            mbar_wait(&bar[b], (unsigned int)(it >> 1) & 1u);
+            const unsigned int* row = buf + (size_t)b * stride;
+            const unsigned int self = (unsigned int)k | (pi.w & 0xFF000000u);  // rows are padded to 32 with the self entry (r2 = 0)
+            for (int t0 = 0; t0 < n; t0 += 128) {
+                unsigned int e[4];
+                uint4 pj[4];
+                float4 c[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) e[u] = (t0 + u * 32 < n) ? row[t0 + u * 32 + lane] : self;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    pj[u] = __ldg(&spos[(int)(e[u] & 0xFFFFFFu)]);
+                    c[u] = tab[trow + (int)(e[u] >> 24)];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (t0 + u * 32 >= n) break;  // warp-uniform
+                    float dx, dy, dz;
+                    delta<PER>(pi, pj[u], P.fscale, dx, dy, dz);
+                    const float r2 = norm2(dx, dy, dz);
+                    const bool in = (r2 < rc2) && (r2 > 0.f);
+                    tz_pair<SW>(c[u], r2, in, dx, dy, dz, kin, rsw, rsw2, inv_sw, fx, fy, fz);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        if (lane == 0) add_force_fixed(fbuf, P.n, (int)(pi.w & 0xFFFFFFu), fx, fy, fz);
+    }
+}
+
+// T = 32 path, rows streamed from global memory with register double-buffering: the next four row entries
+// (and the first four of the next bead's row) are requested before the current four pairs are evaluated, so the
+// row stream's L2 latency overlaps arithmetic; four gathers + four table look-ups are in flight per lane.
+template <bool PER, bool SW>
+__device__ __forceinline__ void pair_tz_rows_warp(const PairListDev& L, int k_lo, int k_hi, const StepParams& P,
+                                                  unsigned long long* __restrict__ fbuf, const float4* tab) {
+    constexpr int G = kBlock / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint4* __restrict__ spos = L.spos;
+    const unsigned int* __restrict__ nbr = L.nbr;
+    const int nt = L.ntypes, stride = L.stride;
+    const float rc2 = L.rc2, rsw = L.rsw, inv_sw = L.inv_sw, rsw2 = rsw * rsw;
+    const float kin = L.k_in;
+    int k = k_lo + warp;
+    if (k >= k_hi) return;
+    int n = L.nbr_count[k];
+    int n_in = L.nbr_inner[k];
+    const unsigned int* row = nbr + (size_t)k * stride + lane;
+    unsigned int en[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) en[u] = (u * 32 < n) ? __ldg(row + u * 32) : 0u;
+    for (; k < k_hi; k += G) {
+        const uint4 pi = spos[k];
+        const int trow = (int)(pi.w >> 24) * nt;
+        const unsigned int self = (unsigned int)k | (pi.w & 0xFF000000u);  // rows are padded to 32 with the self entry (r2 = 0)
+        const int kn = k + G;
+        const int n_next = (kn < k_hi) ? L.nbr_count[kn] : 0;
+        const int n_in_next = (kn < k_hi) ? L.nbr_inner[kn] : 0;
+        const unsigned int* row_next = nbr + (size_t)kn * stride + lane;
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        for (int t0 = 0; t0 < n; t0 += 128) {
+            unsigned int e[4];
+            uint4 pj[4];
+            float4 c[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                e[u] = (t0 + u * 32 < n) ? en[u] : self;
+                pj[u] = __ldg(&spos[(int)(e[u] & 0xFFFFFFu)]);
+                c[u] = tab[trow + (int)(e[u] >> 24)];
+            }
+            // request the following group: rest of this row, or the head of the next bead's row
+            if (t0 + 128 < n) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) en[u] = (t0 + 128 + u * 32 < n) ? __ldg(row + t0 + 128 + u * 32) : 0u;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) en[u] = (u * 32 < n_next) ? __ldg(row_next + u * 32) : 0u;
+            }
+            if (t0 + 128 <= n_in) {
+                // the whole group lies in zone A
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    float dx, dy, dz;
+                    delta<PER>(pi, pj[u], P.fscale, dx, dy, dz);
+                    tz_pair_inner(c[u], norm2(dx, dy, dz), dx, dy, dz, kin, fx, fy, fz);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (t0 + u * 32 >= n) break;  // warp-uniform
+                    float dx, dy, dz;
+                    delta<PER>(pi, pj[u], P.fscale, dx, dy, dz);
+                    const float r2 = norm2(dx, dy, dz);
+                    const bool in = (r2 < rc2) && (r2 > 0.f);
+                    tz_pair<SW>(c[u], r2, in, dx, dy, dz, kin, rsw, rsw2, inv_sw, fx, fy, fz);
+                }
+            }
+        }
+        if (n == 0) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) en[u] = (u * 32 < n_next) ? __ldg(row_next + u * 32) : 0u;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        if (lane == 0) add_force_fixed(fbuf, P.n, (int)(pi.w & 0xFFFFFFu), fx, fy, fz);
+        n = n_next;
+        n_in = n_in_next;
+        row = row_next;
+    }
+}
+
+template <bool PER>
+__device__ __forceinline__ void pair_tz_block_staged(const PairListDev& L, int blk, int chunk, const StepParams& P,
+                                                     unsigned long long* __restrict__ fbuf, float* smem) {
+    // dynamic shared memory: [barriers: 2 per warp][coefficient table nt^2 float4][row buffers: 2 x stride per warp]
+    const int nt2 = L.ntypes * L.ntypes;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);
+    float4* sF = reinterpret_cast<float4*>(smem + 2 * 2 * (kBlock / 32));
+    unsigned int* rowbuf = reinterpret_cast<unsigned int*>(sF + nt2);
+    if (threadIdx.x < 2 * (kBlock / 32)) mbar_init(&bars[threadIdx.x], 1);
+    for (int k = threadIdx.x; k < nt2; k += kBlock) sF[k] = L.tabF[k];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const int k_lo = blk * chunk, k_hi = min(L.np, k_lo + chunk);
+    if (L.has_switch) pair_tz_rows_staged<PER, true>(L, k_lo, k_hi, P, fbuf, sF, rowbuf, bars);
+    else pair_tz_rows_staged<PER, false>(L, k_lo, k_hi, P, fbuf, sF, rowbuf, bars);
 }
 
 template <bool PER, int T>
-__device__ __forceinline__ void pair_dh_block(const PairListDev& L, int blk, const StepParams& P,
-                                              const uint4* __restrict__ posq, unsigned long long* __restrict__ fbuf) {
-    constexpr int BPB = kBlock / T;
-    const int a = blk * BPB + threadIdx.x / T, s = threadIdx.x % T;
-    float fx = 0.f, fy = 0.f, fz = 0.f;
-    int i = 0;
-    const bool active = a < L.np;
-    if (active) {
-        i = L.part[a];
-        const uint4 pi = posq[i];
-        const int nt = L.ntypes;
-        const int trow = (int)L.type[a] * nt;
-        const int n = L.nbr_count[a];
-        const unsigned int* __restrict__ row = L.nbr + (size_t)a * L.stride;
-        const float rc2 = L.rc2, ik = L.inv_debye;
-        for (int k = s; k < n; k += T) {
-            const unsigned int e = __ldg(&row[k]);
-            const uint4 pj = __ldg(&posq[e & 0xFFFFFFu]);
-            float dx, dy, dz;
-            delta<PER>(pi, pj, P.fscale, dx, dy, dz);
-            const float r2 = norm2(dx, dy, dz);
-            if (r2 < rc2) {
-                const float qq = __ldg(&L.tabQ[trow + (int)(e >> 24)]);
-                const float ir = rsqrtf(r2);
+__device__ __forceinline__ void pair_tz_block(const PairListDev& L, int blk, int chunk, const StepParams& P,
+                                              unsigned long long* __restrict__ fbuf, float* smem) {
+    const int nt2 = L.ntypes * L.ntypes;
+    const float4* tab = L.tabF;
+    if (L.smem_tab) {
+        float4* sF = reinterpret_cast<float4*>(smem);
+        for (int k = threadIdx.x; k < nt2; k += kBlock) sF[k] = L.tabF[k];
+        __syncthreads();
+        tab = sF;
+    }
+    const int k_lo = blk * chunk, k_hi = min(L.np, k_lo + chunk);
+    if (T == 32 && L.smem_tab) {
+        const float4* sF = reinterpret_cast<const float4*>(smem);
+        if (L.has_switch) pair_tz_rows_warp<PER, true>(L, k_lo, k_hi, P, fbuf, sF);
+        else pair_tz_rows_warp<PER, false>(L, k_lo, k_hi, P, fbuf, sF);
+        return;
+    }
+    if (L.has_switch) pair_tz_rows<PER, T, true>(L, k_lo, k_hi, P, fbuf, tab);
+    else pair_tz_rows<PER, T, false>(L, k_lo, k_hi, P, fbuf, tab);
+}
+
+// screened Coulomb: E = qq (exp(-r/debye)/r - cc)
+template <bool PER, int T>
+__device__ __forceinline__ void pair_dh_block(const PairListDev& L, int blk, int chunk, const StepParams& P,
+                                              unsigned long long* __restrict__ fbuf) {
+    constexpr int G = kBlock / T;
+    const int g = threadIdx.x / T, s = threadIdx.x % T;
+    const uint4* __restrict__ spos = L.spos;
+    const float rc2 = L.rc2, ik = L.inv_debye;
+    const int k_lo = blk * chunk, k_hi = min(L.np, k_lo + chunk);
+    for (int base = k_lo; base < k_hi; base += G) {
+        const int k = base + g;
+        const bool active = k < k_hi;
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        unsigned int wi = 0;
+        if (active) {
+            const uint4 pi = spos[k];
+            wi = (unsigned int)L.bead_of_rank[k];
+            const float qi = __uint_as_float(pi.w);
+            const int n = L.nbr_count[k];
+            const unsigned int* __restrict__ row = L.nbr + (size_t)k * L.stride;
+#pragma unroll 2
+            for (int t = s; t < n; t += T) {
+                const unsigned int e = __ldg(&row[t]);
+                const uint4 pj = __ldg(&spos[(int)(e & 0xFFFFFFu)]);
+                float dx, dy, dz;
+                delta<PER>(pi, pj, P.fscale, dx, dy, dz);
+                const float r2 = norm2(dx, dy, dz);
+                const float qq = qi * __uint_as_float(pj.w);
+                const float ir = fast_rsqrt(r2);
                 const float r = r2 * ir;
                 const float ex = __expf(-r * ik);
-                const float fr = qq * ex * (ir + ik) * ir * ir;
+                float fr = qq * ex * (ir + ik) * ir * ir;
+                fr = (r2 < rc2) ? fr : 0.f;
                 fx = fmaf(fr, dx, fx); fy = fmaf(fr, dy, fy); fz = fmaf(fr, dz, fz);
             }
         }
-    }
 #pragma unroll
-    for (int o = T / 2; o > 0; o >>= 1) {
-        fx += __shfl_xor_sync(0xffffffffu, fx, o);
-        fy += __shfl_xor_sync(0xffffffffu, fy, o);
-        fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        for (int o = T / 2; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        if (active && s == 0) add_force_fixed(fbuf, P.n, (int)(wi & 0xFFFFFFu), fx, fy, fz);
     }
-    if (active && s == 0) add_force_fixed(fbuf, P.n, i, fx, fy, fz);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -500,6 +865,212 @@ __device__ __forceinline__ void spline_eval_dev(const double* y, const double* y
     const double a = (tmin + (k + 1) * h - t) / h, b = 1.0 - a;
     val = a * y[k] + b * y[k + 1] + ((a * a * a - a) * y2[k] + (b * b * b - b) * y2[k + 1]) * h * h / 6.0;
     der = (y[k + 1] - y[k]) / h + ((1.0 - 3.0 * a * a) * y2[k] + (3.0 * b * b - 1.0) * y2[k + 1]) * h / 6.0;
+}
+
+// ---- geometry with gradients (double precision), shared by base stacking and the donor x acceptor terms ----
+// angle at the vertex between a = p_i - p_j and b = p_k - p_j; gi = d(theta)/d(p_i), gk = d(theta)/d(p_k)
+__device__ __forceinline__ double angle_grad(D3 a, D3 b, D3& gi, D3& gk) {
+    const double la = sqrt(d3dot(a, a)), lb = sqrt(d3dot(b, b));
+    double cs = d3dot(a, b) / (la * lb);
+    cs = fmax(-1.0, fmin(1.0, cs));
+    const double sn = sqrt(fmax(1.0 - cs * cs, 1e-24));
+    const double ila = 1.0 / la, ilb = 1.0 / lb, ci = -1.0 / (sn * la), ck = -1.0 / (sn * lb);
+    gi = {ci * (b.x * ilb - cs * a.x * ila), ci * (b.y * ilb - cs * a.y * ila), ci * (b.z * ilb - cs * a.z * ila)};
+    gk = {ck * (a.x * ila - cs * b.x * ilb), ck * (a.y * ila - cs * b.y * ilb), ck * (a.z * ila - cs * b.z * ilb)};
+    return acos(cs);
+}
+// angle between two free vectors U and W with the cosine clamped to +-lim (the reference's
+// "acos(min(max(sin t1 sin t2 cos phi - cos t1 cos t2, -lim), lim))" is exactly the angle between the two
+// bond vectors); gU = d(theta)/dU, gW = d(theta)/dW, zero where the clamp is active
+__device__ __forceinline__ double vector_angle_grad(D3 U, D3 W, double lim, D3& gU, D3& gW) {
+    const double lu = sqrt(d3dot(U, U)), lw = sqrt(d3dot(W, W));
+    const double cs = d3dot(U, W) / (lu * lw);
+    if (cs >= lim || cs <= -lim) {
+        gU = {0, 0, 0}; gW = {0, 0, 0};
+        return acos(cs >= lim ? lim : -lim);
+    }
+    const double sn = sqrt(1.0 - cs * cs);
+    const double ilu = 1.0 / lu, ilw = 1.0 / lw, cu = -1.0 / (sn * lu), cw = -1.0 / (sn * lw);
+    gU = {cu * (W.x * ilw - cs * U.x * ilu), cu * (W.y * ilw - cs * U.y * ilu), cu * (W.z * ilw - cs * U.z * ilu)};
+    gW = {cw * (U.x * ilu - cs * W.x * ilw), cw * (U.y * ilu - cs * W.y * ilw), cw * (U.z * ilu - cs * W.z * ilw)};
+    return acos(cs);
+}
+// dihedral(p1,p2,p3,p4) with OpenMM's sign rule, F = p1-p2, G = p2-p3, H = p4-p3; g1..g4 = d(phi)/d(p1..p4)
+__device__ __forceinline__ double dihedral_grad(D3 Fv, D3 G, D3 H, D3& g1, D3& g2, D3& g3, D3& g4) {
+    const D3 A = d3cross(Fv, G), Bv = d3cross(H, G);
+    const double A2 = d3dot(A, A), B2 = d3dot(Bv, Bv), lG = sqrt(d3dot(G, G));
+    double cs = d3dot(A, Bv) / sqrt(A2 * B2);
+    cs = fmax(-1.0, fmin(1.0, cs));
+    double phi = acos(cs);
+    if (d3dot(Fv, Bv) > 0.0) phi = -phi;
+    const double FG = d3dot(Fv, G), HG = d3dot(H, G);
+    const double ca = lG / A2, cb = lG / B2, ea = FG / (A2 * lG), eb = HG / (B2 * lG);
+    g1 = {-ca * A.x, -ca * A.y, -ca * A.z};
+    g4 = {cb * Bv.x, cb * Bv.y, cb * Bv.z};
+    g2 = {(ca + ea) * A.x - eb * Bv.x, (ca + ea) * A.y - eb * Bv.y, (ca + ea) * A.z - eb * Bv.z};
+    g3 = {-(cb - eb) * Bv.x - ea * A.x, -(cb - eb) * Bv.y - ea * A.y, -(cb - eb) * Bv.z - ea * A.z};
+    return phi;
+}
+// f(x) = 1 for |x| <= pi/2, sin^2 x for |x| <= pi, 0 beyond ("max(f*rect0, rect1)" of the 3SPN.2 / PDNS strings)
+__device__ __forceinline__ void modulation(double xx, double& f, double& df) {
+    const double PI = 3.1415926535897932385, ax = fabs(xx);
+    if (ax <= 0.5 * PI) { f = 1.0; df = 0.0; }
+    else if (ax <= PI) { double sn, cs; sincos(xx, &sn, &cs); f = sn * sn; df = 2.0 * sn * cs; }
+    else { f = 0.0; df = 0.0; }
+}
+// rep = eps (1-e^{-a dr})^2 [dr < 0];  attr = eps (1-e^{-a dr})^2 [dr >= 0] - eps;  and d/d(dr)
+__device__ __forceinline__ void morse_terms(double eps, double alpha, double dr, double& rep, double& drep, double& attr, double& dattr) {
+    const double ex = exp(-alpha * dr), om = 1.0 - ex;
+    const double mval = eps * om * om, dm = 2.0 * eps * alpha * ex * om;
+    if (dr < 0.0) { rep = mval; drep = dm; attr = -eps; dattr = 0.0; }
+    else { rep = 0.0; drep = 0.0; attr = mval - eps; dattr = dm; }
+}
+__device__ __forceinline__ void d3axpy(D3& y, double a, const D3& v) { y.x += a * v.x; y.y += a * v.y; y.z += a * v.z; }
+
+// one donor x acceptor combination: energy, and forces into fbuf when it is non-null
+__device__ __forceinline__ double da_eval(const DATermDev& T, int d, int a, const StepParams& P, const double* __restrict__ x,
+                                          unsigned long long* __restrict__ fbuf) {
+    const bool per = T.periodic != 0;
+    const int d1 = T.donors[3 * d], d2 = T.donors[3 * d + 1], d3 = T.donors[3 * d + 2];
+    const int a1 = T.acceptors[3 * a], a2 = T.acceptors[3 * a + 1], a3 = T.acceptors[3 * a + 2];
+    D3 fd1 = {0, 0, 0}, fd2 = {0, 0, 0}, fd3 = {0, 0, 0}, fa1 = {0, 0, 0}, fa2 = {0, 0, 0}, fa3 = {0, 0, 0};
+    double E;
+    if (T.kind == 0) {
+        // 3SPN.2 base pair, per-donor eps, r0, theta0_1, theta0_2, phi0; g0 = alpha, g1 = K_BP
+        // ThreeSPN2BasePairForceFieldGenerator.cpp:8-26
+        const double* p = T.par + (size_t)d * T.npar;
+        const D3 rv = d3sub(x, d1, a1, per, P);                 // d1 - a1
+        const D3 sd = d3sub(x, d2, d1, per, P);                 // d2 - d1
+        const D3 sa = d3sub(x, a2, a1, per, P);                 // a2 - a1
+        const D3 nrv = {-rv.x, -rv.y, -rv.z};                   // a1 - d1
+        const double r = sqrt(d3dot(rv, rv));
+        D3 g1i, g1k, g2i, g2k, h1, h2, h3, h4;
+        const double th1 = angle_grad(sd, nrv, g1i, g1k);       // angle(d2, d1, a1): vertex d1
+        const double th2 = angle_grad(sa, rv, g2i, g2k);        // angle(a2, a1, d1): vertex a1
+        const double phi = dihedral_grad(sd, rv, sa, h1, h2, h3, h4);  // dihedral(d2, d1, a1, a2)
+        double rep, drep, attr, dattr, f1, df1, f2, df2;
+        morse_terms(p[0], T.g0, r - p[1], rep, drep, attr, dattr);
+        modulation(T.g1 * (th1 - p[2]), f1, df1);
+        modulation(T.g1 * (th2 - p[3]), f2, df2);
+        double sphi, cphi;
+        sincos(phi - p[4], &sphi, &cphi);
+        const double hc = 0.5 * (1.0 + cphi);
+        E = rep + hc * f1 * f2 * attr;
+        if (fbuf) {
+            const double dEdr = drep + hc * f1 * f2 * dattr;
+            const double dE1 = hc * df1 * T.g1 * f2 * attr, dE2 = hc * f1 * df2 * T.g1 * attr, dEp = -0.5 * sphi * f1 * f2 * attr;
+            const double sr = dEdr / r;
+            d3axpy(fd1, -sr, rv); d3axpy(fa1, sr, rv);
+            // theta1: i = d2, vertex d1, k = a1
+            d3axpy(fd2, -dE1, g1i); d3axpy(fa1, -dE1, g1k); d3axpy(fd1, dE1, g1i); d3axpy(fd1, dE1, g1k);
+            // theta2: i = a2, vertex a1, k = d1
+            d3axpy(fa2, -dE2, g2i); d3axpy(fd1, -dE2, g2k); d3axpy(fa1, dE2, g2i); d3axpy(fa1, dE2, g2k);
+            d3axpy(fd2, -dEp, h1); d3axpy(fd1, -dEp, h2); d3axpy(fa1, -dEp, h3); d3axpy(fa2, -dEp, h4);
+        }
+    } else if (T.kind == 1) {
+        // 3SPN.2 cross stacking, per-acceptor eps, r0, theta0_3, theta0_CS; g0 = K_BP, g1 = K_CS, g2 = alpha
+        // ThreeSPN2CrossStackingForceFieldGenerator.cpp:8-31
+        const double* p = T.par + (size_t)a * T.npar;
+        const D3 rv = d3sub(x, d1, a3, per, P);                 // d1 - a3
+        const D3 sd = d3sub(x, d2, d1, per, P);                 // d2 - d1
+        const D3 sa = d3sub(x, a2, a1, per, P);                 // a2 - a1
+        const D3 nrv = {-rv.x, -rv.y, -rv.z};                   // a3 - d1
+        const double r = sqrt(d3dot(rv, rv));
+        D3 gci, gck, gU, gW;
+        const double tcs = angle_grad(sd, nrv, gci, gck);       // angle(d2, d1, a3): vertex d1
+        const double t3 = vector_angle_grad(sd, sa, 0.99, gU, gW);
+        double rep, drep, attr, dattr, f3, df3, fc, dfc;
+        morse_terms(p[0], T.g2, r - p[1], rep, drep, attr, dattr);
+        modulation(T.g0 * (t3 - p[2]), f3, df3);
+        modulation(T.g1 * (tcs - p[3]), fc, dfc);
+        E = 0.5 * f3 * fc * attr;
+        if (fbuf) {
+            const double dEdr = 0.5 * f3 * fc * dattr, dE3 = 0.5 * df3 * T.g0 * fc * attr, dEc = 0.5 * f3 * dfc * T.g1 * attr;
+            const double sr = dEdr / r;
+            d3axpy(fd1, -sr, rv); d3axpy(fa3, sr, rv);
+            d3axpy(fd2, -dEc, gci); d3axpy(fa3, -dEc, gck); d3axpy(fd1, dEc, gci); d3axpy(fd1, dEc, gck);
+            d3axpy(fd2, -dE3, gU); d3axpy(fd1, dE3, gU); d3axpy(fa2, -dE3, gW); d3axpy(fa1, dE3, gW);
+        }
+    } else {
+        // PDNS, per-donor k, r0, theta0, phi0; g0 = sigma, g1 = delta   ProteinDNANonSpecificForceFieldGenerator.cpp:60-83
+        const double* p = T.par + (size_t)d * T.npar;
+        const double K = 3.1415926535897932385 / (2.0 * T.g1);
+        const D3 rv = d3sub(x, d2, a1, per, P);                 // d2 - a1  (CA - P)
+        const D3 uu = d3sub(x, d1, d3, per, P);                 // d1 - d3  (CA_N - CA_C)
+        const D3 sa = d3sub(x, a2, a1, per, P);                 // a2 - a1  (S3' - P)
+        const double r = sqrt(d3dot(rv, rv));
+        D3 gU, gW, gpi, gpk;
+        const double th = vector_angle_grad(uu, rv, 0.99999, gU, gW);
+        const double ph = angle_grad(rv, sa, gpi, gpk);         // angle(d2, a1, a2): vertex a1
+        const double dr = r - p[1], is2 = 1.0 / (T.g0 * T.g0);
+        const double fr = exp(-0.5 * dr * dr * is2);
+        double gt, dgt, gp, dgp;
+        modulation(K * (th - p[2]), gt, dgt);
+        modulation(K * (ph - p[3]), gp, dgp);
+        E = -p[0] * fr * gt * gp;
+        if (fbuf) {
+            const double dEdr = p[0] * dr * is2 * fr * gt * gp, dEt = -p[0] * fr * dgt * K * gp, dEp = -p[0] * fr * gt * dgp * K;
+            const double sr = dEdr / r;
+            d3axpy(fd2, -sr, rv); d3axpy(fa1, sr, rv);
+            d3axpy(fd1, -dEt, gU); d3axpy(fd3, dEt, gU); d3axpy(fd2, -dEt, gW); d3axpy(fa1, dEt, gW);
+            d3axpy(fd2, -dEp, gpi); d3axpy(fa2, -dEp, gpk); d3axpy(fa1, dEp, gpi); d3axpy(fa1, dEp, gpk);
+        }
+    }
+    if (fbuf) {
+        add_force_fixed_d(fbuf, P.n, d1, fd1.x, fd1.y, fd1.z);
+        add_force_fixed_d(fbuf, P.n, d2, fd2.x, fd2.y, fd2.z);
+        add_force_fixed_d(fbuf, P.n, a1, fa1.x, fa1.y, fa1.z);
+        add_force_fixed_d(fbuf, P.n, a2, fa2.x, fa2.y, fa2.z);
+        if (T.kind == 2) add_force_fixed_d(fbuf, P.n, d3, fd3.x, fd3.y, fd3.z);
+        if (T.kind == 1) add_force_fixed_d(fbuf, P.n, a3, fa3.x, fa3.y, fa3.z);
+    }
+    return E;
+}
+
+// canonical donor-acceptor distance test, identical (operation for operation) to the oracle's for_each_da
+__device__ __forceinline__ double da_r2(const DATermDev& T, int d, int a, const StepParams& P, const double* __restrict__ x) {
+    const int i = T.donors[3 * d], j = T.acceptors[3 * a];
+    double dx = __dsub_rn(x[3 * i], x[3 * j]), dy = __dsub_rn(x[3 * i + 1], x[3 * j + 1]), dz = __dsub_rn(x[3 * i + 2], x[3 * j + 2]);
+    if (T.periodic) {
+        dx = __dsub_rn(dx, __dmul_rn(P.box[0], nearbyint(__ddiv_rn(dx, P.box[0]))));
+        dy = __dsub_rn(dy, __dmul_rn(P.box[1], nearbyint(__ddiv_rn(dy, P.box[1]))));
+        dz = __dsub_rn(dz, __dmul_rn(P.box[2], nearbyint(__ddiv_rn(dz, P.box[2]))));
+    }
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// Verlet list of donor x acceptor combinations inside cutoff + skin (one thread per candidate)
+__global__ void da_build_kernel(DAListDev D, StepParams P, const double* __restrict__ x, int* __restrict__ flags) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= D.ncand) return;
+    int t = 0;
+    while (t + 1 < D.nterms && c >= D.terms[t + 1].cand_begin) t++;
+    const DATermDev& T = D.terms[t];
+    const long long local = c - T.cand_begin;
+    const int d = (int)(local / T.na), a = (int)(local % T.na);
+    if (!(da_r2(T, d, a, P, x) < T.rlist2)) return;
+    const unsigned long long key = (unsigned long long)d * (unsigned long long)T.na + (unsigned long long)a;
+    int lo = 0, hi = T.nexcl;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (T.excl[mid] < key) lo = mid + 1; else hi = mid; }
+    if (lo < T.nexcl && T.excl[lo] == key) return;
+    const unsigned int pos = atomicAdd(D.count, 1u);
+    if (pos < (unsigned int)D.capacity) D.entries[pos] = make_uint2(((unsigned int)t << 24) | (unsigned int)d, (unsigned int)a);
+    else flags[FLAG_DA_OVERFLOW] = 1;
+}
+
+// (donor, acceptor) combinations of term `term` inside the interaction cutoff at the current positions
+__global__ void da_extract_kernel(DAListDev D, int term, StepParams P, const double* __restrict__ x, int* __restrict__ out,
+                                  long long capacity, unsigned long long* __restrict__ counter) {
+    const unsigned int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= min(*D.count, (unsigned int)D.capacity)) return;
+    const uint2 e = D.entries[m];
+    if ((int)(e.x >> 24) != term) return;
+    const DATermDev& T = D.terms[term];
+    const int d = (int)(e.x & 0xFFFFFFu), a = (int)e.y;
+    if (da_r2(T, d, a, P, x) < T.rc2) {
+        const unsigned long long pos = atomicAdd(counter, 1ull);
+        if (out && (long long)pos < capacity) { out[2 * pos] = d; out[2 * pos + 1] = a; }
+    }
 }
 
 // E and dE/dq (q = r, theta or phi) of one bonded term; formulas cite the reference generators
@@ -568,6 +1139,28 @@ __device__ __forceinline__ double bonded_term(int kind, const BondedDev& B, int 
     const double* p = B.par + (size_t)m * B.npar;
     const double* tab = B.tabs + (size_t)(meta >> 16) * 24;
     double E, dE;
+    if (kind == 9) {
+        // 3SPN.2 base stacking, p = eps, r0, theta0, alpha, K_BS   ThreeSPN2BaseStackingForceFieldGenerator.cpp:6-21
+        const int i = B.idx[3 * m], j = B.idx[3 * m + 1], k = B.idx[3 * m + 2];
+        const D3 a = d3sub(x, i, j, per, P), b = d3sub(x, k, j, per, P);
+        D3 gi, gk;
+        const double lb = sqrt(d3dot(b, b));
+        const double th = angle_grad(a, b, gi, gk);
+        double rep, drep, attr, dattr, f, df;
+        morse_terms(p[0], p[3], lb - p[1], rep, drep, attr, dattr);
+        modulation(p[4] * (th - p[2]), f, df);
+        E = rep + f * attr;
+        if (fbuf) {
+            const double dEdr = drep + f * dattr, dEdth = df * p[4] * attr;
+            const double sr = dEdr / lb;  // d|b|/dp_k = b/|b|, d|b|/dp_j = -b/|b|
+            const D3 fi = {-dEdth * gi.x, -dEdth * gi.y, -dEdth * gi.z};
+            const D3 fk = {-dEdth * gk.x - sr * b.x, -dEdth * gk.y - sr * b.y, -dEdth * gk.z - sr * b.z};
+            add_force_fixed_d(fbuf, P.n, i, fi.x, fi.y, fi.z);
+            add_force_fixed_d(fbuf, P.n, k, fk.x, fk.y, fk.z);
+            add_force_fixed_d(fbuf, P.n, j, -fi.x - fk.x, -fi.y - fk.y, -fi.z - fk.z);
+        }
+        return E;
+    }
     if (kind <= 3) {
         const int i = B.idx[2 * m], j = B.idx[2 * m + 1];
         const D3 d = d3sub(x, i, j, per, P);
@@ -624,13 +1217,11 @@ __device__ __forceinline__ double bonded_term(int kind, const BondedDev& B, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// the fused per-step force launch
+// the fused per-step pair-force launch: every pair list in one grid (block ranges map to lists)
 template <bool PER>
-__global__ void __launch_bounds__(kBlock) force_kernel(const WorkSeg* __restrict__ segs, int nsegs,
+__global__ void __launch_bounds__(kBlock, OCM_FORCE_MINBLOCKS) force_kernel(const WorkSeg* __restrict__ segs, int nsegs,
                                                        const PairListDev* __restrict__ lists,
-                                                       const BondedDev* __restrict__ bonded, StepParams P,
-                                                       const uint4* __restrict__ posq, const double* __restrict__ x,
-                                                       unsigned long long* __restrict__ fbuf) {
+                                                       StepParams P, unsigned long long* __restrict__ fbuf) {
     extern __shared__ __align__(16) float smem[];
     int s = 0;
     while (s + 1 < nsegs && (int)blockIdx.x >= segs[s + 1].block_begin) s++;
@@ -638,28 +1229,41 @@ __global__ void __launch_bounds__(kBlock) force_kernel(const WorkSeg* __restrict
     const int blk = blockIdx.x - sg.block_begin;
     if (sg.kind == SEG_PAIR_TZ) {
         const PairListDev& L = lists[sg.id];
-        if (L.smem_tab) {
-            switch (sg.tpb) {
-                case 4: pair_tz_block<PER, 4, true>(L, blk, P, posq, fbuf, smem); break;
-                case 8: pair_tz_block<PER, 8, true>(L, blk, P, posq, fbuf, smem); break;
-                case 16: pair_tz_block<PER, 16, true>(L, blk, P, posq, fbuf, smem); break;
-                default: pair_tz_block<PER, 32, true>(L, blk, P, posq, fbuf, smem);
-            }
-        } else {
-            switch (sg.tpb) {
-                case 4: pair_tz_block<PER, 4, false>(L, blk, P, posq, fbuf, smem); break;
-                case 8: pair_tz_block<PER, 8, false>(L, blk, P, posq, fbuf, smem); break;
-                case 16: pair_tz_block<PER, 16, false>(L, blk, P, posq, fbuf, smem); break;
-                default: pair_tz_block<PER, 32, false>(L, blk, P, posq, fbuf, smem);
-            }
+        if (sg.staged) { pair_tz_block_staged<PER>(L, blk, sg.chunk, P, fbuf, smem); return; }
+        switch (sg.tpb) {
+            case 4: pair_tz_block<PER, 4>(L, blk, sg.chunk, P, fbuf, smem); break;
+            case 8: pair_tz_block<PER, 8>(L, blk, sg.chunk, P, fbuf, smem); break;
+            case 16: pair_tz_block<PER, 16>(L, blk, sg.chunk, P, fbuf, smem); break;
+            default: pair_tz_block<PER, 32>(L, blk, sg.chunk, P, fbuf, smem);
         }
     } else if (sg.kind == SEG_PAIR_DH) {
         const PairListDev& L = lists[sg.id];
         switch (sg.tpb) {
-            case 4: pair_dh_block<PER, 4>(L, blk, P, posq, fbuf); break;
-            case 8: pair_dh_block<PER, 8>(L, blk, P, posq, fbuf); break;
-            case 16: pair_dh_block<PER, 16>(L, blk, P, posq, fbuf); break;
-            default: pair_dh_block<PER, 32>(L, blk, P, posq, fbuf);
+            case 4: pair_dh_block<PER, 4>(L, blk, sg.chunk, P, fbuf); break;
+            case 8: pair_dh_block<PER, 8>(L, blk, sg.chunk, P, fbuf); break;
+            case 16: pair_dh_block<PER, 16>(L, blk, sg.chunk, P, fbuf); break;
+            default: pair_dh_block<PER, 32>(L, blk, sg.chunk, P, fbuf);
+        }
+    }
+}
+
+// bonded terms + donor x acceptor terms (double precision, one thread per term).  Launched beside force_kernel on
+// a forked graph branch: the pair kernel keeps its own tight register budget and the two overlap.
+template <bool PER>
+__global__ void __launch_bounds__(kBlock) local_kernel(const WorkSeg* __restrict__ segs, int nsegs,
+                                                       const BondedDev* __restrict__ bonded, DAListDev da, StepParams P,
+                                                       const double* __restrict__ x, unsigned long long* __restrict__ fbuf) {
+    int s = 0;
+    while (s + 1 < nsegs && (int)blockIdx.x >= segs[s + 1].block_begin - segs[0].block_begin) s++;
+    const WorkSeg sg = segs[s];
+    const int blk = blockIdx.x - (sg.block_begin - segs[0].block_begin);
+    if (sg.kind == SEG_DA) {
+        const unsigned int m = blk * kBlock + threadIdx.x;
+        if (m < min(*da.count, (unsigned int)da.capacity)) {
+            const uint2 e = da.entries[m];
+            const DATermDev& T = da.terms[e.x >> 24];
+            const int d = (int)(e.x & 0xFFFFFFu), a = (int)e.y;
+            if (da_r2(T, d, a, P, x) < T.rc2) da_eval(T, d, a, P, x, fbuf);
         }
     } else {
         const BondedDev& B = bonded[sg.id];
@@ -698,6 +1302,7 @@ __device__ __forceinline__ void normals3(uint4 o, float& g0, float& g1, float& g
 // unless this is the last step before a rebuild.
 __global__ void integrate_kernel(StepParams P, double* __restrict__ x, float4* __restrict__ v,
                                  unsigned long long* __restrict__ fbuf, uint4* __restrict__ posq,
+                                 const PairListDev* __restrict__ lists, int nlists,
                                  const double* __restrict__ xref, unsigned long long* __restrict__ step_base,
                                  int step_offset, int window, int last_in_window, int* __restrict__ flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -728,6 +1333,15 @@ __global__ void integrate_kernel(StepParams P, double* __restrict__ x, float4* _
             else { q.x = __float_as_uint((float)px); q.y = __float_as_uint((float)py); q.z = __float_as_uint((float)pz); }
             q.w = 0;
             posq[i] = q;
+            // refresh the cell-sorted copies the pair kernels read (w keeps bead | type)
+            for (int l = 0; l < nlists; l++) {
+                const int k = lists[l].rank_of_bead[i];
+                if (k >= 0) {
+                    uint4* sp = lists[l].spos + k;
+                    q.w = sp->w;
+                    *sp = q;
+                }
+            }
             const float ex = (float)(px - xref[3 * i]), ey = (float)(py - xref[3 * i + 1]), ez = (float)(pz - xref[3 * i + 2]);
             d2 = ex * ex + ey * ey + ez * ez;
             if (!(d2 == d2) || !(fx == fx)) flags[FLAG_NAN] = 1;
@@ -778,47 +1392,57 @@ __device__ __forceinline__ void block_add(double val, double* target) {
 template <bool PER>
 __global__ void __launch_bounds__(kBlock) energy_kernel(const WorkSeg* __restrict__ segs, int nsegs,
                                                         const PairListDev* __restrict__ lists,
-                                                        const BondedDev* __restrict__ bonded, StepParams P,
-                                                        const uint4* __restrict__ posq, const double* __restrict__ x,
-                                                        double* __restrict__ egroup) {
+                                                        const BondedDev* __restrict__ bonded, DAListDev da, StepParams P,
+                                                        const double* __restrict__ x, double* __restrict__ egroup) {
     int s = 0;
     while (s + 1 < nsegs && (int)blockIdx.x >= segs[s + 1].block_begin) s++;
     const WorkSeg sg = segs[s];
     const int blk = blockIdx.x - sg.block_begin;
-    if (sg.kind == SEG_BONDED) {
-        const BondedDev& B = bonded[sg.id];
-        const int m = blk * kBlock + threadIdx.x;
+    if (sg.kind == SEG_BONDED || sg.kind == SEG_DA) {
         double E = 0.0;
-        int g = 0;
-        if (m < B.n) E = bonded_term(sg.id, B, m, P, x, nullptr, &g);
-        // terms of one kind may belong to different groups: accumulate per distinct group
+        int g = -1;
+        if (sg.kind == SEG_BONDED) {
+            const BondedDev& B = bonded[sg.id];
+            const int m = blk * kBlock + threadIdx.x;
+            if (m < B.n) E = bonded_term(sg.id, B, m, P, x, nullptr, &g);
+        } else {
+            const unsigned int m = blk * kBlock + threadIdx.x;
+            if (m < min(*da.count, (unsigned int)da.capacity)) {
+                const uint2 e = da.entries[m];
+                const DATermDev& T = da.terms[e.x >> 24];
+                const int d = (int)(e.x & 0xFFFFFFu), a = (int)e.y;
+                if (da_r2(T, d, a, P, x) < T.rc2) { E = da_eval(T, d, a, P, x, nullptr); g = T.group; }
+            }
+        }
+        // terms handled by one block may belong to different groups: accumulate per distinct group
         for (int gg = 0; gg < 32; gg++) {
-            const unsigned int any = __syncthreads_or(m < B.n && g == gg);
-            if (any) block_add((m < B.n && g == gg) ? E : 0.0, &egroup[gg]);
+            const unsigned int any = __syncthreads_or(g == gg);
+            if (any) block_add((g == gg) ? E : 0.0, &egroup[gg]);
         }
         return;
     }
     const PairListDev& L = lists[sg.id];
-    const int T = sg.tpb, BPB = kBlock / T;
-    const int a = blk * BPB + threadIdx.x / T, sl = threadIdx.x % T;
+    const int T = sg.tpb, G = kBlock / T;
+    const int g = threadIdx.x / T, sl = threadIdx.x % T;
     double Em[kMaxMembers] = {0, 0, 0, 0};
-    if (a < L.np) {
-        const int i = L.part[a];
-        const uint4 pi = posq[i];
-        const int nt = L.ntypes, nt2 = nt * nt;
-        const int trow = (int)L.type[a] * nt;
-        const int n = L.nbr_count[a];
-        const unsigned int* row = L.nbr + (size_t)a * L.stride;
-        for (int k = sl; k < n; k += T) {
-            const unsigned int e = row[k];
+    const int k_lo = blk * sg.chunk, k_hi = min(L.np, k_lo + sg.chunk);
+    for (int k = k_lo + g; k < k_hi; k += G) {
+        const uint4 pi = L.spos[k];
+        const int nt = L.ntypes;
+        const int trow = (int)(pi.w >> 24) * nt;
+        const int n = L.nbr_count[k];
+        const unsigned int* row = L.nbr + (size_t)k * L.stride;
+        for (int t = sl; t < n; t += T) {
+            const unsigned int e = row[t];
+            const uint4 pj = L.spos[e & 0xFFFFFFu];
             float dx, dy, dz;
-            delta<PER>(pi, posq[e & 0xFFFFFFu], P.fscale, dx, dy, dz);
+            delta<PER>(pi, pj, P.fscale, dx, dy, dz);
             const float r2 = norm2(dx, dy, dz);
             const int ti = trow + (int)(e >> 24);
             if (sg.kind == SEG_PAIR_DH) {
                 if (r2 < L.rc2) {
                     const float ir = rsqrtf(r2), r = r2 * ir;
-                    Em[0] += (double)(L.tabQ[ti] * (__expf(-r * L.inv_debye) * ir - L.dh_cc));
+                    Em[0] += (double)(__uint_as_float(pi.w) * __uint_as_float(pj.w) * (__expf(-r * L.inv_debye) * ir - L.dh_cc));
                 }
             } else {
                 for (int m = 0; m < L.nmem; m++) {
@@ -859,21 +1483,22 @@ __global__ void kinetic_kernel(StepParams P, const float4* __restrict__ v, const
 
 // pairs (i<j) of list `li` inside rc2_term, appended unordered (host sorts)
 template <bool PER>
-__global__ void extract_pairs_kernel(const PairListDev* lists, int li, StepParams P, const uint4* __restrict__ posq,
-                                     float rc2_term, int* __restrict__ out, long long capacity,
-                                     unsigned long long* __restrict__ counter) {
+__global__ void extract_pairs_kernel(const PairListDev* lists, int li, StepParams P, float rc2_term,
+                                     int* __restrict__ out, long long capacity, unsigned long long* __restrict__ counter) {
     const PairListDev& L = lists[li];
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= L.np) return;
-    const int i = L.part[a];
-    const uint4 pi = posq[i];
-    const int n = L.nbr_count[a];
-    const unsigned int* row = L.nbr + (size_t)a * L.stride;
-    for (int k = 0; k < n; k++) {
-        const int j = (int)(row[k] & 0xFFFFFFu);
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L.np) return;
+    const uint4 pi = L.spos[k];
+    const int i = L.bead_of_rank[k];
+    const int n = L.nbr_count[k];
+    const unsigned int* row = L.nbr + (size_t)k * L.stride;
+    for (int t = 0; t < n; t++) {
+        const int kj = (int)(row[t] & 0xFFFFFFu);
+        const uint4 pj = L.spos[kj];
+        const int j = L.bead_of_rank[kj];
         if (j <= i) continue;
         float dx, dy, dz;
-        delta<PER>(pi, posq[j], P.fscale, dx, dy, dz);
+        delta<PER>(pi, pj, P.fscale, dx, dy, dz);
         if (norm2(dx, dy, dz) < rc2_term) {
             const unsigned long long pos = atomicAdd(counter, 1ull);
             if (out && (long long)pos < capacity) { out[2 * pos] = i; out[2 * pos + 1] = j; }

@@ -67,13 +67,15 @@ struct PairListHost {
     double rc_list = 0;      // largest effective cutoff of the members
     std::vector<double> rc_eff;  // per member
     // device storage
-    DevBuf<int> part, excl_off, excl_idx, cell_of_slot, cell_count, cell_start, cell_cursor, sorted_slots, nbr_count;
+    DevBuf<int> part, excl_off, excl_idx, cell_of_slot, cell_count, cell_start, cell_cursor, tmp_slots, sorted_slots,
+        rank_of_bead, bead_of_rank, nbr_count, nbr_inner;
+    DevBuf<uint4> spos;
+    DevBuf<float> qscaled;
     DevBuf<unsigned char> type;
     DevBuf<signed char> cls;
     DevBuf<unsigned int> nbr;
     DevBuf<GridDev> grid;
     DevBuf<float4> tabF;
-    DevBuf<float> tabA2, tabQ;
     DevBuf<float4> memE[kMaxMembers];
     PairListDev dev{};       // host mirror of the device descriptor
     int max_cells = 0;
@@ -110,16 +112,30 @@ struct ocm_context {
     DevBuf<int> b_idx[B_NUM_KINDS], b_meta[B_NUM_KINDS];
     DevBuf<double> b_par[B_NUM_KINDS], b_tabs;
     DevBuf<BondedDev> d_bonded;
+    // donor x acceptor terms
+    std::vector<DATermDev> da_terms_h;
+    std::vector<std::unique_ptr<DevBuf<int>>> da_idx;
+    std::vector<std::unique_ptr<DevBuf<double>>> da_par;
+    std::vector<std::unique_ptr<DevBuf<unsigned long long>>> da_excl;
+    DevBuf<DATermDev> d_da_terms;
+    DevBuf<unsigned int> da_count;
+    DevBuf<uint2> da_entries;
+    DAListDev da{};
+    double da_rcmax = 0;
     std::vector<WorkSeg> segs;
     DevBuf<WorkSeg> d_segs;
-    int total_blocks = 0;
+    int total_blocks = 0, pair_blocks = 0, local_blocks = 0, n_pair_segs = 0, n_local_segs = 0;
     size_t smem_bytes = 0;
+    cudaStream_t side = nullptr;            // forked branch: bonded + donor-acceptor kernel beside the pair kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     // options
     double skin = 0.3;
     int nstlist_fixed = 0;   // 0 = adaptive
     int nst = 10;
     int tpb_opt = 0;         // 0 = auto
+    int chunk_opt = 0;       // beads per block of the pair kernels, 0 = auto
+    int staging_opt = 0;     // stage Verlet rows in shared memory with bulk async copies
     bool lists_ready = false, positions_set = false, lists_current = false;
     std::map<int, cudaGraphExec_t> graphs;
     // counters
@@ -130,6 +146,9 @@ struct ocm_context {
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (side) cudaStreamDestroy(side);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -194,9 +213,10 @@ static void plan_lists(ocm_context* c) {
                 bool partner = (o.kind == P_LJREP && pt.kind == P_LJATT) || (o.kind == P_LJATT && pt.kind == P_LJREP);
                 if (!partner || !same_topology(o, pt)) continue;
                 bool same_sigma = true;
-                for (int i : pt.part) if (o.p1[i] != pt.p1[i]) { same_sigma = false; break; }
                 const PairTerm& rep = (o.kind == P_LJREP) ? o : pt;
                 const PairTerm& att = (o.kind == P_LJREP) ? pt : o;
+                // the fused table stores the repulsive coefficients and the ratio eps_att/eps_rep
+                for (int i : pt.part) if (o.p1[i] != pt.p1[i] || !(rep.p0[i] > 0)) { same_sigma = false; break; }
                 // the repulsive term must be zero beyond its zone inside both cutoffs, and the switch
                 // must start outside the zone
                 double zone = effective_rc(rep);
@@ -223,7 +243,7 @@ static void compile_list(ocm_context* c, PairListHost& L) {
     std::map<std::vector<double>, int> ids;
     std::vector<int> rep_bead;
     std::vector<unsigned char> type(L.np);
-    for (int a = 0; a < L.np; a++) {
+    for (int a = 0; a < L.np && L.form != SEG_PAIR_DH; a++) {
         int i = t0.part[a];
         std::vector<double> key;
         for (int m = 0; m < nm; m++) { key.push_back(pairs[L.terms[m]].p0[i]); key.push_back(pairs[L.terms[m]].p1[i]); }
@@ -274,16 +294,39 @@ static void compile_list(ocm_context* c, PairListHost& L) {
     D.rc2 = (float)(L.rc_list * L.rc_list);
     D.rsw = (float)L.rc_list; D.inv_sw = 0.f; D.has_switch = 0;
     if (L.form == SEG_PAIR_DH) {
-        std::vector<float> tq(nt2);
-        for (int a = 0; a < nt; a++)
-            for (int b = 0; b < nt; b++) tq[a * nt + b] = (float)(t0.p0[rep_bead[a]] * t0.p0[rep_bead[b]] * t0.g0);
-        if (rep_bead.empty()) tq.assign(1, 0.f);
-        L.tabQ.upload(tq);
+        // the charges ride in the w slot of the cell-sorted positions, pre-scaled so that w_i w_j = K q_i q_j
+        if (!(t0.g0 >= 0)) throw std::runtime_error("debye_huckel: the Coulomb constant must not be negative");
+        std::vector<float> qs(std::max(L.np, 1), 0.f);
+        const double sk = std::sqrt(t0.g0);
+        for (int a = 0; a < L.np; a++) qs[a] = (float)(t0.p0[t0.part[a]] * sk);
+        L.qscaled.upload(qs);
+        D.qscaled = L.qscaled.p;
         D.inv_debye = (float)(1.0 / t0.g1); D.dh_cc = (float)t0.g2;
         D.mem_group[0] = t0.group; D.mem_rc2[0] = D.rc2;
     } else {
-        std::vector<float4> tf(nt2, make_float4(0, 0, 0, 0));
-        std::vector<float> ta(nt2, INFINITY);
+        // force table: {12 c12, 6 c6, a2, w}; zone factor = r^2 < a2 ? k_in : k_out + k_w w
+        std::vector<float4> tf(nt2, make_float4(0, 0, INFINITY, 0));
+        const PairTerm* rep = nullptr; const PairTerm* att = nullptr;
+        if (nm == 2) {
+            rep = &pairs[L.terms[0]]; att = &pairs[L.terms[1]];
+            if (rep->kind != P_LJREP) std::swap(rep, att);
+            D.k_in = 1.f;
+        } else if (nm == 1) {
+            D.k_in = (t0.kind == P_LJATT) ? 0.f : 1.f;
+        } else throw std::runtime_error("internal: unsupported pair-list fusion");
+        for (int a = 0; a < nt && !rep_bead.empty(); a++)
+            for (int b = 0; b < nt; b++) {
+                const int k = a * nt + b;
+                if (nm == 2) {
+                    TZ zr = tz_coeffs(*rep, rep_bead[a], rep_bead[b]), za = tz_coeffs(*att, rep_bead[a], rep_bead[b]);
+                    tf[k] = make_float4((float)(12.0 * zr.c12i), (float)(6.0 * zr.c6i), (float)zr.a2, (float)(za.c12o / zr.c12i));
+                } else {
+                    TZ z = tz_coeffs(t0, rep_bead[a], rep_bead[b]);
+                    // w = factor of the outer zone: LJ-attractive alone acts only there, the others vanish there
+                    if (t0.kind == P_LJATT) tf[k] = make_float4((float)(12.0 * z.c12o), (float)(6.0 * z.c6o), (float)z.a2, 1.f);
+                    else tf[k] = make_float4((float)(12.0 * z.c12i), (float)(6.0 * z.c6i), std::isfinite(z.a2) ? (float)z.a2 : INFINITY, 0.f);
+                }
+            }
         for (int m = 0; m < nm; m++) {
             const PairTerm& t = pairs[L.terms[m]];
             std::vector<float4> te(2 * nt2, make_float4(0, 0, 0, 0));
@@ -291,8 +334,6 @@ static void compile_list(ocm_context* c, PairListHost& L) {
                 for (int b = 0; b < nt; b++) {
                     TZ z = tz_coeffs(t, rep_bead[a], rep_bead[b]);
                     int k = a * nt + b;
-                    tf[k].x += (float)z.c12i; tf[k].y += (float)z.c6i; tf[k].z += (float)z.c12o; tf[k].w += (float)z.c6o;
-                    if (std::isfinite(z.a2)) ta[k] = (float)z.a2;
                     te[2 * k] = make_float4((float)z.c12i, (float)z.c6i, (float)z.c0i, (float)z.a2);
                     te[2 * k + 1] = make_float4((float)z.c12o, (float)z.c6o, (float)z.c0o, 0.f);
                 }
@@ -305,15 +346,21 @@ static void compile_list(ocm_context* c, PairListHost& L) {
                 D.has_switch = 1; D.rsw = (float)t.rsw; D.inv_sw = (float)(1.0 / (t.rc - t.rsw));
             }
         }
-        L.tabF.upload(tf); L.tabA2.upload(ta);
+        L.tabF.upload(tf);
     }
     D.part = L.part.p; D.type = L.type.p; D.cls = L.cls.p;
     D.excl_off = L.excl_off.p; D.excl_idx = L.excl_idx.p;
-    D.tabF = L.tabF.p; D.tabA2 = L.tabA2.p; D.tabQ = L.tabQ.p;
+    D.tabF = L.tabF.p;
     D.smem_tab = (L.form == SEG_PAIR_TZ && nt <= 64) ? 1 : 0;
-    L.cell_of_slot.alloc(std::max(L.np, 1)); L.sorted_slots.alloc(std::max(L.np, 1)); L.nbr_count.alloc(std::max(L.np, 1));
-    L.nbr_count.zero();
-    D.cell_of_slot = L.cell_of_slot.p; D.sorted_slots = L.sorted_slots.p; D.nbr_count = L.nbr_count.p;
+    const size_t np1 = (size_t)std::max(L.np, 1);
+    L.cell_of_slot.alloc(np1); L.tmp_slots.alloc(np1); L.sorted_slots.alloc(np1); L.nbr_count.alloc(np1); L.spos.alloc(np1);
+    L.bead_of_rank.alloc(np1); L.nbr_inner.alloc(np1);
+    L.rank_of_bead.alloc(c->n);
+    L.nbr_count.zero(); L.nbr_inner.zero(); L.spos.zero(); L.bead_of_rank.zero();
+    D.bead_of_rank = L.bead_of_rank.p; D.nbr_inner = L.nbr_inner.p;
+    CUDA_TRY(cudaMemset(L.rank_of_bead.p, 0xFF, (size_t)c->n * sizeof(int)));
+    D.cell_of_slot = L.cell_of_slot.p; D.tmp_slots = L.tmp_slots.p; D.sorted_slots = L.sorted_slots.p; D.nbr_count = L.nbr_count.p;
+    D.spos = L.spos.p; D.rank_of_bead = L.rank_of_bead.p;
 }
 
 // (re)derive everything that depends on the skin: list radius, cell grid
@@ -322,6 +369,14 @@ static void configure_grid(ocm_context* c, PairListHost& L) {
     const double rlist = L.rc_list + c->skin;
     D.rlist2 = (float)(rlist * rlist);
     D.wmin = 0.5f * (float)rlist;
+    {
+        // build-time distance zones of a row (see build_list_kernel).  A is a guarantee (pairs cannot leave it before
+        // the next rebuild), the others only order the row so that warp-uniform votes can skip work.
+        const double r_hi = L.rc_list, r_lo = D.has_switch ? (double)D.rsw : L.rc_list, d = 0.25 * c->skin;
+        const double za = std::max(0.0, r_lo - c->skin), zb = std::max(za, r_lo - d), zc = r_hi + d;
+        D.zone_a2 = (L.form == SEG_PAIR_TZ) ? (float)(za * za) * (1.f - 1e-6f) : 0.f;
+        D.zone_b2 = (float)(zb * zb); D.zone_c2 = (float)(zc * zc);
+    }
     GridDev g{};
     for (int k = 0; k < 3; k++) { g.bmin[k] = 0x7FFFFFFF; g.bmax[k] = (int)0x80000000; g.lo[k] = 0.f; }
     if (c->periodic) {
@@ -356,10 +411,8 @@ static void upload_lists(ocm_context* c) {
 
 static int pick_tpb(const ocm_context* c, const PairListHost& L) {
     if (c->tpb_opt == 4 || c->tpb_opt == 8 || c->tpb_opt == 16 || c->tpb_opt == 32) return c->tpb_opt;
-    // enough warps to fill 148 SMs x 16 resident warps, but not more lanes per bead than useful
-    const double lanes_wanted = 148.0 * 16 * 32;
+    // one warp per bead unless the rows are too short to keep 32 lanes busy
     int t = 32;
-    while (t > 4 && (double)L.np * t > 4.0 * lanes_wanted) t >>= 1;
     if (L.stride > 0) while (t > 4 && L.stride < 4 * t) t >>= 1;
     return t;
 }
@@ -372,26 +425,45 @@ static void build_segments(ocm_context* c) {
         auto& L = *c->lists[l];
         if (L.np == 0) continue;
         L.tpb = pick_tpb(c, L);
-        int bpb = kBlock / L.tpb;
-        int nb = (L.np + bpb - 1) / bpb;
-        c->segs.push_back({blk, nb, L.form, (int)l, L.tpb});
+        // a block owns `chunk` consecutive ranks of the cell-sorted order (spatially compact: rows overlap in L1,
+        // one coefficient-table load per block); about 16 blocks per SM for load balance
+        const int gpb = kBlock / L.tpb;
+        int chunk = c->chunk_opt > 0 ? c->chunk_opt : (L.np + 148 * 16 - 1) / (148 * 16);
+        chunk = std::max(gpb, (chunk + gpb - 1) / gpb * gpb);
+        int nb = (L.np + chunk - 1) / chunk;
+        // T = 32 two-zone lists stage their rows in shared memory (bulk async copies) when two rows per warp fit
+        const size_t tab_bytes = (size_t)L.ntypes * L.ntypes * 16;
+        const size_t staged_bytes = 64 + tab_bytes + (size_t)(kBlock / 32) * 2 * L.stride * sizeof(unsigned int);
+        const int staged = (c->staging_opt && L.form == SEG_PAIR_TZ && L.tpb == 32 && L.dev.smem_tab && staged_bytes <= 56 * 1024) ? 1 : 0;
+        c->segs.push_back({blk, nb, L.form, (int)l, L.tpb, chunk, staged});
         blk += nb;
-        if (L.dev.smem_tab) smem = std::max(smem, (size_t)L.ntypes * L.ntypes * 20);
+        if (staged) smem = std::max(smem, staged_bytes);
+        else if (L.dev.smem_tab) smem = std::max(smem, tab_bytes);
     }
+    c->pair_blocks = blk;
+    c->n_pair_segs = (int)c->segs.size();
     for (int k = 0; k < B_NUM_KINDS; k++) {
         if (c->bonded_h[k].n == 0) continue;
         int nb = (c->bonded_h[k].n + kBlock - 1) / kBlock;
-        c->segs.push_back({blk, nb, SEG_BONDED, k, 0});
+        c->segs.push_back({blk, nb, SEG_BONDED, k, 0, 0, 0});
+        blk += nb;
+    }
+    if (c->da.nterms > 0 && c->da.capacity > 0) {
+        int nb = (c->da.capacity + kBlock - 1) / kBlock;
+        c->segs.push_back({blk, nb, SEG_DA, 0, 0, 0, 0});
         blk += nb;
     }
     c->total_blocks = blk;
+    c->local_blocks = blk - c->pair_blocks;
+    c->n_local_segs = (int)c->segs.size() - c->n_pair_segs;
     c->smem_bytes = smem;
-    if (c->segs.empty()) c->segs.push_back({0, 0, SEG_BONDED, 0, 0});
+    if (c->segs.empty()) c->segs.push_back({0, 0, SEG_BONDED, 0, 0, 0, 0});
     c->d_segs.upload(c->segs);
     if (smem > 48 * 1024) {
         CUDA_TRY(cudaFuncSetAttribute(force_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(force_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+
     drop_graphs(c);
 }
 
@@ -426,6 +498,63 @@ static void compile_bonded(ocm_context* c) {
     c->d_bonded.upload(std::vector<BondedDev>(c->bonded_h, c->bonded_h + B_NUM_KINDS));
 }
 
+static void compile_da(ocm_context* c) {
+    long long cand = 0;
+    for (const auto& t : c->sys.das) {
+        DATermDev D{};
+        D.kind = t.kind; D.group = t.group; D.periodic = t.periodic; D.npar = t.npar;
+        D.nd = (int)t.nd(); D.na = (int)t.na(); D.nexcl = (int)t.excl.size();
+        D.cand_begin = cand;
+        cand += (long long)D.nd * D.na;
+        D.rc2 = t.cutoff * t.cutoff;
+        D.g0 = t.g0; D.g1 = t.g1; D.g2 = t.g2;
+        auto bi = std::make_unique<DevBuf<int>>();
+        std::vector<int> idx(t.donors.begin(), t.donors.end());
+        idx.insert(idx.end(), t.acceptors.begin(), t.acceptors.end());
+        if (idx.empty()) idx.push_back(0);
+        bi->upload(idx);
+        D.donors = bi->p; D.acceptors = bi->p + t.donors.size();
+        auto bp = std::make_unique<DevBuf<double>>();
+        bp->upload(t.p.empty() ? std::vector<double>(1, 0.0) : t.p);
+        D.par = bp->p;
+        auto be = std::make_unique<DevBuf<unsigned long long>>();
+        std::vector<unsigned long long> ex(t.excl.begin(), t.excl.end());
+        if (ex.empty()) ex.push_back(~0ull);
+        be->upload(ex);
+        D.excl = be->p;
+        c->da_idx.push_back(std::move(bi)); c->da_par.push_back(std::move(bp)); c->da_excl.push_back(std::move(be));
+        c->da_terms_h.push_back(D);
+        c->da_rcmax = std::max(c->da_rcmax, t.cutoff);
+    }
+    if (c->da_terms_h.size() > 255) throw std::runtime_error("more than 255 donor-acceptor terms");
+    c->da_count.alloc(1); c->da_count.zero();
+    c->da.nterms = (int)c->da_terms_h.size();
+    c->da.ncand = cand;
+    c->da.capacity = 0;
+    c->da.count = c->da_count.p;
+    c->da.entries = nullptr;
+    c->da.terms = nullptr;
+}
+
+// (re)derive what depends on the skin and upload the term table
+static void upload_da(ocm_context* c) {
+    if (c->da_terms_h.empty()) return;
+    for (size_t k = 0; k < c->da_terms_h.size(); k++) {
+        const double rl = c->sys.das[k].cutoff + c->skin;
+        c->da_terms_h[k].rlist2 = rl * rl;
+    }
+    c->d_da_terms.upload(c->da_terms_h);
+    c->da.terms = c->d_da_terms.p;
+}
+
+static void enqueue_da_build(ocm_context* c, cudaStream_t s) {
+    if (c->da.nterms == 0 || c->da.ncand == 0) return;
+    CUDA_TRY(cudaMemsetAsync(c->da_count.p, 0, sizeof(unsigned int), s));
+    const long long nb = (c->da.ncand + 255) / 256;
+    da_build_kernel<<<(unsigned int)nb, 256, 0, s>>>(c->da, c->P, c->x.p, c->flags.p);
+    c->n_launches += 1;
+}
+
 static void update_params(ocm_context* c) {
     StepParams& P = c->P;
     P.n = c->n; P.periodic = c->periodic ? 1 : 0;
@@ -446,6 +575,15 @@ static void update_params(ocm_context* c) {
 // ---- enqueue helpers ----------------------------------------------------------------------------
 static inline int nblk(int n, int b) { return std::max(1, (n + b - 1) / b); }
 
+// the list-build launch: rows are staged in shared memory (8 warps x stride x 5 bytes) to be written out in zone order
+static void launch_build(ocm_context* c, PairListHost& L, int li, cudaStream_t s, bool count_only) {
+    const size_t bytes = (size_t)8 * L.stride * 5 + 16;
+    const int zoned = (!count_only && L.stride > 0 && bytes <= 160 * 1024) ? 1 : 0;
+    const size_t smem = zoned ? bytes : 0;
+    if (c->periodic) build_list_kernel<true><<<nblk(L.np * 32, 256), 256, smem, s>>>(c->d_lists.p, li, c->P, c->flags.p, count_only ? 1 : 0, zoned);
+    else build_list_kernel<false><<<nblk(L.np * 32, 256), 256, smem, s>>>(c->d_lists.p, li, c->P, c->flags.p, count_only ? 1 : 0, zoned);
+}
+
 static void enqueue_rebuild(ocm_context* c, cudaStream_t s, bool count_only) {
     const int n = c->n;
     if (!count_only) save_ref_kernel<<<nblk(3 * n, 256), 256, 0, s>>>(n, c->x.p, c->xref.p);
@@ -462,23 +600,38 @@ static void enqueue_rebuild(ocm_context* c, cudaStream_t s, bool count_only) {
         }
         scan_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li);
         scatter_kernel<<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li);
-        sortcell_kernel<<<std::min(nblk(L.max_cells, 128), 2048), 128, 0, s>>>(c->d_lists.p, li);
-        if (c->periodic)
-            build_list_kernel<true><<<nblk(L.np * 32, 256), 256, 0, s>>>(c->d_lists.p, li, c->P, c->posq.p, c->flags.p, count_only ? 1 : 0);
-        else
-            build_list_kernel<false><<<nblk(L.np * 32, 256), 256, 0, s>>>(c->d_lists.p, li, c->P, c->posq.p, c->flags.p, count_only ? 1 : 0);
+        rank_fill_kernel<<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->posq.p);
+        launch_build(c, L, li, s, count_only);
         c->n_launches += c->periodic ? 5 : 7;
     }
-    if (!count_only) { c->n_launches += 1; c->n_rebuilds += 1; }
+    if (!count_only) {
+        enqueue_da_build(c, s);
+        c->n_launches += 1; c->n_rebuilds += 1;
+    }
 }
 
 static void enqueue_forces(ocm_context* c, cudaStream_t s) {
     if (c->total_blocks == 0) return;
-    if (c->periodic)
-        force_kernel<true><<<c->total_blocks, kBlock, c->smem_bytes, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->P, c->posq.p, c->x.p, c->fbuf.p);
-    else
-        force_kernel<false><<<c->total_blocks, kBlock, c->smem_bytes, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->P, c->posq.p, c->x.p, c->fbuf.p);
-    c->n_launches += 1;
+    const bool fork = c->local_blocks > 0 && c->pair_blocks > 0;
+    if (c->local_blocks > 0) {
+        cudaStream_t sl = s;
+        if (fork) {
+            CUDA_TRY(cudaEventRecord(c->ev_fork, s));
+            CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+            sl = c->side;
+        }
+        const WorkSeg* ls = c->d_segs.p + c->n_pair_segs;
+        if (c->periodic) local_kernel<true><<<c->local_blocks, kBlock, 0, sl>>>(ls, c->n_local_segs, c->d_bonded.p, c->da, c->P, c->x.p, c->fbuf.p);
+        else local_kernel<false><<<c->local_blocks, kBlock, 0, sl>>>(ls, c->n_local_segs, c->d_bonded.p, c->da, c->P, c->x.p, c->fbuf.p);
+        if (fork) CUDA_TRY(cudaEventRecord(c->ev_join, c->side));
+        c->n_launches += 1;
+    }
+    if (c->pair_blocks > 0) {
+        if (c->periodic) force_kernel<true><<<c->pair_blocks, kBlock, c->smem_bytes, s>>>(c->d_segs.p, c->n_pair_segs, c->d_lists.p, c->P, c->fbuf.p);
+        else force_kernel<false><<<c->pair_blocks, kBlock, c->smem_bytes, s>>>(c->d_segs.p, c->n_pair_segs, c->d_lists.p, c->P, c->fbuf.p);
+        c->n_launches += 1;
+    }
+    if (fork) CUDA_TRY(cudaStreamWaitEvent(s, c->ev_join, 0));
 }
 
 // size (or re-size) the Verlet rows from a counting pass at the current positions
@@ -501,9 +654,8 @@ static void size_lists(ocm_context* c, double growth) {
         }
         scan_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li);
         scatter_kernel<<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li);
-        sortcell_kernel<<<std::min(nblk(L.max_cells, 128), 2048), 128, 0, s>>>(c->d_lists.p, li);
-        if (c->periodic) build_list_kernel<true><<<nblk(L.np * 32, 256), 256, 0, s>>>(c->d_lists.p, li, c->P, c->posq.p, c->flags.p, 1);
-        else build_list_kernel<false><<<nblk(L.np * 32, 256), 256, 0, s>>>(c->d_lists.p, li, c->P, c->posq.p, c->flags.p, 1);
+        rank_fill_kernel<<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->posq.p);
+        launch_build(c, L, li, s, true);
         CUDA_TRY(cudaMemcpyAsync(fl.data(), c->flags.p, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         int maxn = fl[FLAG_MAXDISP + 1];
@@ -514,6 +666,24 @@ static void size_lists(ocm_context* c, double growth) {
             L.nbr.alloc((size_t)std::max(L.np, 1) * L.stride);
         }
         L.dev.stride = L.stride; L.dev.nbr = L.nbr.p;
+    }
+    if (c->da.nterms > 0 && c->da.ncand > 0) {
+        // counting pass with capacity 0: every hit only bumps the counter
+        upload_da(c);
+        DAListDev probe = c->da;
+        probe.capacity = 0; probe.entries = nullptr;
+        CUDA_TRY(cudaMemsetAsync(c->da_count.p, 0, sizeof(unsigned int), s));
+        da_build_kernel<<<(unsigned int)((c->da.ncand + 255) / 256), 256, 0, s>>>(probe, c->P, c->x.p, c->flags.p);
+        unsigned int cnt = 0;
+        CUDA_TRY(cudaMemcpyAsync(&cnt, c->da_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        int want = (int)(cnt * growth) + 256;
+        want = (want + 127) / 128 * 128;
+        if (want > c->da.capacity) {
+            c->da_entries.alloc((size_t)want);
+            c->da.capacity = want;
+            c->da.entries = c->da_entries.p;
+        }
     }
     CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, FLAG_COUNT * sizeof(int), s));
     upload_lists(c);
@@ -531,7 +701,7 @@ static void ensure_lists_current(ocm_context* c) {
         int fl[FLAG_COUNT];
         CUDA_TRY(cudaMemcpyAsync(fl, c->flags.p, sizeof(fl), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        if (!fl[FLAG_OVERFLOW]) { c->lists_current = true; return; }
+        if (!fl[FLAG_OVERFLOW] && !fl[FLAG_DA_OVERFLOW]) { c->lists_current = true; return; }
         size_lists(c, 1.5);
     }
     throw std::runtime_error("neighbour list keeps overflowing");
@@ -547,7 +717,7 @@ static cudaGraphExec_t window_graph(ocm_context* c, int nst) {
     enqueue_rebuild(c, s, false);
     for (int k = 0; k < nst; k++) {
         enqueue_forces(c, s);
-        integrate_kernel<<<nblk(c->n, 128), 128, 0, s>>>(c->P, c->x.p, c->v.p, c->fbuf.p, c->posq.p, c->xref.p,
+        integrate_kernel<<<nblk(c->n, 128), 128, 0, s>>>(c->P, c->x.p, c->v.p, c->fbuf.p, c->posq.p, c->d_lists.p, (int)c->lists.size(), c->xref.p,
                                                          c->step_base.p, k, nst, k == nst - 1 ? 1 : 0, c->flags.p);
     }
     CUDA_TRY(cudaStreamEndCapture(s, &g));
@@ -562,7 +732,8 @@ static cudaGraphExec_t window_graph(ocm_context* c, int nst) {
 static double launches_per_window(const ocm_context* c, int nst) {
     double per_rebuild = 1;
     for (auto& L : c->lists) if (L->np) per_rebuild += c->periodic ? 5 : 7;
-    return per_rebuild + nst * (1.0 + (c->total_blocks > 0 ? 1.0 : 0.0));
+    if (c->da.nterms > 0 && c->da.ncand > 0) per_rebuild += 1;
+    return per_rebuild + nst * (1.0 + (c->pair_blocks > 0 ? 1.0 : 0.0) + (c->local_blocks > 0 ? 1.0 : 0.0));
 }
 
 static int quantise_nst(double want) {
@@ -612,14 +783,14 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
         CUDA_TRY(cudaMemcpyAsync(fl, c->flags.p, sizeof(fl), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (fl[FLAG_NAN]) throw std::runtime_error("particle coordinate or force is NaN");
-        if (fl[FLAG_VIOLATION] || fl[FLAG_OVERFLOW]) {
+        if (fl[FLAG_VIOLATION] || fl[FLAG_OVERFLOW] || fl[FLAG_DA_OVERFLOW]) {
             // roll back and replay the batch with a safer configuration
             CUDA_TRY(cudaMemcpyAsync(c->x.p, c->xbak.p, xb, cudaMemcpyDeviceToDevice, s));
             CUDA_TRY(cudaMemcpyAsync(c->v.p, c->vbak.p, vb, cudaMemcpyDeviceToDevice, s));
             CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, (size_t)3 * c->n * sizeof(unsigned long long), s));
             canon_kernel<<<nblk(c->n, 256), 256, 0, s>>>(c->P, c->x.p, c->posq.p);
             c->n_rollbacks += 1;
-            if (fl[FLAG_OVERFLOW]) size_lists(c, 1.5);
+            if (fl[FLAG_OVERFLOW] || fl[FLAG_DA_OVERFLOW]) size_lists(c, 1.5);
             if (fl[FLAG_VIOLATION]) {
                 if (c->nst <= 1) throw std::runtime_error("a particle crosses the Verlet buffer within one step; increase skin_nm or reduce the time step");
                 c->nst = quantise_nst(std::max(1.0, c->nst * 0.6));
@@ -731,6 +902,25 @@ int ocm_system_add_flexible_local_dihedral(ocm_system* s, int g, int per, int64_
     return 0;
 }
 
+int ocm_system_add_3spn2_base_stacking(ocm_system* s, int g, int per, int64_t n, const int32_t* ijk, const double* eps, const double* r0,
+                                       const double* theta0, double alpha, double K_BS) {
+    std::vector<double> al((size_t)std::max<int64_t>(n, 0), alpha), kb((size_t)std::max<int64_t>(n, 0), K_BS);
+    return add_bonded(s, B_3SPN2_STACK, g, per, n, ijk, {eps, r0, theta0, al.data(), kb.data()}, "3spn2_base_stacking");
+}
+int ocm_system_add_3spn2_base_pair(ocm_system* s, int g, const ocm_da_topology* topo, const double* eps, const double* r0,
+                                   const double* t01, const double* t02, const double* phi0, double alpha, double K_BP) {
+    return add_da(s, DA_BASE_PAIR, g, topo, true, {eps, r0, t01, t02, phi0}, alpha, K_BP, 0, "3spn2_base_pair");
+}
+int ocm_system_add_3spn2_cross_stacking(ocm_system* s, int g, const ocm_da_topology* topo, const double* eps, const double* r0,
+                                        const double* t03, const double* t0CS, double K_BP, double K_CS, double alpha) {
+    return add_da(s, DA_CROSS_STACK, g, topo, false, {eps, r0, t03, t0CS}, K_BP, K_CS, alpha, "3spn2_cross_stacking");
+}
+int ocm_system_add_pdns(ocm_system* s, int g, const ocm_da_topology* topo, const double* k, const double* r0, const double* theta0,
+                        const double* phi0, double sigma, double delta) {
+    if (!(sigma > 0) || !(delta > 0)) return fail("pdns: sigma and delta must be positive");
+    return add_da(s, DA_PDNS, g, topo, true, {k, r0, theta0, phi0}, sigma, delta, 0, "pdns");
+}
+
 int ocm_system_add_excluded_volume(ocm_system* s, int g, double eps, double rc, const double* radius, const ocm_pair_topology* topo) {
     return add_pair(s, P_EXV, g, rc, rc, eps, std::pow(1.0 / rc, 12), 0, radius, nullptr, topo, "excluded_volume");
 }
@@ -765,8 +955,13 @@ int ocm_context_create(const ocm_system* sys, double T, double gamma, double dt,
     c->sys = *sys; c->n = sys->n; c->periodic = sys->has_box;
     c->T = T; c->gamma = gamma; c->dt = dt; c->seed = seed; c->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
+    CUDA_TRY(cudaFuncSetAttribute(build_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 16));
+    CUDA_TRY(cudaFuncSetAttribute(build_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 16));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     const int n = c->n;
     c->x.alloc(3 * (size_t)n); c->xref.alloc(3 * (size_t)n); c->xbak.alloc(3 * (size_t)n);
     c->v.alloc(n); c->vbak.alloc(n); c->posq.alloc(n); c->fbuf.alloc(3 * (size_t)n);
@@ -779,7 +974,12 @@ int ocm_context_create(const ocm_system* sys, double T, double gamma, double dt,
     plan_lists(c);
     double rcmax = 0;
     for (auto& L : c->lists) { compile_list(c, *L); rcmax = std::max(rcmax, L->rc_list); }
+    compile_da(c);
+    rcmax = std::max(rcmax, c->da_rcmax);
     c->skin = std::min(0.4, std::max(0.1, 0.08 * rcmax));
+    if (c->periodic)
+        for (int k = 0; k < 3; k++)
+            if (c->da_rcmax > 0 && c->da_rcmax + c->skin > 0.5 * sys->box[k]) c->skin = std::max(0.0, 0.5 * sys->box[k] - c->da_rcmax) * 0.999;
     if (c->periodic)
         for (auto& L : c->lists)
             for (int k = 0; k < 3; k++)
@@ -812,6 +1012,9 @@ int ocm_context_set_option(ocm_context* c, const char* key, double value) {
             for (auto& L : c->lists)
                 for (int d = 0; d < 3; d++)
                     if (L->rc_list + value > 0.5 * c->sys.box[d]) return fail("skin_nm: cutoff + skin exceeds half the box");
+        if (c->periodic && c->da_rcmax > 0)
+            for (int d = 0; d < 3; d++)
+                if (c->da_rcmax + value > 0.5 * c->sys.box[d]) return fail("skin_nm: cutoff + skin exceeds half the box");
         c->skin = value;
         update_params(c);
         c->lists_ready = false; c->lists_current = false;
@@ -826,6 +1029,13 @@ int ocm_context_set_option(ocm_context* c, const char* key, double value) {
         if (!(t == 0 || t == 4 || t == 8 || t == 16 || t == 32)) return fail("threads_per_bead must be 0 (auto), 4, 8, 16 or 32");
         c->tpb_opt = t;
         if (c->lists_ready) build_segments(c);
+    } else if (k == "row_staging") {
+        c->staging_opt = value != 0 ? 1 : 0;
+        if (c->lists_ready) build_segments(c);
+    } else if (k == "beads_per_block") {
+        if (value < 0 || value > 65536) return fail("beads_per_block out of range");
+        c->chunk_opt = (int)value;
+        if (c->lists_ready) build_segments(c);
     } else {
         return fail("unknown option: " + k);
     }
@@ -838,6 +1048,8 @@ int ocm_context_get_option(ocm_context* c, const char* key, double* value) {
     if (k == "skin_nm") *value = c->skin;
     else if (k == "nstlist") *value = c->nstlist_fixed;
     else if (k == "threads_per_bead") *value = c->tpb_opt;
+    else if (k == "beads_per_block") *value = c->chunk_opt;
+    else if (k == "row_staging") *value = c->staging_opt;
     else return fail("unknown option: " + k);
     return 0;
 }
@@ -912,8 +1124,8 @@ int ocm_get_state(ocm_context* c, uint32_t mask, double* pos, double* vel, doubl
         CUDA_TRY(cudaMemsetAsync(c->egroup.p, 0, 40 * sizeof(double), s));
         if (epot || ebg) {
             if (c->total_blocks > 0) {
-                if (c->periodic) energy_kernel<true><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->P, c->posq.p, c->x.p, c->egroup.p);
-                else energy_kernel<false><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->P, c->posq.p, c->x.p, c->egroup.p);
+                if (c->periodic) energy_kernel<true><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->da, c->P, c->x.p, c->egroup.p);
+                else energy_kernel<false><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->da, c->P, c->x.p, c->egroup.p);
             }
         }
         if (force || ekin) {
@@ -952,8 +1164,8 @@ int ocm_get_neighbor_pairs(ocm_context* c, int term, int32_t* ij, int64_t capaci
     if (ij && capacity > 0) out.alloc((size_t)2 * capacity);
     CUDA_TRY(cudaMemsetAsync(c->pair_counter.p, 0, sizeof(unsigned long long), s));
     if (L.np > 0) {
-        if (c->periodic) extract_pairs_kernel<true><<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->P, c->posq.p, rc2, out.p, capacity, c->pair_counter.p);
-        else extract_pairs_kernel<false><<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->P, c->posq.p, rc2, out.p, capacity, c->pair_counter.p);
+        if (c->periodic) extract_pairs_kernel<true><<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->P, rc2, out.p, capacity, c->pair_counter.p);
+        else extract_pairs_kernel<false><<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->P, rc2, out.p, capacity, c->pair_counter.p);
     }
     unsigned long long cnt = 0;
     CUDA_TRY(cudaMemcpyAsync(&cnt, c->pair_counter.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
@@ -967,6 +1179,37 @@ int ocm_get_neighbor_pairs(ocm_context* c, int term, int32_t* ij, int64_t capaci
         for (size_t k = 0; k < cnt; k++) pr[k] = {raw[2 * k], raw[2 * k + 1]};
         std::sort(pr.begin(), pr.end());
         for (size_t k = 0; k < cnt; k++) { ij[2 * k] = pr[k].first; ij[2 * k + 1] = pr[k].second; }
+    }
+    return 0;
+    OCM_GUARD_END
+}
+
+int ocm_num_da_terms(const ocm_context* c) { return c ? (int)c->sys.das.size() : -1; }
+
+int ocm_get_da_pairs(ocm_context* c, int term, int32_t* da, int64_t capacity, int64_t* n_pairs) {
+    if (!c || !n_pairs) return fail("null argument");
+    if (term < 0 || term >= (int)c->sys.das.size()) return fail("donor-acceptor term index out of range");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    ensure_lists_current(c);
+    cudaStream_t s = c->stream;
+    DevBuf<int> out;
+    if (da && capacity > 0) out.alloc((size_t)2 * capacity);
+    CUDA_TRY(cudaMemsetAsync(c->pair_counter.p, 0, sizeof(unsigned long long), s));
+    if (c->da.capacity > 0)
+        da_extract_kernel<<<nblk(c->da.capacity, 128), 128, 0, s>>>(c->da, term, c->P, c->x.p, out.p, capacity, c->pair_counter.p);
+    unsigned long long cnt = 0;
+    CUDA_TRY(cudaMemcpyAsync(&cnt, c->pair_counter.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *n_pairs = (int64_t)cnt;
+    if (da) {
+        if ((int64_t)cnt > capacity) return fail("get_da_pairs: capacity too small");
+        std::vector<int> raw((size_t)2 * cnt);
+        if (cnt) CUDA_TRY(cudaMemcpy(raw.data(), out.p, raw.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<std::pair<int, int>> pr(cnt);
+        for (size_t k = 0; k < cnt; k++) pr[k] = {raw[2 * k], raw[2 * k + 1]};
+        std::sort(pr.begin(), pr.end());
+        for (size_t k = 0; k < cnt; k++) { da[2 * k] = pr[k].first; da[2 * k + 1] = pr[k].second; }
     }
     return 0;
     OCM_GUARD_END
@@ -1041,7 +1284,7 @@ int ocm_profile_kernel(ocm_context* c, const char* which, int reps, double* avg_
             else if (w == "rebuild") enqueue_rebuild(c, s, false);
             else if (w == "integrate") {
                 // dt = 0 copy of the parameters would change the physics; instead integrate a scratch copy
-                integrate_kernel<<<nblk(c->n, 128), 128, 0, s>>>(c->P, c->xbak.p, c->vbak.p, c->fbuf.p, c->posq.p, c->xref.p,
+                integrate_kernel<<<nblk(c->n, 128), 128, 0, s>>>(c->P, c->xbak.p, c->vbak.p, c->fbuf.p, c->posq.p, c->d_lists.p, (int)c->lists.size(), c->xref.p,
                                                                  c->step_base.p, 0, 1, 0, c->flags.p);
             } else throw std::runtime_error("profile_kernel: unknown kernel " + w);
         }

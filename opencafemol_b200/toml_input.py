@@ -19,7 +19,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import tables
-from .capi import Context, Library, PairTopology, System
+from .capi import DATopology, Context, Library, PairTopology, System
 
 NM_PER_ANGSTROM = 0.1
 ANGSTROM_PER_NM = 10.0
@@ -515,8 +515,167 @@ def _read_local(spec, lf, topo, periodic):
                     dict(ijkl=idx, k=k, coef7=tables.FLD_FOURIER[key], e_min=_fld_cache[key], periodic=periodic),
                 )
             )
+    elif inter == "3SPN2BaseStacking" and pot in ("3SPN2", "3SPN2C"):
+        _base_stacking(spec, lf, params, env, topo, periodic, pot)
     else:
         raise NotImplementedError(f"local force field {inter}/{pot} is not in scope yet")
+
+
+_T3 = None
+
+
+def tables_3spn2():
+    """3SPN.2 / 3SPN.2C parameter tables (opencafemol_b200/tables_3spn2.json, generated from the reference
+    headers by tools/extract_3spn2_tables.py; units nm, rad, kJ/mol)."""
+    global _T3
+    if _T3 is None:
+        import json
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tables_3spn2.json")) as fh:
+            _T3 = json.load(fh)
+    return _T3
+
+
+def _nucleotides(params, env):
+    """{strand, P?, S, B, Base} records of the 3SPN.2 tables (ReadTOMLForceFieldGenerator.cpp:801-858)."""
+    out = []
+    for p in params:
+        base = p["Base"]
+        if base not in "ATGC" or len(base) != 1:
+            raise RuntimeError(f'[error] invalid base type {base} here. One of the "A", "T", "C", "G" is expected.')
+        out.append(dict(P=_param(p, env, "P") if "P" in p else None, S=_param(p, env, "S"), B=_param(p, env, "B"),
+                        strand=_param(p, env, "strand"), base=base))
+    return out
+
+
+def _base_stacking(spec, lf, params, env, topo, periodic, pot):
+    """read_toml_3spn2_base_stacking_ff_generator (ReadTOMLForceFieldGenerator.cpp:769-958)."""
+    tab = tables_3spn2()["ThreeSPN2BaseStackingPotentialParameter" if pot == "3SPN2" else "ThreeSPN2CBaseStackingPotentialParameter"]
+    nucs = _nucleotides(params, env)
+    idx, eps, r0, th0 = [], [], [], []
+    for b5, b3 in zip(nucs[:-1], nucs[1:]):
+        if b5["strand"] != b3["strand"]:
+            continue
+        kind = b5["base"] + b3["base"]
+        idx.append([b5["S"], b5["B"], b3["B"]])
+        eps.append(tab["maps"]["epsilon_BS"][kind])
+        r0.append(tab["maps"]["r0_BS"][kind] * NM_PER_ANGSTROM)
+        th0.append(tab["maps"]["theta0_BS"][kind] * math.pi / 180.0)
+    if "topology" in lf:
+        for b5, b3 in zip(nucs[:-1], nucs[1:]):
+            if b5["strand"] != b3["strand"]:
+                continue
+            edges = [(b5["S"], b3["S"]), (b5["S"], b3["B"]), (b5["B"], b3["S"]), (b5["B"], b3["B"])]
+            if b5["P"] is not None:
+                edges += [(b5["P"], b3["S"]), (b5["P"], b3["B"])]
+            if b3["P"] is not None:
+                edges += [(b5["S"], b3["P"]), (b5["B"], b3["P"])]
+            if b5["P"] is not None and b3["P"] is not None:
+                edges.append((b5["P"], b3["P"]))
+            topo.add_edges(edges, lf["topology"])
+    spec.add_term(Term("3spn2_base_stacking", "3SPN2BaseStacking",
+                       dict(ijk=idx, eps=eps, r0=r0, theta0=th0, alpha=tab["scalars"]["alpha_BS"] / NM_PER_ANGSTROM,
+                            K_BS=tab["scalars"]["K_BS"], periodic=periodic)))
+
+
+def _da_exclusions(donors, acceptors, ignore):
+    """donor x acceptor exclusions: base-particle pairs found in the ignore list
+    (ThreeSPN2BasePairForceFieldGenerator.cpp:76-96, ThreeSPN2CrossStackingForceFieldGenerator.cpp:84-100)."""
+    ign = {(int(a), int(b)) for a, b in ignore}
+    out = []
+    for di, d in enumerate(donors):
+        for ai, a in enumerate(acceptors):
+            if (min(d[0], a[0]), max(d[0], a[0])) in ign:
+                out.append((di, ai))
+    return np.array(out, np.int32).reshape(-1, 2)
+
+
+def _pad3(rows):
+    out = np.full((len(rows), 3), -1, np.int32)
+    for k, r in enumerate(rows):
+        out[k, :len(r)] = r
+    return out
+
+
+def _base_pair(spec, gf, topo, periodic, pot):
+    """read_toml_3spn2_base_pair_ff_generator x {A-T, G-C} (ReadTOMLForceFieldGenerator.cpp:1645-1771,
+    ReadTOMLInput.cpp:716-760)."""
+    tab = tables_3spn2()["ThreeSPN2BasePairPotentialParameter" if pot == "3SPN2" else "ThreeSPN2CBasePairPotentialParameter"]
+    env = gf.get("env")
+    nucs = _nucleotides(gf["parameters"], env)
+    ignore, _ = _read_ignore(gf, topo)
+    for donor, acceptor in (("A", "T"), ("G", "C")):
+        don = [[n["B"], n["S"]] for n in nucs if n["base"] == donor]
+        acc = [[n["B"], n["S"]] for n in nucs if n["base"] == acceptor]
+        kind = donor + acceptor
+        m, sc = tab["maps"], tab["scalars"]
+        nd = len(don)
+        t = DATopology(donors=_pad3(don), acceptors=_pad3(acc), cutoff=sc["cutoff"], excl=_da_exclusions(don, acc, ignore),
+                       periodic=periodic)
+        spec.add_term(Term("3spn2_base_pair", f"{pot}BasePair ({donor}-{acceptor})",
+                           dict(topo=t, eps=np.full(nd, m["epsilon_BP"][kind]), r0=np.full(nd, m["r0"][kind]),
+                                theta0_1=np.full(nd, m["theta0_1"][kind]), theta0_2=np.full(nd, m["theta0_2"][kind]),
+                                phi0=np.full(nd, m["phi0"][kind]), alpha=sc["alpha_BP"], K_BP=sc["K_BP"])))
+
+
+def _cross_stacking(spec, gf, topo, periodic, pot):
+    """read_toml_3spn2_cross_stacking_ff_generator x {A-T, T-A, G-C, C-G} x {sense, antisense}
+    (ReadTOMLForceFieldGenerator.cpp:1904-2101, ReadTOMLInput.cpp:662-714)."""
+    tab = tables_3spn2()["ThreeSPN2CrossStackingPotentialParameter" if pot == "3SPN2" else "ThreeSPN2CCrossStackingPotentialParameter"]
+    env = gf.get("env")
+    nucs = _nucleotides(gf["parameters"], env)
+    ignore, _ = _read_ignore(gf, topo)
+    m, sc = tab["maps"], tab["scalars"]
+    for first, second in (("A", "T"), ("T", "A"), ("G", "C"), ("C", "G")):
+        for strand_kind in ("sense", "antisense"):
+            don, acc, acc_kind = [], [], []
+            for i, nuc in enumerate(nucs):
+                nxt = nucs[i + 1] if i + 1 < len(nucs) and nucs[i + 1]["strand"] == nuc["strand"] else None
+                prv = nucs[i - 1] if i > 0 and nucs[i - 1]["strand"] == nuc["strand"] else None
+                if strand_kind == "sense":
+                    if nuc["base"] == first and nxt is not None:
+                        don.append([nuc["B"], nuc["S"], nxt["B"]])
+                    if nuc["base"] == second and prv is not None:
+                        acc.append([nuc["B"], nuc["S"], prv["B"]])
+                        acc_kind.append(first + prv["base"] + "5")
+                else:
+                    if nuc["base"] == first and nxt is not None:
+                        acc.append([nuc["B"], nuc["S"], nxt["B"]])
+                        acc_kind.append(second + nxt["base"] + "3")
+                    if nuc["base"] == second and prv is not None:
+                        don.append([nuc["B"], nuc["S"], prv["B"]])
+            t = DATopology(donors=_pad3(don), acceptors=_pad3(acc), cutoff=sc["cutoff"], excl=_da_exclusions(don, acc, ignore),
+                           periodic=periodic)
+            spec.add_term(Term("3spn2_cross_stacking", f"{pot}CrossStacking ({first}-{second})",
+                               dict(topo=t, eps=[m["epsilon_CS"][k] for k in acc_kind], r0=[m["r0_CS"][k] for k in acc_kind],
+                                    theta0_3=[m["theta3_0"][first + second]] * len(acc), theta0_CS=[m["theta_CS_0"][k] for k in acc_kind],
+                                    K_BP=sc["K_BP"], K_CS=sc["K_CS"], alpha=sc["alpha_CS"])))
+
+
+def _pdns(spec, gf, periodic):
+    """read_toml_protein_dna_non_specific_ff_generator (ReadTOMLForceFieldGenerator.cpp:2413-2493) and the
+    generator's cutoff rule (ProteinDNANonSpecificForceFieldGenerator.cpp:124-135)."""
+    env = gf.get("env")
+    n = spec.mass.size
+    sigma = _param(gf, env, "sigma", 1.0) * NM_PER_ANGSTROM
+    delta = _param(gf, env, "delta", 0.17453)
+    ratio = _param(gf, env, "cutoff", 10.0)
+    unit = _param(gf, env, "energy_unit", 0.593) * KJ_PER_KCAL
+    dna, pro, k, r0, th0, ph0 = [], [], [], [], [], []
+    for p in gf["parameters"]:
+        index = _index(p, env, "read_toml_protein_dna_non_specific_ff_generator", n)
+        if p["kind"] == "DNA":
+            dna.append([index, _param(p, env, "S3"), -1])
+        if p["kind"] == "Protein":
+            # donor slots: d1 = CA of the N-side neighbour, d2 = CA, d3 = CA of the C-side neighbour
+            pro.append([_param(p, env, "PN"), index, _param(p, env, "PC")])
+            k.append(_param(p, env, "k") * unit)
+            r0.append(_param(p, env, "r0") * NM_PER_ANGSTROM)
+            th0.append(_param(p, env, "theta0") * math.pi / 180.0)
+            ph0.append(_param(p, env, "phi0") * math.pi / 180.0)
+    cutoff = max([0.0] + [r + ratio * sigma for r in r0])
+    t = DATopology(donors=np.array(pro, np.int32).reshape(-1, 3), acceptors=np.array(dna, np.int32).reshape(-1, 3), cutoff=cutoff,
+                   periodic=periodic)
+    spec.add_term(Term("pdns", "PDNS", dict(topo=t, k=k, r0=r0, theta0=th0, phi0=ph0, sigma=sigma, delta=delta)))
 
 
 def _gaussian_dihedral(spec, params, env, topo, lf, periodic):
@@ -561,6 +720,17 @@ def debye_huckel_constants(temperature, ionic_strength, cutoff_ratio):
 
 def _read_global(spec, gf, topo, periodic, attr):
     pot = gf["potential"]
+    inter = gf.get("interaction")
+    if inter == "3SPN2CrossStacking":
+        if pot not in ("3SPN2", "3SPN2C"):
+            raise RuntimeError(f"[error] invalid potential {pot} found.")
+        return _cross_stacking(spec, gf, topo, periodic, pot)
+    if inter == "3SPN2BasePair":
+        if pot not in ("3SPN2", "3SPN2C"):
+            raise RuntimeError(f"[error] invalid potential {pot} found.")
+        return _base_pair(spec, gf, topo, periodic, pot)
+    if pot == "PDNS":
+        return _pdns(spec, gf, periodic)
     env = gf.get("env")
     n = topo.size()
     params = gf.get("parameters", [])
@@ -581,6 +751,26 @@ def _read_global(spec, gf, topo, periodic, attr):
         mx, sm = _two_largest(rad[has], strict=True)
         rc = (mx + sm) * cutoff
         spec.add_term(Term("excluded_volume", "ExcludedVolume", dict(eps=eps, rc=rc, radius=rad, topo=topo_for(has))))
+    elif pot == "3SPN2ExcludedVolume":
+        # read_toml_3spn2_excluded_volume_ff_generator (ReadTOMLForceFieldGenerator.cpp:1136-1224) and the
+        # generator's cutoff rule (ThreeSPN2ExcludedVolumeForceFieldGenerator.cpp:19-60)
+        tab = tables_3spn2()["ThreeSPN2ExcludedVolumePotentialParameter"]
+        cutoff = float(gf.get("cutoff", 2.0))
+        sig = np.full(n, np.nan)
+        kinds = []
+        for p in params:
+            i = _index(p, env, "read_toml_3spn2_excluded_volume_ff_generator", n)
+            sig[i] = tab["maps"]["sigma"][p["kind"]]
+            kinds.append((i, p["kind"]))
+        has = ~np.isnan(sig)
+        t = topo_for(has)
+        comp = {("A", "T"), ("T", "A"), ("G", "C"), ("C", "G")}
+        extra = [(min(i, j), max(i, j)) for a, (i, ki) in enumerate(kinds) for (j, kj) in kinds[a + 1:] if (ki, kj) in comp]
+        allx = {tuple(e) for e in np.asarray(t.excl).reshape(-1, 2).tolist()} | set(extra)
+        t.excl = np.array(sorted(allx), np.int32).reshape(-1, 2)
+        mx, sm = _two_largest(sig[has], strict=True)
+        eps = np.where(has, tab["scalars"]["epsilon"], np.nan)
+        spec.add_term(Term("3spn2_excluded_volume", "3SPN2ExcludedVolume", dict(rc=(mx + sm) * cutoff, eps=eps, sigma=sig, topo=t)))
     elif pot == "DebyeHuckel":
         ratio = float(gf.get("cutoff", 5.5))
         q = np.full(n, np.nan)
@@ -641,6 +831,9 @@ def spec_to_dict(spec: SystemSpec) -> dict:
         if isinstance(v, PairTopology):
             return {"__topo__": True, "excl": np.asarray(v.excl).tolist(),
                     "igroups": [[list(map(int, a)), list(map(int, b))] for a, b in v.igroups], "periodic": bool(v.periodic)}
+        if isinstance(v, DATopology):
+            return {"__da__": True, "donors": np.asarray(v.donors).tolist(), "acceptors": np.asarray(v.acceptors).tolist(),
+                    "cutoff": float(v.cutoff), "excl": np.asarray(v.excl).tolist(), "periodic": bool(v.periodic)}
         if isinstance(v, np.ndarray):
             return {"__nd__": True, "v": [None if (isinstance(x, float) and math.isnan(x)) else x for x in v.reshape(-1).tolist()],
                     "shape": list(v.shape)}
@@ -667,6 +860,9 @@ def spec_from_dict(d: dict) -> SystemSpec:
         if isinstance(v, dict) and v.get("__topo__"):
             return PairTopology(excl=np.array(v["excl"], np.int32).reshape(-1, 2),
                                 igroups=[(a, b) for a, b in v["igroups"]], periodic=v["periodic"])
+        if isinstance(v, dict) and v.get("__da__"):
+            return DATopology(donors=np.array(v["donors"], np.int32).reshape(-1, 3), acceptors=np.array(v["acceptors"], np.int32).reshape(-1, 3),
+                              cutoff=v["cutoff"], excl=np.array(v["excl"], np.int32).reshape(-1, 2), periodic=v["periodic"])
         if isinstance(v, dict) and v.get("__nd__"):
             return np.array([np.nan if x is None else x for x in v["v"]], float).reshape(v["shape"])
         return v

@@ -52,7 +52,7 @@ inline Vec3 cross(Vec3 a, Vec3 b) {
 
 enum BondedKind {
     B_HARMONIC_BOND, B_GAUSSIAN_BOND, B_GO_CONTACT, B_3SPN2_BOND,
-    B_HARMONIC_ANGLE, B_FLEX_ANGLE, B_GAUSSIAN_DIHEDRAL, B_COSINE_DIHEDRAL, B_FLEX_DIHEDRAL
+    B_HARMONIC_ANGLE, B_FLEX_ANGLE, B_GAUSSIAN_DIHEDRAL, B_COSINE_DIHEDRAL, B_FLEX_DIHEDRAL, B_3SPN2_STACK
 };
 
 struct BondedTerm {
@@ -82,6 +82,21 @@ struct PairTerm {
     int ncls;
 };
 
+// donor x acceptor ("CustomHbondForce"-like) term, SURVEY.md B.5
+enum DAKind { DA_BASE_PAIR, DA_CROSS_STACK, DA_PDNS };
+struct DATerm {
+    DAKind kind;
+    int group, periodic;
+    double cutoff;
+    std::vector<int32_t> donors, acceptors;           // 3 per entry, -1 = unused
+    std::vector<std::pair<int32_t, int32_t>> excl;    // (donor index, acceptor index), sorted
+    std::vector<double> p;                            // 4 or 5 per donor (BP, PDNS) / per acceptor (CS)
+    int npar;
+    double g0, g1, g2;                                // BP: alpha, K; CS: K_BP, K_CS, alpha; PDNS: sigma, delta
+    int64_t nd() const { return (int64_t)donors.size() / 3; }
+    int64_t na() const { return (int64_t)acceptors.size() / 3; }
+};
+
 }  // namespace
 
 struct ocm_system {
@@ -91,6 +106,7 @@ struct ocm_system {
     double box[3];
     std::vector<BondedTerm> bonded;
     std::vector<PairTerm> pairs;
+    std::vector<DATerm> das;
 };
 
 struct ocm_context {
@@ -222,7 +238,10 @@ inline void dihedral_like(const BondedTerm& t, int64_t m, double phi, double* E,
     }
 }
 
+void eval_base_stacking(const ocm_context& c, const BondedTerm& t, std::vector<Vec3>* F, double* Egroup);
+
 void eval_bonded(const ocm_context& c, const BondedTerm& t, std::vector<Vec3>* F, double* Egroup) {
+    if (t.kind == B_3SPN2_STACK) { eval_base_stacking(c, t, F, Egroup); return; }
     const double* box = c.sys.box;
     double Esum = 0;
     for (int64_t m = 0; m < t.n(); m++) {
@@ -544,6 +563,8 @@ void eval_pair(const ocm_context& c, const PairTerm& t, std::vector<Vec3>* F, do
             for (int i = 0; i < n; i++) (*F)[i] = (*F)[i] + Fl[k][i];
 }
 
+void eval_da(const ocm_context& c, const DATerm& t, std::vector<Vec3>* F, double* Egroup);
+
 void compute(const ocm_context& c, std::vector<Vec3>* F, double* Egroup, uint32_t mask) {
     if (F) F->assign(c.sys.n, Vec3{0, 0, 0});
     if (Egroup) std::fill(Egroup, Egroup + 32, 0.0);
@@ -551,6 +572,204 @@ void compute(const ocm_context& c, std::vector<Vec3>* F, double* Egroup, uint32_
         if (mask >> t.group & 1) eval_bonded(c, t, F, Egroup);
     for (const auto& t : c.sys.pairs)
         if (mask >> t.group & 1) eval_pair(c, t, F, Egroup);
+    for (const auto& t : c.sys.das)
+        if (mask >> t.group & 1) eval_da(c, t, F, Egroup);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3SPN.2 base stacking / base pairing / cross stacking and PDNS.
+// These restate the reference's Lepton expression strings LITERALLY and differentiate them with
+// forward-mode automatic differentiation (dual numbers carrying d/d(x,y,z) of up to six particles), with
+// Lepton's conventions: step(x) = (x >= 0), d step = 0, max/min differentiate the selected branch
+// (ties pick the first argument).  No hand-derived gradient is involved, so the CUDA engine's analytic
+// forces are checked against an independent derivation.
+constexpr int kND = 18;
+struct Dual {
+    double v;
+    double d[kND];
+};
+inline Dual dconst(double v) { Dual r; r.v = v; for (int k = 0; k < kND; k++) r.d[k] = 0; return r; }
+inline Dual operator+(const Dual& a, const Dual& b) { Dual r; r.v = a.v + b.v; for (int k = 0; k < kND; k++) r.d[k] = a.d[k] + b.d[k]; return r; }
+inline Dual operator-(const Dual& a, const Dual& b) { Dual r; r.v = a.v - b.v; for (int k = 0; k < kND; k++) r.d[k] = a.d[k] - b.d[k]; return r; }
+inline Dual operator-(const Dual& a) { Dual r; r.v = -a.v; for (int k = 0; k < kND; k++) r.d[k] = -a.d[k]; return r; }
+inline Dual operator*(const Dual& a, const Dual& b) { Dual r; r.v = a.v * b.v; for (int k = 0; k < kND; k++) r.d[k] = a.d[k] * b.v + a.v * b.d[k]; return r; }
+inline Dual operator/(const Dual& a, const Dual& b) { Dual r; r.v = a.v / b.v; for (int k = 0; k < kND; k++) r.d[k] = (a.d[k] - r.v * b.d[k]) / b.v; return r; }
+inline Dual operator+(const Dual& a, double b) { Dual r = a; r.v += b; return r; }
+inline Dual operator-(const Dual& a, double b) { Dual r = a; r.v -= b; return r; }
+inline Dual operator-(double a, const Dual& b) { Dual r = -b; r.v += a; return r; }
+inline Dual operator+(double a, const Dual& b) { return b + a; }
+inline Dual operator*(const Dual& a, double b) { Dual r; r.v = a.v * b; for (int k = 0; k < kND; k++) r.d[k] = a.d[k] * b; return r; }
+inline Dual operator*(double a, const Dual& b) { return b * a; }
+inline Dual chain(const Dual& a, double v, double dv) { Dual r; r.v = v; for (int k = 0; k < kND; k++) r.d[k] = dv * a.d[k]; return r; }
+inline Dual dexp(const Dual& a) { double e = std::exp(a.v); return chain(a, e, e); }
+inline Dual dsin(const Dual& a) { return chain(a, std::sin(a.v), std::cos(a.v)); }
+inline Dual dcos(const Dual& a) { return chain(a, std::cos(a.v), -std::sin(a.v)); }
+inline Dual dsqrt(const Dual& a) { double r = std::sqrt(a.v); return chain(a, r, 0.5 / r); }
+inline Dual dacos(const Dual& a) { return chain(a, std::acos(a.v), -1.0 / std::sqrt(1.0 - a.v * a.v)); }
+inline Dual datan2(const Dual& y, const Dual& x) {
+    Dual r; r.v = std::atan2(y.v, x.v);
+    const double den = x.v * x.v + y.v * y.v;
+    for (int k = 0; k < kND; k++) r.d[k] = (x.v * y.d[k] - y.v * x.d[k]) / den;
+    return r;
+}
+inline Dual dstep(const Dual& a) { return dconst(a.v >= 0.0 ? 1.0 : 0.0); }
+inline Dual dmax(const Dual& a, const Dual& b) { return (a.v >= b.v) ? a : b; }
+inline Dual dmin(const Dual& a, const Dual& b) { return (a.v <= b.v) ? a : b; }
+inline Dual dsq(const Dual& a) { return a * a; }
+
+struct DVec { Dual x, y, z; };
+inline DVec operator-(const DVec& a, const DVec& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline Dual ddot(const DVec& a, const DVec& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline DVec dcross(const DVec& a, const DVec& b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+// up to six particles; slot s carries the seeds d/d(x_s, y_s, z_s)
+struct DAGeom {
+    const ocm_context* c;
+    bool periodic;
+    int bead[6];
+    DVec pos(int s) const {
+        DVec p{dconst(c->x[bead[s]].x), dconst(c->x[bead[s]].y), dconst(c->x[bead[s]].z)};
+        p.x.d[3 * s] = 1.0; p.y.d[3 * s + 1] = 1.0; p.z.d[3 * s + 2] = 1.0;
+        return p;
+    }
+    // separation vector p_a - p_b with the minimum image (the image shift is a constant)
+    DVec sep(int a, int b) const {
+        DVec d = pos(a) - pos(b);
+        if (periodic) {
+            Vec3 raw{d.x.v, d.y.v, d.z.v}, mi = min_image(raw, c->sys.box);
+            d.x.v = mi.x; d.y.v = mi.y; d.z.v = mi.z;
+        }
+        return d;
+    }
+    Dual distance(int a, int b) const { DVec d = sep(a, b); return dsqrt(ddot(d, d)); }
+    // OpenMM angle(p1,p2,p3): angle at p2, acos of the normalised dot product
+    Dual angle(int a, int b, int c3) const {
+        DVec u = sep(a, b), w = sep(c3, b);
+        Dual cs = ddot(u, w) / dsqrt(ddot(u, u) * ddot(w, w));
+        if (cs.v > 1.0) cs.v = 1.0;
+        if (cs.v < -1.0) cs.v = -1.0;
+        return dacos(cs);
+    }
+    // OpenMM dihedral(p1,p2,p3,p4) with its sign rule, written with atan2:
+    // F = p1-p2, G = p2-p3, H = p4-p3, A = F x G, B = H x G; phi = atan2([F,G,H] |G|, A.B)
+    Dual dihedral(int a, int b, int c3, int d4) const {
+        DVec F = sep(a, b), G = sep(b, c3), H = sep(d4, c3);
+        DVec A = dcross(F, G), B = dcross(H, G);
+        Dual triple = ddot(F, dcross(G, H));
+        return datan2(triple * dsqrt(ddot(G, G)), ddot(A, B));
+    }
+};
+
+const double kPi = 3.1415926535897932385;
+// "max(f*rect0, rect1)" with f = 1 - cos(dt)^2, rect0 = step(pi+dt) step(pi-dt), rect1 = step(pi/2+dt) step(pi/2-dt)
+inline Dual modulation(const Dual& dt) {
+    Dual f = 1.0 - dsq(dcos(dt));
+    Dual rect0 = dstep(kPi + dt) * dstep(kPi - dt);
+    Dual rect1 = dstep(kPi / 2 + dt) * dstep(kPi / 2 - dt);
+    return dmax(f * rect0, rect1);
+}
+inline Dual morse_rep(double eps, double alpha, const Dual& dr) {  // eps (1 - exp(-alpha dr))^2 step(-dr)
+    return eps * dsq(1.0 - dexp(-(alpha * dr))) * dstep(-dr);
+}
+inline Dual morse_attr(double eps, double alpha, const Dual& dr) {  // eps (1 - exp(-alpha dr))^2 step(dr) - eps
+    return eps * dsq(1.0 - dexp(-(alpha * dr))) * dstep(dr) - eps;
+}
+
+inline void scatter_dual(const Dual& E, const int* bead, int nslots, std::vector<Vec3>* F) {
+    for (int s = 0; s < nslots; s++) {
+        if (bead[s] < 0) continue;
+        Vec3& f = (*F)[bead[s]];
+        f.x -= E.d[3 * s]; f.y -= E.d[3 * s + 1]; f.z -= E.d[3 * s + 2];
+    }
+}
+
+// ThreeSPN2BaseStackingForceFieldGenerator.cpp:6-21 (CustomCompoundBondForce, 3 particles)
+void eval_base_stacking(const ocm_context& c, const BondedTerm& t, std::vector<Vec3>* F, double* Egroup) {
+    double Esum = 0;
+    for (int64_t m = 0; m < t.n(); m++) {
+        DAGeom g{&c, t.periodic != 0, {t.idx[3 * m], t.idx[3 * m + 1], t.idx[3 * m + 2], -1, -1, -1}};
+        const double* p = &t.p[m * t.npar];  // eps, r0, t0, alpha, K_BS
+        Dual dr = g.distance(1, 2) - p[1];
+        Dual dt = p[4] * (g.angle(0, 1, 2) - p[2]);
+        Dual f = 1.0 - dsq(dcos(dt));
+        Dual rect1 = dstep(dt + kPi / 2) * dstep(kPi / 2 - dt);
+        Dual rect2 = dstep(dt + kPi) * dstep(kPi - dt);
+        Dual f2 = dmax(f * rect2, rect1);
+        Dual E = morse_rep(p[0], p[3], dr) + f2 * morse_attr(p[0], p[3], dr);
+        Esum += E.v;
+        if (F) scatter_dual(E, g.bead, 3, F);
+    }
+    if (Egroup) Egroup[t.group] += Esum;
+}
+
+// slots: 0,1,2 = d1,d2,d3 ; 3,4,5 = a1,a2,a3
+Dual da_energy(const ocm_context& c, const DATerm& t, int64_t d, int64_t a) {
+    DAGeom g{&c, t.periodic != 0, {t.donors[3 * d], t.donors[3 * d + 1], t.donors[3 * d + 2],
+                                  t.acceptors[3 * a], t.acceptors[3 * a + 1], t.acceptors[3 * a + 2]}};
+    enum { d1 = 0, d2 = 1, d3 = 2, a1 = 3, a2 = 4, a3 = 5 };
+    if (t.kind == DA_BASE_PAIR) {
+        // ThreeSPN2BasePairForceFieldGenerator.cpp:8-26; per-donor eps, r0, t01, t02, phi0; alpha = g0, K = g1
+        const double* p = &t.p[d * t.npar];
+        Dual dphi = g.dihedral(d2, d1, a1, a2) - p[4];
+        Dual dr = g.distance(d1, a1) - p[1];
+        Dual dt1 = t.g1 * (g.angle(d2, d1, a1) - p[2]);
+        Dual dt2 = t.g1 * (g.angle(a2, a1, d1) - p[3]);
+        Dual rep = p[0] * dsq(1.0 - dexp(-(t.g0 * dr))) * (1.0 - dstep(dr));
+        Dual attr = morse_attr(p[0], t.g0, dr);
+        return rep + 0.5 * (1.0 + dcos(dphi)) * modulation(dt1) * modulation(dt2) * attr;
+    }
+    if (t.kind == DA_CROSS_STACK) {
+        // ThreeSPN2CrossStackingForceFieldGenerator.cpp:8-31; per-acceptor eps, r0, t03, t0CS; g0 = K_BP, g1 = K_CS, g2 = alpha
+        const double* p = &t.p[a * t.npar];
+        Dual t1 = g.angle(d2, d1, a1), t2 = g.angle(d1, a1, a2), phi = g.dihedral(d2, d1, a1, a2);
+        Dual cost3 = dsin(t1) * dsin(t2) * dcos(phi) - dcos(t1) * dcos(t2);
+        Dual cost3lim = dmin(dmax(cost3, dconst(-0.99)), dconst(0.99));
+        Dual t3 = dacos(cost3lim);
+        Dual tCS = g.angle(d2, d1, a3);
+        Dual dt3 = t.g0 * (t3 - p[2]), dtCS = t.g1 * (tCS - p[3]);
+        Dual dr = g.distance(d1, a3) - p[1];
+        return modulation(dt3) * modulation(dtCS) * morse_attr(p[0], t.g2, dr) * 0.5;
+    }
+    // ProteinDNANonSpecificForceFieldGenerator.cpp:60-83; per-donor k, r0, theta0, phi0; g0 = sigma, g1 = delta
+    const double* p = &t.p[d * t.npar];
+    const double K = kPi / (2.0 * t.g1);
+    Dual t1 = g.angle(d1, d3, a1), t2 = g.angle(d3, a1, d2), phi1 = g.dihedral(d1, d3, a1, d2);
+    Dual cost1 = dsin(t1) * dsin(t2) * dcos(phi1) - dcos(t1) * dcos(t2);
+    Dual cost1lim = dmin(dmax(cost1, dconst(-0.99999)), dconst(0.99999));
+    Dual theta = dacos(cost1lim);
+    Dual phi = g.angle(d2, a1, a2);
+    Dual dtheta = K * (theta - p[2]), dphi = K * (phi - p[3]);
+    Dual dr = g.distance(d2, a1) - p[1];
+    Dual f_r = dexp(-(dsq(dr) * (1.0 / (2.0 * t.g0 * t.g0))));
+    return -(p[0] * f_r * modulation(dtheta) * modulation(dphi));
+}
+
+// all donor x acceptor combinations, not excluded, |d1 - a1| < cutoff
+template <class Fn>
+void for_each_da(const ocm_context& c, const DATerm& t, Fn fn) {
+    for (int64_t d = 0; d < t.nd(); d++)
+        for (int64_t a = 0; a < t.na(); a++) {
+            Vec3 dv = c.x[t.donors[3 * d]] - c.x[t.acceptors[3 * a]];
+            if (t.periodic) dv = min_image(dv, c.sys.box);
+            if (!(dot(dv, dv) < t.cutoff * t.cutoff)) continue;
+            if (std::binary_search(t.excl.begin(), t.excl.end(), std::make_pair((int32_t)d, (int32_t)a))) continue;
+            fn(d, a);
+        }
+}
+
+void eval_da(const ocm_context& c, const DATerm& t, std::vector<Vec3>* F, double* Egroup) {
+    double Esum = 0;
+    for_each_da(c, t, [&](int64_t d, int64_t a) {
+        Dual E = da_energy(c, t, d, a);
+        Esum += E.v;
+        if (F) {
+            int bead[6] = {t.donors[3 * d], t.donors[3 * d + 1], t.donors[3 * d + 2],
+                           t.acceptors[3 * a], t.acceptors[3 * a + 1], t.acceptors[3 * a + 2]};
+            // a bead may sit in two slots (e.g. d2 == a-side sugar never, but keep general): contributions add
+            scatter_dual(E, bead, 6, F);
+        }
+    });
+    if (Egroup) Egroup[t.group] += Esum;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -739,6 +958,66 @@ int oracle_system_add_flexible_local_dihedral(ocm_system* s, int g, int per, int
     BondedTerm& t = s->bonded.back();
     for (int q = 0; q < 7; q++) t.tab[q] = coef7[q];
     t.tab[7] = emin;
+    return 0;
+}
+
+int oracle_system_add_3spn2_base_stacking(ocm_system* s, int g, int per, int64_t n, const int32_t* ijk, const double* eps,
+                                          const double* r0, const double* theta0, double alpha, double K_BS) {
+    std::vector<double> al((size_t)std::max<int64_t>(n, 0), alpha), kb((size_t)std::max<int64_t>(n, 0), K_BS);
+    return add_bonded(s, B_3SPN2_STACK, g, per, 3, n, ijk, 5, {eps, r0, theta0, al.data(), kb.data()}, "3spn2_base_stacking");
+}
+
+static int add_da(ocm_system* s, DAKind kind, int group, const ocm_da_topology* topo, int npar, bool per_donor,
+                  std::vector<const double*> cols, double g0, double g1, double g2, const char* what) {
+    if (!s || !topo) return fail(std::string(what) + ": null argument");
+    if (group < 0 || group > 31) return fail("force group must be in 0..31");
+    if (topo->periodic && !s->has_box) return fail(std::string(what) + ": periodic term without a box");
+    if (!(topo->cutoff > 0)) return fail(std::string(what) + ": cutoff must be positive");
+    DATerm t;
+    t.kind = kind; t.group = group; t.periodic = topo->periodic ? 1 : 0; t.cutoff = topo->cutoff;
+    t.npar = npar; t.g0 = g0; t.g1 = g1; t.g2 = g2;
+    t.donors.assign(topo->donors, topo->donors + 3 * topo->n_donors);
+    t.acceptors.assign(topo->acceptors, topo->acceptors + 3 * topo->n_acceptors);
+    for (int32_t v : t.donors) if (v < -1 || v >= s->n) return fail(std::string(what) + ": donor index out of range");
+    for (int32_t v : t.acceptors) if (v < -1 || v >= s->n) return fail(std::string(what) + ": acceptor index out of range");
+    for (int64_t e = 0; e < topo->n_excl; e++) {
+        int32_t d = topo->excl_da[2 * e], a = topo->excl_da[2 * e + 1];
+        if (d < 0 || d >= topo->n_donors || a < 0 || a >= topo->n_acceptors) return fail(std::string(what) + ": exclusion index out of range");
+        t.excl.emplace_back(d, a);
+    }
+    std::sort(t.excl.begin(), t.excl.end());
+    t.excl.erase(std::unique(t.excl.begin(), t.excl.end()), t.excl.end());
+    const int64_t cnt = per_donor ? topo->n_donors : topo->n_acceptors;
+    t.p.resize((size_t)cnt * npar);
+    for (int64_t m = 0; m < cnt; m++)
+        for (int q = 0; q < npar; q++) t.p[m * npar + q] = cols[q][m];
+    s->das.push_back(std::move(t));
+    return 0;
+}
+int oracle_system_add_3spn2_base_pair(ocm_system* s, int g, const ocm_da_topology* topo, const double* eps, const double* r0,
+                                      const double* t01, const double* t02, const double* phi0, double alpha, double K_BP) {
+    return add_da(s, DA_BASE_PAIR, g, topo, 5, true, {eps, r0, t01, t02, phi0}, alpha, K_BP, 0, "3spn2_base_pair");
+}
+int oracle_system_add_3spn2_cross_stacking(ocm_system* s, int g, const ocm_da_topology* topo, const double* eps, const double* r0,
+                                           const double* t03, const double* t0CS, double K_BP, double K_CS, double alpha) {
+    return add_da(s, DA_CROSS_STACK, g, topo, 4, false, {eps, r0, t03, t0CS}, K_BP, K_CS, alpha, "3spn2_cross_stacking");
+}
+int oracle_system_add_pdns(ocm_system* s, int g, const ocm_da_topology* topo, const double* k, const double* r0,
+                           const double* theta0, const double* phi0, double sigma, double delta) {
+    return add_da(s, DA_PDNS, g, topo, 4, true, {k, r0, theta0, phi0}, sigma, delta, 0, "pdns");
+}
+int oracle_num_da_terms(const ocm_context* c) { return c ? (int)c->sys.das.size() : -1; }
+// (donor index, acceptor index) pairs of donor-acceptor term `term` evaluated at the current positions, sorted
+int oracle_get_da_pairs(ocm_context* c, int term, int32_t* da, int64_t cap, int64_t* npairs) {
+    if (!c || !npairs) return fail("null argument");
+    if (term < 0 || term >= (int)c->sys.das.size()) return fail("donor-acceptor term index out of range");
+    std::vector<std::pair<int32_t, int32_t>> out;
+    for_each_da(*c, c->sys.das[term], [&](int64_t d, int64_t a) { out.emplace_back((int32_t)d, (int32_t)a); });
+    *npairs = (int64_t)out.size();
+    if (da) {
+        if ((int64_t)out.size() > cap) return fail("get_da_pairs: capacity too small");
+        for (size_t k = 0; k < out.size(); k++) { da[2 * k] = out[k].first; da[2 * k + 1] = out[k].second; }
+    }
     return 0;
 }
 

@@ -20,7 +20,7 @@ from opencafemol_b200 import toml_input as ti  # noqa: E402
 from opencafemol_b200.capi import Library  # noqa: E402
 
 REF = "/root/reference/sample/toml_input"
-SAMPLES = {"sh3": "sh3_AICG2+.toml"}
+SAMPLES = {"sh3": "sh3_AICG2+.toml", "dna_3spn2": "dna_3SPN2.toml", "nucleosome": "nucleosome_1kx5.toml"}
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -36,8 +36,9 @@ def main():
             "source": fn,
             "energy_by_group_kj": {k: st["energy_by_group"][g] for k, g in spec.group_ids.items()},
             "kinetic_energy_kj": st["kinetic_energy"],
-            "forces": np.round(st["forces"], 9).tolist(),
-            "pairs": {str(t): ctx.neighbor_pairs(t).tolist() for t in range(ctx.num_pair_terms())},
+            "forces": np.round(st["forces"], 7).tolist(),
+            "pairs": {str(t): ctx.neighbor_pairs(t).tolist() for t in range(ctx.num_pair_terms())} if spec.mass.size < 500 else {},
+            "da_pairs": {str(t): ctx.da_pairs(t).tolist() for t in range(ctx.num_da_terms())},
         }
         with open(os.path.join(HERE, name + "_oracle.json"), "w") as fh:
             json.dump(out, fh)

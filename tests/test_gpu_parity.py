@@ -73,6 +73,67 @@ def test_hps_c2_full_size(engine, oracle):
     assert np.abs(f.sum(0)).max() < 1e-3 * np.abs(f).max()
 
 
+def check_da_sets(ctx, ora):
+    assert ctx.num_da_terms() == ora.num_da_terms()
+    for t in range(ctx.num_da_terms()):
+        assert np.array_equal(ctx.da_pairs(t), ora.da_pairs(t)), f"donor-acceptor set of term {t} differs"
+
+
+@pytest.mark.parametrize("name", ["dna_3spn2", "nucleosome"])
+def test_dna_samples(engine, oracle, name):
+    """3SPN.2 base stacking / base pairing / cross stacking, 3SPN.2 excluded volume, PDNS (config C3): the engine's
+    analytic forces against the oracle's automatic differentiation of the reference's expression strings."""
+    spec = load_golden_spec(name)
+    gold = load_golden_values(name)
+    ctx, ora = ti.make_context(engine, spec), ti.make_context(oracle, spec)
+    a, _ = check_state(ctx, ora, spec)
+    check_sets(ctx, ora)
+    check_da_sets(ctx, ora)
+    for k, gid in spec.group_ids.items():
+        ref = gold["energy_by_group_kj"][k]
+        assert abs(a["energy_by_group"][gid] - ref) <= ENERGY_TOL * max(abs(ref), 0.1)
+    assert force_error(a["forces"], np.array(gold["forces"])).max() < FORCE_TOL
+    for t in range(ctx.num_da_terms()):
+        assert ctx.da_pairs(t).tolist() == gold["da_pairs"][str(t)]
+
+
+def test_nucleosome_trajectory(engine, oracle):
+    spec = load_golden_spec("nucleosome")
+    ctx, ora = ti.make_context(engine, spec), ti.make_context(oracle, spec)
+    ctx.step(12); ora.step(12)
+    a = ctx.get_state(positions=True); b = ora.get_state(positions=True)
+    assert np.abs(a["positions"] - b["positions"]).max() < 2e-5
+    check_state(ctx, ora, spec, ftol=5e-3, etol=5e-3)
+
+
+@pytest.mark.parametrize("kind", ["3spn2_base_pair", "3spn2_cross_stacking", "pdns"])
+@pytest.mark.parametrize("periodic", [False, True])
+def test_donor_acceptor_random(engine, oracle, kind, periodic):
+    from test_oracle_kat import _da_system
+    n = 16
+    box = np.array([3.1, 2.9, 3.3]) if periodic else None
+    for seed in range(4):
+        ctxs = []
+        for lib in (engine, oracle):
+            rng = np.random.default_rng(100 + seed)
+            s = System(lib, np.full(n, 60.0), box)
+            pos = _da_system(s, rng, kind, periodic, n)
+            c = Context(s, 300.0, 0.2, 0.002, seed=3)
+            c.set_positions(pos)
+            ctxs.append(c)
+        ctx, ora = ctxs
+
+        class Spec:
+            group_ids = {"0": 0}
+        check_state(ctx, ora, Spec)
+        check_da_sets(ctx, ora)
+        ctx.step(10); ora.step(10)
+        a = ctx.get_state(positions=True); b = ora.get_state(positions=True)
+        dev = np.abs(a["positions"] - b["positions"]).max()
+        assert dev < 5e-5, f"seed {seed}: trajectories deviate by {dev:.3e} nm after 10 steps"
+        check_state(ctx, ora, Spec, ftol=2e-3, etol=2e-3)
+
+
 def test_cell_assignment_bit_exact(engine, oracle):
     import ctypes as C
     for spec in (synth.hps_slab(n_chains=12), load_golden_spec("sh3")):

@@ -6,7 +6,7 @@ import pytest
 
 from conftest import load_golden_spec, load_golden_values
 from opencafemol_b200 import synth, toml_input as ti
-from opencafemol_b200.capi import Context, PairTopology, System
+from opencafemol_b200.capi import Context, DATopology, PairTopology, System
 
 KCAL = 4.184
 
@@ -60,6 +60,7 @@ def _fd_check(lib, build, n, box=None, seed=0, h=1e-6, tol=2e-6):
             em = ctx.get_state(energy=True)["potential_energy"]
             fd[i, k] = -(ep - em) / (2 * h)
     scale = max(np.abs(f).max(), 1.0)
+    assert np.abs(f).max() > 1e-3, "vacuous check: the configuration exerts no force"
     assert np.abs(f - fd).max() / scale < tol, (np.abs(f - fd).max(), scale)
 
 
@@ -109,6 +110,98 @@ def test_bonded_finite_difference(oracle, kind, periodic):
         return _chain(n, rng)
 
     _fd_check(oracle, build, n, box, seed=BONDED.index(kind))
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_base_stacking_finite_difference(oracle, periodic):
+    n = 9
+    box = np.array([2.5, 2.2, 2.0]) if periodic else None
+
+    def build(s, rng):
+        ijk = np.array([[i, i + 1, i + 2] for i in range(n - 2)])
+        m = len(ijk)
+        # K_BS (theta - theta0) spread over all three branches of the modulating function, dr of both signs
+        s.add_3spn2_base_stacking(0, ijk, rng.uniform(10, 15, m), rng.uniform(0.3, 0.45, m), rng.uniform(1.2, 2.4, m), 30.0, 6.0, periodic)
+        return _chain(n, rng)
+
+    _fd_check(oracle, build, n, box, seed=31, tol=5e-6)
+
+
+DA_KINDS = ["3spn2_base_pair", "3spn2_cross_stacking", "pdns"]
+
+
+def _da_system(s, rng, kind, periodic, n):
+    """two rows of beads facing each other: donors on one row, acceptors on the other.  The angular stiffnesses K
+    are softer than 3SPN.2's so that random geometries populate all three branches of the modulating function."""
+    half = n // 2
+    don = np.array([[i, i + 1, i + 2] for i in range(0, half - 2)])
+    acc = np.array([[half + i, half + i + 1, half + i + 2] for i in range(0, half - 2)])
+    excl = np.array([[0, 0], [1, 2]])
+    nd, na = len(don), len(acc)
+    if kind == "3spn2_base_pair":
+        t = DATopology(donors=np.c_[don[:, :2], -np.ones(nd, int)], acceptors=np.c_[acc[:, :2], -np.ones(na, int)], cutoff=0.9, excl=excl,
+                       periodic=periodic)
+        s.add_3spn2_base_pair(0, t, rng.uniform(10, 20, nd), rng.uniform(0.45, 0.6, nd), rng.uniform(1.5, 2.6, nd),
+                              rng.uniform(1.5, 2.6, nd), rng.uniform(-1, 1, nd), 20.0, 2.0)
+    elif kind == "3spn2_cross_stacking":
+        t = DATopology(donors=don, acceptors=acc, cutoff=0.9, excl=excl, periodic=periodic)
+        s.add_3spn2_cross_stacking(0, t, rng.uniform(2, 5, na), rng.uniform(0.45, 0.65, na), rng.uniform(1.5, 2.6, na),
+                                   rng.uniform(1.5, 2.6, na), 2.0, 1.5, 40.0)
+    else:
+        t = DATopology(donors=don, acceptors=np.c_[acc[:, :2], -np.ones(na, int)], cutoff=0.9, periodic=periodic)
+        s.add_pdns(0, t, rng.uniform(1, 3, nd), rng.uniform(0.45, 0.6, nd), rng.uniform(1.2, 2.2, nd), rng.uniform(1.2, 2.2, nd),
+                   0.1, 0.4)
+    a = _chain(half, rng, 0.4)
+    b = a + np.array([0.0, 0.0, 0.55]) + rng.uniform(-0.08, 0.08, a.shape)
+    return np.concatenate([a, b])
+
+
+@pytest.mark.parametrize("kind", DA_KINDS)
+@pytest.mark.parametrize("periodic", [False, True])
+def test_donor_acceptor_finite_difference(oracle, kind, periodic):
+    """The oracle differentiates the reference's expression strings by forward-mode AD; central differences of
+    the energy check that machinery (pairs that cross the hard cutoff during the stencil are avoided by h)."""
+    n = 16
+    box = np.array([3.1, 2.9, 3.3]) if periodic else None
+    _fd_check(oracle, lambda s, rng: _da_system(s, rng, kind, periodic, n), n, box, seed=40 + DA_KINDS.index(kind), h=1e-6, tol=2e-5)
+
+
+def test_dna_3spn2_known_answers(oracle):
+    """dna_3SPN2.toml is the ideal B-DNA of its own parameter set: every Watson-Crick pair
+    sits at dr, dtheta1, dtheta2, dphi ~ 1e-4, so E_BP = -eps per pair (A-T 16.73, G-C 21.18 kJ/mol; this also
+    pins the first-wins GC angles of quirk C1 and the (d2,d1,a1,a2) ordering), every stacking step at its
+    minimum (E_BS = -sum eps), bonds and angles at theirs."""
+    spec = load_golden_spec("dna_3spn2")
+    ctx = ti.make_context(oracle, spec)
+    e = ctx.get_state(energy=True)["energy_by_group"]
+    g = spec.group_ids
+    seq_pairs = {"AT": 0, "GC": 0}
+    names = spec.names
+    bases = [x for x in names if x in "ATGC"]
+    half = len(bases) // 2
+    for k in range(half):
+        kind = "".join(sorted(bases[k] + bases[len(bases) - 1 - k]))
+        seq_pairs["AT" if kind == "AT" else "GC"] += 1
+    # non-native donor-acceptor combinations inside the 1.8 nm cutoff contribute < 0.2 % (angle-modulated to ~0)
+    assert e[g["3SPN2BasePair (A-T)"]] == pytest.approx(-16.73 * seq_pairs["AT"], rel=2e-3)
+    assert e[g["3SPN2BasePair (G-C)"]] == pytest.approx(-21.18 * seq_pairs["GC"], rel=2e-3)
+    bs = [t for t in spec.terms if t.kind == "3spn2_base_stacking"][0]
+    assert e[g["3SPN2BaseStacking"]] == pytest.approx(-np.sum(bs.args["eps"]), rel=1e-3)
+    assert abs(e[g["3SPN2Bond"]]) < 0.05 and abs(e[g["HarmonicAngle"]]) < 0.05
+    assert e[g["3SPN2ExcludedVolume"]] == 0.0
+
+
+@pytest.mark.parametrize("name", ["dna_3spn2", "nucleosome"])
+def test_dna_samples_match_golden(oracle, name):
+    spec = load_golden_spec(name)
+    gold = load_golden_values(name)
+    ctx = ti.make_context(oracle, spec)
+    st = ctx.get_state(forces=True, energy=True)
+    for k, gid in spec.group_ids.items():
+        assert st["energy_by_group"][gid] == pytest.approx(gold["energy_by_group_kj"][k], rel=1e-9, abs=1e-9)
+    assert np.allclose(st["forces"], np.array(gold["forces"]), atol=1e-6)
+    for t in range(ctx.num_da_terms()):
+        assert ctx.da_pairs(t).tolist() == gold["da_pairs"][str(t)]
 
 
 PAIRS = ["excluded_volume", "debye_huckel", "lj_repulsive", "lj_attractive", "3spn2_excluded_volume"]

@@ -394,62 +394,112 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
     int nz, ny, z0, y0;
     if (PER) { nz = min(5, ncz); z0 = (ncz >= 5) ? cz - 2 : 0; ny = min(5, ncy); y0 = (ncy >= 5) ? cy - 2 : 0; }
     else { z0 = max(cz - 2, 0); nz = min(cz + 2, ncz - 1) - z0 + 1; y0 = max(cy - 2, 0); ny = min(cy + 2, ncy - 1) - y0 + 1; }
-    // x segments: at most two contiguous runs
-    int xs[2], xe[2], nseg = 1;
+    // Geometric pruning of the 5x5x5 block: a (y,z) row of cells whose nearest edge is farther than the list radius
+    // is skipped, and the x-run of the others is cut to the chord of the sphere.  Conservative (1e-4 margins): every
+    // surviving candidate still passes through the canonical distance test, so the pair set is unchanged.
+    float fx_c, fy_c, fz_c, wx, wy, wz;  // position inside the own cell (cell units), cell widths (nm)
+    bool prune;
     if (PER) {
-        if (ncx < 5) { xs[0] = 0; xe[0] = ncx - 1; }
-        else {
-            int lo = cx - 2, hi = cx + 2;
-            if (lo < 0) { xs[0] = 0; xe[0] = hi; xs[1] = lo + ncx; xe[1] = ncx - 1; nseg = 2; }
-            else if (hi >= ncx) { xs[0] = 0; xe[0] = hi - ncx; xs[1] = lo; xe[1] = ncx - 1; nseg = 2; }
-            else { xs[0] = lo; xe[0] = hi; }
-        }
-    } else { xs[0] = max(cx - 2, 0); xe[0] = min(cx + 2, ncx - 1); }
+        const float s32 = 2.3283064365386963e-10f;
+        fx_c = (float)pi.x * s32 * (float)ncx - (float)cx; fy_c = (float)pi.y * s32 * (float)ncy - (float)cy; fz_c = (float)pi.z * s32 * (float)ncz - (float)cz;
+        wx = P.fscale[0] * 4294967296.f / (float)ncx; wy = P.fscale[1] * 4294967296.f / (float)ncy; wz = P.fscale[2] * 4294967296.f / (float)ncz;
+        prune = ncx >= 5 && ncy >= 5 && ncz >= 5;
+    } else {
+        fx_c = (__uint_as_float(pi.x) - g.lo[0]) * g.inv_w - (float)cx; fy_c = (__uint_as_float(pi.y) - g.lo[1]) * g.inv_w - (float)cy;
+        fz_c = (__uint_as_float(pi.z) - g.lo[2]) * g.inv_w - (float)cz;
+        wx = wy = wz = 1.0f / g.inv_w;
+        prune = true;
+    }
+    fx_c = fminf(fmaxf(fx_c, 0.f), 1.f); fy_c = fminf(fmaxf(fy_c, 0.f), 1.f); fz_c = fminf(fmaxf(fz_c, 0.f), 1.f);
+    const float rl2m = rl2 * 1.0002f;
 
-    for (int kz = 0; kz < nz; kz++) {
-        int oz = z0 + kz;
-        if (PER) { if (oz < 0) oz += ncz; else if (oz >= ncz) oz -= ncz; }
-        for (int ky = 0; ky < ny; ky++) {
-            int oy = y0 + ky;
-            if (PER) { if (oy < 0) oy += ncy; else if (oy >= ncy) oy -= ncy; }
-            const int rowbase = (oz * ncy + oy) * ncx;
-            for (int sgm = 0; sgm < nseg; sgm++) {
-                const int kb = L.cell_start[rowbase + xs[sgm]], ke = L.cell_start[rowbase + xe[sgm] + 1];
-                for (int k0 = kb; k0 < ke; k0 += 32) {
-                    const int k = k0 + lane;
-                    bool ok = false;
-                    unsigned int entry = 0;
-                    int zone = 3;
-                    if (k < ke && k != w) {
-                        const uint4 pj = spos[k];
-                        float dx, dy, dz;
-                        delta<PER>(pi, pj, P.fscale, dx, dy, dz);
-                        const float r2 = norm2(dx, dy, dz);
-                        if (r2 < rl2) {
-                            ok = true;
-                            if (L.cls) ok = (my_allow >> (int)L.cls[L.sorted_slots[k]]) & 1u;
-                            const int j = dh ? L.bead_of_rank[k] : (int)(pj.w & 0xFFFFFFu);
-                            for (int e = e0; ok && e < e1; e++) ok = L.excl_idx[e] != j;
-                            entry = dh ? (unsigned int)k : ((unsigned int)k | (pj.w & 0xFF000000u));
-                            zone = (r2 < za2) ? 0 : (r2 < zb2) ? 1 : (r2 < zc2) ? 2 : 3;
-                        }
-                    }
-                    const unsigned int m = __ballot_sync(0xffffffffu, ok);
-                    if (m == 0u) continue;
-                    if (!count_only) {
-                        const int pos = count + __popc(m & ((1u << lane) - 1u));
-                        if (ok && pos < stride) {
-                            if (stage) { s_row[pos] = entry; s_zone[pos] = (unsigned char)zone; }
-                            else row[pos] = entry;
-                        }
-                        if (stage) {
-                            cz0 += __popc(__ballot_sync(0xffffffffu, ok && zone == 0));
-                            cz1 += __popc(__ballot_sync(0xffffffffu, ok && zone == 1));
-                            cz2 += __popc(__ballot_sync(0xffffffffu, ok && zone == 2));
-                        }
-                    }
-                    count += __popc(m);
+    // lane r < nz*ny sets up (y,z) row r: up to two contiguous runs [kb0,ke0) [kb1,ke1) of the cell-sorted order.
+    // All rows are resolved in parallel (their cell_start look-ups overlap) and broadcast by shuffles below.
+    int kb0 = 0, ke0 = 0, kb1 = 0, ke1 = 0;
+    const int nrows = nz * ny;
+    if (lane < nrows) {
+        const int kz = lane / ny, ky = lane - kz * ny;
+        int oz = z0 + kz, oy = y0 + ky;
+        const int dzc = oz - cz, dyc = oy - cy;
+        if (PER) {
+            if (oz < 0) oz += ncz; else if (oz >= ncz) oz -= ncz;
+            if (oy < 0) oy += ncy; else if (oy >= ncy) oy -= ncy;
+        }
+        const float gz = prune ? wz * fmaxf(0.f, dzc > 0 ? (float)dzc - fz_c - 1e-4f : (dzc < 0 ? fz_c - (float)dzc - 1.f - 1e-4f : 0.f)) : 0.f;
+        const float gy = prune ? wy * fmaxf(0.f, dyc > 0 ? (float)dyc - fy_c - 1e-4f : (dyc < 0 ? fy_c - (float)dyc - 1.f - 1e-4f : 0.f)) : 0.f;
+        const float rem2 = rl2m - gz * gz - gy * gy;
+        if (rem2 >= 0.f) {
+            // x cells reached by the chord: [cx + dlo, cx + dhi] within +-2
+            int dlo = -2, dhi = 2;
+            if (prune) {
+                const float rx = sqrtf(rem2) / wx + 1e-4f;
+                dlo = max(-2, (int)floorf(fx_c - rx)); dhi = min(2, (int)floorf(fx_c + rx));
+            }
+            int xs0, xe0, xs1 = 0, xe1 = -1;
+            if (PER) {
+                if (ncx < 5) { xs0 = 0; xe0 = ncx - 1; }
+                else {
+                    const int lo = cx + dlo, hi = cx + dhi;
+                    if (lo < 0) { xs0 = 0; xe0 = hi; xs1 = lo + ncx; xe1 = ncx - 1; }
+                    else if (hi >= ncx) { xs0 = 0; xe0 = hi - ncx; xs1 = lo; xe1 = ncx - 1; }
+                    else { xs0 = lo; xe0 = hi; }
                 }
+            } else { xs0 = max(cx + dlo, 0); xe0 = min(cx + dhi, ncx - 1); }
+            const int rowbase = (oz * ncy + oy) * ncx;
+            if (xs0 <= xe0) { kb0 = L.cell_start[rowbase + xs0]; ke0 = L.cell_start[rowbase + xe0 + 1]; }
+            if (xs1 <= xe1) { kb1 = L.cell_start[rowbase + xs1]; ke1 = L.cell_start[rowbase + xe1 + 1]; }
+        }
+    }
+    // the first four exclusions of this bead live in registers
+    const int ex0 = (e0 < e1) ? L.excl_idx[e0] : -1, ex1 = (e0 + 1 < e1) ? L.excl_idx[e0 + 1] : -1;
+    const int ex2 = (e0 + 2 < e1) ? L.excl_idx[e0 + 2] : -1, ex3 = (e0 + 3 < e1) ? L.excl_idx[e0 + 3] : -1;
+
+    for (int r = 0; r < 2 * nrows; r++) {
+        const int kb = __shfl_sync(0xffffffffu, (r & 1) ? kb1 : kb0, r >> 1);
+        const int ke = __shfl_sync(0xffffffffu, (r & 1) ? ke1 : ke0, r >> 1);
+        for (int k0 = kb; k0 < ke; k0 += 64) {
+            // two 32-candidate groups per iteration: both position loads are in flight together
+            const int ka = k0 + lane, kbb = k0 + 32 + lane;
+            uint4 pja = make_uint4(0, 0, 0, 0), pjb = make_uint4(0, 0, 0, 0);
+            if (ka < ke) pja = spos[ka];
+            if (kbb < ke) pjb = spos[kbb];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int k = h ? kbb : ka;
+                const uint4 pj = h ? pjb : pja;
+                if (h && k0 + 32 >= ke) break;  // warp-uniform
+                bool ok = false;
+                unsigned int entry = 0;
+                int zone = 3;
+                if (k < ke && k != w) {
+                    float dx, dy, dz;
+                    delta<PER>(pi, pj, P.fscale, dx, dy, dz);
+                    const float r2 = norm2(dx, dy, dz);
+                    if (r2 < rl2) {
+                        ok = true;
+                        if (L.cls) ok = (my_allow >> (int)L.cls[L.sorted_slots[k]]) & 1u;
+                        const int j = dh ? L.bead_of_rank[k] : (int)(pj.w & 0xFFFFFFu);
+                        ok = ok && j != ex0 && j != ex1 && j != ex2 && j != ex3;
+                        for (int e = e0 + 4; ok && e < e1; e++) ok = L.excl_idx[e] != j;
+                        entry = dh ? (unsigned int)k : ((unsigned int)k | (pj.w & 0xFF000000u));
+                        zone = (r2 < za2) ? 0 : (r2 < zb2) ? 1 : (r2 < zc2) ? 2 : 3;
+                    }
+                }
+                const unsigned int m = __ballot_sync(0xffffffffu, ok);
+                if (m == 0u) continue;
+                if (!count_only) {
+                    const int pos = count + __popc(m & ((1u << lane) - 1u));
+                    if (ok && pos < stride) {
+                        if (stage) { s_row[pos] = entry; s_zone[pos] = (unsigned char)zone; }
+                        else row[pos] = entry;
+                    }
+                    if (stage) {
+                        cz0 += __popc(__ballot_sync(0xffffffffu, ok && zone == 0));
+                        cz1 += __popc(__ballot_sync(0xffffffffu, ok && zone == 1));
+                        cz2 += __popc(__ballot_sync(0xffffffffu, ok && zone == 2));
+                    }
+                }
+                count += __popc(m);
             }
         }
     }
@@ -1217,11 +1267,13 @@ __device__ __forceinline__ double bonded_term(int kind, const BondedDev& B, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// the fused per-step pair-force launch: every pair list in one grid (block ranges map to lists)
+// the fused per-step force launch: every pair list and every bonded kind in one grid (block ranges map to
+// segments).  Donor x acceptor terms, when a system has them, run in local_kernel on a forked graph branch.
 template <bool PER>
 __global__ void __launch_bounds__(kBlock, OCM_FORCE_MINBLOCKS) force_kernel(const WorkSeg* __restrict__ segs, int nsegs,
                                                        const PairListDev* __restrict__ lists,
-                                                       StepParams P, unsigned long long* __restrict__ fbuf) {
+                                                       const BondedDev* __restrict__ bonded, StepParams P,
+                                                       const double* __restrict__ x, unsigned long long* __restrict__ fbuf) {
     extern __shared__ __align__(16) float smem[];
     int s = 0;
     while (s + 1 < nsegs && (int)blockIdx.x >= segs[s + 1].block_begin) s++;
@@ -1244,31 +1296,23 @@ __global__ void __launch_bounds__(kBlock, OCM_FORCE_MINBLOCKS) force_kernel(cons
             case 16: pair_dh_block<PER, 16>(L, blk, sg.chunk, P, fbuf); break;
             default: pair_dh_block<PER, 32>(L, blk, sg.chunk, P, fbuf);
         }
-    }
-}
-
-// bonded terms + donor x acceptor terms (double precision, one thread per term).  Launched beside force_kernel on
-// a forked graph branch: the pair kernel keeps its own tight register budget and the two overlap.
-template <bool PER>
-__global__ void __launch_bounds__(kBlock) local_kernel(const WorkSeg* __restrict__ segs, int nsegs,
-                                                       const BondedDev* __restrict__ bonded, DAListDev da, StepParams P,
-                                                       const double* __restrict__ x, unsigned long long* __restrict__ fbuf) {
-    int s = 0;
-    while (s + 1 < nsegs && (int)blockIdx.x >= segs[s + 1].block_begin - segs[0].block_begin) s++;
-    const WorkSeg sg = segs[s];
-    const int blk = blockIdx.x - (sg.block_begin - segs[0].block_begin);
-    if (sg.kind == SEG_DA) {
-        const unsigned int m = blk * kBlock + threadIdx.x;
-        if (m < min(*da.count, (unsigned int)da.capacity)) {
-            const uint2 e = da.entries[m];
-            const DATermDev& T = da.terms[e.x >> 24];
-            const int d = (int)(e.x & 0xFFFFFFu), a = (int)e.y;
-            if (da_r2(T, d, a, P, x) < T.rc2) da_eval(T, d, a, P, x, fbuf);
-        }
     } else {
         const BondedDev& B = bonded[sg.id];
         const int m = blk * kBlock + threadIdx.x;
         if (m < B.n) { int g; bonded_term(sg.id, B, m, P, x, fbuf, &g); }
+    }
+}
+
+// donor x acceptor terms (double precision, one thread per listed combination).  Launched beside force_kernel on
+// a forked graph branch, so the pair kernel keeps its own tight register budget and the two overlap.
+__global__ void __launch_bounds__(kBlock) local_kernel(DAListDev da, StepParams P, const double* __restrict__ x,
+                                                       unsigned long long* __restrict__ fbuf) {
+    const unsigned int m = blockIdx.x * kBlock + threadIdx.x;
+    if (m < min(*da.count, (unsigned int)da.capacity)) {
+        const uint2 e = da.entries[m];
+        const DATermDev& T = da.terms[e.x >> 24];
+        const int d = (int)(e.x & 0xFFFFFFu), a = (int)e.y;
+        if (da_r2(T, d, a, P, x) < T.rc2) da_eval(T, d, a, P, x, fbuf);
     }
 }
 

@@ -440,14 +440,14 @@ static void build_segments(ocm_context* c) {
         if (staged) smem = std::max(smem, staged_bytes);
         else if (L.dev.smem_tab) smem = std::max(smem, tab_bytes);
     }
-    c->pair_blocks = blk;
-    c->n_pair_segs = (int)c->segs.size();
     for (int k = 0; k < B_NUM_KINDS; k++) {
         if (c->bonded_h[k].n == 0) continue;
         int nb = (c->bonded_h[k].n + kBlock - 1) / kBlock;
         c->segs.push_back({blk, nb, SEG_BONDED, k, 0, 0, 0});
         blk += nb;
     }
+    c->pair_blocks = blk;  // blocks of force_kernel: pair lists + bonded kinds
+    c->n_pair_segs = (int)c->segs.size();
     if (c->da.nterms > 0 && c->da.capacity > 0) {
         int nb = (c->da.capacity + kBlock - 1) / kBlock;
         c->segs.push_back({blk, nb, SEG_DA, 0, 0, 0, 0});
@@ -620,15 +620,13 @@ static void enqueue_forces(ocm_context* c, cudaStream_t s) {
             CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
             sl = c->side;
         }
-        const WorkSeg* ls = c->d_segs.p + c->n_pair_segs;
-        if (c->periodic) local_kernel<true><<<c->local_blocks, kBlock, 0, sl>>>(ls, c->n_local_segs, c->d_bonded.p, c->da, c->P, c->x.p, c->fbuf.p);
-        else local_kernel<false><<<c->local_blocks, kBlock, 0, sl>>>(ls, c->n_local_segs, c->d_bonded.p, c->da, c->P, c->x.p, c->fbuf.p);
+        local_kernel<<<c->local_blocks, kBlock, 0, sl>>>(c->da, c->P, c->x.p, c->fbuf.p);
         if (fork) CUDA_TRY(cudaEventRecord(c->ev_join, c->side));
         c->n_launches += 1;
     }
     if (c->pair_blocks > 0) {
-        if (c->periodic) force_kernel<true><<<c->pair_blocks, kBlock, c->smem_bytes, s>>>(c->d_segs.p, c->n_pair_segs, c->d_lists.p, c->P, c->fbuf.p);
-        else force_kernel<false><<<c->pair_blocks, kBlock, c->smem_bytes, s>>>(c->d_segs.p, c->n_pair_segs, c->d_lists.p, c->P, c->fbuf.p);
+        if (c->periodic) force_kernel<true><<<c->pair_blocks, kBlock, c->smem_bytes, s>>>(c->d_segs.p, c->n_pair_segs, c->d_lists.p, c->d_bonded.p, c->P, c->x.p, c->fbuf.p);
+        else force_kernel<false><<<c->pair_blocks, kBlock, c->smem_bytes, s>>>(c->d_segs.p, c->n_pair_segs, c->d_lists.p, c->d_bonded.p, c->P, c->x.p, c->fbuf.p);
         c->n_launches += 1;
     }
     if (fork) CUDA_TRY(cudaStreamWaitEvent(s, c->ev_join, 0));

@@ -142,11 +142,11 @@ def _da_system(s, rng, kind, periodic, n):
         t = DATopology(donors=np.c_[don[:, :2], -np.ones(nd, int)], acceptors=np.c_[acc[:, :2], -np.ones(na, int)], cutoff=0.9, excl=excl,
                        periodic=periodic)
         s.add_3spn2_base_pair(0, t, rng.uniform(10, 20, nd), rng.uniform(0.45, 0.6, nd), rng.uniform(1.5, 2.6, nd),
-                              rng.uniform(1.5, 2.6, nd), rng.uniform(-1, 1, nd), 20.0, 2.0)
+                              rng.uniform(1.5, 2.6, nd), rng.uniform(-1, 1, nd), 6.0, 2.0)
     elif kind == "3spn2_cross_stacking":
         t = DATopology(donors=don, acceptors=acc, cutoff=0.9, excl=excl, periodic=periodic)
         s.add_3spn2_cross_stacking(0, t, rng.uniform(2, 5, na), rng.uniform(0.45, 0.65, na), rng.uniform(1.5, 2.6, na),
-                                   rng.uniform(1.5, 2.6, na), 2.0, 1.5, 40.0)
+                                   rng.uniform(1.5, 2.6, na), 2.0, 1.5, 8.0)
     else:
         t = DATopology(donors=don, acceptors=np.c_[acc[:, :2], -np.ones(na, int)], cutoff=0.9, periodic=periodic)
         s.add_pdns(0, t, rng.uniform(1, 3, nd), rng.uniform(0.45, 0.6, nd), rng.uniform(1.2, 2.2, nd), rng.uniform(1.2, 2.2, nd),

@@ -185,6 +185,21 @@ int  ocm_context_create(const ocm_system* sys, double temperature_K, double fric
                         double dt_ps, uint64_t seed, int device_index, ocm_context** out);
 void ocm_context_destroy(ocm_context* ctx);
 
+/* Replica ensemble: n_replicas independent copies of `sys` (unlimited boundary only) advanced by the same kernel
+ * launches; replica r integrates with seeds[r] and follows exactly the trajectory a stand-alone context with that
+ * seed would.  What the reference runs as n_replicas processes, each with its own OpenMM::Context
+ * (src/Simulator.cpp:14-17).  Every per-bead array of the calls below then has n_replicas * N entries, replica-major;
+ * ocm_set_velocities_to_temperature gives replica r the seed `seed + r`; ocm_get_state reports energies summed over
+ * the replicas. */
+int ocm_context_create_batch(const ocm_system* sys, int32_t n_replicas, double temperature_K,
+                             double friction_inv_ps, double dt_ps, const uint64_t* seeds,
+                             int device_index, ocm_context** out);
+int ocm_num_replicas(const ocm_context* ctx);
+/* per-replica energies: epot[n_replicas] (groups in group_mask), ekin[n_replicas], epot_by_group[32 * n_replicas];
+ * any pointer may be NULL */
+int ocm_get_replica_energies(ocm_context*, uint32_t group_mask, double* epot, double* ekin,
+                             double* epot_by_group);
+
 /* tunables: "skin_nm" (Verlet buffer), "nstlist" (0 = adaptive), "threads_per_bead" */
 int ocm_context_set_option(ocm_context*, const char* key, double value);
 int ocm_context_get_option(ocm_context*, const char* key, double* value);

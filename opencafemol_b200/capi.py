@@ -191,6 +191,12 @@ class Library:
             [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)],
         ),
         "context_destroy": (None, [C.c_void_p]),
+        "context_create_batch": (
+            C.c_int,
+            [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_void_p)],
+        ),
+        "num_replicas": (C.c_int, [C.c_void_p]),
+        "get_replica_energies": (C.c_int, [C.c_void_p, C.c_uint32, _f64p, _f64p, _f64p]),
         "context_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
         "context_get_option": (C.c_int, [C.c_void_p, C.c_char_p, _f64p]),
         "set_positions": (C.c_int, [C.c_void_p, _f64p]),
@@ -413,13 +419,24 @@ class System:
 class Context:
     """OpenMM::Context + LangevinIntegrator equivalent."""
 
-    def __init__(self, system: System, temperature, friction, dt, seed=0, device=0):
+    def __init__(self, system: System, temperature, friction, dt, seed=0, device=0, replica_seeds=None):
         self.lib = system.lib
-        self.n = system.n
         h = C.c_void_p()
-        self.lib.check(
-            self.lib.fn["context_create"](system.handle, float(temperature), float(friction), float(dt), int(seed), int(device), C.byref(h))
-        )
+        if replica_seeds is None:
+            self.n = system.n
+            self.n_replicas = 1
+            self.lib.check(
+                self.lib.fn["context_create"](system.handle, float(temperature), float(friction), float(dt), int(seed), int(device), C.byref(h))
+            )
+        else:
+            # replica ensemble: one context, len(replica_seeds) independent copies of the system
+            seeds = np.ascontiguousarray(np.asarray(replica_seeds, np.uint64))
+            self.n_replicas = int(seeds.size)
+            self.n = system.n * self.n_replicas
+            self.lib.check(
+                self.lib.fn["context_create_batch"](system.handle, self.n_replicas, float(temperature), float(friction), float(dt),
+                                                    seeds.ctypes.data_as(C.POINTER(C.c_uint64)), int(device), C.byref(h))
+            )
         self.handle = h
         self.pair_terms = list(system.pair_terms)
 
@@ -486,6 +503,12 @@ class Context:
             out["kinetic_energy"] = ek.value
             out["energy_by_group"] = ebg
         return out
+
+    def replica_energies(self, groups=0xFFFFFFFF):
+        r = self.n_replicas
+        ep, ek, ebg = np.zeros(r), np.zeros(r), np.zeros((r, 32))
+        self.lib.check(self.lib.fn["get_replica_energies"](self.handle, int(groups) & 0xFFFFFFFF, _p(ep, _f64p), _p(ek, _f64p), _p(ebg, _f64p)))
+        return {"potential_energy": ep, "kinetic_energy": ek, "energy_by_group": ebg}
 
     def num_pair_terms(self):
         return int(self.lib.fn["num_pair_terms"](self.handle))

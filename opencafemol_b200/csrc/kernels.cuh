@@ -36,6 +36,7 @@ struct GridDev {
 
 struct PairListDev {
     int np, stride, ntypes, ncls, form, nmem, has_switch, smem_tab;
+    int nrep, nper;             // replica batch: cells are keyed (replica, local cell); pairs never cross replicas
     const int* part;            // [np] bead index of each participant slot, ascending
     const unsigned char* type;  // [np]
     const signed char* cls;     // [np] interaction class or null
@@ -116,6 +117,11 @@ struct StepParams {
     float a, b, c;     // Langevin coefficients
     unsigned int seed_lo, seed_hi;
     float half_skin2;
+    // replica batch (unlimited boundary only): beads [r*nper, (r+1)*nper) form replica r, which has its own noise
+    // key and its own local frame (pair-kernel positions are FP32 offsets from the replica's origin)
+    int nrep, nper;
+    const double* origin;       // [3*nrep] or null (single system, origin 0)
+    const uint2* rep_seed;      // [nrep] or null
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -202,10 +208,27 @@ __global__ void canon_kernel(StepParams P, const double* __restrict__ x, uint4* 
     if (P.periodic) {
         q.x = to_fix(px, P.inv_box[0]); q.y = to_fix(py, P.inv_box[1]); q.z = to_fix(pz, P.inv_box[2]);
     } else {
+        if (P.origin) { const double* o = P.origin + 3 * (i / P.nper); px -= o[0]; py -= o[1]; pz -= o[2]; }
         q.x = __float_as_uint((float)px); q.y = __float_as_uint((float)py); q.z = __float_as_uint((float)pz);
     }
     q.w = 0;
     posq[i] = q;
+}
+
+// replica batch: move every replica's local frame to its current centroid (one warp per replica).  Forces are
+// translation invariant, so this only keeps the FP32 offsets small and the shared cell grid compact.
+__global__ void recentre_kernel(StepParams P, const double* __restrict__ x, double* __restrict__ origin) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= P.nrep) return;
+    double sx = 0, sy = 0, sz = 0;
+    for (int k = lane; k < P.nper; k += 32) {
+        const int i = r * P.nper + k;
+        sx += x[3 * i]; sy += x[3 * i + 1]; sz += x[3 * i + 2];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    if (lane == 0) { origin[3 * r] = sx / P.nper; origin[3 * r + 1] = sy / P.nper; origin[3 * r + 2] = sz / P.nper; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -250,7 +273,7 @@ __global__ void grid_kernel(const PairListDev* lists, int li) {
             nc[k] = max(1, min(v, 1024));
             tot *= nc[k];
         }
-        if (tot <= (long long)L.max_cells) break;
+        if (tot <= (long long)(L.max_cells / L.nrep)) break;
         w *= 1.26f;
     }
     for (int k = 0; k < 3; k++) {
@@ -281,24 +304,31 @@ __global__ void bin_kernel(const PairListDev* lists, int li, const uint4* __rest
     if (a >= L.np) return;
     const GridDev& g = *L.grid;
     int cx, cy, cz;
-    cell_coords<PER>(g, posq[L.part[a]], cx, cy, cz);
+    const int bead = L.part[a];
+    cell_coords<PER>(g, posq[bead], cx, cy, cz);
     int c = (cz * g.nc[1] + cy) * g.nc[0] + cx;
+    if (L.nrep > 1) c += (bead / L.nper) * g.ncell;
     L.cell_of_slot[a] = c;
     atomicAdd(&L.cell_count[c], 1);
 }
 
-// single block: exclusive scan of cell_count[0..ncell) -> cell_start, cursor; zero the counts
+// single block: exclusive scan of cell_count[0..ncell*nrep) -> cell_start, cursor; zero the counts.
+// Every thread owns kScanItems consecutive cells per pass, so large (replica-keyed) grids stay cheap.
+constexpr int kScanItems = 8;
 __global__ void scan_kernel(const PairListDev* lists, int li) {
     const PairListDev& L = lists[li];
-    const int ncell = L.grid->ncell;
+    const int ncell = L.grid->ncell * L.nrep;
     __shared__ int warp_sums[32];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int base = 0; base < ncell; base += blockDim.x) {
-        int i = base + threadIdx.x;
-        int v = (i < ncell) ? L.cell_count[i] : 0;
+    for (int base = 0; base < ncell; base += blockDim.x * kScanItems) {
+        const int i0 = base + threadIdx.x * kScanItems;
+        int vals[kScanItems];
+        int v = 0;
+#pragma unroll
+        for (int q = 0; q < kScanItems; q++) { vals[q] = (i0 + q < ncell) ? L.cell_count[i0 + q] : 0; v += vals[q]; }
         int s = v;
         for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, s, o);
@@ -315,8 +345,12 @@ __global__ void scan_kernel(const PairListDev* lists, int li) {
             warp_sums[lane] = ws;  // inclusive
         }
         __syncthreads();
-        int excl = carry + (wid > 0 ? warp_sums[wid - 1] : 0) + s - v;
-        if (i < ncell) { L.cell_start[i] = excl; L.cell_cursor[i] = excl; L.cell_count[i] = 0; }
+        int run = carry + (wid > 0 ? warp_sums[wid - 1] : 0) + s - v;
+#pragma unroll
+        for (int q = 0; q < kScanItems; q++) {
+            if (i0 + q < ncell) { L.cell_start[i0 + q] = run; L.cell_cursor[i0 + q] = run; L.cell_count[i0 + q] = 0; }
+            run += vals[q];
+        }
         __syncthreads();
         if (threadIdx.x == 0) carry += warp_sums[nw - 1];
         __syncthreads();
@@ -377,8 +411,10 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
     const bool dh = L.form == SEG_PAIR_DH;
     const int a = L.sorted_slots[w];
     const uint4 pi = spos[w];
-    const int ci = L.cell_of_slot[a];
+    const int cig = L.cell_of_slot[a];
     const int ncx = g.nc[0], ncy = g.nc[1], ncz = g.nc[2];
+    const int cell_base = (L.nrep > 1) ? (cig / g.ncell) * g.ncell : 0;  // first cell of this bead's replica
+    const int ci = cig - cell_base;
     const int cx = ci % ncx, cy = (ci / ncx) % ncy, cz = ci / (ncx * ncy);
     const int e0 = L.excl_off[a], e1 = L.excl_off[a + 1];
     const unsigned int my_allow = L.cls ? L.allow[(int)L.cls[a]] : 0xffffffffu;
@@ -445,7 +481,7 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
                     else { xs0 = lo; xe0 = hi; }
                 }
             } else { xs0 = max(cx + dlo, 0); xe0 = min(cx + dhi, ncx - 1); }
-            const int rowbase = (oz * ncy + oy) * ncx;
+            const int rowbase = cell_base + (oz * ncy + oy) * ncx;
             if (xs0 <= xe0) { kb0 = L.cell_start[rowbase + xs0]; ke0 = L.cell_start[rowbase + xe0 + 1]; }
             if (xs1 <= xe1) { kb1 = L.cell_start[rowbase + xs1]; ke1 = L.cell_start[rowbase + xe1 + 1]; }
         }
@@ -1362,8 +1398,10 @@ __global__ void integrate_kernel(StepParams P, double* __restrict__ x, float4* _
         const float im = vi.w;
         if (im > 0.f) {
             float g0, g1, g2;
-            normals3(philox4x32_10(make_uint4((unsigned int)i, (unsigned int)step, (unsigned int)(step >> 32), 0u),
-                                   make_uint2(P.seed_lo, P.seed_hi)), g0, g1, g2);
+            const int rep = (P.nrep > 1) ? i / P.nper : 0;
+            const uint2 key = P.rep_seed ? P.rep_seed[rep] : make_uint2(P.seed_lo, P.seed_hi);
+            normals3(philox4x32_10(make_uint4((unsigned int)(i - rep * P.nper), (unsigned int)step, (unsigned int)(step >> 32), 0u), key),
+                     g0, g1, g2);
             const float cs = P.c * sqrtf(im), bm = P.b * im;
             vi.x = P.a * vi.x + bm * fx + cs * g0;
             vi.y = P.a * vi.y + bm * fy + cs * g1;
@@ -1374,7 +1412,11 @@ __global__ void integrate_kernel(StepParams P, double* __restrict__ x, float4* _
             x[3 * i] = px; x[3 * i + 1] = py; x[3 * i + 2] = pz;
             uint4 q;
             if (P.periodic) { q.x = to_fix(px, P.inv_box[0]); q.y = to_fix(py, P.inv_box[1]); q.z = to_fix(pz, P.inv_box[2]); }
-            else { q.x = __float_as_uint((float)px); q.y = __float_as_uint((float)py); q.z = __float_as_uint((float)pz); }
+            else {
+                double lx = px, ly = py, lz = pz;
+                if (P.origin) { const double* o = P.origin + 3 * rep; lx -= o[0]; ly -= o[1]; lz -= o[2]; }
+                q.x = __float_as_uint((float)lx); q.y = __float_as_uint((float)ly); q.z = __float_as_uint((float)lz);
+            }
             q.w = 0;
             posq[i] = q;
             // refresh the cell-sorted copies the pair kernels read (w keeps bead | type)
@@ -1407,12 +1449,15 @@ __global__ void integrate_kernel(StepParams P, double* __restrict__ x, float4* _
 }
 
 // v = sqrt(kT/m) N(0,1), noise stream 1 (Context::setVelocitiesToTemperature)
-__global__ void init_velocity_kernel(int n, float kT, unsigned int seed_lo, unsigned int seed_hi, float4* __restrict__ v) {
+__global__ void init_velocity_kernel(int n, int nper, float kT, unsigned long long seed, float4* __restrict__ v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 vi = v[i];
     float g0, g1, g2;
-    normals3(philox4x32_10(make_uint4((unsigned int)i, 0u, 0u, 1u), make_uint2(seed_lo, seed_hi)), g0, g1, g2);
+    // replica r of a batch draws from seed + r with its local bead index: the same numbers as a standalone run
+    const int rep = i / nper;
+    const unsigned long long sd = seed + (unsigned long long)rep;
+    normals3(philox4x32_10(make_uint4((unsigned int)(i - rep * nper), 0u, 0u, 1u), make_uint2((unsigned int)sd, (unsigned int)(sd >> 32))), g0, g1, g2);
     const float s = vi.w > 0.f ? sqrtf(kT * vi.w) : 0.f;
     vi.x = s * g0; vi.y = s * g1; vi.z = s * g2;
     v[i] = vi;
@@ -1458,6 +1503,16 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(const WorkSeg* __restric
                 if (da_r2(T, d, a, P, x) < T.rc2) { E = da_eval(T, d, a, P, x, nullptr); g = T.group; }
             }
         }
+        if (P.nrep > 1) {
+            // replica batch: energies are kept per replica (40 slots each); bonded terms never span replicas
+            if (g >= 0 && sg.kind == SEG_BONDED) {
+                const BondedDev& B = bonded[sg.id];
+                const int nbody = (sg.id <= 3) ? 2 : ((sg.id <= 5 || sg.id == 9) ? 3 : 4);
+                const int rep = B.idx[nbody * (blk * kBlock + threadIdx.x)] / P.nper;
+                atomicAdd(&egroup[rep * 40 + g], E);
+            }
+            return;
+        }
         // terms handled by one block may belong to different groups: accumulate per distinct group
         for (int gg = 0; gg < 32; gg++) {
             const unsigned int any = __syncthreads_or(g == gg);
@@ -1476,6 +1531,8 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(const WorkSeg* __restric
         const int trow = (int)(pi.w >> 24) * nt;
         const int n = L.nbr_count[k];
         const unsigned int* row = L.nbr + (size_t)k * L.stride;
+        double Ekeep[kMaxMembers];
+        if (P.nrep > 1) for (int m = 0; m < kMaxMembers; m++) { Ekeep[m] = Em[m]; Em[m] = 0.0; }
         for (int t = sl; t < n; t += T) {
             const unsigned int e = row[t];
             const uint4 pj = L.spos[e & 0xFFFFFFu];
@@ -1504,7 +1561,17 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(const WorkSeg* __restric
                 }
             }
         }
+        if (P.nrep > 1) {
+            // this bead's share goes to its replica's slots (full list: each pair is seen twice)
+            const int rep = L.bead_of_rank[k] / P.nper;
+            const int nmm = (sg.kind == SEG_PAIR_DH) ? 1 : L.nmem;
+            for (int m = 0; m < nmm; m++) {
+                if (Em[m] != 0.0) atomicAdd(&egroup[rep * 40 + L.mem_group[m]], 0.5 * Em[m]);
+                Em[m] = Ekeep[m];
+            }
+        }
     }
+    if (P.nrep > 1) return;
     const int nm = (sg.kind == SEG_PAIR_DH) ? 1 : L.nmem;
     for (int m = 0; m < nm; m++) block_add(0.5 * Em[m], &egroup[L.mem_group[m]]);  // full list: each pair twice
 }
@@ -1522,7 +1589,8 @@ __global__ void kinetic_kernel(StepParams P, const float4* __restrict__ v, const
             e = 0.5 / im * (vx * vx + vy * vy + vz * vz);
         }
     }
-    block_add(e, ke);
+    if (P.nrep > 1) { if (i < P.n) atomicAdd(&ke[(i / P.nper) * 40], e); }
+    else block_add(e, ke);
 }
 
 // pairs (i<j) of list `li` inside rc2_term, appended unordered (host sorts)

@@ -93,6 +93,10 @@ struct ocm_context {
     uint64_t seed = 0;
     int64_t step = 0;
     int device = 0;
+    int nrep = 1, nper = 0;                 // replica batch: nrep independent copies of nper beads
+    std::vector<uint64_t> rep_seeds;
+    DevBuf<double> origin;                  // [3*nrep] local-frame origins (replica batch)
+    DevBuf<uint2> d_rep_seed;
     cudaStream_t stream = nullptr;
     StepParams P{};
 
@@ -290,6 +294,7 @@ static void compile_list(ocm_context* c, PairListHost& L) {
     PairListDev& D = L.dev;
     std::memset(&D, 0, sizeof(D));
     D.np = L.np; D.ntypes = nt; D.ncls = t0.ncls; D.form = L.form; D.nmem = nm;
+    D.nrep = c->nrep; D.nper = c->nper;
     for (int k = 0; k < t0.ncls && k < 32; k++) D.allow[k] = t0.allow[k];
     D.rc2 = (float)(L.rc_list * L.rc_list);
     D.rsw = (float)L.rc_list; D.inv_sw = 0.f; D.has_switch = 0;
@@ -392,7 +397,7 @@ static void configure_grid(ocm_context* c, PairListHost& L) {
         L.max_cells = g.ncell;
     } else {
         g.nc[0] = g.nc[1] = g.nc[2] = 1; g.ncell = 1; g.inv_w = 1.0f / D.wmin;
-        L.max_cells = std::max(4096, std::min(1 << 21, 8 * L.np + 64));
+        L.max_cells = std::max(std::max(4096, 64 * c->nrep), std::min(1 << 21, 8 * L.np + 64));
     }
     L.grid.upload(std::vector<GridDev>(1, g));
     L.cell_count.alloc(L.max_cells + 1); L.cell_count.zero();
@@ -570,6 +575,9 @@ static void update_params(ocm_context* c) {
     P.c = (float)std::sqrt(kBoltz * c->T * (1.0 - a * a));
     P.seed_lo = (unsigned int)c->seed; P.seed_hi = (unsigned int)(c->seed >> 32);
     P.half_skin2 = (float)(0.25 * c->skin * c->skin);
+    P.nrep = c->nrep; P.nper = c->nper;
+    P.origin = c->nrep > 1 ? c->origin.p : nullptr;
+    P.rep_seed = c->nrep > 1 ? c->d_rep_seed.p : nullptr;
 }
 
 // ---- enqueue helpers ----------------------------------------------------------------------------
@@ -586,6 +594,12 @@ static void launch_build(ocm_context* c, PairListHost& L, int li, cudaStream_t s
 
 static void enqueue_rebuild(ocm_context* c, cudaStream_t s, bool count_only) {
     const int n = c->n;
+    if (c->nrep > 1) {
+        // replica batch: re-centre every replica's local frame, then refresh the FP32 offsets
+        recentre_kernel<<<nblk(c->nrep * 32, 128), 128, 0, s>>>(c->P, c->x.p, c->origin.p);
+        canon_kernel<<<nblk(n, 256), 256, 0, s>>>(c->P, c->x.p, c->posq.p);
+        c->n_launches += 2;
+    }
     if (!count_only) save_ref_kernel<<<nblk(3 * n, 256), 256, 0, s>>>(n, c->x.p, c->xref.p);
     for (size_t l = 0; l < c->lists.size(); l++) {
         auto& L = *c->lists[l];
@@ -637,6 +651,10 @@ static void size_lists(ocm_context* c, double growth) {
     cudaStream_t s = c->stream;
     for (auto& L : c->lists) configure_grid(c, *L);
     upload_lists(c);
+    if (c->nrep > 1) {
+        recentre_kernel<<<nblk(c->nrep * 32, 128), 128, 0, s>>>(c->P, c->x.p, c->origin.p);
+        canon_kernel<<<nblk(c->n, 256), 256, 0, s>>>(c->P, c->x.p, c->posq.p);
+    }
     std::vector<int> fl(FLAG_COUNT, 0);
     // one counting pass per list: FLAG_MAXDISP+1 receives the largest neighbour count of that list
     for (size_t l = 0; l < c->lists.size(); l++) {
@@ -730,6 +748,7 @@ static cudaGraphExec_t window_graph(ocm_context* c, int nst) {
 static double launches_per_window(const ocm_context* c, int nst) {
     double per_rebuild = 1;
     for (auto& L : c->lists) if (L->np) per_rebuild += c->periodic ? 5 : 7;
+    if (c->nrep > 1) per_rebuild += 2;
     if (c->da.nterms > 0 && c->da.ncand > 0) per_rebuild += 1;
     return per_rebuild + nst * (1.0 + (c->pair_blocks > 0 ? 1.0 : 0.0) + (c->local_blocks > 0 ? 1.0 : 0.0));
 }
@@ -940,9 +959,14 @@ int ocm_system_add_3spn2_excluded_volume(ocm_system* s, int g, double rc, const 
     return add_pair(s, P_3SPN2EXV, g, rc, rc, 0, 0, 0, eps, sigma, topo, "3spn2_excluded_volume");
 }
 
-int ocm_context_create(const ocm_system* sys, double T, double gamma, double dt, uint64_t seed, int device, ocm_context** out) {
-    if (!sys || !out) return fail("context_create: bad arguments");
+static int create_context(const ocm_system* sys, int nrep, double T, double gamma, double dt, const uint64_t* seeds, int device,
+                          ocm_context** out) {
+    if (!sys || !out || !seeds) return fail("context_create: bad arguments");
     if (!(dt > 0)) return fail("context_create: time step must be positive");
+    if (nrep < 1) return fail("context_create_batch: at least one replica");
+    if (nrep > 1 && sys->has_box) return fail("context_create_batch: replica batches need an unlimited boundary (no box)");
+    if (nrep > 1 && !sys->das.empty()) return fail("context_create_batch: donor-acceptor terms are not supported in replica batches yet");
+    if ((int64_t)sys->n * nrep >= (1 << 24)) return fail("context_create: at most 16,777,215 particles are supported");
     int ndev = ocm_device_count();
     if (ndev <= 0) return fail("context_create: no CUDA device available (this engine has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail("context_create: device index out of range");
@@ -950,7 +974,41 @@ int ocm_context_create(const ocm_system* sys, double T, double gamma, double dt,
     OCM_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(device));
     c = new ocm_context();
-    c->sys = *sys; c->n = sys->n; c->periodic = sys->has_box;
+    c->nrep = nrep; c->nper = sys->n;
+    if (nrep == 1) c->sys = *sys;
+    else {
+        // the batch is one big system: every table replicated with shifted bead indices
+        const int np = sys->n;
+        ocm_system& S = c->sys;
+        S.n = np * nrep; S.has_box = false;
+        S.mass.reserve((size_t)S.n);
+        for (int r = 0; r < nrep; r++) S.mass.insert(S.mass.end(), sys->mass.begin(), sys->mass.end());
+        for (const auto& t : sys->bonded) {
+            BondedTerm u = t;
+            u.idx.clear(); u.p.clear();
+            u.idx.reserve(t.idx.size() * nrep); u.p.reserve(t.p.size() * nrep);
+            for (int r = 0; r < nrep; r++) {
+                for (int32_t v : t.idx) u.idx.push_back(v + r * np);
+                u.p.insert(u.p.end(), t.p.begin(), t.p.end());
+            }
+            S.bonded.push_back(std::move(u));
+        }
+        for (const auto& t : sys->pairs) {
+            PairTerm u = t;
+            u.p0.clear(); u.p1.clear(); u.part.clear(); u.excl.clear(); u.cls.clear();
+            for (int r = 0; r < nrep; r++) {
+                u.p0.insert(u.p0.end(), t.p0.begin(), t.p0.end());
+                u.p1.insert(u.p1.end(), t.p1.begin(), t.p1.end());
+                u.cls.insert(u.cls.end(), t.cls.begin(), t.cls.end());
+                for (int32_t v : t.part) u.part.push_back(v + r * np);
+                for (auto& e : t.excl) u.excl.emplace_back(e.first + r * np, e.second + r * np);
+            }
+            S.pairs.push_back(std::move(u));
+        }
+    }
+    c->n = c->sys.n; c->periodic = c->sys.has_box;
+    c->rep_seeds.assign(seeds, seeds + nrep);
+    const uint64_t seed = seeds[0];
     c->T = T; c->gamma = gamma; c->dt = dt; c->seed = seed; c->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
@@ -963,10 +1021,16 @@ int ocm_context_create(const ocm_system* sys, double T, double gamma, double dt,
     const int n = c->n;
     c->x.alloc(3 * (size_t)n); c->xref.alloc(3 * (size_t)n); c->xbak.alloc(3 * (size_t)n);
     c->v.alloc(n); c->vbak.alloc(n); c->posq.alloc(n); c->fbuf.alloc(3 * (size_t)n);
-    c->flags.alloc(FLAG_COUNT); c->step_base.alloc(1); c->egroup.alloc(40); c->pair_counter.alloc(1);
+    c->flags.alloc(FLAG_COUNT); c->step_base.alloc(1); c->egroup.alloc((size_t)40 * nrep); c->pair_counter.alloc(1);
     c->x.zero(); c->xref.zero(); c->fbuf.zero(); c->flags.zero(); c->step_base.zero(); c->posq.zero();
+    if (nrep > 1) {
+        c->origin.alloc((size_t)3 * nrep); c->origin.zero();
+        std::vector<uint2> ks(nrep);
+        for (int r = 0; r < nrep; r++) ks[r] = make_uint2((unsigned int)seeds[r], (unsigned int)(seeds[r] >> 32));
+        c->d_rep_seed.upload(ks);
+    }
     std::vector<float4> v0(n);
-    for (int i = 0; i < n; i++) v0[i] = make_float4(0, 0, 0, sys->mass[i] > 0 ? (float)(1.0 / sys->mass[i]) : 0.f);
+    for (int i = 0; i < n; i++) v0[i] = make_float4(0, 0, 0, c->sys.mass[i] > 0 ? (float)(1.0 / c->sys.mass[i]) : 0.f);
     CUDA_TRY(cudaMemcpy(c->v.p, v0.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
     // default skin: 8 % of the largest cutoff, within [0.1, 0.4] nm
     plan_lists(c);
@@ -992,6 +1056,15 @@ int ocm_context_create(const ocm_system* sys, double T, double gamma, double dt,
     catch (const std::exception& e) { delete c; return ocm::fail(e.what()); }
     catch (...) { delete c; return ocm::fail("unknown error"); }
 }
+
+int ocm_context_create(const ocm_system* sys, double T, double gamma, double dt, uint64_t seed, int device, ocm_context** out) {
+    return create_context(sys, 1, T, gamma, dt, &seed, device, out);
+}
+int ocm_context_create_batch(const ocm_system* sys, int32_t n_replicas, double T, double gamma, double dt, const uint64_t* seeds,
+                             int device, ocm_context** out) {
+    return create_context(sys, n_replicas, T, gamma, dt, seeds, device, out);
+}
+int ocm_num_replicas(const ocm_context* c) { return c ? c->nrep : -1; }
 void ocm_context_destroy(ocm_context* c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -1080,7 +1153,7 @@ int ocm_set_velocities_to_temperature(ocm_context* c, double T, uint64_t seed) {
     if (!c) return fail("null context");
     OCM_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
-    init_velocity_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->n, (float)(kBoltz * T), (unsigned int)seed, (unsigned int)(seed >> 32), c->v.p);
+    init_velocity_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->n, c->nper, (float)(kBoltz * T), (unsigned long long)seed, c->v.p);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
     OCM_GUARD_END
@@ -1107,7 +1180,7 @@ int ocm_get_state(ocm_context* c, uint32_t mask, double* pos, double* vel, doubl
     std::vector<float4> hv;
     if (vel) { hv.resize(n); CUDA_TRY(cudaMemcpyAsync(hv.data(), c->v.p, n * sizeof(float4), cudaMemcpyDeviceToHost, s)); }
     std::vector<unsigned long long> hf;
-    double he[40];
+    std::vector<double> he((size_t)40 * c->nrep, 0.0);
     if (force || epot || ekin || ebg) {
         ensure_lists_current(c);
         if (force && mask != 0xFFFFFFFFu) {
@@ -1119,7 +1192,7 @@ int ocm_get_state(ocm_context* c, uint32_t mask, double* pos, double* vel, doubl
             }
             return fail("get_state: forces restricted to a force-group mask are not supported; request all groups");
         }
-        CUDA_TRY(cudaMemsetAsync(c->egroup.p, 0, 40 * sizeof(double), s));
+        CUDA_TRY(cudaMemsetAsync(c->egroup.p, 0, he.size() * sizeof(double), s));
         if (epot || ebg) {
             if (c->total_blocks > 0) {
                 if (c->periodic) energy_kernel<true><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->da, c->P, c->x.p, c->egroup.p);
@@ -1132,15 +1205,48 @@ int ocm_get_state(ocm_context* c, uint32_t mask, double* pos, double* vel, doubl
             if (force) { hf.resize((size_t)3 * n); CUDA_TRY(cudaMemcpyAsync(hf.data(), c->fbuf.p, hf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s)); }
             CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, (size_t)3 * n * sizeof(unsigned long long), s));
         }
-        CUDA_TRY(cudaMemcpyAsync(he, c->egroup.p, 40 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(he.data(), c->egroup.p, he.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     CUDA_TRY(cudaStreamSynchronize(s));
     if (vel) for (int i = 0; i < n; i++) { vel[3 * i] = hv[i].x; vel[3 * i + 1] = hv[i].y; vel[3 * i + 2] = hv[i].z; }
     if (force) for (int i = 0; i < n; i++)
         for (int k = 0; k < 3; k++) force[3 * i + k] = (double)(long long)hf[(size_t)k * n + i] / kFixScale;
+    // a replica batch reports sums over its replicas here; ocm_get_replica_energies has them one by one
+    for (int r = 1; r < c->nrep; r++)
+        for (int q = 0; q < 40; q++) he[q] += he[(size_t)40 * r + q];
     if (epot) { double e = 0; for (int g = 0; g < 32; g++) if (mask >> g & 1) e += he[g]; *epot = e; }
-    if (ebg) std::copy(he, he + 32, ebg);
+    if (ebg) std::copy(he.begin(), he.begin() + 32, ebg);
     if (ekin) *ekin = he[32];
+    return 0;
+    OCM_GUARD_END
+}
+
+int ocm_get_replica_energies(ocm_context* c, uint32_t mask, double* epot, double* ekin, double* ebg) {
+    if (!c) return fail("null context");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int n = c->n;
+    std::vector<double> he((size_t)40 * c->nrep, 0.0);
+    ensure_lists_current(c);
+    CUDA_TRY(cudaMemsetAsync(c->egroup.p, 0, he.size() * sizeof(double), s));
+    if ((epot || ebg) && c->total_blocks > 0) {
+        if (c->periodic) energy_kernel<true><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->da, c->P, c->x.p, c->egroup.p);
+        else energy_kernel<false><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->da, c->P, c->x.p, c->egroup.p);
+    }
+    if (ekin) {
+        compute_forces_into_fbuf(c);
+        kinetic_kernel<<<nblk(n, kBlock), kBlock, 0, s>>>(c->P, c->v.p, c->fbuf.p, c->egroup.p + 32);
+        CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, (size_t)3 * n * sizeof(unsigned long long), s));
+    }
+    CUDA_TRY(cudaMemcpyAsync(he.data(), c->egroup.p, he.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int r = 0; r < c->nrep; r++) {
+        const double* h = &he[(size_t)40 * r];
+        if (epot) { double e = 0; for (int g = 0; g < 32; g++) if (mask >> g & 1) e += h[g]; epot[r] = e; }
+        if (ebg) std::copy(h, h + 32, ebg + (size_t)32 * r);
+        if (ekin) ekin[r] = h[32];
+    }
     return 0;
     OCM_GUARD_END
 }

@@ -811,15 +811,27 @@ def build_system(lib: Library, spec: SystemSpec) -> System:
     return sysm
 
 
-def make_context(lib: Library, spec: SystemSpec, device=0, seed=None) -> Context:
-    """Simulator ctor + initialize + set_velocity (src/Simulator.cpp:4-47, ReadTOMLInput.cpp:1094-1121)."""
+def make_context(lib: Library, spec: SystemSpec, device=0, seed=None, replicas=None) -> Context:
+    """Simulator ctor + initialize + set_velocity (src/Simulator.cpp:4-47, ReadTOMLInput.cpp:1094-1121).
+    replicas = R builds a replica ensemble (config C4): R copies of the system in one context, replica r with the
+    integrator seed `seed + r` (and velocity seed `vel_seed + r`), all starting from the spec's coordinates."""
     sysm = build_system(lib, spec)
-    ctx = Context(sysm, spec.temperature, spec.friction, spec.dt, spec.seed if seed is None else seed, device)
-    ctx.set_positions(spec.positions)
-    if spec.velocities is not None:
-        ctx.set_velocities(spec.velocities)
+    base_seed = spec.seed if seed is None else seed
+    if replicas is None:
+        ctx = Context(sysm, spec.temperature, spec.friction, spec.dt, base_seed, device)
+        ctx.set_positions(spec.positions)
+        if spec.velocities is not None:
+            ctx.set_velocities(spec.velocities)
+        else:
+            ctx.set_velocities_to_temperature(spec.temperature, spec.vel_seed)
     else:
-        ctx.set_velocities_to_temperature(spec.temperature, spec.vel_seed)
+        ctx = Context(sysm, spec.temperature, spec.friction, spec.dt, device=device,
+                      replica_seeds=[base_seed + r for r in range(replicas)])
+        ctx.set_positions(np.tile(spec.positions, (replicas, 1)))
+        if spec.velocities is not None:
+            ctx.set_velocities(np.tile(spec.velocities, (replicas, 1)))
+        else:
+            ctx.set_velocities_to_temperature(spec.temperature, spec.vel_seed)
     ctx.group_ids = dict(spec.group_ids)
     return ctx
 

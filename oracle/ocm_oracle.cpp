@@ -24,6 +24,7 @@
 #include <limits>
 #include <map>
 #include <set>
+#include <memory>
 #include <string>
 #include <vector>
 #ifdef _OPENMP
@@ -80,6 +81,7 @@ struct PairTerm {
     std::vector<int32_t> cls;     // interaction class per bead (-1 none)
     std::vector<uint8_t> allow;   // ncls x ncls
     int ncls;
+    int nper = 0;                 // replica batch: beads of different replicas (i / nper) never interact
 };
 
 // donor x acceptor ("CustomHbondForce"-like) term, SURVEY.md B.5
@@ -111,6 +113,9 @@ struct ocm_system {
 
 struct ocm_context {
     ocm_system sys;
+    int nrep = 1, nper = 0;          // replica batch
+    std::vector<uint64_t> rep_seeds;
+    std::shared_ptr<ocm_system> base; // the single-replica system of a batch
     double T, gamma, dt;
     uint64_t seed;
     int64_t step;
@@ -363,6 +368,7 @@ inline void pair_energy(const PairTerm& t, int i, int j, double r, double* E, do
 }
 
 inline bool pair_allowed(const PairTerm& t, int i, int j) {
+    if (t.nper > 0 && i / t.nper != j / t.nper) return false;
     if (t.ncls > 0) {
         int ci = t.cls[i], cj = t.cls[j];
         if (ci < 0 || cj < 0 || !t.allow[ci * t.ncls + cj]) return false;
@@ -1048,6 +1054,54 @@ int oracle_context_create(const ocm_system* sys, double T, double gamma, double 
     *out = c;
     return 0;
 }
+// Replica ensemble restated independently of the engine's cell keying: one concatenated system in which beads of
+// different replicas never pair (pair_allowed), each replica with its own noise key and local bead counter.
+int oracle_context_create_batch(const ocm_system* sys, int32_t nrep, double T, double gamma, double dt, const uint64_t* seeds,
+                                int device, ocm_context** out) {
+    (void)device;
+    if (!sys || !out || !seeds || nrep < 1) return fail("context_create_batch: bad arguments");
+    if (sys->has_box) return fail("context_create_batch: replica batches need an unlimited boundary (no box)");
+    if (!sys->das.empty()) return fail("context_create_batch: donor-acceptor terms are not supported in replica batches yet");
+    auto* c = new ocm_context();
+    const int np = sys->n;
+    ocm_system& S = c->sys;
+    S.n = np * nrep; S.has_box = false; S.box[0] = S.box[1] = S.box[2] = 0;
+    for (int r = 0; r < nrep; r++) S.mass.insert(S.mass.end(), sys->mass.begin(), sys->mass.end());
+    for (const auto& t : sys->bonded) {
+        BondedTerm u = t;
+        u.idx.clear(); u.p.clear();
+        for (int r = 0; r < nrep; r++) {
+            for (int32_t v : t.idx) u.idx.push_back(v + r * np);
+            u.p.insert(u.p.end(), t.p.begin(), t.p.end());
+        }
+        S.bonded.push_back(std::move(u));
+    }
+    for (const auto& t : sys->pairs) {
+        PairTerm u = t;
+        u.p0.clear(); u.p1.clear(); u.part.clear(); u.excl.clear(); u.cls.clear();
+        u.nper = np;
+        for (int r = 0; r < nrep; r++) {
+            u.p0.insert(u.p0.end(), t.p0.begin(), t.p0.end());
+            u.p1.insert(u.p1.end(), t.p1.begin(), t.p1.end());
+            u.cls.insert(u.cls.end(), t.cls.begin(), t.cls.end());
+            for (int32_t v : t.part) u.part.push_back(v + r * np);
+            for (const auto& e : t.excl) {
+                std::vector<int32_t> sh;
+                for (int32_t v : e) sh.push_back(v + r * np);
+                u.excl.push_back(std::move(sh));
+            }
+        }
+        S.pairs.push_back(std::move(u));
+    }
+    c->nrep = nrep; c->nper = np; c->rep_seeds.assign(seeds, seeds + nrep);
+    c->base = std::make_shared<ocm_system>(*sys);
+    c->T = T; c->gamma = gamma; c->dt = dt; c->seed = seeds[0]; c->step = 0;
+    c->x.assign(S.n, Vec3{0, 0, 0}); c->v.assign(S.n, Vec3{0, 0, 0});
+    c->force_brute = false;
+    *out = c;
+    return 0;
+}
+int oracle_num_replicas(const ocm_context* c) { return c ? c->nrep : -1; }
 void oracle_context_destroy(ocm_context* c) { delete c; }
 
 int oracle_context_set_option(ocm_context* c, const char* key, double v) {
@@ -1089,7 +1143,8 @@ int oracle_set_velocities_to_temperature(ocm_context* c, double T, uint64_t seed
     if (!c) return fail("null context");
     for (int i = 0; i < c->sys.n; i++) {
         double g[3];
-        normals3(seed, (uint32_t)i, 0, 1, g);
+        const int rep = c->nrep > 1 ? i / c->nper : 0;
+        normals3(seed + (uint64_t)rep, (uint32_t)(i - rep * c->nper), 0, 1, g);
         double m = c->sys.mass[i];
         double s = m > 0 ? std::sqrt(kBoltz * T / m) : 0.0;
         c->v[i] = {s * g[0], s * g[1], s * g[2]};
@@ -1110,7 +1165,8 @@ int oracle_step(ocm_context* c, int64_t nsteps) {
             double m = c->sys.mass[i];
             if (!(m > 0)) continue;
             double g[3];
-            normals3(c->seed, (uint32_t)i, (uint64_t)c->step, 0, g);
+            const int rep = c->nrep > 1 ? i / c->nper : 0;
+            normals3(c->nrep > 1 ? c->rep_seeds[rep] : c->seed, (uint32_t)(i - rep * c->nper), (uint64_t)c->step, 0, g);
             double im = 1.0 / m, sq = std::sqrt(im);
             Vec3& v = c->v[i];
             v.x = a * v.x + b * F[i].x * im + cc * sq * g[0];
@@ -1148,6 +1204,25 @@ int oracle_get_state(ocm_context* c, uint32_t mask, double* pos, double* vel, do
             ke += 0.5 * m * dot(vs, vs);
         }
         *ekin = ke;
+    }
+    return 0;
+}
+
+// per-replica energies: every replica is evaluated as the stand-alone system it is
+int oracle_get_replica_energies(ocm_context* c, uint32_t mask, double* epot, double* ekin, double* ebg) {
+    if (!c) return fail("null context");
+    for (int r = 0; r < c->nrep; r++) {
+        ocm_context one;
+        one.sys = c->nrep > 1 ? *c->base : c->sys;
+        one.T = c->T; one.gamma = c->gamma; one.dt = c->dt; one.seed = c->seed; one.step = c->step; one.force_brute = c->force_brute;
+        const int np = one.sys.n;
+        one.x.assign(c->x.begin() + (size_t)r * np, c->x.begin() + (size_t)(r + 1) * np);
+        one.v.assign(c->v.begin() + (size_t)r * np, c->v.begin() + (size_t)(r + 1) * np);
+        double ep = 0, ek = 0, eg[32];
+        if (oracle_get_state(&one, mask, nullptr, nullptr, nullptr, &ep, ekin ? &ek : nullptr, eg)) return 1;
+        if (epot) epot[r] = ep;
+        if (ekin) ekin[r] = ek;
+        if (ebg) std::copy(eg, eg + 32, ebg + (size_t)32 * r);
     }
     return 0;
 }

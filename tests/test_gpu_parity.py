@@ -134,6 +134,44 @@ def test_donor_acceptor_random(engine, oracle, kind, periodic):
         check_state(ctx, ora, Spec, ftol=2e-3, etol=2e-3)
 
 
+def test_replica_batch(engine, oracle):
+    """Config C4: a replica ensemble in one context.  Every replica matches the oracle's batch (which equals
+    stand-alone runs, tests/test_oracle_kat.py) in forces, per-replica energies, pair sets and trajectory."""
+    spec = load_golden_spec("sh3")
+    R, n = 7, spec.mass.size
+    ctx, ora = ti.make_context(engine, spec, replicas=R), ti.make_context(oracle, spec, replicas=R)
+    assert ctx.n_replicas == R
+    check_state(ctx, ora, spec)
+    check_sets(ctx, ora)
+    ctx.step(20); ora.step(20)
+    a = ctx.get_state(positions=True, velocities=True); b = ora.get_state(positions=True, velocities=True)
+    assert np.abs(a["positions"] - b["positions"]).max() < 2e-5
+    assert np.abs(a["positions"][:n] - a["positions"][n:2 * n]).max() > 1e-4   # replicas have their own noise
+    ea, eb = ctx.replica_energies(), ora.replica_energies()
+    for r in range(R):
+        assert ea["potential_energy"][r] == pytest.approx(eb["potential_energy"][r], rel=5e-4, abs=0.05)
+        assert ea["kinetic_energy"][r] == pytest.approx(eb["kinetic_energy"][r], rel=5e-4)
+    tot = ctx.get_state(energy=True)
+    assert tot["potential_energy"] == pytest.approx(ea["potential_energy"].sum(), rel=1e-9)
+    # a longer run keeps the replicas apart from each other's pair lists: forces still match replica by replica
+    ctx.step(200)
+    ora.set_positions(ctx.get_state(positions=True)["positions"])
+    fa, fb = ctx.get_state(forces=True)["forces"], ora.get_state(forces=True)["forces"]
+    assert force_error(fa, fb).max() < FORCE_TOL
+
+
+def test_replica_batch_large(engine):
+    """512 SH3 replicas (the full C4 ensemble) step and stay finite; replica 0 equals a 1-replica batch."""
+    spec = load_golden_spec("sh3")
+    n = spec.mass.size
+    big = ti.make_context(engine, spec, replicas=512)
+    one = ti.make_context(engine, spec, replicas=1)
+    big.step(50); one.step(50)
+    a = big.get_state(positions=True)["positions"]; b = one.get_state(positions=True)["positions"]
+    assert np.isfinite(a).all()
+    assert np.abs(a[:n] - b).max() < 2e-5
+
+
 def test_cell_assignment_bit_exact(engine, oracle):
     import ctypes as C
     for spec in (synth.hps_slab(n_chains=12), load_golden_spec("sh3")):

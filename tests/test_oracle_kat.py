@@ -273,3 +273,35 @@ def test_langevin_equipartition(oracle):
     v = ctx.get_state(velocities=True)["velocities"]
     kT = 8.31446261815324e-3 * 300
     assert (80.0 * (v ** 2).mean()) == pytest.approx(kT, rel=0.05)
+
+
+def test_replica_batch_equals_standalone_runs(oracle):
+    """Config C4 semantics: replica r of a batch follows exactly the trajectory of a stand-alone context with seed
+    base + r (own noise key, local bead counter, no cross-replica pairs although all replicas overlap in space)."""
+    spec = load_golden_spec("sh3")
+    R = 3
+    batch = ti.make_context(oracle, spec, replicas=R)
+    singles = [ti.make_context(oracle, spec, seed=spec.seed + r) for r in range(R)]
+    n = spec.mass.size
+    assert batch.n_replicas == R and batch.n == R * n
+    batch.step(15)
+    for c in singles:
+        c.step(15)
+    a = batch.get_state(positions=True, velocities=True, forces=True, energy=True)
+    re = batch.replica_energies()
+    for r, c in enumerate(singles):
+        b = c.get_state(positions=True, velocities=True, forces=True, energy=True)
+        sl = slice(r * n, (r + 1) * n)
+        assert np.array_equal(a["positions"][sl], b["positions"])
+        assert np.array_equal(a["velocities"][sl], b["velocities"])
+        assert np.allclose(a["forces"][sl], b["forces"], rtol=0, atol=1e-9)
+        assert re["potential_energy"][r] == pytest.approx(b["potential_energy"], rel=1e-12)
+        assert re["kinetic_energy"][r] == pytest.approx(b["kinetic_energy"], rel=1e-12)
+        assert np.allclose(re["energy_by_group"][r], b["energy_by_group"], rtol=1e-12, atol=1e-12)
+    assert a["potential_energy"] == pytest.approx(re["potential_energy"].sum(), rel=1e-12)
+    # replicas diverge from each other (different noise)
+    assert np.abs(a["positions"][:n] - a["positions"][n:2 * n]).max() > 1e-4
+    # pair set of the batch = union of the replicas' sets, shifted
+    for t in range(batch.num_pair_terms()):
+        want = np.concatenate([c.neighbor_pairs(t) + r * n for r, c in enumerate(singles)])
+        assert np.array_equal(batch.neighbor_pairs(t), want)

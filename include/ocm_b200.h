@@ -200,6 +200,32 @@ int ocm_num_replicas(const ocm_context* ctx);
 int ocm_get_replica_energies(ocm_context*, uint32_t group_mask, double* epot, double* ekin,
                              double* epot_by_group);
 
+/* ---- slab domain decomposition of one periodic system over several GPUs --------------------------
+ * Replaces nothing in the reference (one OpenMM::Context drives one device, src/Simulator.cpp:14-17); this is the
+ * multi-GPU extension for large condensates.  The box is cut into `world` slabs along `axis` (0,1,2 = x,y,z); each
+ * rank owns the beads inside its slab, keeps the beads within one list radius of its faces as a halo, and exchanges
+ * halo positions with its two neighbours every MD step (full state and migrations at every list rebuild).
+ * Every rank builds the SAME ocm_system and makes the SAME sequence of calls (SPMD): ocm_set_positions /
+ * ocm_set_velocities take the whole system on every rank, ocm_step / ocm_get_state are collective, and
+ * ocm_get_state returns the whole system (and the total energies) on every rank.  ocm_get_neighbor_pairs returns the
+ * pairs found by this rank (i owned here); the union over ranks is the pair set.
+ *
+ * Communicators:
+ *   nccl  : one process per GPU.  Rank 0 calls ocm_comm_unique_id, the host program broadcasts the 128 bytes
+ *           (e.g. torch.distributed.broadcast), every rank calls ocm_comm_create_nccl.
+ *   local : all ranks live in one process, each driven by its own host thread (one or several devices). */
+typedef struct ocm_comm ocm_comm;
+int  ocm_comm_unique_id(char* id128);
+int  ocm_comm_create_nccl(const char* id128, int world, int rank, int device, ocm_comm** out);
+int  ocm_comm_create_local(int world, ocm_comm** out);
+void ocm_comm_destroy(ocm_comm* comm);   /* after the contexts using it */
+int  ocm_context_create_slab(const ocm_system* sys, double temperature_K, double friction_inv_ps, double dt_ps,
+                             uint64_t seed, int device_index, ocm_comm* comm, int rank, int axis,
+                             ocm_context** out);
+int  ocm_slab_info(const ocm_context*, int* rank, int* world, int* axis, double* halo_nm);
+/* role of every bead on this rank: 0 = absent, 1 = owned, 2 = halo (all 1 without a decomposition) */
+int  ocm_get_roles(ocm_context*, unsigned char* role);
+
 /* tunables: "skin_nm" (Verlet buffer), "nstlist" (0 = adaptive), "threads_per_bead" */
 int ocm_context_set_option(ocm_context*, const char* key, double value);
 int ocm_context_get_option(ocm_context*, const char* key, double* value);

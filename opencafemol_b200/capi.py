@@ -197,6 +197,16 @@ class Library:
         ),
         "num_replicas": (C.c_int, [C.c_void_p]),
         "get_replica_energies": (C.c_int, [C.c_void_p, C.c_uint32, _f64p, _f64p, _f64p]),
+        "comm_unique_id": (C.c_int, [C.c_char_p]),
+        "comm_create_nccl": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+        "comm_create_local": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+        "comm_destroy": (None, [C.c_void_p]),
+        "context_create_slab": (
+            C.c_int,
+            [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)],
+        ),
+        "slab_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _f64p]),
+        "get_roles": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte)]),
         "context_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
         "context_get_option": (C.c_int, [C.c_void_p, C.c_char_p, _f64p]),
         "set_positions": (C.c_int, [C.c_void_p, _f64p]),
@@ -416,13 +426,56 @@ class System:
         self.pair_terms.append("3SPN2ExcludedVolume")
 
 
+class Comm:
+    """Communicator of a slab decomposition (include/ocm_b200.h): `Comm.local(lib, world)` for ranks that are threads
+    of this process, `Comm.nccl(lib, uid, world, rank, device)` for one process per GPU (uid = Comm.unique_id(lib) on
+    rank 0, broadcast by the host program)."""
+
+    def __init__(self, lib: Library, handle, world, kind):
+        self.lib, self.handle, self.world, self.kind = lib, handle, int(world), kind
+
+    @staticmethod
+    def unique_id(lib: Library) -> bytes:
+        buf = C.create_string_buffer(128)
+        lib.check(lib.fn["comm_unique_id"](buf))
+        return buf.raw
+
+    @classmethod
+    def nccl(cls, lib: Library, uid: bytes, world, rank, device):
+        h = C.c_void_p()
+        assert len(uid) == 128
+        lib.check(lib.fn["comm_create_nccl"](C.create_string_buffer(uid, 128), int(world), int(rank), int(device), C.byref(h)))
+        return cls(lib, h, world, "nccl")
+
+    @classmethod
+    def local(cls, lib: Library, world):
+        h = C.c_void_p()
+        lib.check(lib.fn["comm_create_local"](int(world), C.byref(h)))
+        return cls(lib, h, world, "local")
+
+    def close(self):
+        if self.handle:
+            self.lib.fn["comm_destroy"](self.handle)
+            self.handle = None
+
+
 class Context:
     """OpenMM::Context + LangevinIntegrator equivalent."""
 
-    def __init__(self, system: System, temperature, friction, dt, seed=0, device=0, replica_seeds=None):
+    def __init__(self, system: System, temperature, friction, dt, seed=0, device=0, replica_seeds=None, comm: Comm = None,
+                 rank=0, axis=1):
         self.lib = system.lib
         h = C.c_void_p()
-        if replica_seeds is None:
+        self.comm = comm
+        if comm is not None:
+            # one rank of a slab decomposition (collective calls: every rank makes the same sequence)
+            self.n = system.n
+            self.n_replicas = 1
+            self.lib.check(
+                self.lib.fn["context_create_slab"](system.handle, float(temperature), float(friction), float(dt), int(seed), int(device),
+                                                   comm.handle, int(rank), int(axis), C.byref(h))
+            )
+        elif replica_seeds is None:
             self.n = system.n
             self.n_replicas = 1
             self.lib.check(
@@ -502,6 +555,16 @@ class Context:
             out["potential_energy"] = ep.value
             out["kinetic_energy"] = ek.value
             out["energy_by_group"] = ebg
+        return out
+
+    def slab_info(self):
+        r, w, a, h = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        self.lib.check(self.lib.fn["slab_info"](self.handle, C.byref(r), C.byref(w), C.byref(a), C.byref(h)))
+        return {"rank": r.value, "world": w.value, "axis": a.value, "halo_nm": h.value}
+
+    def roles(self):
+        out = np.zeros(self.n, np.uint8)
+        self.lib.check(self.lib.fn["get_roles"](self.handle, out.ctypes.data_as(C.POINTER(C.c_ubyte))))
         return out
 
     def replica_energies(self, groups=0xFFFFFFFF):

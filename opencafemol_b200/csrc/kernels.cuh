@@ -24,7 +24,9 @@ constexpr double kFixScale = 4294967296.0;  // force accumulator: 64-bit fixed p
 constexpr int kMaxMembers = 4;
 
 enum SegKind : int { SEG_PAIR_TZ = 0, SEG_PAIR_DH = 1, SEG_BONDED = 2, SEG_DA = 3 };
-enum FlagSlot : int { FLAG_VIOLATION = 0, FLAG_OVERFLOW = 1, FLAG_TICKET = 2, FLAG_NAN = 3, FLAG_MAXDISP = 4, FLAG_DA_OVERFLOW = 6, FLAG_COUNT = 8 };
+enum FlagSlot : int { FLAG_VIOLATION = 0, FLAG_OVERFLOW = 1, FLAG_TICKET = 2, FLAG_NAN = 3, FLAG_MAXDISP = 4, FLAG_DA_OVERFLOW = 6,
+                       // slab decomposition: halo message overflow, a bonded term reaching beyond the halo, largest message (entries)
+                       FLAG_DD_OVERFLOW = 7, FLAG_DD_REACH = 8, FLAG_DD_MAXSEND = 9, FLAG_COUNT = 12 };
 
 struct GridDev {
     int nc[3];
@@ -37,6 +39,7 @@ struct GridDev {
 struct PairListDev {
     int np, stride, ntypes, ncls, form, nmem, has_switch, smem_tab;
     int nrep, nper;             // replica batch: cells are keyed (replica, local cell); pairs never cross replicas
+    const unsigned char* role;  // slab decomposition: per bead 0 = not on this rank, 1 = owned, 2 = halo; null = single domain
     const int* part;            // [np] bead index of each participant slot, ascending
     const unsigned char* type;  // [np]
     const signed char* cls;     // [np] interaction class or null
@@ -122,7 +125,12 @@ struct StepParams {
     int nrep, nper;
     const double* origin;       // [3*nrep] or null (single system, origin 0)
     const uint2* rep_seed;      // [nrep] or null
+    const unsigned char* role;  // slab decomposition: 0 = not on this rank, 1 = owned, 2 = halo; null = single domain
 };
+
+// rows (ranks of the cell-sorted order) in use: under a slab decomposition only the beads present on this rank are binned
+__device__ __forceinline__ int list_rows(const PairListDev& L) { return L.role ? L.cell_start[L.grid->ncell * L.nrep] : L.np; }
+__device__ __forceinline__ int bonded_nbody_dev(int kind) { return kind <= 3 ? 2 : ((kind <= 5 || kind == 9) ? 3 : 4); }
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int to_fix(double x, double inv_l) {
@@ -305,6 +313,7 @@ __global__ void bin_kernel(const PairListDev* lists, int li, const uint4* __rest
     const GridDev& g = *L.grid;
     int cx, cy, cz;
     const int bead = L.part[a];
+    if (L.role && L.role[bead] == 0) { L.cell_of_slot[a] = -1; L.rank_of_bead[bead] = -1; return; }
     cell_coords<PER>(g, posq[bead], cx, cy, cz);
     int c = (cz * g.nc[1] + cy) * g.nc[0] + cx;
     if (L.nrep > 1) c += (bead / L.nper) * g.ncell;
@@ -362,7 +371,9 @@ __global__ void scatter_kernel(const PairListDev* lists, int li) {
     const PairListDev& L = lists[li];
     int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= L.np) return;
-    int pos = atomicAdd(&L.cell_cursor[L.cell_of_slot[a]], 1);
+    const int c = L.cell_of_slot[a];
+    if (c < 0) return;
+    int pos = atomicAdd(&L.cell_cursor[c], 1);
     L.tmp_slots[pos] = a;
 }
 
@@ -372,7 +383,7 @@ __global__ void scatter_kernel(const PairListDev* lists, int li) {
 __global__ void rank_fill_kernel(const PairListDev* lists, int li, const uint4* __restrict__ posq) {
     const PairListDev& L = lists[li];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= L.np) return;
+    if (p >= list_rows(L)) return;
     const int a = L.tmp_slots[p];
     const int c = L.cell_of_slot[a];
     const int s = L.cell_start[c], e = L.cell_start[c + 1];
@@ -405,11 +416,16 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
     const PairListDev& L = lists[li];
     const int lane = threadIdx.x & 31;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= L.np) return;
+    if (w >= list_rows(L)) return;
     const GridDev& g = *L.grid;
     const uint4* __restrict__ spos = L.spos;
     const bool dh = L.form == SEG_PAIR_DH;
     const int a = L.sorted_slots[w];
+    if (L.role && L.role[L.part[a]] != 1) {
+        // halo bead: present as a partner only, its own row stays empty (its owner computes its forces)
+        if (lane == 0) { L.nbr_count[w] = 0; L.nbr_inner[w] = 0; }
+        return;
+    }
     const uint4 pi = spos[w];
     const int cig = L.cell_of_slot[a];
     const int ncx = g.nc[0], ncy = g.nc[1], ncz = g.nc[2];
@@ -855,7 +871,7 @@ __device__ __forceinline__ void pair_tz_block_staged(const PairListDev& L, int b
     for (int k = threadIdx.x; k < nt2; k += kBlock) sF[k] = L.tabF[k];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    const int k_lo = blk * chunk, k_hi = min(L.np, k_lo + chunk);
+    const int k_lo = blk * chunk, k_hi = min(list_rows(L), k_lo + chunk);
     if (L.has_switch) pair_tz_rows_staged<PER, true>(L, k_lo, k_hi, P, fbuf, sF, rowbuf, bars);
     else pair_tz_rows_staged<PER, false>(L, k_lo, k_hi, P, fbuf, sF, rowbuf, bars);
 }
@@ -871,7 +887,7 @@ __device__ __forceinline__ void pair_tz_block(const PairListDev& L, int blk, int
         __syncthreads();
         tab = sF;
     }
-    const int k_lo = blk * chunk, k_hi = min(L.np, k_lo + chunk);
+    const int k_lo = blk * chunk, k_hi = min(list_rows(L), k_lo + chunk);
     if (T == 32 && L.smem_tab) {
         const float4* sF = reinterpret_cast<const float4*>(smem);
         if (L.has_switch) pair_tz_rows_warp<PER, true>(L, k_lo, k_hi, P, fbuf, sF);
@@ -890,7 +906,7 @@ __device__ __forceinline__ void pair_dh_block(const PairListDev& L, int blk, int
     const int g = threadIdx.x / T, s = threadIdx.x % T;
     const uint4* __restrict__ spos = L.spos;
     const float rc2 = L.rc2, ik = L.inv_debye;
-    const int k_lo = blk * chunk, k_hi = min(L.np, k_lo + chunk);
+    const int k_lo = blk * chunk, k_hi = min(list_rows(L), k_lo + chunk);
     for (int base = k_lo; base < k_hi; base += G) {
         const int k = base + g;
         const bool active = k < k_hi;
@@ -1335,7 +1351,18 @@ __global__ void __launch_bounds__(kBlock, OCM_FORCE_MINBLOCKS) force_kernel(cons
     } else {
         const BondedDev& B = bonded[sg.id];
         const int m = blk * kBlock + threadIdx.x;
-        if (m < B.n) { int g; bonded_term(sg.id, B, m, P, x, fbuf, &g); }
+        if (m < B.n) {
+            if (P.role) {
+                // slab decomposition: a term is evaluated by every rank that owns one of its beads (the forces on the
+                // other beads are discarded with the accumulator); all its beads must be present here
+                const int nb = bonded_nbody_dev(sg.id);
+                bool mine = false;
+                for (int q = 0; q < nb; q++) mine = mine || P.role[B.idx[nb * m + q]] == 1;
+                if (!mine) return;
+            }
+            int g;
+            bonded_term(sg.id, B, m, P, x, fbuf, &g);
+        }
     }
 }
 
@@ -1395,7 +1422,7 @@ __global__ void integrate_kernel(StepParams P, double* __restrict__ x, float4* _
                     fz = (float)(long long)fbuf[2 * n + i] * inv32;
         fbuf[i] = 0ull; fbuf[n + i] = 0ull; fbuf[2 * n + i] = 0ull;
         float4 vi = v[i];
-        const float im = vi.w;
+        const float im = (P.role && P.role[i] != 1) ? 0.f : vi.w;  // slab decomposition: only owned beads move here
         if (im > 0.f) {
             float g0, g1, g2;
             const int rep = (P.nrep > 1) ? i / P.nper : 0;
@@ -1493,7 +1520,8 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(const WorkSeg* __restric
         if (sg.kind == SEG_BONDED) {
             const BondedDev& B = bonded[sg.id];
             const int m = blk * kBlock + threadIdx.x;
-            if (m < B.n) E = bonded_term(sg.id, B, m, P, x, nullptr, &g);
+            // slab decomposition: the rank owning the first bead of a term reports its energy
+            if (m < B.n && (!P.role || P.role[B.idx[bonded_nbody_dev(sg.id) * m]] == 1)) E = bonded_term(sg.id, B, m, P, x, nullptr, &g);
         } else {
             const unsigned int m = blk * kBlock + threadIdx.x;
             if (m < min(*da.count, (unsigned int)da.capacity)) {
@@ -1524,7 +1552,7 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(const WorkSeg* __restric
     const int T = sg.tpb, G = kBlock / T;
     const int g = threadIdx.x / T, sl = threadIdx.x % T;
     double Em[kMaxMembers] = {0, 0, 0, 0};
-    const int k_lo = blk * sg.chunk, k_hi = min(L.np, k_lo + sg.chunk);
+    const int k_lo = blk * sg.chunk, k_hi = min(list_rows(L), k_lo + sg.chunk);
     for (int k = k_lo + g; k < k_hi; k += G) {
         const uint4 pi = L.spos[k];
         const int nt = L.ntypes;
@@ -1582,7 +1610,7 @@ __global__ void kinetic_kernel(StepParams P, const float4* __restrict__ v, const
     double e = 0.0;
     if (i < P.n) {
         const float4 vi = v[i];
-        if (vi.w > 0.f) {
+        if (vi.w > 0.f && (!P.role || P.role[i] == 1)) {
             const double im = vi.w, h = 0.5 * P.dt * im, inv = 1.0 / kFixScale;
             const double vx = vi.x + h * (double)(long long)fbuf[i] * inv, vy = vi.y + h * (double)(long long)fbuf[P.n + i] * inv,
                          vz = vi.z + h * (double)(long long)fbuf[2 * P.n + i] * inv;
@@ -1599,7 +1627,7 @@ __global__ void extract_pairs_kernel(const PairListDev* lists, int li, StepParam
                                      int* __restrict__ out, long long capacity, unsigned long long* __restrict__ counter) {
     const PairListDev& L = lists[li];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= L.np) return;
+    if (k >= list_rows(L)) return;
     const uint4 pi = L.spos[k];
     const int i = L.bead_of_rank[k];
     const int n = L.nbr_count[k];

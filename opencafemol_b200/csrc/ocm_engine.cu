@@ -24,6 +24,8 @@
 
 #include "host_system.hpp"
 #include "kernels.cuh"
+#include "dd_kernels.cuh"
+#include "dd_comm.hpp"
 
 namespace ocm {
 thread_local std::string g_err;
@@ -85,6 +87,33 @@ struct PairListHost {
 
 using namespace ocm;
 
+// slab decomposition state of one rank (dd_kernels.cuh)
+struct DDState {
+    DDComm* comm = nullptr;
+    int rank = 0, world = 1, axis = 1;
+    DDGeom G{};
+    double halo = 0;
+    int cap = 0;                                  // entries per halo message
+    DevBuf<unsigned char> role, role_bak, role_tmp, known;
+    DevBuf<char> a_send[2], a_recv[2];            // phase A: [count | idx | x | v], lo / hi
+    DevBuf<char> b_send[2], b_recv[2];            // phase B: [count | idx]
+    DevBuf<double> s_send[2], s_recv[2];          // per-step positions
+    DevBuf<double> gx; DevBuf<float> gv; DevBuf<long long> gf;  // state gather
+    std::vector<int> rows_est;                    // per pair list: rows in use at the last sizing pass
+    double n_exchanges = 0;
+    size_t bytes_a() const { return 16 + (size_t)cap * (4 + 24 + 16); }
+    size_t bytes_b() const { return 16 + (size_t)cap * 4; }
+    size_t bytes_s() const { return (size_t)cap * 24; }
+    static DDMsg msg(char* base, int cap) {
+        DDMsg m;
+        m.count = reinterpret_cast<int*>(base);
+        m.idx = reinterpret_cast<int*>(base + 16);
+        m.x = reinterpret_cast<double*>(base + 16 + (size_t)cap * 4);
+        m.v = reinterpret_cast<float4*>(base + 16 + (size_t)cap * 28);
+        return m;
+    }
+};
+
 struct ocm_context {
     ocm_system sys;  // host copy of the term tables
     int n = 0;
@@ -95,6 +124,7 @@ struct ocm_context {
     int device = 0;
     int nrep = 1, nper = 0;                 // replica batch: nrep independent copies of nper beads
     std::vector<uint64_t> rep_seeds;
+    std::unique_ptr<DDState> dd;            // slab decomposition (null: the whole system lives on this device)
     DevBuf<double> origin;                  // [3*nrep] local-frame origins (replica batch)
     DevBuf<uint2> d_rep_seed;
     cudaStream_t stream = nullptr;
@@ -160,6 +190,8 @@ struct ocm_context {
 namespace ocm {
 
 static const int kNstChoices[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 56, 64, 80, 100};
+
+static void dd_configure(ocm_context* c);
 
 static void drop_graphs(ocm_context* c) {
     for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
@@ -295,6 +327,7 @@ static void compile_list(ocm_context* c, PairListHost& L) {
     std::memset(&D, 0, sizeof(D));
     D.np = L.np; D.ntypes = nt; D.ncls = t0.ncls; D.form = L.form; D.nmem = nm;
     D.nrep = c->nrep; D.nper = c->nper;
+    D.role = c->dd ? c->dd->role.p : nullptr;
     for (int k = 0; k < t0.ncls && k < 32; k++) D.allow[k] = t0.allow[k];
     D.rc2 = (float)(L.rc_list * L.rc_list);
     D.rsw = (float)L.rc_list; D.inv_sw = 0.f; D.has_switch = 0;
@@ -433,7 +466,9 @@ static void build_segments(ocm_context* c) {
         // a block owns `chunk` consecutive ranks of the cell-sorted order (spatially compact: rows overlap in L1,
         // one coefficient-table load per block); about 16 blocks per SM for load balance
         const int gpb = kBlock / L.tpb;
-        int chunk = c->chunk_opt > 0 ? c->chunk_opt : (L.np + 148 * 16 - 1) / (148 * 16);
+        // under a slab decomposition only the rows of the beads present on this rank are in use
+        const int rows = (c->dd && l < c->dd->rows_est.size() && c->dd->rows_est[l] > 0) ? std::min(L.np, c->dd->rows_est[l]) : L.np;
+        int chunk = c->chunk_opt > 0 ? c->chunk_opt : (rows + 148 * 16 - 1) / (148 * 16);
         chunk = std::max(gpb, (chunk + gpb - 1) / gpb * gpb);
         int nb = (L.np + chunk - 1) / chunk;
         // T = 32 two-zone lists stage their rows in shared memory (bulk async copies) when two rows per warp fit
@@ -578,10 +613,91 @@ static void update_params(ocm_context* c) {
     P.nrep = c->nrep; P.nper = c->nper;
     P.origin = c->nrep > 1 ? c->origin.p : nullptr;
     P.rep_seed = c->nrep > 1 ? c->d_rep_seed.p : nullptr;
+    P.role = c->dd ? c->dd->role.p : nullptr;
+    if (c->dd) dd_configure(c);
 }
 
 // ---- enqueue helpers ----------------------------------------------------------------------------
 static inline int nblk(int n, int b) { return std::max(1, (n + b - 1) / b); }
+
+// ---- slab decomposition: host side ---------------------------------------------------------------
+// (re)derive what depends on the skin: the halo width = largest list radius
+static void dd_configure(ocm_context* c) {
+    DDState& d = *c->dd;
+    double h = 0;
+    for (auto& L : c->lists) if (L->np) h = std::max(h, L->rc_list + c->skin);
+    h = std::max(h, 4.0 * c->skin);
+    const double len = c->sys.box[d.axis];
+    if (len / d.world < h + c->skin)
+        throw std::runtime_error("slab decomposition: a slab (" + std::to_string(len / d.world) + " nm) must be wider than the halo (" +
+                                 std::to_string(h) + " nm) plus the skin; use fewer ranks or another axis");
+    d.halo = h;
+    const double two32 = 4294967296.0;
+    auto face = [&](int r) { return (unsigned int)(unsigned long long)std::ceil((double)r * two32 / d.world); };
+    d.G.world = d.world; d.G.rank = d.rank; d.G.axis = d.axis;
+    d.G.lo = face(d.rank);
+    d.G.hi = d.rank + 1 == d.world ? 0u : face(d.rank + 1);
+    d.G.halo_fix = (unsigned int)std::ceil(h / len * two32) + 2u;
+}
+
+static void dd_alloc(ocm_context* c, int cap) {
+    DDState& d = *c->dd;
+    cap = (cap + 255) / 256 * 256;
+    d.cap = cap;
+    for (int k = 0; k < 2; k++) {
+        d.a_send[k].alloc(d.bytes_a()); d.a_recv[k].alloc(d.bytes_a());
+        d.b_send[k].alloc(d.bytes_b()); d.b_recv[k].alloc(d.bytes_b());
+        d.s_send[k].alloc((size_t)3 * cap); d.s_recv[k].alloc((size_t)3 * cap);
+        d.a_send[k].zero(); d.a_recv[k].zero(); d.b_send[k].zero(); d.b_recv[k].zero(); d.s_send[k].zero(); d.s_recv[k].zero();
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+}
+
+// rebuild-time exchange: migration + halo state (phase A), per-step halo lists (phase B)
+static void dd_exchange_rebuild(ocm_context* c, cudaStream_t s) {
+    DDState& d = *c->dd;
+    const int n = c->n, cap = d.cap;
+    const DDMsg slo = DDState::msg(d.a_send[0].p, cap), shi = DDState::msg(d.a_send[1].p, cap);
+    const DDMsg rlo = DDState::msg(d.a_recv[0].p, cap), rhi = DDState::msg(d.a_recv[1].p, cap);
+    CUDA_TRY(cudaMemsetAsync(d.a_send[0].p, 0, 16, s));
+    CUDA_TRY(cudaMemsetAsync(d.a_send[1].p, 0, 16, s));
+    dd_select_kernel<<<nblk(n, 256), 256, 0, s>>>(n, d.G, cap, d.role.p, c->posq.p, c->x.p, c->v.p, slo, shi, c->flags.p);
+    d.comm->ring_exchange(d.rank, d.a_send[0].p, d.a_send[1].p, d.a_recv[0].p, d.a_recv[1].p, d.bytes_a(), s);
+    dd_install_kernel<<<nblk(cap, 256), 256, 0, s>>>(d.G, c->P, cap, rlo, c->x.p, c->v.p, c->posq.p, d.known.p);
+    dd_install_kernel<<<nblk(cap, 256), 256, 0, s>>>(d.G, c->P, cap, rhi, c->x.p, c->v.p, c->posq.p, d.known.p);
+    dd_assign_kernel<<<nblk(n, 256), 256, 0, s>>>(n, d.G, c->posq.p, d.role.p, d.known.p);
+    CUDA_TRY(cudaMemsetAsync(d.b_send[0].p, 0, 16, s));
+    CUDA_TRY(cudaMemsetAsync(d.b_send[1].p, 0, 16, s));
+    dd_steplist_kernel<<<nblk(n, 256), 256, 0, s>>>(n, d.G, cap, d.role.p, c->posq.p, reinterpret_cast<int*>(d.b_send[0].p),
+                                                    reinterpret_cast<int*>(d.b_send[0].p + 16), reinterpret_cast<int*>(d.b_send[1].p),
+                                                    reinterpret_cast<int*>(d.b_send[1].p + 16), c->flags.p);
+    d.comm->ring_exchange(d.rank, d.b_send[0].p, d.b_send[1].p, d.b_recv[0].p, d.b_recv[1].p, d.bytes_b(), s);
+    for (int k = 0; k < B_NUM_KINDS; k++)
+        if (c->bonded_h[k].n > 0) dd_check_bonded_kernel<<<nblk(c->bonded_h[k].n, 256), 256, 0, s>>>(c->d_bonded.p, k, d.role.p, c->flags.p);
+    c->n_launches += 5; d.n_exchanges += 2;
+}
+
+// per MD step: ship the positions of the halo-list beads to both neighbours
+static void dd_halo_step(ocm_context* c, cudaStream_t s) {
+    DDState& d = *c->dd;
+    const int cap = d.cap;
+    auto cnt = [](DevBuf<char>& b) { return reinterpret_cast<int*>(b.p); };
+    auto idx = [](DevBuf<char>& b) { return reinterpret_cast<int*>(b.p + 16); };
+    dd_pack_kernel<<<nblk(cap, 256), 256, 0, s>>>(cnt(d.b_send[0]), idx(d.b_send[0]), d.s_send[0].p, cnt(d.b_send[1]), idx(d.b_send[1]),
+                                                  d.s_send[1].p, cap, c->x.p);
+    d.comm->ring_exchange(d.rank, d.s_send[0].p, d.s_send[1].p, d.s_recv[0].p, d.s_recv[1].p, d.bytes_s(), s);
+    dd_unpack_kernel<<<nblk(cap, 256), 256, 0, s>>>(cnt(d.b_recv[0]), idx(d.b_recv[0]), d.s_recv[0].p, cnt(d.b_recv[1]), idx(d.b_recv[1]),
+                                                    d.s_recv[1].p, cap, c->P, c->x.p, c->posq.p, c->d_lists.p, (int)c->lists.size());
+    c->n_launches += 2; d.n_exchanges += 1;
+}
+
+// flags as every rank must see them (max over ranks under a slab decomposition), on the host
+static void read_flags(ocm_context* c, int* fl) {
+    if (c->dd) c->dd->comm->allreduce(c->dd->rank, c->flags.p, FLAG_COUNT, DD_I32, true, c->stream);
+    CUDA_TRY(cudaMemcpyAsync(fl, c->flags.p, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (fl[FLAG_DD_REACH]) throw std::runtime_error("slab decomposition: a bonded term reaches beyond the halo");
+}
 
 // the list-build launch: rows are staged in shared memory (8 warps x stride x 5 bytes) to be written out in zone order
 static void launch_build(ocm_context* c, PairListHost& L, int li, cudaStream_t s, bool count_only) {
@@ -600,6 +716,7 @@ static void enqueue_rebuild(ocm_context* c, cudaStream_t s, bool count_only) {
         canon_kernel<<<nblk(n, 256), 256, 0, s>>>(c->P, c->x.p, c->posq.p);
         c->n_launches += 2;
     }
+    if (c->dd && !count_only) dd_exchange_rebuild(c, s);
     if (!count_only) save_ref_kernel<<<nblk(3 * n, 256), 256, 0, s>>>(n, c->x.p, c->xref.p);
     for (size_t l = 0; l < c->lists.size(); l++) {
         auto& L = *c->lists[l];
@@ -655,6 +772,24 @@ static void size_lists(ocm_context* c, double growth) {
         recentre_kernel<<<nblk(c->nrep * 32, 128), 128, 0, s>>>(c->P, c->x.p, c->origin.p);
         canon_kernel<<<nblk(c->n, 256), 256, 0, s>>>(c->P, c->x.p, c->posq.p);
     }
+    if (c->dd) {
+        // bring roles and halo up to date first (collective: every rank sizes its lists at the same points); the halo
+        // messages grow until nothing overflows
+        DDState& d = *c->dd;
+        if (d.cap == 0) dd_alloc(c, (int)(1.5 * c->n * d.halo / c->sys.box[d.axis]) + 1024);
+        CUDA_TRY(cudaMemcpyAsync(d.role_tmp.p, d.role.p, (size_t)c->n, cudaMemcpyDeviceToDevice, s));
+        for (int attempt = 0;; attempt++) {
+            CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, FLAG_COUNT * sizeof(int), s));
+            dd_exchange_rebuild(c, s);
+            int fl[FLAG_COUNT];
+            read_flags(c, fl);
+            if (!fl[FLAG_DD_OVERFLOW]) break;
+            if (attempt >= 8) throw std::runtime_error("slab decomposition: halo messages keep overflowing");
+            CUDA_TRY(cudaMemcpyAsync(d.role.p, d.role_tmp.p, (size_t)c->n, cudaMemcpyDeviceToDevice, s));
+            dd_alloc(c, std::max(2 * d.cap, (int)(1.5 * fl[FLAG_DD_MAXSEND])));
+        }
+        d.rows_est.assign(c->lists.size(), 0);
+    }
     std::vector<int> fl(FLAG_COUNT, 0);
     // one counting pass per list: FLAG_MAXDISP+1 receives the largest neighbour count of that list
     for (size_t l = 0; l < c->lists.size(); l++) {
@@ -674,6 +809,7 @@ static void size_lists(ocm_context* c, double growth) {
         launch_build(c, L, li, s, true);
         CUDA_TRY(cudaMemcpyAsync(fl.data(), c->flags.p, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
+        if (c->dd) CUDA_TRY(cudaMemcpy(&c->dd->rows_est[l], L.cell_start.p + L.max_cells, sizeof(int), cudaMemcpyDeviceToHost));
         int maxn = fl[FLAG_MAXDISP + 1];
         int want = (int)(maxn * growth) + 16;
         want = (want + 31) / 32 * 32;
@@ -713,14 +849,32 @@ static void ensure_lists_current(ocm_context* c) {
     if (!c->lists_ready) size_lists(c, 1.25);
     if (c->lists_current) return;
     for (int attempt = 0; attempt < 6; attempt++) {
+        if (c->dd) CUDA_TRY(cudaMemcpyAsync(c->dd->role_tmp.p, c->dd->role.p, (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
         enqueue_rebuild(c, c->stream, false);
         int fl[FLAG_COUNT];
-        CUDA_TRY(cudaMemcpyAsync(fl, c->flags.p, sizeof(fl), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        if (!fl[FLAG_OVERFLOW] && !fl[FLAG_DA_OVERFLOW]) { c->lists_current = true; return; }
+        read_flags(c, fl);
+        if (!fl[FLAG_OVERFLOW] && !fl[FLAG_DA_OVERFLOW] && !fl[FLAG_DD_OVERFLOW]) { c->lists_current = true; return; }
+        if (c->dd) {
+            // an overflowed halo message may have dropped a migrating bead: go back to the roles before the attempt
+            CUDA_TRY(cudaMemcpyAsync(c->dd->role.p, c->dd->role_tmp.p, (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
+            if (fl[FLAG_DD_OVERFLOW]) dd_alloc(c, std::max(2 * c->dd->cap, (int)(1.5 * fl[FLAG_DD_MAXSEND])));
+        }
+        CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, FLAG_COUNT * sizeof(int), c->stream));
         size_lists(c, 1.5);
     }
     throw std::runtime_error("neighbour list keeps overflowing");
+}
+
+// one window: rebuild, then nst x [forces, integrate (+ halo positions to the neighbouring slabs)]
+static void enqueue_window(ocm_context* c, cudaStream_t s, int nst) {
+    enqueue_rebuild(c, s, false);
+    for (int k = 0; k < nst; k++) {
+        enqueue_forces(c, s);
+        integrate_kernel<<<nblk(c->n, 128), 128, 0, s>>>(c->P, c->x.p, c->v.p, c->fbuf.p, c->posq.p, c->d_lists.p, (int)c->lists.size(), c->xref.p,
+                                                         c->step_base.p, k, nst, k == nst - 1 ? 1 : 0, c->flags.p);
+        // the next window starts with a full halo refresh, so the last step of a window ships nothing
+        if (c->dd && k < nst - 1) dd_halo_step(c, s);
+    }
 }
 
 static cudaGraphExec_t window_graph(ocm_context* c, int nst) {
@@ -730,12 +884,7 @@ static cudaGraphExec_t window_graph(ocm_context* c, int nst) {
     cudaGraph_t g;
     double launches_before = c->n_launches, rebuilds_before = c->n_rebuilds;
     CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    enqueue_rebuild(c, s, false);
-    for (int k = 0; k < nst; k++) {
-        enqueue_forces(c, s);
-        integrate_kernel<<<nblk(c->n, 128), 128, 0, s>>>(c->P, c->x.p, c->v.p, c->fbuf.p, c->posq.p, c->d_lists.p, (int)c->lists.size(), c->xref.p,
-                                                         c->step_base.p, k, nst, k == nst - 1 ? 1 : 0, c->flags.p);
-    }
+    enqueue_window(c, s, nst);
     CUDA_TRY(cudaStreamEndCapture(s, &g));
     c->n_launches = launches_before; c->n_rebuilds = rebuilds_before;  // counted per launch of the graph instead
     cudaGraphExec_t ge;
@@ -750,6 +899,8 @@ static double launches_per_window(const ocm_context* c, int nst) {
     for (auto& L : c->lists) if (L->np) per_rebuild += c->periodic ? 5 : 7;
     if (c->nrep > 1) per_rebuild += 2;
     if (c->da.nterms > 0 && c->da.ncand > 0) per_rebuild += 1;
+    if (c->dd) per_rebuild += 5;
+    if (c->dd) return per_rebuild + 2.0 * (nst - 1) + nst * (1.0 + (c->pair_blocks > 0 ? 1.0 : 0.0) + (c->local_blocks > 0 ? 1.0 : 0.0));
     return per_rebuild + nst * (1.0 + (c->pair_blocks > 0 ? 1.0 : 0.0) + (c->local_blocks > 0 ? 1.0 : 0.0));
 }
 
@@ -782,6 +933,7 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
         // one batch = up to 16 windows between host synchronisations
         CUDA_TRY(cudaMemcpyAsync(c->xbak.p, c->x.p, xb, cudaMemcpyDeviceToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(c->vbak.p, c->v.p, vb, cudaMemcpyDeviceToDevice, s));
+        if (c->dd) CUDA_TRY(cudaMemcpyAsync(c->dd->role_bak.p, c->dd->role.p, (size_t)c->n, cudaMemcpyDeviceToDevice, s));
         const int64_t step0 = c->step + done;
         unsigned long long sb = (unsigned long long)step0;
         CUDA_TRY(cudaMemcpyAsync(c->step_base.p, &sb, sizeof(sb), cudaMemcpyHostToDevice, s));
@@ -792,22 +944,30 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
         const int nst = c->nst;
         while (done + batch < nsteps && windows < 16) {
             int w = (int)std::min<int64_t>(nst, nsteps - done - batch);
-            CUDA_TRY(cudaGraphLaunch(window_graph(c, w), s));
+            if (c->dd) {
+                // slab decomposition: direct launches (the exchanges are host-ordered across ranks)
+                const double l0 = c->n_launches, r0 = c->n_rebuilds;
+                enqueue_window(c, s, w);
+                c->n_launches = l0; c->n_rebuilds = r0;
+            } else CUDA_TRY(cudaGraphLaunch(window_graph(c, w), s));
             launches += launches_per_window(c, w);
             batch += w; windows++;
         }
         int fl[FLAG_COUNT];
-        CUDA_TRY(cudaMemcpyAsync(fl, c->flags.p, sizeof(fl), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
+        read_flags(c, fl);
         if (fl[FLAG_NAN]) throw std::runtime_error("particle coordinate or force is NaN");
-        if (fl[FLAG_VIOLATION] || fl[FLAG_OVERFLOW] || fl[FLAG_DA_OVERFLOW]) {
+        if (fl[FLAG_VIOLATION] || fl[FLAG_OVERFLOW] || fl[FLAG_DA_OVERFLOW] || fl[FLAG_DD_OVERFLOW]) {
             // roll back and replay the batch with a safer configuration
             CUDA_TRY(cudaMemcpyAsync(c->x.p, c->xbak.p, xb, cudaMemcpyDeviceToDevice, s));
             CUDA_TRY(cudaMemcpyAsync(c->v.p, c->vbak.p, vb, cudaMemcpyDeviceToDevice, s));
             CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, (size_t)3 * c->n * sizeof(unsigned long long), s));
             canon_kernel<<<nblk(c->n, 256), 256, 0, s>>>(c->P, c->x.p, c->posq.p);
             c->n_rollbacks += 1;
-            if (fl[FLAG_OVERFLOW] || fl[FLAG_DA_OVERFLOW]) size_lists(c, 1.5);
+            if (c->dd) {
+                CUDA_TRY(cudaMemcpyAsync(c->dd->role.p, c->dd->role_bak.p, (size_t)c->n, cudaMemcpyDeviceToDevice, s));
+                if (fl[FLAG_DD_OVERFLOW]) dd_alloc(c, std::max(2 * c->dd->cap, (int)(1.5 * fl[FLAG_DD_MAXSEND])));
+            }
+            if (fl[FLAG_OVERFLOW] || fl[FLAG_DA_OVERFLOW] || fl[FLAG_DD_OVERFLOW]) size_lists(c, 1.5);
             if (fl[FLAG_VIOLATION]) {
                 if (c->nst <= 1) throw std::runtime_error("a particle crosses the Verlet buffer within one step; increase skin_nm or reduce the time step");
                 c->nst = quantise_nst(std::max(1.0, c->nst * 0.6));
@@ -842,6 +1002,48 @@ static void compute_forces_into_fbuf(ocm_context* c) {
     ensure_lists_current(c);
     CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, (size_t)3 * c->n * sizeof(unsigned long long), c->stream));
     enqueue_forces(c, c->stream);
+}
+
+// Context::getState under a slab decomposition: every rank contributes what it owns, the sums over ranks (exact for
+// positions, velocities and fixed-point forces: all other contributions are zero) give every rank the whole state
+static void get_state_dd(ocm_context* c, uint32_t mask, double* pos, double* vel, double* force, double* epot, double* ekin, double* ebg) {
+    DDState& d = *c->dd;
+    cudaStream_t s = c->stream;
+    const int n = c->n;
+    if (force && mask != 0xFFFFFFFFu) throw std::runtime_error("get_state: forces restricted to a force-group mask are not supported; request all groups");
+    ensure_lists_current(c);
+    std::vector<double> he(40, 0.0);
+    CUDA_TRY(cudaMemsetAsync(c->egroup.p, 0, he.size() * sizeof(double), s));
+    if ((epot || ebg) && c->total_blocks > 0)
+        energy_kernel<true><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->da, c->P, c->x.p, c->egroup.p);
+    if (force || ekin) {
+        compute_forces_into_fbuf(c);
+        if (ekin) kinetic_kernel<<<nblk(n, kBlock), kBlock, 0, s>>>(c->P, c->v.p, c->fbuf.p, c->egroup.p + 32);
+    }
+    if (pos && d.gx.n < (size_t)3 * n) d.gx.alloc((size_t)3 * n);
+    if (vel && d.gv.n < (size_t)3 * n) d.gv.alloc((size_t)3 * n);
+    if (force && d.gf.n < (size_t)3 * n) d.gf.alloc((size_t)3 * n);
+    if (pos || vel || force)
+        dd_mask_state_kernel<<<nblk(n, 256), 256, 0, s>>>(n, d.role.p, c->x.p, c->v.p, c->fbuf.p, pos ? d.gx.p : nullptr, vel ? d.gv.p : nullptr,
+                                                          force ? d.gf.p : nullptr);
+    if (force || ekin) CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, (size_t)3 * n * sizeof(unsigned long long), s));
+    if (pos) d.comm->allreduce(d.rank, d.gx.p, (size_t)3 * n, DD_F64, false, s);
+    if (vel) d.comm->allreduce(d.rank, d.gv.p, (size_t)3 * n, DD_F32, false, s);
+    if (force) d.comm->allreduce(d.rank, d.gf.p, (size_t)3 * n, DD_I64, false, s);
+    if (epot || ekin || ebg) d.comm->allreduce(d.rank, c->egroup.p, 40, DD_F64, false, s);
+    std::vector<float> hv;
+    std::vector<long long> hf;
+    if (pos) CUDA_TRY(cudaMemcpyAsync(pos, d.gx.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (vel) { hv.resize((size_t)3 * n); CUDA_TRY(cudaMemcpyAsync(hv.data(), d.gv.p, hv.size() * sizeof(float), cudaMemcpyDeviceToHost, s)); }
+    if (force) { hf.resize((size_t)3 * n); CUDA_TRY(cudaMemcpyAsync(hf.data(), d.gf.p, hf.size() * sizeof(long long), cudaMemcpyDeviceToHost, s)); }
+    CUDA_TRY(cudaMemcpyAsync(he.data(), c->egroup.p, he.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (vel) for (size_t k = 0; k < hv.size(); k++) vel[k] = hv[k];
+    if (force) for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) force[3 * i + k] = (double)hf[(size_t)k * n + i] / kFixScale;
+    if (epot) { double e = 0; for (int g = 0; g < 32; g++) if (mask >> g & 1) e += he[g]; *epot = e; }
+    if (ebg) std::copy(he.begin(), he.begin() + 32, ebg);
+    if (ekin) *ekin = he[32];
 }
 
 }  // namespace ocm
@@ -960,13 +1162,22 @@ int ocm_system_add_3spn2_excluded_volume(ocm_system* s, int g, double rc, const 
 }
 
 static int create_context(const ocm_system* sys, int nrep, double T, double gamma, double dt, const uint64_t* seeds, int device,
-                          ocm_context** out) {
+                          ocm_context** out, ocm_comm* comm = nullptr, int dd_rank = 0, int dd_axis = 1) {
     if (!sys || !out || !seeds) return fail("context_create: bad arguments");
     if (!(dt > 0)) return fail("context_create: time step must be positive");
     if (nrep < 1) return fail("context_create_batch: at least one replica");
     if (nrep > 1 && sys->has_box) return fail("context_create_batch: replica batches need an unlimited boundary (no box)");
     if (nrep > 1 && !sys->das.empty()) return fail("context_create_batch: donor-acceptor terms are not supported in replica batches yet");
     if ((int64_t)sys->n * nrep >= (1 << 24)) return fail("context_create: at most 16,777,215 particles are supported");
+    if (comm) {
+        if (!comm->impl) return fail("context_create_slab: communicator is closed");
+        if (!sys->has_box) return fail("context_create_slab: a slab decomposition needs a periodic box");
+        if (!sys->das.empty()) return fail("context_create_slab: donor-acceptor terms are not supported under a slab decomposition");
+        if (dd_axis < 0 || dd_axis > 2) return fail("context_create_slab: axis must be 0, 1 or 2");
+        if (dd_rank < 0 || dd_rank >= comm->impl->world) return fail("context_create_slab: rank out of range");
+        if (comm->rank >= 0 && comm->rank != dd_rank) return fail("context_create_slab: the communicator belongs to another rank");
+        for (const auto& t : sys->pairs) if (!t.periodic) return fail("context_create_slab: every pair term must be periodic");
+    }
     int ndev = ocm_device_count();
     if (ndev <= 0) return fail("context_create: no CUDA device available (this engine has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail("context_create: device index out of range");
@@ -975,6 +1186,13 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
     CUDA_TRY(cudaSetDevice(device));
     c = new ocm_context();
     c->nrep = nrep; c->nper = sys->n;
+    if (comm && comm->impl->world > 1) {
+        c->dd.reset(new DDState());
+        c->dd->comm = comm->impl; c->dd->rank = dd_rank; c->dd->world = comm->impl->world; c->dd->axis = dd_axis;
+        c->dd->role.alloc(sys->n); c->dd->role_bak.alloc(sys->n); c->dd->role_tmp.alloc(sys->n); c->dd->known.alloc(sys->n);
+        c->dd->role.zero(); c->dd->role_bak.zero(); c->dd->role_tmp.zero(); c->dd->known.zero();
+        if (auto* lc = dynamic_cast<LocalComm*>(comm->impl)) lc->attach(dd_rank, device);
+    }
     if (nrep == 1) c->sys = *sys;
     else {
         // the batch is one big system: every table replicated with shifted bead indices
@@ -1065,6 +1283,68 @@ int ocm_context_create_batch(const ocm_system* sys, int32_t n_replicas, double T
     return create_context(sys, n_replicas, T, gamma, dt, seeds, device, out);
 }
 int ocm_num_replicas(const ocm_context* c) { return c ? c->nrep : -1; }
+
+// ---- slab decomposition --------------------------------------------------------------------------
+int ocm_comm_unique_id(char* id128) {
+    if (!id128) return fail("null argument");
+    OCM_GUARD_BEGIN
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NcclApi& A = NcclApi::get();
+    A.ok(A.GetUniqueId(&id), "ncclGetUniqueId");
+    std::memcpy(id128, &id, 128);
+    return 0;
+    OCM_GUARD_END
+}
+int ocm_comm_create_nccl(const char* id128, int world, int rank, int device, ocm_comm** out) {
+    if (!id128 || !out) return fail("null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail("comm_create_nccl: rank/world out of range");
+    OCM_GUARD_BEGIN
+    int ndev = ocm_device_count();
+    if (device < 0 || device >= ndev) return fail("comm_create_nccl: device index out of range");
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    auto cm = std::make_unique<ocm_comm>();
+    cm->impl = new NcclComm(id, world, rank, device);
+    cm->rank = rank;
+    *out = cm.release();
+    return 0;
+    OCM_GUARD_END
+}
+int ocm_comm_create_local(int world, ocm_comm** out) {
+    if (!out) return fail("null argument");
+    if (world < 1 || world > kMaxLocalRanks) return fail("comm_create_local: world must be in 1..16");
+    OCM_GUARD_BEGIN
+    auto cm = std::make_unique<ocm_comm>();
+    cm->impl = new LocalComm(world);
+    *out = cm.release();
+    return 0;
+    OCM_GUARD_END
+}
+void ocm_comm_destroy(ocm_comm* comm) { delete comm; }
+int ocm_context_create_slab(const ocm_system* sys, double T, double gamma, double dt, uint64_t seed, int device, ocm_comm* comm,
+                            int rank, int axis, ocm_context** out) {
+    if (!comm) return fail("context_create_slab: null communicator");
+    return create_context(sys, 1, T, gamma, dt, &seed, device, out, comm, rank, axis);
+}
+int ocm_slab_info(const ocm_context* c, int* rank, int* world, int* axis, double* halo_nm) {
+    if (!c) return fail("null context");
+    if (rank) *rank = c->dd ? c->dd->rank : 0;
+    if (world) *world = c->dd ? c->dd->world : 1;
+    if (axis) *axis = c->dd ? c->dd->axis : -1;
+    if (halo_nm) *halo_nm = c->dd ? c->dd->halo : 0.0;
+    return 0;
+}
+int ocm_get_roles(ocm_context* c, unsigned char* role) {
+    if (!c || !role) return fail("null argument");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->dd) { std::memset(role, 1, (size_t)c->n); return 0; }
+    ensure_lists_current(c);
+    CUDA_TRY(cudaMemcpy(role, c->dd->role.p, (size_t)c->n, cudaMemcpyDeviceToHost));
+    return 0;
+    OCM_GUARD_END
+}
 void ocm_context_destroy(ocm_context* c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -1131,6 +1411,8 @@ int ocm_set_positions(ocm_context* c, const double* xyz) {
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaMemcpyAsync(c->x.p, xyz, (size_t)3 * c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     canon_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->P, c->x.p, c->posq.p);
+    // slab decomposition: every rank is handed the whole system; ownership follows from the positions
+    if (c->dd) dd_role_from_position_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->n, c->dd->G, c->posq.p, c->dd->role.p);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->positions_set = true; c->lists_current = false;
     return 0;
@@ -1174,6 +1456,7 @@ int ocm_get_state(ocm_context* c, uint32_t mask, double* pos, double* vel, doubl
     if (!c) return fail("null context");
     OCM_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
+    if (c->dd) { get_state_dd(c, mask, pos, vel, force, epot, ekin, ebg); return 0; }
     cudaStream_t s = c->stream;
     const int n = c->n;
     if (pos) CUDA_TRY(cudaMemcpyAsync(pos, c->x.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1348,6 +1631,18 @@ int ocm_get_counter(ocm_context* c, const char* key, double* value) {
     else if (k == "nstlist") *value = c->nst;
     else if (k == "last_step_ms") *value = c->last_step_ms;
     else if (k == "num_pair_lists") *value = (double)c->lists.size();
+    else if (k == "halo_exchanges") *value = c->dd ? c->dd->n_exchanges : 0.0;
+    else if (k == "halo_message_bytes") *value = c->dd ? (double)c->dd->bytes_s() : 0.0;
+    else if (k == "owned_beads") {
+        if (!c->dd) *value = c->n;
+        else {
+            CUDA_TRY(cudaSetDevice(c->device));
+            std::vector<unsigned char> r(c->n);
+            CUDA_TRY(cudaMemcpy(r.data(), c->dd->role.p, r.size(), cudaMemcpyDeviceToHost));
+            double cnt = 0; for (unsigned char q : r) cnt += q == 1;
+            *value = cnt;
+        }
+    }
     else if (k == "max_neighbors") { int m = 0; for (auto& L : c->lists) m = std::max(m, L->stride); *value = m; }
     else if (k == "pair_evals_per_step") {
         CUDA_TRY(cudaSetDevice(c->device));
@@ -1355,8 +1650,10 @@ int ocm_get_counter(ocm_context* c, const char* key, double* value) {
         double tot = 0;
         for (auto& L : c->lists) {
             if (!L->np) continue;
-            std::vector<int> cnt(L->np);
-            CUDA_TRY(cudaMemcpy(cnt.data(), L->nbr_count.p, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            int rows = L->np;
+            if (c->dd) CUDA_TRY(cudaMemcpy(&rows, L->cell_start.p + L->max_cells, sizeof(int), cudaMemcpyDeviceToHost));
+            std::vector<int> cnt(rows);
+            if (rows) CUDA_TRY(cudaMemcpy(cnt.data(), L->nbr_count.p, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
             for (int v : cnt) tot += v;
         }
         *value = tot;

@@ -811,14 +811,15 @@ def build_system(lib: Library, spec: SystemSpec) -> System:
     return sysm
 
 
-def make_context(lib: Library, spec: SystemSpec, device=0, seed=None, replicas=None) -> Context:
+def make_context(lib: Library, spec: SystemSpec, device=0, seed=None, replicas=None, comm=None, rank=0, axis=1) -> Context:
     """Simulator ctor + initialize + set_velocity (src/Simulator.cpp:4-47, ReadTOMLInput.cpp:1094-1121).
     replicas = R builds a replica ensemble (config C4): R copies of the system in one context, replica r with the
-    integrator seed `seed + r` (and velocity seed `vel_seed + r`), all starting from the spec's coordinates."""
+    integrator seed `seed + r` (and velocity seed `vel_seed + r`), all starting from the spec's coordinates.
+    comm/rank/axis build one rank of a slab decomposition (config C5); every rank passes the same spec."""
     sysm = build_system(lib, spec)
     base_seed = spec.seed if seed is None else seed
     if replicas is None:
-        ctx = Context(sysm, spec.temperature, spec.friction, spec.dt, base_seed, device)
+        ctx = Context(sysm, spec.temperature, spec.friction, spec.dt, base_seed, device, comm=comm, rank=rank, axis=axis)
         ctx.set_positions(spec.positions)
         if spec.velocities is not None:
             ctx.set_velocities(spec.velocities)

@@ -121,7 +121,12 @@ struct ocm_context {
     int64_t step;
     std::vector<Vec3> x, v;
     bool force_brute;
+    // slab decomposition (restated as a plan only: which rank owns / sees which bead; the arithmetic is rank-free)
+    int dd_rank = 0, dd_world = 1, dd_axis = -1;
+    double dd_halo = 0;
 };
+
+struct ocm_comm { int world; };
 
 namespace {
 
@@ -1102,11 +1107,61 @@ int oracle_context_create_batch(const ocm_system* sys, int32_t nrep, double T, d
     return 0;
 }
 int oracle_num_replicas(const ocm_context* c) { return c ? c->nrep : -1; }
+
+// ---- slab decomposition: the oracle restates the ownership rule of include/ocm_b200.h (rank r owns the beads whose
+// fixed-point coordinate q on the axis has (q * world) >> 32 == r; halo = outside the slab within halo_nm of a face).
+// Forces, energies and trajectories do not depend on the decomposition, so a slab context is a plain context.
+int oracle_comm_unique_id(char*) { return fail("the oracle has no NCCL transport"); }
+int oracle_comm_create_nccl(const char*, int, int, int, ocm_comm**) { return fail("the oracle has no NCCL transport"); }
+int oracle_comm_create_local(int world, ocm_comm** out) {
+    if (!out || world < 1) return fail("comm_create_local: bad arguments");
+    *out = new ocm_comm{world};
+    return 0;
+}
+void oracle_comm_destroy(ocm_comm* c) { delete c; }
+int oracle_context_create_slab(const ocm_system* sys, double T, double gamma, double dt, uint64_t seed, int device, ocm_comm* comm,
+                               int rank, int axis, ocm_context** out) {
+    if (!comm) return fail("context_create_slab: null communicator");
+    if (!sys || !sys->has_box) return fail("context_create_slab: a slab decomposition needs a periodic box");
+    if (axis < 0 || axis > 2) return fail("context_create_slab: axis must be 0, 1 or 2");
+    if (rank < 0 || rank >= comm->world) return fail("context_create_slab: rank out of range");
+    if (oracle_context_create(sys, T, gamma, dt, seed, device, out)) return 1;
+    (*out)->dd_rank = rank; (*out)->dd_world = comm->world; (*out)->dd_axis = axis;
+    return 0;
+}
+int oracle_slab_info(const ocm_context* c, int* rank, int* world, int* axis, double* halo_nm) {
+    if (!c) return fail("null context");
+    if (rank) *rank = c->dd_rank;
+    if (world) *world = c->dd_world;
+    if (axis) *axis = c->dd_axis;
+    if (halo_nm) *halo_nm = c->dd_halo;
+    return 0;
+}
+int oracle_get_roles(ocm_context* c, unsigned char* role) {
+    if (!c || !role) return fail("null argument");
+    const int n = c->sys.n;
+    if (c->dd_world <= 1) { for (int i = 0; i < n; i++) role[i] = 1; return 0; }
+    Canon q = canonicalise(*c);
+    const std::vector<uint32_t>& f = c->dd_axis == 0 ? q.fx : (c->dd_axis == 1 ? q.fy : q.fz);
+    const double two32 = 4294967296.0, len = c->sys.box[c->dd_axis];
+    const int W = c->dd_world, r = c->dd_rank;
+    const uint32_t lo = (uint32_t)(uint64_t)std::ceil((double)r * two32 / W);
+    const uint32_t hi = r + 1 == W ? 0u : (uint32_t)(uint64_t)std::ceil((double)(r + 1) * two32 / W);
+    const int32_t hf = (int32_t)((uint32_t)std::ceil(c->dd_halo / len * two32) + 2u);
+    for (int i = 0; i < n; i++) {
+        const int owner = (int)(((uint64_t)f[i] * (uint64_t)W) >> 32);
+        const int32_t below = (int32_t)(lo - 1u - f[i]), above = (int32_t)(f[i] - hi);
+        const bool halo = (below >= 0 && below < hf) || (above >= 0 && above < hf);
+        role[i] = owner == r ? 1 : (halo ? 2 : 0);
+    }
+    return 0;
+}
 void oracle_context_destroy(ocm_context* c) { delete c; }
 
 int oracle_context_set_option(ocm_context* c, const char* key, double v) {
     if (!c) return fail("null context");
     if (!strcmp(key, "brute_force")) { c->force_brute = v != 0; return 0; }
+    if (!strcmp(key, "slab_halo_nm")) { c->dd_halo = v; return 0; }
     if (!strcmp(key, "threads")) {
 #ifdef _OPENMP
         omp_set_num_threads((int)v);

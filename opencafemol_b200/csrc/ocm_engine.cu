@@ -696,7 +696,8 @@ static void read_flags(ocm_context* c, int* fl) {
     if (c->dd) c->dd->comm->allreduce(c->dd->rank, c->flags.p, FLAG_COUNT, DD_I32, true, c->stream);
     CUDA_TRY(cudaMemcpyAsync(fl, c->flags.p, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (fl[FLAG_DD_REACH]) throw std::runtime_error("slab decomposition: a bonded term reaches beyond the halo");
+    // (an overflowed halo message leaves beads missing: the reach check is only meaningful without overflow)
+    if (fl[FLAG_DD_REACH] && !fl[FLAG_DD_OVERFLOW]) throw std::runtime_error("slab decomposition: a bonded term reaches beyond the halo");
 }
 
 // the list-build launch: rows are staged in shared memory (8 warps x stride x 5 bytes) to be written out in zone order
@@ -1372,6 +1373,13 @@ int ocm_context_set_option(ocm_context* c, const char* key, double value) {
         for (auto& L : c->lists) L->stride = 0;
         drop_graphs(c);
         if (c->nstlist_fixed <= 0) c->nst = initial_nst(c);
+    } else if (k == "halo_capacity") {
+        // entries per halo message of a slab decomposition (grown automatically on overflow)
+        if (!c->dd) return fail("halo_capacity: not a slab context");
+        if (value < 1 || value > (1 << 24)) return fail("halo_capacity out of range");
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        dd_alloc(c, (int)value);
+        c->lists_current = false;
     } else if (k == "nstlist") {
         c->nstlist_fixed = (int)value;
         if (c->nstlist_fixed > 0) c->nst = c->nstlist_fixed; else c->nst = initial_nst(c);
@@ -1401,6 +1409,7 @@ int ocm_context_get_option(ocm_context* c, const char* key, double* value) {
     else if (k == "threads_per_bead") *value = c->tpb_opt;
     else if (k == "beads_per_block") *value = c->chunk_opt;
     else if (k == "row_staging") *value = c->staging_opt;
+    else if (k == "halo_capacity") *value = c->dd ? c->dd->cap : 0;
     else return fail("unknown option: " + k);
     return 0;
 }

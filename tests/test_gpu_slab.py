@@ -128,7 +128,10 @@ def test_slab_adaptive_rebuild_and_message_growth(engine):
     a = ref.get_state(positions=True)
     run = SlabRun(engine, spec, 2, 1)
     try:
+        for c in run.ctx:
+            c.set_option("halo_capacity", 256)
         run.each(lambda c: c.step(300))
+        assert all(c.get_option("halo_capacity") > 256 for c in run.ctx)
         for st in run.each(lambda c: c.get_state(positions=True)):
             # different rebuild cadence changes only the FP32 summation order
             assert np.abs(st["positions"] - a["positions"]).max() < 1e-4

@@ -1,0 +1,209 @@
+"""Golden vectors from the REFERENCE ITSELF (run in the build container, where /root/reference is mounted):
+
+    make -C oracle ref && python tests/golden/make_ref_golden.py
+
+oracle/_ref/libocm_ref.so is the reference's own reader, Topology, force-field generators, SystemGenerator,
+Simulator and Observers compiled unmodified against the stand-in OpenMM / toml11 headers of oracle/ref_shim
+(see oracle/Makefile).  For each sample input this script stores, under tests/golden/ref_<name>.json.gz:
+
+  * per-force-group energies (kJ/mol), forces, kinetic energy at the sample's coordinates (FUS: after an energy
+    minimisation, because the shipped coordinates overlap);
+  * a digest of every OpenMM::Force the reference built (class, group, counts, cutoff, exclusion hash);
+  * a short Langevin trajectory (shared Philox noise) for the small systems;
+  * the files the reference's own main program writes (.ene lines, PDB head, DCD bytes) for a short run.
+
+The fixtures travel to the GPU box; /root/reference does not.
+"""
+import gzip
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import tomllib
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_binding as rb  # noqa: E402
+from opencafemol_b200 import toml_input as ti  # noqa: E402
+
+REF = "/root/reference/sample/toml_input"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ---- a minimal TOML writer (enough for the sample inputs) ---------------------------------------------
+def _inline(v):
+    if isinstance(v, bool):
+        return "true" if v else "false"
+    if isinstance(v, (int, float)):
+        return repr(v)
+    if isinstance(v, str):
+        return json.dumps(v)
+    if isinstance(v, list):
+        return "[" + ", ".join(_inline(x) for x in v) + "]"
+    if isinstance(v, dict):
+        return "{" + ", ".join(f"{json.dumps(k)} = {_inline(x)}" for k, x in v.items()) + "}"
+    raise TypeError(type(v))
+
+
+def dump_toml(d, prefix=""):
+    out = []
+    for k, v in d.items():
+        if not isinstance(v, dict) and not (isinstance(v, list) and v and all(isinstance(x, dict) for x in v) and k in ("systems", "forcefields", "local", "global")):
+            if isinstance(v, list) and v and all(isinstance(x, dict) for x in v):
+                out.append(f"{k} = [\n" + "".join("  " + _inline(x) + ",\n" for x in v) + "]")
+            else:
+                out.append(f"{k} = {_inline(v)}")
+    for k, v in d.items():
+        if isinstance(v, dict):
+            out.append(f"[{prefix}{k}]")
+            out.append(dump_toml(v, prefix + k + "."))
+        elif isinstance(v, list) and v and all(isinstance(x, dict) for x in v) and k in ("systems", "forcefields", "local", "global"):
+            for x in v:
+                out.append(f"[[{prefix}{k}]]")
+                out.append(dump_toml(x, prefix + k + "."))
+    return "\n".join(out)
+
+
+def fus_subset(n_chains=10, chain_len=163):
+    """FUS_100_HPS.toml restricted to its first n_chains chains (same box, same parameters)."""
+    with open(os.path.join(REF, "FUS_100_HPS.toml"), "rb") as fh:
+        d = tomllib.load(fh)
+    n = n_chains * chain_len
+    d["systems"][0]["particles"] = d["systems"][0]["particles"][:n]
+    ff = d["forcefields"][0]
+    for key in ("local", "global"):
+        for f in ff.get(key, []):
+            keep = []
+            for p in f["parameters"]:
+                idx = p.get("indices", p.get("index"))
+                idx = idx if isinstance(idx, list) else [idx]
+                if all(i < n for i in idx):
+                    keep.append(p)
+            f["parameters"] = keep
+    d["simulator"]["energy_minimization"] = False
+    return dump_toml(d)
+
+
+def force_digest(desc):
+    out = []
+    for f in desc["forces"]:
+        e = {"class": f["class"], "group": f["group"]}
+        for key in ("bonds", "angles", "torsions", "particles", "donors", "acceptors"):
+            if key in f:
+                e["n_" + key] = len(f[key])
+        if "cutoff" in f:
+            e["cutoff"] = f["cutoff"]
+            e["method"] = f["method"]
+        if "use_switch" in f:
+            e["use_switch"] = f["use_switch"]
+            e["switch_distance"] = f["switch_distance"]
+        if "exclusions" in f:
+            ex = sorted((min(a, b), max(a, b)) for a, b in f["exclusions"]) if f["class"] == "CustomNonbondedForce" else sorted(map(tuple, f["exclusions"]))
+            e["n_exclusions"] = len(ex)
+            e["exclusions_sha1"] = hashlib.sha1(np.asarray(ex, np.int32).tobytes()).hexdigest()
+        if "interaction_groups" in f:
+            e["interaction_groups"] = [[len(a), len(b), hashlib.sha1(np.asarray(a + b, np.int32).tobytes()).hexdigest()] for a, b in f["interaction_groups"]]
+        if "expression" in f:
+            e["expression"] = f["expression"]
+            e["globals"] = f["globals"]
+        out.append(e)
+    return out
+
+
+def run_program(toml_text, workdir, fmt):
+    """the reference's main program on `toml_text`; returns the bytes of the files it wrote"""
+    d = tomllib.loads(toml_text)
+    d["files"]["output"]["format"] = fmt
+    d["files"]["output"]["path"] = "./out/"
+    d["files"]["output"]["prefix"] = "run"
+    d["simulator"]["energy_minimization"] = False
+    d["simulator"]["total_step"] = 40
+    d["simulator"]["save_step"] = 10
+    os.makedirs(os.path.join(workdir, "out"), exist_ok=True)
+    with open(os.path.join(workdir, "in.toml"), "w") as fh:
+        fh.write(dump_toml(d))
+    subprocess.run([rb.REF_BIN, "in.toml"], cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    files = {}
+    for fn in sorted(os.listdir(os.path.join(workdir, "out"))):
+        with open(os.path.join(workdir, "out", fn), "rb") as fh:
+            files[fn] = fh.read()
+    return files, dump_toml(d)
+
+
+def main():
+    assert rb.available(), "build oracle/_ref first: make -C oracle ref"
+    R = rb.RefLibrary()
+    tmp = tempfile.mkdtemp(prefix="refgold_")
+    samples = {"sh3": open(os.path.join(REF, "sh3_AICG2+.toml")).read(),
+               "dna_3spn2": open(os.path.join(REF, "dna_3SPN2.toml")).read(),
+               "nucleosome": open(os.path.join(REF, "nucleosome_1kx5.toml")).read(),
+               "fus10": fus_subset(10)}
+    for name, text in samples.items():
+        path = os.path.join(tmp, name + ".toml")
+        with open(path, "w") as fh:
+            fh.write(text)
+        rs = R.open_toml(path)
+        spec = ti.read_toml(path)
+        out = {"source": name, "n": rs.n, "group_map": rs.group_map(), "integrator": rs.integrator()}
+        if name == "fus10":
+            rs.minimize(tolerance=10.0, max_iterations=400)
+            # the spec fixture for this case is written here (the other samples have theirs from make_golden.py)
+            spec.positions = rs.positions()
+            with gzip.open(os.path.join(HERE, "fus10_spec.json.gz"), "wt") as fh:
+                json.dump(ti.spec_to_dict(spec), fh)
+        x0 = rs.positions()
+        out["positions"] = x0.tolist()
+        out["energy_by_group_kj"] = rs.energy_by_group()
+        e, f = rs.energy(forces=True)
+        out["potential_energy_kj"] = e
+        out["forces"] = f.tolist()
+        out["force_digest"] = force_digest(rs.describe())
+        # short Langevin run with the documented Philox noise (same streams as oracle/ocm_oracle.cpp and the engine)
+        if spec.velocities is not None:
+            rs.set_velocities(spec.velocities)
+        else:
+            rs.set_velocities_to_temperature(spec.temperature, 2026)
+        out["vel_seed_used"] = None if spec.velocities is not None else 2026
+        out["kinetic_energy_kj"] = rs.kinetic_energy()
+        nst = 20
+        rs.step(nst)
+        out["trajectory"] = {"steps": nst, "positions": rs.positions().tolist(), "velocities": rs.velocities().tolist()}
+        rs.close()
+        # what the reference's own main program writes
+        if name in ("sh3", "fus10"):
+            files = {}
+            for fmt in ("pdb", "dcd"):
+                wd = os.path.join(tmp, name + "_" + fmt)
+                os.makedirs(wd, exist_ok=True)
+                if name == "fus10":
+                    # start the program from the minimised coordinates
+                    d = tomllib.loads(text)
+                    for p, xyz in zip(d["systems"][0]["particles"], x0 * 10.0):
+                        p["pos"] = [float(v) for v in xyz]
+                    text_run = dump_toml(d)
+                else:
+                    text_run = text
+                got, used = run_program(text_run, wd, fmt)
+                for fn, b in got.items():
+                    if fn.endswith((".ene", ".pdb")):
+                        files[fn] = {"text": b.decode()} if len(b) < 200000 else {"sha256": hashlib.sha256(b).hexdigest(), "head": b[:2000].decode(), "size": len(b)}
+                    else:
+                        files[fn] = {"sha256": hashlib.sha256(b).hexdigest(), "size": len(b), "head_hex": b[:400].hex()}
+                if fmt == "dcd":
+                    with gzip.open(os.path.join(HERE, f"ref_{name}_run.toml.gz"), "wt") as fh:
+                        fh.write(used)
+            out["program_files"] = files
+        with gzip.open(os.path.join(HERE, f"ref_{name}.json.gz"), "wt") as fh:
+            json.dump(out, fh)
+        print(name, "N", out["n"], {k: round(v / 4.184, 6) for k, v in out["energy_by_group_kj"].items()})
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -240,6 +240,13 @@ int ocm_set_velocities_to_temperature(ocm_context*, double temperature_K, uint64
 int ocm_step(ocm_context*, int64_t nsteps);
 int64_t ocm_current_step(const ocm_context*);
 
+/* LocalEnergyMinimizer::minimize(context) (Simulator.cpp:43-46; OpenMM defaults: tolerance 10 kJ/mol/nm,
+ * maxIterations 0 = until convergence): L-BFGS on the potential energy from the current positions until the
+ * RMS force per particle drops below `tolerance`.  Energies and forces are evaluated on the device, the
+ * two-loop recursion runs on the host.  Velocities are untouched.  Outputs may be NULL. */
+int ocm_minimize(ocm_context*, double tolerance_kj_mol_nm, int max_iterations, int* iterations,
+                 double* final_energy);
+
 /* Context::getState (Observer.cpp:34,107,113,340,344).  Any output pointer may be NULL.
  * pos/vel/force: 3*N doubles; epot: sum over groups in group_mask; ekin: leap-frog kinetic
  * energy shifted by dt/2 as OpenMM reports it; epot_by_group: 32 doubles (all groups). */

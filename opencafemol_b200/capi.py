@@ -214,6 +214,7 @@ class Library:
         "set_velocities_to_temperature": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64]),
         "step": (C.c_int, [C.c_void_p, C.c_int64]),
         "current_step": (C.c_int64, [C.c_void_p]),
+        "minimize": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
         "get_state": (C.c_int, [C.c_void_p, C.c_uint32, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]),
         "num_pair_terms": (C.c_int, [C.c_void_p]),
         "get_neighbor_pairs": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int64, _i64p]),
@@ -527,6 +528,12 @@ class Context:
 
     def step(self, nsteps):
         self.lib.check(self.lib.fn["step"](self.handle, int(nsteps)))
+
+    def minimize(self, tolerance=10.0, max_iterations=0):
+        """LocalEnergyMinimizer::minimize (src/Simulator.cpp:43-46); returns (iterations, final potential energy)"""
+        it, e = C.c_int(), C.c_double()
+        self.lib.check(self.lib.fn["minimize"](self.handle, float(tolerance), int(max_iterations), C.byref(it), C.byref(e)))
+        return it.value, e.value
 
     @property
     def current_step(self):

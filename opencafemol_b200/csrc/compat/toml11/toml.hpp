@@ -1,10 +1,12 @@
-// toml.hpp — stand-in for the toml11 header the reference includes (`#include <toml.hpp>`).
+// toml.hpp — the slice of the toml11 v4 interface the reference's reader is written against
+// (`#include <toml.hpp>` in src/input/*.cpp, src/util/Utility.hpp), on top of this repository's TOML reader
+// (../../host/toml_lite.hpp).
 //
-// TEST INFRASTRUCTURE (oracle/_ref build only).  The reference reads its inputs through toml11 (git
-// submodule, not vendored under /root/reference, no network).  To compile the reference's OWN reader
-// (src/input/*.cpp) unmodified, this header offers the slice of the toml11 v4 interface those files use
-// (toml::value, find / find_or / get / get_or, parse, format_error, make_error_info) on top of the
-// repository's small TOML reader (opencafemol_b200/csrc/host/toml_lite.hpp).  Nothing of toml11 is copied.
+// The reference reads its inputs through toml11 (git submodule, not vendored in its tree, not available
+// offline).  With this directory on the include path its reader compiles unmodified — both for the drop-in
+// build on the B200 engine (compat/Makefile) and for the checker build (oracle/Makefile, target `ref`).
+// Offered: toml::value, array, table, find / find_or / get / get_or, parse, format_error, make_error_info.
+// Nothing of toml11 is copied.
 #ifndef OCM_REF_SHIM_TOML_HPP
 #define OCM_REF_SHIM_TOML_HPP
 
@@ -21,7 +23,7 @@
 #include <utility>
 #include <vector>
 
-#include "toml_lite.hpp"
+#include "../../host/toml_lite.hpp"
 
 namespace toml {
 

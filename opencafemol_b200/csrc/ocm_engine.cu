@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -23,6 +24,7 @@
 #include <vector>
 
 #include "host_system.hpp"
+#include "host/lbfgs.hpp"
 #include "kernels.cuh"
 #include "dd_kernels.cuh"
 #include "dd_comm.hpp"
@@ -121,6 +123,7 @@ struct ocm_context {
     double T = 0, gamma = 0, dt = 0;
     uint64_t seed = 0;
     int64_t step = 0;
+    int counters_minimize_evals = 0;
     int device = 0;
     int nrep = 1, nper = 0;                 // replica batch: nrep independent copies of nper beads
     std::vector<uint64_t> rep_seeds;
@@ -1461,6 +1464,38 @@ int ocm_step(ocm_context* c, int64_t nsteps) {
 }
 int64_t ocm_current_step(const ocm_context* c) { return c ? c->step : -1; }
 
+int ocm_minimize(ocm_context* c, double tolerance, int max_iterations, int* iterations, double* final_energy) {
+    if (!c) return fail("null context");
+    if (c->dd) return fail("minimize: not available under slab decomposition; minimise on one device first");
+    if (c->nrep > 1) return fail("minimize: not available for replica batches");
+    if (!(tolerance > 0)) return fail("minimize: tolerance must be positive");
+    OCM_GUARD_BEGIN
+    const int n = c->n;
+    std::vector<double> x((size_t)3 * n), f((size_t)3 * n);
+    if (ocm_get_state(c, 0xFFFFFFFFu, x.data(), nullptr, nullptr, nullptr, nullptr, nullptr)) return 1;
+    bool bad = false;
+    auto eval = [&](const std::vector<double>& at, std::vector<double>& grad) {
+        double e = 0;
+        if (ocm_set_positions(c, at.data()) || ocm_get_state(c, 0xFFFFFFFFu, nullptr, nullptr, f.data(), &e, nullptr, nullptr)) {
+            bad = true;
+            return std::numeric_limits<double>::infinity();
+        }
+        for (int i = 0; i < n; i++) {
+            const bool mobile = c->sys.mass[i] > 0;
+            for (int k = 0; k < 3; k++) grad[3 * i + k] = mobile ? -f[3 * i + k] : 0.0;
+        }
+        return e;
+    };
+    const ocmhost::LbfgsReport rep = ocmhost::lbfgs_minimize(x, eval, tolerance, max_iterations);
+    if (bad) return 1;
+    if (ocm_set_positions(c, x.data())) return 1;
+    if (iterations) *iterations = rep.iterations;
+    if (final_energy) *final_energy = rep.energy;
+    c->counters_minimize_evals = rep.evaluations;
+    return 0;
+    OCM_GUARD_END
+}
+
 int ocm_get_state(ocm_context* c, uint32_t mask, double* pos, double* vel, double* force, double* epot, double* ekin, double* ebg) {
     if (!c) return fail("null context");
     OCM_GUARD_BEGIN
@@ -1635,6 +1670,7 @@ int ocm_get_counter(ocm_context* c, const char* key, double* value) {
     OCM_GUARD_BEGIN
     std::string k(key);
     if (k == "rebuilds") *value = c->n_rebuilds;
+    else if (k == "minimize_evaluations") *value = c->counters_minimize_evals;
     else if (k == "rollbacks") *value = c->n_rollbacks;
     else if (k == "kernel_launches") *value = c->n_launches;
     else if (k == "nstlist") *value = c->nst;

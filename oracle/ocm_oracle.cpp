@@ -1235,6 +1235,85 @@ int oracle_step(ocm_context* c, int64_t nsteps) {
 }
 int64_t oracle_current_step(const ocm_context* c) { return c ? c->step : -1; }
 
+// LocalEnergyMinimizer::minimize (src/Simulator.cpp:43-46): L-BFGS (history 8) with step halving, until the RMS
+// force per particle is below `tolerance` (kJ/mol/nm).  Written independently of the engine's host/lbfgs.hpp; the
+// tests compare outcomes (a stationary point below the tolerance), not iterates.
+int oracle_minimize(ocm_context* c, double tolerance, int max_iterations, int* iterations, double* final_energy) {
+    if (!c) return fail("null context");
+    if (!(tolerance > 0)) return fail("minimize: tolerance must be positive");
+    const int n = c->sys.n;
+    const size_t N = (size_t)3 * n;
+    auto energy_grad = [&](const std::vector<double>& at, std::vector<double>& grad) {
+        for (int i = 0; i < n; i++) c->x[i] = {at[3 * i], at[3 * i + 1], at[3 * i + 2]};
+        std::vector<Vec3> F; double Eg[32];
+        compute(*c, &F, Eg, 0xFFFFFFFFu);
+        double e = 0;
+        for (int g = 0; g < 32; g++) e += Eg[g];
+        for (int i = 0; i < n; i++) {
+            const bool mobile = c->sys.mass[i] > 0;
+            grad[3 * i] = mobile ? -F[i].x : 0; grad[3 * i + 1] = mobile ? -F[i].y : 0; grad[3 * i + 2] = mobile ? -F[i].z : 0;
+        }
+        return e;
+    };
+    std::vector<double> x(N), g(N), xt(N), gt(N), q(N);
+    for (int i = 0; i < n; i++) { x[3 * i] = c->x[i].x; x[3 * i + 1] = c->x[i].y; x[3 * i + 2] = c->x[i].z; }
+    double E = energy_grad(x, g);
+    std::vector<std::vector<double>> dx, dg;
+    const int hist = 8, itmax = max_iterations > 0 ? max_iterations : 1000000;
+    int it = 0, stalls = 0;
+    for (; it < itmax; it++) {
+        double gg = 0;
+        for (double v : g) gg += v * v;
+        if (std::sqrt(gg / std::max(1, n)) < tolerance) break;
+        q = g;
+        std::vector<double> a(dx.size());
+        for (int k = (int)dx.size() - 1; k >= 0; k--) {
+            double sy = 0, sq = 0;
+            for (size_t i = 0; i < N; i++) { sy += dx[k][i] * dg[k][i]; sq += dx[k][i] * q[i]; }
+            a[k] = sq / sy;
+            for (size_t i = 0; i < N; i++) q[i] -= a[k] * dg[k][i];
+        }
+        double scale = 0.01 / std::sqrt(std::max(gg, 1e-300));
+        if (!dx.empty()) {
+            double sy = 0, yy = 0;
+            for (size_t i = 0; i < N; i++) { sy += dx.back()[i] * dg.back()[i]; yy += dg.back()[i] * dg.back()[i]; }
+            scale = sy / yy;
+        }
+        for (double& v : q) v *= scale;
+        for (size_t k = 0; k < dx.size(); k++) {
+            double sy = 0, yq = 0;
+            for (size_t i = 0; i < N; i++) { sy += dx[k][i] * dg[k][i]; yq += dg[k][i] * q[i]; }
+            const double b = yq / sy;
+            for (size_t i = 0; i < N; i++) q[i] += dx[k][i] * (a[k] - b);
+        }
+        double slope = 0;
+        for (size_t i = 0; i < N; i++) slope += g[i] * q[i];
+        bool moved = false;
+        if (slope > 0) {
+            double t = 1.0;
+            for (int h = 0; h < 50 && !moved; h++, t *= 0.5) {
+                for (size_t i = 0; i < N; i++) xt[i] = x[i] - t * q[i];
+                const double Et = energy_grad(xt, gt);
+                if (std::isfinite(Et) && Et <= E - 1e-4 * t * slope) {
+                    std::vector<double> s(N), y(N);
+                    double sy = 0;
+                    for (size_t i = 0; i < N; i++) { s[i] = xt[i] - x[i]; y[i] = gt[i] - g[i]; sy += s[i] * y[i]; }
+                    if (sy > 1e-12) { dx.push_back(s); dg.push_back(y); if ((int)dx.size() > hist) { dx.erase(dx.begin()); dg.erase(dg.begin()); } }
+                    x = xt; g = gt; E = Et; moved = true;
+                }
+            }
+        }
+        if (!moved) {
+            if (dx.empty() || ++stalls > 50) break;
+            dx.clear(); dg.clear();
+        }
+    }
+    for (int i = 0; i < n; i++) c->x[i] = {x[3 * i], x[3 * i + 1], x[3 * i + 2]};
+    if (iterations) *iterations = it;
+    if (final_energy) *final_energy = E;
+    return 0;
+}
+
 int oracle_get_state(ocm_context* c, uint32_t mask, double* pos, double* vel, double* force, double* epot, double* ekin, double* ebg) {
     if (!c) return fail("null context");
     int n = c->sys.n;

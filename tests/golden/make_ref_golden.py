@@ -186,6 +186,7 @@ def main():
                     d = tomllib.loads(text)
                     for p, xyz in zip(d["systems"][0]["particles"], x0 * 10.0):
                         p["pos"] = [float(v) for v in xyz]
+                    d["systems"][0]["vel_seed"] = 2026  # the sample has neither velocities nor a seed: make the run reproducible
                     text_run = dump_toml(d)
                 else:
                     text_run = text
@@ -195,6 +196,8 @@ def main():
                         files[fn] = {"text": b.decode()} if len(b) < 200000 else {"sha256": hashlib.sha256(b).hexdigest(), "head": b[:2000].decode(), "size": len(b)}
                     else:
                         files[fn] = {"sha256": hashlib.sha256(b).hexdigest(), "size": len(b), "head_hex": b[:400].hex()}
+                        if len(b) < 65536:
+                            files[fn]["hex"] = b.hex()
                 if fmt == "dcd":
                     with gzip.open(os.path.join(HERE, f"ref_{name}_run.toml.gz"), "wt") as fh:
                         fh.write(used)

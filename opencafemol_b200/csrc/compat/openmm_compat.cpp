@@ -193,13 +193,19 @@ class SystemCompiler {
     };
     static Norm normalise(const CustomForceBase& f, const std::vector<std::string>* aparams = nullptr) {
         Norm nz;
-        std::string first;
-        if (!f.params_.empty()) first = f.params_[0];
-        else if (aparams && !aparams->empty()) first = (*aparams)[0];
-        else if (!f.globals_.empty()) first = f.globals_[0].first;
-        std::string prefix;
-        const std::size_t us = first.find('_');
-        if (us != std::string::npos) prefix = first.substr(0, us + 1);
+        // the generator id ("EXV0", "TSPN2_CS7", ...) is the longest common prefix of all parameter names, cut back
+        // to its last underscore
+        std::vector<std::string> names = f.params_;
+        if (aparams) names.insert(names.end(), aparams->begin(), aparams->end());
+        for (auto& g : f.globals_) names.push_back(g.first);
+        std::string prefix = names.empty() ? std::string() : names[0];
+        for (auto& nm : names) {
+            std::size_t k = 0;
+            while (k < prefix.size() && k < nm.size() && prefix[k] == nm[k]) ++k;
+            prefix.resize(k);
+        }
+        const std::size_t us = prefix.rfind('_');
+        prefix = us == std::string::npos ? std::string() : prefix.substr(0, us + 1);
         auto strip = [&](const std::string& s) { return (!prefix.empty() && s.compare(0, prefix.size(), prefix) == 0) ? s.substr(prefix.size()) : s; };
         nz.expr = strip_ws(f.expr_);
         replace_all(nz.expr, prefix, "");

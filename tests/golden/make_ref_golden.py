@@ -176,7 +176,7 @@ def main():
         out["trajectory"] = {"steps": nst, "positions": rs.positions().tolist(), "velocities": rs.velocities().tolist()}
         rs.close()
         # what the reference's own main program writes
-        if name in ("sh3", "fus10"):
+        if name in ("sh3", "dna_3spn2", "fus10"):
             files = {}
             for fmt in ("pdb", "dcd"):
                 wd = os.path.join(tmp, name + "_" + fmt)

@@ -85,7 +85,7 @@ def test_frontend_fails_loudly_without_gpu(built, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,periodic", [("sh3", False), ("fus10", True)])
+@pytest.mark.parametrize("name,periodic", [("sh3", False), ("dna_3spn2", False), ("fus10", True)])
 def test_frontend_writes_the_reference_files(engine, tmp_path, name, periodic):
     if not os.path.exists(BIN):
         pytest.fail("bin/open_cafemol_b200 missing: it is built by __graft_entry__.build() in the build container and travels with the snapshot")

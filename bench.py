@@ -98,6 +98,17 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def ncu_traffic():
+    """dram bytes (read + write) per force_kernel launch from the committed `ncu --set full` capture, or None"""
+    p = os.path.join(ROOT, "profiles", "force_kernel_ncu.json")
+    try:
+        with open(p) as fh:
+            d = json.load(fh)
+        return {"dram_bytes_per_launch": d["dram_bytes_read"] + d["dram_bytes_write"], "source": d.get("source", "profiles/force_kernel_ncu.json")}
+    except Exception:
+        return None
+
+
 def cpu_port_run(spec, md_steps, threads=None):
     """Times the CPU oracle (OpenMM-equivalent CPU restatement of the reference path; OpenMM itself is
     not installable offline) on `md_steps` MD steps of the same workload."""
@@ -135,12 +146,20 @@ def config_dict(spec, extra=None):
     return c
 
 
+CPU_SAMPLE_STEPS = 100      # MD steps per bench step of the CPU arm (a few seconds on 16 cores)
+CPU_BASELINE_STEPS = 400    # MD steps of the cpu_baseline leg of the engine arm (10-30 s of CPU work)
+
+
 def run_reference(args):
+    """CPU arm.  The reference's arithmetic lives in OpenMM, which cannot be installed offline; what runs here is the
+    OpenMP double-precision restatement (oracle/ocm_oracle.cpp, kind "port") on all host cores.  oracle/_ref (the
+    reference's own sources on a stand-in OpenMM with an expression interpreter) is the parity checker, not a fair
+    performance baseline: it is single-threaded and interprets every pair."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     spec = workload()
-    sample_steps = 20
+    sample_steps = CPU_SAMPLE_STEPS
     for _ in range(args.warmup):
         cpu_port_run(spec, 2)
     vals, cores = [], 1
@@ -254,7 +273,7 @@ def run_engine(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp32", "kernel": "force_kernel (fused pair lists + bonded)", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": ncu_traffic(),
                          "peak_source": "register-resident FMA microbenchmark on this GPU (SURVEY.md 8d); no tensor-core work on this path",
                          "algorithmic_flop_per_launch": flop, "ms_per_launch": ms_force,
                          "in_cutoff_pairs": {"ashbaugh_hatch": n_ah, "debye_huckel": n_dh}},
@@ -264,7 +283,7 @@ def run_engine(args):
             "kernel_ms": {"force": ms_force, "integrate": ms_int, "rebuild_all_lists": ms_reb},
         }
         if world == 1 and not args.no_cpu_baseline:
-            sample = 20
+            sample = CPU_BASELINE_STEPS
             v, cores, dt = cpu_port_run(spec, sample)
             line["cpu_baseline"] = {"value": v, "unit": "ns/day", "cores": cores, "kind": "port",
                                     "sample": f"{sample} MD steps of the same C2 workload ({dt:.1f} s); OpenMM-equivalent CPU restatement "

@@ -12,6 +12,7 @@
 #include <nccl.h>
 
 #include <chrono>
+#include <cstring>
 #include <condition_variable>
 #include <mutex>
 #include <stdexcept>
@@ -32,6 +33,11 @@ struct DDComm {
     // in-place all-reduce: max for DD_I32 flags (is_max) or sum
     virtual void allreduce(int rank, void* buf, size_t count, DDType type, bool is_max, cudaStream_t s) = 0;
     virtual const char* kind() const = 0;
+    // peer memory (NVLink/NVSwitch P2P): map the device allocation `base` of the two ring neighbours into this rank's
+    // address space, so that kernels here can store straight into it.  Collective.  false = not available with this
+    // transport (the caller keeps using ring_exchange).  peer_unmap releases what peer_map opened.
+    virtual bool peer_map(int rank, void* base, void** lo_base, void** hi_base, cudaStream_t s) { (void)rank; (void)base; (void)lo_base; (void)hi_base; (void)s; return false; }
+    virtual void peer_unmap(int rank) { (void)rank; }
 };
 
 #define OCM_CUDA_OK(expr)                                                                                          \
@@ -90,7 +96,7 @@ struct NcclComm : DDComm {
         OCM_CUDA_OK(cudaSetDevice(device));
         A.ok(A.CommInitRank(&comm, world, id, rank), "ncclCommInitRank");
     }
-    ~NcclComm() override { if (comm) NcclApi::get().CommDestroy(comm); }
+    ~NcclComm() override { peer_unmap(rank); if (stage) cudaFree(stage); if (comm) NcclApi::get().CommDestroy(comm); }
     const char* kind() const override { return "nccl"; }
     void ring_exchange(int r, const void* send_lo, const void* send_hi, void* recv_lo, void* recv_hi, size_t bytes, cudaStream_t s) override {
         NcclApi& A = NcclApi::get();
@@ -108,6 +114,46 @@ struct NcclComm : DDComm {
         NcclApi& A = NcclApi::get();
         const ncclDataType_t t = type == DD_I32 ? ncclInt32 : type == DD_I64 ? ncclInt64 : type == DD_F32 ? ncclFloat32 : ncclFloat64;
         A.ok(A.AllReduce(buf, buf, count, t, is_max ? ncclMax : ncclSum, comm, s), "ncclAllReduce");
+    }
+
+    // CUDA IPC: every rank exports its allocation, the 64-byte handles travel round the ring over NCCL, each rank opens
+    // its two neighbours' handles (one process per GPU on one node: NVLink peer access)
+    void* opened[2] = {nullptr, nullptr};
+    char* stage = nullptr;  // device: [my handle | from prev | from next], 64 bytes each
+    bool peer_map(int r, void* base, void** lo_base, void** hi_base, cudaStream_t s) override {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+        peer_unmap(r);
+        cudaIpcMemHandle_t mine, from_prev, from_next;
+        int ok = cudaIpcGetMemHandle(&mine, base) == cudaSuccess ? 1 : 0;
+        if (!ok) { cudaGetLastError(); std::memset(&mine, 0, sizeof(mine)); }
+        if (!stage) OCM_CUDA_OK(cudaMalloc(&stage, 4 * 64));
+        OCM_CUDA_OK(cudaMemcpyAsync(stage, &mine, 64, cudaMemcpyHostToDevice, s));
+        ring_exchange(r, stage, stage, stage + 64, stage + 128, 64, s);
+        // everybody must have exported successfully, or nobody maps
+        int* flag = reinterpret_cast<int*>(stage + 192);
+        OCM_CUDA_OK(cudaMemcpyAsync(flag, &ok, sizeof(int), cudaMemcpyHostToDevice, s));
+        NcclApi::get().ok(NcclApi::get().AllReduce(flag, flag, 1, ncclInt32, ncclMin, comm, s), "ncclAllReduce");
+        OCM_CUDA_OK(cudaMemcpyAsync(&from_prev, stage + 64, 64, cudaMemcpyDeviceToHost, s));
+        OCM_CUDA_OK(cudaMemcpyAsync(&from_next, stage + 128, 64, cudaMemcpyDeviceToHost, s));
+        OCM_CUDA_OK(cudaMemcpyAsync(&ok, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+        OCM_CUDA_OK(cudaStreamSynchronize(s));
+        if (!ok) return false;
+        const int prev = (r + world - 1) % world, next = (r + 1) % world;
+        int opened_ok = 1;
+        if (cudaIpcOpenMemHandle(&opened[0], from_prev, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened[0] = nullptr; opened_ok = 0; }
+        if (prev == next) opened[1] = nullptr;  // the same allocation: opened once
+        else if (cudaIpcOpenMemHandle(&opened[1], from_next, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened[1] = nullptr; opened_ok = 0; }
+        OCM_CUDA_OK(cudaMemcpyAsync(flag, &opened_ok, sizeof(int), cudaMemcpyHostToDevice, s));
+        NcclApi::get().ok(NcclApi::get().AllReduce(flag, flag, 1, ncclInt32, ncclMin, comm, s), "ncclAllReduce");
+        OCM_CUDA_OK(cudaMemcpyAsync(&opened_ok, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+        OCM_CUDA_OK(cudaStreamSynchronize(s));
+        if (!opened_ok) { peer_unmap(r); return false; }
+        *lo_base = opened[0];
+        *hi_base = prev == next ? opened[0] : opened[1];
+        return true;
+    }
+    void peer_unmap(int) override {
+        for (void*& q : opened) { if (q) cudaIpcCloseMemHandle(q); q = nullptr; }
     }
 };
 

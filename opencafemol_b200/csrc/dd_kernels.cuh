@@ -140,6 +140,30 @@ __global__ void dd_pack_kernel(const int* __restrict__ cnt_lo, const int* __rest
     if (p < nhi) { const int i = idx_hi[p]; out_hi[3 * p] = x[3 * i]; out_hi[3 * p + 1] = x[3 * i + 1]; out_hi[3 * p + 2] = x[3 * i + 2]; }
 }
 
+// per MD step over peer memory: the positions go straight into the neighbours' receive buffers (NVLink stores); the
+// last block to finish publishes the step's sequence number in both neighbours' flags (release at system scope), on
+// which their streams wait (cuStreamWaitValue32) before they unpack.  No staging copy, no collective call.
+__global__ void dd_push_kernel(const int* __restrict__ cnt_lo, const int* __restrict__ idx_lo, double* __restrict__ out_lo,
+                               const int* __restrict__ cnt_hi, const int* __restrict__ idx_hi, double* __restrict__ out_hi,
+                               int cap, const double* __restrict__ x, unsigned int* flag_lo, unsigned int* flag_hi,
+                               unsigned int seq, unsigned int* __restrict__ ticket) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nlo = min(*cnt_lo, cap), nhi = min(*cnt_hi, cap);
+    if (p < nlo) { const int i = idx_lo[p]; out_lo[3 * p] = x[3 * i]; out_lo[3 * p + 1] = x[3 * i + 1]; out_lo[3 * p + 2] = x[3 * i + 2]; }
+    if (p < nhi) { const int i = idx_hi[p]; out_hi[3 * p] = x[3 * i]; out_hi[3 * p + 1] = x[3 * i + 1]; out_hi[3 * p + 2] = x[3 * i + 2]; }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *ticket = 0u;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_lo), "r"(seq) : "memory");
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_hi), "r"(seq) : "memory");
+        }
+    }
+}
+
 __global__ void dd_unpack_kernel(const int* __restrict__ cnt_lo, const int* __restrict__ idx_lo, const double* __restrict__ in_lo,
                                  const int* __restrict__ cnt_hi, const int* __restrict__ idx_hi, const double* __restrict__ in_hi,
                                  int cap, StepParams P, double* __restrict__ x, uint4* __restrict__ posq,

@@ -126,6 +126,7 @@ struct StepParams {
     const double* origin;       // [3*nrep] or null (single system, origin 0)
     const uint2* rep_seed;      // [nrep] or null
     const unsigned char* role;  // slab decomposition: 0 = not on this rank, 1 = owned, 2 = halo; null = single domain
+    int pdl_early;              // programmatic dependent launch: release the successor's launch at block start
 };
 
 // rows (ranks of the cell-sorted order) in use: under a slab decomposition only the beads present on this rank are binned
@@ -191,6 +192,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int 
             "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
+
+// programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// begin while its predecessor drains; it must not touch the predecessor's output before pdl_wait().  pdl_trigger() lets
+// the successor's launch start as soon as every block of this grid has begun.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ int enc_float(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
 __device__ __forceinline__ float dec_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
@@ -843,16 +850,18 @@ __device__ __forceinline__ void pair_tz_rows_warp(const PairListDev& L, int k_lo
             }
         }
         if (n == 0) {
+            // empty row (a halo bead of a slab decomposition, or a bead without partners): nothing to reduce or add
 #pragma unroll
             for (int u = 0; u < 4; u++) en[u] = (u * 32 < n_next) ? __ldg(row_next + u * 32) : 0u;
-        }
+        } else {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            fx += __shfl_xor_sync(0xffffffffu, fx, o);
-            fy += __shfl_xor_sync(0xffffffffu, fy, o);
-            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+            for (int o = 16; o > 0; o >>= 1) {
+                fx += __shfl_xor_sync(0xffffffffu, fx, o);
+                fy += __shfl_xor_sync(0xffffffffu, fy, o);
+                fz += __shfl_xor_sync(0xffffffffu, fz, o);
+            }
+            if (lane == 0) add_force_fixed(fbuf, P.n, (int)(pi.w & 0xFFFFFFu), fx, fy, fz);
         }
-        if (lane == 0) add_force_fixed(fbuf, P.n, (int)(pi.w & 0xFFFFFFu), fx, fy, fz);
         n = n_next;
         n_in = n_in_next;
         row = row_next;
@@ -1327,6 +1336,8 @@ __global__ void __launch_bounds__(kBlock, OCM_FORCE_MINBLOCKS) force_kernel(cons
                                                        const BondedDev* __restrict__ bonded, StepParams P,
                                                        const double* __restrict__ x, unsigned long long* __restrict__ fbuf) {
     extern __shared__ __align__(16) float smem[];
+    if (P.pdl_early) pdl_trigger();
+    pdl_wait();
     int s = 0;
     while (s + 1 < nsegs && (int)blockIdx.x >= segs[s + 1].block_begin) s++;
     const WorkSeg sg = segs[s];
@@ -1412,6 +1423,8 @@ __global__ void integrate_kernel(StepParams P, double* __restrict__ x, float4* _
                                  const PairListDev* __restrict__ lists, int nlists,
                                  const double* __restrict__ xref, unsigned long long* __restrict__ step_base,
                                  int step_offset, int window, int last_in_window, int* __restrict__ flags) {
+    if (P.pdl_early) pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long step = *step_base + (unsigned long long)step_offset;
     float d2 = 0.f;

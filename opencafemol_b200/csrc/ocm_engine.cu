@@ -103,6 +103,15 @@ struct DDState {
     DevBuf<double> gx; DevBuf<float> gv; DevBuf<long long> gf;  // state gather
     std::vector<int> rows_est;                    // per pair list: rows in use at the last sizing pass
     double n_exchanges = 0;
+    // per-step halo over peer memory (dd_push_kernel): [4 flags x 128 B][side 0/1][parity 0/1][cap x 3 doubles]
+    DevBuf<char> push;
+    DevBuf<unsigned int> ticket;
+    char* peer_lo = nullptr; char* peer_hi = nullptr;  // the neighbours' push buffers, mapped here
+    bool push_ok = false, push_wanted = true;
+    unsigned int seq = 0;
+    size_t push_flag_off(int side, int parity) const { return (size_t)(side * 2 + parity) * 128; }
+    size_t push_data_off(int side, int parity) const { return 512 + (size_t)(side * 2 + parity) * bytes_s(); }
+    size_t bytes_push() const { return 512 + 4 * bytes_s(); }
     size_t bytes_a() const { return 16 + (size_t)cap * (4 + 24 + 16); }
     size_t bytes_b() const { return 16 + (size_t)cap * 4; }
     size_t bytes_s() const { return (size_t)cap * 24; }
@@ -169,6 +178,13 @@ struct ocm_context {
     // options
     double skin = 0.3;
     int nstlist_fixed = 0;   // 0 = adaptive
+    // optional phase timing (option "phase_timing"): events between the phases of directly launched windows
+    bool phase_timing = false;
+    bool pdl = false;        // programmatic dependent launch of the per-step kernels (option "pdl")
+    std::vector<cudaEvent_t> ph_ev;
+    std::vector<int> ph_tag;
+    size_t ph_used = 0;
+    double ph_ms[4] = {0, 0, 0, 0};  // rebuild, force, integrate, halo exchange
     int nst = 10;
     int tpb_opt = 0;         // 0 = auto
     int chunk_opt = 0;       // beads per block of the pair kernels, 0 = auto
@@ -643,9 +659,28 @@ static void dd_configure(ocm_context* c) {
     d.G.halo_fix = (unsigned int)std::ceil(h / len * two32) + 2u;
 }
 
+// cuStreamWaitValue32 through the runtime's driver entry point (the engine links only the CUDA runtime)
+typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static StreamWaitValue32Fn stream_wait_value32() {
+    static StreamWaitValue32Fn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); f = nullptr; }
+        return (StreamWaitValue32Fn)f;
+    }();
+    return fn;
+}
+
 static void dd_alloc(ocm_context* c, int cap) {
     DDState& d = *c->dd;
     cap = (cap + 255) / 256 * 256;
+    // neighbours still map the old push buffer: unmap everywhere before anybody frees (collective)
+    if (d.push_ok) {
+        d.comm->peer_unmap(d.rank);
+        d.comm->allreduce(d.rank, c->flags.p + FLAG_COUNT, 1, DD_I32, true, c->stream);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        d.push_ok = false;
+    }
     d.cap = cap;
     for (int k = 0; k < 2; k++) {
         d.a_send[k].alloc(d.bytes_a()); d.a_recv[k].alloc(d.bytes_a());
@@ -653,7 +688,15 @@ static void dd_alloc(ocm_context* c, int cap) {
         d.s_send[k].alloc((size_t)3 * cap); d.s_recv[k].alloc((size_t)3 * cap);
         d.a_send[k].zero(); d.a_recv[k].zero(); d.b_send[k].zero(); d.b_recv[k].zero(); d.s_send[k].zero(); d.s_recv[k].zero();
     }
+    d.push.alloc(d.bytes_push());
+    d.push.zero();
+    if (!d.ticket.p) { d.ticket.alloc(1); d.ticket.zero(); }
     CUDA_TRY(cudaDeviceSynchronize());
+    if (d.push_wanted && stream_wait_value32()) {
+        void *lo = nullptr, *hi = nullptr;
+        d.push_ok = d.comm->peer_map(d.rank, d.push.p, &lo, &hi, c->stream);
+        d.peer_lo = (char*)lo; d.peer_hi = (char*)hi;
+    }
 }
 
 // rebuild-time exchange: migration + halo state (phase A), per-step halo lists (phase B)
@@ -686,6 +729,24 @@ static void dd_halo_step(ocm_context* c, cudaStream_t s) {
     const int cap = d.cap;
     auto cnt = [](DevBuf<char>& b) { return reinterpret_cast<int*>(b.p); };
     auto idx = [](DevBuf<char>& b) { return reinterpret_cast<int*>(b.p + 16); };
+    if (d.push_ok) {
+        // peer-memory path: my low-side list lands in the previous rank's "from the high side" buffer and vice versa;
+        // two parities so that a neighbour one step ahead never overwrites what is still being unpacked here
+        const unsigned int seq = ++d.seq;
+        const int par = (int)(seq & 1u);
+        dd_push_kernel<<<nblk(cap, 256), 256, 0, s>>>(cnt(d.b_send[0]), idx(d.b_send[0]), reinterpret_cast<double*>(d.peer_lo + d.push_data_off(1, par)),
+                                                      cnt(d.b_send[1]), idx(d.b_send[1]), reinterpret_cast<double*>(d.peer_hi + d.push_data_off(0, par)), cap, c->x.p,
+                                                      reinterpret_cast<unsigned int*>(d.peer_lo + d.push_flag_off(1, par)),
+                                                      reinterpret_cast<unsigned int*>(d.peer_hi + d.push_flag_off(0, par)), seq, d.ticket.p);
+        for (int side = 0; side < 2; side++)
+            if (stream_wait_value32()(s, (unsigned long long)(uintptr_t)(d.push.p + d.push_flag_off(side, par)), seq, 0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
+                throw std::runtime_error("slab decomposition: cuStreamWaitValue32 failed");
+        dd_unpack_kernel<<<nblk(cap, 256), 256, 0, s>>>(cnt(d.b_recv[0]), idx(d.b_recv[0]), reinterpret_cast<const double*>(d.push.p + d.push_data_off(0, par)),
+                                                        cnt(d.b_recv[1]), idx(d.b_recv[1]), reinterpret_cast<const double*>(d.push.p + d.push_data_off(1, par)), cap, c->P,
+                                                        c->x.p, c->posq.p, c->d_lists.p, (int)c->lists.size());
+        c->n_launches += 2; d.n_exchanges += 1;
+        return;
+    }
     dd_pack_kernel<<<nblk(cap, 256), 256, 0, s>>>(cnt(d.b_send[0]), idx(d.b_send[0]), d.s_send[0].p, cnt(d.b_send[1]), idx(d.b_send[1]),
                                                   d.s_send[1].p, cap, c->x.p);
     d.comm->ring_exchange(d.rank, d.s_send[0].p, d.s_send[1].p, d.s_recv[0].p, d.s_recv[1].p, d.bytes_s(), s);
@@ -745,6 +806,19 @@ static void enqueue_rebuild(ocm_context* c, cudaStream_t s, bool count_only) {
     }
 }
 
+// launch with the programmatic-stream-serialization attribute (option "pdl"): the grid may be scheduled while the
+// previous kernel of the stream drains; force_kernel and integrate_kernel wait (griddepcontrol.wait) before they read
+template <class... KArgs, class... Args>
+static void launch_chained(ocm_context* c, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = c->pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
 static void enqueue_forces(ocm_context* c, cudaStream_t s) {
     if (c->total_blocks == 0) return;
     const bool fork = c->local_blocks > 0 && c->pair_blocks > 0;
@@ -760,8 +834,9 @@ static void enqueue_forces(ocm_context* c, cudaStream_t s) {
         c->n_launches += 1;
     }
     if (c->pair_blocks > 0) {
-        if (c->periodic) force_kernel<true><<<c->pair_blocks, kBlock, c->smem_bytes, s>>>(c->d_segs.p, c->n_pair_segs, c->d_lists.p, c->d_bonded.p, c->P, c->x.p, c->fbuf.p);
-        else force_kernel<false><<<c->pair_blocks, kBlock, c->smem_bytes, s>>>(c->d_segs.p, c->n_pair_segs, c->d_lists.p, c->d_bonded.p, c->P, c->x.p, c->fbuf.p);
+        // (not chained when the donor-acceptor kernel runs on the forked side stream: the join is an event wait)
+        if (c->periodic) launch_chained(c, force_kernel<true>, c->pair_blocks, kBlock, c->smem_bytes, s, c->d_segs.p, c->n_pair_segs, c->d_lists.p, c->d_bonded.p, c->P, c->x.p, c->fbuf.p);
+        else launch_chained(c, force_kernel<false>, c->pair_blocks, kBlock, c->smem_bytes, s, c->d_segs.p, c->n_pair_segs, c->d_lists.p, c->d_bonded.p, c->P, c->x.p, c->fbuf.p);
         c->n_launches += 1;
     }
     if (fork) CUDA_TRY(cudaStreamWaitEvent(s, c->ev_join, 0));
@@ -869,15 +944,40 @@ static void ensure_lists_current(ocm_context* c) {
     throw std::runtime_error("neighbour list keeps overflowing");
 }
 
+static void phase_mark(ocm_context* c, cudaStream_t s, int tag) {
+    if (!c->phase_timing) return;
+    if (c->ph_used == c->ph_ev.size()) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        c->ph_ev.push_back(e);
+        c->ph_tag.push_back(0);
+    }
+    c->ph_tag[c->ph_used] = tag;
+    CUDA_TRY(cudaEventRecord(c->ph_ev[c->ph_used++], s));
+}
+static void phase_collect(ocm_context* c) {
+    for (size_t i = 1; i < c->ph_used; i++) {
+        if (c->ph_tag[i] < 0) continue;  // start of a window
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, c->ph_ev[i - 1], c->ph_ev[i]));
+        c->ph_ms[c->ph_tag[i]] += ms;
+    }
+    c->ph_used = 0;
+}
+
 // one window: rebuild, then nst x [forces, integrate (+ halo positions to the neighbouring slabs)]
 static void enqueue_window(ocm_context* c, cudaStream_t s, int nst) {
+    phase_mark(c, s, -1);
     enqueue_rebuild(c, s, false);
+    phase_mark(c, s, 0);
     for (int k = 0; k < nst; k++) {
         enqueue_forces(c, s);
-        integrate_kernel<<<nblk(c->n, 128), 128, 0, s>>>(c->P, c->x.p, c->v.p, c->fbuf.p, c->posq.p, c->d_lists.p, (int)c->lists.size(), c->xref.p,
-                                                         c->step_base.p, k, nst, k == nst - 1 ? 1 : 0, c->flags.p);
+        phase_mark(c, s, 1);
+        launch_chained(c, integrate_kernel, nblk(c->n, 128), 128, 0, s, c->P, c->x.p, c->v.p, c->fbuf.p, c->posq.p, c->d_lists.p, (int)c->lists.size(), c->xref.p,
+                       c->step_base.p, k, nst, k == nst - 1 ? 1 : 0, c->flags.p);
+        phase_mark(c, s, 2);
         // the next window starts with a full halo refresh, so the last step of a window ships nothing
-        if (c->dd && k < nst - 1) dd_halo_step(c, s);
+        if (c->dd && k < nst - 1) { dd_halo_step(c, s); phase_mark(c, s, 3); }
     }
 }
 
@@ -948,8 +1048,8 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
         const int nst = c->nst;
         while (done + batch < nsteps && windows < 16) {
             int w = (int)std::min<int64_t>(nst, nsteps - done - batch);
-            if (c->dd) {
-                // slab decomposition: direct launches (the exchanges are host-ordered across ranks)
+            if (c->dd || c->phase_timing) {
+                // slab decomposition: direct launches (the exchanges are host-ordered across ranks); also when phases are timed
                 const double l0 = c->n_launches, r0 = c->n_rebuilds;
                 enqueue_window(c, s, w);
                 c->n_launches = l0; c->n_rebuilds = r0;
@@ -959,6 +1059,7 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
         }
         int fl[FLAG_COUNT];
         read_flags(c, fl);
+        if (c->phase_timing) phase_collect(c);
         if (fl[FLAG_NAN]) throw std::runtime_error("particle coordinate or force is NaN");
         if (fl[FLAG_VIOLATION] || fl[FLAG_OVERFLOW] || fl[FLAG_DA_OVERFLOW] || fl[FLAG_DD_OVERFLOW]) {
             // roll back and replay the batch with a safer configuration
@@ -1243,7 +1344,7 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
     const int n = c->n;
     c->x.alloc(3 * (size_t)n); c->xref.alloc(3 * (size_t)n); c->xbak.alloc(3 * (size_t)n);
     c->v.alloc(n); c->vbak.alloc(n); c->posq.alloc(n); c->fbuf.alloc(3 * (size_t)n);
-    c->flags.alloc(FLAG_COUNT); c->step_base.alloc(1); c->egroup.alloc((size_t)40 * nrep); c->pair_counter.alloc(1);
+    c->flags.alloc(FLAG_COUNT + 4); /* + scratch words for barriers */ c->step_base.alloc(1); c->egroup.alloc((size_t)40 * nrep); c->pair_counter.alloc(1);
     c->x.zero(); c->xref.zero(); c->fbuf.zero(); c->flags.zero(); c->step_base.zero(); c->posq.zero();
     if (nrep > 1) {
         c->origin.alloc((size_t)3 * nrep); c->origin.zero();
@@ -1353,6 +1454,16 @@ void ocm_context_destroy(ocm_context* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (c->dd && c->dd->push_ok) {
+        // neighbours map this rank's push buffer: everybody unmaps before anybody frees (slab contexts are destroyed
+        // collectively, like every other call on them)
+        try {
+            c->dd->comm->peer_unmap(c->dd->rank);
+            c->dd->comm->allreduce(c->dd->rank, c->flags.p + FLAG_COUNT, 1, DD_I32, true, c->stream);
+            cudaStreamSynchronize(c->stream);
+        } catch (...) {
+        }
+    }
     delete c;
 }
 
@@ -1376,6 +1487,20 @@ int ocm_context_set_option(ocm_context* c, const char* key, double value) {
         for (auto& L : c->lists) L->stride = 0;
         drop_graphs(c);
         if (c->nstlist_fixed <= 0) c->nst = initial_nst(c);
+    } else if (k == "pdl") {
+        // 0 = plain launches, 1 = chained launches (successor released when the grid ends), 2 = released at block start
+        c->pdl = value != 0;
+        c->P.pdl_early = value >= 2 ? 1 : 0;
+        drop_graphs(c);
+    } else if (k == "phase_timing") {
+        c->phase_timing = value != 0;
+        for (double& v : c->ph_ms) v = 0;
+    } else if (k == "halo_push") {
+        // per-step halo over peer memory (1, default where the transport can map neighbours) or NCCL send/recv (0); collective
+        if (!c->dd) return fail("halo_push: not a slab context");
+        c->dd->push_wanted = value != 0;
+        if (c->dd->cap > 0) dd_alloc(c, c->dd->cap);
+        c->lists_current = false;
     } else if (k == "halo_capacity") {
         // entries per halo message of a slab decomposition (grown automatically on overflow)
         if (!c->dd) return fail("halo_capacity: not a slab context");
@@ -1671,12 +1796,17 @@ int ocm_get_counter(ocm_context* c, const char* key, double* value) {
     std::string k(key);
     if (k == "rebuilds") *value = c->n_rebuilds;
     else if (k == "minimize_evaluations") *value = c->counters_minimize_evals;
+    else if (k == "phase_ms.rebuild") *value = c->ph_ms[0];
+    else if (k == "phase_ms.force") *value = c->ph_ms[1];
+    else if (k == "phase_ms.integrate") *value = c->ph_ms[2];
+    else if (k == "phase_ms.halo") *value = c->ph_ms[3];
     else if (k == "rollbacks") *value = c->n_rollbacks;
     else if (k == "kernel_launches") *value = c->n_launches;
     else if (k == "nstlist") *value = c->nst;
     else if (k == "last_step_ms") *value = c->last_step_ms;
     else if (k == "num_pair_lists") *value = (double)c->lists.size();
     else if (k == "halo_exchanges") *value = c->dd ? c->dd->n_exchanges : 0.0;
+    else if (k == "halo_push") *value = (c->dd && c->dd->push_ok) ? 1.0 : 0.0;
     else if (k == "halo_message_bytes") *value = c->dd ? (double)c->dd->bytes_s() : 0.0;
     else if (k == "owned_beads") {
         if (!c->dd) *value = c->n;

@@ -188,6 +188,11 @@ def main():
                         p["pos"] = [float(v) for v in xyz]
                     d["systems"][0]["vel_seed"] = 2026  # the sample has neither velocities nor a seed: make the run reproducible
                     text_run = dump_toml(d)
+                elif spec.velocities is None:
+                    # neither velocities nor a velocity seed in the sample: make the program run reproducible
+                    d = tomllib.loads(text)
+                    d["systems"][0]["vel_seed"] = 2026
+                    text_run = dump_toml(d)
                 else:
                     text_run = text
                 got, used = run_program(text_run, wd, fmt)

@@ -42,6 +42,8 @@ def main():
     ap.add_argument("--axis", type=int, default=1)
     ap.add_argument("--nstlist", type=int, default=0)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--halo", choices=["push", "nccl"], default="push", help="per-step halo: peer-memory push kernel or NCCL send/recv")
+    ap.add_argument("--phases", action="store_true", help="time the phases of a step with CUDA events (engine option phase_timing)")
     args = ap.parse_args()
 
     import torch
@@ -65,7 +67,11 @@ def main():
     ctx = ti.make_context(lib, spec, device=local, comm=comm, rank=rank, axis=args.axis)
     if args.nstlist:
         ctx.set_option("nstlist", args.nstlist)
+    if world > 1 and args.halo == "nccl":
+        ctx.set_option("halo_push", 0)
     ctx.step(args.warmup)
+    if args.phases:
+        ctx.set_option("phase_timing", 1)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -100,7 +106,10 @@ def main():
             "n_gpus": world, "beads": int(spec.mass.size), "md_steps": args.steps, "device_s": dev_s, "wall_s": wall_s,
             "md_steps_per_s": args.steps / dev_s, "ns_per_day": args.steps * spec.dt * 1e-3 / dev_s * 86400.0,
             "nstlist": ctx.counter("nstlist"), "rollbacks": ctx.counter("rollbacks"), "owned": [int(o.item()) for o in owned_all],
-            "halo_message_bytes": ctx.counter("halo_message_bytes"), "transport": "nccl" if world > 1 else "none", "check": ok}))
+            "halo_message_bytes": ctx.counter("halo_message_bytes"),
+            "phase_ms_per_step": {k: ctx.counter("phase_ms." + k) / args.steps for k in ("rebuild", "force", "integrate", "halo")} if args.phases else None,
+            "transport": "nccl" if world > 1 else "none",
+            "halo": ("peer-memory push" if ctx.counter("halo_push") else "nccl send/recv") if world > 1 else None, "check": ok}))
     if world > 1:
         dist.barrier()
         ctx.close()

@@ -48,6 +48,7 @@ struct PairListDev {
     const int* excl_idx;        // excluded partner bead ids, ascending per slot
     GridDev* grid;
     int max_cells;
+    int row_capacity;           // rows covered by the force launch (slab decomposition: below np)
     float wmin;                 // minimum cell width = (rc_list + skin)/2
     int* cell_of_slot;          // [np]
     int* cell_count;            // [max_cells+1]
@@ -423,6 +424,7 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
     const PairListDev& L = lists[li];
     const int lane = threadIdx.x & 31;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w == 0 && lane == 0 && !count_only && list_rows(L) > L.row_capacity) flags[FLAG_OVERFLOW] = 1;
     if (w >= list_rows(L)) return;
     const GridDev& g = *L.grid;
     const uint4* __restrict__ spos = L.spos;
@@ -1345,6 +1347,8 @@ __global__ void __launch_bounds__(kBlock, OCM_FORCE_MINBLOCKS) force_kernel(cons
     if (sg.kind == SEG_PAIR_TZ) {
         const PairListDev& L = lists[sg.id];
         if (sg.staged) { pair_tz_block_staged<PER>(L, blk, sg.chunk, P, fbuf, smem); return; }
+        // (under a slab decomposition the grid covers L.row_capacity rows, the rows in use at the last sizing pass plus
+        // head-room; build_list_kernel raises the overflow flag, i.e. a re-sizing pass, if more rows ever exist)
         switch (sg.tpb) {
             case 4: pair_tz_block<PER, 4>(L, blk, sg.chunk, P, fbuf, smem); break;
             case 8: pair_tz_block<PER, 8>(L, blk, sg.chunk, P, fbuf, smem); break;
@@ -1428,14 +1432,18 @@ __global__ void integrate_kernel(StepParams P, double* __restrict__ x, float4* _
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long step = *step_base + (unsigned long long)step_offset;
     float d2 = 0.f;
-    if (i < P.n) {
+    // slab decomposition: beads that are not on this rank cost one byte; halo beads only have their accumulator cleared
+    // (bonded terms evaluated here add to it); owned beads move
+    const int role_i = (i < P.n && P.role) ? (int)P.role[i] : 1;
+    if (i < P.n && role_i == 2) { fbuf[i] = 0ull; fbuf[P.n + i] = 0ull; fbuf[2 * P.n + i] = 0ull; }
+    if (i < P.n && role_i == 1) {
         const int n = P.n;
         const float inv32 = 2.3283064365386963e-10f;
         const float fx = (float)(long long)fbuf[i] * inv32, fy = (float)(long long)fbuf[n + i] * inv32,
                     fz = (float)(long long)fbuf[2 * n + i] * inv32;
         fbuf[i] = 0ull; fbuf[n + i] = 0ull; fbuf[2 * n + i] = 0ull;
         float4 vi = v[i];
-        const float im = (P.role && P.role[i] != 1) ? 0.f : vi.w;  // slab decomposition: only owned beads move here
+        const float im = vi.w;
         if (im > 0.f) {
             float g0, g1, g2;
             const int rep = (P.nrep > 1) ? i / P.nper : 0;

@@ -489,11 +489,14 @@ static void build_segments(ocm_context* c) {
         const int rows = (c->dd && l < c->dd->rows_est.size() && c->dd->rows_est[l] > 0) ? std::min(L.np, c->dd->rows_est[l]) : L.np;
         int chunk = c->chunk_opt > 0 ? c->chunk_opt : (rows + 148 * 16 - 1) / (148 * 16);
         chunk = std::max(gpb, (chunk + gpb - 1) / gpb * gpb);
-        int nb = (L.np + chunk - 1) / chunk;
+        // (slab decomposition: 25 % head-room over the rows in use at the sizing pass; more rows than that raise the
+        // overflow flag in build_list_kernel and the lists are sized again)
+        int nb = ((c->dd ? std::min(L.np, (int)(1.25 * rows) + chunk) : L.np) + chunk - 1) / chunk;
+        L.dev.row_capacity = c->dd ? std::min(L.np, nb * chunk) : L.np;
         // T = 32 two-zone lists stage their rows in shared memory (bulk async copies) when two rows per warp fit
         const size_t tab_bytes = (size_t)L.ntypes * L.ntypes * 16;
         const size_t staged_bytes = 64 + tab_bytes + (size_t)(kBlock / 32) * 2 * L.stride * sizeof(unsigned int);
-        const int staged = (c->staging_opt && L.form == SEG_PAIR_TZ && L.tpb == 32 && L.dev.smem_tab && staged_bytes <= 56 * 1024) ? 1 : 0;
+        const int staged = (c->staging_opt && !c->dd && L.form == SEG_PAIR_TZ && L.tpb == 32 && L.dev.smem_tab && staged_bytes <= 56 * 1024) ? 1 : 0;
         c->segs.push_back({blk, nb, L.form, (int)l, L.tpb, chunk, staged});
         blk += nb;
         if (staged) smem = std::max(smem, staged_bytes);
@@ -917,8 +920,8 @@ static void size_lists(ocm_context* c, double growth) {
         }
     }
     CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, FLAG_COUNT * sizeof(int), s));
-    upload_lists(c);
     build_segments(c);
+    upload_lists(c);  // after build_segments: it sets row_capacity
     c->lists_ready = true;
     c->lists_current = false;
 }

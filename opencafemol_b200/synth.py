@@ -139,3 +139,60 @@ def hps_slab(n_chains=100, tile=(1, 1), seq=FUS_LC, temperature=300.0, ionic_str
                        dict(K=K, debye=debye, rc=rc_dh, cutoff_correction=cc, charge=qq,
                             topo=PairTopology(excl=within(3), igroups=[(charged, charged)], periodic=True))))
     return spec
+
+
+def replicate(spec, shifts_nm):
+    """`len(shifts_nm)` copies of an unlimited-boundary system side by side in one system (config C3: the
+    nucleosome sample on a 2 x 3 grid).  Bead indices of copy c are offset by c*N, positions shifted by
+    shifts_nm[c]; per-term and per-bead tables are tiled; exclusions, donor/acceptor tables and interaction-group
+    sets are offset per copy (sets become the union over copies, so copies interact like any other beads)."""
+    import copy as _copy
+
+    from .capi import DATopology, PairTopology
+    from .toml_input import SystemSpec, Term
+
+    shifts = np.asarray(shifts_nm, float).reshape(-1, 3)
+    m, n = shifts.shape[0], spec.mass.size
+    assert spec.box is None, "replicate() is for unlimited-boundary systems"
+    out = SystemSpec(mass=np.tile(spec.mass, m), box=None,
+                     positions=np.concatenate([spec.positions + s for s in shifts]),
+                     velocities=None if spec.velocities is None else np.tile(spec.velocities, (m, 1)),
+                     names=list(spec.names) * m, groups=list(spec.groups) * m)
+    for k in ("temperature", "friction", "dt", "seed", "vel_seed", "total_step", "save_step", "delta_t_raw", "energy_minimization", "periodic"):
+        setattr(out, k, getattr(spec, k))
+    out.group_ids = dict(spec.group_ids)
+    index_keys = {"ij": 2, "ijk": 3, "ijkl": 4}
+    for t in spec.terms:
+        a = {}
+        nterm = None
+        for key, w in index_keys.items():
+            if key in t.args:
+                nterm = np.asarray(t.args[key]).reshape(-1, w).shape[0]
+        topo = t.args.get("topo")
+        nd = na = None
+        if isinstance(topo, DATopology):
+            nd, na = np.asarray(topo.donors).reshape(-1, 3).shape[0], np.asarray(topo.acceptors).reshape(-1, 3).shape[0]
+        for key, v in t.args.items():
+            if key in index_keys:
+                idx = np.asarray(v, np.int64).reshape(-1, index_keys[key])
+                a[key] = np.concatenate([idx + c * n for c in range(m)])
+            elif isinstance(v, PairTopology):
+                ex = np.asarray(v.excl, np.int64).reshape(-1, 2)
+                a[key] = PairTopology(excl=np.concatenate([ex + c * n for c in range(m)]).astype(np.int32),
+                                      igroups=[(np.concatenate([np.asarray(s1, np.int64) + c * n for c in range(m)]),
+                                                np.concatenate([np.asarray(s2, np.int64) + c * n for c in range(m)])) for s1, s2 in v.igroups],
+                                      periodic=v.periodic)
+            elif isinstance(v, DATopology):
+                def off(sites):
+                    sites = np.asarray(sites, np.int64).reshape(-1, 3)
+                    return np.concatenate([np.where(sites >= 0, sites + c * n, -1) for c in range(m)]).astype(np.int32)
+                ex = np.asarray(v.excl, np.int64).reshape(-1, 2)
+                a[key] = DATopology(donors=off(v.donors), acceptors=off(v.acceptors), cutoff=v.cutoff,
+                                    excl=np.concatenate([ex + np.array([c * nd, c * na]) for c in range(m)]).astype(np.int32), periodic=v.periodic)
+            elif isinstance(v, (list, np.ndarray)) and key not in ("y10", "coef7") and np.asarray(v).ndim == 1 and \
+                    np.asarray(v).size in {x for x in (nterm, n, nd, na) if x is not None}:
+                a[key] = np.tile(np.asarray(v), m)
+            else:
+                a[key] = _copy.deepcopy(v)
+        out.terms.append(Term(t.kind, t.name, a, t.group))
+    return out

@@ -243,10 +243,9 @@ def run_engine(args):
     h2d = 2 * n * 3 * 8
     d2h = 2 * n * 3 * 8 + 33 * 8
 
-    times = torch.tensor([t_dev, t_e2e, t_wall], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e, t_wall = times.tolist()
+    from opencafemol_b200 import sharding
+
+    t_dev, t_e2e, t_wall = sharding.max_over_ranks([t_dev, t_e2e, t_wall], device=f"cuda:{local}")
 
     if rank == 0:
         md = args.steps * MD_STEPS_PER_STEP

@@ -86,10 +86,12 @@ def main():
                  extra={"nstlist": ctx.counter("nstlist")})
             ctx.close()
         elif mode == "c4":
+            from opencafemol_b200 import sharding
+
             total = 512
-            per = total // world
+            first, per = sharding.replica_shard(total, world, rank)
             spec = load_golden_spec("sh3")
-            ctx = ti.make_context(lib, spec, device=local, seed=spec.seed + rank * per, replicas=per)
+            ctx = ti.make_context(lib, spec, device=local, seed=spec.seed + first, replicas=per)
             steps = 20000
             ctx.step(5000)
             if world > 1:

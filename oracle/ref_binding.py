@@ -51,17 +51,22 @@ class RefLibrary:
         L.ref_integrator.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ref_toml_to_json.argtypes = [C.c_char_p, C.c_char_p, C.c_long]
         L.ref_toml_to_json.restype = C.c_long
+        L.ref_toml11_to_json.argtypes = [C.c_char_p, C.c_char_p, C.c_long]
+        L.ref_toml11_to_json.restype = C.c_long
 
     def check(self, rc):
         if rc != 0:
             raise RefError(self.lib.ref_last_error().decode(errors="replace"))
 
-    def toml_to_json(self, path: str):
-        n = self.lib.ref_toml_to_json(path.encode(), None, 0)
+    def toml_to_json(self, path: str, reader="lite"):
+        """`path` parsed by this repository's TOML reader ("lite") or by the toml library the reference was compiled
+        with ("toml11": its own submodule when checked out), as a JSON-able object"""
+        fn = self.lib.ref_toml_to_json if reader == "lite" else self.lib.ref_toml11_to_json
+        n = fn(path.encode(), None, 0)
         if n < 0:
             raise RefError(self.lib.ref_last_error().decode(errors="replace"))
         buf = C.create_string_buffer(n)
-        self.lib.ref_toml_to_json(path.encode(), buf, n)
+        fn(path.encode(), buf, n)
         return json.loads(buf.value.decode())
 
     def open_toml(self, path: str) -> "RefSystem":

@@ -16,6 +16,7 @@
 #include <string>
 
 #include "openmm_lite_internal.h"
+#include "toml_lite.hpp"  // this repository's TOML reader (cross-checked below against the toml11 the reference uses)
 #include "src/IntegratorGenerator.hpp"
 #include "src/Simulator.hpp"
 #include "src/SystemGenerator.hpp"
@@ -208,11 +209,58 @@ int ref_integrator(void* hv, double* temperature, double* friction, double* dt, 
     });
 }
 
-// the repository's TOML reader alone: file -> JSON (cross-checked against Python's tomllib by the tests)
+// the repository's TOML reader alone: file -> JSON (cross-checked against Python's tomllib and against toml11)
 long ref_toml_to_json(const char* path, char* buf, long cap) {
     try {
         std::ostringstream os;
         tomllite::to_json(tomllite::parse_file(path), os);
+        const std::string s = os.str();
+        const long need = (long)s.size() + 1;
+        if (buf && cap >= need) std::memcpy(buf, s.c_str(), need);
+        return need;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// the same file through the toml library this build of the reference was compiled with (its own toml11 submodule when
+// that is checked out): toml::parse -> JSON
+static void toml11_json(const toml::value& v, std::ostream& os) {
+    if (v.is_boolean()) os << (v.as_boolean() ? "true" : "false");
+    else if (v.is_integer()) os << v.as_integer();
+    else if (v.is_floating()) {
+        const double d = v.as_floating();
+        if (std::isnan(d)) os << "\"nan\"";
+        else if (std::isinf(d)) os << (d > 0 ? "\"inf\"" : "\"-inf\"");
+        else { std::ostringstream t; t.precision(17); t << d; std::string q = t.str(); if (q.find_first_of(".en") == std::string::npos) q += ".0"; os << q; }
+    } else if (v.is_string()) {
+        os << '"';
+        for (unsigned char c : std::string(v.as_string())) {
+            if (c == '"' || c == '\\') os << '\\' << c;
+            else if (c < 0x20) { char b[8]; std::snprintf(b, sizeof b, "\\u%04x", c); os << b; }
+            else os << c;
+        }
+        os << '"';
+    } else if (v.is_array()) {
+        os << '[';
+        bool first = true;
+        for (const auto& e : v.as_array()) { if (!first) os << ','; first = false; toml11_json(e, os); }
+        os << ']';
+    } else if (v.is_table()) {
+        // sorted keys, as the other dumper writes them
+        std::map<std::string, const toml::value*> sorted;
+        for (const auto& kv : v.as_table()) sorted.emplace(kv.first, &kv.second);
+        os << '{';
+        bool first = true;
+        for (const auto& kv : sorted) { if (!first) os << ','; first = false; toml11_json(toml::value(kv.first), os); os << ':'; toml11_json(*kv.second, os); }
+        os << '}';
+    } else os << "null";
+}
+long ref_toml11_to_json(const char* path, char* buf, long cap) {
+    try {
+        std::ostringstream os;
+        toml11_json(toml::parse(std::string(path)), os);
         const std::string s = os.str();
         const long need = (long)s.size() + 1;
         if (buf && cap >= need) std::memcpy(buf, s.c_str(), need);

@@ -73,15 +73,42 @@ def test_host_layer_is_built(built):
     assert os.path.exists(COMPAT_SO), "libocm_openmm_compat.so missing: __graft_entry__.build() must produce it"
 
 
-@pytest.mark.skipif(not os.path.exists(BIN), reason="bin/open_cafemol_b200 is built where the reference tree is mounted")
-def test_frontend_fails_loudly_without_gpu(built, tmp_path):
+needs_frontend = pytest.mark.skipif(not os.path.exists(BIN), reason="bin/open_cafemol_b200 is built where the reference tree is mounted")
+
+
+@needs_frontend
+@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "fus10"])
+def test_frontend_translates_every_force_then_fails_loudly_without_gpu(built, tmp_path, name):
+    """without a device the run must stop at ocm_context_create, i.e. after the reference's reader and generators ran
+    and every OpenMM::Force they produced was recognised and translated into the C ABI (host code)"""
     from opencafemol_b200.capi import product_library
 
     if product_library().device_count() > 0:
         pytest.skip("a GPU is visible")
-    r = run_frontend(tmp_path, "sh3", "pdb")
+    r = run_frontend(tmp_path, name, "pdb")
     assert r.returncode == 1
-    assert "no CUDA device available" in r.stdout + r.stderr
+    assert "ocm_context_create" in r.stdout + r.stderr and "no CUDA device available" in r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "bin", "ref_tests_b200")), reason="built where the reference tree is mounted")
+def test_reference_unit_tests_pass_on_the_host_layer():
+    """test/test_read_toml_ff_generator.cpp of the reference (googletest from its tree), compiled unmodified against
+    compat/OpenMM.h: its readers construct every generator class, no device needed"""
+    r = subprocess.run([os.path.join(ROOT, "bin", "ref_tests_b200")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "[  PASSED  ] 32 tests." in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree")
+def test_toml11_stand_in_compiles_with_the_reference_reader():
+    """compat/toml11/toml.hpp is the fallback when the reference's toml11 submodule is not checked out: the reader's
+    translation units must keep compiling against it"""
+    ref = "/root/reference"
+    cmd = ["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-w", "-I", os.path.join(ROOT, "opencafemol_b200", "csrc", "compat"),
+           "-I", os.path.join(ROOT, "opencafemol_b200", "csrc", "compat", "toml11"), "-I", ref, "-I", ref + "/src", "-I", ref + "/fmt/include",
+           "-DFMT_HEADER_ONLY", "-DOPENMM_PLUGIN_DIR=none", ref + "/src/input/Utility.cpp", ref + "/src/input/ReadTOMLInput.cpp"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
 
 
 @pytest.mark.gpu

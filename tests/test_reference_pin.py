@@ -146,6 +146,8 @@ def test_toml_reader_matches_tomllib():
             want = tomllib.load(fh)
         got = R.toml_to_json(path)
         assert norm(got) == norm(want), path
+        # and the toml library the reference itself was compiled with (its toml11 submodule) reads the same
+        assert norm(R.toml_to_json(path, reader="toml11")) == norm(want), path
 
 
 @needs_ref
@@ -187,6 +189,16 @@ def test_reader_tables_match_reference_live(oracle, sample, name):
         assert abs(st["energy_by_group"][g] - eg[k]) <= 1e-10 * max(abs(eg[k]), 1e-3 * escale), (k, st["energy_by_group"][g], eg[k])
     _, f = rs.energy(forces=True)
     assert force_error(st["forces"], f).max() < 1e-9
+
+
+@needs_ref
+def test_reference_unit_tests_pass_on_the_checker():
+    """the reference's own googletest file (test/test_read_toml_ff_generator.cpp) built by `make -C oracle ref`"""
+    import subprocess
+
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_tests")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "[  PASSED  ] 32 tests." in r.stdout, r.stdout[-2000:]
 
 
 @needs_ref

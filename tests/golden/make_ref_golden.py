@@ -210,7 +210,39 @@ def main():
         with gzip.open(os.path.join(HERE, f"ref_{name}.json.gz"), "wt") as fh:
             json.dump(out, fh)
         print(name, "N", out["n"], {k: round(v / 4.184, 6) for k, v in out["energy_by_group_kj"].items()})
+    genesis_fixture(tmp)
     shutil.rmtree(tmp, ignore_errors=True)
+
+
+def genesis_fixture(tmp):
+    """the GENESIS sample (sample/genesis_input/1SRL_cg.*, run shortened to 40 steps) as an input fixture, and the files
+    the reference's own program writes for it"""
+    import tarfile
+
+    src = "/root/reference/sample/genesis_input"
+    work = os.path.join(tmp, "genesis_1SRL")
+    os.makedirs(work)
+    for f in ("1SRL_cg.gro", "1SRL_cg.inp", "1SRL_cg.itp", "1SRL_cg.top"):
+        shutil.copy(os.path.join(src, f), work)
+    shutil.copytree(os.path.join(src, "param"), os.path.join(work, "param"))
+    inp = os.path.join(work, "1SRL_cg.inp")
+    t = open(inp).read()
+    for a, b in (("nsteps              = 1000", "nsteps              = 40"), ("eneout_period       = 100", "eneout_period       = 10"),
+                 ("crdout_period       = 100", "crdout_period       = 10"), ("rstout_period       = 100", "rstout_period       = 10")):
+        assert a in t
+        t = t.replace(a, b)
+    open(inp, "w").write(t)
+    with tarfile.open(os.path.join(HERE, "genesis_1SRL_input.tar.gz"), "w:gz") as tf:
+        tf.add(work, arcname="genesis_1SRL")
+    os.makedirs(os.path.join(work, "output"))
+    subprocess.run([rb.REF_BIN, "1SRL_cg.inp"], cwd=work, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    out = {}
+    for fn in sorted(os.listdir(os.path.join(work, "output"))):
+        b = open(os.path.join(work, "output", fn), "rb").read()
+        out[fn] = {"text": b.decode()} if fn.endswith((".ene", ".pdb")) else {"hex": b.hex(), "size": len(b)}
+    with gzip.open(os.path.join(HERE, "ref_genesis_1SRL.json.gz"), "wt") as fh:
+        json.dump(out, fh)
+    print("genesis_1SRL", sorted(out))
 
 
 if __name__ == "__main__":

@@ -26,7 +26,9 @@ constexpr int kMaxMembers = 4;
 enum SegKind : int { SEG_PAIR_TZ = 0, SEG_PAIR_DH = 1, SEG_BONDED = 2, SEG_DA = 3 };
 enum FlagSlot : int { FLAG_VIOLATION = 0, FLAG_OVERFLOW = 1, FLAG_TICKET = 2, FLAG_NAN = 3, FLAG_MAXDISP = 4, FLAG_DA_OVERFLOW = 6,
                        // slab decomposition: halo message overflow, a bonded term reaching beyond the halo, largest message (entries)
-                       FLAG_DD_OVERFLOW = 7, FLAG_DD_REACH = 8, FLAG_DD_MAXSEND = 9, FLAG_COUNT = 12 };
+                       FLAG_DD_OVERFLOW = 7, FLAG_DD_REACH = 8, FLAG_DD_MAXSEND = 9,
+                       // unlimited boundary: a bead left the range the virtual box was laid out for
+                       FLAG_VBOX = 10, FLAG_COUNT = 12 };
 
 struct GridDev {
     int nc[3];
@@ -597,6 +599,16 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
     const int pad = count + lane;
     if (pad < ((count + 31) & ~31) && pad < stride) row[pad] = dh ? (unsigned int)w : ((unsigned int)w | (pi.w & 0xFF000000u));
     if (lane == 0) { L.nbr_count[w] = count; L.nbr_inner[w] = n_inner; }
+}
+
+// unlimited boundary (virtual box, see ocm_engine.cu): every bead must stay inside [lo, hi], the range for which the
+// virtual box keeps periodic images out of every list radius
+__global__ void vbox_check_kernel(int n, const double* __restrict__ x, double lo0, double lo1, double lo2, double hi0, double hi1, double hi2,
+                                  int* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double px = x[3 * i], py = x[3 * i + 1], pz = x[3 * i + 2];
+    if (!(px >= lo0 && px <= hi0 && py >= lo1 && py <= hi1 && pz >= lo2 && pz <= hi2)) flags[FLAG_VBOX] = 1;
 }
 
 __global__ void save_ref_kernel(int n, const double* __restrict__ x, double* __restrict__ xref) {

@@ -178,6 +178,13 @@ struct ocm_context {
     // options
     double skin = 0.3;
     int nstlist_fixed = 0;   // 0 = adaptive
+    // Unlimited boundary, single system: the pair kernels run in a VIRTUAL periodic box laid out around the beads, large
+    // enough that no periodic image ever comes within a list radius: positions are then 32-bit fixed-point fractions of
+    // that box (uniform resolution L / 2^32 ~ 1e-8 nm) instead of FP32 coordinates, whose resolution at 60 nm from the
+    // origin (4e-6 nm) costs 1e-4 in the r^-12 forces.  Bonded and donor-acceptor terms keep their plain differences.
+    bool vbox = false;
+    double vb_lo[3] = {0, 0, 0}, vb_hi[3] = {0, 0, 0};  // beads must stay inside (vbox_check_kernel at every rebuild)
+    int n_vbox_resize = 0;
     // optional phase timing (option "phase_timing"): events between the phases of directly launched windows
     bool phase_timing = false;
     bool pdl = false;        // programmatic dependent launch of the per-step kernels (option "pdl")
@@ -617,6 +624,36 @@ static void enqueue_da_build(ocm_context* c, cudaStream_t s) {
     c->n_launches += 1;
 }
 
+static void update_params(ocm_context* c);
+// lay the virtual box of an unlimited-boundary system out around the given positions: returns true if it changed
+static bool vbox_layout(ocm_context* c, const double* xyz, bool force) {
+    const int n = c->n;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], xyz[3 * i + k]); hi[k] = std::max(hi[k], xyz[3 * i + k]); }
+    for (int k = 0; k < 3; k++) if (!(lo[k] <= hi[k]) || !std::isfinite(lo[k]) || !std::isfinite(hi[k])) throw std::runtime_error("positions are not finite");
+    bool inside = !force;
+    for (int k = 0; k < 3 && inside; k++) inside = lo[k] >= c->vb_lo[k] && hi[k] <= c->vb_hi[k];
+    if (inside) return false;
+    double R = c->da_rcmax;
+    for (auto& L : c->lists) R = std::max(R, L->rc_list);
+    R += c->skin;
+    R = std::max(R, 0.5);
+    for (int k = 0; k < 3; k++) {
+        const double ext = hi[k] - lo[k];
+        const double grow = std::max(R, 0.15 * ext) * (1.0 + 0.5 * std::min(c->n_vbox_resize, 8));  // room to move before a re-layout
+        c->vb_lo[k] = lo[k] - grow; c->vb_hi[k] = hi[k] + grow;
+        // images stay out of reach: L > (extent the beads may reach) + R; and at least 4 R for the cell grid
+        c->sys.box[k] = std::max(4.0 * R, (ext + 2.0 * grow + R) * 1.01);
+    }
+    c->n_vbox_resize++;
+    update_params(c);
+    c->lists_ready = false; c->lists_current = false;
+    for (auto& L : c->lists) L->stride = 0;
+    drop_graphs(c);
+    return true;
+}
+
 static void update_params(ocm_context* c) {
     StepParams& P = c->P;
     P.n = c->n; P.periodic = c->periodic ? 1 : 0;
@@ -786,6 +823,8 @@ static void enqueue_rebuild(ocm_context* c, cudaStream_t s, bool count_only) {
     }
     if (c->dd && !count_only) dd_exchange_rebuild(c, s);
     if (!count_only) save_ref_kernel<<<nblk(3 * n, 256), 256, 0, s>>>(n, c->x.p, c->xref.p);
+    if (c->vbox && !count_only)
+        vbox_check_kernel<<<nblk(n, 256), 256, 0, s>>>(n, c->x.p, c->vb_lo[0], c->vb_lo[1], c->vb_lo[2], c->vb_hi[0], c->vb_hi[1], c->vb_hi[2], c->flags.p);
     for (size_t l = 0; l < c->lists.size(); l++) {
         auto& L = *c->lists[l];
         if (L.np == 0) continue;
@@ -935,7 +974,17 @@ static void ensure_lists_current(ocm_context* c) {
         enqueue_rebuild(c, c->stream, false);
         int fl[FLAG_COUNT];
         read_flags(c, fl);
-        if (!fl[FLAG_OVERFLOW] && !fl[FLAG_DA_OVERFLOW] && !fl[FLAG_DD_OVERFLOW]) { c->lists_current = true; return; }
+        if (!fl[FLAG_OVERFLOW] && !fl[FLAG_DA_OVERFLOW] && !fl[FLAG_DD_OVERFLOW] && !fl[FLAG_VBOX]) { c->lists_current = true; return; }
+        if (fl[FLAG_VBOX]) {
+            // unlimited boundary: the beads left the range of the virtual box; lay it out again around them
+            std::vector<double> hx((size_t)3 * c->n);
+            CUDA_TRY(cudaMemcpy(hx.data(), c->x.p, hx.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            vbox_layout(c, hx.data(), true);
+            canon_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->P, c->x.p, c->posq.p);
+            CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, FLAG_COUNT * sizeof(int), c->stream));
+            size_lists(c, 1.25);
+            continue;
+        }
         if (c->dd) {
             // an overflowed halo message may have dropped a migrating bead: go back to the roles before the attempt
             CUDA_TRY(cudaMemcpyAsync(c->dd->role.p, c->dd->role_tmp.p, (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
@@ -1064,7 +1113,7 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
         read_flags(c, fl);
         if (c->phase_timing) phase_collect(c);
         if (fl[FLAG_NAN]) throw std::runtime_error("particle coordinate or force is NaN");
-        if (fl[FLAG_VIOLATION] || fl[FLAG_OVERFLOW] || fl[FLAG_DA_OVERFLOW] || fl[FLAG_DD_OVERFLOW]) {
+        if (fl[FLAG_VIOLATION] || fl[FLAG_OVERFLOW] || fl[FLAG_DA_OVERFLOW] || fl[FLAG_DD_OVERFLOW] || fl[FLAG_VBOX]) {
             // roll back and replay the batch with a safer configuration
             CUDA_TRY(cudaMemcpyAsync(c->x.p, c->xbak.p, xb, cudaMemcpyDeviceToDevice, s));
             CUDA_TRY(cudaMemcpyAsync(c->v.p, c->vbak.p, vb, cudaMemcpyDeviceToDevice, s));
@@ -1074,6 +1123,15 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
             if (c->dd) {
                 CUDA_TRY(cudaMemcpyAsync(c->dd->role.p, c->dd->role_bak.p, (size_t)c->n, cudaMemcpyDeviceToDevice, s));
                 if (fl[FLAG_DD_OVERFLOW]) dd_alloc(c, std::max(2 * c->dd->cap, (int)(1.5 * fl[FLAG_DD_MAXSEND])));
+            }
+            if (fl[FLAG_VBOX]) {
+                // the system outgrew the range its virtual box was laid out for: lay it out again around the restored state
+                std::vector<double> hx((size_t)3 * c->n);
+                CUDA_TRY(cudaMemcpyAsync(hx.data(), c->x.p, xb, cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+                vbox_layout(c, hx.data(), true);
+                canon_kernel<<<nblk(c->n, 256), 256, 0, s>>>(c->P, c->x.p, c->posq.p);
+                size_lists(c, 1.25);
             }
             if (fl[FLAG_OVERFLOW] || fl[FLAG_DA_OVERFLOW] || fl[FLAG_DD_OVERFLOW]) size_lists(c, 1.5);
             if (fl[FLAG_VIOLATION]) {
@@ -1333,6 +1391,10 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
         }
     }
     c->n = c->sys.n; c->periodic = c->sys.has_box;
+    if (!c->sys.has_box && nrep == 1) {
+        c->vbox = true; c->periodic = true;
+        for (int k = 0; k < 3; k++) c->sys.box[k] = 1.0e4;  // placeholder until the positions are known
+    }
     c->rep_seeds.assign(seeds, seeds + nrep);
     const uint64_t seed = seeds[0];
     c->T = T; c->gamma = gamma; c->dt = dt; c->seed = seed; c->device = device;
@@ -1549,6 +1611,7 @@ int ocm_set_positions(ocm_context* c, const double* xyz) {
     if (!c || !xyz) return fail("null argument");
     OCM_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
+    if (c->vbox) vbox_layout(c, xyz, !c->positions_set);
     CUDA_TRY(cudaMemcpyAsync(c->x.p, xyz, (size_t)3 * c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     canon_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->P, c->x.p, c->posq.p);
     // slab decomposition: every rank is handed the whole system; ownership follows from the positions
@@ -1810,6 +1873,10 @@ int ocm_get_counter(ocm_context* c, const char* key, double* value) {
     else if (k == "num_pair_lists") *value = (double)c->lists.size();
     else if (k == "halo_exchanges") *value = c->dd ? c->dd->n_exchanges : 0.0;
     else if (k == "halo_push") *value = (c->dd && c->dd->push_ok) ? 1.0 : 0.0;
+    else if (k == "virtual_box_x") *value = c->vbox ? c->sys.box[0] : 0.0;
+    else if (k == "virtual_box_y") *value = c->vbox ? c->sys.box[1] : 0.0;
+    else if (k == "virtual_box_z") *value = c->vbox ? c->sys.box[2] : 0.0;
+    else if (k == "virtual_box_layouts") *value = c->n_vbox_resize;
     else if (k == "halo_message_bytes") *value = c->dd ? (double)c->dd->bytes_s() : 0.0;
     else if (k == "owned_beads") {
         if (!c->dd) *value = c->n;

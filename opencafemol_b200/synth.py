@@ -141,11 +141,12 @@ def hps_slab(n_chains=100, tile=(1, 1), seq=FUS_LC, temperature=300.0, ionic_str
     return spec
 
 
-def replicate(spec, shifts_nm):
-    """`len(shifts_nm)` copies of an unlimited-boundary system side by side in one system (config C3: the
-    nucleosome sample on a 2 x 3 grid).  Bead indices of copy c are offset by c*N, positions shifted by
-    shifts_nm[c]; per-term and per-bead tables are tiled; exclusions, donor/acceptor tables and interaction-group
-    sets are offset per copy (sets become the union over copies, so copies interact like any other beads)."""
+def replicate(spec, shifts_nm, box=None):
+    """`len(shifts_nm)` copies of a system side by side in one system (config C3: the nucleosome sample on a
+    2 x 3 grid; with `box`: a periodic system tiled into a larger box, whose forces must equal the original's copy
+    by copy).  Bead indices of copy c are offset by c*N, positions shifted by shifts_nm[c]; per-term and per-bead
+    tables are tiled; exclusions, donor/acceptor tables and interaction-group sets are offset per copy (sets become
+    the union over copies, so copies interact like any other beads)."""
     import copy as _copy
 
     from .capi import DATopology, PairTopology
@@ -153,8 +154,8 @@ def replicate(spec, shifts_nm):
 
     shifts = np.asarray(shifts_nm, float).reshape(-1, 3)
     m, n = shifts.shape[0], spec.mass.size
-    assert spec.box is None, "replicate() is for unlimited-boundary systems"
-    out = SystemSpec(mass=np.tile(spec.mass, m), box=None,
+    assert (spec.box is None) == (box is None), "give the tiled box of a periodic system (and only of a periodic one)"
+    out = SystemSpec(mass=np.tile(spec.mass, m), box=None if box is None else np.asarray(box, float),
                      positions=np.concatenate([spec.positions + s for s in shifts]),
                      velocities=None if spec.velocities is None else np.tile(spec.velocities, (m, 1)),
                      names=list(spec.names) * m, groups=list(spec.groups) * m)

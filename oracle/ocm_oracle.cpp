@@ -124,6 +124,7 @@ struct ocm_context {
     // slab decomposition (restated as a plan only: which rank owns / sees which bead; the arithmetic is rank-free)
     int dd_rank = 0, dd_world = 1, dd_axis = -1;
     double dd_halo = 0;
+    double vbox[3] = {0, 0, 0};  // the engine's virtual box of an unlimited-boundary system (canonical predicate only)
 };
 
 struct ocm_comm { int world; };
@@ -395,10 +396,13 @@ struct Canon {
 Canon canonicalise(const ocm_context& c) {
     Canon q;
     int n = c.sys.n;
-    q.periodic = c.sys.has_box;
+    // (unlimited boundary with the engine's virtual box: the same fixed-point quantisation in that box; option
+    // "virtual_box_x/y/z", as the engine reports it)
+    q.periodic = c.sys.has_box || c.vbox[0] > 0;
+    const double* box = c.sys.has_box ? c.sys.box : c.vbox;
     if (q.periodic) {
         q.fx.resize(n); q.fy.resize(n); q.fz.resize(n);
-        double inv[3] = {1.0 / c.sys.box[0], 1.0 / c.sys.box[1], 1.0 / c.sys.box[2]};
+        double inv[3] = {1.0 / box[0], 1.0 / box[1], 1.0 / box[2]};
         for (int i = 0; i < n; i++) {
             double u[3] = {c.x[i].x * inv[0], c.x[i].y * inv[1], c.x[i].z * inv[2]};
             uint32_t f[3];
@@ -408,9 +412,9 @@ Canon canonicalise(const ocm_context& c) {
             }
             q.fx[i] = f[0]; q.fy[i] = f[1]; q.fz[i] = f[2];
         }
-        q.sx = (float)(c.sys.box[0] / 4294967296.0);
-        q.sy = (float)(c.sys.box[1] / 4294967296.0);
-        q.sz = (float)(c.sys.box[2] / 4294967296.0);
+        q.sx = (float)(box[0] / 4294967296.0);
+        q.sy = (float)(box[1] / 4294967296.0);
+        q.sz = (float)(box[2] / 4294967296.0);
     } else {
         q.px.resize(n); q.py.resize(n); q.pz.resize(n);
         for (int i = 0; i < n; i++) {
@@ -1162,6 +1166,9 @@ int oracle_context_set_option(ocm_context* c, const char* key, double v) {
     if (!c) return fail("null context");
     if (!strcmp(key, "brute_force")) { c->force_brute = v != 0; return 0; }
     if (!strcmp(key, "slab_halo_nm")) { c->dd_halo = v; return 0; }
+    if (!strcmp(key, "virtual_box_x")) { c->vbox[0] = v; return 0; }
+    if (!strcmp(key, "virtual_box_y")) { c->vbox[1] = v; return 0; }
+    if (!strcmp(key, "virtual_box_z")) { c->vbox[2] = v; return 0; }
     if (!strcmp(key, "threads")) {
 #ifdef _OPENMP
         omp_set_num_threads((int)v);
@@ -1412,7 +1419,7 @@ int oracle_get_cell_ids_rlist(ocm_context* c, int term, double rlist, int32_t* c
     if (q.periodic) {
         int nc[3];
         for (int k = 0; k < 3; k++) {
-            nc[k] = (int)floorf((float)c->sys.box[k] / wmin);
+            nc[k] = (int)floorf((float)(c->sys.has_box ? c->sys.box[k] : c->vbox[k]) / wmin);
             nc[k] = std::max(1, std::min(nc[k], 1024));
             dims[k] = nc[k];
         }

@@ -176,7 +176,7 @@ def test_frontend_genesis_input(engine, tmp_path):
     if not os.path.exists(BIN):
         pytest.skip("bin/open_cafemol_b200 missing")
     with tarfile.open(os.path.join(GOLDEN, "genesis_1SRL_input.tar.gz")) as tf:
-        tf.extractall(tmp_path)
+        tf.extractall(tmp_path, filter="data")
     work = tmp_path / "genesis_1SRL"
     os.makedirs(work / "output")
     r = subprocess.run([BIN, "1SRL_cg.inp"], cwd=work, capture_output=True, text=True, timeout=600)

@@ -34,7 +34,15 @@ def check_state(ctx, ora, spec, ftol=FORCE_TOL, etol=ENERGY_TOL):
     return a, b
 
 
+def sync_canon(ctx, ora):
+    """Unlimited boundary: the engine quantises pair-kernel positions in a virtual periodic box (fixed point, uniform
+    resolution); the oracle's canonical predicate needs that box to reproduce pair sets and cell ids bit for bit."""
+    for ax in "xyz":
+        ora.set_option("virtual_box_" + ax, ctx.counter("virtual_box_" + ax))
+
+
 def check_sets(ctx, ora):
+    sync_canon(ctx, ora)
     for t in range(ctx.num_pair_terms()):
         pa, pb = ctx.neighbor_pairs(t), ora.neighbor_pairs(t)
         assert pa.shape == pb.shape and np.array_equal(pa, pb), f"pair set of term {t} differs"
@@ -176,6 +184,8 @@ def test_cell_assignment_bit_exact(engine, oracle):
     import ctypes as C
     for spec in (synth.hps_slab(n_chains=12), load_golden_spec("sh3")):
         ctx, ora = ti.make_context(engine, spec), ti.make_context(oracle, spec)
+        ctx.get_state(energy=True)  # lists sized: the virtual box of the unlimited-boundary case is laid out
+        sync_canon(ctx, ora)
         for t in range(ctx.num_pair_terms()):
             rlist = ctx.counter(f"list_cutoff_nm.{t}")
             ids, dims = ctx.cell_ids(t)
@@ -356,3 +366,31 @@ def test_every_bonded_kind_and_interaction_groups(engine, oracle):
         group_ids = {str(g): g for g in range(11)}
     check_state(ctx, ora, Spec)
     check_sets(ctx, ora)
+
+
+def test_c3_nucleosome_grid(engine, oracle):
+    """config C3: nucleosome_1kx5 on a 2 x 3 grid (11 160 beads: 3SPN.2C DNA, AICG2+ protein, PDNS, Debye-Hueckel)"""
+    one = load_golden_spec("nucleosome")
+    spec = synth.replicate(one, [[30.0 * i, 30.0 * j, 0.0] for i in range(2) for j in range(3)])
+    ctx, ora = ti.make_context(engine, spec), ti.make_context(oracle, spec)
+    a, b = check_state(ctx, ora, spec)
+    single = ti.make_context(oracle, one).get_state(energy=True)
+    assert a["potential_energy"] == pytest.approx(6.0 * single["potential_energy"], rel=1e-5)
+    for t in range(ctx.num_da_terms()):
+        assert np.array_equal(ctx.da_pairs(t), ora.da_pairs(t))
+    ctx.step(200)
+    assert np.isfinite(ctx.get_state(energy=True)["potential_energy"])
+
+
+def test_periodic_tiling_reproduces_the_forces(engine):
+    """a periodic system tiled 2 x 2 in x, y into a box twice as large has, copy by copy, the forces
+    of the original (exact periodic images); the fixed-point grid is twice as coarse, hence 1e-5 and not bit-exact"""
+    base = synth.hps_slab(n_chains=12)
+    lx, ly, lz = base.box
+    tiled = synth.replicate(base, [[i * lx, j * ly, 0.0] for i in range(2) for j in range(2)], box=[2 * lx, 2 * ly, lz])
+    a = ti.make_context(engine, base).get_state(forces=True, energy=True)
+    b = ti.make_context(engine, tiled).get_state(forces=True, energy=True)
+    n = base.mass.size
+    for c in range(4):
+        assert force_error(b["forces"][c * n:(c + 1) * n], a["forces"]).max() < FORCE_TOL
+    assert b["potential_energy"] == pytest.approx(4.0 * a["potential_energy"], rel=1e-6)

@@ -305,3 +305,18 @@ def test_replica_batch_equals_standalone_runs(oracle):
     for t in range(batch.num_pair_terms()):
         want = np.concatenate([c.neighbor_pairs(t) + r * n for r, c in enumerate(singles)])
         assert np.array_equal(batch.neighbor_pairs(t), want)
+
+
+def test_replicate_tiles_a_periodic_system_exactly(oracle):
+    """synth.replicate with a tiled box: every copy feels the forces of the original (periodic images), 4x the energy"""
+    from opencafemol_b200 import synth, toml_input as ti
+
+    base = synth.hps_slab(n_chains=3)
+    lx, ly, lz = base.box
+    tiled = synth.replicate(base, [[i * lx, j * ly, 0.0] for i in range(2) for j in range(2)], box=[2 * lx, 2 * ly, lz])
+    a = ti.make_context(oracle, base).get_state(forces=True, energy=True)
+    b = ti.make_context(oracle, tiled).get_state(forces=True, energy=True)
+    n = base.mass.size
+    for c in range(4):
+        assert np.abs(b["forces"][c * n:(c + 1) * n] - a["forces"]).max() < 1e-8 * max(1.0, np.abs(a["forces"]).max())
+    assert b["potential_energy"] == pytest.approx(4.0 * a["potential_energy"], rel=1e-12)

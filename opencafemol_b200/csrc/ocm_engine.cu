@@ -445,10 +445,19 @@ static void configure_grid(ocm_context* c, PairListHost& L) {
     for (int k = 0; k < 3; k++) { g.bmin[k] = 0x7FFFFFFF; g.bmax[k] = (int)0x80000000; g.lo[k] = 0.f; }
     if (c->periodic) {
         long long tot = 1;
-        for (int k = 0; k < 3; k++) {
-            int nc = (int)floorf((float)c->sys.box[k] / D.wmin);
-            g.nc[k] = std::max(1, std::min(nc, 1024));
-            tot *= g.nc[k];
+        // a virtual box (unlimited boundary) is mostly empty: widen the cells until their number is of the order of the
+        // participants (same rule in the oracle's restatement of the grid)
+        const long long cap = std::max(4096, 8 * L.np + 64);
+        float w = D.wmin;
+        for (;;) {
+            tot = 1;
+            for (int k = 0; k < 3; k++) {
+                int nc = (int)floorf((float)c->sys.box[k] / w);
+                g.nc[k] = std::max(1, std::min(nc, 1024));
+                tot *= g.nc[k];
+            }
+            if (!c->vbox || tot <= cap) break;
+            w *= 1.25f;
         }
         if (tot > (1ll << 26)) throw std::runtime_error("cell grid too large");
         g.ncell = (int)tot;
@@ -1429,11 +1438,11 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
     c->skin = std::min(0.4, std::max(0.1, 0.08 * rcmax));
     if (c->periodic)
         for (int k = 0; k < 3; k++)
-            if (c->da_rcmax > 0 && c->da_rcmax + c->skin > 0.5 * sys->box[k]) c->skin = std::max(0.0, 0.5 * sys->box[k] - c->da_rcmax) * 0.999;
+            if (c->da_rcmax > 0 && c->da_rcmax + c->skin > 0.5 * c->sys.box[k]) c->skin = std::max(0.0, 0.5 * c->sys.box[k] - c->da_rcmax) * 0.999;
     if (c->periodic)
         for (auto& L : c->lists)
             for (int k = 0; k < 3; k++)
-                if (L->rc_list + c->skin > 0.5 * sys->box[k]) c->skin = std::max(0.0, 0.5 * sys->box[k] - L->rc_list) * 0.999;
+                if (L->rc_list + c->skin > 0.5 * c->sys.box[k]) c->skin = std::max(0.0, 0.5 * c->sys.box[k] - L->rc_list) * 0.999;
     compile_bonded(c);
     update_params(c);
     c->nst = initial_nst(c);

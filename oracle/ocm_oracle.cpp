@@ -1418,10 +1418,19 @@ int oracle_get_cell_ids_rlist(ocm_context* c, int term, double rlist, int32_t* c
     for (int i = 0; i < n; i++) cell_of_bead[i] = -1;
     if (q.periodic) {
         int nc[3];
-        for (int k = 0; k < 3; k++) {
-            nc[k] = (int)floorf((float)(c->sys.has_box ? c->sys.box[k] : c->vbox[k]) / wmin);
-            nc[k] = std::max(1, std::min(nc[k], 1024));
-            dims[k] = nc[k];
+        // (virtual box of an unlimited-boundary system: cells widened until their number is of the order of the participants)
+        const long long cap = std::max<long long>(4096, 8 * (long long)t.part.size() + 64);
+        float w = wmin;
+        for (;;) {
+            long long tot = 1;
+            for (int k = 0; k < 3; k++) {
+                nc[k] = (int)floorf((float)(c->sys.has_box ? c->sys.box[k] : c->vbox[k]) / w);
+                nc[k] = std::max(1, std::min(nc[k], 1024));
+                dims[k] = nc[k];
+                tot *= nc[k];
+            }
+            if (c->sys.has_box || tot <= cap) break;
+            w *= 1.25f;
         }
         for (int i : t.part) {
             uint32_t cx = (uint32_t)(((uint64_t)q.fx[i] * (uint64_t)nc[0]) >> 32);

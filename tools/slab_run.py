@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--nstlist", type=int, default=0)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--halo", choices=["push", "nccl"], default="push", help="per-step halo: peer-memory push kernel or NCCL send/recv")
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
     ap.add_argument("--phases", action="store_true", help="time the phases of a step with CUDA events (engine option phase_timing)")
     args = ap.parse_args()
 
@@ -69,6 +70,9 @@ def main():
         ctx.set_option("nstlist", args.nstlist)
     if world > 1 and args.halo == "nccl":
         ctx.set_option("halo_push", 0)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, float(v))
     ctx.step(args.warmup)
     if args.phases:
         ctx.set_option("phase_timing", 1)

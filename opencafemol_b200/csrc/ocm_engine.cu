@@ -507,7 +507,8 @@ static void build_segments(ocm_context* c) {
         // Neighbour counts vary across a slab (dense centre, thin surface) and, under a slab decomposition, owned rows
         // alternate with empty halo rows: with the former "16 blocks per SM" rule the last blocks left SMs idle
         // (130 k rows per GPU: force launch 0.202 -> 0.169 ms).
-        int chunk = c->chunk_opt > 0 ? c->chunk_opt : (int)(std::sqrt((double)std::max(rows, 1)) / 12.0);
+        // (small systems keep the finer "16 blocks per SM" split: 8 rows per block at 16 k rows)
+        int chunk = c->chunk_opt > 0 ? c->chunk_opt : std::min((rows + 148 * 16 - 1) / (148 * 16), (int)(std::sqrt((double)std::max(rows, 1)) / 12.0));
         chunk = std::max(gpb, (chunk + gpb - 1) / gpb * gpb);
         // (slab decomposition: 25 % head-room over the rows in use at the sizing pass; more rows than that raise the
         // overflow flag in build_list_kernel and the lists are sized again)

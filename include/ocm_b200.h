@@ -167,6 +167,12 @@ int ocm_system_add_debye_huckel(ocm_system*, int group, double K, double debye_n
  *                                         LennardJonesRepulsiveForceFieldGenerator.cpp:33-115 */
 int ocm_system_add_lj_repulsive(ocm_system*, int group, double rc, const double* eps,
                                 const double* sigma, const ocm_pair_topology* topo);
+/* Weeks-Chandler-Andersen: E = step(2^(1/6) s - r) (4 e ((s/r)^12-(s/r)^6) + e), e GEOMETRIC, s arithmetic mean
+ *                                         WeeksChandlerAndersenForceFieldGenerator.cpp:32-105
+ * (also serves UniformWeeksChandlerAndersenForceFieldGenerator.cpp:136-175: one sigma, eps for all members of the
+ * interaction groups) */
+int ocm_system_add_wca(ocm_system*, int group, double rc, const double* eps, const double* sigma,
+                       const ocm_pair_topology* topo);
 /* E = e (step(r - 2^(1/6) s) 4((s/r)^12-(s/r)^6) - step(2^(1/6) s - r)), OpenMM switching
  * function on [r_switch, rc]             LennardJonesAttractiveForceFieldGenerator.cpp:38-123 */
 int ocm_system_add_lj_attractive(ocm_system*, int group, double rc, double r_switch,

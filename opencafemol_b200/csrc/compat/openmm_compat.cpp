@@ -143,6 +143,14 @@ const char* kLJRepulsive =                                                    //
 const char* kLJAttractive =                                                   // LennardJonesAttractiveForceFieldGenerator.cpp:40-50
     "epsilon*(step(r-threthold)*4*(sigma_r_12-sigma_r_6)-step(threthold-r));sigma_r_12=sigma_r_6^2;sigma_r_6=sigma_r^6;sigma_r=sigma/r;"
     "threthold=sigma*2^(1/6);sigma=(sigma1+sigma2)*0.5;epsilon=(epsilon1+epsilon2)*0.5";
+const char* kWCA =                                                            // WeeksChandlerAndersenForceFieldGenerator.cpp:34-41
+    "step(sigma*2^(1/6)-r)*(4*eps*(sigma_r_12-sigma_r_6)+eps);sigma_r_12=sigma_r_6^2;sigma_r_6=sigma_r^6;sigma_r=sigma/r;"
+    "eps=sqrt(eps1*eps2);sigma=(sigma1+sigma2)*0.5";
+const char* kUniformWCA =                                                     // UniformWeeksChandlerAndersenForceFieldGenerator.cpp:138-143
+    "4*eps*(sigma_r_12-sigma_r_6+0.25);sigma_r_12=sigma_r_6^2;sigma_r_6=sigma_r^6;sigma_r=sigma/r";
+const char* kUniformLJAttractive =                                            // UniformLennardJonesAttractiveForceFieldGenerator.cpp:145-152
+    "epsilon*(step(r-threthold)*4*(sigma_r_12-sigma_r_6)-step(threthold-r));sigma_r_12=sigma_r_6^2;sigma_r_6=sigma_r^6;sigma_r=sigma/r;"
+    "threthold=sigma*2^(1/6)";
 const char* k3SPN2ExcludedVolume =                                            // ThreeSPN2ExcludedVolumeForceFieldGenerator.cpp:21-26
     "step(sigma-r)*(epsilon*((sigma/r)^12-2*(sigma/r)^6)+epsilon);epsilon=sqrt(epsilon1*epsilon2);sigma=0.5*(sigma1+sigma2)";
 const char* kBasePair =                                                       // ThreeSPN2BasePairForceFieldGenerator.cpp:8-26
@@ -387,7 +395,8 @@ class SystemCompiler {
         const Norm nz = normalise(f);
         PairTopo pt;
         fill_topology(f, pt);
-        if (f.use_switch_ && nz.expr != kLJAttractive) throw OpenMMException("B200 engine: a switching function is only supported for LennardJonesAttractive");
+        if (f.use_switch_ && nz.expr != kLJAttractive && nz.expr != kUniformLJAttractive)
+            throw OpenMMException("B200 engine: a switching function is only supported for the LennardJonesAttractive potentials");
         if (nz.expr == kExcludedVolume) {
             expect_names(nz.params, {"sigma"}, "ExcludedVolume");
             const double rc = f.cutoff_, cc = global_value(f, nz, "cutoff_correction");
@@ -405,6 +414,27 @@ class SystemCompiler {
             // without OpenMM's switching function the potential is simply cut at rc: r_switch = rc
             const double rsw = f.use_switch_ ? f.switch_ : f.cutoff_;
             check(ocm_system_add_lj_attractive(out_, g, f.cutoff_, rsw, column(f.rows_, 0).data(), column(f.rows_, 1).data(), &pt.t), "LennardJonesAttractive");
+        } else if (nz.expr == kWCA) {
+            expect_names(nz.params, {"sigma", "eps"}, "WCA");
+            check(ocm_system_add_wca(out_, g, f.cutoff_, column(f.rows_, 1).data(), column(f.rows_, 0).data(), &pt.t), "WCA");
+        } else if (nz.expr == kUniformWCA || nz.expr == kUniformLJAttractive) {
+            // one sigma / epsilon for every member of the interaction groups (one Force per residue-name pair): hand the
+            // engine per-bead arrays that carry the parameter on the members and NaN elsewhere
+            if (!nz.params.empty()) throw OpenMMException("B200 engine: a uniform pair potential has no per-particle parameters");
+            if (f.groups_.empty()) throw OpenMMException("B200 engine: a uniform pair potential needs its interaction groups");
+            const bool wca = nz.expr == kUniformWCA;
+            const double sigma = global_value(f, nz, "sigma"), eps = global_value(f, nz, wca ? "eps" : "epsilon");
+            std::vector<double> sg(f.rows_.size(), std::numeric_limits<double>::quiet_NaN()), ep(sg);
+            for (auto& gp : f.groups_)
+                for (const std::set<int>* st : {&gp.first, &gp.second})
+                    for (int i : *st) { sg.at(i) = sigma; ep.at(i) = eps; }
+            if (wca) {
+                if (std::fabs(f.cutoff_ - sigma * std::pow(2.0, 1.0 / 6.0)) > 1e-9 * f.cutoff_) throw OpenMMException("B200 engine: UniformWCA cutoff is not 2^(1/6) sigma");
+                check(ocm_system_add_wca(out_, g, f.cutoff_, ep.data(), sg.data(), &pt.t), "UniformWeeksChandlerAndersen");
+            } else {
+                if (!f.use_switch_) throw OpenMMException("B200 engine: UniformLennardJonesAttractive without its switching function");
+                check(ocm_system_add_lj_attractive(out_, g, f.cutoff_, f.switch_, ep.data(), sg.data(), &pt.t), "UniformLennardJonesAttractive");
+            }
         } else if (nz.expr == k3SPN2ExcludedVolume) {
             expect_names(nz.params, {"epsilon", "sigma"}, "3SPN2ExcludedVolume");
             check(ocm_system_add_3spn2_excluded_volume(out_, g, f.cutoff_, column(f.rows_, 0).data(), column(f.rows_, 1).data(), &pt.t), "3SPN2ExcludedVolume");

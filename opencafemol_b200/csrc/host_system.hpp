@@ -35,7 +35,7 @@ struct BondedTerm {
     int64_t n() const { return (int64_t)idx.size() / nbody; }
 };
 
-enum PairKind : int { P_EXV = 0, P_DH, P_LJREP, P_LJATT, P_3SPN2EXV };
+enum PairKind : int { P_EXV = 0, P_DH, P_LJREP, P_LJATT, P_3SPN2EXV, P_WCA };
 
 struct PairTerm {
     int kind, group, periodic;
@@ -261,10 +261,10 @@ inline int add_da(ocm_system* s, int kind, int group, const ocm_da_topology* top
 }
 
 // effective interaction range of one pair term: beyond it the term is exactly zero.
-// (LJ-repulsive vanishes beyond 2^(1/6) sigma_ij, the 3SPN.2 excluded volume beyond sigma_ij.)
+// (LJ-repulsive and WCA vanish beyond 2^(1/6) sigma_ij, the 3SPN.2 excluded volume beyond sigma_ij.)
 inline double effective_rc(const PairTerm& t) {
     double rc = t.rc;
-    if (t.kind == P_LJREP || t.kind == P_3SPN2EXV) {
+    if (t.kind == P_LJREP || t.kind == P_WCA || t.kind == P_3SPN2EXV) {
         double m1 = 0, m2 = 0;
         for (int i : t.part) {
             double s = t.p1[i];
@@ -272,7 +272,7 @@ inline double effective_rc(const PairTerm& t) {
         }
         if (t.part.size() < 2) m2 = m1;
         double smax = 0.5 * (m1 + m2);
-        double zone = (t.kind == P_LJREP) ? smax * std::pow(2.0, 1.0 / 6.0) : smax;
+        double zone = (t.kind != P_3SPN2EXV) ? smax * std::pow(2.0, 1.0 / 6.0) : smax;
         zone *= (1.0 + 1e-6);
         rc = std::min(rc, zone);
     }

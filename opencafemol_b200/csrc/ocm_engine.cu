@@ -239,6 +239,11 @@ static TZ tz_coeffs(const PairTerm& t, int i, int j) {
             double th = sg * std::pow(2.0, 1.0 / 6.0);
             z.c12i = 4 * ep * std::pow(sg, 12); z.c6i = 4 * ep * std::pow(sg, 6); z.c0i = ep; z.a2 = th * th;
         } break;
+        case P_WCA: {  // as LJ-repulsive, with the geometric mean of epsilon
+            double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = std::sqrt(t.p0[i] * t.p0[j]);
+            double th = sg * std::pow(2.0, 1.0 / 6.0);
+            z.c12i = 4 * ep * std::pow(sg, 12); z.c6i = 4 * ep * std::pow(sg, 6); z.c0i = ep; z.a2 = th * th;
+        } break;
         case P_LJATT: {
             double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = 0.5 * (t.p0[i] + t.p0[j]);
             double th = sg * std::pow(2.0, 1.0 / 6.0);
@@ -1332,6 +1337,10 @@ int ocm_system_add_debye_huckel(ocm_system* s, int g, double K, double debye, do
 int ocm_system_add_lj_repulsive(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
     if (!sigma) return fail("lj_repulsive: null sigma");
     return add_pair(s, P_LJREP, g, rc, rc, 0, 0, 0, eps, sigma, topo, "lj_repulsive");
+}
+int ocm_system_add_wca(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
+    if (!sigma) return fail("wca: null sigma");
+    return add_pair(s, P_WCA, g, rc, rc, 0, 0, 0, eps, sigma, topo, "wca");
 }
 int ocm_system_add_lj_attractive(ocm_system* s, int g, double rc, double rsw, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
     if (!sigma) return fail("lj_attractive: null sigma");

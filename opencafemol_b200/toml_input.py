@@ -798,6 +798,24 @@ def _read_global(spec, gf, topo, periodic, attr):
             spec.add_term(Term("lj_repulsive", pot, dict(rc=rc, eps=eps, sigma=sig, topo=topo_for(has))))
         else:
             spec.add_term(Term("lj_attractive", pot, dict(rc=rc, r_switch=0.9 * rc, eps=eps, sigma=sig, topo=topo_for(has))))
+    elif pot == "WCA":
+        # read_toml_weeks_chandler_andersen_ff_generator (ReadTOMLForceFieldGenerator.cpp:1238-1293) and the generator's
+        # cutoff (WeeksChandlerAndersenForceFieldGenerator.cpp:49-96): (max + 2nd max sigma)/2 * 2^(1/6), "<=" updates.
+        # The name-pair table form (UniformWeeksChandlerAndersen) is served through the C++ host layer only.
+        if "table" in gf:
+            raise NotImplementedError("UniformWeeksChandlerAndersen (table form): use the C++ host layer")
+        eps = np.full(n, np.nan)
+        sig = np.full(n, np.nan)
+        for p in params:
+            i = _param(p, env, "index") + _param(p, env, "offset", 0)
+            if i >= n:
+                raise RuntimeError(f"[error] read_toml_weeks_chandler_andersen_ff_generator : index {i} exceeds the system's largest index {n - 1}.")
+            sig[i] = _param_either(p, env, "sigma", "σ") * NM_PER_ANGSTROM
+            eps[i] = _param_either(p, env, "epsilon", "ε") * KJ_PER_KCAL
+        has = ~np.isnan(sig)
+        mx, sm = _two_largest(sig[has], strict=False)
+        rc = (mx + sm) * 0.5 * 2.0 ** (1.0 / 6.0)
+        spec.add_term(Term("wca", "WeeksChandlerAndersen", dict(rc=rc, eps=eps, sigma=sig, topo=topo_for(has))))
     else:
         raise NotImplementedError(f"global force field {pot} is not in scope yet")
 

@@ -68,7 +68,7 @@ struct BondedTerm {
     int64_t n() const { return (int64_t)idx.size() / nbody; }
 };
 
-enum PairKind { P_EXV, P_DH, P_LJREP, P_LJATT, P_3SPN2EXV };
+enum PairKind { P_EXV, P_DH, P_LJREP, P_LJATT, P_3SPN2EXV, P_WCA };
 
 struct PairTerm {
     PairKind kind;
@@ -342,6 +342,15 @@ inline void pair_energy(const PairTerm& t, int i, int j, double r, double* E, do
                 *dEdr = ep * 4.0 * (-12.0 * s12 + 6.0 * s6) / r;
             } else { *E = 0; *dEdr = 0; }
         } break;
+        case P_WCA: {  // WeeksChandlerAndersenForceFieldGenerator.cpp:34-41; p0 = eps (geometric mean), p1 = sigma
+            double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = std::sqrt(t.p0[i] * t.p0[j]);
+            double th = sg * std::pow(2.0, 1.0 / 6.0);
+            if (th - r >= 0.0) {
+                double sr = sg / r, s6 = std::pow(sr, 6), s12 = s6 * s6;
+                *E = 4.0 * ep * (s12 - s6) + ep;
+                *dEdr = ep * 4.0 * (-12.0 * s12 + 6.0 * s6) / r;
+            } else { *E = 0; *dEdr = 0; }
+        } break;
         case P_LJATT: {  // LennardJonesAttractiveForceFieldGenerator.cpp:40-50 (+ switch :113-115)
             double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = 0.5 * (t.p0[i] + t.p0[j]);
             double th = sg * std::pow(2.0, 1.0 / 6.0);
@@ -439,7 +448,7 @@ inline float canon_r2(const Canon& q, int i, int j) {
 // effective interaction cutoff of a term (pairs beyond contribute exactly zero)
 double effective_rc(const PairTerm& t) {
     double rc = t.rc;
-    if (t.kind == P_LJREP || t.kind == P_3SPN2EXV) {
+    if (t.kind == P_LJREP || t.kind == P_WCA || t.kind == P_3SPN2EXV) {
         // zero beyond max over pairs of the zone boundary
         double m1 = 0, m2 = 0;  // two largest sigma
         for (int i : t.part) {
@@ -448,7 +457,7 @@ double effective_rc(const PairTerm& t) {
         }
         if (t.part.size() < 2) m2 = m1;
         double smax = 0.5 * (m1 + m2);
-        double zone = (t.kind == P_LJREP) ? smax * std::pow(2.0, 1.0 / 6.0) : smax;
+        double zone = (t.kind != P_3SPN2EXV) ? smax * std::pow(2.0, 1.0 / 6.0) : smax;
         zone *= (1.0 + 1e-6);
         rc = std::min(rc, zone);
     }
@@ -1044,6 +1053,9 @@ int oracle_system_add_debye_huckel(ocm_system* s, int g, double K, double debye,
 }
 int oracle_system_add_lj_repulsive(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
     return add_pair(s, P_LJREP, g, rc, rc, 0, 0, 0, eps, sigma, topo, "lj_repulsive");
+}
+int oracle_system_add_wca(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
+    return add_pair(s, P_WCA, g, rc, rc, 0, 0, 0, eps, sigma, topo, "wca");
 }
 int oracle_system_add_lj_attractive(ocm_system* s, int g, double rc, double rsw, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
     if (!(rsw < rc)) return fail("lj_attractive: r_switch must be below rc");

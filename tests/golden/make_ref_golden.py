@@ -143,13 +143,13 @@ def main():
     samples = {"sh3": open(os.path.join(REF, "sh3_AICG2+.toml")).read(),
                "dna_3spn2": open(os.path.join(REF, "dna_3SPN2.toml")).read(),
                "nucleosome": open(os.path.join(REF, "nucleosome_1kx5.toml")).read(),
-               "fus10": fus_subset(10)}
+               "fus10": fus_subset(10), "wcamix": wcamix_toml()}
     for name, text in samples.items():
         path = os.path.join(tmp, name + ".toml")
         with open(path, "w") as fh:
             fh.write(text)
         rs = R.open_toml(path)
-        spec = ti.read_toml(path)
+        spec = ti.read_toml(path) if name != "wcamix" else None  # (table forms are read by the reference's reader only)
         out = {"source": name, "n": rs.n, "group_map": rs.group_map(), "integrator": rs.integrator()}
         if name == "fus10":
             rs.minimize(tolerance=10.0, max_iterations=400)
@@ -165,18 +165,18 @@ def main():
         out["forces"] = f.tolist()
         out["force_digest"] = force_digest(rs.describe())
         # short Langevin run with the documented Philox noise (same streams as oracle/ocm_oracle.cpp and the engine)
-        if spec.velocities is not None:
+        if spec is not None and spec.velocities is not None:
             rs.set_velocities(spec.velocities)
         else:
-            rs.set_velocities_to_temperature(spec.temperature, 2026)
-        out["vel_seed_used"] = None if spec.velocities is not None else 2026
+            rs.set_velocities_to_temperature(300.0 if spec is None else spec.temperature, 2026)
+        out["vel_seed_used"] = None if (spec is not None and spec.velocities is not None) else 2026
         out["kinetic_energy_kj"] = rs.kinetic_energy()
         nst = 20
         rs.step(nst)
         out["trajectory"] = {"steps": nst, "positions": rs.positions().tolist(), "velocities": rs.velocities().tolist()}
         rs.close()
         # what the reference's own main program writes
-        if name in ("sh3", "dna_3spn2", "fus10"):
+        if name in ("sh3", "dna_3spn2", "fus10", "wcamix"):
             files = {}
             for fmt in ("pdb", "dcd"):
                 wd = os.path.join(tmp, name + "_" + fmt)
@@ -188,6 +188,8 @@ def main():
                         p["pos"] = [float(v) for v in xyz]
                     d["systems"][0]["vel_seed"] = 2026  # the sample has neither velocities nor a seed: make the run reproducible
                     text_run = dump_toml(d)
+                elif spec is None:
+                    text_run = text
                 elif spec.velocities is None:
                     # neither velocities nor a velocity seed in the sample: make the program run reproducible
                     d = tomllib.loads(text)
@@ -212,6 +214,43 @@ def main():
         print(name, "N", out["n"], {k: round(v / 4.184, 6) for k, v in out["energy_by_group_kj"].items()})
     genesis_fixture(tmp)
     shutil.rmtree(tmp, ignore_errors=True)
+
+
+def wcamix_toml():
+    """a small synthetic system for the potentials of SURVEY.md 8f rank 4 that share the two-zone 12-6 kernel: per-particle
+    WCA, name-pair table WCA (UniformWeeksChandlerAndersen) and name-pair table LennardJonesAttractive
+    (UniformLennardJonesAttractive), 4 chains of 12 beads, unlimited boundary"""
+    rng = np.random.default_rng(7)
+    nch, L = 4, 12
+    n = nch * L
+    grid = np.stack(np.meshgrid(np.arange(4), np.arange(4), np.arange(3), indexing="ij"), -1).reshape(-1, 3)
+    pos = grid * 5.6 + rng.uniform(-0.5, 0.5, (n, 3))
+    order = np.lexsort((grid[:, 0] if False else grid[:, 2], grid[:, 1], grid[:, 0]))
+    pos = pos[order]
+    names = ["A" if (i // 3) % 2 == 0 else "B" for i in range(n)]
+    particles = [{"m": 100.0 + i % 5, "pos": [float(v) for v in pos[i]], "name": names[i], "group": "G%d" % (i // L)} for i in range(n)]
+    bonds = [{"indices": [c * L + k, c * L + k + 1], "v0": float(np.linalg.norm(pos[c * L + k] - pos[c * L + k + 1])), "k": 5.0}
+             for c in range(nch) for k in range(L - 1)]
+    d = {
+        "files": {"output": {"prefix": "run", "path": "./out/", "format": "dcd"}},
+        "units": {"length": "angstrom", "energy": "kcal/mol"},
+        "simulator": {"type": "MolecularDynamics", "boundary_type": "Unlimited", "precision": "double", "delta_t": 0.1, "total_step": 40,
+                      "save_step": 10, "seed": 777, "integrator": {"type": "BAOABLangevin", "gammas": []}},
+        "systems": [{"attributes": {"temperature": 300.0}, "vel_seed": 2026, "particles": particles}],
+        "forcefields": [{
+            "local": [{"interaction": "BondLength", "potential": "Harmonic", "topology": "bond", "parameters": bonds}],
+            "global": [
+                {"interaction": "Pair", "potential": "WCA", "ignore": {"particles_within": {"bond": 1}},
+                 "parameters": [{"index": i, "sigma": 4.6 + 0.2 * (i % 4), "epsilon": 0.3 + 0.05 * (i % 3)} for i in range(0, n, 2)]},
+                {"interaction": "Pair", "potential": "WCA", "ignore": {"particles_within": {"bond": 2}},
+                 "table": {"A": {"A": {"sigma": 5.2, "epsilon": 0.4}, "B": {"sigma": 4.8, "epsilon": 0.6}}, "B": {"B": {"sigma": 5.0, "epsilon": 0.5}}},
+                 "parameters": [{"index": i, "name": names[i]} for i in range(n)]},
+                {"interaction": "Pair", "potential": "LennardJonesAttractive", "cutoff": 2.5, "ignore": {"particles_within": {"bond": 1}},
+                 "table": {"A": {"A": {"sigma": 5.0, "epsilon": 0.25}, "B": {"sigma": 5.4, "epsilon": 0.15}}, "B": {"B": {"sigma": 4.9, "epsilon": 0.3}}},
+                 "parameters": [{"index": i, "name": names[i]} for i in range(n)]},
+            ]}],
+    }
+    return dump_toml(d)
 
 
 def genesis_fixture(tmp):

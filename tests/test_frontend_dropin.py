@@ -77,7 +77,7 @@ needs_frontend = pytest.mark.skipif(not os.path.exists(BIN), reason="bin/open_ca
 
 
 @needs_frontend
-@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "fus10"])
+@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "fus10", "wcamix"])
 def test_frontend_translates_every_force_then_fails_loudly_without_gpu(built, tmp_path, name):
     """without a device the run must stop at ocm_context_create, i.e. after the reference's reader and generators ran
     and every OpenMM::Force they produced was recognised and translated into the C ABI (host code)"""
@@ -112,7 +112,7 @@ def test_toml11_stand_in_compiles_with_the_reference_reader():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,periodic", [("sh3", False), ("dna_3spn2", False), ("fus10", True)])
+@pytest.mark.parametrize("name,periodic", [("sh3", False), ("dna_3spn2", False), ("fus10", True), ("wcamix", False)])
 def test_frontend_writes_the_reference_files(engine, tmp_path, name, periodic):
     if not os.path.exists(BIN):
         pytest.skip("bin/open_cafemol_b200 missing: it is built by __graft_entry__.build() where the reference tree is mounted and travels with the snapshot")

@@ -394,3 +394,36 @@ def test_periodic_tiling_reproduces_the_forces(engine):
     for c in range(4):
         assert force_error(b["forces"][c * n:(c + 1) * n], a["forces"]).max() < FORCE_TOL
     assert b["potential_energy"] == pytest.approx(4.0 * a["potential_energy"], rel=1e-6)
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_wca_random(engine, oracle, periodic):
+    """Weeks-Chandler-Andersen (geometric epsilon): same kernel path as LJ-repulsive, its own coefficient table"""
+    rng = np.random.default_rng(21)
+    n = 600
+    box = np.array([6.0, 5.5, 6.5]) if periodic else None
+    g = np.stack(np.meshgrid(np.arange(8), np.arange(8), np.arange(10), indexing="ij"), -1).reshape(-1, 3)[:n]
+    pos = g * 0.62 + rng.uniform(-0.08, 0.08, (n, 3)) + 0.3
+    eps, sig = rng.uniform(0.5, 2.0, n), rng.uniform(0.5, 0.75, n)
+    eps[::17] = np.nan
+    sig[::17] = np.nan
+    has = ~np.isnan(sig)
+    two = np.sort(sig[has])[-2:]
+    rc = two.sum() * 0.5 * 2.0 ** (1.0 / 6.0)
+    excl = np.array([[i, i + 1] for i in range(0, n - 1, 3) if has[i] and has[i + 1]], np.int32)
+    part = np.nonzero(has)[0]
+
+    def make(lib):
+        s = System(lib, np.full(n, 100.0), box)
+        s.add_wca(0, rc, eps, sig, PairTopology(excl=excl, igroups=[(part, part)], periodic=periodic))
+        c = Context(s, 300.0, 0.2, 0.002, seed=5)
+        c.set_positions(pos)
+        c.set_velocities_to_temperature(300.0, 3)
+        return c
+
+    ctx, ora = make(engine), make(oracle)
+    a, b = ctx.get_state(forces=True, energy=True), ora.get_state(forces=True, energy=True)
+    assert force_error(a["forces"], b["forces"]).max() < FORCE_TOL
+    assert a["potential_energy"] == pytest.approx(b["potential_energy"], rel=ENERGY_TOL)
+    assert b["potential_energy"] > 0
+    check_sets(ctx, ora)

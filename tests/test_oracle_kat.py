@@ -204,7 +204,7 @@ def test_dna_samples_match_golden(oracle, name):
         assert ctx.da_pairs(t).tolist() == gold["da_pairs"][str(t)]
 
 
-PAIRS = ["excluded_volume", "debye_huckel", "lj_repulsive", "lj_attractive", "3spn2_excluded_volume"]
+PAIRS = ["excluded_volume", "debye_huckel", "lj_repulsive", "lj_attractive", "3spn2_excluded_volume", "wca"]
 
 
 @pytest.mark.parametrize("kind", PAIRS)
@@ -223,6 +223,8 @@ def test_pair_finite_difference(oracle, kind, periodic):
             s.add_lj_repulsive(0, 1.2, rng.uniform(0.5, 1.0, n), rng.uniform(0.4, 0.6, n), topo)
         elif kind == "lj_attractive":
             s.add_lj_attractive(0, 1.2, 1.08, rng.uniform(0.5, 1.0, n), rng.uniform(0.4, 0.6, n), topo)
+        elif kind == "wca":
+            s.add_wca(0, 0.75 * 2.0 ** (1.0 / 6.0), rng.uniform(0.5, 1.0, n), rng.uniform(0.55, 0.75, n), topo)
         else:
             s.add_3spn2_excluded_volume(0, 1.2, rng.uniform(0.8, 1.2, n), rng.uniform(0.4, 0.7, n), topo)
         # jittered lattice: no overlaps, many pairs in every zone

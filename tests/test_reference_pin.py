@@ -192,6 +192,37 @@ def test_reader_tables_match_reference_live(oracle, sample, name):
 
 
 @needs_ref
+def test_wca_reader_and_oracle_match_reference_live(oracle, tmp_path):
+    """per-particle Weeks-Chandler-Andersen: this repository's reader + oracle against the
+    reference's reader + generator on the same input"""
+    sys.path.insert(0, GOLDEN)
+    import make_ref_golden as mk
+
+    d = tomllib.loads(mk.wcamix_toml())
+    d["forcefields"][0]["global"] = [g for g in d["forcefields"][0]["global"] if "table" not in g]
+    path = tmp_path / "wca.toml"
+    path.write_text(mk.dump_toml(d))
+    rs = rb.RefLibrary().open_toml(str(path))
+    spec = ti.read_toml(str(path))
+    assert spec.group_ids == rs.group_map()
+    ctx = ti.make_context(oracle, spec)
+    rng = np.random.default_rng(2)
+    x = spec.positions + rng.normal(scale=0.03, size=spec.positions.shape)
+    rs.set_positions(x)
+    ctx.set_positions(x)
+    st = ctx.get_state(forces=True, energy=True)
+    eg = rs.energy_by_group()
+    assert eg["WeeksChandlerAndersen"] > 0
+    for k, g in spec.group_ids.items():
+        assert st["energy_by_group"][g] == pytest.approx(eg[k], rel=1e-11, abs=1e-9)
+    _, f = rs.energy(forces=True)
+    assert force_error(st["forces"], f).max() < 1e-9
+    wca_ref = [fo for fo in rs.describe()["forces"] if fo["class"] == "CustomNonbondedForce"][0]
+    wca_mine = [t for t in spec.terms if t.kind == "wca"][0]
+    assert wca_mine.args["rc"] == pytest.approx(wca_ref["cutoff"], rel=1e-14)
+
+
+@needs_ref
 def test_reference_unit_tests_pass_on_the_checker():
     """the reference's own googletest file (test/test_read_toml_ff_generator.cpp) built by `make -C oracle ref`"""
     import subprocess

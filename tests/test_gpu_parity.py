@@ -404,7 +404,8 @@ def test_wca_random(engine, oracle, periodic):
     box = np.array([6.0, 5.5, 6.5]) if periodic else None
     g = np.stack(np.meshgrid(np.arange(8), np.arange(8), np.arange(10), indexing="ij"), -1).reshape(-1, 3)[:n]
     pos = g * 0.62 + rng.uniform(-0.08, 0.08, (n, 3)) + 0.3
-    eps, sig = rng.uniform(0.5, 2.0, n), rng.uniform(0.5, 0.75, n)
+    # (a handful of distinct parameter sets, as real force fields have: the engine keys its coefficient table on them)
+    eps, sig = rng.choice([0.5, 0.9, 1.4, 2.0], n), rng.choice([0.5, 0.56, 0.62, 0.7, 0.75], n)
     eps[::17] = np.nan
     sig[::17] = np.nan
     has = ~np.isnan(sig)

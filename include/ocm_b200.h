@@ -232,7 +232,12 @@ int  ocm_slab_info(const ocm_context*, int* rank, int* world, int* axis, double*
 /* role of every bead on this rank: 0 = absent, 1 = owned, 2 = halo (all 1 without a decomposition) */
 int  ocm_get_roles(ocm_context*, unsigned char* role);
 
-/* tunables: "skin_nm" (Verlet buffer), "nstlist" (0 = adaptive), "threads_per_bead" */
+/* tunables (set_option / get_option):
+ *   "skin_nm" (Verlet buffer), "nstlist" (0 = adaptive), "threads_per_bead" (0 = auto, 4/8/16/32),
+ *   "beads_per_block" (rows per force block, 0 = auto ~ sqrt(rows)/12), "row_staging" (bulk-copy row staging, off),
+ *   "pdl" (programmatic dependent launch of the per-step kernels: 0 off, 1, 2; no gain inside CUDA graphs),
+ *   "phase_timing" (CUDA events between the phases of a step; counters "phase_ms.rebuild|force|integrate|halo"),
+ *   slab contexts: "halo_capacity", "halo_push" (1 = per-step halo over NVLink peer memory, 0 = ncclSend/ncclRecv). */
 int ocm_context_set_option(ocm_context*, const char* key, double value);
 int ocm_context_get_option(ocm_context*, const char* key, double* value);
 
@@ -275,7 +280,10 @@ int ocm_num_da_terms(const ocm_context*);
 int ocm_get_da_pairs(ocm_context*, int term, int32_t* da, int64_t capacity, int64_t* n_pairs);
 /* counters: "pair_evals_per_step" (neighbor-list entries walked), "rebuilds", "rollbacks",
  * "kernel_launches", "nstlist", "max_neighbors", "num_pair_lists", "last_step_ms" (device time of the
- * last ocm_step, CUDA events on the engine's stream), "list_cutoff_nm.<term>", "threads_per_bead.<term>" */
+ * last ocm_step, CUDA events on the engine's stream), "list_cutoff_nm.<term>", "threads_per_bead.<term>",
+ * "virtual_box_x|y|z" (unlimited boundary: the periodic box the pair kernels run in, 0 otherwise; the oracle takes it
+ * as an option of the same name so that pair sets and cell ids stay bit-exact), "virtual_box_layouts",
+ * "minimize_evaluations", "owned_beads", "halo_exchanges", "halo_message_bytes", "halo_push" (slab contexts) */
 int ocm_get_counter(ocm_context*, const char* key, double* value);
 
 /* ---- measurement hooks (bench.py; CUDA events on the engine's own stream) ------------------- */

@@ -54,3 +54,18 @@ def test_host_side_validation_without_gpu(built):
         from opencafemol_b200.capi import Context
         with pytest.raises(OcmError, match="no CUDA device"):
             Context(s, 300.0, 0.2, 0.001)
+
+
+def test_header_is_valid_c_and_links_from_c(built, tmp_path):
+    """include/ocm_b200.h compiled as C99 and linked from a C program (no torch, no C++ types at the boundary)"""
+    import subprocess
+
+    exe = tmp_path / "abi_smoke"
+    libdir = os.path.dirname(built.ENGINE_SO)
+    cmd = ["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_smoke.c"),
+           "-o", str(exe), "-L", libdir, "-locm_b200", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "abi ok" in r.stdout

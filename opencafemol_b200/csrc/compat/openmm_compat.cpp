@@ -164,6 +164,22 @@ const char* kCrossStacking =                                                  //
     "rect1tCS=step(pi/2+dtCS)*step(pi/2-dtCS);f1=1-cos(dt3)^2;f2=1-cos(dtCS)^2;dr=distance(d1,a3)-r0;dt3=K_BP*(t3-t03);dtCS=K_CS*(tCS-t0CS);"
     "tCS=angle(d2,d1,a3);t3=acos(cost3lim);cost3lim=min(max(cost3,-0.99),0.99);cost3=sin(t1)*sin(t2)*cos(phi)-cos(t1)*cos(t2);"
     "t1=angle(d2,d1,a1);t2=angle(d1,a1,a2);phi=dihedral(d2,d1,a1,a2);pi=3.1415926535897932385";
+// the *Local variants: the same energies over an explicit list of (donor, acceptor) nucleotide pairs, as compound bonds
+const char* kBasePairLocal =                                                  // ThreeSPN2BasePairLocalForceFieldGenerator.cpp:6-25
+    "rep+1/2*(1+cos(dphi))*fdt1*fdt2*attr;rep=epsilon*(1-exp(-alpha_BP*dr))^2*(1-step(dr));attr=epsilon*(1-exp(-alpha_BP*dr))^2*step(dr)-epsilon;"
+    "fdt1=max(f1*rect0t1,rect1t1);fdt2=max(f2*rect0t2,rect1t2);rect1t1=step(pi/2+dt1)*step(pi/2-dt1);rect1t2=step(pi/2+dt2)*step(pi/2-dt2);"
+    "rect0t1=step(pi+dt1)*step(pi-dt1);rect0t2=step(pi+dt2)*step(pi-dt2);f1=1-cos(dt1)^2;f2=1-cos(dt2)^2;dphi=dihedral(p1,p2,p3,p4)-phi0;"
+    "dr=distance(p2,p3)-r0;dt1=K_BP*(angle(p1,p2,p3)-t01);dt2=K_BP*(angle(p4,p3,p2)-t02);pi=3.1415926535897932385";
+const char* kCrossStackingLocal =                                             // ThreeSPN2CrossStackingLocalForceFieldGenerator.cpp:6-30
+    "fdt3*fdtCS*attr/2;attr=epsilon*(1-exp(-alpha_CS*dr))^2*step(dr)-epsilon;fdt3=max(f1*rect0t3,rect1t3);fdtCS=max(f2*rect0tCS,rect1tCS);"
+    "rect0t3=step(pi+dt3)*step(pi-dt3);rect0tCS=step(pi+dtCS)*step(pi-dtCS);rect1t3=step(pi/2+dt3)*step(pi/2-dt3);"
+    "rect1tCS=step(pi/2+dtCS)*step(pi/2-dtCS);f1=1-cos(dt3)^2;f2=1-cos(dtCS)^2;dr=distance(p2,p6)-r0;dt3=K_BP*(t3-t03);dtCS=K_CS*(tCS-t0CS);"
+    "tCS=angle(p1,p2,p6);t3=acos(cost3lim);cost3lim=min(max(cost3,-0.99),0.99);cost3=sin(t1)*sin(t2)*cos(phi)-cos(t1)*cos(t2);"
+    "t1=angle(p1,p2,p3);t2=angle(p2,p3,p4);phi=dihedral(p1,p2,p3,p4);pi=3.1415926535897932385";
+// Range inside which the *Local pairs are evaluated.  The compound bonds have no cutoff, but their energy beyond
+// r0 + 1.9 nm is below eps * 2 exp(-alpha * 1.9 nm) < 1e-15 kJ/mol (alpha >= 20 / nm): nothing is lost at double precision.
+constexpr double kLocalPairRange = 2.5;
+
 const char* kPDNS =                                                           // ProteinDNANonSpecificForceFieldGenerator.cpp:60-83
     "-k*f_r*g_theta*g_phi;f_r=exp(-dr^2/(2*sigma*sigma));g_theta=max(g1*rect0t,rect1t);g_phi=max(g2*rect0p,rect1p);"
     "rect0t=step(pi+dtheta)*step(pi-dtheta);rect1t=step(pi/2+dtheta)*step(pi/2-dtheta);rect0p=step(pi+dphi)*step(pi-dphi);"
@@ -362,6 +378,33 @@ class SystemCompiler {
             const auto ijk = indices(f.rows_, 3);
             check(ocm_system_add_3spn2_base_stacking(out_, g, f.periodic_, n, ijk.data(), column(f.rows_, 0).data(), column(f.rows_, 1).data(), column(f.rows_, 2).data(),
                                                      uniform(f.rows_, 3, "3SPN2BaseStacking alpha"), uniform(f.rows_, 4, "3SPN2BaseStacking K_BS")), "3SPN2BaseStacking");
+        } else if ((nz.expr == kBasePairLocal && f.np_ == 4) || (nz.expr == kCrossStackingLocal && f.np_ == 6)) {
+            // explicit nucleotide pairs = a donor-acceptor term in which bond i contributes donor i and acceptor i and every
+            // other combination is excluded
+            const bool bp = f.np_ == 4;
+            if (bp) expect_names(nz.params, {"epsilon", "r0", "t01", "t02", "phi0", "alpha_BP", "K_BP"}, "3SPN2BasePairLocal");
+            else expect_names(nz.params, {"epsilon", "r0", "t03", "t0CS", "K_BP", "K_CS", "alpha_CS"}, "3SPN2CrossStackingLocal");
+            std::vector<std::int32_t> donors, acceptors, excl;
+            for (auto& r : f.rows_) {
+                // base pair: (p1, p2, p3, p4) = (sugar_d, base_d, base_a, sugar_a); cross stacking adds p6 = the cross base
+                donors.insert(donors.end(), {r.p[1], r.p[0], -1});
+                acceptors.insert(acceptors.end(), {r.p[2], r.p[3], bp ? -1 : r.p[5]});
+            }
+            for (std::int32_t d = 0; d < (std::int32_t)n; d++)
+                for (std::int32_t a = 0; a < (std::int32_t)n; a++)
+                    if (a != d) { excl.push_back(d); excl.push_back(a); }
+            ocm_da_topology t{};
+            t.n_donors = n; t.donors = donors.data(); t.n_acceptors = n; t.acceptors = acceptors.data();
+            t.n_excl = (std::int64_t)excl.size() / 2; t.excl_da = excl.data();
+            t.cutoff = kLocalPairRange;
+            t.periodic = f.periodic_;
+            if (bp)
+                check(ocm_system_add_3spn2_base_pair(out_, g, &t, column(f.rows_, 0).data(), column(f.rows_, 1).data(), column(f.rows_, 2).data(), column(f.rows_, 3).data(),
+                                                     column(f.rows_, 4).data(), uniform(f.rows_, 5, "3SPN2BasePairLocal alpha_BP"), uniform(f.rows_, 6, "3SPN2BasePairLocal K_BP")), "3SPN2BasePairLocal");
+            else
+                check(ocm_system_add_3spn2_cross_stacking(out_, g, &t, column(f.rows_, 0).data(), column(f.rows_, 1).data(), column(f.rows_, 2).data(), column(f.rows_, 3).data(),
+                                                          uniform(f.rows_, 4, "3SPN2CrossStackingLocal K_BP"), uniform(f.rows_, 5, "3SPN2CrossStackingLocal K_CS"),
+                                                          uniform(f.rows_, 6, "3SPN2CrossStackingLocal alpha_CS")), "3SPN2CrossStackingLocal");
         } else {
             unsupported("CustomCompoundBondForce", f);
         }

@@ -143,13 +143,16 @@ def main():
     samples = {"sh3": open(os.path.join(REF, "sh3_AICG2+.toml")).read(),
                "dna_3spn2": open(os.path.join(REF, "dna_3SPN2.toml")).read(),
                "nucleosome": open(os.path.join(REF, "nucleosome_1kx5.toml")).read(),
-               "fus10": fus_subset(10), "wcamix": wcamix_toml()}
+               "fus10": fus_subset(10), "wcamix": wcamix_toml(),
+               # 3SPN2BasePairLocal / 3SPN2CrossStackingLocal (explicit nucleotide pairs as compound bonds)
+               "dna_localize": open(os.path.join(REF, "dna_3SPN2_localize.toml")).read()}
     for name, text in samples.items():
         path = os.path.join(tmp, name + ".toml")
         with open(path, "w") as fh:
             fh.write(text)
         rs = R.open_toml(path)
-        spec = ti.read_toml(path) if name != "wcamix" else None  # (table forms are read by the reference's reader only)
+        # (the name-pair table forms and the *Local forms are read by the reference's reader only)
+        spec = ti.read_toml(path) if name not in ("wcamix", "dna_localize") else None
         out = {"source": name, "n": rs.n, "group_map": rs.group_map(), "integrator": rs.integrator()}
         if name == "fus10":
             rs.minimize(tolerance=10.0, max_iterations=400)
@@ -176,7 +179,7 @@ def main():
         out["trajectory"] = {"steps": nst, "positions": rs.positions().tolist(), "velocities": rs.velocities().tolist()}
         rs.close()
         # what the reference's own main program writes
-        if name in ("sh3", "dna_3spn2", "fus10", "wcamix"):
+        if name in ("sh3", "dna_3spn2", "fus10", "wcamix", "dna_localize"):
             files = {}
             for fmt in ("pdb", "dcd"):
                 wd = os.path.join(tmp, name + "_" + fmt)
@@ -189,7 +192,9 @@ def main():
                     d["systems"][0]["vel_seed"] = 2026  # the sample has neither velocities nor a seed: make the run reproducible
                     text_run = dump_toml(d)
                 elif spec is None:
-                    text_run = text
+                    d = tomllib.loads(text)
+                    d["systems"][0].setdefault("vel_seed", 2026)
+                    text_run = dump_toml(d)
                 elif spec.velocities is None:
                     # neither velocities nor a velocity seed in the sample: make the program run reproducible
                     d = tomllib.loads(text)

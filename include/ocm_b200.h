@@ -72,6 +72,12 @@ int ocm_system_add_gaussian_bond(ocm_system*, int group, int periodic, int64_t n
 /* E = k (5 (r0/r)^12 - 6 (r0/r)^10)       GoContactForceFieldGenerator.cpp:3-20 */
 int ocm_system_add_go_contact(ocm_system*, int group, int periodic, int64_t n,
                               const int32_t* ij, const double* k, const double* r0);
+/* Go contact with a linear cap at short range: for r/r0 <= cap  E = k (slope r/r0 + intercept), else as above
+ * (slope, intercept: the tangent of the 12-10 curve at r = cap r0, as the generator computes them)
+ *                                         CappedGoContactForceFieldGenerator.cpp:3-30 */
+int ocm_system_add_capped_go_contact(ocm_system*, int group, int periodic, int64_t n, const int32_t* ij,
+                                     const double* k, const double* r0, const double* slope,
+                                     const double* intercept, const double* cap);
 /* E = k2 (r-r0)^2 + k4 (r-r0)^4           ThreeSPN2BondForceFieldGenerator.cpp:3-25
  * (the reference passes k4 = 100*k_4th; give the final coefficient here) */
 int ocm_system_add_3spn2_bond(ocm_system*, int group, int periodic, int64_t n,

@@ -139,6 +139,7 @@ class Library:
         "system_add_harmonic_bond": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p]),
         "system_add_gaussian_bond": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p, _f64p]),
         "system_add_go_contact": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p]),
+        "system_add_capped_go_contact": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p, _f64p, _f64p, _f64p]),
         "system_add_3spn2_bond": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p, _f64p]),
         "system_add_harmonic_angle": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p]),
         "system_add_flexible_local_angle": (
@@ -317,6 +318,9 @@ class System:
 
     def add_go_contact(self, group, ij, k, r0, periodic=False):
         self._bonded("system_add_go_contact", group, periodic, ij, 2, _f64(k), _f64(r0))
+
+    def add_capped_go_contact(self, group, ij, k, r0, slope, intercept, cap, periodic=False):
+        self._bonded("system_add_capped_go_contact", group, periodic, ij, 2, _f64(k), _f64(r0), _f64(slope), _f64(intercept), _f64(cap))
 
     def add_3spn2_bond(self, group, ij, k2, k4, r0, periodic=False):
         self._bonded("system_add_3spn2_bond", group, periodic, ij, 2, _f64(k2), _f64(k4), _f64(r0))

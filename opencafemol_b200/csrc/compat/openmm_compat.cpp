@@ -120,6 +120,9 @@ void replace_all(std::string& s, const std::string& from, const std::string& to)
 
 // expressions emitted by the reference's generators, normalised
 const char* kGoContact = "k*(5*(r0/r)^12-6*(r0/r)^10)";                       // GoContactForceFieldGenerator.cpp:5-18
+const char* kCappedGoContact =                                                // CappedGoContactForceFieldGenerator.cpp:5-9
+    "cap_val*cap_formula+(1-cap_val)*lj_formula;cap_formula=k*slope/roverdist+k*intercept;lj_formula=k*(5*roverdist^12-6*roverdist^10);"
+    "cap_val=step(cap-1/roverdist);roverdist=r0/r";
 const char* kGaussianBond = "k*exp(-(r-v0)^2/(2*sigma^2))";                   // GaussianBondForceFieldGenerator.cpp:5-21
 const char* k3SPN2Bond = "k2*(r-v0)^2+100.0*k4*(r-v0)^4";                     // ThreeSPN2BondForceFieldGenerator.cpp:5-20
 const char* kFLA =                                                            // FlexibleLocalAngleForceFieldGenerator.cpp:21-27
@@ -306,6 +309,10 @@ class SystemCompiler {
         if (nz.expr == kGoContact) {
             expect_names(nz.params, {"k", "r0"}, "GoContact");
             check(ocm_system_add_go_contact(out_, g, f.periodic_, n, ij.data(), column(f.rows_, 0).data(), column(f.rows_, 1).data()), "GoContact");
+        } else if (nz.expr == kCappedGoContact) {
+            expect_names(nz.params, {"k", "r0", "slope", "intercept", "cap"}, "CappedGoContact");
+            check(ocm_system_add_capped_go_contact(out_, g, f.periodic_, n, ij.data(), column(f.rows_, 0).data(), column(f.rows_, 1).data(), column(f.rows_, 2).data(),
+                                                   column(f.rows_, 3).data(), column(f.rows_, 4).data()), "CappedGoContact");
         } else if (nz.expr == kGaussianBond) {
             expect_names(nz.params, {"k", "v0", "sigma"}, "GaussianBond");
             check(ocm_system_add_gaussian_bond(out_, g, f.periodic_, n, ij.data(), column(f.rows_, 0).data(), column(f.rows_, 1).data(), column(f.rows_, 2).data()), "GaussianBond");

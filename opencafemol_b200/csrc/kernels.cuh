@@ -1210,9 +1210,15 @@ __device__ __forceinline__ void bonded_eval(int kind, const double* __restrict__
             const double d = q - p[1], is2 = 1.0 / (p[2] * p[2]);
             E = p[0] * exp(-0.5 * d * d * is2); dE = -E * d * is2;
         } break;
-        case 2: {  // GoContact     p = k, r0          GoContactForceFieldGenerator.cpp:5-7
-            const double s = p[1] / q, s2 = s * s, s4 = s2 * s2, s10 = s4 * s4 * s2, s12 = s10 * s2;
-            E = p[0] * (5.0 * s12 - 6.0 * s10); dE = p[0] * 60.0 * (s10 - s12) / q;
+        case 2: {  // GoContact     p = k, r0, slope, intercept, cap   GoContactForceFieldGenerator.cpp:5-7,
+                   // CappedGoContactForceFieldGenerator.cpp:5-9 (cap = 0: plain contact; step(cap - r/r0) selects the line)
+            const double u = q / p[1];
+            if (p[4] - u >= 0.0) {
+                E = p[0] * (p[2] * u + p[3]); dE = p[0] * p[2] / p[1];
+            } else {
+                const double s = p[1] / q, s2 = s * s, s4 = s2 * s2, s10 = s4 * s4 * s2, s12 = s10 * s2;
+                E = p[0] * (5.0 * s12 - 6.0 * s10); dE = p[0] * 60.0 * (s10 - s12) / q;
+            }
         } break;
         case 3: {  // 3SPN2Bond     p = k2, k4, r0     ThreeSPN2BondForceFieldGenerator.cpp:5-10
             const double d = q - p[2], d2 = d * d;

@@ -1271,8 +1271,16 @@ int ocm_system_add_harmonic_bond(ocm_system* s, int g, int per, int64_t n, const
 int ocm_system_add_gaussian_bond(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* k, const double* r0, const double* sigma) {
     return add_bonded(s, B_GAUSSIAN_BOND, g, per, n, ij, {k, r0, sigma}, "gaussian_bond");
 }
+// (Go contacts carry five parameters k, r0, slope, intercept, cap; cap = 0 is the plain 12-10 contact)
 int ocm_system_add_go_contact(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* k, const double* r0) {
-    return add_bonded(s, B_GO_CONTACT, g, per, n, ij, {k, r0}, "go_contact");
+    if (n < 0) return fail("go_contact: negative count");
+    const std::vector<double> zero((size_t)std::max<int64_t>(n, 1), 0.0);
+    return add_bonded(s, B_GO_CONTACT, g, per, n, ij, {k, r0, zero.data(), zero.data(), zero.data()}, "go_contact");
+}
+int ocm_system_add_capped_go_contact(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* k, const double* r0,
+                                     const double* slope, const double* intercept, const double* cap) {
+    if (!slope || !intercept || !cap) return fail("capped_go_contact: null argument");
+    return add_bonded(s, B_GO_CONTACT, g, per, n, ij, {k, r0, slope, intercept, cap}, "capped_go_contact");
 }
 int ocm_system_add_3spn2_bond(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* k2, const double* k4, const double* r0) {
     return add_bonded(s, B_3SPN2_BOND, g, per, n, ij, {k2, k4, r0}, "3spn2_bond");

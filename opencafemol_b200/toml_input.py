@@ -436,6 +436,19 @@ def _read_local(spec, lf, topo, periodic):
         r0 = [_param(p, env, "v0") * NM_PER_ANGSTROM for p in params]
         add_topology(idx)
         spec.add_term(Term("go_contact", "GoContact", dict(ij=idx, k=k, r0=r0, periodic=periodic)))
+    elif inter == "BondLength" and pot == "CappedGoContact":
+        # read_toml_capped_go_contact_ff_generator (ReadTOMLForceFieldGenerator.cpp:226-275) and the generator's tangent
+        # (CappedGoContactForceFieldGenerator.cpp:19-20)
+        cap = float(lf.get("capping_ratio", 0.75))
+        idx = [_indices(p, env, 2, "read_toml_capped_go_contact_ff_generator", n) for p in params]
+        k = [_param(p, env, "k") * KJ_PER_KCAL for p in params]
+        r0 = [_param(p, env, "v0") * NM_PER_ANGSTROM for p in params]
+        slope = -60.0 * ((1.0 / cap) ** 13.0 - (1.0 / cap) ** 11.0)
+        intercept = 65.0 * (1.0 / cap) ** 12.0 - 66.0 * (1.0 / cap) ** 10.0
+        add_topology(idx)
+        m = len(idx)
+        spec.add_term(Term("capped_go_contact", "CappedGoContact",
+                           dict(ij=idx, k=k, r0=r0, slope=[slope] * m, intercept=[intercept] * m, cap=[cap] * m, periodic=periodic)))
     elif inter == "BondLength" and pot == "3SPN2Bond":
         idx = [_indices(p, env, 2, "read_toml_3spn2_bond_ff_generator", n) for p in params]
         r0 = [_param(p, env, "v0") * NM_PER_ANGSTROM for p in params]

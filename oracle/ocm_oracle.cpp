@@ -191,10 +191,16 @@ inline void bond_like(const BondedTerm& t, int64_t m, double r, double* E, doubl
             double e = p[0] * std::exp(-d * d / (2.0 * p[2] * p[2]));
             *E = e; *dEdr = -e * d / (p[2] * p[2]);
         } break;
-        case B_GO_CONTACT: {  // p = k, r0     GoContactForceFieldGenerator.cpp:5-7
-            double s = p[1] / r, s2 = s * s, s10 = s2 * s2 * s2 * s2 * s2, s12 = s10 * s2;
-            *E = p[0] * (5.0 * s12 - 6.0 * s10);
-            *dEdr = p[0] * 60.0 * (s10 - s12) / r;
+        case B_GO_CONTACT: {  // p = k, r0, slope, intercept, cap     GoContactForceFieldGenerator.cpp:5-7;
+                              // CappedGoContactForceFieldGenerator.cpp:5-9: cap_val = step(cap - r/r0) selects the linear cap
+            if (p[4] - r / p[1] >= 0.0) {
+                *E = p[0] * p[2] * (r / p[1]) + p[0] * p[3];
+                *dEdr = p[0] * p[2] / p[1];
+            } else {
+                double s = p[1] / r, s2 = s * s, s10 = s2 * s2 * s2 * s2 * s2, s12 = s10 * s2;
+                *E = p[0] * (5.0 * s12 - 6.0 * s10);
+                *dEdr = p[0] * 60.0 * (s10 - s12) / r;
+            }
         } break;
         case B_3SPN2_BOND: {  // p = k2, k4, r0  ThreeSPN2BondForceFieldGenerator.cpp:5-10
             double d = r - p[2], d2 = d * d;
@@ -952,7 +958,12 @@ int oracle_system_add_gaussian_bond(ocm_system* s, int g, int per, int64_t n, co
     return add_bonded(s, B_GAUSSIAN_BOND, g, per, 2, n, ij, 3, {k, r0, sigma}, "gaussian_bond");
 }
 int oracle_system_add_go_contact(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* k, const double* r0) {
-    return add_bonded(s, B_GO_CONTACT, g, per, 2, n, ij, 2, {k, r0}, "go_contact");
+    const std::vector<double> zero((size_t)std::max<int64_t>(n, 1), 0.0);
+    return add_bonded(s, B_GO_CONTACT, g, per, 2, n, ij, 5, {k, r0, zero.data(), zero.data(), zero.data()}, "go_contact");
+}
+int oracle_system_add_capped_go_contact(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* k, const double* r0,
+                                        const double* slope, const double* intercept, const double* cap) {
+    return add_bonded(s, B_GO_CONTACT, g, per, 2, n, ij, 5, {k, r0, slope, intercept, cap}, "capped_go_contact");
 }
 int oracle_system_add_3spn2_bond(ocm_system* s, int g, int per, int64_t n, const int32_t* ij, const double* k2, const double* k4, const double* r0) {
     return add_bonded(s, B_3SPN2_BOND, g, per, 2, n, ij, 3, {k2, k4, r0}, "3spn2_bond");

@@ -222,9 +222,9 @@ def main():
 
 
 def wcamix_toml():
-    """a small synthetic system for the potentials of SURVEY.md 8f rank 4 that share the two-zone 12-6 kernel: per-particle
-    WCA, name-pair table WCA (UniformWeeksChandlerAndersen) and name-pair table LennardJonesAttractive
-    (UniformLennardJonesAttractive), 4 chains of 12 beads, unlimited boundary"""
+    """a small synthetic system for the potentials of SURVEY.md 8f rank 4: per-particle WCA, name-pair table WCA
+    (UniformWeeksChandlerAndersen), name-pair table LennardJonesAttractive (UniformLennardJonesAttractive), capped Go
+    contacts; 4 chains of 12 beads, unlimited boundary"""
     rng = np.random.default_rng(7)
     nch, L = 4, 12
     n = nch * L
@@ -243,7 +243,10 @@ def wcamix_toml():
                       "save_step": 10, "seed": 777, "integrator": {"type": "BAOABLangevin", "gammas": []}},
         "systems": [{"attributes": {"temperature": 300.0}, "vel_seed": 2026, "particles": particles}],
         "forcefields": [{
-            "local": [{"interaction": "BondLength", "potential": "Harmonic", "topology": "bond", "parameters": bonds}],
+            "local": [{"interaction": "BondLength", "potential": "Harmonic", "topology": "bond", "parameters": bonds},
+                      # contacts between chains: with v0 = 7.5 or 9.5 A and neighbours 5.6 A apart, some sit on the linear cap (r/v0 <= 0.75)
+                      {"interaction": "BondLength", "potential": "CappedGoContact", "topology": "contact", "capping_ratio": 0.75,
+                       "parameters": [{"indices": [i, i + L], "v0": 7.5 + 2.0 * (i % 2), "k": 0.3} for i in range(0, n - L, 2)]}],
             "global": [
                 {"interaction": "Pair", "potential": "WCA", "ignore": {"particles_within": {"bond": 1}},
                  "parameters": [{"index": i, "sigma": 4.6 + 0.2 * (i % 4), "epsilon": 0.3 + 0.05 * (i % 3)} for i in range(0, n, 2)]},

@@ -428,3 +428,32 @@ def test_wca_random(engine, oracle, periodic):
     assert a["potential_energy"] == pytest.approx(b["potential_energy"], rel=ENERGY_TOL)
     assert b["potential_energy"] > 0
     check_sets(ctx, ora)
+
+
+def test_capped_go_contact(engine, oracle):
+    """Go contacts with the linear short-range cap (CappedGoContactForceFieldGenerator): both branches, against the oracle"""
+    rng = np.random.default_rng(8)
+    n = 40
+    pos = np.cumsum(rng.normal(scale=0.22, size=(n, 3)), axis=0) + 5.0
+    ij = np.array([[i, j] for i in range(n) for j in range(i + 3, n, 5)], np.int32)
+    r = np.linalg.norm(pos[ij[:, 0]] - pos[ij[:, 1]], axis=1)
+    r0 = r * rng.choice([0.8, 1.0, 1.2, 1.6, 2.0], len(ij))  # r/r0 from 0.5 (on the cap) to 1.25
+    cap = 0.75
+    slope, icpt = -60 * (cap ** -13 - cap ** -11), 65 * cap ** -12 - 66 * cap ** -10
+    assert ((r / r0) <= cap).any() and ((r / r0) > cap).any()
+
+    def make(lib):
+        s = System(lib, np.full(n, 100.0), None)
+        s.add_capped_go_contact(0, ij, rng_k, r0, np.full(len(ij), slope), np.full(len(ij), icpt), np.full(len(ij), cap))
+        s.add_go_contact(1, ij[::3], rng_k[::3], r0[::3])
+        c = Context(s, 300.0, 0.2, 0.002, seed=5)
+        c.set_positions(pos)
+        c.set_velocities_to_temperature(300.0, 3)
+        return c
+
+    rng_k = rng.uniform(0.3, 1.5, len(ij))
+    ctx, ora = make(engine), make(oracle)
+    a, b = ctx.get_state(forces=True, energy=True), ora.get_state(forces=True, energy=True)
+    assert force_error(a["forces"], b["forces"]).max() < FORCE_TOL
+    for g in (0, 1):
+        assert a["energy_by_group"][g] == pytest.approx(b["energy_by_group"][g], rel=ENERGY_TOL)

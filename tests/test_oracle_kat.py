@@ -73,7 +73,7 @@ def _chain(n, rng, bond=0.38):
 
 
 BONDED = ["harmonic_bond", "gaussian_bond", "go_contact", "3spn2_bond", "harmonic_angle", "flexible_local_angle",
-          "gaussian_dihedral", "cosine_dihedral", "flexible_local_dihedral"]
+          "gaussian_dihedral", "cosine_dihedral", "flexible_local_dihedral", "capped_go_contact"]
 
 
 @pytest.mark.parametrize("kind", BONDED)
@@ -94,6 +94,12 @@ def test_bonded_finite_difference(oracle, kind, periodic):
             s.add_gaussian_bond(0, ij, -rng.uniform(1, 5, m2), rng.uniform(0.3, 0.5, m2), rng.uniform(0.05, 0.2, m2), periodic)
         elif kind == "go_contact":
             s.add_go_contact(0, ij, rng.uniform(0.5, 2, m2), rng.uniform(0.3, 0.45, m2), periodic)
+        elif kind == "capped_go_contact":
+            # bonds are 0.38 nm: with r0 in 0.4..0.6 some contacts sit on the linear cap (r/r0 <= 0.75), the others on the 12-10 curve
+            cap = 0.75
+            slope, icpt = -60 * (cap ** -13 - cap ** -11), 65 * cap ** -12 - 66 * cap ** -10
+            s.add_capped_go_contact(0, ij, rng.uniform(0.5, 2, m2), np.array([0.4, 0.6, 0.45, 0.55, 0.42])[:m2], np.full(m2, slope), np.full(m2, icpt),
+                                    np.full(m2, cap), periodic)
         elif kind == "3spn2_bond":
             s.add_3spn2_bond(0, ij, rng.uniform(100, 300, m2), rng.uniform(1e4, 3e4, m2), rng.uniform(0.3, 0.45, m2), periodic)
         elif kind == "harmonic_angle":

@@ -119,8 +119,10 @@ def cpu_port_run(spec, md_steps, threads=None):
     g.build_oracle()
     lib = Library(g.ORACLE_SO, "oracle_")
     ctx = toml_input.make_context(lib, spec)
-    if threads:
-        ctx.set_option("threads", threads)
+    # all host cores this process may run on: torchrun exports OMP_NUM_THREADS=1 to its workers, which would time the
+    # CPU arm on one thread although rank 0 is the only rank that runs it (OCM_CPU_THREADS overrides)
+    threads = threads or int(os.environ.get("OCM_CPU_THREADS", "0")) or len(os.sched_getaffinity(0))
+    ctx.set_option("threads", threads)
     cores = int(ctx.get_option("threads"))
     ctx.step(1)
     t0 = time.perf_counter()

@@ -8,7 +8,8 @@ from conftest import ROOT
 
 
 def test_reference_arm_prints_one_contract_line(built):
-    env = dict(os.environ, OMP_NUM_THREADS=str(min(8, os.cpu_count() or 1)))
+    # OMP_NUM_THREADS=1 is what torchrun exports to its workers: the CPU arm must still use every core it may run on
+    env = dict(os.environ, OMP_NUM_THREADS="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -17,7 +18,7 @@ def test_reference_arm_prints_one_contract_line(built):
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "ns/day" and d["unit"] == "ns/day" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None and d["data"] == "synthetic"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["config"]["beads"] == 16300
     assert "model" not in d["config"]

@@ -325,6 +325,9 @@ void eval_bonded(const ocm_context& c, const BondedTerm& t, std::vector<Vec3>* F
 
 // ------------------------------------------------------------------------------------------------
 // pair potentials: E(r) and dE/dr for one pair of term t (r < rc, not excluded, groups allowed)
+inline double pow6(double x) { double x2 = x * x; return x2 * x2 * x2; }
+static const double kTwoSixth = std::pow(2.0, 1.0 / 6.0);
+
 inline void pair_energy(const PairTerm& t, int i, int j, double r, double* E, double* dEdr) {
     switch (t.kind) {
         case P_EXV: {  // ExcludedVolumeForceFieldGenerator.cpp:25-27; g0 = eps, g1 = rc^-12
@@ -341,28 +344,28 @@ inline void pair_energy(const PairTerm& t, int i, int j, double r, double* E, do
         } break;
         case P_LJREP: {  // LennardJonesRepulsiveForceFieldGenerator.cpp:35-43; p0 = eps, p1 = sigma
             double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = 0.5 * (t.p0[i] + t.p0[j]);
-            double th = sg * std::pow(2.0, 1.0 / 6.0);
+            double th = sg * kTwoSixth;
             if (th - r >= 0.0) {
-                double sr = sg / r, s6 = std::pow(sr, 6), s12 = s6 * s6;
+                double sr = sg / r, s6 = pow6(sr), s12 = s6 * s6;
                 *E = ep * (4.0 * (s12 - s6) + 1.0);
                 *dEdr = ep * 4.0 * (-12.0 * s12 + 6.0 * s6) / r;
             } else { *E = 0; *dEdr = 0; }
         } break;
         case P_WCA: {  // WeeksChandlerAndersenForceFieldGenerator.cpp:34-41; p0 = eps (geometric mean), p1 = sigma
             double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = std::sqrt(t.p0[i] * t.p0[j]);
-            double th = sg * std::pow(2.0, 1.0 / 6.0);
+            double th = sg * kTwoSixth;
             if (th - r >= 0.0) {
-                double sr = sg / r, s6 = std::pow(sr, 6), s12 = s6 * s6;
+                double sr = sg / r, s6 = pow6(sr), s12 = s6 * s6;
                 *E = 4.0 * ep * (s12 - s6) + ep;
                 *dEdr = ep * 4.0 * (-12.0 * s12 + 6.0 * s6) / r;
             } else { *E = 0; *dEdr = 0; }
         } break;
         case P_LJATT: {  // LennardJonesAttractiveForceFieldGenerator.cpp:40-50 (+ switch :113-115)
             double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = 0.5 * (t.p0[i] + t.p0[j]);
-            double th = sg * std::pow(2.0, 1.0 / 6.0);
+            double th = sg * kTwoSixth;
             double e = 0, de = 0;
             if (r - th >= 0.0) {
-                double sr = sg / r, s6 = std::pow(sr, 6), s12 = s6 * s6;
+                double sr = sg / r, s6 = pow6(sr), s12 = s6 * s6;
                 e += ep * 4.0 * (s12 - s6);
                 de += ep * 4.0 * (-12.0 * s12 + 6.0 * s6) / r;
             }
@@ -380,7 +383,7 @@ inline void pair_energy(const PairTerm& t, int i, int j, double r, double* E, do
         case P_3SPN2EXV: {  // ThreeSPN2ExcludedVolumeForceFieldGenerator.cpp:21-26
             double sg = 0.5 * (t.p1[i] + t.p1[j]), ep = std::sqrt(t.p0[i] * t.p0[j]);
             if (sg - r >= 0.0) {
-                double sr = sg / r, s6 = std::pow(sr, 6), s12 = s6 * s6;
+                double sr = sg / r, s6 = pow6(sr), s12 = s6 * s6;
                 *E = ep * (s12 - 2.0 * s6) + ep;
                 *dEdr = ep * (-12.0 * s12 + 12.0 * s6) / r;
             } else { *E = 0; *dEdr = 0; }
@@ -515,22 +518,31 @@ void for_each_pair(const ocm_context& c, const PairTerm& t, double rc, bool para
         }
         return;
     }
-    // bin
+    // bin; beads are copied in cell order (wrapped into the box when periodic) so that a cell's candidates are
+    // contiguous, and the image of a neighbour cell is a constant shift per cell pair (cell width >= rc and
+    // >= 3 cells per periodic axis: the pair found through adjacent cells is the minimum image)
     int64_t ncell = (int64_t)nc[0] * nc[1] * nc[2];
-    std::vector<int> cell_of(np), count(ncell + 1, 0), order(np);
+    std::vector<int> cell_of(np), count(ncell + 1, 0), ids(np);
+    std::vector<Vec3> xw(np), xs(np);
     for (int a = 0; a < np; a++) {
         const double* xi = &c.x[t.part[a]].x;
         int ci[3];
+        double u[3];
         for (int k = 0; k < 3; k++) {
-            double u = per ? (xi[k] - box[k] * std::floor(xi[k] / box[k])) : (xi[k] - lo[k]);
-            ci[k] = std::max(0, std::min(nc[k] - 1, (int)std::floor(u / w[k])));
+            u[k] = per ? (xi[k] - box[k] * std::floor(xi[k] / box[k])) : xi[k];
+            ci[k] = std::max(0, std::min(nc[k] - 1, (int)std::floor((per ? u[k] : u[k] - lo[k]) / w[k])));
         }
+        xw[a] = Vec3{u[0], u[1], u[2]};
         cell_of[a] = (ci[2] * nc[1] + ci[1]) * nc[0] + ci[0];
         count[cell_of[a] + 1]++;
     }
     for (int64_t k = 0; k < ncell; k++) count[k + 1] += count[k];
     std::vector<int> cursor(count.begin(), count.end() - 1);
-    for (int a = 0; a < np; a++) order[cursor[cell_of[a]]++] = a;
+    for (int a = 0; a < np; a++) {
+        int slot = cursor[cell_of[a]]++;
+        ids[slot] = t.part[a];
+        xs[slot] = xw[a];
+    }
 #pragma omp parallel for schedule(dynamic, 4) if (parallel)
     for (int64_t cidx = 0; cidx < ncell; cidx++) {
         int cx = cidx % nc[0], cy = (cidx / nc[0]) % nc[1], cz = cidx / ((int64_t)nc[0] * nc[1]);
@@ -538,20 +550,23 @@ void for_each_pair(const ocm_context& c, const PairTerm& t, double rc, bool para
             for (int dy = -1; dy <= 1; dy++)
                 for (int dx = -1; dx <= 1; dx++) {
                     int ox = cx + dx, oy = cy + dy, oz = cz + dz;
+                    Vec3 shift{0, 0, 0};  // position of the neighbour cell's image relative to its wrapped copy
                     if (per) {
-                        ox = (ox + nc[0]) % nc[0]; oy = (oy + nc[1]) % nc[1]; oz = (oz + nc[2]) % nc[2];
+                        if (ox < 0) { ox += nc[0]; shift.x = -box[0]; } else if (ox >= nc[0]) { ox -= nc[0]; shift.x = box[0]; }
+                        if (oy < 0) { oy += nc[1]; shift.y = -box[1]; } else if (oy >= nc[1]) { oy -= nc[1]; shift.y = box[1]; }
+                        if (oz < 0) { oz += nc[2]; shift.z = -box[2]; } else if (oz >= nc[2]) { oz -= nc[2]; shift.z = box[2]; }
                     } else if (ox < 0 || oy < 0 || oz < 0 || ox >= nc[0] || oy >= nc[1] || oz >= nc[2]) continue;
                     int64_t oidx = ((int64_t)oz * nc[1] + oy) * nc[0] + ox;
                     if (oidx < cidx) continue;  // each unordered cell pair once (nc>=3 => no aliasing)
                     for (int ua = count[cidx]; ua < count[cidx + 1]; ua++) {
-                        int a = order[ua], i = t.part[a];
+                        const int i = ids[ua];
+                        const Vec3 xi = xs[ua] - shift;
                         int vb0 = (oidx == cidx) ? ua + 1 : count[oidx];
                         for (int vb = vb0; vb < count[oidx + 1]; vb++) {
-                            int b = order[vb], j = t.part[b];
-                            Vec3 d = c.x[i] - c.x[j];
-                            if (per) d = min_image(d, box);
+                            Vec3 d = xi - xs[vb];
                             double r2 = dot(d, d);
                             if (r2 < rc2) {
+                                const int j = ids[vb];
                                 if (i < j) fn(i, j, d, std::sqrt(r2));
                                 else fn(j, i, d * -1.0, std::sqrt(r2));
                             }

@@ -252,6 +252,17 @@ def test_cell_list_matches_brute_force(oracle):
     p1 = ctx.neighbor_pairs(1)
     ctx.set_option("brute_force", 1)
     assert np.array_equal(p1, ctx.neighbor_pairs(1))
+    # unwrapped master positions (beads that left the box by whole periods): the cell path wraps and shifts per
+    # cell pair, the brute-force path takes nearbyint minimum images; same forces as before the shift
+    rng = np.random.default_rng(4)
+    x = ctx.get_state(positions=True)["positions"]
+    ctx.set_positions(x + rng.integers(-2, 3, x.shape) * np.asarray(spec.box))
+    ctx.set_option("brute_force", 0)
+    c = ctx.get_state(forces=True, energy=True)
+    ctx.set_option("brute_force", 1)
+    d = ctx.get_state(forces=True, energy=True)
+    assert np.abs(c["forces"] - d["forces"]).max() < 1e-8 and np.abs(c["forces"] - a["forces"]).max() < 1e-7
+    assert np.allclose(c["energy_by_group"], d["energy_by_group"], rtol=1e-11, atol=1e-9)
 
 
 def test_interaction_groups_and_errors(oracle):

@@ -90,6 +90,24 @@ def test_frontend_translates_every_force_then_fails_loudly_without_gpu(built, tm
     assert "ocm_context_create" in r.stdout + r.stderr and "no CUDA device available" in r.stdout + r.stderr
 
 
+REF_POPC = "/root/reference/sample/toml_input/POPC_flat_membrane_128.toml"
+
+
+@needs_frontend
+@pytest.mark.skipif(not os.path.exists(REF_POPC), reason="reference tree not mounted")
+def test_frontend_refuses_out_of_scope_potentials_loudly(built, tmp_path):
+    """the lipid-membrane sample (iSoLF attraction + Monte Carlo barostat) is outside the hot-path scope: the
+    host layer names the expression it does not implement and stops; no interpreter, no CPU fallback, no silent skip"""
+    import shutil
+
+    shutil.copy(REF_POPC, tmp_path / "popc.toml")
+    os.makedirs(tmp_path / "output", exist_ok=True)
+    r = subprocess.run([BIN, "popc.toml"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    out = r.stdout + r.stderr
+    assert r.returncode == 1
+    assert "not one of the potentials of the hot-path scope" in out and "no CPU fallback" in out and "cos(0.5*pi*(r - base)/omega)^2" in out
+
+
 HOSTLAYER_ON_ORACLE = os.path.join(ROOT, "oracle", "_ref", "open_cafemol_hostlayer_oracle")
 
 

@@ -109,9 +109,10 @@ def ncu_traffic():
         return None
 
 
-def cpu_port_run(spec, md_steps, threads=None):
+def cpu_port_run(spec, md_steps, threads=None, state=None):
     """Times the CPU oracle (OpenMM-equivalent CPU restatement of the reference path; OpenMM itself is
-    not installable offline) on `md_steps` MD steps of the same workload."""
+    not installable offline) on `md_steps` MD steps of the same workload; state = (positions, velocities) to start
+    from (the condensate compacts over the first 10^4..10^5 steps, so the start state sets the pair count)."""
     import __graft_entry__ as g
     from opencafemol_b200 import toml_input
     from opencafemol_b200.capi import Library
@@ -123,6 +124,9 @@ def cpu_port_run(spec, md_steps, threads=None):
     # CPU arm on one thread although rank 0 is the only rank that runs it (OCM_CPU_THREADS overrides)
     threads = threads or int(os.environ.get("OCM_CPU_THREADS", "0")) or len(os.sched_getaffinity(0))
     ctx.set_option("threads", threads)
+    if state is not None:
+        ctx.set_positions(state[0])
+        ctx.set_velocities(state[1])
     cores = int(ctx.get_option("threads"))
     ctx.step(1)
     t0 = time.perf_counter()
@@ -285,10 +289,11 @@ def run_engine(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             sample = CPU_BASELINE_STEPS
-            v, cores, dt = cpu_port_run(spec, sample)
+            v, cores, dt = cpu_port_run(spec, sample, state=(pos, vel))
             line["cpu_baseline"] = {"value": v, "unit": "ns/day", "cores": cores, "kind": "port",
-                                    "sample": f"{sample} MD steps of the same C2 workload ({dt:.1f} s); OpenMM-equivalent CPU restatement "
-                                              "(oracle), OpenMM not installable offline"}
+                                    "sample": f"{sample} MD steps of the same C2 workload from the state the engine was timed on "
+                                              f"({n_ah} in-cutoff pairs; {dt:.1f} s); OpenMM-equivalent CPU restatement (oracle), "
+                                              "OpenMM not installable offline"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

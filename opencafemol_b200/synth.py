@@ -13,6 +13,8 @@ between consecutive chains.  It is deterministic (no RNG).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .capi import PairTopology
@@ -138,6 +140,23 @@ def hps_slab(n_chains=100, tile=(1, 1), seq=FUS_LC, temperature=300.0, ionic_str
     spec.add_term(Term("debye_huckel", "DebyeHuckel",
                        dict(K=K, debye=debye, rc=rc_dh, cutoff_correction=cc, charge=qq,
                             topo=PairTopology(excl=within(3), igroups=[(charged, charged)], periodic=True))))
+    return spec
+
+
+C2_STATE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "c2_state.npz")
+
+
+def c2_equilibrated() -> SystemSpec:
+    """Config C2 (hps_slab, 100 chains) started from the committed compacted state data/c2_state.npz instead of the
+    serpentine (tools/make_c2_state.py: 20 000 Langevin steps; the slab compacts from 2.5 M to ~4.6 M in-cutoff pairs
+    over that time, and the timed step cost follows the pair count).  Positions nm, velocities nm/ps."""
+    spec = hps_slab(n_chains=100)
+    with np.load(C2_STATE) as d:
+        assert d["x"].shape == spec.positions.shape
+        spec.positions = d["x"].astype(np.float64)
+        spec.velocities = d["v"].astype(np.float64)
+        spec.state = "compacted condensate: %d Langevin steps from the serpentine start, %d in-cutoff Ashbaugh-Hatch pairs " \
+                     "(start: 2.5 M)" % (int(d["steps"]), int(d["pairs"]))
     return spec
 
 

@@ -131,6 +131,7 @@ class SystemSpec:
     periodic: bool = False
     output: dict = field(default_factory=dict)
     platform: dict = field(default_factory=dict)
+    state: str = ""  # provenance of positions/velocities when they are not the input file's (synth.c2_equilibrated)
 
     def add_term(self, term: Term):
         """SystemGenerator::add_ff_generator group rule (src/SystemGenerator.cpp:4-32): the group id is

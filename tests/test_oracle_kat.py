@@ -339,3 +339,32 @@ def test_replicate_tiles_a_periodic_system_exactly(oracle):
     for c in range(4):
         assert np.abs(b["forces"][c * n:(c + 1) * n] - a["forces"]).max() < 1e-8 * max(1.0, np.abs(a["forces"]).max())
     assert b["potential_energy"] == pytest.approx(4.0 * a["potential_energy"], rel=1e-12)
+
+
+def test_committed_c2_state_is_a_valid_compacted_condensate(oracle):
+    """opencafemol_b200/data/c2_state.npz (tools/make_c2_state.py), the start state of both bench arms: same system as
+    hps_slab(100), chains intact, finite energy, and the pair count its metadata states (bit-exact set size)."""
+    import os
+
+    if not os.path.exists(synth.C2_STATE):
+        pytest.skip("no committed C2 state")
+    spec = synth.c2_equilibrated()
+    ref = synth.hps_slab(n_chains=100)
+    assert spec.positions.shape == ref.positions.shape == (16300, 3) and spec.velocities.shape == (16300, 3)
+    assert np.isfinite(spec.positions).all() and np.isfinite(spec.velocities).all()
+    bonds = next(t for t in spec.terms if t.kind == "harmonic_bond").args["ij"]
+    d = spec.positions[bonds[:, 0]] - spec.positions[bonds[:, 1]]
+    d -= spec.box * np.round(d / spec.box)
+    r = np.linalg.norm(d, axis=1)
+    assert 0.30 < r.min() and r.max() < 0.46  # k = 92 383 kJ/mol/nm^2 around 0.38 nm at 300 K
+    # thermal velocities: kinetic temperature within 3 % of 300 K
+    ke = 0.5 * (spec.mass[:, None] * spec.velocities ** 2).sum()
+    T = 2.0 * ke / (3 * 16300 * 0.0083144626)
+    assert abs(T - 300.0) < 9.0
+    ctx = ti.make_context(oracle, spec)
+    with np.load(synth.C2_STATE) as meta:
+        n_pairs = int(meta["pairs"])
+    # float32 storage moves a handful of pairs across the cutoff
+    assert abs(len(ctx.neighbor_pairs(1)) - n_pairs) < 200 and n_pairs > 4_000_000
+    e = ctx.get_state(energy=True)["energy_by_group"]
+    assert np.isfinite(e).all()

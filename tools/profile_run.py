@@ -11,7 +11,7 @@ equil = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 chains = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 lib = product_library()
-spec = synth.hps_slab(n_chains=chains)
+spec = synth.c2_equilibrated() if chains == 100 and os.path.exists(synth.C2_STATE) else synth.hps_slab(n_chains=chains)
 ctx = toml_input.make_context(lib, spec)
 for k, v in [a.split("=") for a in sys.argv[4:]]:
     ctx.set_option(k, float(v))

@@ -138,7 +138,7 @@ def cpu_port_run(spec, md_steps, threads=None, state=None):
 def workload():
     from opencafemol_b200 import synth
 
-    # both arms start from the committed compacted state (tools/make_c2_state.py): the serpentine start keeps compacting
+    # both arms start from the committed compacted state (tests/golden/make_c2_state.py): the serpentine start keeps compacting
     # for tens of thousands of steps, so the pair work per step would otherwise depend on the warm-up length and differ
     # between the GPU arm and the (short) CPU arm
     return synth.c2_equilibrated() if os.path.exists(synth.C2_STATE) else synth.hps_slab(n_chains=100)

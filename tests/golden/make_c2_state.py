@@ -2,7 +2,7 @@
 """Generates opencafemol_b200/data/c2_state.npz: the synthetic C2 condensate (synth.hps_slab, 16 300 beads) after
 `steps` Langevin steps from its serpentine start.
 
-    python tools/make_c2_state.py [steps=20000]
+    python tests/golden/make_c2_state.py [steps=20000]
 
 Why: the serpentine start has the bead density of the reference's sample file (1.12 nm^-3, 2.5 M in-cutoff pairs), but
 under the HPS force field the slab compacts for tens of thousands of steps (3.1 M pairs after 3 000 steps, 4.6 M after
@@ -18,7 +18,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as g  # noqa: E402
 from opencafemol_b200 import synth, toml_input  # noqa: E402

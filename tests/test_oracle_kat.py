@@ -342,7 +342,7 @@ def test_replicate_tiles_a_periodic_system_exactly(oracle):
 
 
 def test_committed_c2_state_is_a_valid_compacted_condensate(oracle):
-    """opencafemol_b200/data/c2_state.npz (tools/make_c2_state.py), the start state of both bench arms: same system as
+    """opencafemol_b200/data/c2_state.npz (tests/golden/make_c2_state.py), the start state of both bench arms: same system as
     hps_slab(100), chains intact, finite energy, and the pair count its metadata states (bit-exact set size)."""
     import os
 

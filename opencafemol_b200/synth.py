@@ -148,7 +148,7 @@ C2_STATE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "c2_
 
 def c2_equilibrated() -> SystemSpec:
     """Config C2 (hps_slab, 100 chains) started from the committed compacted state data/c2_state.npz instead of the
-    serpentine (tests/golden/make_c2_state.py: 20 000 Langevin steps; the slab compacts from 2.5 M to ~4.6 M in-cutoff pairs
+    serpentine (tests/golden/make_c2_state.py: 40 000 Langevin steps; the slab compacts from 2.5 M to ~4.8 M in-cutoff pairs
     over that time, and the timed step cost follows the pair count).  Positions nm, velocities nm/ps."""
     spec = hps_slab(n_chains=100)
     with np.load(C2_STATE) as d:

@@ -2,11 +2,11 @@
 """Generates opencafemol_b200/data/c2_state.npz: the synthetic C2 condensate (synth.hps_slab, 16 300 beads) after
 `steps` Langevin steps from its serpentine start.
 
-    python tests/golden/make_c2_state.py [steps=20000]
+    python tests/golden/make_c2_state.py [steps=40000]
 
 Why: the serpentine start has the bead density of the reference's sample file (1.12 nm^-3, 2.5 M in-cutoff pairs), but
-under the HPS force field the slab compacts for tens of thousands of steps (3.1 M pairs after 3 000 steps, 4.6 M after
-~20 000), so a benchmark that starts there times a different amount of pair work depending on how long it warms up, and
+under the HPS force field the slab compacts for tens of thousands of steps (3.1 M pairs after 3 000 steps, 4.5 M after
+20 000, 4.76 M after 32 000, 4.79 M after 40 000), so a benchmark that starts there times a different amount of pair work depending on how long it warms up, and
 a CPU arm that can only afford a few hundred steps would time a much lighter state than the GPU arm.  bench.py and
 tools/profile_run.py therefore start both arms from this committed state.  It is an INPUT file (positions and velocities
 as float32, nm and nm/ps); it is produced offline by the double-precision CPU restatement (oracle/) because that runs in
@@ -24,7 +24,7 @@ import __graft_entry__ as g  # noqa: E402
 from opencafemol_b200 import synth, toml_input  # noqa: E402
 from opencafemol_b200.capi import Library  # noqa: E402
 
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 40000
 g.build_oracle()
 lib = Library(g.ORACLE_SO, "oracle_")
 spec = synth.hps_slab(n_chains=100)

@@ -146,17 +146,23 @@ def hps_slab(n_chains=100, tile=(1, 1), seq=FUS_LC, temperature=300.0, ionic_str
 C2_STATE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "c2_state.npz")
 
 
-def c2_equilibrated() -> SystemSpec:
+def c2_equilibrated(tile=(1, 1)) -> SystemSpec:
     """Config C2 (hps_slab, 100 chains) started from the committed compacted state data/c2_state.npz instead of the
     serpentine (tests/golden/make_c2_state.py: 40 000 Langevin steps; the slab compacts from 2.5 M to ~4.8 M in-cutoff pairs
-    over that time, and the timed step cost follows the pair count).  Positions nm, velocities nm/ps."""
-    spec = hps_slab(n_chains=100)
+    over that time, and the timed step cost follows the pair count).  Positions nm, velocities nm/ps.
+    tile = (tx, ty): that state repeated tx x ty times in a box tx x ty times as large (tile (8, 8) = config C5,
+    1 043 200 beads): exact periodic images, so the forces at t = 0 are the C2 forces copy by copy; the copies decorrelate
+    through the per-bead Langevin noise."""
+    tx, ty = tile
+    spec = hps_slab(n_chains=100 * tx * ty, tile=(tx, ty))
     with np.load(C2_STATE) as d:
-        assert d["x"].shape == spec.positions.shape
-        spec.positions = d["x"].astype(np.float64)
-        spec.velocities = d["v"].astype(np.float64)
+        x, v = d["x"].astype(np.float64), d["v"].astype(np.float64)
+        assert x.shape[0] * tx * ty == spec.positions.shape[0]
+        lx, ly = C2_BOX_A[0] * NM_PER_ANGSTROM, C2_BOX_A[1] * NM_PER_ANGSTROM
+        spec.positions = np.concatenate([x + np.array([i * lx, j * ly, 0.0]) for i in range(tx) for j in range(ty)])
+        spec.velocities = np.tile(v, (tx * ty, 1))
         spec.state = "compacted condensate: %d Langevin steps from the serpentine start, %d in-cutoff Ashbaugh-Hatch pairs " \
-                     "(start: 2.5 M)" % (int(d["steps"]), int(d["pairs"]))
+                     "per 16 300 beads (start: 2.5 M)" % (int(d["steps"]), int(d["pairs"]))
     return spec
 
 

@@ -368,3 +368,9 @@ def test_committed_c2_state_is_a_valid_compacted_condensate(oracle):
     assert abs(len(ctx.neighbor_pairs(1)) - n_pairs) < 200 and n_pairs > 4_000_000
     e = ctx.get_state(energy=True)["energy_by_group"]
     assert np.isfinite(e).all()
+    # tiling: exact periodic images, so the forces of the 2 x 1 tiling are the C2 forces twice (SURVEY.md 8d, C5 input)
+    f1 = ctx.get_state(forces=True)["forces"]
+    two = synth.c2_equilibrated(tile=(2, 1))
+    assert two.positions.shape == (32600, 3) and np.allclose(two.box, spec.box * np.array([2, 1, 1]))
+    f2 = ti.make_context(oracle, two).get_state(forces=True)["forces"]
+    assert np.abs(f2 - np.concatenate([f1, f1])).max() < 1e-7 * max(1.0, np.abs(f1).max())

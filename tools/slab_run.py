@@ -2,10 +2,12 @@
 """One rank of a slab-decomposed run (config C5 and smaller), one process per GPU under torchrun:
 
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tools/slab_run.py --tile 8 8 --chains 6400 --steps 2000 [--check]
+        tools/slab_run.py --tile 8 8 --chains 6400 --steps 2000 [--check] [--equilibrated]
 
 Prints one JSON line on rank 0: ns/day, MD steps/s, per-rank owned beads.  --check compares positions after the run
 with a single-domain run of the same system on rank 0's GPU (bit-exact with a fixed rebuild interval).
+--equilibrated starts from the committed compacted C2 state tiled --tile times (synth.c2_equilibrated) instead of the
+serpentine start, which is still compacting during a short run.
 With WORLD_SIZE unset it runs the single-domain engine (the 1-GPU point of the scaling curve)."""
 import argparse
 import json
@@ -44,6 +46,8 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--halo", choices=["push", "nccl"], default="push", help="per-step halo: peer-memory push kernel or NCCL send/recv")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
+    ap.add_argument("--equilibrated", action="store_true",
+                    help="start from the committed compacted C2 state tiled --tile times (needs --chains = 100 x tiles) instead of the serpentine")
     ap.add_argument("--phases", action="store_true", help="time the phases of a step with CUDA events (engine option phase_timing)")
     args = ap.parse_args()
 
@@ -57,7 +61,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     lib = product_library()
-    spec = synth.hps_slab(n_chains=args.chains, tile=tuple(args.tile))
+    if args.equilibrated:
+        assert args.chains == 100 * args.tile[0] * args.tile[1], "--equilibrated tiles the 100-chain state: --chains must be 100 x tiles"
+        spec = synth.c2_equilibrated(tile=tuple(args.tile))
+    else:
+        spec = synth.hps_slab(n_chains=args.chains, tile=tuple(args.tile))
     comm = None
     if world > 1:
         import torch.distributed as dist
@@ -107,7 +115,7 @@ def main():
                   "epot": [a["potential_energy"], st["potential_energy"]]}
     if rank == 0:
         print(json.dumps({
-            "n_gpus": world, "beads": int(spec.mass.size), "md_steps": args.steps, "device_s": dev_s, "wall_s": wall_s,
+            "n_gpus": world, "beads": int(spec.mass.size), "state": spec.state or "serpentine start", "md_steps": args.steps, "device_s": dev_s, "wall_s": wall_s,
             "md_steps_per_s": args.steps / dev_s, "ns_per_day": args.steps * spec.dt * 1e-3 / dev_s * 86400.0,
             "nstlist": ctx.counter("nstlist"), "rollbacks": ctx.counter("rollbacks"), "owned": [int(o.item()) for o in owned_all],
             "halo_message_bytes": ctx.counter("halo_message_bytes"),

@@ -10,6 +10,9 @@ with save_step = 1000 MD steps (src/Simulator.cpp:49-76); ns/day = MD steps/s x 
     python bench.py --impl reference --steps 2 --warmup 1      # CPU arm: the oracle port of the reference path
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N   # N independent replicas
 
+Both arms start from the same committed state of the workload, opencafemol_b200/data/c2_state.npz (the condensate after
+40 000 steps, when its compaction has levelled off: config.state), so they time the same pair work per step.
+
 The line printed by rank 0 follows the driver's contract (metric/value/unit/..., e2e, roofline,
 cpu_baseline, clocks, gpu_launches).
 """

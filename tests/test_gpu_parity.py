@@ -81,6 +81,53 @@ def test_hps_c2_full_size(engine, oracle):
     assert np.abs(f.sum(0)).max() < 1e-3 * np.abs(f).max()
 
 
+def test_c2_equilibrated_bench_state(engine, oracle):
+    """The state bench.py times (synth.c2_equilibrated: the compacted condensate, ~4.8 M in-cutoff Ashbaugh-Hatch pairs, closer
+    contacts than the serpentine start -> the hard case for FP32 r^-12): forces, per-group energies, pair sets bit-exact."""
+    spec = synth.c2_equilibrated()
+    ctx, ora = ti.make_context(engine, spec), ti.make_context(oracle, spec)
+    check_state(ctx, ora, spec)
+    check_sets(ctx, ora)
+    assert len(ctx.neighbor_pairs(1)) > 4_000_000
+
+
+def test_fus100_reference_full_size(engine):
+    """sample/toml_input/FUS_100_HPS.toml at full size (16 300 beads) against the REFERENCE's own answer at the same relaxed
+    coordinates (tests/golden/make_ref_fus100.py: oracle/_ref, the reference's reader, generators and expression strings)."""
+    import os
+
+    from conftest import GOLDEN
+    spec = load_golden_spec("ref_fus100")
+    with np.load(os.path.join(GOLDEN, "ref_fus100.npz")) as d:
+        fref, names, eg, etot = d["forces"], [str(s) for s in d["group_names"]], d["group_energies_kj"], float(d["potential_energy_kj"])
+        assert np.array_equal(d["positions"], spec.positions)
+    ctx = ti.make_context(engine, spec)
+    a = ctx.get_state(forces=True, energy=True)
+    assert force_error(a["forces"], fref).max() < FORCE_TOL
+    escale = max(np.abs(eg).max(), 1.0)
+    for name, ref in zip(names, eg):
+        got = a["energy_by_group"][spec.group_ids[name]]
+        assert abs(got - ref) <= ENERGY_TOL * max(abs(ref), 1e-3 * escale), (name, got, ref)
+    assert a["potential_energy"] == pytest.approx(etot, rel=ENERGY_TOL)
+
+
+def test_c5_tiling_reproduces_the_c2_forces(engine):
+    """Config C5 (the compacted C2 state tiled 8 x 8: 1 043 200 beads) on one GPU: exact periodic images, so every copy must
+    feel the C2 forces (SURVEY.md 8d "free correctness check"); the C2 forces themselves are pinned to the oracle above."""
+    base = synth.c2_equilibrated()
+    f1 = ti.make_context(engine, base).get_state(forces=True)["forces"]
+    big = synth.c2_equilibrated(tile=(8, 8))
+    assert big.mass.size == 1_043_200
+    ctx = ti.make_context(engine, big)
+    f = ctx.get_state(forces=True)["forces"].reshape(64, -1, 3)
+    frms = np.sqrt((f1 ** 2).sum(1).mean())
+    worst = max(np.abs(f[c] - f1).max() for c in range(64))
+    # FP32 pair arithmetic in a box 8 x larger (coarser fixed-point grid): copies agree to ~1e-6 of the rms force
+    assert worst < 1e-5 * frms, worst / frms
+    ctx.step(20)
+    assert np.isfinite(ctx.get_state(energy=True)["potential_energy"])
+
+
 def check_da_sets(ctx, ora):
     assert ctx.num_da_terms() == ora.num_da_terms()
     for t in range(ctx.num_da_terms()):

@@ -74,6 +74,19 @@ def test_oracle_matches_reference_vectors(oracle, name):
     assert spec.temperature == integ["temperature"] and spec.seed == integ["seed"]
 
 
+def test_oracle_matches_reference_fus100_full_size(oracle):
+    """sample/toml_input/FUS_100_HPS.toml at full size (16 300 beads, config C2's sample): the oracle against the reference's own
+    energies and forces at relaxed coordinates (tests/golden/make_ref_fus100.py)."""
+    spec = load_golden_spec("ref_fus100")
+    with np.load(os.path.join(GOLDEN, "ref_fus100.npz")) as d:
+        fref, names, eg = d["forces"], [str(s) for s in d["group_names"]], d["group_energies_kj"]
+        assert spec.group_ids == json.loads(str(d["group_map"]))
+    st = ti.make_context(oracle, spec).get_state(forces=True, energy=True)
+    assert force_error(st["forces"], fref).max() < 1e-9
+    for name, ref in zip(names, eg):
+        assert st["energy_by_group"][spec.group_ids[name]] == pytest.approx(ref, rel=1e-10, abs=1e-7)
+
+
 @pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "nucleosome"])
 def test_oracle_trajectory_matches_reference_run(oracle, name):
     """20 leap-frog Langevin steps of the reference's LangevinIntegrator semantics with the shared Philox noise."""

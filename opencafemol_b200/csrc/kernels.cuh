@@ -78,6 +78,28 @@ struct PairListDev {
     int mem_switch[kMaxMembers];
     float mem_rc2[kMaxMembers];
     const float4* memE[kMaxMembers];  // [2*nt*nt] {c12_in,c6_in,c0_in,a2},{c12_out,c6_out,c0_out,0}
+    // ---- cluster-pair ("tile") form of the list (tile_kernels.cuh); Verlet rows are not built when tiled != 0 ----
+    int tiled;
+    const int* cell_rank;       // [grid cells] Hilbert rank of each cell: tile lists sort their beads along the curve
+    int* sbead;                 // [rows padded to 64] bead | type << 24 of rank k, -1 = padding
+    float2* sparam;             // [rows padded] per-bead mixing parameters (inner, outer strength); spos.w carries a
+    uint4* saux;                // [rows padded] {inner, outer strength, bead | type << 24, 0}: what the force kernel loads per j-bead
+    const float* slot_a;        // [np] per slot: half sigma / radius / scaled charge
+    const float2* slot_b;       // [np]
+    uint4* sc_center;           // [superclusters] bounding-box centre (fixed point)
+    float4* sc_half;            // [superclusters] half extents (nm)
+    int tl_nsc, tl_stride;      // superclusters allocated; entries per supercluster row
+    int* tl_count;              // [tl_nsc] entries in use
+    int* tl_weight;             // [tl_nsc] estimated work of the row (tile evaluations + overheads)
+    int* tl_start;              // [tl_nsc + 1] exclusive prefix sum of tl_weight (tile_scan_kernel)
+    uint2* tl_entries;          // [tl_nsc * tl_stride] {j-group, i-cluster mask | mask block << 8}
+    unsigned int* tl_masks;     // [tl_mask_cap * 8] lane masks of the entries that need them (block index is 1-based)
+    int* tl_mask_count;
+    int tl_mask_cap;
+    const int2* excl_pairs;     // excluded bead pairs (tile_excl_kernel)
+    int n_excl_pairs;
+    float t_alpha, t_beta, t_qz, t_kappa;  // pair form, see TileForm
+    int t_geo;
 };
 
 struct BondedDev {
@@ -326,6 +348,7 @@ __global__ void bin_kernel(const PairListDev* lists, int li, const uint4* __rest
     if (L.role && L.role[bead] == 0) { L.cell_of_slot[a] = -1; L.rank_of_bead[bead] = -1; return; }
     cell_coords<PER>(g, posq[bead], cx, cy, cz);
     int c = (cz * g.nc[1] + cy) * g.nc[0] + cx;
+    if (L.cell_rank) c = L.cell_rank[c];  // tile lists: cells are keyed by their rank along the Hilbert curve
     if (L.nrep > 1) c += (bead / L.nper) * g.ncell;
     L.cell_of_slot[a] = c;
     atomicAdd(&L.cell_count[c], 1);

@@ -26,6 +26,7 @@
 #include "host_system.hpp"
 #include "host/lbfgs.hpp"
 #include "kernels.cuh"
+#include "tile_kernels.cuh"
 #include "dd_kernels.cuh"
 #include "dd_comm.hpp"
 
@@ -83,6 +84,25 @@ struct PairListHost {
     DevBuf<float4> memE[kMaxMembers];
     PairListDev dev{};       // host mirror of the device descriptor
     int max_cells = 0;
+    // cluster-pair ("tile") form (tile_kernels.cuh)
+    bool tile_ok = false;    // the static tile tables exist (periodic or virtual box, single system)
+    bool tiled = false;      // the list is built and evaluated in tile form
+    bool t_switch = false;
+    int np_pad = 0, tl_stride = 0, tl_nsc = 0, tl_mask_cap = 0;
+    int grid_dims[3] = {0, 0, 0};
+    float cell_width = 0.f;  // width the grid was derived from (before any widening), reported for the oracle
+    long long cell_cap = -1; // cap on the number of cells that widened them (-1: none)
+    std::vector<int> cell_inv;  // Hilbert rank -> linear cell id
+    DevBuf<int> cell_rank, sbead, tl_count, tl_weight, tl_start, tl_mask_count;
+    TileLaunch launch{};     // by-value description of the list's force launch
+    int tile_nblocks = 0;
+    DevBuf<float2> sparam, slot_b;
+    DevBuf<float> slot_a;
+    DevBuf<uint4> sc_center, saux;
+    DevBuf<float4> sc_half;
+    DevBuf<uint2> tl_entries;
+    DevBuf<unsigned int> tl_masks;
+    DevBuf<int2> excl_pairs;
 };
 
 }  // namespace ocm
@@ -170,6 +190,10 @@ struct ocm_context {
     double da_rcmax = 0;
     std::vector<WorkSeg> segs;
     DevBuf<WorkSeg> d_segs;
+    int tile_blocks = 0;                    // blocks of all tile force launches (tile lists have one launch each)
+    int tile_opt = 1;                       // option "pair_kernel": 1 = cluster-pair tiles where possible, 0 = Verlet rows
+    int tile_debug = 0;
+    int tile_chunk_opt = 0;                 // blocks of the tile force launch per list, 0 = auto (one wave)
     int total_blocks = 0, pair_blocks = 0, local_blocks = 0, n_pair_segs = 0, n_local_segs = 0;
     size_t smem_bytes = 0;
     cudaStream_t side = nullptr;            // forked branch: bonded + donor-acceptor kernel beside the pair kernel
@@ -301,6 +325,94 @@ static void plan_lists(ocm_context* c) {
     }
 }
 
+// ---- cluster-pair ("tile") form: static tables ------------------------------------------------------
+// Hilbert index of a grid cell (Skilling's transpose algorithm), `bits` bits per axis
+static uint64_t hilbert_index(uint32_t x, uint32_t y, uint32_t z, int bits) {
+    uint32_t X[3] = {x, y, z};
+    const uint32_t M = 1u << (bits - 1);
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t Pm = Q - 1;
+        for (int i = 0; i < 3; i++) {
+            if (X[i] & Q) X[0] ^= Pm;
+            else { const uint32_t t = (X[0] ^ X[i]) & Pm; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    for (int i = 1; i < 3; i++) X[i] ^= X[i - 1];
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+    for (int i = 0; i < 3; i++) X[i] ^= t;
+    uint64_t h = 0;
+    for (int b = bits - 1; b >= 0; b--)
+        for (int i = 0; i < 3; i++) h = (h << 1) | ((X[i] >> b) & 1u);
+    return h;
+}
+
+// per-bead mixing parameters of the two-zone 12-6 family (tile_pair_tz): with s = a_i + a_j, q = s^2 / r^2,
+//   -dE/dr / r = e q^3 (alpha q^3 - beta) / r^2,  e = inner zone (q > qz) ? mix(b_i, b_j) : c_i + c_j
+// which restates tz_coeffs() term by term:
+//   ExcludedVolume      eps (s_i+s_j)^12 / r^12                 a = radius,   b = 6 eps (sum),        alpha 1, beta 0, qz 0
+//   LennardJonesRepulsive / WCA   4 eps (q^6 - q^3) + eps inside 2^(1/6) sigma   a = sigma/2, b = 12 eps_i (sum) or sqrt(24 eps_i) (product)
+//   LennardJonesAttractive        4 eps (q^6 - q^3) beyond 2^(1/6) sigma, switched   c = 12 eps_i
+//   3SPN2ExcludedVolume eps (q^6 - 2 q^3) + eps inside sigma    a = sigma/2,  b = sqrt(12 eps_i) (product), alpha 1, beta 1, qz 1
+static void compile_tile_tables(ocm_context* c, PairListHost& L) {
+    // (small lists -- a few hundred charged beads -- stay Verlet rows inside the fused launch: a tile launch of their own costs more)
+    L.tile_ok = c->periodic && c->nrep == 1 && L.np >= 1024;
+    if (!L.tile_ok) return;
+    const auto& pairs = c->sys.pairs;
+    const PairTerm& t0 = pairs[L.terms[0]];
+    PairListDev& D = L.dev;
+    std::vector<float> sa(L.np, 0.f);
+    std::vector<float2> sb(L.np, make_float2(0.f, 0.f));
+    D.t_alpha = 2.f; D.t_beta = 1.f; D.t_qz = (float)std::pow(2.0, -1.0 / 3.0); D.t_kappa = (float)(1.0 / 6.0); D.t_geo = 0;
+    L.t_switch = false;
+    if (L.form == SEG_PAIR_DH) {
+        const double sk = std::sqrt(t0.g0);
+        for (int a = 0; a < L.np; a++) sa[a] = (float)(t0.p0[t0.part[a]] * sk);
+    } else {
+        for (int m : L.terms) {
+            const PairTerm& t = pairs[m];
+            for (int a = 0; a < L.np; a++) {
+                const int i = t0.part[a];
+                switch (t.kind) {
+                    case P_EXV: sa[a] = (float)t.p0[i]; sb[a].x = (float)(6.0 * t.g0); break;
+                    case P_LJREP: sa[a] = (float)(0.5 * t.p1[i]); sb[a].x = (float)(12.0 * t.p0[i]); break;
+                    case P_WCA: sa[a] = (float)(0.5 * t.p1[i]); sb[a].x = (float)std::sqrt(24.0 * t.p0[i]); break;
+                    case P_LJATT: sa[a] = (float)(0.5 * t.p1[i]); sb[a].y = (float)(12.0 * t.p0[i]); break;
+                    case P_3SPN2EXV: sa[a] = (float)(0.5 * t.p1[i]); sb[a].x = (float)std::sqrt(12.0 * t.p0[i]); break;
+                    default: throw std::runtime_error("internal: pair kind without a tile form");
+                }
+            }
+            if (t.kind == P_EXV) { D.t_alpha = 1.f; D.t_beta = 0.f; D.t_qz = 0.f; }
+            if (t.kind == P_3SPN2EXV) { D.t_alpha = 1.f; D.t_beta = 1.f; D.t_qz = 1.f; D.t_geo = 1; }
+            if (t.kind == P_WCA) D.t_geo = 1;
+            if (t.kind == P_LJATT) L.t_switch = true;
+        }
+    }
+    L.slot_a.upload(sa); L.slot_b.upload(sb);
+    D.slot_a = L.slot_a.p; D.slot_b = L.slot_b.p;
+    std::vector<int2> ex;
+    {
+        std::vector<char> in_list(c->n, 0);
+        for (int i : t0.part) in_list[i] = 1;
+        for (auto& e : t0.excl) if (in_list[e.first] && in_list[e.second]) ex.push_back(make_int2(e.first, e.second));
+    }
+    D.n_excl_pairs = (int)ex.size();
+    if (ex.empty()) ex.push_back(make_int2(0, 0));
+    L.excl_pairs.upload(ex);
+    D.excl_pairs = L.excl_pairs.p;
+    // sorted arrays padded to whole superclusters
+    L.np_pad = (L.np + 63) / 64 * 64;
+    L.tl_nsc = L.np_pad / 64;
+    L.spos.alloc(L.np_pad); L.spos.zero();
+    L.sbead.alloc(L.np_pad); CUDA_TRY(cudaMemset(L.sbead.p, 0xFF, (size_t)L.np_pad * sizeof(int)));
+    L.sparam.alloc(L.np_pad); L.sparam.zero();
+    L.saux.alloc(L.np_pad); L.saux.zero();
+    L.sc_center.alloc(L.tl_nsc); L.sc_half.alloc(L.tl_nsc); L.tl_count.alloc(L.tl_nsc); L.tl_count.zero(); L.tl_start.alloc(L.tl_nsc + 1); L.tl_start.zero(); L.tl_weight.alloc(L.tl_nsc); L.tl_weight.zero();
+    L.tl_mask_count.alloc(1); L.tl_mask_count.zero();
+    D.spos = L.spos.p; D.sbead = L.sbead.p; D.sparam = L.sparam.p; D.saux = L.saux.p; D.sc_center = L.sc_center.p; D.sc_half = L.sc_half.p;
+    D.tl_nsc = L.tl_nsc; D.tl_count = L.tl_count.p; D.tl_start = L.tl_start.p; D.tl_weight = L.tl_weight.p; D.tl_mask_count = L.tl_mask_count.p;
+}
+
 static void compile_list(ocm_context* c, PairListHost& L) {
     const auto& pairs = c->sys.pairs;
     const PairTerm& t0 = pairs[L.terms[0]];
@@ -430,6 +542,7 @@ static void compile_list(ocm_context* c, PairListHost& L) {
     CUDA_TRY(cudaMemset(L.rank_of_bead.p, 0xFF, (size_t)c->n * sizeof(int)));
     D.cell_of_slot = L.cell_of_slot.p; D.tmp_slots = L.tmp_slots.p; D.sorted_slots = L.sorted_slots.p; D.nbr_count = L.nbr_count.p;
     D.spos = L.spos.p; D.rank_of_bead = L.rank_of_bead.p;
+    compile_tile_tables(c, L);
 }
 
 // (re)derive everything that depends on the skin: list radius, cell grid
@@ -452,8 +565,15 @@ static void configure_grid(ocm_context* c, PairListHost& L) {
         long long tot = 1;
         // a virtual box (unlimited boundary) is mostly empty: widen the cells until their number is of the order of the
         // participants (same rule in the oracle's restatement of the grid)
-        const long long cap = std::max(4096, 8 * L.np + 64);
+        long long cap = c->vbox ? std::max(4096, 8 * L.np + 64) : -1;
         float w = D.wmin;
+        if (L.tiled) {
+            // tile lists only sort by cell (the list build works on cluster bounding boxes): fine cells, a sixth of the
+            // list radius, about one bead per cell at most, ordered along a Hilbert curve
+            w = (float)rlist / 6.0f;
+            cap = std::max(4096, L.np);
+        }
+        L.cell_width = w; L.cell_cap = cap;
         for (;;) {
             tot = 1;
             for (int k = 0; k < 3; k++) {
@@ -461,14 +581,34 @@ static void configure_grid(ocm_context* c, PairListHost& L) {
                 g.nc[k] = std::max(1, std::min(nc, 1024));
                 tot *= g.nc[k];
             }
-            if (!c->vbox || tot <= cap) break;
+            if (cap < 0 || tot <= cap) break;
             w *= 1.25f;
         }
         if (tot > (1ll << 26)) throw std::runtime_error("cell grid too large");
         g.ncell = (int)tot;
         g.inv_w = 1.0f / D.wmin;
         L.max_cells = g.ncell;
+        if (L.tiled && (L.grid_dims[0] != g.nc[0] || L.grid_dims[1] != g.nc[1] || L.grid_dims[2] != g.nc[2] || !L.cell_rank.p)) {
+            // rank of every cell along the Hilbert curve through the enclosing power-of-two cube
+            int bits = 1;
+            while ((1 << bits) < std::max(g.nc[0], std::max(g.nc[1], g.nc[2]))) bits++;
+            std::vector<std::pair<uint64_t, int>> key((size_t)g.ncell);
+            for (int z = 0; z < g.nc[2]; z++)
+                for (int y = 0; y < g.nc[1]; y++)
+                    for (int x = 0; x < g.nc[0]; x++) {
+                        const int cidx = (z * g.nc[1] + y) * g.nc[0] + x;
+                        key[cidx] = {hilbert_index((uint32_t)x, (uint32_t)y, (uint32_t)z, bits), cidx};
+                    }
+            std::sort(key.begin(), key.end());
+            std::vector<int> rank((size_t)g.ncell);
+            L.cell_inv.resize((size_t)g.ncell);
+            for (int r = 0; r < g.ncell; r++) { rank[key[r].second] = r; L.cell_inv[r] = key[r].second; }
+            L.cell_rank.upload(rank);
+            for (int k = 0; k < 3; k++) L.grid_dims[k] = g.nc[k];
+        }
+        D.cell_rank = L.tiled ? L.cell_rank.p : nullptr;
     } else {
+        L.cell_width = D.wmin; L.cell_cap = -1;
         g.nc[0] = g.nc[1] = g.nc[2] = 1; g.ncell = 1; g.inv_w = 1.0f / D.wmin;
         L.max_cells = std::max(std::max(4096, 64 * c->nrep), std::min(1 << 21, 8 * L.np + 64));
     }
@@ -497,11 +637,34 @@ static int pick_tpb(const ocm_context* c, const PairListHost& L) {
 
 static void build_segments(ocm_context* c) {
     c->segs.clear();
-    int blk = 0;
+    int blk = 0, tblk = 0;
     size_t smem = 0;
     for (size_t l = 0; l < c->lists.size(); l++) {
         auto& L = *c->lists[l];
         if (L.np == 0) continue;
+        if (L.tiled) {
+            // tile lists: block = (supercluster, chunk of its entry row).  About 32 entries per block (8 per warp) keeps
+            // the per-block prologue / i-force epilogue below 5 % and gives some 2 000 blocks at 16 k beads.
+            const int rows = (c->dd && l < c->dd->rows_est.size() && c->dd->rows_est[l] > 0) ? std::min(L.np_pad, (int)(1.25 * c->dd->rows_est[l]) + 64) : L.np_pad;
+            L.dev.row_capacity = std::min(L.np_pad, (rows + 63) / 64 * 64);
+            const int nsc = L.dev.row_capacity / 64;
+            // persistent launch, one wave of OCM_TILE_MINBLOCKS blocks per SM (fewer when the list is small)
+            int sms = 148;
+            { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess) sms = prop.multiProcessorCount; }
+            const int want = c->tile_chunk_opt > 0 ? c->tile_chunk_opt : sms * OCM_TILE_MINBLOCKS;
+            TileLaunch& T = L.launch;
+            T = TileLaunch{};
+            T.n = c->n; T.pdl_early = c->P.pdl_early; T.debug = c->tile_debug;
+            for (int k = 0; k < 3; k++) { T.fscale[k] = c->P.fscale[k]; T.half_box[k] = (float)(0.5 * c->sys.box[k]); }
+            TileSegP& ts = T.seg;
+            ts.nblocks = std::max(1, std::min(want, nsc * 8)); ts.nsc = nsc; ts.stride = L.tl_stride; ts.start = L.tl_start.p;
+            L.tile_nblocks = ts.nblocks;
+            ts.entries = L.tl_entries.p; ts.count = L.tl_count.p; ts.spos = L.spos.p; ts.saux = L.saux.p; ts.masks = L.tl_masks.p; ts.sc_center = L.sc_center.p;
+            ts.rc2 = L.dev.rc2; ts.alpha = L.dev.t_alpha; ts.beta = L.dev.t_beta; ts.qz = L.dev.t_qz; ts.inv_sw = L.dev.inv_sw;
+            ts.sw_c0 = L.dev.rsw * L.dev.inv_sw; ts.sw_c1 = 30.f * L.dev.inv_sw * L.dev.t_kappa; ts.inv_debye = L.dev.inv_debye;
+            tblk += L.tile_nblocks;
+            continue;
+        }
         L.tpb = pick_tpb(c, L);
         // a block owns `chunk` consecutive ranks of the cell-sorted order (spatially compact: rows overlap in L1,
         // one coefficient-table load per block); about 16 blocks per SM for load balance
@@ -547,6 +710,7 @@ static void build_segments(ocm_context* c) {
     c->smem_bytes = smem;
     if (c->segs.empty()) c->segs.push_back({0, 0, SEG_BONDED, 0, 0, 0, 0});
     c->d_segs.upload(c->segs);
+    c->tile_blocks = tblk;
     if (smem > 48 * 1024) {
         CUDA_TRY(cudaFuncSetAttribute(force_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(force_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -834,6 +998,36 @@ static void launch_build(ocm_context* c, PairListHost& L, int li, cudaStream_t s
     else build_list_kernel<false><<<nblk(rows * 32, 256), 256, smem, s>>>(c->d_lists.p, li, c->P, c->flags.p, count_only ? 1 : 0, zoned);
 }
 
+// sort the beads of one list into cells and build its pair list (Verlet rows or cluster-pair tiles)
+static void enqueue_list_rebuild(ocm_context* c, PairListHost& L, int li, cudaStream_t s, bool count_only) {
+    if (c->periodic) {
+        bin_kernel<true><<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
+    } else {
+        bbox_kernel<<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
+        grid_kernel<<<1, 1, 0, s>>>(c->d_lists.p, li);
+        bin_kernel<false><<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
+    }
+    scan_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li);
+    scatter_kernel<<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li);
+    if (L.tiled) {
+        // (the grids cover the rows the force launch covers: all of them, or the estimate of a slab decomposition)
+        const int rows = (c->dd && !count_only && L.dev.row_capacity > 0) ? L.dev.row_capacity : L.np_pad;
+        const int nsc = (rows + 63) / 64;
+        tile_fill_kernel<<<nblk(L.np_pad, 128), 128, 0, s>>>(c->d_lists.p, li, c->posq.p);
+        tile_bbox_kernel<<<nblk(nsc * 32, 128), 128, 0, s>>>(c->d_lists.p, li, c->P);
+        CUDA_TRY(cudaMemsetAsync(L.tl_mask_count.p, 0, sizeof(int), s));
+        tile_build_kernel<true><<<nsc, kBuildBlock, 0, s>>>(c->d_lists.p, li, c->P, c->flags.p, count_only ? 1 : 0);
+        if (L.dev.n_excl_pairs > 0)
+            tile_excl_kernel<<<nblk(L.dev.n_excl_pairs, 256), 256, 0, s>>>(c->d_lists.p, li, c->flags.p, count_only ? 1 : 0);
+        if (!count_only) tile_scan_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li, nsc);
+        c->n_launches += 9;
+        return;
+    }
+    rank_fill_kernel<<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->posq.p);
+    launch_build(c, L, li, s, count_only);
+    c->n_launches += c->periodic ? 5 : 7;
+}
+
 static void enqueue_rebuild(ocm_context* c, cudaStream_t s, bool count_only) {
     const int n = c->n;
     if (c->nrep > 1) {
@@ -849,19 +1043,7 @@ static void enqueue_rebuild(ocm_context* c, cudaStream_t s, bool count_only) {
     for (size_t l = 0; l < c->lists.size(); l++) {
         auto& L = *c->lists[l];
         if (L.np == 0) continue;
-        const int li = (int)l;
-        if (c->periodic) {
-            bin_kernel<true><<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
-        } else {
-            bbox_kernel<<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
-            grid_kernel<<<1, 1, 0, s>>>(c->d_lists.p, li);
-            bin_kernel<false><<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
-        }
-        scan_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li);
-        scatter_kernel<<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li);
-        rank_fill_kernel<<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->posq.p);
-        launch_build(c, L, li, s, count_only);
-        c->n_launches += c->periodic ? 5 : 7;
+        enqueue_list_rebuild(c, L, (int)l, s, count_only);
     }
     if (!count_only) {
         enqueue_da_build(c, s);
@@ -883,7 +1065,7 @@ static void launch_chained(ocm_context* c, void (*kernel)(KArgs...), int grid, i
 }
 
 static void enqueue_forces(ocm_context* c, cudaStream_t s) {
-    if (c->total_blocks == 0) return;
+    if (c->total_blocks == 0 && c->tile_blocks == 0) return;
     const bool fork = c->local_blocks > 0 && c->pair_blocks > 0;
     if (c->local_blocks > 0) {
         cudaStream_t sl = s;
@@ -894,6 +1076,16 @@ static void enqueue_forces(ocm_context* c, cudaStream_t s) {
         }
         local_kernel<<<c->local_blocks, kBlock, 0, sl>>>(c->da, c->P, c->x.p, c->fbuf.p);
         if (fork) CUDA_TRY(cudaEventRecord(c->ev_join, c->side));
+        c->n_launches += 1;
+    }
+    for (auto& Lp : c->lists) {
+        PairListHost& L = *Lp;
+        if (!L.tiled || L.np == 0) continue;
+        // one launch per tile list; the pair form is a template parameter, the list's constants ride in the kernel parameters
+        if (L.form == SEG_PAIR_DH) launch_chained(c, tile_force_kernel<SEG_PAIR_DH, false, false>, L.tile_nblocks, kTileBlock, 0, s, L.launch, c->fbuf.p);
+        else if (L.t_switch && !(c->tile_debug & 4)) launch_chained(c, tile_force_kernel<SEG_PAIR_TZ, true, false>, L.tile_nblocks, kTileBlock, 0, s, L.launch, c->fbuf.p);
+        else if (L.dev.t_geo) launch_chained(c, tile_force_kernel<SEG_PAIR_TZ, false, true>, L.tile_nblocks, kTileBlock, 0, s, L.launch, c->fbuf.p);
+        else launch_chained(c, tile_force_kernel<SEG_PAIR_TZ, false, false>, L.tile_nblocks, kTileBlock, 0, s, L.launch, c->fbuf.p);
         c->n_launches += 1;
     }
     if (c->pair_blocks > 0) {
@@ -908,7 +1100,11 @@ static void enqueue_forces(ocm_context* c, cudaStream_t s) {
 // size (or re-size) the Verlet rows from a counting pass at the current positions
 static void size_lists(ocm_context* c, double growth) {
     cudaStream_t s = c->stream;
-    for (auto& L : c->lists) configure_grid(c, *L);
+    for (auto& L : c->lists) {
+        L->tiled = L->tile_ok && c->tile_opt != 0;
+        L->dev.tiled = L->tiled ? 1 : 0;
+        configure_grid(c, *L);
+    }
     upload_lists(c);
     if (c->nrep > 1) {
         recentre_kernel<<<nblk(c->nrep * 32, 128), 128, 0, s>>>(c->P, c->x.p, c->origin.p);
@@ -939,20 +1135,28 @@ static void size_lists(ocm_context* c, double growth) {
         if (L.np == 0) continue;
         CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, FLAG_COUNT * sizeof(int), s));
         const int li = (int)l;
-        if (c->periodic) bin_kernel<true><<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
-        else {
-            bbox_kernel<<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
-            grid_kernel<<<1, 1, 0, s>>>(c->d_lists.p, li);
-            bin_kernel<false><<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
-        }
-        scan_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li);
-        scatter_kernel<<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li);
-        rank_fill_kernel<<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->posq.p);
-        launch_build(c, L, li, s, true);
+        const double launches = c->n_launches;
+        enqueue_list_rebuild(c, L, li, s, true);
+        c->n_launches = launches;
         CUDA_TRY(cudaMemcpyAsync(fl.data(), c->flags.p, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (c->dd) CUDA_TRY(cudaMemcpy(&c->dd->rows_est[l], L.cell_start.p + L.max_cells, sizeof(int), cudaMemcpyDeviceToHost));
         int maxn = fl[FLAG_MAXDISP + 1];
+        if (L.tiled) {
+            // entries per supercluster row, and the lane-mask blocks (counted: partial tiles + one per exclusion at most)
+            int want = ((int)(maxn * growth) + 16 + 7) / 8 * 8;
+            if (want > L.tl_stride) {
+                L.tl_stride = want;
+                L.tl_entries.alloc((size_t)L.tl_nsc * L.tl_stride);
+            }
+            int nmask = 0;
+            CUDA_TRY(cudaMemcpy(&nmask, L.tl_mask_count.p, sizeof(int), cudaMemcpyDeviceToHost));
+            const int cap = (int)(nmask * growth) + 64;
+            if (cap > L.tl_mask_cap) { L.tl_mask_cap = cap; L.tl_masks.alloc((size_t)cap * 8); }
+            L.dev.tl_stride = L.tl_stride; L.dev.tl_entries = L.tl_entries.p; L.dev.tl_masks = L.tl_masks.p; L.dev.tl_mask_cap = L.tl_mask_cap;
+            L.stride = std::max(L.stride, 32);  // (rows are not built; a non-zero stride marks the list as sized)
+            continue;
+        }
         int want = (int)(maxn * growth) + 16;
         want = (want + 31) / 32 * 32;
         if (want > L.stride) {
@@ -1073,12 +1277,15 @@ static cudaGraphExec_t window_graph(ocm_context* c, int nst) {
 
 static double launches_per_window(const ocm_context* c, int nst) {
     double per_rebuild = 1;
-    for (auto& L : c->lists) if (L->np) per_rebuild += c->periodic ? 5 : 7;
+    for (auto& L : c->lists) if (L->np) per_rebuild += L->tiled ? 9 : (c->periodic ? 5 : 7);
     if (c->nrep > 1) per_rebuild += 2;
     if (c->da.nterms > 0 && c->da.ncand > 0) per_rebuild += 1;
     if (c->dd) per_rebuild += 5;
-    if (c->dd) return per_rebuild + 2.0 * (nst - 1) + nst * (1.0 + (c->pair_blocks > 0 ? 1.0 : 0.0) + (c->local_blocks > 0 ? 1.0 : 0.0));
-    return per_rebuild + nst * (1.0 + (c->pair_blocks > 0 ? 1.0 : 0.0) + (c->local_blocks > 0 ? 1.0 : 0.0));
+    double n_tiled = 0;
+    for (auto& L : c->lists) if (L->np && L->tiled) n_tiled += 1;
+    const double per_step = 1.0 + n_tiled + (c->pair_blocks > 0 ? 1.0 : 0.0) + (c->local_blocks > 0 ? 1.0 : 0.0);
+    if (c->dd) return per_rebuild + 2.0 * (nst - 1) + nst * per_step;
+    return per_rebuild + nst * per_step;
 }
 
 static int quantise_nst(double want) {
@@ -1185,6 +1392,19 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
     c->lists_current = false;
 }
 
+// per-group energies of every term at the current positions (lists must be current), added into egroup
+static void enqueue_energies(ocm_context* c, cudaStream_t s) {
+    if (c->total_blocks > 0) {
+        if (c->periodic) energy_kernel<true><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->da, c->P, c->x.p, c->egroup.p);
+        else energy_kernel<false><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->da, c->P, c->x.p, c->egroup.p);
+    }
+    for (size_t l = 0; l < c->lists.size(); l++) {
+        auto& L = *c->lists[l];
+        if (L.np == 0 || !L.tiled) continue;
+        tile_energy_kernel<true><<<L.dev.row_capacity / 64, kBlock, 0, s>>>(c->d_lists.p, (int)l, c->P, c->egroup.p);
+    }
+}
+
 static void compute_forces_into_fbuf(ocm_context* c) {
     ensure_lists_current(c);
     CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, (size_t)3 * c->n * sizeof(unsigned long long), c->stream));
@@ -1201,8 +1421,7 @@ static void get_state_dd(ocm_context* c, uint32_t mask, double* pos, double* vel
     ensure_lists_current(c);
     std::vector<double> he(40, 0.0);
     CUDA_TRY(cudaMemsetAsync(c->egroup.p, 0, he.size() * sizeof(double), s));
-    if ((epot || ebg) && c->total_blocks > 0)
-        energy_kernel<true><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->da, c->P, c->x.p, c->egroup.p);
+    if (epot || ebg) enqueue_energies(c, s);
     if (force || ekin) {
         compute_forces_into_fbuf(c);
         if (ekin) kinetic_kernel<<<nblk(n, kBlock), kBlock, 0, s>>>(c->P, c->v.p, c->fbuf.p, c->egroup.p + 32);
@@ -1613,14 +1832,27 @@ int ocm_context_set_option(ocm_context* c, const char* key, double value) {
         int t = (int)value;
         if (!(t == 0 || t == 4 || t == 8 || t == 16 || t == 32)) return fail("threads_per_bead must be 0 (auto), 4, 8, 16 or 32");
         c->tpb_opt = t;
-        if (c->lists_ready) build_segments(c);
+        if (c->lists_ready) { build_segments(c); upload_lists(c); c->lists_current = false; }
     } else if (k == "row_staging") {
         c->staging_opt = value != 0 ? 1 : 0;
-        if (c->lists_ready) build_segments(c);
+        if (c->lists_ready) { build_segments(c); upload_lists(c); c->lists_current = false; }
+    } else if (k == "pair_kernel") {
+        // 1 (default): cluster-pair tile lists where the system allows them; 0: per-bead Verlet rows
+        c->tile_opt = value != 0 ? 1 : 0;
+        c->lists_ready = false; c->lists_current = false;
+        drop_graphs(c);
+    } else if (k == "tile_debug") {
+        // timing experiments only (wrong forces): see TileLaunch::debug; 4 = evaluate the list without its switching function
+        c->tile_debug = (int)value;
+        if (c->lists_ready) { build_segments(c); upload_lists(c); }
+    } else if (k == "tile_blocks") {
+        if (value < 0 || value > 65536) return fail("tile_blocks out of range");
+        c->tile_chunk_opt = (int)value;
+        if (c->lists_ready) { build_segments(c); upload_lists(c); }
     } else if (k == "beads_per_block") {
         if (value < 0 || value > 65536) return fail("beads_per_block out of range");
         c->chunk_opt = (int)value;
-        if (c->lists_ready) build_segments(c);
+        if (c->lists_ready) { build_segments(c); upload_lists(c); c->lists_current = false; }
     } else {
         return fail("unknown option: " + k);
     }
@@ -1636,6 +1868,8 @@ int ocm_context_get_option(ocm_context* c, const char* key, double* value) {
     else if (k == "beads_per_block") *value = c->chunk_opt;
     else if (k == "row_staging") *value = c->staging_opt;
     else if (k == "halo_capacity") *value = c->dd ? c->dd->cap : 0;
+    else if (k == "pair_kernel") *value = c->tile_opt;
+    else if (k == "tile_blocks") *value = c->tile_chunk_opt;
     else return fail("unknown option: " + k);
     return 0;
 }
@@ -1744,12 +1978,7 @@ int ocm_get_state(ocm_context* c, uint32_t mask, double* pos, double* vel, doubl
             return fail("get_state: forces restricted to a force-group mask are not supported; request all groups");
         }
         CUDA_TRY(cudaMemsetAsync(c->egroup.p, 0, he.size() * sizeof(double), s));
-        if (epot || ebg) {
-            if (c->total_blocks > 0) {
-                if (c->periodic) energy_kernel<true><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->da, c->P, c->x.p, c->egroup.p);
-                else energy_kernel<false><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->da, c->P, c->x.p, c->egroup.p);
-            }
-        }
+        if (epot || ebg) enqueue_energies(c, s);
         if (force || ekin) {
             compute_forces_into_fbuf(c);
             if (ekin) kinetic_kernel<<<nblk(n, kBlock), kBlock, 0, s>>>(c->P, c->v.p, c->fbuf.p, c->egroup.p + 32);
@@ -1781,10 +2010,7 @@ int ocm_get_replica_energies(ocm_context* c, uint32_t mask, double* epot, double
     std::vector<double> he((size_t)40 * c->nrep, 0.0);
     ensure_lists_current(c);
     CUDA_TRY(cudaMemsetAsync(c->egroup.p, 0, he.size() * sizeof(double), s));
-    if ((epot || ebg) && c->total_blocks > 0) {
-        if (c->periodic) energy_kernel<true><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->da, c->P, c->x.p, c->egroup.p);
-        else energy_kernel<false><<<c->total_blocks, kBlock, 0, s>>>(c->d_segs.p, (int)c->segs.size(), c->d_lists.p, c->d_bonded.p, c->da, c->P, c->x.p, c->egroup.p);
-    }
+    if (epot || ebg) enqueue_energies(c, s);
     if (ekin) {
         compute_forces_into_fbuf(c);
         kinetic_kernel<<<nblk(n, kBlock), kBlock, 0, s>>>(c->P, c->v.p, c->fbuf.p, c->egroup.p + 32);
@@ -1819,7 +2045,8 @@ int ocm_get_neighbor_pairs(ocm_context* c, int term, int32_t* ij, int64_t capaci
     if (ij && capacity > 0) out.alloc((size_t)2 * capacity);
     CUDA_TRY(cudaMemsetAsync(c->pair_counter.p, 0, sizeof(unsigned long long), s));
     if (L.np > 0) {
-        if (c->periodic) extract_pairs_kernel<true><<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->P, rc2, out.p, capacity, c->pair_counter.p);
+        if (L.tiled) tile_extract_pairs_kernel<true><<<L.dev.row_capacity / 64, 128, 0, s>>>(c->d_lists.p, li, c->P, rc2, out.p, capacity, c->pair_counter.p);
+        else if (c->periodic) extract_pairs_kernel<true><<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->P, rc2, out.p, capacity, c->pair_counter.p);
         else extract_pairs_kernel<false><<<nblk(L.np, 128), 128, 0, s>>>(c->d_lists.p, li, c->P, rc2, out.p, capacity, c->pair_counter.p);
     }
     unsigned long long cnt = 0;
@@ -1883,7 +2110,8 @@ int ocm_get_cell_ids(ocm_context* c, int term, int32_t* cell_of_bead, int32_t di
     CUDA_TRY(cudaMemcpy(&g, L.grid.p, sizeof(g), cudaMemcpyDeviceToHost));
     for (int i = 0; i < c->n; i++) cell_of_bead[i] = -1;
     const auto& part = c->sys.pairs[L.terms[0]].part;
-    for (int a = 0; a < L.np; a++) cell_of_bead[part[a]] = cs[a];
+    // (tile lists key their cells by Hilbert rank: report the linear cell id)
+    for (int a = 0; a < L.np; a++) cell_of_bead[part[a]] = (L.tiled && cs[a] >= 0) ? L.cell_inv[cs[a]] : cs[a];
     for (int k = 0; k < 3; k++) dims[k] = g.nc[k];
     return 0;
     OCM_GUARD_END
@@ -1926,8 +2154,19 @@ int ocm_get_counter(ocm_context* c, const char* key, double* value) {
         CUDA_TRY(cudaSetDevice(c->device));
         ensure_lists_current(c);
         double tot = 0;
-        for (auto& L : c->lists) {
+        for (size_t l = 0; l < c->lists.size(); l++) {
+            auto& L = c->lists[l];
             if (!L->np) continue;
+            if (L->tiled) {
+                // lane pairs the tile kernel evaluates: 32 per (i-cluster, j-group) tile
+                unsigned long long nt = 0;
+                CUDA_TRY(cudaMemsetAsync(c->pair_counter.p, 0, sizeof(nt), c->stream));
+                tile_count_kernel<<<L->dev.row_capacity / 64, 128, 0, c->stream>>>(c->d_lists.p, (int)l, c->pair_counter.p);
+                CUDA_TRY(cudaMemcpyAsync(&nt, c->pair_counter.p, sizeof(nt), cudaMemcpyDeviceToHost, c->stream));
+                CUDA_TRY(cudaStreamSynchronize(c->stream));
+                tot += 32.0 * (double)nt;
+                continue;
+            }
             int rows = L->np;
             if (c->dd) CUDA_TRY(cudaMemcpy(&rows, L->cell_start.p + L->max_cells, sizeof(int), cudaMemcpyDeviceToHost));
             std::vector<int> cnt(rows);
@@ -1935,6 +2174,14 @@ int ocm_get_counter(ocm_context* c, const char* key, double* value) {
             for (int v : cnt) tot += v;
         }
         *value = tot;
+    } else if (k.rfind("cell_width_nm.", 0) == 0 || k.rfind("cell_cap.", 0) == 0 || k.rfind("tiled.", 0) == 0) {
+        // the grid rule of the list serving a pair term (the oracle restates it: oracle_get_cell_ids_grid)
+        int term = std::atoi(k.c_str() + k.find('.') + 1);
+        if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");
+        CUDA_TRY(cudaSetDevice(c->device));
+        ensure_lists_current(c);
+        const PairListHost& L = *c->lists[c->term_list[term]];
+        *value = k[0] == 't' ? (L.tiled ? 1.0 : 0.0) : (k[5] == 'w' ? (double)L.cell_width : (double)L.cell_cap);
     } else if (k.rfind("list_cutoff_nm.", 0) == 0) {
         int term = std::atoi(k.c_str() + 15);
         if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");

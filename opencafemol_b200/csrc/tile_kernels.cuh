@@ -1,0 +1,690 @@
+// tile_kernels.cuh — cluster-pair ("tile") pair lists and the warp-tiled pair kernel (sm_100a).
+//
+// What it replaces: the per-bead Verlet rows of kernels.cuh (one 4-byte entry and one 16-byte gather per bead pair,
+// every pair evaluated from both sides).  Here the beads of a pair list are sorted along a Hilbert curve over a fine
+// cell grid; 8 consecutive beads form an i-cluster, 8 i-clusters a supercluster, 4 consecutive beads a j-group.
+// The list of a supercluster S holds one 8-byte entry per j-group that has at least one bead pair inside the list
+// radius, with an 8-bit mask of the i-clusters concerned.  A warp evaluates one (i-cluster, j-group) tile per pass:
+// lane = tj * 8 + ti works on the pair (i = ci * 8 + ti, j = tj), so
+//   * the j-bead is loaded once per entry (coalesced 16-byte loads, 4 addresses per warp) and reused by 8 i-clusters,
+//   * the 64 i-beads sit in shared memory (LDS.128 with 8 distinct addresses per warp),
+//   * Newton's third law: the i-forces stay in registers over the whole list of S (24 accumulators), the j-force
+//     is summed over the 8 i-clusters in registers and reduced over the 8 ti lanes with 9 shuffles per entry,
+//   * per-pair parameters are mixed from per-bead values in registers (no type decode, no coefficient-table look-up).
+// Exclusions, the i < j rule inside a supercluster, interaction classes and padding are 32-bit lane masks, stored only
+// for the entries that need them.  Forces are accumulated in the same 64-bit fixed-point buffer as everything else.
+//
+// OpenMM side this stands for: the CustomNonbondedForce kernels the reference's generators trigger
+// (src/forcefield/*ForceFieldGenerator.cpp::generate), as kernels.cuh.
+#pragma once
+#include "kernels.cuh"
+
+namespace ocm {
+
+constexpr int kTileBlock = 128;       // threads per block of the tile force kernel (4 warps share one supercluster)
+constexpr int kBuildBlock = 256;      // threads per block of the tile list build (8 warps per supercluster)
+constexpr int kBuildBatch = 128;      // candidate superclusters per batch of the build
+
+// supercluster-pair ownership: which of two superclusters lists the other (each unordered pair exactly once, balanced)
+__device__ __forceinline__ bool tile_lists(int s, int o) { return (o > s) == (((s + o) & 1) == 0); }
+
+__device__ __forceinline__ int tile_rows_pad(const PairListDev& L) { return (list_rows(L) + 63) & ~63; }
+
+// ------------------------------------------------------------------------------------------------
+// sorted per-bead arrays of a tile list (after bin / scan / scatter, which key the cells by their Hilbert rank):
+// rank k -> position + mixing parameter a (spos), bead | type << 24 (sbead), (b_in, b_out) (sparam); ranks past the
+// beads present are padding up to a multiple of 64 (sbead = -1)
+__global__ void tile_fill_kernel(const PairListDev* lists, int li, const uint4* __restrict__ posq) {
+    const PairListDev& L = lists[li];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int rows = list_rows(L);
+    if (p >= rows) {
+        if (p < ((rows + 63) & ~63)) {
+            L.spos[p] = make_uint4(0u, 0u, 0u, 0u); L.sbead[p] = -1; L.sparam[p] = make_float2(0.f, 0.f);
+            L.saux[p] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+        }
+        return;
+    }
+    const int a = L.tmp_slots[p];
+    const int c = L.cell_of_slot[a];
+    const int s = L.cell_start[c], e = L.cell_start[c + 1];
+    int r = 0;
+    for (int q = s; q < e; q++) r += (L.tmp_slots[q] < a) ? 1 : 0;
+    const int k = s + r;
+    const int bead = L.part[a];
+    L.sorted_slots[k] = a;
+    L.rank_of_bead[bead] = k;
+    L.bead_of_rank[k] = bead;
+    uint4 q4 = posq[bead];
+    q4.w = __float_as_uint(L.slot_a[a]);
+    L.spos[k] = q4;
+    const int sb = bead | ((L.form == SEG_PAIR_DH) ? 0 : ((int)L.type[a] << 24));
+    const float2 b = L.slot_b[a];
+    L.sbead[k] = sb;
+    L.sparam[k] = b;
+    L.saux[k] = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), (unsigned int)sb, 0u);
+}
+
+// bounding boxes of the superclusters (64 consecutive ranks): centre (fixed point) and half extents (nm).
+// One warp per supercluster.  The extents are taken relative to the first bead with wrapped differences, so the box
+// is a valid periodic interval whatever the spread of the beads.
+__global__ void tile_bbox_kernel(const PairListDev* lists, int li, StepParams P) {
+    const PairListDev& L = lists[li];
+    const int S = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int rows = list_rows(L);
+    if (S * 64 >= rows) return;
+    const uint4 p0 = L.spos[S * 64];
+    int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int h = 0; h < 2; h++) {
+        const int k = S * 64 + h * 32 + lane;
+        if (k < rows) {
+            const uint4 p = L.spos[k];
+            const int d[3] = {(int)(p.x - p0.x), (int)(p.y - p0.y), (int)(p.z - p0.z)};
+            for (int q = 0; q < 3; q++) { lo[q] = min(lo[q], d[q]); hi[q] = max(hi[q], d[q]); }
+        }
+    }
+    for (int q = 0; q < 3; q++)
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[q] = min(lo[q], __shfl_xor_sync(0xffffffffu, lo[q], o));
+            hi[q] = max(hi[q], __shfl_xor_sync(0xffffffffu, hi[q], o));
+        }
+    if (lane == 0) {
+        const unsigned int base[3] = {p0.x, p0.y, p0.z};
+        unsigned int c[3];
+        float hf[3];
+        for (int q = 0; q < 3; q++) {
+            const long long mid = ((long long)lo[q] + (long long)hi[q]) >> 1;
+            c[q] = base[q] + (unsigned int)(int)mid;
+            // half extent, rounded up generously (one fixed-point unit + float rounding)
+            hf[q] = ((float)(((long long)hi[q] - (long long)lo[q] + 3) >> 1)) * P.fscale[q] * 1.000001f;
+        }
+        L.sc_center[S] = make_uint4(c[0], c[1], c[2], 0u);
+        L.sc_half[S] = make_float4(hf[0], hf[1], hf[2], 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// list build.  One block (8 warps) per supercluster S:
+//   1. candidate superclusters O (those S lists by the ownership rule, and S itself) whose bounding box comes within
+//      the list radius of S's box, found in batches of kBuildBatch by an ordered block-wide compaction;
+//   2. every j-group of a candidate is tested against the 64 beads of S with the canonical distance: warp-wide, lane
+//      (ti, tj), one i-cluster per pass.  An entry is emitted when some allowed pair lies inside the list radius; its
+//      lane masks are stored only when they are not all ones.
+// Entries come out ordered by j-group (deterministic).  count_only: only count entries (to size the rows).
+template <bool PER>
+__global__ void __launch_bounds__(kBuildBlock) tile_build_kernel(const PairListDev* lists, int li, StepParams P, int* __restrict__ flags,
+                                                                 int count_only) {
+    const PairListDev& L = lists[li];
+    const int S = blockIdx.x;
+    const int rows = list_rows(L);
+    if (S == 0 && threadIdx.x == 0 && !count_only && rows > L.row_capacity) flags[FLAG_OVERFLOW] = 1;
+    if (S * 64 >= rows) {
+        if (threadIdx.x == 0 && S < L.tl_nsc) { L.tl_count[S] = 0; L.tl_weight[S] = 0; }
+        return;
+    }
+    const int nsc = (rows + 63) >> 6;
+    __shared__ uint4 s_pos[64];
+    __shared__ int s_info[64];            // bead | cls << 24, -1 = padding; bit 31 of a real bead never set
+    __shared__ unsigned char s_own[64];
+    __shared__ int s_cand[kBuildBatch];
+    __shared__ int s_warp_cnt[kBuildBlock / 32];
+    __shared__ uint2 s_stage[kBuildBatch * 16];
+    __shared__ int s_total;   // lane pairs' tiles of the row (sum of the i-cluster mask bits)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 64) {
+        const int k = S * 64 + threadIdx.x;
+        s_pos[threadIdx.x] = L.spos[k];
+        const int sb = L.sbead[k];
+        int info = -1;
+        unsigned char own = 0;
+        if (sb >= 0) {
+            const int bead = sb & 0xFFFFFF;
+            const int cl = L.cls ? (int)L.cls[L.sorted_slots[k]] : 0;
+            info = bead | (cl << 24);
+            own = L.role ? (L.role[bead] == 1) : 1;
+        }
+        s_info[threadIdx.x] = info;
+        s_own[threadIdx.x] = own;
+    }
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    const uint4 cS = L.sc_center[S];
+    const float4 hS = L.sc_half[S];
+    const float rl2 = L.rlist2;
+    const int stride = L.tl_stride;
+    uint2* out = L.tl_entries + (size_t)S * stride;
+    const int ti = lane & 7, tj = lane >> 3;
+    int n_out = 0;  // entries written so far (uniform across the block)
+
+    for (int base = 0; base < nsc; base += kBuildBlock) {
+        // ---- 1. candidates among superclusters [base, base + kBuildBlock) ----
+        const int O = base + threadIdx.x;
+        bool cand = false;
+        if (O < nsc && (O == S || tile_lists(S, O))) {
+            const uint4 cO = L.sc_center[O];
+            const float4 hO = L.sc_half[O];
+            float dx, dy, dz;
+            delta<PER>(cS, cO, P.fscale, dx, dy, dz);
+            dx = fmaxf(0.f, fabsf(dx) - (hS.x + hO.x));
+            dy = fmaxf(0.f, fabsf(dy) - (hS.y + hO.y));
+            dz = fmaxf(0.f, fabsf(dz) - (hS.z + hO.z));
+            cand = (dx * dx + dy * dy + dz * dz) < rl2 * 1.0001f;
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, cand);
+        if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, ncand = 0;
+        for (int w = 0; w < kBuildBlock / 32; w++) { if (w < warp) before += s_warp_cnt[w]; ncand += s_warp_cnt[w]; }
+        // (kBuildBlock may exceed kBuildBatch: process the candidates of this sweep in batches)
+        for (int b0 = 0; b0 < ncand; b0 += kBuildBatch) {
+            __syncthreads();
+            if (cand) {
+                const int pos = before + __popc(bal & ((1u << lane) - 1u)) - b0;
+                if (pos >= 0 && pos < kBuildBatch) s_cand[pos] = O;
+            }
+            __syncthreads();
+            const int nb = min(kBuildBatch, ncand - b0);
+            // ---- 2. the j-groups of the batch: candidate q = (candidate index) * 16 + (j-group within it) ----
+            for (int q = warp; q < nb * 16; q += kBuildBlock / 32) {
+                const int Oq = s_cand[q >> 4];
+                const int j4 = Oq * 16 + (q & 15);
+                const int kj = j4 * 4 + tj;
+                uint2 entry = make_uint2(0xFFFFFFFFu, 0u);
+                if (j4 * 4 < rows) {
+                    const uint4 pj = L.spos[kj];
+                    const int sbj = L.sbead[kj];
+                    const bool real_j = sbj >= 0;
+                    const int bead_j = sbj & 0xFFFFFF;
+                    const int cls_j = (real_j && L.cls) ? (int)L.cls[L.sorted_slots[kj]] : 0;
+                    const bool own_j = real_j && (L.role ? (L.role[bead_j] == 1) : true);
+                    // quick rejection: distance of the j-bead from the box of S
+                    float qx, qy, qz;
+                    delta<PER>(cS, pj, P.fscale, qx, qy, qz);
+                    qx = fmaxf(0.f, fabsf(qx) - hS.x); qy = fmaxf(0.f, fabsf(qy) - hS.y); qz = fmaxf(0.f, fabsf(qz) - hS.z);
+                    const bool near = real_j && (qx * qx + qy * qy + qz * qz) < rl2 * 1.0001f;
+                    if (__any_sync(0xffffffffu, near)) {
+                        unsigned int act = 0;
+                        bool partial = false;
+                        unsigned int masks[8];
+#pragma unroll
+                        for (int ci = 0; ci < 8; ci++) {
+                            const int il = ci * 8 + ti;
+                            const uint4 pi = s_pos[il];
+                            const int info = s_info[il];
+                            bool allowed = real_j && info >= 0;
+                            if (Oq == S) allowed = allowed && (S * 64 + il) < kj;
+                            if (L.cls) allowed = allowed && ((L.allow[(info >> 24) & 31] >> cls_j) & 1u);
+                            if (L.role) allowed = allowed && (own_j || s_own[il]);
+                            float dx, dy, dz;
+                            delta<PER>(pi, pj, P.fscale, dx, dy, dz);
+                            const bool in = allowed && norm2(dx, dy, dz) < rl2;
+                            const unsigned int m = __ballot_sync(0xffffffffu, allowed);
+                            masks[ci] = m;
+                            if (__any_sync(0xffffffffu, in)) { act |= 1u << ci; partial = partial || (m != 0xffffffffu); }
+                        }
+                        if (act) {
+                            unsigned int midx = 0;
+                            if (partial && !count_only) {
+                                if (lane == 0) midx = (unsigned int)atomicAdd(L.tl_mask_count, 1) + 1u;
+                                midx = __shfl_sync(0xffffffffu, midx, 0);
+                                if (midx > (unsigned int)L.tl_mask_cap) { if (lane == 0) flags[FLAG_OVERFLOW] = 1; midx = 0; }
+                                else if (lane < 8) {
+                                    unsigned int mv = 0;
+#pragma unroll
+                                    for (int ci = 0; ci < 8; ci++) mv = (lane == ci) ? masks[ci] : mv;
+                                    L.tl_masks[(size_t)(midx - 1u) * 8 + lane] = mv;
+                                }
+                            } else if (partial && lane == 0) atomicAdd(L.tl_mask_count, 1);
+                            entry = make_uint2((unsigned int)j4, act | (midx << 8));
+                        }
+                    }
+                }
+                if (lane == 0) s_stage[q] = entry;
+            }
+            __syncthreads();
+            // ---- ordered compaction of the batch's entries into the row of S ----
+            for (int q0 = 0; q0 < nb * 16; q0 += kBuildBlock) {
+                const int q = q0 + threadIdx.x;
+                const uint2 e = (q < nb * 16) ? s_stage[q] : make_uint2(0xFFFFFFFFu, 0u);
+                const bool hit = e.x != 0xFFFFFFFFu;
+                const unsigned int hb = __ballot_sync(0xffffffffu, hit);
+                __syncthreads();
+                if (lane == 0) s_warp_cnt[warp] = __popc(hb);
+                __syncthreads();
+                int off = 0, tot = 0;
+                for (int w = 0; w < kBuildBlock / 32; w++) { if (w < warp) off += s_warp_cnt[w]; tot += s_warp_cnt[w]; }
+                if (hit && !count_only) {
+                    const int pos = n_out + off + __popc(hb & ((1u << lane) - 1u));
+                    if (pos < stride) out[pos] = e;
+                    atomicAdd(&s_total, __popc(e.y & 0xffu));
+                }
+                n_out += tot;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (count_only) atomicMax(&flags[FLAG_MAXDISP + 1], n_out);
+        else {
+            if (n_out > stride) { flags[FLAG_OVERFLOW] = 1; n_out = stride; }
+            L.tl_count[S] = n_out;
+            // work estimate of the row in units of one tile evaluation: tiles + entry overheads + the per-row prologue / epilogue
+            L.tl_weight[S] = n_out ? s_total + n_out + 8 : 0;
+        }
+    }
+}
+
+// exclusions: clear the lane bit of every excluded bead pair that the list holds (one thread per exclusion).
+// An entry that had no masks yet gets a block of all ones first (compare-and-swap on its mask index).
+__global__ void tile_excl_kernel(const PairListDev* lists, int li, int* __restrict__ flags, int count_only) {
+    const PairListDev& L = lists[li];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= L.n_excl_pairs) return;
+    const int2 ab = L.excl_pairs[x];
+    const int ka = L.rank_of_bead[ab.x], kb = L.rank_of_bead[ab.y];
+    if (ka < 0 || kb < 0) return;
+    const int Sa = ka >> 6, Sb = kb >> 6;
+    int ki, kj;
+    if (Sa == Sb) { ki = min(ka, kb); kj = max(ka, kb); }
+    else if (tile_lists(Sa, Sb)) { ki = ka; kj = kb; }
+    else { ki = kb; kj = ka; }
+    const int S = ki >> 6, ci = (ki >> 3) & 7, lane = ((kj & 3) << 3) | (ki & 7);
+    const unsigned int j4 = (unsigned int)(kj >> 2);
+    uint2* row = L.tl_entries + (size_t)S * L.tl_stride;
+    int lo = 0, hi = count_only ? 0 : L.tl_count[S];
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (row[mid].x < j4) lo = mid + 1; else hi = mid; }
+    if (count_only) { atomicAdd(L.tl_mask_count, 1); return; }  // worst case: every exclusion opens a mask block
+    if (lo >= L.tl_count[S] || row[lo].x != j4) return;
+    unsigned int* py = &row[lo].y;
+    unsigned int y = *(volatile unsigned int*)py;
+    if ((y >> 8) == 0u) {
+        const unsigned int mine = (unsigned int)atomicAdd(L.tl_mask_count, 1) + 1u;
+        if (mine > (unsigned int)L.tl_mask_cap) { flags[FLAG_OVERFLOW] = 1; return; }
+        for (int w = 0; w < 8; w++) L.tl_masks[(size_t)(mine - 1u) * 8 + w] = 0xffffffffu;
+        __threadfence();
+        const unsigned int old = atomicCAS(py, y, y | (mine << 8));
+        y = (old == y) ? (y | (mine << 8)) : old;  // lost the race: use the winner's block (ours stays unused)
+    }
+    atomicAnd(&L.tl_masks[(size_t)((y >> 8) - 1u) * 8 + ci], ~(1u << lane));
+}
+
+// exclusive prefix sum of the row weights (tl_weight: estimated work of a row): the force launch cuts the concatenated
+// entry stream into shares of equal weight, one per block.  tl_start[nsc] = total.  Single block.
+__global__ void tile_scan_kernel(const PairListDev* lists, int li, int nsc) {
+    const PairListDev& L = lists[li];
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int base = 0; base < nsc; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = (i < nsc) ? L.tl_weight[i] : 0;
+        int s = v;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        if (lane == 31) warp_sums[wid] = s;
+        __syncthreads();
+        if (wid == 0) {
+            int ws = (lane < nw) ? warp_sums[lane] : 0;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += t; }
+            warp_sums[lane] = ws;
+        }
+        __syncthreads();
+        if (i < nsc) L.tl_start[i] = carry + (wid > 0 ? warp_sums[wid - 1] : 0) + s - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_sums[nw - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) L.tl_start[nsc] = carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair evaluation
+struct TileForm {
+    float rc2;
+    float alpha, beta;     // -dE/dr / r = e q3 (alpha q3 - beta) / r^2, q = s^2 / r^2, s = a_i + a_j
+    float qz;              // inner zone: q > qz
+    float rsw, inv_sw, sw_c0, sw_c1;  // switch: t = sat(r inv_sw - sw_c0), -kappa S'(r) = sw_c1 (t - t^2)^2
+    float kappa;           // switched energy: E = e kappa q3 (q3 - 1)
+    float inv_debye;       // screened Coulomb
+};
+
+// two-zone 12-6 family with per-bead mixing.  a = s_i + s_j partial sums, (b, c) = inner / outer strength.
+template <bool SW, bool GEO>
+__device__ __forceinline__ float tile_pair_tz(const TileForm& F, float r2, float ai, float aj, float2 bi, float2 bj) {
+    const float s = ai + aj;
+    const float s2 = s * s;
+    const float ir = fast_rsqrt(r2);
+    const float ir2 = ir * ir;
+    const float q = s2 * ir2;
+    const float q3 = q * q * q;
+    const float e_in = GEO ? bi.x * bj.x : bi.x + bj.x;
+    const float e_out = bi.y + bj.y;
+    const float e = (q > F.qz) ? e_in : e_out;
+    const float g = fmaf(F.alpha, q3, -F.beta);
+    if (!SW) return (e * q3) * (g * ir2);
+    // OpenMM switching function on [rsw, rc]: S = 1 - 10 t^3 + 15 t^4 - 6 t^5, S' = -30 t^2 (1-t)^2 / (rc - rsw);
+    //   -d(S E)/dr / r = S (e q3 g / r^2) - E S'/r,  E = e kappa q3 (q3 - 1)
+    //                  = (e q3 / r) [ (g / r) S - kappa S'(r) (q3 - 1) ]
+    const float r = r2 * ir;
+    const float t = __saturatef(fmaf(r, F.inv_sw, -F.sw_c0));
+    const float t2 = t * t;
+    const float Sw = fmaf(t2 * t, fmaf(t, fmaf(t, -6.f, 15.f), -10.f), 1.f);
+    const float w = t - t2;
+    const float u3 = (q3 - 1.f) * (w * w);
+    const float inner = fmaf(u3, F.sw_c1, (g * ir) * Sw);   // sw_c1 = 30 kappa / (rc - rsw)
+    return ((e * q3) * ir) * inner;
+}
+
+// screened Coulomb: E = q_i q_j K (exp(-r / debye) / r - cc); a = q sqrt(K)
+__device__ __forceinline__ float tile_pair_dh(const TileForm& F, float r2, float ai, float aj) {
+    const float ir = fast_rsqrt(r2);
+    const float r = r2 * ir;
+    const float ex = __expf(-r * F.inv_debye);
+    return ai * aj * ex * (ir + F.inv_debye) * ir * ir;
+}
+
+// Launch description of the tile force kernel (one launch per tile list), passed BY VALUE: every field is a constant-bank
+// operand, no dependent global loads before the first useful instruction and no registers spent on per-list constants.
+struct TileSegP {
+    int nblocks, nsc, stride, pad;
+    const uint2* entries; const int* count; const int* start; const uint4* spos; const uint4* saux; const unsigned int* masks; const uint4* sc_center;
+    float rc2, alpha, beta, qz, inv_sw, sw_c0, sw_c1, inv_debye;
+};
+struct TileLaunch {
+    int n, pdl_early;
+    int debug;   // timing experiments only (option tile_debug): 1 = no j-force atomics, 2 = no i-force atomics, 8 = skip every tile evaluation
+    float fscale[3];
+    float half_box[3];
+    TileSegP seg;
+};
+
+// one (i, j) lane pair in two phases (so that two tiles can share a basic block and a vote).
+// pi = (x, y, z fixed point, a) of the i-bead, pj likewise.  The difference of the fixed-point integers is the minimum
+// image whatever the box (FP32 offsets from the supercluster centre would save 6 instructions per pair but are only
+// the minimum image when supercluster extent + cutoff < half the box, which a 15 nm slab box does not guarantee).
+struct TilePair { float dx, dy, dz, r2; bool in; };
+__device__ __forceinline__ TilePair tile_geom(const TileLaunch& T, const uint4 pi, const uint4 pj, bool ok) {
+    TilePair t;
+    t.dx = __int2float_rn((int)(pi.x - pj.x)) * T.fscale[0];
+    t.dy = __int2float_rn((int)(pi.y - pj.y)) * T.fscale[1];
+    t.dz = __int2float_rn((int)(pi.z - pj.z)) * T.fscale[2];
+    t.r2 = norm2(t.dx, t.dy, t.dz);
+    t.in = ok && t.r2 < T.seg.rc2;
+    return t;
+}
+template <int FORM, bool SW, bool GEO>
+__device__ __forceinline__ void tile_eval(const TileLaunch& T, const TilePair& t, float ai, const float2 bi, float aj, const float2 bj,
+                                          float& fix, float& fiy, float& fiz, float& fjx, float& fjy, float& fjz) {
+    TileForm F;
+    const TileSegP& G = T.seg;
+    F.rc2 = G.rc2; F.alpha = G.alpha; F.beta = G.beta; F.qz = G.qz; F.inv_sw = G.inv_sw; F.sw_c0 = G.sw_c0; F.sw_c1 = G.sw_c1; F.inv_debye = G.inv_debye;
+    float fr;
+    if (FORM == SEG_PAIR_TZ) fr = tile_pair_tz<SW, GEO>(F, t.r2, ai, aj, bi, bj);
+    else fr = tile_pair_dh(F, t.r2, ai, aj);
+    fr = t.in ? fr : 0.f;
+    fix = fmaf(fr, t.dx, fix); fiy = fmaf(fr, t.dy, fiy); fiz = fmaf(fr, t.dz, fiz);
+    fjx = fmaf(-fr, t.dx, fjx); fjy = fmaf(-fr, t.dy, fjy); fjz = fmaf(-fr, t.dz, fjz);
+}
+
+// One block = 4 warps on one chunk (`per` entries) of the entry row of one supercluster.
+template <int FORM, bool SW, bool GEO>
+__device__ __forceinline__ void tile_chunk(const TileLaunch& T, int S, int e_begin, int e_end,
+                                           unsigned long long* __restrict__ fbuf, uint4* s_pos, float2* s_par, int* s_bead, float* s_acc) {
+    const TileSegP& G = T.seg;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ti = lane & 7, tj = lane >> 3;
+    __syncthreads();  // (a block may work on several superclusters in turn: the previous one is done with shared memory)
+    if (threadIdx.x < 64) {
+        const uint4 ax = G.saux[S * 64 + threadIdx.x];
+        s_pos[threadIdx.x] = G.spos[S * 64 + threadIdx.x];
+        s_par[threadIdx.x] = make_float2(__uint_as_float(ax.x), __uint_as_float(ax.y));
+        s_bead[threadIdx.x] = (int)ax.z;
+    }
+    // this warp's entries e_begin + warp + 4 l (l = 0, 1, ...): lane l fetches entry l, shuffles hand them out
+    const uint2* __restrict__ row = G.entries + (size_t)S * G.stride;
+    const int n_mine = (e_end - e_begin - warp + 3) >> 2;
+    uint2 ent_l = make_uint2(0u, 0u);
+    if (lane < n_mine) ent_l = __ldg(&row[e_begin + warp + 4 * lane]);
+    __syncthreads();
+    const uint4* my_pos = s_pos + ti;
+    const float2* my_par = s_par + ti;
+    float fi[8][3];
+#pragma unroll
+    for (int ci = 0; ci < 8; ci++) { fi[ci][0] = 0.f; fi[ci][1] = 0.f; fi[ci][2] = 0.f; }
+
+    uint4 pj = make_uint4(0u, 0u, 0u, 0u), xj = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+    {
+        const unsigned int j4 = __shfl_sync(0xffffffffu, ent_l.x, 0);
+        if (n_mine > 0) { const int kj = (int)j4 * 4 + tj; pj = __ldg(&G.spos[kj]); xj = __ldg(&G.saux[kj]); }
+    }
+    for (int it = 0; it < n_mine; it++) {
+        const unsigned int ey = __shfl_sync(0xffffffffu, ent_l.y, it);
+        // prefetch the j-bead of the next entry
+        uint4 pj_n = make_uint4(0u, 0u, 0u, 0u), xj_n = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+        {
+            const unsigned int j4n = __shfl_sync(0xffffffffu, ent_l.x, (it + 1) & 31);
+            if (it + 1 < n_mine) { const int kn = (int)j4n * 4 + tj; pj_n = __ldg(&G.spos[kn]); xj_n = __ldg(&G.saux[kn]); }
+        }
+        const unsigned int act = ey & 0xffu, midx = ey >> 8;
+        // lane masks of the entry (only the entries with exclusions, the i < j rule or padding have any)
+        unsigned int lane_ok = 0xffu;
+        if (midx) {
+            const unsigned int mw = __ldg(&G.masks[(size_t)(midx - 1u) * 8 + ti]);   // lane ti fetches the word of i-cluster ti
+            lane_ok = 0u;
+#pragma unroll
+            for (int ci = 0; ci < 8; ci++) lane_ok |= ((__shfl_sync(0xffffffffu, mw, ci) >> lane) & 1u) << ci;
+        }
+        const float aj = __uint_as_float(pj.w);
+        const float2 bj = make_float2(__uint_as_float(xj.x), __uint_as_float(xj.y));
+        float fjx = 0.f, fjy = 0.f, fjz = 0.f;
+        // i-clusters in pairs: when both are active the two evaluations share a basic block and interleave (ILP 2)
+#pragma unroll
+        for (int c2 = 0; c2 < 8; c2 += 2) {
+            const unsigned int a2 = (T.debug & 8) ? 0u : ((act >> c2) & 3u);
+            if (a2 == 0u) continue;  // warp-uniform
+            if (a2 == 3u) {
+                const uint4 pa = my_pos[c2 * 8], pb = my_pos[c2 * 8 + 8];
+                const TilePair ta = tile_geom(T, pa, pj, (lane_ok >> c2) & 1u), tb = tile_geom(T, pb, pj, (lane_ok >> (c2 + 1)) & 1u);
+                if (!__any_sync(0xffffffffu, ta.in || tb.in)) continue;  // both tiles sit in the skin at this step
+                tile_eval<FORM, SW, GEO>(T, ta, __uint_as_float(pa.w), my_par[c2 * 8], aj, bj, fi[c2][0], fi[c2][1], fi[c2][2], fjx, fjy, fjz);
+                tile_eval<FORM, SW, GEO>(T, tb, __uint_as_float(pb.w), my_par[c2 * 8 + 8], aj, bj, fi[c2 + 1][0], fi[c2 + 1][1], fi[c2 + 1][2], fjx, fjy, fjz);
+            } else if (a2 == 1u) {
+                const uint4 pa = my_pos[c2 * 8];
+                const TilePair ta = tile_geom(T, pa, pj, (lane_ok >> c2) & 1u);
+                if (!__any_sync(0xffffffffu, ta.in)) continue;
+                tile_eval<FORM, SW, GEO>(T, ta, __uint_as_float(pa.w), my_par[c2 * 8], aj, bj, fi[c2][0], fi[c2][1], fi[c2][2], fjx, fjy, fjz);
+            } else {
+                const uint4 pb = my_pos[c2 * 8 + 8];
+                const TilePair tb = tile_geom(T, pb, pj, (lane_ok >> (c2 + 1)) & 1u);
+                if (!__any_sync(0xffffffffu, tb.in)) continue;
+                tile_eval<FORM, SW, GEO>(T, tb, __uint_as_float(pb.w), my_par[c2 * 8 + 8], aj, bj, fi[c2 + 1][0], fi[c2 + 1][1], fi[c2 + 1][2], fjx, fjy, fjz);
+            }
+        }
+        // j-force: sum over the 8 ti lanes of each tj group with 6 shuffles; x, y, z end up in lanes ti = 0, 1, 2
+        fjx += __shfl_down_sync(0xffffffffu, fjx, 1);
+        fjy += __shfl_up_sync(0xffffffffu, fjy, 1);
+        fjz += __shfl_down_sync(0xffffffffu, fjz, 1);
+        if (ti & 1) fjx = fjy;
+        fjx += __shfl_down_sync(0xffffffffu, fjx, 2);
+        fjz += __shfl_up_sync(0xffffffffu, fjz, 2);
+        if (ti & 2) fjx = fjz;
+        fjx += __shfl_down_sync(0xffffffffu, fjx, 4);
+        const int sbj = (int)xj.z;
+        if (sbj >= 0 && ti < 3 && !(T.debug & 1))
+            atomicAdd(&fbuf[(size_t)ti * T.n + (sbj & 0xFFFFFF)], (unsigned long long)(long long)(fjx * 4294967296.0f));
+        pj = pj_n; xj = xj_n;
+    }
+    // i-forces: over the 4 tj groups by a transposing shuffle reduction (24 values -> 12 -> 6 per lane), over the 4 warps
+    // in shared memory in a fixed order (run-to-run reproducible), then one atomic triple per i-bead
+    float r1[12];
+#pragma unroll
+    for (int m = 0; m < 12; m++) {
+        const float lo = fi[m / 3][m % 3], hi = fi[m / 3 + 4][m % 3];
+        const float send = (tj & 1) ? lo : hi, keep = (tj & 1) ? hi : lo;
+        r1[m] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int m = 0; m < 6; m++) {
+        const float send = (tj & 2) ? r1[m] : r1[m + 6], keep = (tj & 2) ? r1[m + 6] : r1[m];
+        const float v = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        // this lane now holds component q of i-cluster ci, both functions of (m, tj)
+        const int M = m + ((tj & 2) ? 6 : 0) + ((tj & 1) ? 12 : 0);
+        const int ci = M / 3, q = M - ci * 3;
+        s_acc[warp * 192 + q * 64 + ci * 8 + ti] = v;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 192; t += kTileBlock) {
+        const float v = (s_acc[t] + s_acc[192 + t]) + (s_acc[384 + t] + s_acc[576 + t]);
+        const int il = t & 63, q = t >> 6;
+        const int sb = s_bead[il];
+        if (sb >= 0 && v != 0.f && !(T.debug & 2)) atomicAdd(&fbuf[(size_t)q * T.n + (sb & 0xFFFFFF)], (unsigned long long)(long long)(v * 4294967296.0f));
+    }
+}
+
+#ifndef OCM_TILE_MINBLOCKS
+#define OCM_TILE_MINBLOCKS 5
+#endif
+// Persistent launch, one wave: block b works on the share [W b / B, W (b+1) / B) of the list's work W (row weights, prefix
+// sums in start[]); inside a row the weight is taken as spread evenly over its entries.
+template <int FORM, bool SW, bool GEO>
+__global__ void __launch_bounds__(kTileBlock, OCM_TILE_MINBLOCKS) tile_force_kernel(const __grid_constant__ TileLaunch T, unsigned long long* __restrict__ fbuf) {
+    __shared__ uint4 s_pos[64];
+    __shared__ float2 s_par[64];
+    __shared__ int s_bead[64];
+    __shared__ float s_acc[(kTileBlock / 32) * 192];
+    if (T.pdl_early) pdl_trigger();
+    pdl_wait();
+    const TileSegP& G = T.seg;
+    const int* __restrict__ start = G.start;
+    const long long W = start[G.nsc];
+    const int t0 = (int)(W * blockIdx.x / G.nblocks), t1 = (int)(W * (blockIdx.x + 1) / G.nblocks);
+    if (t0 >= t1) return;
+    // first row: the last S with start[S] <= t0
+    int lo = 0, hi = G.nsc - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (start[mid] <= t0) lo = mid; else hi = mid - 1; }
+    for (int S = lo; S < G.nsc; S++) {
+        const int w0 = start[S], w1 = start[S + 1];
+        if (w0 >= t1) break;
+        if (w1 == w0) continue;
+        const int cnt = G.count[S];
+        // entry range of this block inside the row (multiples of 4: one entry per warp and pass); both neighbours of a cut use
+        // the same formula, so the shares tile the row exactly
+        const int e_begin = (t0 <= w0) ? 0 : (int)(((long long)(t0 - w0) * cnt / (w1 - w0)) & ~3ll);
+        const int e_end = (t1 >= w1) ? cnt : (int)(((long long)(t1 - w0) * cnt / (w1 - w0)) & ~3ll);
+        // (at most 128 entries per pass: each lane of a warp fetches one of its warp's entries)
+        for (int eb = e_begin; eb < e_end; eb += 128)
+            tile_chunk<FORM, SW, GEO>(T, S, eb, min(e_end, eb + 128), fbuf, s_pos, s_par, s_bead, s_acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// observer side on tile lists: per-member energies (double accumulation), one warp per (supercluster, 8 entries)
+template <bool PER>
+__global__ void __launch_bounds__(kBlock) tile_energy_kernel(const PairListDev* __restrict__ lists, int li, StepParams P, double* __restrict__ egroup) {
+    const PairListDev& L = lists[li];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ti = lane & 7, tj = lane >> 3;
+    const int S = blockIdx.x;
+    double Em[kMaxMembers] = {0, 0, 0, 0};
+    if (S * 64 < list_rows(L)) {
+        const int cnt = L.tl_count[S];
+        const uint2* row = L.tl_entries + (size_t)S * L.tl_stride;
+        const int nt = L.ntypes;
+        for (int e = warp; e < cnt; e += kBlock / 32) {
+            const uint2 ent = row[e];
+            const int kj = (int)ent.x * 4 + tj;
+            const uint4 pj = L.spos[kj];
+            const int sbj = L.sbead[kj];
+            const unsigned int act = ent.y & 0xffu, midx = ent.y >> 8;
+            for (int ci = 0; ci < 8; ci++) {
+                if (!((act >> ci) & 1u)) continue;
+                const int ki = S * 64 + ci * 8 + ti;
+                const uint4 pi = L.spos[ki];
+                const int sbi = L.sbead[ki];
+                bool ok = sbi >= 0 && sbj >= 0;
+                if (midx) ok = ok && ((L.tl_masks[(size_t)(midx - 1u) * 8 + ci] >> lane) & 1u);
+                if (!ok) continue;
+                float dx, dy, dz;
+                delta<PER>(pi, pj, P.fscale, dx, dy, dz);
+                const float r2 = norm2(dx, dy, dz);
+                // slab decomposition: a pair of beads owned by two ranks is listed on both; each reports half
+                double wgt = 1.0;
+                if (L.role) wgt = 0.5 * ((L.role[sbi & 0xFFFFFF] == 1 ? 1.0 : 0.0) + (L.role[sbj & 0xFFFFFF] == 1 ? 1.0 : 0.0));
+                if (L.form == SEG_PAIR_DH) {
+                    if (r2 < L.rc2) {
+                        const float ir = rsqrtf(r2), r = r2 * ir;
+                        Em[0] += wgt * (double)(__uint_as_float(pi.w) * __uint_as_float(pj.w) * (__expf(-r * L.inv_debye) * ir - L.dh_cc));
+                    }
+                } else {
+                    const int tix = (int)((unsigned int)sbi >> 24) * nt + (int)((unsigned int)sbj >> 24);
+                    for (int m = 0; m < L.nmem; m++) {
+                        if (!(r2 < L.mem_rc2[m])) continue;
+                        const float4 cin = L.memE[m][2 * tix], co = L.memE[m][2 * tix + 1];
+                        const bool inner = r2 < cin.w;
+                        const float c12 = inner ? cin.x : co.x, c6 = inner ? cin.y : co.y, c0 = inner ? cin.z : co.z;
+                        const float ir2 = 1.0f / r2, ir6 = ir2 * ir2 * ir2;
+                        float E = (c12 * ir6 - c6) * ir6 + c0;
+                        if (L.mem_switch[m] && r2 > L.rsw * L.rsw) {
+                            const float t = (sqrtf(r2) - L.rsw) * L.inv_sw;
+                            E *= 1.f + t * t * t * (-10.f + t * (15.f - 6.f * t));
+                        }
+                        Em[m] += wgt * (double)E;
+                    }
+                }
+            }
+        }
+    }
+    const int nm = (L.form == SEG_PAIR_DH) ? 1 : L.nmem;
+    for (int m = 0; m < nm; m++) block_add(Em[m], &egroup[L.mem_group[m]]);
+}
+
+// pairs (i < j by bead index) of a tile list inside rc2_term, appended unordered (host sorts); canonical distance
+template <bool PER>
+__global__ void tile_extract_pairs_kernel(const PairListDev* lists, int li, StepParams P, float rc2_term, int* __restrict__ out, long long capacity,
+                                          unsigned long long* __restrict__ counter) {
+    const PairListDev& L = lists[li];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ti = lane & 7, tj = lane >> 3;
+    const int S = blockIdx.x;
+    if (S * 64 >= list_rows(L)) return;
+    const int cnt = L.tl_count[S];
+    const uint2* row = L.tl_entries + (size_t)S * L.tl_stride;
+    for (int e = warp; e < cnt; e += blockDim.x / 32) {
+        const uint2 ent = row[e];
+        const int kj = (int)ent.x * 4 + tj;
+        const uint4 pj = L.spos[kj];
+        const int sbj = L.sbead[kj];
+        const unsigned int act = ent.y & 0xffu, midx = ent.y >> 8;
+        for (int ci = 0; ci < 8; ci++) {
+            if (!((act >> ci) & 1u)) continue;
+            const int ki = S * 64 + ci * 8 + ti;
+            const int sbi = L.sbead[ki];
+            bool ok = sbi >= 0 && sbj >= 0;
+            if (midx) ok = ok && ((L.tl_masks[(size_t)(midx - 1u) * 8 + ci] >> lane) & 1u);
+            if (!ok) continue;
+            float dx, dy, dz;
+            delta<PER>(L.spos[ki], pj, P.fscale, dx, dy, dz);
+            if (norm2(dx, dy, dz) < rc2_term) {
+                const int bi = sbi & 0xFFFFFF, bj = sbj & 0xFFFFFF;
+                const unsigned long long pos = atomicAdd(counter, 1ull);
+                if (out && (long long)pos < capacity) { out[2 * pos] = min(bi, bj); out[2 * pos + 1] = max(bi, bj); }
+            }
+        }
+    }
+}
+
+// number of (i-cluster, j-group) tiles the force launch evaluates (32 lane pairs each)
+__global__ void tile_count_kernel(const PairListDev* lists, int li, unsigned long long* __restrict__ counter) {
+    const PairListDev& L = lists[li];
+    const int S = blockIdx.x;
+    if (S * 64 >= list_rows(L)) return;
+    const int cnt = L.tl_count[S];
+    const uint2* row = L.tl_entries + (size_t)S * L.tl_stride;
+    unsigned long long n = 0;
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) n += __popc(row[e].y & 0xffu);
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, n);
+}
+
+}  // namespace ocm

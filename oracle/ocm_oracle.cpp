@@ -1446,18 +1446,33 @@ int oracle_get_neighbor_pairs(ocm_context* c, int term, int32_t* ij, int64_t cap
 // term's list cutoff (effective rc + skin); see DESIGN.md "cell grid".
 // rlist = list cutoff (interaction cutoff of the list serving the term + skin), reported by the engine
 // through ocm_get_counter("list_cutoff_nm.<term>").
+static int cell_ids_grid(ocm_context* c, int term, float wmin, long long cap, int32_t* cell_of_bead, int32_t dims[3]);
+
 int oracle_get_cell_ids_rlist(ocm_context* c, int term, double rlist, int32_t* cell_of_bead, int32_t dims[3]) {
     if (!c || !cell_of_bead || !dims) return fail("null argument");
     if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");
+    // Verlet-row lists: cells of half the list radius; only the (mostly empty) virtual box of an unlimited-boundary system
+    // widens them, until their number is of the order of the participants
+    const long long cap = c->sys.has_box ? -1 : std::max<long long>(4096, 8 * (long long)c->sys.pairs[term].part.size() + 64);
+    return cell_ids_grid(c, term, 0.5f * (float)rlist, cap, cell_of_bead, dims);
+}
+
+// The grid rule with its two inputs given explicitly (the engine reports them: counters cell_width_nm.<term> and
+// cell_cap.<term>): cells of width >= wmin, widened by factors of 1.25 until there are at most `cap` of them (cap < 0: never).
+// Tile lists use cells of a sixth of the list radius capped at one cell per participant.
+int oracle_get_cell_ids_grid(ocm_context* c, int term, double wmin, long long cap, int32_t* cell_of_bead, int32_t dims[3]) {
+    if (!c || !cell_of_bead || !dims) return fail("null argument");
+    if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");
+    return cell_ids_grid(c, term, (float)wmin, cap, cell_of_bead, dims);
+}
+
+static int cell_ids_grid(ocm_context* c, int term, float wmin, long long cap, int32_t* cell_of_bead, int32_t dims[3]) {
     const PairTerm& t = c->sys.pairs[term];
     Canon q = canonicalise(*c);
     int n = c->sys.n;
-    float wmin = 0.5f * (float)rlist;
     for (int i = 0; i < n; i++) cell_of_bead[i] = -1;
     if (q.periodic) {
         int nc[3];
-        // (virtual box of an unlimited-boundary system: cells widened until their number is of the order of the participants)
-        const long long cap = std::max<long long>(4096, 8 * (long long)t.part.size() + 64);
         float w = wmin;
         for (;;) {
             long long tot = 1;
@@ -1467,7 +1482,7 @@ int oracle_get_cell_ids_rlist(ocm_context* c, int term, double rlist, int32_t* c
                 dims[k] = nc[k];
                 tot *= nc[k];
             }
-            if (c->sys.has_box || tot <= cap) break;
+            if (cap < 0 || tot <= cap) break;
             w *= 1.25f;
         }
         for (int i : t.part) {

@@ -234,13 +234,14 @@ def test_cell_assignment_bit_exact(engine, oracle):
         ctx.get_state(energy=True)  # lists sized: the virtual box of the unlimited-boundary case is laid out
         sync_canon(ctx, ora)
         for t in range(ctx.num_pair_terms()):
-            rlist = ctx.counter(f"list_cutoff_nm.{t}")
+            # the grid rule has two inputs, which the engine reports (rows: half the list radius; tiles: a sixth of it, capped)
+            width, cap = ctx.counter(f"cell_width_nm.{t}"), int(ctx.counter(f"cell_cap.{t}"))
             ids, dims = ctx.cell_ids(t)
             oid = np.zeros(spec.mass.size, np.int32)
             od = np.zeros(3, np.int32)
-            fn = oracle.dll.oracle_get_cell_ids_rlist
-            fn.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
-            assert fn(ora.handle, t, rlist, oid.ctypes.data_as(C.POINTER(C.c_int32)), od.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+            fn = oracle.dll.oracle_get_cell_ids_grid
+            fn.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_longlong, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+            assert fn(ora.handle, t, width, cap, oid.ctypes.data_as(C.POINTER(C.c_int32)), od.ctypes.data_as(C.POINTER(C.c_int32))) == 0
             assert np.array_equal(dims, od), (dims, od)
             assert np.array_equal(ids, oid)
 

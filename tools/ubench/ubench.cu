@@ -1,13 +1,13 @@
 // ubench.cu — instruction-throughput microbenchmarks behind the pair-kernel design.
-// Each test runs N_ITER x 8 independent chains of one instruction per thread, 148 x 2 blocks of 512 threads
-// (16 warps per SMSP), and reports warp-instructions per clock per SM from the per-block clock64() span.
+// Each test runs N_ITER x 8 independent chains of one instruction per thread, 148 blocks of 1024 threads
+// (8 warps per SMSP), and reports warp-instructions per clock per SM from the per-block clock64() span.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench ubench.cu && ./ubench
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 
-constexpr int N_ITER = 512;
+constexpr int N_ITER = 4096;
 
 enum Op { FFMA, FMUL, FADD, I2F, MUFU_RCP, MUFU_RSQ, MUFU_EX2, SHFL, IADD, LOP, FSEL, FSETP_SEL, LDS128_BCAST, LDS128_8, LDS128_RAND, LDS64_RAND, LDS32_RAND,
           FFMA_I2F, FFMA_MUFU, FFMA_IADD, FFMA_SHFL, FFMA_LDS, F2I, IMAD, RED64, RED32F, FFMA2, FADD2, FFMA2_ALU, FFMA_ALU3, N_OPS };
@@ -18,7 +18,7 @@ const char* names[] = {"FFMA", "FMUL", "FADD", "I2FP.F32.S32", "MUFU.RCP", "MUFU
                        "FFMA2+IADD3+LOP3+FSEL (1:1:1:1)", "FFMA+IADD3+LOP3+FSEL (1:1:1:1)"};
 
 template <int OP>
-__global__ void __launch_bounds__(512) k(float* out, long long* cyc, unsigned long long* red, int seed) {
+__global__ void __launch_bounds__(1024) k(float* out, long long* cyc, unsigned long long* red, int seed) {
     __shared__ float4 sm[1024];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = make_float4(i * 1e-3f, 1.f, 2.f, 3.f);
     __syncthreads();
@@ -26,25 +26,25 @@ __global__ void __launch_bounds__(512) k(float* out, long long* cyc, unsigned lo
     int b[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) { a[u] = 1.0f + (threadIdx.x + u) * 1e-6f; a2[u] = a[u] + 0.5f; b[u] = threadIdx.x * 7 + u + seed; }
-    const float m = 0.999f + seed * 1e-9f, c = 1e-3f;
+    const float m = 0.999f + seed * 1e-9f, c = 1e-3f, cc = 1e-3f + seed * 1e-9f;
     const int lane = threadIdx.x & 31;
     unsigned int r = (threadIdx.x * 2654435761u) >> 22;  // random 10-bit index
     const long long t0 = clock64();
     for (int it = 0; it < N_ITER; it++) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            if (OP == FFMA) a[u] = fmaf(a[u], m, c);
-            if (OP == FMUL) a[u] = a[u] * m;
-            if (OP == FADD) a[u] = a[u] + c;
-            if (OP == I2F) { a[u] += 0.f; asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(a[u]) : "r"(b[u])); b[u] = __float_as_int(a[u]); }
+            if (OP == FFMA) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[u]) : "f"(m), "f"(cc));
+            if (OP == FMUL) asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(a[u]) : "f"(m));
+            if (OP == FADD) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[u]) : "f"(cc));
+            if (OP == I2F) { asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(a[u]) : "r"(b[u])); b[u] = __float_as_int(a[u]); }
             if (OP == F2I) { asm volatile("cvt.rni.s32.f32 %0, %1;" : "=r"(b[u]) : "f"(a[u])); a[u] = __int_as_float(b[u] | 0x3f800000); }
-            if (OP == MUFU_RCP) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[u]));
+            if (OP == MUFU_RCP) { float t; asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(a[u])); a[u] = t; }
             if (OP == MUFU_RSQ) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(a[u]));
             if (OP == MUFU_EX2) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[u]));
             if (OP == SHFL) a[u] = __shfl_xor_sync(0xffffffffu, a[u], 1 + (u & 3));
-            if (OP == IADD) asm volatile("add.s32 %0, %0, %1;" : "+r"(b[u]) : "r"(seed + u));
+            if (OP == IADD) asm volatile("add.s32 %0, %0, %1;" : "+r"(b[u]) : "r"(b[(u + 1) & 7]));
             if (OP == IMAD) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(b[u]) : "r"(seed + 3), "r"(u));
-            if (OP == LOP) asm volatile("xor.b32 %0, %0, %1;" : "+r"(b[u]) : "r"(seed + u));
+            if (OP == LOP) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[u]) : "r"(seed + u), "r"(it));
             if (OP == FSEL) a[u] = (b[u] > seed) ? a[u] : c;
             if (OP == FSETP_SEL) a[u] = (a[u] < m) ? a[u] + 0.f : c;
             if (OP == LDS128_BCAST) { float4 v = sm[(it + u) & 1023]; a[u] += v.x; }
@@ -83,21 +83,27 @@ __global__ void __launch_bounds__(512) k(float* out, long long* cyc, unsigned lo
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+static float g_ms = 0;
 template <int OP>
 void run(float* out, long long* cyc, unsigned long long* red, int nblk) {
     std::vector<long long> h(nblk);
     double best = 1e30;
     for (int rep = 0; rep < 3; rep++) {
-        k<OP><<<nblk, 512>>>(out, cyc, red, rep);
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        k<OP><<<nblk, 1024>>>(out, cyc, red, rep);
+        cudaEventRecord(e1);
         cudaDeviceSynchronize();
+        float ms; cudaEventElapsedTime(&ms, e0, e1); g_ms = ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
         cudaMemcpy(h.data(), cyc, nblk * sizeof(long long), cudaMemcpyDeviceToHost);
         double mx = 0;
         for (long long v : h) mx = v > mx ? v : mx;
         if (rep && mx < best) best = mx;
     }
-    // per SM: 2 blocks x 16 warps x N_ITER x 8 instructions (mixed tests count every instruction)
-    const double instr = 2.0 * 16 * N_ITER * 8;
-    printf("%-34s %8.3f warp-instr/clk/SM   (%.2f clk per warp-instr per SMSP)\n", names[OP], instr / best, best * 4 / instr);
+    // per SM: 1 block x 32 warps x N_ITER x 8 instructions (mixed tests count every instruction)
+    const double instr = 32.0 * N_ITER * 8;
+    printf("%-34s %8.3f warp-instr/clk64/SM  (%.2f clk64 per warp-instr per SMSP)   kernel %.3f ms -> clock64 at %.0f MHz, %.3f warp-instr/ns/SM\n", names[OP], instr / best, best * 4 / instr, g_ms, best / (g_ms * 1e3), instr / (g_ms * 1e6));
     if (OP + 1 < N_OPS) run<(OP + 1 < N_OPS ? OP + 1 : OP)>(out, cyc, red, nblk);
 }
 template <> void run<N_OPS>(float*, long long*, unsigned long long*, int) {}
@@ -105,13 +111,13 @@ template <> void run<N_OPS>(float*, long long*, unsigned long long*, int) {}
 int main() {
     cudaDeviceProp p;
     cudaGetDeviceProperties(&p, 0);
-    const int nblk = p.multiProcessorCount * 2;
-    printf("%s, %d SMs, %d blocks x 512 threads\n", p.name, p.multiProcessorCount, nblk);
+    const int nblk = p.multiProcessorCount;
+    printf("%s, %d SMs, %d blocks x 1024 threads\n", p.name, p.multiProcessorCount, nblk);
     float* out; long long* cyc; unsigned long long* red;
-    cudaMalloc(&out, (size_t)nblk * 512 * 4);
+    cudaMalloc(&out, (size_t)nblk * 1024 * 4);
     cudaMalloc(&cyc, nblk * 8);
-    cudaMalloc(&red, (size_t)nblk * 512 * 8 * 8);
-    cudaMemset(red, 0, (size_t)nblk * 512 * 8 * 8);
+    cudaMalloc(&red, (size_t)nblk * 1024 * 8 * 8);
+    cudaMemset(red, 0, (size_t)nblk * 1024 * 8 * 8);
     run<0>(out, cyc, red, nblk);
     printf("cuda status: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;

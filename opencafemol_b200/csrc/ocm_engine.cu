@@ -86,6 +86,7 @@ struct PairListHost {
     int max_cells = 0;
     // cluster-pair ("tile") form (tile_kernels.cuh)
     bool tile_ok = false;    // the static tile tables exist (periodic or virtual box, single system)
+    bool tile_auto = false;  // large enough for tiles to be the default (option pair_kernel = -1)
     bool tiled = false;      // the list is built and evaluated in tile form
     bool t_switch = false;
     int np_pad = 0, tl_stride = 0, tl_nsc = 0, tl_mask_cap = 0;
@@ -191,7 +192,7 @@ struct ocm_context {
     std::vector<WorkSeg> segs;
     DevBuf<WorkSeg> d_segs;
     int tile_blocks = 0;                    // blocks of all tile force launches (tile lists have one launch each)
-    int tile_opt = 1;                       // option "pair_kernel": 1 = cluster-pair tiles where possible, 0 = Verlet rows
+    int tile_opt = -1;                      // option "pair_kernel": 1 = cluster-pair tiles where possible, 0 = Verlet rows, -1 = by size
     int tile_debug = 0;
     int tile_chunk_opt = 0;                 // blocks of the tile force launch per list, 0 = auto (one wave)
     int total_blocks = 0, pair_blocks = 0, local_blocks = 0, n_pair_segs = 0, n_local_segs = 0;
@@ -239,6 +240,7 @@ struct ocm_context {
 
 namespace ocm {
 
+static const int kTileAutoBeads = 131072;
 static const int kNstChoices[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 56, 64, 80, 100};
 
 static void dd_configure(ocm_context* c);
@@ -357,6 +359,7 @@ static uint64_t hilbert_index(uint32_t x, uint32_t y, uint32_t z, int bits) {
 static void compile_tile_tables(ocm_context* c, PairListHost& L) {
     // (small lists -- a few hundred charged beads -- stay Verlet rows inside the fused launch: a tile launch of their own costs more)
     L.tile_ok = c->periodic && c->nrep == 1 && L.np >= 1024;
+    L.tile_auto = L.np >= kTileAutoBeads;
     if (!L.tile_ok) return;
     const auto& pairs = c->sys.pairs;
     const PairTerm& t0 = pairs[L.terms[0]];
@@ -1101,7 +1104,7 @@ static void enqueue_forces(ocm_context* c, cudaStream_t s) {
 static void size_lists(ocm_context* c, double growth) {
     cudaStream_t s = c->stream;
     for (auto& L : c->lists) {
-        L->tiled = L->tile_ok && c->tile_opt != 0;
+        L->tiled = L->tile_ok && (c->tile_opt > 0 || (c->tile_opt < 0 && L->tile_auto));
         L->dev.tiled = L->tiled ? 1 : 0;
         configure_grid(c, *L);
     }
@@ -1837,8 +1840,10 @@ int ocm_context_set_option(ocm_context* c, const char* key, double value) {
         c->staging_opt = value != 0 ? 1 : 0;
         if (c->lists_ready) { build_segments(c); upload_lists(c); c->lists_current = false; }
     } else if (k == "pair_kernel") {
-        // 1 (default): cluster-pair tile lists where the system allows them; 0: per-bead Verlet rows
-        c->tile_opt = value != 0 ? 1 : 0;
+        // 1: cluster-pair tile lists where the system allows them; 0: per-bead Verlet rows; -1 (default): tiles for the lists of
+        // at least kTileAutoBeads beads (measured on B200: rows 38.6 us vs tiles 48 us per force launch at 16 300 beads, where one wave
+        // of blocks is short; at 1 043 200 beads the launches tie at 2.0 ms and the tile list builds 3 x faster and is 60 x smaller)
+        c->tile_opt = value > 0 ? 1 : (value < 0 ? -1 : 0);
         c->lists_ready = false; c->lists_current = false;
         drop_graphs(c);
     } else if (k == "tile_debug") {

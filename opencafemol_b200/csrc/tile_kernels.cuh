@@ -413,6 +413,65 @@ __device__ __forceinline__ TilePair tile_geom(const TileLaunch& T, const uint4 p
     t.in = ok && t.r2 < T.seg.rc2;
     return t;
 }
+// ---- two tiles at once with the packed FP32 instructions of sm_100 (FFMA2 / FMUL2 / FADD2: two independent FP32 results
+// per issue slot).  The kernel is bound by instruction issue, not by the FMA pipe, so halving the issue slots of the
+// floating-point part of a pair of evaluations is a direct gain.  Component .x is tile A, .y is tile B; the operations are
+// those of the scalar path (up to the compiler's FMA contraction there).
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+struct TilePair2 { float2 dx, dy, dz, r2; bool in_a, in_b; };
+__device__ __forceinline__ TilePair2 tile_geom2(const TileLaunch& T, const uint4 pa, const uint4 pb, const uint4 pj, bool ok_a, bool ok_b) {
+    TilePair2 t;
+    t.dx = __fmul2_rn(f2(__int2float_rn((int)(pa.x - pj.x)), __int2float_rn((int)(pb.x - pj.x))), f2(T.fscale[0]));
+    t.dy = __fmul2_rn(f2(__int2float_rn((int)(pa.y - pj.y)), __int2float_rn((int)(pb.y - pj.y))), f2(T.fscale[1]));
+    t.dz = __fmul2_rn(f2(__int2float_rn((int)(pa.z - pj.z)), __int2float_rn((int)(pb.z - pj.z))), f2(T.fscale[2]));
+    t.r2 = __ffma2_rn(t.dz, t.dz, __ffma2_rn(t.dy, t.dy, __fmul2_rn(t.dx, t.dx)));   // norm2() on both
+    t.in_a = ok_a && t.r2.x < T.seg.rc2;
+    t.in_b = ok_b && t.r2.y < T.seg.rc2;
+    return t;
+}
+template <bool SW, bool GEO>
+__device__ __forceinline__ float2 tile_pair_tz2(const TileSegP& G, float2 r2, float2 ai, float aj, float2 bi_in, float2 bi_out, float2 bj) {
+    const float2 s = __fadd2_rn(ai, f2(aj));
+    const float2 s2 = __fmul2_rn(s, s);
+    const float2 ir = f2(fast_rsqrt(r2.x), fast_rsqrt(r2.y));
+    const float2 ir2 = __fmul2_rn(ir, ir);
+    const float2 q = __fmul2_rn(s2, ir2);
+    const float2 q3 = __fmul2_rn(__fmul2_rn(q, q), q);
+    const float2 e_in = GEO ? __fmul2_rn(bi_in, f2(bj.x)) : __fadd2_rn(bi_in, f2(bj.x));
+    const float2 e_out = __fadd2_rn(bi_out, f2(bj.y));
+    const float2 e = f2((q.x > G.qz) ? e_in.x : e_out.x, (q.y > G.qz) ? e_in.y : e_out.y);
+    const float2 g = __ffma2_rn(f2(G.alpha), q3, f2(-G.beta));
+    if (!SW) return __fmul2_rn(__fmul2_rn(e, q3), __fmul2_rn(g, ir2));
+    const float2 r = __fmul2_rn(r2, ir);
+    float2 t = __ffma2_rn(r, f2(G.inv_sw), f2(-G.sw_c0));
+    t = f2(__saturatef(t.x), __saturatef(t.y));
+    const float2 t2 = __fmul2_rn(t, t);
+    const float2 Sw = __ffma2_rn(__fmul2_rn(t2, t), __ffma2_rn(t, __ffma2_rn(t, f2(-6.f), f2(15.f)), f2(-10.f)), f2(1.f));
+    const float2 w = __fadd2_rn(t, f2(-t2.x, -t2.y));
+    const float2 u3 = __fmul2_rn(__fadd2_rn(q3, f2(-1.f)), __fmul2_rn(w, w));
+    const float2 inner = __ffma2_rn(u3, f2(G.sw_c1), __fmul2_rn(__fmul2_rn(g, ir), Sw));
+    return __fmul2_rn(__fmul2_rn(__fmul2_rn(e, q3), ir), inner);
+}
+__device__ __forceinline__ float2 tile_pair_dh2(const TileSegP& G, float2 r2, float2 ai, float aj) {
+    const float2 ir = f2(fast_rsqrt(r2.x), fast_rsqrt(r2.y));
+    const float2 r = __fmul2_rn(r2, ir);
+    const float2 ex = f2(__expf(-r.x * G.inv_debye), __expf(-r.y * G.inv_debye));
+    return __fmul2_rn(__fmul2_rn(__fmul2_rn(__fmul2_rn(ai, f2(aj)), ex), __fadd2_rn(ir, f2(G.inv_debye))), __fmul2_rn(ir, ir));
+}
+// evaluate tiles A and B; fi* are the (A, B) i-force accumulators, fj* the j-force accumulators of the two tiles (summed later)
+template <int FORM, bool SW, bool GEO>
+__device__ __forceinline__ void tile_eval2(const TileLaunch& T, const TilePair2& t, float2 ai, float2 bi_in, float2 bi_out, float aj, float2 bj,
+                                           float2& fix, float2& fiy, float2& fiz, float2& fjx, float2& fjy, float2& fjz) {
+    float2 fr;
+    if (FORM == SEG_PAIR_TZ) fr = tile_pair_tz2<SW, GEO>(T.seg, t.r2, ai, aj, bi_in, bi_out, bj);
+    else fr = tile_pair_dh2(T.seg, t.r2, ai, aj);
+    fr = f2(t.in_a ? fr.x : 0.f, t.in_b ? fr.y : 0.f);
+    fix = __ffma2_rn(fr, t.dx, fix); fiy = __ffma2_rn(fr, t.dy, fiy); fiz = __ffma2_rn(fr, t.dz, fiz);
+    const float2 nfr = f2(-fr.x, -fr.y);
+    fjx = __ffma2_rn(nfr, t.dx, fjx); fjy = __ffma2_rn(nfr, t.dy, fjy); fjz = __ffma2_rn(nfr, t.dz, fjz);
+}
+
 template <int FORM, bool SW, bool GEO>
 __device__ __forceinline__ void tile_eval(const TileLaunch& T, const TilePair& t, float ai, const float2 bi, float aj, const float2 bj,
                                           float& fix, float& fiy, float& fiz, float& fjx, float& fjy, float& fjz) {
@@ -427,100 +486,144 @@ __device__ __forceinline__ void tile_eval(const TileLaunch& T, const TilePair& t
     fjx = fmaf(-fr, t.dx, fjx); fjy = fmaf(-fr, t.dy, fjy); fjz = fmaf(-fr, t.dz, fjz);
 }
 
-// One block = 4 warps on one chunk (`per` entries) of the entry row of one supercluster.
-template <int FORM, bool SW, bool GEO>
-__device__ __forceinline__ void tile_chunk(const TileLaunch& T, int S, int e_begin, int e_end,
-                                           unsigned long long* __restrict__ fbuf, uint4* s_pos, float2* s_par, int* s_bead, float* s_acc) {
-    const TileSegP& G = T.seg;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ti = lane & 7, tj = lane >> 3;
-    __syncthreads();  // (a block may work on several superclusters in turn: the previous one is done with shared memory)
-    if (threadIdx.x < 64) {
-        const uint4 ax = G.saux[S * 64 + threadIdx.x];
-        s_pos[threadIdx.x] = G.spos[S * 64 + threadIdx.x];
-        s_par[threadIdx.x] = make_float2(__uint_as_float(ax.x), __uint_as_float(ax.y));
-        s_bead[threadIdx.x] = (int)ax.z;
-    }
-    // this warp's entries e_begin + warp + 4 l (l = 0, 1, ...): lane l fetches entry l, shuffles hand them out
-    const uint2* __restrict__ row = G.entries + (size_t)S * G.stride;
-    const int n_mine = (e_end - e_begin - warp + 3) >> 2;
-    uint2 ent_l = make_uint2(0u, 0u);
-    if (lane < n_mine) ent_l = __ldg(&row[e_begin + warp + 4 * lane]);
-    __syncthreads();
-    const uint4* my_pos = s_pos + ti;
-    const float2* my_par = s_par + ti;
-    float fi[8][3];
-#pragma unroll
-    for (int ci = 0; ci < 8; ci++) { fi[ci][0] = 0.f; fi[ci][1] = 0.f; fi[ci][2] = 0.f; }
+// Shared memory of one block of the force kernel.  Everything an entry needs is staged here for 32 entries at a time by
+// all 128 threads at once (one memory latency per batch instead of one per entry), and the j-forces leave through it too.
+constexpr int kTileBatch = 32;   // entries per batch (8 per warp)
+struct TileShared {
+    uint4 pos[64];                       // the 64 i-beads of the supercluster: fixed-point position + mixing parameter a
+    float2 par[64];                      // (b_in, b_out)
+    float4 pp4[32];                      // the same per PAIR of i-clusters (2p, 2p+1) and lane ti: (a_A, a_B, b_in_A, b_in_B) ...
+    float2 pp2[32];                      // ... and (b_out_A, b_out_B): aligned operands of the packed two-tile evaluation
+    int bead[64];
+    float acc[(kTileBlock / 32) * 192];  // per-warp i-force partial sums
+    uint2 ent[kTileBatch];
+    uint4 jpos[kTileBatch * 4], jaux[kTileBatch * 4];
+    unsigned int mask[kTileBatch * 8];
+    float fj[kTileBatch * 4 * 3];
+};
 
-    uint4 pj = make_uint4(0u, 0u, 0u, 0u), xj = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
-    {
-        const unsigned int j4 = __shfl_sync(0xffffffffu, ent_l.x, 0);
-        if (n_mine > 0) { const int kj = (int)j4 * 4 + tj; pj = __ldg(&G.spos[kj]); xj = __ldg(&G.saux[kj]); }
+// One piece [e_begin, e_end) of the entry row of supercluster S, by the 4 warps of a block.
+template <int FORM, bool SW, bool GEO>
+__device__ __forceinline__ void tile_chunk(const TileLaunch& T, int S, int e_begin, int e_end, unsigned long long* __restrict__ fbuf, TileShared& sh) {
+    const TileSegP& G = T.seg;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ti = lane & 7, tj = lane >> 3;
+    __syncthreads();  // (a block works on several rows in turn: the previous one is done with shared memory)
+    if (tid < 64) {
+        const uint4 ax = __ldg(&G.saux[S * 64 + tid]);
+        const uint4 p = __ldg(&G.spos[S * 64 + tid]);
+        sh.pos[tid] = p;
+        sh.par[tid] = make_float2(__uint_as_float(ax.x), __uint_as_float(ax.y));
+        sh.bead[tid] = (int)ax.z;
+        // pair layout: bead tid = cluster c, lane t; pair p = c / 2, half h = c & 1
+        const int c = tid >> 3, t = tid & 7, pidx = (c >> 1) * 8 + t, h = c & 1;
+        float* q4 = reinterpret_cast<float*>(&sh.pp4[pidx]);
+        float* q2 = reinterpret_cast<float*>(&sh.pp2[pidx]);
+        q4[h] = __uint_as_float(p.w); q4[2 + h] = __uint_as_float(ax.x); q2[h] = __uint_as_float(ax.y);
     }
-    for (int it = 0; it < n_mine; it++) {
-        const unsigned int ey = __shfl_sync(0xffffffffu, ent_l.y, it);
-        // prefetch the j-bead of the next entry
-        uint4 pj_n = make_uint4(0u, 0u, 0u, 0u), xj_n = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
-        {
-            const unsigned int j4n = __shfl_sync(0xffffffffu, ent_l.x, (it + 1) & 31);
-            if (it + 1 < n_mine) { const int kn = (int)j4n * 4 + tj; pj_n = __ldg(&G.spos[kn]); xj_n = __ldg(&G.saux[kn]); }
-        }
-        const unsigned int act = ey & 0xffu, midx = ey >> 8;
-        // lane masks of the entry (only the entries with exclusions, the i < j rule or padding have any)
-        unsigned int lane_ok = 0xffu;
-        if (midx) {
-            const unsigned int mw = __ldg(&G.masks[(size_t)(midx - 1u) * 8 + ti]);   // lane ti fetches the word of i-cluster ti
-            lane_ok = 0u;
+    const uint2* __restrict__ row = G.entries + (size_t)S * G.stride;
+    const uint4* my_pos = sh.pos + ti;
+    const float2* my_par = sh.par + ti;
+    // i-force accumulators: component .x = cluster 2p, .y = cluster 2p + 1
+    float2 fi[4][3];
 #pragma unroll
-            for (int ci = 0; ci < 8; ci++) lane_ok |= ((__shfl_sync(0xffffffffu, mw, ci) >> lane) & 1u) << ci;
+    for (int p2 = 0; p2 < 4; p2++) { fi[p2][0] = f2(0.f); fi[p2][1] = f2(0.f); fi[p2][2] = f2(0.f); }
+
+    for (int eb = e_begin; eb < e_end; eb += kTileBatch) {
+        const int n_e = min(kTileBatch, e_end - eb);
+        // ---- stage the batch: entries, their j-beads, their lane masks ----
+        if (tid < n_e) sh.ent[tid] = __ldg(&row[eb + tid]);
+        __syncthreads();
+        if ((tid >> 2) < n_e) {
+            const int kj = (int)sh.ent[tid >> 2].x * 4 + (tid & 3);
+            sh.jpos[tid] = __ldg(&G.spos[kj]);
+            sh.jaux[tid] = __ldg(&G.saux[kj]);
         }
-        const float aj = __uint_as_float(pj.w);
-        const float2 bj = make_float2(__uint_as_float(xj.x), __uint_as_float(xj.y));
-        float fjx = 0.f, fjy = 0.f, fjz = 0.f;
-        // i-clusters in pairs: when both are active the two evaluations share a basic block and interleave (ILP 2)
 #pragma unroll
-        for (int c2 = 0; c2 < 8; c2 += 2) {
-            const unsigned int a2 = (T.debug & 8) ? 0u : ((act >> c2) & 3u);
-            if (a2 == 0u) continue;  // warp-uniform
-            if (a2 == 3u) {
-                const uint4 pa = my_pos[c2 * 8], pb = my_pos[c2 * 8 + 8];
-                const TilePair ta = tile_geom(T, pa, pj, (lane_ok >> c2) & 1u), tb = tile_geom(T, pb, pj, (lane_ok >> (c2 + 1)) & 1u);
-                if (!__any_sync(0xffffffffu, ta.in || tb.in)) continue;  // both tiles sit in the skin at this step
-                tile_eval<FORM, SW, GEO>(T, ta, __uint_as_float(pa.w), my_par[c2 * 8], aj, bj, fi[c2][0], fi[c2][1], fi[c2][2], fjx, fjy, fjz);
-                tile_eval<FORM, SW, GEO>(T, tb, __uint_as_float(pb.w), my_par[c2 * 8 + 8], aj, bj, fi[c2 + 1][0], fi[c2 + 1][1], fi[c2 + 1][2], fjx, fjy, fjz);
-            } else if (a2 == 1u) {
-                const uint4 pa = my_pos[c2 * 8];
-                const TilePair ta = tile_geom(T, pa, pj, (lane_ok >> c2) & 1u);
-                if (!__any_sync(0xffffffffu, ta.in)) continue;
-                tile_eval<FORM, SW, GEO>(T, ta, __uint_as_float(pa.w), my_par[c2 * 8], aj, bj, fi[c2][0], fi[c2][1], fi[c2][2], fjx, fjy, fjz);
-            } else {
-                const uint4 pb = my_pos[c2 * 8 + 8];
-                const TilePair tb = tile_geom(T, pb, pj, (lane_ok >> (c2 + 1)) & 1u);
-                if (!__any_sync(0xffffffffu, tb.in)) continue;
-                tile_eval<FORM, SW, GEO>(T, tb, __uint_as_float(pb.w), my_par[c2 * 8 + 8], aj, bj, fi[c2 + 1][0], fi[c2 + 1][1], fi[c2 + 1][2], fjx, fjy, fjz);
+        for (int h = 0; h < 2; h++) {
+            const int w = tid + h * kTileBlock;   // word (entry w / 8, i-cluster w % 8)
+            if ((w >> 3) < n_e) {
+                const unsigned int midx = sh.ent[w >> 3].y >> 8;
+                if (midx) sh.mask[w] = __ldg(&G.masks[(size_t)(midx - 1u) * 8 + (w & 7)]);
             }
         }
-        // j-force: sum over the 8 ti lanes of each tj group with 6 shuffles; x, y, z end up in lanes ti = 0, 1, 2
-        fjx += __shfl_down_sync(0xffffffffu, fjx, 1);
-        fjy += __shfl_up_sync(0xffffffffu, fjy, 1);
-        fjz += __shfl_down_sync(0xffffffffu, fjz, 1);
-        if (ti & 1) fjx = fjy;
-        fjx += __shfl_down_sync(0xffffffffu, fjx, 2);
-        fjz += __shfl_up_sync(0xffffffffu, fjz, 2);
-        if (ti & 2) fjx = fjz;
-        fjx += __shfl_down_sync(0xffffffffu, fjx, 4);
-        const int sbj = (int)xj.z;
-        if (sbj >= 0 && ti < 3 && !(T.debug & 1))
-            atomicAdd(&fbuf[(size_t)ti * T.n + (sbj & 0xFFFFFF)], (unsigned long long)(long long)(fjx * 4294967296.0f));
-        pj = pj_n; xj = xj_n;
+        __syncthreads();
+        // ---- evaluate: warp w takes entries w, w + 4, ... of the batch ----
+        for (int e = warp; e < n_e; e += kTileBlock / 32) {
+            const unsigned int ey = sh.ent[e].y;
+            const unsigned int act = (T.debug & 8) ? 0u : (ey & 0xffu);
+            const uint4 pj = sh.jpos[e * 4 + tj];
+            const uint4 xj = sh.jaux[e * 4 + tj];
+            // lane masks (only the entries with exclusions, the i < j rule or padding have any)
+            unsigned int lane_ok = 0xffu;
+            if (ey >> 8) {
+                lane_ok = 0u;
+#pragma unroll
+                for (int ci = 0; ci < 8; ci++) lane_ok |= ((sh.mask[e * 8 + ci] >> lane) & 1u) << ci;
+            }
+            const float aj = __uint_as_float(pj.w);
+            const float2 bj = make_float2(__uint_as_float(xj.x), __uint_as_float(xj.y));
+            float2 fjx = f2(0.f), fjy = f2(0.f), fjz = f2(0.f);
+            // i-clusters in pairs: when both are active the two tiles are evaluated together with packed FP32 instructions
+#pragma unroll
+            for (int p2 = 0; p2 < 4; p2++) {
+                const int c2 = 2 * p2;
+                const unsigned int a2 = (act >> c2) & 3u;
+                if (a2 == 0u) continue;  // warp-uniform
+                if (a2 == 3u) {
+                    const uint4 pa = my_pos[c2 * 8], pb = my_pos[c2 * 8 + 8];
+                    const TilePair2 t = tile_geom2(T, pa, pb, pj, (lane_ok >> c2) & 1u, (lane_ok >> (c2 + 1)) & 1u);
+                    if (!__any_sync(0xffffffffu, t.in_a || t.in_b)) continue;  // both tiles sit in the skin at this step
+                    const float4 q4 = sh.pp4[p2 * 8 + ti];
+                    const float2 q2 = sh.pp2[p2 * 8 + ti];
+                    tile_eval2<FORM, SW, GEO>(T, t, f2(q4.x, q4.y), f2(q4.z, q4.w), q2, aj, bj, fi[p2][0], fi[p2][1], fi[p2][2], fjx, fjy, fjz);
+                } else if (a2 == 1u) {
+                    const uint4 pa = my_pos[c2 * 8];
+                    const TilePair ta = tile_geom(T, pa, pj, (lane_ok >> c2) & 1u);
+                    if (!__any_sync(0xffffffffu, ta.in)) continue;
+                    tile_eval<FORM, SW, GEO>(T, ta, __uint_as_float(pa.w), my_par[c2 * 8], aj, bj, fi[p2][0].x, fi[p2][1].x, fi[p2][2].x, fjx.x, fjy.x, fjz.x);
+                } else {
+                    const uint4 pb = my_pos[c2 * 8 + 8];
+                    const TilePair tb = tile_geom(T, pb, pj, (lane_ok >> (c2 + 1)) & 1u);
+                    if (!__any_sync(0xffffffffu, tb.in)) continue;
+                    tile_eval<FORM, SW, GEO>(T, tb, __uint_as_float(pb.w), my_par[c2 * 8 + 8], aj, bj, fi[p2][0].y, fi[p2][1].y, fi[p2][2].y, fjx.x, fjy.x, fjz.x);
+                }
+            }
+            // j-force: the two tile accumulators, then over the 8 ti lanes of each tj group with 6 shuffles; x, y, z end up in
+            // lanes ti = 0, 1, 2
+            float gx = fjx.x + fjx.y, gy = fjy.x + fjy.y, gz = fjz.x + fjz.y;
+            gx += __shfl_down_sync(0xffffffffu, gx, 1);
+            gy += __shfl_up_sync(0xffffffffu, gy, 1);
+            gz += __shfl_down_sync(0xffffffffu, gz, 1);
+            if (ti & 1) gx = gy;
+            gx += __shfl_down_sync(0xffffffffu, gx, 2);
+            gz += __shfl_up_sync(0xffffffffu, gz, 2);
+            if (ti & 2) gx = gz;
+            gx += __shfl_down_sync(0xffffffffu, gx, 4);
+            if (ti < 3) sh.fj[(e * 4 + tj) * 3 + ti] = gx;
+        }
+        __syncthreads();
+        // ---- the j-forces of the batch leave together: one fixed-point atomic per (j-bead, component) ----
+#pragma unroll
+        for (int h = 0; h < 3; h++) {
+            const int v = tid + h * kTileBlock;
+            const int j = v / 3, q = v - j * 3;
+            if (j < n_e * 4) {
+                const int sbj = (int)sh.jaux[j].z;
+                const float f = sh.fj[v];
+                if (sbj >= 0 && f != 0.f && !(T.debug & 1)) atomicAdd(&fbuf[(size_t)q * T.n + (sbj & 0xFFFFFF)], (unsigned long long)(long long)(f * 4294967296.0f));
+            }
+        }
+        // (the next batch's first barrier comes after its entry loads: jaux / fj are not overwritten before every thread is past here)
     }
     // i-forces: over the 4 tj groups by a transposing shuffle reduction (24 values -> 12 -> 6 per lane), over the 4 warps
     // in shared memory in a fixed order (run-to-run reproducible), then one atomic triple per i-bead
     float r1[12];
 #pragma unroll
     for (int m = 0; m < 12; m++) {
-        const float lo = fi[m / 3][m % 3], hi = fi[m / 3 + 4][m % 3];
+        // value index m = cluster (m / 3), component (m % 3); its partner is cluster + 4
+        const float2 a = fi[(m / 3) >> 1][m % 3], bb = fi[((m / 3) + 4) >> 1][m % 3];
+        const float lo = ((m / 3) & 1) ? a.y : a.x, hi = ((m / 3) & 1) ? bb.y : bb.x;
         const float send = (tj & 1) ? lo : hi, keep = (tj & 1) ? hi : lo;
         r1[m] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
     }
@@ -531,13 +634,13 @@ __device__ __forceinline__ void tile_chunk(const TileLaunch& T, int S, int e_beg
         // this lane now holds component q of i-cluster ci, both functions of (m, tj)
         const int M = m + ((tj & 2) ? 6 : 0) + ((tj & 1) ? 12 : 0);
         const int ci = M / 3, q = M - ci * 3;
-        s_acc[warp * 192 + q * 64 + ci * 8 + ti] = v;
+        sh.acc[warp * 192 + q * 64 + ci * 8 + ti] = v;
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < 192; t += kTileBlock) {
-        const float v = (s_acc[t] + s_acc[192 + t]) + (s_acc[384 + t] + s_acc[576 + t]);
+    for (int t = tid; t < 192; t += kTileBlock) {
+        const float v = (sh.acc[t] + sh.acc[192 + t]) + (sh.acc[384 + t] + sh.acc[576 + t]);
         const int il = t & 63, q = t >> 6;
-        const int sb = s_bead[il];
+        const int sb = sh.bead[il];
         if (sb >= 0 && v != 0.f && !(T.debug & 2)) atomicAdd(&fbuf[(size_t)q * T.n + (sb & 0xFFFFFF)], (unsigned long long)(long long)(v * 4294967296.0f));
     }
 }
@@ -549,10 +652,8 @@ __device__ __forceinline__ void tile_chunk(const TileLaunch& T, int S, int e_beg
 // sums in start[]); inside a row the weight is taken as spread evenly over its entries.
 template <int FORM, bool SW, bool GEO>
 __global__ void __launch_bounds__(kTileBlock, OCM_TILE_MINBLOCKS) tile_force_kernel(const __grid_constant__ TileLaunch T, unsigned long long* __restrict__ fbuf) {
-    __shared__ uint4 s_pos[64];
-    __shared__ float2 s_par[64];
-    __shared__ int s_bead[64];
-    __shared__ float s_acc[(kTileBlock / 32) * 192];
+    __shared__ TileShared sh;
+    __shared__ int s_first;
     if (T.pdl_early) pdl_trigger();
     pdl_wait();
     const TileSegP& G = T.seg;
@@ -560,10 +661,22 @@ __global__ void __launch_bounds__(kTileBlock, OCM_TILE_MINBLOCKS) tile_force_ker
     const long long W = start[G.nsc];
     const int t0 = (int)(W * blockIdx.x / G.nblocks), t1 = (int)(W * (blockIdx.x + 1) / G.nblocks);
     if (t0 >= t1) return;
-    // first row: the last S with start[S] <= t0
-    int lo = 0, hi = G.nsc - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (start[mid] <= t0) lo = mid; else hi = mid - 1; }
-    for (int S = lo; S < G.nsc; S++) {
+    // first row: the last S with start[S] <= t0.  One warp looks at 32 evenly spaced rows per round (two rounds cover 1024 rows)
+    if (threadIdx.x < 32) {
+        int lo = 0, hi = G.nsc;  // start[lo] <= t0 < start[hi]  (start[nsc] = W > t0)
+        while (hi - lo > 1) {
+            const int step = (hi - lo + 31) / 32;
+            const int probe = min(hi, lo + (int)threadIdx.x * step);
+            const bool le = probe < hi && start[probe] <= t0;
+            const unsigned int m = __ballot_sync(0xffffffffu, le);
+            const int top = 31 - __clz((int)m);   // lane 0 probes lo itself, which qualifies
+            const int nlo = lo + top * step;
+            hi = min(hi, nlo + step); lo = nlo;
+        }
+        if (threadIdx.x == 0) s_first = lo;
+    }
+    __syncthreads();
+    for (int S = s_first; S < G.nsc; S++) {
         const int w0 = start[S], w1 = start[S + 1];
         if (w0 >= t1) break;
         if (w1 == w0) continue;
@@ -572,9 +685,7 @@ __global__ void __launch_bounds__(kTileBlock, OCM_TILE_MINBLOCKS) tile_force_ker
         // the same formula, so the shares tile the row exactly
         const int e_begin = (t0 <= w0) ? 0 : (int)(((long long)(t0 - w0) * cnt / (w1 - w0)) & ~3ll);
         const int e_end = (t1 >= w1) ? cnt : (int)(((long long)(t1 - w0) * cnt / (w1 - w0)) & ~3ll);
-        // (at most 128 entries per pass: each lane of a warp fetches one of its warp's entries)
-        for (int eb = e_begin; eb < e_end; eb += 128)
-            tile_chunk<FORM, SW, GEO>(T, S, eb, min(e_end, eb + 128), fbuf, s_pos, s_par, s_bead, s_acc);
+        if (e_begin < e_end) tile_chunk<FORM, SW, GEO>(T, S, e_begin, e_end, fbuf, sh);
     }
 }
 

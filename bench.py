@@ -8,7 +8,8 @@ with save_step = 1000 MD steps (src/Simulator.cpp:49-76); ns/day = MD steps/s x 
 
     python bench.py --gpus 1 --steps 10 --warmup 3            # the engine (this repo)
     python bench.py --impl reference --steps 2 --warmup 1      # CPU arm: the oracle port of the reference path
-    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N   # N independent replicas
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N   # N independent replicas (headline) + the
+                                                                               # slab-decomposed C5 run and its bit-exact check
 
 Both arms start from the same committed state of the workload, opencafemol_b200/data/c2_state.npz (the condensate after
 40 000 steps, when its compaction has levelled off: config.state), so they time the same pair work per step.
@@ -183,15 +184,142 @@ def run_reference(args):
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": "ns/day", "value": value, "unit": "ns/day", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t_all / args.steps * 1e3 * (MD_STEPS_PER_STEP / sample_steps),
+        "warmup": args.warmup, "ms_per_step": t_all / args.steps * 1e3, "md_steps_timed_per_step": sample_steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(spec),
         "cpu_baseline": {"value": value, "unit": "ns/day", "cores": cores, "kind": "port",
-                         "sample": f"{sample_steps} MD steps of the C2 workload per bench step (a bench step is extrapolated "
-                                   f"to {MD_STEPS_PER_STEP}); OpenMM-equivalent CPU restatement, OpenMM not installable offline"},
+                         "sample": f"{sample_steps} MD steps of the C2 workload per bench step (ms_per_step is the measured time of "
+                                   f"those {sample_steps} steps, not of {MD_STEPS_PER_STEP}); OpenMM-equivalent CPU restatement, OpenMM "
+                                   "not installable offline"},
         "e2e": {"value": value, "unit": "ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def nccl_comm(lib, rank, world, local):
+    """NCCL communicator of the engine: rank 0 draws the unique id, torch.distributed carries it to the others."""
+    import torch
+    import torch.distributed as dist
+
+    from opencafemol_b200.capi import Comm
+
+    uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(Comm.unique_id(lib)), dtype=torch.uint8).to(f"cuda:{local}")
+    dist.broadcast(uid, 0)
+    return Comm.nccl(lib, bytes(uid.cpu().numpy().tobytes()), world, rank, local)
+
+
+def timed_steps(ctx, warm, steps, local, world):
+    """device seconds (MAX over ranks) of `steps` MD steps after `warm` warm-up steps"""
+    import torch
+    import torch.distributed as dist
+
+    from opencafemol_b200 import sharding
+
+    ctx.step(warm)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ctx.step(steps)
+    return sharding.max_over_ranks([ctx.counter("last_step_ms") * 1e-3], device=f"cuda:{local}")[0]
+
+
+def single_gpu_records(lib, local):
+    """N = 1: the other single-GPU configurations of BASELINE.json beside the C2 headline (each a few seconds)"""
+    import sys as _sys
+
+    from opencafemol_b200 import synth, toml_input
+
+    out = {}
+    # C5: the compacted C2 state tiled 8 x 8 = 1 043 200 beads on one GPU
+    spec = synth.c2_equilibrated(tile=(8, 8))
+    ctx = toml_input.make_context(lib, spec, device=local)
+    dev = timed_steps(ctx, 200, 400, local, 1)
+    out["c5"] = {"workload": "C5: C2 compacted state tiled 8 x 8, 1 043 200 beads, one GPU", "md_steps_per_s": 400 / dev,
+                 "ns_per_day": ns_per_day(400, spec.dt, dev), "ms_per_md_step": dev / 400 * 1e3, "nstlist": ctx.counter("nstlist"),
+                 "pair_kernel": "tiles" if ctx.counter("tiled.1") else "rows", "lane_pairs_evaluated_per_step": ctx.counter("pair_evals_per_step"),
+                 "kernel_ms": {k: ctx.profile_kernel(k, 5) for k in ("force", "integrate", "rebuild")}}
+    hbm = spec.mass.size * BYTES_PER_BEAD_INTEGRATE / (out["c5"]["kernel_ms"]["integrate"] * 1e-3) / 1e9
+    peaks, how = measured_peaks()
+    out["c5"]["roofline_hbm"] = {"bound": "hbm", "kernel": "integrate_kernel", "achieved": hbm, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                 "frac": hbm / peaks.get("hbm_gbs", 1.0), "peak_source": how}
+    ctx.close()
+    # C4: 512 SH3 replicas (8 groups x 64) in one context
+    _sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import load_golden_spec
+
+    sh3 = load_golden_spec("sh3")
+    ctx = toml_input.make_context(lib, sh3, device=local, replicas=512)
+    dev = timed_steps(ctx, 500, 2000, local, 1)
+    out["c4"] = {"workload": "C4: 512 replicas of the SH3 AICG2+ sample (56 beads each) in one context", "replica_steps_per_s": 512 * 2000 / dev,
+                 "md_steps_per_s": 2000 / dev}
+    ctx.close()
+    ctx = toml_input.make_context(lib, sh3, device=local)
+    dev = timed_steps(ctx, 500, 5000, local, 1)
+    out["c1"] = {"workload": "C1: sample/toml_input/sh3_AICG2+.toml (56 beads)", "md_steps_per_s": 5000 / dev, "ns_per_day": ns_per_day(5000, sh3.dt, dev)}
+    ctx.close()
+    return out
+
+
+def multi_gpu_records(lib, rank, world, local):
+    """N > 1: the path that shards.  (1) slab_check: the C2 state decomposed into `world` slabs along z over NCCL + the
+    peer-memory halo, compared with the single-domain run on rank 0 (bit for bit with a fixed rebuild interval).
+    (2) c5: the 1 043 200-bead condensate decomposed along y, against the one-GPU figure measured on rank 0 in the same run."""
+    import torch.distributed as dist
+
+    from opencafemol_b200 import synth, toml_input
+
+    comm = nccl_comm(lib, rank, world, local)
+    out = {}
+    # ---- slab_check ----
+    spec = synth.c2_equilibrated()
+    ctx = toml_input.make_context(lib, spec, device=local, comm=comm, rank=rank, axis=2)
+    ctx.set_option("nstlist", 10)
+    ctx.step(200)
+    st = ctx.get_state(positions=True, velocities=True, energy=True)
+    transport = "peer-memory push (CUDA IPC over NVLink)" if ctx.counter("halo_push") else "nccl send/recv"
+    exchanges = ctx.counter("halo_exchanges")
+    if rank == 0:
+        ref = toml_input.make_context(lib, spec, device=local)
+        ref.set_option("nstlist", 10)
+        ref.step(200)
+        a = ref.get_state(positions=True, velocities=True, energy=True)
+        out["slab_check"] = {"workload": "C2 state, %d slabs along z, 200 MD steps, rebuild every 10" % world,
+                             "positions_equal": bool(np.array_equal(a["positions"], st["positions"])),
+                             "velocities_equal": bool(np.array_equal(a["velocities"], st["velocities"])),
+                             "max_abs_dx_nm": float(np.abs(a["positions"] - st["positions"]).max()),
+                             "epot_kj": [a["potential_energy"], st["potential_energy"]], "halo": transport, "halo_exchanges": exchanges}
+        ref.close()
+    dist.barrier()
+    ctx.close()
+    # ---- C5 ----
+    spec = synth.c2_equilibrated(tile=(8, 8))
+    one = None
+    if rank == 0:
+        c1 = toml_input.make_context(lib, spec, device=local)
+        c1.step(200)
+        c1.step(400)
+        one = 400 / (c1.counter("last_step_ms") * 1e-3)
+        c1.close()
+    dist.barrier()
+    ctx = toml_input.make_context(lib, spec, device=local, comm=comm, rank=rank, axis=1)
+    dev = timed_steps(ctx, 300, 600, local, world)
+    nst = ctx.counter("nstlist")
+    ctx.set_option("phase_timing", 1)
+    ctx.step(200)
+    phases = {k: ctx.counter("phase_ms." + k) / 200 for k in ("rebuild", "force", "integrate", "halo")}
+    if rank == 0:
+        sN = 600 / dev
+        out["c5"] = {"workload": "C5: C2 compacted state tiled 8 x 8, 1 043 200 beads, %d slabs along y" % world, "md_steps_per_s": sN,
+                     "ns_per_day": ns_per_day(600, spec.dt, dev), "md_steps_per_s_one_gpu": one, "strong_scaling_efficiency": sN / one / world,
+                     "nstlist": nst, "phase_ms_per_step_rank0": phases, "halo_message_bytes": ctx.counter("halo_message_bytes"),
+                     "halo": "peer-memory push (CUDA IPC over NVLink)" if ctx.counter("halo_push") else "nccl send/recv",
+                     "pair_kernel": "tiles" if ctx.counter("tiled.1") else "rows"}
+    dist.barrier()
+    ctx.close()
+    comm.close()
+    return out
 
 
 def run_engine(args):
@@ -259,6 +387,13 @@ def run_engine(args):
     from opencafemol_b200 import sharding
 
     t_dev, t_e2e, t_wall = sharding.max_over_ranks([t_dev, t_e2e, t_wall], device=f"cuda:{local}")
+    # the configurations beside the headline (outside every timed region above)
+    extra = {}
+    if not args.no_extra:
+        try:
+            extra = single_gpu_records(lib, local) if world == 1 else multi_gpu_records(lib, rank, world, local)
+        except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
+            extra = {"extra_records_error": repr(e)}
 
     if rank == 0:
         md = args.steps * MD_STEPS_PER_STEP
@@ -278,7 +413,8 @@ def run_engine(args):
         line = {
             "metric": "ns/day", "value": value, "unit": "ns/day", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config_dict(spec, {"nstlist": nst, "skin_nm": ctx.get_option("skin_nm")}),
+            "dtype": "f32", "data": "synthetic", "config": config_dict(spec),
+            "engine_options": {"nstlist": nst, "skin_nm": ctx.get_option("skin_nm"), "pair_kernel": "rows" if not ctx.counter("tiled.1") else "tiles"},
             "md_steps_per_s": md / t_dev, "pair_interactions_per_s": (n_ah + n_dh) * md / t_dev * world,
             "wall_ms_per_step": t_wall / args.steps * 1e3,
             "e2e": {"value": e2e, "unit": "ns/day", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -294,6 +430,7 @@ def run_engine(args):
                              "note": "16 300 beads = 1.3 MB per launch: latency-bound, L2-resident"},
             "kernel_ms": {"force": ms_force, "integrate": ms_int, "rebuild_all_lists": ms_reb},
         }
+        line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             sample = CPU_BASELINE_STEPS
             v, cores, dt = cpu_port_run(spec, sample, state=(pos, vel))
@@ -313,6 +450,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C5 / C4 / slab_check records beside the C2 headline")
     args = ap.parse_args()
     import __graft_entry__ as g
 

@@ -27,6 +27,7 @@
 #include "host/lbfgs.hpp"
 #include "kernels.cuh"
 #include "tile_kernels.cuh"
+#include "replica_kernels.cuh"
 #include "dd_kernels.cuh"
 #include "dd_comm.hpp"
 
@@ -192,6 +193,17 @@ struct ocm_context {
     std::vector<WorkSeg> segs;
     DevBuf<WorkSeg> d_segs;
     int tile_blocks = 0;                    // blocks of all tile force launches (tile lists have one launch each)
+    // whole-step persistent kernel for small unlimited-boundary systems and replica ensembles (replica_kernels.cuh)
+    ocm_system sys1;                        // the system of ONE replica (replica batches keep it beside the replicated tables)
+    bool rep_ok = false;
+    int rep_opt = 0;                        // option "replica_kernel": 1 = use it where possible, 0 (default) = general path
+    RepParams rep{};
+    size_t rep_smem = 0;
+    std::vector<std::unique_ptr<DevBuf<ushort2>>> rep_ij;
+    std::vector<std::unique_ptr<DevBuf<float4>>> rep_coef;
+    DevBuf<int> rep_b_idx[B_NUM_KINDS], rep_b_meta[B_NUM_KINDS];
+    DevBuf<double> rep_b_par[B_NUM_KINDS];
+    double n_rep_launches = 0;
     int tile_opt = -1;                      // option "pair_kernel": 1 = cluster-pair tiles where possible, 0 = Verlet rows, -1 = by size
     int tile_debug = 0;
     int tile_chunk_opt = 0;                 // blocks of the tile force launch per list, 0 = auto (one wave)
@@ -753,6 +765,97 @@ static void compile_bonded(ocm_context* c) {
     c->d_bonded.upload(std::vector<BondedDev>(c->bonded_h, c->bonded_h + B_NUM_KINDS));
 }
 
+// ---- whole-step persistent kernel: static tables of one replica ------------------------------------------
+static void compile_replica_tables(ocm_context* c) {
+    c->rep_ok = false;
+    const ocm_system& S1 = c->nrep > 1 ? c->sys1 : c->sys;
+    const int nper = c->nper;
+    if (c->dd || (c->sys.has_box && !c->vbox) || !S1.das.empty() || nper > 256 || nper < 2) return;
+    if ((int)c->lists.size() > kRepMaxLists) return;
+    RepParams& R = c->rep;
+    R = RepParams{};
+    R.nper = nper; R.nrep = c->nrep; R.nlists = 0;
+    for (auto& Lp : c->lists) {
+        PairListHost& L = *Lp;
+        if (L.np == 0) continue;
+        const int nm = (int)L.terms.size();
+        const PairTerm& t0 = S1.pairs[L.terms[0]];
+        const PairTerm* rep = nullptr; const PairTerm* att = nullptr;
+        if (nm == 2) { rep = &S1.pairs[L.terms[0]]; att = &S1.pairs[L.terms[1]]; if (rep->kind != P_LJREP) std::swap(rep, att); }
+        std::vector<ushort2> ij;
+        std::vector<float4> coef;
+        size_t e = 0;  // exclusions are sorted (i < j): walk them alongside the pair loop
+        for (size_t a = 0; a < t0.part.size(); a++)
+            for (size_t b = a + 1; b < t0.part.size(); b++) {
+                const int i = t0.part[a], j = t0.part[b];
+                while (e < t0.excl.size() && (t0.excl[e].first < i || (t0.excl[e].first == i && t0.excl[e].second < j))) e++;
+                if (e < t0.excl.size() && t0.excl[e].first == i && t0.excl[e].second == j) continue;
+                if (t0.ncls > 0 && !((t0.allow[t0.cls[i]] >> t0.cls[j]) & 1u)) continue;
+                float4 cf;
+                if (L.form == SEG_PAIR_DH) cf = make_float4((float)(t0.g0 * t0.p0[i] * t0.p0[j]), 0.f, 0.f, 0.f);
+                else if (nm == 2) {
+                    const TZ zr = tz_coeffs(*rep, i, j), za = tz_coeffs(*att, i, j);
+                    cf = make_float4((float)(12.0 * zr.c12i), (float)(6.0 * zr.c6i), (float)zr.a2, (float)(za.c12o / zr.c12i));
+                } else {
+                    const TZ z = tz_coeffs(t0, i, j);
+                    if (t0.kind == P_LJATT) cf = make_float4((float)(12.0 * z.c12o), (float)(6.0 * z.c6o), (float)z.a2, 1.f);
+                    else cf = make_float4((float)(12.0 * z.c12i), (float)(6.0 * z.c6i), std::isfinite(z.a2) ? (float)z.a2 : INFINITY, 0.f);
+                }
+                ij.push_back(make_ushort2((unsigned short)i, (unsigned short)j));
+                coef.push_back(cf);
+            }
+        RepList& Q = R.lists[R.nlists++];
+        Q.npairs = (int)ij.size(); Q.form = L.form; Q.has_switch = L.dev.has_switch;
+        Q.rc2 = L.dev.rc2; Q.k_in = L.dev.k_in; Q.rsw = L.dev.rsw; Q.inv_sw = L.dev.inv_sw; Q.inv_debye = L.dev.inv_debye;
+        if (ij.empty()) { ij.push_back(make_ushort2(0, 0)); coef.push_back(make_float4(0, 0, 0, 0)); }
+        c->rep_ij.emplace_back(new DevBuf<ushort2>()); c->rep_ij.back()->upload(ij);
+        c->rep_coef.emplace_back(new DevBuf<float4>()); c->rep_coef.back()->upload(coef);
+        Q.ij = c->rep_ij.back()->p; Q.coef = c->rep_coef.back()->p;
+    }
+    // bonded tables of one replica (local bead indices); a single system uses the engine's own tables
+    if (c->nrep == 1) for (int k = 0; k < B_NUM_KINDS; k++) R.bonded[k] = c->bonded_h[k];
+    else {
+        // (table ids must match the replicated compile: tables are appended per BondedTerm in system order, once per term)
+        for (int k = 0; k < B_NUM_KINDS; k++) {
+            std::vector<int> idx, meta;
+            std::vector<double> par;
+            int npar = 0;
+            for (size_t ti = 0; ti < S1.bonded.size(); ti++) {
+                const BondedTerm& t = S1.bonded[ti];
+                if (t.kind != k) continue;
+                npar = t.npar;
+                // the table id the replicated compile gave this term: count the flexible-local terms of kinds <= k before it
+                int tab_id = 0;
+                if (k == B_FLEX_ANGLE || k == B_FLEX_DIHEDRAL) {
+                    tab_id = 1;
+                    for (int kk = 0; kk <= k; kk++)
+                        for (size_t tj = 0; tj < S1.bonded.size(); tj++) {
+                            const BondedTerm& u = S1.bonded[tj];
+                            if (u.kind != kk || !(kk == B_FLEX_ANGLE || kk == B_FLEX_DIHEDRAL)) continue;
+                            if (kk == k && tj >= ti) break;
+                            tab_id++;
+                        }
+                }
+                idx.insert(idx.end(), t.idx.begin(), t.idx.end());
+                par.insert(par.end(), t.p.begin(), t.p.end());
+                for (int64_t m = 0; m < t.n(); m++) meta.push_back(t.group | (t.periodic << 8) | (tab_id << 16));
+            }
+            BondedDev& B = R.bonded[k];
+            B = BondedDev{};
+            B.n = (int)(idx.size() / bonded_nbody(k)); B.npar = npar;
+            if (B.n) {
+                c->rep_b_idx[k].upload(idx); c->rep_b_par[k].upload(par); c->rep_b_meta[k].upload(meta);
+                B.idx = c->rep_b_idx[k].p; B.par = c->rep_b_par[k].p; B.meta = c->rep_b_meta[k].p;
+            }
+            B.tabs = c->b_tabs.p;
+        }
+    }
+    R.rep_seed = c->nrep > 1 ? c->d_rep_seed.p : nullptr;
+    c->rep_smem = (size_t)nper * (3 * 8 + 16 + 16);
+    CUDA_TRY(cudaFuncSetAttribute(replica_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(c->rep_smem, 1024)));
+    c->rep_ok = true;
+}
+
 static void compile_da(ocm_context* c) {
     long long cand = 0;
     for (const auto& t : c->sys.das) {
@@ -1307,9 +1410,39 @@ static int initial_nst(const ocm_context* c) {
     return quantise_nst(std::max(1.0, std::min(100.0, n)));
 }
 
+// small unlimited-boundary systems and replica ensembles: the whole MD step in one persistent kernel, one block per replica
+static void do_steps_replica_kernel(ocm_context* c, int64_t nsteps) {
+    cudaStream_t s = c->stream;
+    RepParams& R = c->rep;
+    R.dt = c->P.dt; R.a = c->P.a; R.b = c->P.b; R.c = c->P.c; R.seed_lo = c->P.seed_lo; R.seed_hi = c->P.seed_hi;
+    CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, FLAG_COUNT * sizeof(int), s));
+    CUDA_TRY(cudaEventRecord(c->ev0, s));
+    // (launches of at most 65 536 steps: a block holds its replica for the whole launch)
+    for (int64_t done = 0; done < nsteps;) {
+        const int chunk = (int)std::min<int64_t>(65536, nsteps - done);
+        replica_step_kernel<<<c->nrep, kRepBlock, c->rep_smem, s>>>(R, c->x.p, c->v.p, c->fbuf.p, c->n, (unsigned long long)(c->step + done), chunk, c->flags.p);
+        c->n_launches += 1; c->n_rep_launches += 1;
+        done += chunk;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev1, s));
+    // the general path (observer kernels, list builds) reads posq: bring it up to date
+    canon_kernel<<<nblk(c->n, 256), 256, 0, s>>>(c->P, c->x.p, c->posq.p);
+    int fl[FLAG_COUNT];
+    CUDA_TRY(cudaMemcpyAsync(fl, c->flags.p, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (fl[FLAG_NAN]) throw std::runtime_error("particle coordinate or force is NaN");
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_step_ms = ms;
+    c->step += nsteps;
+    c->lists_current = false;
+}
+
 static void do_steps(ocm_context* c, int64_t nsteps) {
     if (nsteps <= 0) return;
     if (!c->positions_set) throw std::runtime_error("positions have not been set");
+    if (c->rep_ok && c->rep_opt) { do_steps_replica_kernel(c, nsteps); return; }
     if (!c->lists_ready) size_lists(c, 1.25);
     cudaStream_t s = c->stream;
     const size_t xb = (size_t)3 * c->n * sizeof(double), vb = (size_t)c->n * sizeof(float4);
@@ -1616,6 +1749,7 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
     }
     if (nrep == 1) c->sys = *sys;
     else {
+        c->sys1 = *sys;
         // the batch is one big system: every table replicated with shifted bead indices
         const int np = sys->n;
         ocm_system& S = c->sys;
@@ -1691,6 +1825,7 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
                 if (L->rc_list + c->skin > 0.5 * c->sys.box[k]) c->skin = std::max(0.0, 0.5 * c->sys.box[k] - L->rc_list) * 0.999;
     compile_bonded(c);
     update_params(c);
+    compile_replica_tables(c);
     c->nst = initial_nst(c);
     CUDA_TRY(cudaDeviceSynchronize());
     *out = c;
@@ -1846,6 +1981,10 @@ int ocm_context_set_option(ocm_context* c, const char* key, double value) {
         c->tile_opt = value > 0 ? 1 : (value < 0 ? -1 : 0);
         c->lists_ready = false; c->lists_current = false;
         drop_graphs(c);
+    } else if (k == "replica_kernel") {
+        // 1: small unlimited-boundary systems and replica ensembles step in the whole-step persistent kernel; 0 (default: it measured
+        // slower, see replica_kernels.cuh): general path
+        c->rep_opt = (int)value;
     } else if (k == "tile_debug") {
         // timing experiments only (wrong forces): see TileLaunch::debug; 4 = evaluate the list without its switching function
         c->tile_debug = (int)value;
@@ -1874,6 +2013,7 @@ int ocm_context_get_option(ocm_context* c, const char* key, double* value) {
     else if (k == "row_staging") *value = c->staging_opt;
     else if (k == "halo_capacity") *value = c->dd ? c->dd->cap : 0;
     else if (k == "pair_kernel") *value = c->tile_opt;
+    else if (k == "replica_kernel") *value = (c->rep_ok && c->rep_opt) ? 1 : 0;
     else if (k == "tile_blocks") *value = c->tile_chunk_opt;
     else return fail("unknown option: " + k);
     return 0;
@@ -2133,6 +2273,7 @@ int ocm_get_counter(ocm_context* c, const char* key, double* value) {
     else if (k == "phase_ms.integrate") *value = c->ph_ms[2];
     else if (k == "phase_ms.halo") *value = c->ph_ms[3];
     else if (k == "rollbacks") *value = c->n_rollbacks;
+    else if (k == "replica_kernel_launches") *value = c->n_rep_launches;
     else if (k == "kernel_launches") *value = c->n_launches;
     else if (k == "nstlist") *value = c->nst;
     else if (k == "last_step_ms") *value = c->last_step_ms;

@@ -227,6 +227,23 @@ def test_replica_batch_large(engine):
     assert np.abs(a[:n] - b).max() < 2e-5
 
 
+@pytest.mark.parametrize("replicas", [None, 5])
+def test_whole_step_replica_kernel_option(engine, oracle, replicas):
+    """option replica_kernel = 1: the whole MD step of a small system in one persistent kernel, one block per replica
+    (replica_kernels.cuh; off by default because it measured slower).  Same noise streams, so it tracks the oracle like the
+    general path, step by step and across launches."""
+    spec = load_golden_spec("sh3")
+    ctx, ora = ti.make_context(engine, spec, replicas=replicas), ti.make_context(oracle, spec, replicas=replicas)
+    ctx.set_option("replica_kernel", 1)
+    assert ctx.get_option("replica_kernel") == 1
+    ctx.step(7); ctx.step(13); ora.step(20)
+    assert ctx.counter("replica_kernel_launches") == 2 and ctx.current_step == 20
+    a = ctx.get_state(positions=True, velocities=True); b = ora.get_state(positions=True, velocities=True)
+    assert np.abs(a["positions"] - b["positions"]).max() < 2e-5
+    assert np.abs(a["velocities"] - b["velocities"]).max() < 2e-3
+    check_state(ctx, ora, spec, ftol=5e-3, etol=5e-3)  # states differ by the accumulated FP32 drift
+
+
 def test_cell_assignment_bit_exact(engine, oracle):
     import ctypes as C
     for spec in (synth.hps_slab(n_chains=12), load_golden_spec("sh3")):

@@ -210,6 +210,12 @@ def nccl_comm(lib, rank, world, local):
     return Comm.nccl(lib, bytes(uid.cpu().numpy().tobytes()), world, rank, local)
 
 
+def sharding_gather(values, local):
+    from opencafemol_b200 import sharding
+
+    return sharding.gather_concat(values, device=f"cuda:{local}")
+
+
 def timed_steps(ctx, warm, steps, local, world):
     """device seconds (MAX over ranks) of `steps` MD steps after `warm` warm-up steps"""
     import torch
@@ -309,13 +315,14 @@ def multi_gpu_records(lib, rank, world, local):
     ctx.set_option("phase_timing", 1)
     ctx.step(200)
     phases = {k: ctx.counter("phase_ms." + k) / 200 for k in ("rebuild", "force", "integrate", "halo")}
+    owned = sharding_gather([ctx.counter("owned_beads")], local)
     if rank == 0:
         sN = 600 / dev
         out["c5"] = {"workload": "C5: C2 compacted state tiled 8 x 8, 1 043 200 beads, %d slabs along y" % world, "md_steps_per_s": sN,
                      "ns_per_day": ns_per_day(600, spec.dt, dev), "md_steps_per_s_one_gpu": one, "strong_scaling_efficiency": sN / one / world,
                      "nstlist": nst, "phase_ms_per_step_rank0": phases, "halo_message_bytes": ctx.counter("halo_message_bytes"),
                      "halo": "peer-memory push (CUDA IPC over NVLink)" if ctx.counter("halo_push") else "nccl send/recv",
-                     "pair_kernel": "tiles" if ctx.counter("tiled.1") else "rows"}
+                     "pair_kernel": "tiles" if ctx.counter("tiled.1") else "rows", "owned_beads_per_rank": [int(v) for v in owned]}
     dist.barrier()
     ctx.close()
     comm.close()

@@ -2324,10 +2324,14 @@ int ocm_get_counter(ocm_context* c, const char* key, double* value) {
         // the grid rule of the list serving a pair term (the oracle restates it: oracle_get_cell_ids_grid)
         int term = std::atoi(k.c_str() + k.find('.') + 1);
         if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");
-        CUDA_TRY(cudaSetDevice(c->device));
-        ensure_lists_current(c);
+        // (not collective: no list build here.  The grid exists once the lists have been sized, i.e. after the first force,
+        // energy or step call)
         const PairListHost& L = *c->lists[c->term_list[term]];
-        *value = k[0] == 't' ? (L.tiled ? 1.0 : 0.0) : (k[5] == 'w' ? (double)L.cell_width : (double)L.cell_cap);
+        if (k[0] == 't') *value = (L.tile_ok && (c->tile_opt > 0 || (c->tile_opt < 0 && L.tile_auto))) ? 1.0 : 0.0;
+        else {
+            if (!c->lists_ready) return fail("the cell grid is laid out with the first list build: evaluate forces or energies first");
+            *value = k[5] == 'w' ? (double)L.cell_width : (double)L.cell_cap;
+        }
     } else if (k.rfind("list_cutoff_nm.", 0) == 0) {
         int term = std::atoi(k.c_str() + 15);
         if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");

@@ -264,6 +264,21 @@ def single_gpu_records(lib, local):
     ctx = toml_input.make_context(lib, sh3, device=local)
     dev = timed_steps(ctx, 500, 5000, local, 1)
     out["c1"] = {"workload": "C1: sample/toml_input/sh3_AICG2+.toml (56 beads)", "md_steps_per_s": 5000 / dev, "ns_per_day": ns_per_day(5000, sh3.dt, dev)}
+    # end to end with the sample's own save_step = 100: every frame downloads positions + energies (what its observers ask for),
+    # the download of frame k overlapping the steps of frame k + 1
+    import torch
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    req = None
+    for _ in range(50):
+        ctx.step(100)
+        nxt = ctx.get_state_begin(positions=True, energy=True)
+        if req is not None:
+            ctx.get_state_end(req)
+        req = nxt
+    ctx.get_state_end(req)
+    torch.cuda.synchronize()
+    out["c1"]["e2e_md_steps_per_s_save_step_100"] = 5000 / (time.perf_counter() - t0)
     ctx.close()
     return out
 
@@ -381,10 +396,10 @@ def run_engine(args):
     barrier()
     te0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.set_positions(pos)
-        ctx.set_velocities(vel)
+        # (pinned staging + device-side conversion on both sides; the energy kernels reuse the pair lists of the last window)
+        ctx.set_state_async(pos, vel)
         ctx.step(MD_STEPS_PER_STEP)
-        st = ctx.get_state(positions=True, velocities=True, energy=True)
+        st = ctx.get_state_end(ctx.get_state_begin(positions=True, velocities=True, energy=True))
         pos, vel = st["positions"], st["velocities"]
     barrier()
     t_e2e = time.perf_counter() - te0

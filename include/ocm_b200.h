@@ -257,6 +257,27 @@ int ocm_set_velocities_to_temperature(ocm_context*, double temperature_K, uint64
 int ocm_step(ocm_context*, int64_t nsteps);
 int64_t ocm_current_step(const ocm_context*);
 
+/* Observer side of a frame without stalling the run loop (Observer.cpp:103-118: two synchronous getState downloads per
+ * frame; Observer.cpp:324-346: G+1 energy evaluations; caller Simulator.cpp:55-60).
+ *   ocm_get_state_begin  snapshots what was asked for at the current step: the energy / force kernels are queued on the
+ *                        compute stream behind the steps already issued (they reuse the pair lists of the last window
+ *                        when no bead has left its Verlet buffer, so no list build), positions, velocities, forces and
+ *                        energies are converted on the device into one staging block, and its download into PINNED host
+ *                        memory runs on a side stream.  Returns at once; ocm_step may be called right away and the
+ *                        download overlaps the next window.
+ *   ocm_get_state_end    waits for that download only (not for steps issued after begin) and copies to the caller's
+ *                        arrays (any may be NULL); the request is consumed.
+ * ocm_get_state is the blocking form.  Replica batches and slab contexts accept the calls but serve them synchronously
+ * inside ocm_get_state_end (at the state of that moment).
+ * ocm_set_state_async: positions and velocities through pinned staging, converted on the device, no host synchronisation
+ * (velocities may be NULL). */
+typedef struct ocm_state_request ocm_state_request;
+int ocm_get_state_begin(ocm_context*, uint32_t group_mask, int want_positions, int want_velocities, int want_forces,
+                        int want_energies, ocm_state_request** out);
+int ocm_get_state_end(ocm_state_request*, double* pos, double* vel, double* force, double* e_pot, double* e_kin,
+                      double* e_by_group32);
+int ocm_set_state_async(ocm_context*, const double* xyz_nm, const double* vel_nm_per_ps);
+
 /* LocalEnergyMinimizer::minimize(context) (Simulator.cpp:43-46; OpenMM defaults: tolerance 10 kJ/mol/nm,
  * maxIterations 0 = until convergence): L-BFGS on the potential energy from the current positions until the
  * RMS force per particle drops below `tolerance`.  Energies and forces are evaluated on the device, the

@@ -218,6 +218,9 @@ class Library:
         "current_step": (C.c_int64, [C.c_void_p]),
         "minimize": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
         "get_state": (C.c_int, [C.c_void_p, C.c_uint32, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]),
+        "get_state_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+        "get_state_end": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]),
+        "set_state_async": (C.c_int, [C.c_void_p, _f64p, _f64p]),
         "num_pair_terms": (C.c_int, [C.c_void_p]),
         "get_neighbor_pairs": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int64, _i64p]),
         "get_cell_ids": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p]),
@@ -574,6 +577,42 @@ class Context:
             out["kinetic_energy"] = ek.value
             out["energy_by_group"] = ebg
         return out
+
+    def get_state_begin(self, positions=False, velocities=False, forces=False, energy=False, groups=0xFFFFFFFF):
+        """Observer without stalls (Observer.cpp:103-118, 324-346): queues the frame's energy kernels behind the issued steps and
+        its download on a side stream, returns at once; `step` may follow immediately.  Finish with get_state_end(request)."""
+        h = C.c_void_p()
+        self.lib.check(self.lib.fn["get_state_begin"](self.handle, int(groups) & 0xFFFFFFFF, int(positions), int(velocities), int(forces),
+                                                       int(energy), C.byref(h)))
+        return (h, positions, velocities, forces, energy)
+
+    def get_state_end(self, request):
+        h, positions, velocities, forces, energy = request
+        out = {}
+        pos = np.empty((self.n, 3)) if positions else None
+        vel = np.empty((self.n, 3)) if velocities else None
+        frc = np.empty((self.n, 3)) if forces else None
+        ep, ek = C.c_double(), C.c_double()
+        ebg = np.zeros(32) if energy else None
+        self.lib.check(self.lib.fn["get_state_end"](h, _p(pos, _f64p), _p(vel, _f64p), _p(frc, _f64p), C.byref(ep) if energy else None,
+                                                     C.byref(ek) if energy else None, _p(ebg, _f64p)))
+        if positions:
+            out["positions"] = pos
+        if velocities:
+            out["velocities"] = vel
+        if forces:
+            out["forces"] = frc
+        if energy:
+            out["potential_energy"] = ep.value
+            out["kinetic_energy"] = ek.value
+            out["energy_by_group"] = ebg
+        return out
+
+    def set_state_async(self, positions, velocities=None):
+        """positions (and velocities) through pinned staging without a host synchronisation"""
+        a = _f64(positions).reshape(-1)
+        b = _f64(velocities).reshape(-1) if velocities is not None else None
+        self.lib.check(self.lib.fn["set_state_async"](self.handle, _p(a, _f64p), _p(b, _f64p)))
 
     def slab_info(self):
         r, w, a, h = C.c_int(), C.c_int(), C.c_int(), C.c_double()

@@ -412,11 +412,16 @@ class Context {
     Platform* platform_;
     ocm_context* h_ = nullptr;
     // per-group energies are evaluated once per state: the reference's EnergyObserver asks for them group by group
-    mutable bool energy_valid_ = false;
+    // one frame of observer output: the first getState() after a step fetches positions, velocities and all 32 group
+    // energies with ONE asynchronous request (ocm_get_state_begin / _end: side-stream download from pinned staging); the
+    // other getState() calls of the frame (Observer.cpp:103-118: positions, then velocities; Observer.cpp:324-346: one
+    // call per force group) are served from this copy
+    mutable bool energy_valid_ = false, frame_valid_ = false;
     mutable double ebg_[32];
     mutable double ekin_ = 0;
+    mutable std::vector<Vec3> frame_pos_, frame_vel_;
     void create(const std::map<std::string, std::string>& properties);
-    void invalidate() const { energy_valid_ = false; }
+    void invalidate() const { energy_valid_ = false; frame_valid_ = false; }
 };
 
 class LocalEnergyMinimizer {

@@ -590,19 +590,27 @@ State Context::getState(int types, bool enforcePeriodicBox, int groups) const {
     s.time_ = getTime();
     sys_->getDefaultPeriodicBoxVectors(s.box_[0], s.box_[1], s.box_[2]);
     const int n = sys_->getNumParticles();
-    if (types & State::Positions) s.pos_.resize(n);
-    if (types & State::Velocities) s.vel_.resize(n);
     if (types & State::Forces) s.frc_.resize(n);
     if ((types & State::Forces) && (unsigned)groups != 0xFFFFFFFFu) throw OpenMMException("B200 engine: forces restricted to a force-group mask are not supported");
-    const bool want_energy = (types & State::Energy) && !energy_valid_;
-    if ((types & (State::Positions | State::Velocities | State::Forces)) || want_energy) {
+    if (types & State::Forces) {
+        // forces are not part of the frame copy: blocking call
         double epot = 0;
-        check(ocm_get_state(h_, 0xFFFFFFFFu, (types & State::Positions) ? reinterpret_cast<double*>(s.pos_.data()) : nullptr,
-                            (types & State::Velocities) ? reinterpret_cast<double*>(s.vel_.data()) : nullptr,
-                            (types & State::Forces) ? reinterpret_cast<double*>(s.frc_.data()) : nullptr, want_energy ? &epot : nullptr,
+        const bool want_energy = (types & State::Energy) && !energy_valid_;
+        check(ocm_get_state(h_, 0xFFFFFFFFu, nullptr, nullptr, reinterpret_cast<double*>(s.frc_.data()), want_energy ? &epot : nullptr,
                             want_energy ? &ekin_ : nullptr, want_energy ? ebg_ : nullptr), "getState");
         if (want_energy) energy_valid_ = true;
     }
+    if ((types & (State::Positions | State::Velocities | State::Energy)) && !frame_valid_) {
+        frame_pos_.resize(n); frame_vel_.resize(n);
+        double epot = 0;
+        ocm_state_request* rq = nullptr;
+        check(ocm_get_state_begin(h_, 0xFFFFFFFFu, 1, 1, 0, 1, &rq), "getState");
+        check(ocm_get_state_end(rq, reinterpret_cast<double*>(frame_pos_.data()), reinterpret_cast<double*>(frame_vel_.data()), nullptr, &epot, &ekin_, ebg_),
+              "getState");
+        frame_valid_ = true; energy_valid_ = true;
+    }
+    if (types & State::Positions) s.pos_ = frame_pos_;
+    if (types & State::Velocities) s.vel_ = frame_vel_;
     if (types & State::Energy) {
         double e = 0;
         for (int g = 0; g < 32; g++) if ((unsigned)groups >> g & 1u) e += ebg_[g];

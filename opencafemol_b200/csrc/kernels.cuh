@@ -1683,6 +1683,29 @@ __global__ void kinetic_kernel(StepParams P, const float4* __restrict__ v, const
     else block_add(e, ke);
 }
 
+// observer staging: what the host asked for, converted on the device into one block of doubles
+// [positions 3n | velocities 3n | forces 3n | 32 group energies, kinetic energy, 7 spare], so that one copy into pinned
+// host memory serves the frame (ocm_get_state_begin)
+__global__ void pack_state_kernel(int n, const double* __restrict__ x, const float4* __restrict__ v, const unsigned long long* __restrict__ fbuf,
+                                  double* __restrict__ out_x, double* __restrict__ out_v, double* __restrict__ out_f) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (out_x) { out_x[3 * i] = x[3 * i]; out_x[3 * i + 1] = x[3 * i + 1]; out_x[3 * i + 2] = x[3 * i + 2]; }
+    if (out_v) { const float4 vi = v[i]; out_v[3 * i] = vi.x; out_v[3 * i + 1] = vi.y; out_v[3 * i + 2] = vi.z; }
+    if (out_f) {
+        const double inv = 1.0 / kFixScale;
+        out_f[3 * i] = (double)(long long)fbuf[i] * inv; out_f[3 * i + 1] = (double)(long long)fbuf[n + i] * inv;
+        out_f[3 * i + 2] = (double)(long long)fbuf[2 * (size_t)n + i] * inv;
+    }
+}
+// ocm_set_state_async: staged doubles -> master positions, FP32 velocities (w = 1/m is kept)
+__global__ void unpack_state_kernel(int n, const double* __restrict__ in_x, const double* __restrict__ in_v, double* __restrict__ x, float4* __restrict__ v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (in_x) { x[3 * i] = in_x[3 * i]; x[3 * i + 1] = in_x[3 * i + 1]; x[3 * i + 2] = in_x[3 * i + 2]; }
+    if (in_v) { float4 vi = v[i]; vi.x = (float)in_v[3 * i]; vi.y = (float)in_v[3 * i + 1]; vi.z = (float)in_v[3 * i + 2]; v[i] = vi; }
+}
+
 // pairs (i<j) of list `li` inside rc2_term, appended unordered (host sorts)
 template <bool PER>
 __global__ void extract_pairs_kernel(const PairListDev* lists, int li, StepParams P, float rc2_term,

@@ -193,6 +193,14 @@ struct ocm_context {
     std::vector<WorkSeg> segs;
     DevBuf<WorkSeg> d_segs;
     int tile_blocks = 0;                    // blocks of all tile force launches (tile lists have one launch each)
+    // observer staging (ocm_get_state_begin / _end, ocm_set_state_async): device block + pinned host mirrors
+    DevBuf<double> obs_dev[2], in_dev;      // two observer blocks: a download may still run while the next frame is staged
+    double* obs_pin[2] = {nullptr, nullptr}; double* in_pin = nullptr;
+    size_t obs_pin_n[2] = {0, 0}, in_pin_n = 0;
+    cudaEvent_t ev_obs = nullptr, ev_obs_done[2] = {nullptr, nullptr}, ev_in_free = nullptr;
+    bool obs_busy[2] = {false, false}, obs_used[2] = {false, false}, in_pending = false;
+    int obs_next = 0;
+    double n_async_states = 0, n_obs_rebuilds_skipped = 0;
     // whole-step persistent kernel for small unlimited-boundary systems and replica ensembles (replica_kernels.cuh)
     ocm_system sys1;                        // the system of ONE replica (replica batches keep it beside the replicated tables)
     bool rep_ok = false;
@@ -234,6 +242,7 @@ struct ocm_context {
     int chunk_opt = 0;       // beads per block of the pair kernels, 0 = auto
     int staging_opt = 0;     // stage Verlet rows in shared memory with bulk async copies
     bool lists_ready = false, positions_set = false, lists_current = false;
+    bool last_disp2_ok = false;  // every window of the last batch ended with all beads inside their Verlet buffer
     std::map<int, cudaGraphExec_t> graphs;
     // counters
     double n_rebuilds = 0, n_rollbacks = 0, n_launches = 0, n_windows = 0, last_step_ms = 0;
@@ -243,6 +252,10 @@ struct ocm_context {
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_obs) cudaEventDestroy(ev_obs);
+        for (int b = 0; b < 2; b++) { if (ev_obs_done[b]) cudaEventDestroy(ev_obs_done[b]); if (obs_pin[b]) cudaFreeHost(obs_pin[b]); }
+        if (ev_in_free) cudaEventDestroy(ev_in_free);
+        if (in_pin) cudaFreeHost(in_pin);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         if (side) cudaStreamDestroy(side);
@@ -1506,6 +1519,11 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
         }
         c->n_launches += launches; c->n_windows += windows; c->n_rebuilds += windows;
         done += batch;
+        {
+            float d2max;
+            std::memcpy(&d2max, &fl[FLAG_MAXDISP], sizeof(float));
+            c->last_disp2_ok = d2max <= (float)(0.25 * c->skin * c->skin);
+        }
         // adapt the rebuild interval from the largest end-of-window displacement (only full windows count)
         if (c->nstlist_fixed <= 0 && batch >= nst) {
             float d2;
@@ -1525,7 +1543,10 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
     CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->last_step_ms = ms;
     c->step += nsteps;
-    c->lists_current = false;
+    // The pair lists of the last window still hold every pair inside the cutoffs if no bead has moved more than half the skin
+    // from the list's reference positions (the cell-sorted positions are refreshed by every step): the observer can evaluate
+    // energies and forces on them without a list build.  (Slab decomposition: halos are only complete right after a rebuild.)
+    c->lists_current = !c->dd && c->nrep == 1 && c->last_disp2_ok;
 }
 
 // per-group energies of every term at the current positions (lists must be current), added into egroup
@@ -1793,6 +1814,9 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
     CUDA_TRY(cudaEventCreate(&c->ev1));
     CUDA_TRY(cudaFuncSetAttribute(build_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 16));
     CUDA_TRY(cudaFuncSetAttribute(build_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 16));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_obs, cudaEventDisableTiming));
+    for (int b = 0; b < 2; b++) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_obs_done[b], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_in_free, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     const int n = c->n;
@@ -2146,6 +2170,127 @@ int ocm_get_state(ocm_context* c, uint32_t mask, double* pos, double* vel, doubl
     OCM_GUARD_END
 }
 
+// ---- observer without stalls ------------------------------------------------------------------------------
+struct ocm_state_request {
+    ocm_context* c = nullptr;
+    uint32_t mask = 0xFFFFFFFFu;
+    bool pos = false, vel = false, force = false, energy = false;
+    bool deferred = false;   // replica batches / slab contexts: served synchronously in ocm_get_state_end
+    int buf = 0;             // which of the two staging blocks
+    size_t off_x = 0, off_v = 0, off_f = 0, off_e = 0;
+};
+
+static void ensure_pinned(double*& p, size_t& have, size_t want) {
+    if (have >= want) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr; have = 0;
+    CUDA_TRY(cudaHostAlloc((void**)&p, want * sizeof(double), cudaHostAllocDefault));
+    have = want;
+}
+
+int ocm_get_state_begin(ocm_context* c, uint32_t mask, int want_pos, int want_vel, int want_force, int want_energy, ocm_state_request** out) {
+    if (!c || !out) return fail("null argument");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    auto rq = std::make_unique<ocm_state_request>();
+    rq->c = c; rq->mask = mask; rq->pos = want_pos != 0; rq->vel = want_vel != 0; rq->force = want_force != 0; rq->energy = want_energy != 0;
+    if (c->dd || c->nrep > 1) { rq->deferred = true; *out = rq.release(); return 0; }
+    const int b = c->obs_next;
+    if (c->obs_busy[b]) return fail("get_state_begin: two requests are already open; end one first");
+    rq->buf = b;
+    if (rq->force && mask != 0xFFFFFFFFu) return fail("get_state: forces restricted to a force-group mask are not supported; request all groups");
+    cudaStream_t s = c->stream;
+    const int n = c->n;
+    const size_t n3 = (size_t)3 * n;
+    size_t off = 0;
+    if (rq->pos) { rq->off_x = off; off += n3; }
+    if (rq->vel) { rq->off_v = off; off += n3; }
+    if (rq->force) { rq->off_f = off; off += n3; }
+    rq->off_e = off; off += 40;
+    // (block b was last downloaded two requests ago: make sure that copy has left it before it is overwritten)
+    if (c->obs_used[b]) CUDA_TRY(cudaStreamWaitEvent(s, c->ev_obs_done[b], 0));
+    if (c->obs_dev[b].n < off) { CUDA_TRY(cudaStreamSynchronize(c->side)); c->obs_dev[b].alloc(off); }
+    ensure_pinned(c->obs_pin[b], c->obs_pin_n[b], off);
+    double* D = c->obs_dev[b].p;
+    if (rq->force || rq->energy) {
+        if (c->lists_current) c->n_obs_rebuilds_skipped += 1;
+        ensure_lists_current(c);
+        CUDA_TRY(cudaMemsetAsync(c->egroup.p, 0, 40 * sizeof(double), s));
+        if (rq->energy) enqueue_energies(c, s);
+        compute_forces_into_fbuf(c);   // (also what the kinetic energy needs: velocities are half a step behind)
+        if (rq->energy) kinetic_kernel<<<nblk(n, kBlock), kBlock, 0, s>>>(c->P, c->v.p, c->fbuf.p, c->egroup.p + 32);
+        CUDA_TRY(cudaMemcpyAsync(D + rq->off_e, c->egroup.p, 40 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    }
+    if (rq->pos || rq->vel || rq->force)
+        pack_state_kernel<<<nblk(n, 256), 256, 0, s>>>(n, c->x.p, c->v.p, c->fbuf.p, rq->pos ? D + rq->off_x : nullptr, rq->vel ? D + rq->off_v : nullptr,
+                                                        rq->force ? D + rq->off_f : nullptr);
+    if (rq->force || rq->energy) CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, n3 * sizeof(unsigned long long), s));
+    // the download runs on the side stream: the compute stream is free for the next window
+    CUDA_TRY(cudaEventRecord(c->ev_obs, s));
+    CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_obs, 0));
+    CUDA_TRY(cudaMemcpyAsync(c->obs_pin[b], D, off * sizeof(double), cudaMemcpyDeviceToHost, c->side));
+    CUDA_TRY(cudaEventRecord(c->ev_obs_done[b], c->side));
+    c->obs_busy[b] = true; c->obs_used[b] = true; c->obs_next = b ^ 1;
+    c->n_async_states += 1;
+    *out = rq.release();
+    return 0;
+    OCM_GUARD_END
+}
+
+int ocm_get_state_end(ocm_state_request* rq, double* pos, double* vel, double* force, double* epot, double* ekin, double* ebg) {
+    if (!rq) return fail("null request");
+    std::unique_ptr<ocm_state_request> own(rq);
+    ocm_context* c = rq->c;
+    if (rq->deferred)
+        return ocm_get_state(c, rq->mask, rq->pos ? pos : nullptr, rq->vel ? vel : nullptr, rq->force ? force : nullptr, rq->energy ? epot : nullptr,
+                             rq->energy ? ekin : nullptr, rq->energy ? ebg : nullptr);
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int b = rq->buf;
+    c->obs_busy[b] = false;
+    CUDA_TRY(cudaEventSynchronize(c->ev_obs_done[b]));
+    const size_t nb = (size_t)3 * c->n * sizeof(double);
+    const double* H = c->obs_pin[b];
+    if (pos && rq->pos) std::memcpy(pos, H + rq->off_x, nb);
+    if (vel && rq->vel) std::memcpy(vel, H + rq->off_v, nb);
+    if (force && rq->force) std::memcpy(force, H + rq->off_f, nb);
+    if (rq->energy) {
+        const double* he = H + rq->off_e;
+        if (epot) { double e = 0; for (int g = 0; g < 32; g++) if (rq->mask >> g & 1) e += he[g]; *epot = e; }
+        if (ebg) std::copy(he, he + 32, ebg);
+        if (ekin) *ekin = he[32];
+    }
+    return 0;
+    OCM_GUARD_END
+}
+
+int ocm_set_state_async(ocm_context* c, const double* xyz, const double* vel) {
+    if (!c || !xyz) return fail("null argument");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    // (a virtual box may have to be laid out again around the new positions, slab contexts assign roles: blocking forms)
+    if (c->vbox || c->dd) {
+        if (ocm_set_positions(c, xyz)) return 1;
+        return vel ? ocm_set_velocities(c, vel) : 0;
+    }
+    cudaStream_t s = c->stream;
+    const int n = c->n;
+    const size_t n3 = (size_t)3 * n, tot = vel ? 2 * n3 : n3;
+    if (c->in_pending) CUDA_TRY(cudaEventSynchronize(c->ev_in_free));   // the previous upload has left the pinned block
+    ensure_pinned(c->in_pin, c->in_pin_n, tot);
+    if (c->in_dev.n < tot) c->in_dev.alloc(tot);
+    std::memcpy(c->in_pin, xyz, n3 * sizeof(double));
+    if (vel) std::memcpy(c->in_pin + n3, vel, n3 * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(c->in_dev.p, c->in_pin, tot * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(c->ev_in_free, s));
+    c->in_pending = true;
+    unpack_state_kernel<<<nblk(n, 256), 256, 0, s>>>(n, c->in_dev.p, vel ? c->in_dev.p + n3 : nullptr, c->x.p, c->v.p);
+    canon_kernel<<<nblk(n, 256), 256, 0, s>>>(c->P, c->x.p, c->posq.p);
+    c->positions_set = true; c->lists_current = false;
+    return 0;
+    OCM_GUARD_END
+}
+
 int ocm_get_replica_energies(ocm_context* c, uint32_t mask, double* epot, double* ekin, double* ebg) {
     if (!c) return fail("null context");
     OCM_GUARD_BEGIN
@@ -2247,6 +2392,7 @@ int ocm_get_cell_ids(ocm_context* c, int term, int32_t* cell_of_bead, int32_t di
     if (term < 0 || term >= (int)c->sys.pairs.size()) return fail("pair term index out of range");
     OCM_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
+    c->lists_current = false;  // (after a run the lists of the last window may still be in use: cell ids are those of a fresh build)
     ensure_lists_current(c);
     PairListHost& L = *c->lists[c->term_list[term]];
     std::vector<int> cs(std::max(L.np, 1));
@@ -2274,6 +2420,8 @@ int ocm_get_counter(ocm_context* c, const char* key, double* value) {
     else if (k == "phase_ms.halo") *value = c->ph_ms[3];
     else if (k == "rollbacks") *value = c->n_rollbacks;
     else if (k == "replica_kernel_launches") *value = c->n_rep_launches;
+    else if (k == "async_states") *value = c->n_async_states;
+    else if (k == "observer_rebuilds_skipped") *value = c->n_obs_rebuilds_skipped;
     else if (k == "kernel_launches") *value = c->n_launches;
     else if (k == "nstlist") *value = c->nst;
     else if (k == "last_step_ms") *value = c->last_step_ms;

@@ -1524,6 +1524,46 @@ int oracle_get_cell_ids(ocm_context* c, int term, int32_t* cell_of_bead, int32_t
     return oracle_get_cell_ids_rlist(c, term, effective_rc(c->sys.pairs[term]) + 0.3, cell_of_bead, dims);
 }
 
+// the stall-free observer calls of the engine (ocm_get_state_begin / _end, ocm_set_state_async) restated: the oracle has no
+// device to overlap with, so begin snapshots synchronously and end hands the snapshot out
+struct ocm_state_request {
+    std::vector<double> pos, vel, force, ebg;
+    double epot = 0, ekin = 0;
+    bool has_energy = false;
+};
+int oracle_get_state_begin(ocm_context* c, uint32_t mask, int want_pos, int want_vel, int want_force, int want_energy, ocm_state_request** out) {
+    if (!c || !out) return fail("null argument");
+    auto* rq = new ocm_state_request();
+    const size_t n3 = (size_t)3 * c->sys.n;
+    if (want_pos) rq->pos.resize(n3);
+    if (want_vel) rq->vel.resize(n3);
+    if (want_force) rq->force.resize(n3);
+    rq->ebg.resize(32);
+    rq->has_energy = want_energy != 0;
+    int rc = oracle_get_state(c, mask, want_pos ? rq->pos.data() : nullptr, want_vel ? rq->vel.data() : nullptr, want_force ? rq->force.data() : nullptr,
+                              want_energy ? &rq->epot : nullptr, want_energy ? &rq->ekin : nullptr, want_energy ? rq->ebg.data() : nullptr);
+    if (rc) { delete rq; return rc; }
+    *out = rq;
+    return 0;
+}
+int oracle_get_state_end(ocm_state_request* rq, double* pos, double* vel, double* force, double* epot, double* ekin, double* ebg) {
+    if (!rq) return fail("null request");
+    if (pos && !rq->pos.empty()) std::copy(rq->pos.begin(), rq->pos.end(), pos);
+    if (vel && !rq->vel.empty()) std::copy(rq->vel.begin(), rq->vel.end(), vel);
+    if (force && !rq->force.empty()) std::copy(rq->force.begin(), rq->force.end(), force);
+    if (rq->has_energy) {
+        if (epot) *epot = rq->epot;
+        if (ekin) *ekin = rq->ekin;
+        if (ebg) std::copy(rq->ebg.begin(), rq->ebg.end(), ebg);
+    }
+    delete rq;
+    return 0;
+}
+int oracle_set_state_async(ocm_context* c, const double* xyz, const double* vel) {
+    if (int rc = oracle_set_positions(c, xyz)) return rc;
+    return vel ? oracle_set_velocities(c, vel) : 0;
+}
+
 int oracle_get_counter(ocm_context*, const char*, double* v) { if (v) *v = 0; return 0; }
 
 int oracle_profile_kernel(ocm_context*, const char*, int, double* v) { if (v) *v = 0; return fail("the oracle has no kernels"); }

@@ -244,6 +244,41 @@ def test_whole_step_replica_kernel_option(engine, oracle, replicas):
     check_state(ctx, ora, spec, ftol=5e-3, etol=5e-3)  # states differ by the accumulated FP32 drift
 
 
+def test_async_observer_matches_blocking_and_overlaps(engine, oracle):
+    """ocm_get_state_begin / _end (side-stream download from pinned staging, energy kernels on the lists of the last window) against
+    the blocking ocm_get_state, with a step issued between begin and end; ocm_set_state_async against set_positions/velocities."""
+    spec = synth.hps_slab(n_chains=12)
+    a, b = ti.make_context(engine, spec), ti.make_context(engine, spec)
+    a.step(100); b.step(100)
+    req = a.get_state_begin(positions=True, velocities=True, forces=True, energy=True)
+    a.step(50)                                   # runs while the frame of step 100 is on its way to the host
+    sa = a.get_state_end(req)
+    sb = b.get_state(positions=True, velocities=True, forces=True, energy=True)
+    assert np.array_equal(sa["positions"], sb["positions"]) and np.array_equal(sa["velocities"], sb["velocities"])
+    # (the blocking call rebuilds the lists, the asynchronous one reuses the last window's: same pair set, other summation order)
+    assert force_error(sa["forces"], sb["forces"]).max() < 1e-6
+    assert np.allclose(sa["energy_by_group"], sb["energy_by_group"], rtol=1e-7, atol=1e-6)
+    assert sa["kinetic_energy"] == pytest.approx(sb["kinetic_energy"], rel=1e-7)
+    assert a.counter("observer_rebuilds_skipped") >= 1 and a.counter("async_states") == 1
+    b.step(50)
+    assert np.array_equal(a.get_state(positions=True)["positions"], b.get_state(positions=True)["positions"])  # the observer left no trace
+    # two frames in flight, ended in order
+    r1 = a.get_state_begin(positions=True, energy=True); a.step(10)
+    r2 = a.get_state_begin(positions=True, energy=True); a.step(10)
+    f1, f2 = a.get_state_end(r1), a.get_state_end(r2)
+    assert np.abs(f1["positions"] - f2["positions"]).max() > 0
+    # upload through pinned staging: same trajectory as the blocking setters, and the oracle's restatement agrees
+    st = b.get_state(positions=True, velocities=True)
+    c, d, o = ti.make_context(engine, spec), ti.make_context(engine, spec), ti.make_context(oracle, spec)
+    c.set_state_async(st["positions"], st["velocities"])
+    d.set_positions(st["positions"]); d.set_velocities(st["velocities"])
+    o.set_state_async(st["positions"], st["velocities"])
+    c.step(20); d.step(20); o.step(20)
+    pc = c.get_state(positions=True)["positions"]
+    assert np.array_equal(pc, d.get_state(positions=True)["positions"])
+    assert np.abs(pc - o.get_state_end(o.get_state_begin(positions=True))["positions"]).max() < 2e-5
+
+
 def test_cell_assignment_bit_exact(engine, oracle):
     import ctypes as C
     for spec in (synth.hps_slab(n_chains=12), load_golden_spec("sh3")):

@@ -56,6 +56,7 @@ struct PairListDev {
     int* cell_count;            // [max_cells+1]
     int* cell_start;            // [max_cells+1]
     int* cell_cursor;           // [max_cells]
+    int* scan_tmp;              // [max_cells / 8192 + 2] block totals of the three-launch scan of large grids
     int* tmp_slots;             // [np] cell-grouped slots, arbitrary order inside a cell (scatter output)
     int* sorted_slots;          // [np] rank k -> slot; cells in grid order, ascending slot inside a cell
     int* rank_of_bead;          // [N]  bead -> rank k in this list's cell-sorted order, -1 = non participant
@@ -398,6 +399,71 @@ __global__ void scan_kernel(const PairListDev* lists, int li) {
         __syncthreads();
     }
     if (threadIdx.x == 0) L.cell_start[ncell] = carry;
+}
+
+// The same scan for large grids (a million fine cells at 1 M beads took the single block 0.65 ms): three launches.
+//   scan_blocks_kernel  every block scans its 8192 cells locally and leaves its total in scan_tmp[block]
+//   scan_tops_kernel    one block turns the block totals into exclusive offsets (up to 8192 blocks = 2^26 cells)
+//   scan_finish_kernel  adds the offsets, sets the cursors, clears the counts, writes cell_start[ncell]
+constexpr int kScanChunk = 1024 * kScanItems;
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(const PairListDev* lists, int li) {
+    const PairListDev& L = lists[li];
+    const int ncell = L.grid->ncell * L.nrep;
+    __shared__ int warp_sums[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i0 = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+    int vals[kScanItems];
+    int v = 0;
+#pragma unroll
+    for (int q = 0; q < kScanItems; q++) { vals[q] = (i0 + q < ncell) ? L.cell_count[i0 + q] : 0; v += vals[q]; }
+    int s = v;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+    if (lane == 31) warp_sums[wid] = s;
+    __syncthreads();
+    if (wid == 0) {
+        int ws = warp_sums[lane];
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += t; }
+        warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    int run = (wid > 0 ? warp_sums[wid - 1] : 0) + s - v;
+#pragma unroll
+    for (int q = 0; q < kScanItems; q++) { if (i0 + q < ncell) L.cell_start[i0 + q] = run; run += vals[q]; }
+    if (threadIdx.x == 1023) L.scan_tmp[blockIdx.x] = warp_sums[31];
+}
+__global__ void __launch_bounds__(1024) scan_tops_kernel(const PairListDev* lists, int li, int nblocks) {
+    const PairListDev& L = lists[li];
+    __shared__ int warp_sums[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i0 = threadIdx.x * kScanItems;
+    int vals[kScanItems];
+    int v = 0;
+#pragma unroll
+    for (int q = 0; q < kScanItems; q++) { vals[q] = (i0 + q < nblocks) ? L.scan_tmp[i0 + q] : 0; v += vals[q]; }
+    int s = v;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+    if (lane == 31) warp_sums[wid] = s;
+    __syncthreads();
+    if (wid == 0) {
+        int ws = warp_sums[lane];
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += t; }
+        warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    int run = (wid > 0 ? warp_sums[wid - 1] : 0) + s - v;
+#pragma unroll
+    for (int q = 0; q < kScanItems; q++) { if (i0 + q < nblocks) L.scan_tmp[i0 + q] = run; run += vals[q]; }
+    if (threadIdx.x == 1023) L.scan_tmp[nblocks] = warp_sums[31];
+}
+__global__ void __launch_bounds__(1024) scan_finish_kernel(const PairListDev* lists, int li) {
+    const PairListDev& L = lists[li];
+    const int ncell = L.grid->ncell * L.nrep;
+    const int off = L.scan_tmp[blockIdx.x];
+    const int i0 = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+#pragma unroll
+    for (int q = 0; q < kScanItems; q++)
+        if (i0 + q < ncell) { const int v = L.cell_start[i0 + q] + off; L.cell_start[i0 + q] = v; L.cell_cursor[i0 + q] = v; L.cell_count[i0 + q] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) L.cell_start[ncell] = L.scan_tmp[gridDim.x];
 }
 
 __global__ void scatter_kernel(const PairListDev* lists, int li) {

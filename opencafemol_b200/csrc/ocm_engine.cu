@@ -73,7 +73,7 @@ struct PairListHost {
     double rc_list = 0;      // largest effective cutoff of the members
     std::vector<double> rc_eff;  // per member
     // device storage
-    DevBuf<int> part, excl_off, excl_idx, cell_of_slot, cell_count, cell_start, cell_cursor, tmp_slots, sorted_slots,
+    DevBuf<int> part, excl_off, excl_idx, cell_of_slot, cell_count, cell_start, cell_cursor, scan_tmp, tmp_slots, sorted_slots,
         rank_of_bead, bead_of_rank, nbr_count, nbr_inner;
     DevBuf<uint4> spos;
     DevBuf<float> qscaled;
@@ -644,8 +644,9 @@ static void configure_grid(ocm_context* c, PairListHost& L) {
     L.cell_count.alloc(L.max_cells + 1); L.cell_count.zero();
     L.cell_start.alloc(L.max_cells + 1); L.cell_start.zero();
     L.cell_cursor.alloc(L.max_cells);
+    L.scan_tmp.alloc(L.max_cells / kScanChunk + 3);
     D.grid = L.grid.p; D.max_cells = L.max_cells;
-    D.cell_count = L.cell_count.p; D.cell_start = L.cell_start.p; D.cell_cursor = L.cell_cursor.p;
+    D.cell_count = L.cell_count.p; D.cell_start = L.cell_start.p; D.cell_cursor = L.cell_cursor.p; D.scan_tmp = L.scan_tmp.p;
 }
 
 static void upload_lists(ocm_context* c) {
@@ -1126,7 +1127,14 @@ static void enqueue_list_rebuild(ocm_context* c, PairListHost& L, int li, cudaSt
         grid_kernel<<<1, 1, 0, s>>>(c->d_lists.p, li);
         bin_kernel<false><<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li, c->posq.p);
     }
-    scan_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li);
+    if (c->periodic && c->nrep == 1 && L.max_cells > 4 * kScanChunk) {
+        // large grid (its size is known on the host for a periodic or virtual box): block-parallel scan
+        const int nb = (L.max_cells + kScanChunk - 1) / kScanChunk;
+        scan_blocks_kernel<<<nb, 1024, 0, s>>>(c->d_lists.p, li);
+        scan_tops_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li, nb);
+        scan_finish_kernel<<<nb, 1024, 0, s>>>(c->d_lists.p, li);
+        c->n_launches += 2;
+    } else scan_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li);
     scatter_kernel<<<nblk(L.np, 256), 256, 0, s>>>(c->d_lists.p, li);
     if (L.tiled) {
         // (the grids cover the rows the force launch covers: all of them, or the estimate of a slab decomposition)

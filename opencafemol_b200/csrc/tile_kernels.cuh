@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(kBuildBlock) tile_build_kernel(const PairListD
     __shared__ int s_warp_cnt[kBuildBlock / 32];
     __shared__ uint2 s_stage[kBuildBatch * 16];
     __shared__ int s_total;   // lane pairs' tiles of the row (sum of the i-cluster mask bits)
+    __shared__ uint4 s_cc[8];   // bounding boxes of the 8 i-clusters: centre (fixed point) ...
+    __shared__ float4 s_ch[8];  // ... and half extents (nm); .w < 0: no real bead
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 64) {
         const int k = S * 64 + threadIdx.x;
@@ -147,6 +149,29 @@ __global__ void __launch_bounds__(kBuildBlock) tile_build_kernel(const PairListD
         s_own[threadIdx.x] = own;
     }
     if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        // box of i-cluster threadIdx.x, relative to its first real bead (wrapped differences: a valid periodic interval)
+        int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, first = -1;
+        uint4 p0 = make_uint4(0u, 0u, 0u, 0u);
+        for (int t = 0; t < 8; t++) {
+            const int il = threadIdx.x * 8 + t;
+            if (s_info[il] < 0) continue;
+            const uint4 p = s_pos[il];
+            if (first < 0) { first = il; p0 = p; continue; }
+            const int d[3] = {(int)(p.x - p0.x), (int)(p.y - p0.y), (int)(p.z - p0.z)};
+            for (int q = 0; q < 3; q++) { lo[q] = min(lo[q], d[q]); hi[q] = max(hi[q], d[q]); }
+        }
+        const unsigned int base[3] = {p0.x, p0.y, p0.z};
+        unsigned int c[3];
+        float hf[3];
+        for (int q = 0; q < 3; q++) {
+            c[q] = base[q] + (unsigned int)(int)(((long long)lo[q] + (long long)hi[q]) >> 1);
+            hf[q] = ((float)(((long long)hi[q] - (long long)lo[q] + 3) >> 1)) * P.fscale[q] * 1.000001f;
+        }
+        s_cc[threadIdx.x] = make_uint4(c[0], c[1], c[2], 0u);
+        s_ch[threadIdx.x] = make_float4(hf[0], hf[1], hf[2], first < 0 ? -1.f : 0.f);
+    }
     __syncthreads();
     const uint4 cS = L.sc_center[S];
     const float4 hS = L.sc_half[S];
@@ -197,17 +222,23 @@ __global__ void __launch_bounds__(kBuildBlock) tile_build_kernel(const PairListD
                     const int bead_j = sbj & 0xFFFFFF;
                     const int cls_j = (real_j && L.cls) ? (int)L.cls[L.sorted_slots[kj]] : 0;
                     const bool own_j = real_j && (L.role ? (L.role[bead_j] == 1) : true);
-                    // quick rejection: distance of the j-bead from the box of S
+                    // quick rejection: lane (ti, tj) measures the j-bead tj against the box of i-CLUSTER ti; a cluster none of the
+                    // four j-beads comes near is skipped by the exact pass below
                     float qx, qy, qz;
-                    delta<PER>(cS, pj, P.fscale, qx, qy, qz);
-                    qx = fmaxf(0.f, fabsf(qx) - hS.x); qy = fmaxf(0.f, fabsf(qy) - hS.y); qz = fmaxf(0.f, fabsf(qz) - hS.z);
-                    const bool near = real_j && (qx * qx + qy * qy + qz * qz) < rl2 * 1.0001f;
-                    if (__any_sync(0xffffffffu, near)) {
+                    const float4 hC = s_ch[ti];
+                    delta<PER>(s_cc[ti], pj, P.fscale, qx, qy, qz);
+                    qx = fmaxf(0.f, fabsf(qx) - hC.x); qy = fmaxf(0.f, fabsf(qy) - hC.y); qz = fmaxf(0.f, fabsf(qz) - hC.z);
+                    const bool near = real_j && hC.w >= 0.f && (qx * qx + qy * qy + qz * qz) < rl2 * 1.0001f;
+                    const unsigned int nm = __ballot_sync(0xffffffffu, near);
+                    const unsigned int cnear = (nm | (nm >> 8) | (nm >> 16) | (nm >> 24)) & 0xffu;
+                    if (cnear) {
                         unsigned int act = 0;
                         bool partial = false;
                         unsigned int masks[8];
 #pragma unroll
                         for (int ci = 0; ci < 8; ci++) {
+                            masks[ci] = 0xffffffffu;
+                            if (!((cnear >> ci) & 1u)) continue;  // warp-uniform
                             const int il = ci * 8 + ti;
                             const uint4 pi = s_pos[il];
                             const int info = s_info[il];

@@ -331,13 +331,17 @@ def multi_gpu_records(lib, rank, world, local):
     ctx.step(200)
     phases = {k: ctx.counter("phase_ms." + k) / 200 for k in ("rebuild", "force", "integrate", "halo")}
     owned = sharding_gather([ctx.counter("owned_beads")], local)
+    all_phases = sharding_gather([phases[k] for k in ("rebuild", "force", "integrate", "halo")], local).reshape(world, 4)
+    evals = sharding_gather([ctx.counter("pair_evals_per_step")], local)   # (collective: every rank asks)
     if rank == 0:
         sN = 600 / dev
         out["c5"] = {"workload": "C5: C2 compacted state tiled 8 x 8, 1 043 200 beads, %d slabs along y" % world, "md_steps_per_s": sN,
                      "ns_per_day": ns_per_day(600, spec.dt, dev), "md_steps_per_s_one_gpu": one, "strong_scaling_efficiency": sN / one / world,
                      "nstlist": nst, "phase_ms_per_step_rank0": phases, "halo_message_bytes": ctx.counter("halo_message_bytes"),
                      "halo": "peer-memory push (CUDA IPC over NVLink)" if ctx.counter("halo_push") else "nccl send/recv",
-                     "pair_kernel": "tiles" if ctx.counter("tiled.1") else "rows", "owned_beads_per_rank": [int(v) for v in owned]}
+                     "pair_kernel": "tiles" if ctx.counter("tiled.1") else "rows", "owned_beads_per_rank": [int(v) for v in owned],
+                     "phase_ms_per_step_by_rank": {k: [round(float(v), 4) for v in all_phases[:, i]] for i, k in enumerate(("rebuild", "force", "integrate", "halo"))},
+                     "lane_pairs_evaluated_per_step_by_rank": [float(v) for v in evals]}
     dist.barrier()
     ctx.close()
     comm.close()

@@ -80,7 +80,7 @@ struct PairListDev {
     float mem_rc2[kMaxMembers];
     const float4* memE[kMaxMembers];  // [2*nt*nt] {c12_in,c6_in,c0_in,a2},{c12_out,c6_out,c0_out,0}
     // ---- cluster-pair ("tile") form of the list (tile_kernels.cuh); Verlet rows are not built when tiled != 0 ----
-    int tiled;
+    int tiled, halo_split;
     const int* cell_rank;       // [grid cells] Hilbert rank of each cell: tile lists sort their beads along the curve
     int* sbead;                 // [rows padded to 64] bead | type << 24 of rank k, -1 = padding
     float2* sparam;             // [rows padded] per-bead mixing parameters (inner, outer strength); spos.w carries a
@@ -91,7 +91,10 @@ struct PairListDev {
     float4* sc_half;            // [superclusters] half extents (nm)
     int tl_nsc, tl_stride;      // superclusters allocated; entries per supercluster row
     int* tl_count;              // [tl_nsc] entries in use
+    int* tl_count_in;           // [tl_nsc] leading entries that touch owned beads only (slab decomposition: they need no halo data)
+    int* tl_start_in;           // [tl_nsc + 1] prefix sums of the interior weights
     int* tl_weight;             // [tl_nsc] estimated work of the row (tile evaluations + overheads)
+    int* tl_weight_in;          // [tl_nsc] the same for the interior entries
     int* tl_start;              // [tl_nsc + 1] exclusive prefix sum of tl_weight (tile_scan_kernel)
     uint2* tl_entries;          // [tl_nsc * tl_stride] {j-group, i-cluster mask | mask block << 8}
     unsigned int* tl_masks;     // [tl_mask_cap * 8] lane masks of the entries that need them (block index is 1-based)
@@ -156,7 +159,12 @@ struct StepParams {
 };
 
 // rows (ranks of the cell-sorted order) in use: under a slab decomposition only the beads present on this rank are binned
-__device__ __forceinline__ int list_rows(const PairListDev& L) { return L.role ? L.cell_start[L.grid->ncell * L.nrep] : L.np; }
+// number of sort keys: one per cell (per replica); slab-decomposed tile lists keep two copies of the grid, owned beads in the
+// first and halo beads in the second, so that the halo beads come last in the sorted order (halo_split)
+__device__ __forceinline__ int list_nkeys(const PairListDev& L) { return L.grid->ncell * L.nrep * (1 + L.halo_split); }
+__device__ __forceinline__ int list_rows(const PairListDev& L) { return L.role ? L.cell_start[list_nkeys(L)] : L.np; }
+// rows of owned beads (they come first when halo_split is set)
+__device__ __forceinline__ int list_rows_owned(const PairListDev& L) { return L.halo_split ? L.cell_start[L.grid->ncell * L.nrep] : list_rows(L); }
 __device__ __forceinline__ int bonded_nbody_dev(int kind) { return kind <= 3 ? 2 : ((kind <= 5 || kind == 9) ? 3 : 4); }
 
 // ------------------------------------------------------------------------------------------------
@@ -351,6 +359,7 @@ __global__ void bin_kernel(const PairListDev* lists, int li, const uint4* __rest
     int c = (cz * g.nc[1] + cy) * g.nc[0] + cx;
     if (L.cell_rank) c = L.cell_rank[c];  // tile lists: cells are keyed by their rank along the Hilbert curve
     if (L.nrep > 1) c += (bead / L.nper) * g.ncell;
+    if (L.halo_split && L.role[bead] == 2) c += g.ncell;
     L.cell_of_slot[a] = c;
     atomicAdd(&L.cell_count[c], 1);
 }
@@ -360,7 +369,7 @@ __global__ void bin_kernel(const PairListDev* lists, int li, const uint4* __rest
 constexpr int kScanItems = 8;
 __global__ void scan_kernel(const PairListDev* lists, int li) {
     const PairListDev& L = lists[li];
-    const int ncell = L.grid->ncell * L.nrep;
+    const int ncell = list_nkeys(L);
     __shared__ int warp_sums[32];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
@@ -408,7 +417,7 @@ __global__ void scan_kernel(const PairListDev* lists, int li) {
 constexpr int kScanChunk = 1024 * kScanItems;
 __global__ void __launch_bounds__(1024) scan_blocks_kernel(const PairListDev* lists, int li) {
     const PairListDev& L = lists[li];
-    const int ncell = L.grid->ncell * L.nrep;
+    const int ncell = list_nkeys(L);
     __shared__ int warp_sums[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int i0 = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
@@ -457,7 +466,7 @@ __global__ void __launch_bounds__(1024) scan_tops_kernel(const PairListDev* list
 }
 __global__ void __launch_bounds__(1024) scan_finish_kernel(const PairListDev* lists, int li) {
     const PairListDev& L = lists[li];
-    const int ncell = L.grid->ncell * L.nrep;
+    const int ncell = list_nkeys(L);
     const int off = L.scan_tmp[blockIdx.x];
     const int i0 = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
 #pragma unroll

@@ -95,7 +95,9 @@ struct PairListHost {
     float cell_width = 0.f;  // width the grid was derived from (before any widening), reported for the oracle
     long long cell_cap = -1; // cap on the number of cells that widened them (-1: none)
     std::vector<int> cell_inv;  // Hilbert rank -> linear cell id
-    DevBuf<int> cell_rank, sbead, tl_count, tl_weight, tl_start, tl_mask_count;
+    DevBuf<int> cell_rank, sbead, tl_count, tl_weight, tl_start, tl_count_in, tl_weight_in, tl_start_in, tl_mask_count;
+    TileLaunch launch_in{};  // slab decomposition: the launch over the interior entries (no halo data needed)
+    int tile_nblocks_in = 0;
     TileLaunch launch{};     // by-value description of the list's force launch
     int tile_nblocks = 0;
     DevBuf<float2> sparam, slot_b;
@@ -218,7 +220,8 @@ struct ocm_context {
     int total_blocks = 0, pair_blocks = 0, local_blocks = 0, n_pair_segs = 0, n_local_segs = 0;
     size_t smem_bytes = 0;
     cudaStream_t side = nullptr;            // forked branch: bonded + donor-acceptor kernel beside the pair kernel
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_halo_go = nullptr, ev_halo_done = nullptr;
+    bool halo_overlap = true;               // option "halo_overlap": interior tile entries run while the halo positions travel
 
     // options
     double skin = 0.3;
@@ -256,6 +259,8 @@ struct ocm_context {
         for (int b = 0; b < 2; b++) { if (ev_obs_done[b]) cudaEventDestroy(ev_obs_done[b]); if (obs_pin[b]) cudaFreeHost(obs_pin[b]); }
         if (ev_in_free) cudaEventDestroy(ev_in_free);
         if (in_pin) cudaFreeHost(in_pin);
+        if (ev_halo_go) cudaEventDestroy(ev_halo_go);
+        if (ev_halo_done) cudaEventDestroy(ev_halo_done);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         if (side) cudaStreamDestroy(side);
@@ -436,9 +441,10 @@ static void compile_tile_tables(ocm_context* c, PairListHost& L) {
     L.sparam.alloc(L.np_pad); L.sparam.zero();
     L.saux.alloc(L.np_pad); L.saux.zero();
     L.sc_center.alloc(L.tl_nsc); L.sc_half.alloc(L.tl_nsc); L.tl_count.alloc(L.tl_nsc); L.tl_count.zero(); L.tl_start.alloc(L.tl_nsc + 1); L.tl_start.zero(); L.tl_weight.alloc(L.tl_nsc); L.tl_weight.zero();
+    L.tl_count_in.alloc(L.tl_nsc); L.tl_count_in.zero(); L.tl_weight_in.alloc(L.tl_nsc); L.tl_weight_in.zero(); L.tl_start_in.alloc(L.tl_nsc + 1); L.tl_start_in.zero();
     L.tl_mask_count.alloc(1); L.tl_mask_count.zero();
     D.spos = L.spos.p; D.sbead = L.sbead.p; D.sparam = L.sparam.p; D.saux = L.saux.p; D.sc_center = L.sc_center.p; D.sc_half = L.sc_half.p;
-    D.tl_nsc = L.tl_nsc; D.tl_count = L.tl_count.p; D.tl_start = L.tl_start.p; D.tl_weight = L.tl_weight.p; D.tl_mask_count = L.tl_mask_count.p;
+    D.tl_nsc = L.tl_nsc; D.tl_count = L.tl_count.p; D.tl_start = L.tl_start.p; D.tl_weight = L.tl_weight.p; D.tl_count_in = L.tl_count_in.p; D.tl_weight_in = L.tl_weight_in.p; D.tl_start_in = L.tl_start_in.p; D.tl_mask_count = L.tl_mask_count.p;
 }
 
 static void compile_list(ocm_context* c, PairListHost& L) {
@@ -615,7 +621,9 @@ static void configure_grid(ocm_context* c, PairListHost& L) {
         if (tot > (1ll << 26)) throw std::runtime_error("cell grid too large");
         g.ncell = (int)tot;
         g.inv_w = 1.0f / D.wmin;
-        L.max_cells = g.ncell;
+        // (slab-decomposed tile lists sort halo beads behind the owned ones: two copies of the key range)
+        D.halo_split = (L.tiled && c->dd) ? 1 : 0;
+        L.max_cells = g.ncell * (1 + D.halo_split);
         if (L.tiled && (L.grid_dims[0] != g.nc[0] || L.grid_dims[1] != g.nc[1] || L.grid_dims[2] != g.nc[2] || !L.cell_rank.p)) {
             // rank of every cell along the Hilbert curve through the enclosing power-of-two cube
             int bits = 1;
@@ -691,6 +699,15 @@ static void build_segments(ocm_context* c) {
             ts.entries = L.tl_entries.p; ts.count = L.tl_count.p; ts.spos = L.spos.p; ts.saux = L.saux.p; ts.masks = L.tl_masks.p; ts.sc_center = L.sc_center.p;
             ts.rc2 = L.dev.rc2; ts.alpha = L.dev.t_alpha; ts.beta = L.dev.t_beta; ts.qz = L.dev.t_qz; ts.inv_sw = L.dev.inv_sw;
             ts.sw_c0 = L.dev.rsw * L.dev.inv_sw; ts.sw_c1 = 30.f * L.dev.inv_sw * L.dev.t_kappa; ts.inv_debye = L.dev.inv_debye;
+            ts.count_lo = nullptr;
+            L.tile_nblocks_in = 0;
+            if (L.dev.halo_split) {
+                // two launches per step: the interior entries [0, count_in) while the halo positions travel, then the rest
+                L.launch_in = T;
+                L.launch_in.seg.count = L.tl_count_in.p; L.launch_in.seg.count_lo = nullptr; L.launch_in.seg.start = L.tl_start_in.p;
+                L.tile_nblocks_in = ts.nblocks;
+                ts.count_lo = L.tl_count_in.p;
+            }
             tblk += L.tile_nblocks;
             continue;
         }
@@ -1146,7 +1163,10 @@ static void enqueue_list_rebuild(ocm_context* c, PairListHost& L, int li, cudaSt
         tile_build_kernel<true><<<nsc, kBuildBlock, 0, s>>>(c->d_lists.p, li, c->P, c->flags.p, count_only ? 1 : 0);
         if (L.dev.n_excl_pairs > 0)
             tile_excl_kernel<<<nblk(L.dev.n_excl_pairs, 256), 256, 0, s>>>(c->d_lists.p, li, c->flags.p, count_only ? 1 : 0);
-        if (!count_only) tile_scan_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li, nsc);
+        if (!count_only) {
+            tile_scan_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li, nsc, 0);
+            if (L.dev.halo_split) tile_scan_kernel<<<1, 1024, 0, s>>>(c->d_lists.p, li, nsc, 1);
+        }
         c->n_launches += 9;
         return;
     }
@@ -1191,8 +1211,24 @@ static void launch_chained(ocm_context* c, void (*kernel)(KArgs...), int grid, i
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
 }
 
-static void enqueue_forces(ocm_context* c, cudaStream_t s) {
+static void launch_tile(ocm_context* c, PairListHost& L, const TileLaunch& T, int nblocks, cudaStream_t s) {
+    // one launch per tile list; the pair form is a template parameter, the list's constants ride in the kernel parameters
+    if (L.form == SEG_PAIR_DH) launch_chained(c, tile_force_kernel<SEG_PAIR_DH, false, false>, nblocks, kTileBlock, 0, s, T, c->fbuf.p);
+    else if (L.t_switch && !(c->tile_debug & 4)) launch_chained(c, tile_force_kernel<SEG_PAIR_TZ, true, false>, nblocks, kTileBlock, 0, s, T, c->fbuf.p);
+    else if (L.dev.t_geo) launch_chained(c, tile_force_kernel<SEG_PAIR_TZ, false, true>, nblocks, kTileBlock, 0, s, T, c->fbuf.p);
+    else launch_chained(c, tile_force_kernel<SEG_PAIR_TZ, false, false>, nblocks, kTileBlock, 0, s, T, c->fbuf.p);
+    c->n_launches += 1;
+}
+
+// phase 0: all forces.  Slab decomposition with split tile lists: phase 1 = the interior tile entries only (owned beads on
+// both sides: they can run while the step's halo positions are still travelling), phase 2 = everything else.
+static void enqueue_forces(ocm_context* c, cudaStream_t s, int phase = 0) {
     if (c->total_blocks == 0 && c->tile_blocks == 0) return;
+    if (phase == 1) {
+        for (auto& Lp : c->lists)
+            if (Lp->tiled && Lp->np && Lp->tile_nblocks_in > 0) launch_tile(c, *Lp, Lp->launch_in, Lp->tile_nblocks_in, s);
+        return;
+    }
     const bool fork = c->local_blocks > 0 && c->pair_blocks > 0;
     if (c->local_blocks > 0) {
         cudaStream_t sl = s;
@@ -1208,12 +1244,8 @@ static void enqueue_forces(ocm_context* c, cudaStream_t s) {
     for (auto& Lp : c->lists) {
         PairListHost& L = *Lp;
         if (!L.tiled || L.np == 0) continue;
-        // one launch per tile list; the pair form is a template parameter, the list's constants ride in the kernel parameters
-        if (L.form == SEG_PAIR_DH) launch_chained(c, tile_force_kernel<SEG_PAIR_DH, false, false>, L.tile_nblocks, kTileBlock, 0, s, L.launch, c->fbuf.p);
-        else if (L.t_switch && !(c->tile_debug & 4)) launch_chained(c, tile_force_kernel<SEG_PAIR_TZ, true, false>, L.tile_nblocks, kTileBlock, 0, s, L.launch, c->fbuf.p);
-        else if (L.dev.t_geo) launch_chained(c, tile_force_kernel<SEG_PAIR_TZ, false, true>, L.tile_nblocks, kTileBlock, 0, s, L.launch, c->fbuf.p);
-        else launch_chained(c, tile_force_kernel<SEG_PAIR_TZ, false, false>, L.tile_nblocks, kTileBlock, 0, s, L.launch, c->fbuf.p);
-        c->n_launches += 1;
+        if (phase == 0 && L.tile_nblocks_in > 0) launch_tile(c, L, L.launch_in, L.tile_nblocks_in, s);
+        launch_tile(c, L, L.launch, L.tile_nblocks, s);
     }
     if (c->pair_blocks > 0) {
         // (not chained when the donor-acceptor kernel runs on the forked side stream: the join is an event wait)
@@ -1374,14 +1406,34 @@ static void enqueue_window(ocm_context* c, cudaStream_t s, int nst) {
     phase_mark(c, s, -1);
     enqueue_rebuild(c, s, false);
     phase_mark(c, s, 0);
+    // slab decomposition with split tile lists and the peer-memory halo: the halo positions of a step travel on the side stream
+    // while the interior tile entries (owned beads only) are already evaluated on the compute stream
+    bool overlap = false;
+    if (c->dd && c->dd->push_ok && c->halo_overlap) for (auto& L : c->lists) overlap = overlap || (L->tiled && L->np && L->tile_nblocks_in > 0);
+    bool interior_done = false;
     for (int k = 0; k < nst; k++) {
-        enqueue_forces(c, s);
+        if (interior_done) {
+            CUDA_TRY(cudaStreamWaitEvent(s, c->ev_halo_done, 0));
+            phase_mark(c, s, 3);
+            enqueue_forces(c, s, 2);
+        } else enqueue_forces(c, s, 0);
+        interior_done = false;
         phase_mark(c, s, 1);
         launch_chained(c, integrate_kernel, nblk(c->n, 128), 128, 0, s, c->P, c->x.p, c->v.p, c->fbuf.p, c->posq.p, c->d_lists.p, (int)c->lists.size(), c->xref.p,
                        c->step_base.p, k, nst, k == nst - 1 ? 1 : 0, c->flags.p);
         phase_mark(c, s, 2);
         // the next window starts with a full halo refresh, so the last step of a window ships nothing
-        if (c->dd && k < nst - 1) { dd_halo_step(c, s); phase_mark(c, s, 3); }
+        if (c->dd && k < nst - 1) {
+            if (overlap) {
+                CUDA_TRY(cudaEventRecord(c->ev_halo_go, s));
+                CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_halo_go, 0));
+                dd_halo_step(c, c->side);
+                CUDA_TRY(cudaEventRecord(c->ev_halo_done, c->side));
+                enqueue_forces(c, s, 1);
+                phase_mark(c, s, 1);
+                interior_done = true;
+            } else { dd_halo_step(c, s); phase_mark(c, s, 3); }
+        }
     }
 }
 
@@ -1825,6 +1877,8 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_obs, cudaEventDisableTiming));
     for (int b = 0; b < 2; b++) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_obs_done[b], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_in_free, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_halo_go, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_halo_done, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     const int n = c->n;
@@ -1982,6 +2036,8 @@ int ocm_context_set_option(ocm_context* c, const char* key, double value) {
     } else if (k == "phase_timing") {
         c->phase_timing = value != 0;
         for (double& v : c->ph_ms) v = 0;
+    } else if (k == "halo_overlap") {
+        c->halo_overlap = value != 0;
     } else if (k == "halo_push") {
         // per-step halo over peer memory (1, default where the transport can map neighbours) or NCCL send/recv (0); collective
         if (!c->dd) return fail("halo_push: not a slab context");

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kBuildBlock) tile_build_kernel(const PairListD
     const int rows = list_rows(L);
     if (S == 0 && threadIdx.x == 0 && !count_only && rows > L.row_capacity) flags[FLAG_OVERFLOW] = 1;
     if (S * 64 >= rows) {
-        if (threadIdx.x == 0 && S < L.tl_nsc) { L.tl_count[S] = 0; L.tl_weight[S] = 0; }
+        if (threadIdx.x == 0 && S < L.tl_nsc) { L.tl_count[S] = 0; L.tl_weight[S] = 0; L.tl_count_in[S] = 0; L.tl_weight_in[S] = 0; }
         return;
     }
     const int nsc = (rows + 63) >> 6;
@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kBuildBlock) tile_build_kernel(const PairListD
     __shared__ int s_warp_cnt[kBuildBlock / 32];
     __shared__ uint2 s_stage[kBuildBatch * 16];
     __shared__ int s_total;   // lane pairs' tiles of the row (sum of the i-cluster mask bits)
+    __shared__ int s_total_in, s_count_in;   // the same and the entry count for the interior entries (owned beads only)
     __shared__ uint4 s_cc[8];   // bounding boxes of the 8 i-clusters: centre (fixed point) ...
     __shared__ float4 s_ch[8];  // ... and half extents (nm); .w < 0: no real bead
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -148,7 +149,12 @@ __global__ void __launch_bounds__(kBuildBlock) tile_build_kernel(const PairListD
         s_info[threadIdx.x] = info;
         s_own[threadIdx.x] = own;
     }
-    if (threadIdx.x == 0) s_total = 0;
+    if (threadIdx.x == 0) { s_total = 0; s_total_in = 0; s_count_in = 0; }
+    // slab decomposition with halo beads sorted last: a row of owned beads only, and its entries on j-groups of owned beads only,
+    // can be evaluated before the step's halo positions have arrived (entries are ordered by j-group: they form a prefix)
+    const int rows_owned = list_rows_owned(L);
+    const bool interior_S = (S + 1) * 64 <= rows_owned;
+    const int j4_owned = rows_owned >> 2;
     __syncthreads();
     if (threadIdx.x < 8) {
         // box of i-cluster threadIdx.x, relative to its first real bead (wrapped differences: a valid periodic interval)
@@ -288,6 +294,7 @@ __global__ void __launch_bounds__(kBuildBlock) tile_build_kernel(const PairListD
                     const int pos = n_out + off + __popc(hb & ((1u << lane) - 1u));
                     if (pos < stride) out[pos] = e;
                     atomicAdd(&s_total, __popc(e.y & 0xffu));
+                    if (interior_S && (int)e.x < j4_owned) { atomicAdd(&s_total_in, __popc(e.y & 0xffu)); atomicAdd(&s_count_in, 1); }
                 }
                 n_out += tot;
             }
@@ -299,8 +306,12 @@ __global__ void __launch_bounds__(kBuildBlock) tile_build_kernel(const PairListD
         else {
             if (n_out > stride) { flags[FLAG_OVERFLOW] = 1; n_out = stride; }
             L.tl_count[S] = n_out;
-            // work estimate of the row in units of one tile evaluation: tiles + entry overheads + the per-row prologue / epilogue
-            L.tl_weight[S] = n_out ? s_total + n_out + 8 : 0;
+            // work estimate of the row in units of one tile evaluation: tiles + entry overheads + the per-row prologue / epilogue;
+            // tl_weight is what the launch over entries [count_in, count) does, tl_weight_in the launch over [0, count_in)
+            const int n_in = L.halo_split ? min(s_count_in, n_out) : 0, t_in = L.halo_split ? s_total_in : 0;
+            L.tl_count_in[S] = n_in;
+            L.tl_weight_in[S] = n_in ? t_in + n_in + 8 : 0;
+            L.tl_weight[S] = (n_out - n_in) ? (s_total - t_in) + (n_out - n_in) + 8 : 0;
         }
     }
 }
@@ -341,8 +352,10 @@ __global__ void tile_excl_kernel(const PairListDev* lists, int li, int* __restri
 
 // exclusive prefix sum of the row weights (tl_weight: estimated work of a row): the force launch cuts the concatenated
 // entry stream into shares of equal weight, one per block.  tl_start[nsc] = total.  Single block.
-__global__ void tile_scan_kernel(const PairListDev* lists, int li, int nsc) {
+__global__ void tile_scan_kernel(const PairListDev* lists, int li, int nsc, int interior) {
     const PairListDev& L = lists[li];
+    const int* __restrict__ weight = interior ? L.tl_weight_in : L.tl_weight;
+    int* __restrict__ start = interior ? L.tl_start_in : L.tl_start;
     __shared__ int warp_sums[32];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
@@ -350,7 +363,7 @@ __global__ void tile_scan_kernel(const PairListDev* lists, int li, int nsc) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int base = 0; base < nsc; base += blockDim.x) {
         const int i = base + threadIdx.x;
-        const int v = (i < nsc) ? L.tl_weight[i] : 0;
+        const int v = (i < nsc) ? weight[i] : 0;
         int s = v;
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
         if (lane == 31) warp_sums[wid] = s;
@@ -361,12 +374,12 @@ __global__ void tile_scan_kernel(const PairListDev* lists, int li, int nsc) {
             warp_sums[lane] = ws;
         }
         __syncthreads();
-        if (i < nsc) L.tl_start[i] = carry + (wid > 0 ? warp_sums[wid - 1] : 0) + s - v;
+        if (i < nsc) start[i] = carry + (wid > 0 ? warp_sums[wid - 1] : 0) + s - v;
         __syncthreads();
         if (threadIdx.x == 0) carry += warp_sums[nw - 1];
         __syncthreads();
     }
-    if (threadIdx.x == 0) L.tl_start[nsc] = carry;
+    if (threadIdx.x == 0) start[nsc] = carry;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -419,7 +432,7 @@ __device__ __forceinline__ float tile_pair_dh(const TileForm& F, float r2, float
 // operand, no dependent global loads before the first useful instruction and no registers spent on per-list constants.
 struct TileSegP {
     int nblocks, nsc, stride, pad;
-    const uint2* entries; const int* count; const int* start; const uint4* spos; const uint4* saux; const unsigned int* masks; const uint4* sc_center;
+    const uint2* entries; const int* count; const int* count_lo; const int* start; const uint4* spos; const uint4* saux; const unsigned int* masks; const uint4* sc_center;
     float rc2, alpha, beta, qz, inv_sw, sw_c0, sw_c1, inv_debye;
 };
 struct TileLaunch {
@@ -711,12 +724,15 @@ __global__ void __launch_bounds__(kTileBlock, OCM_TILE_MINBLOCKS) tile_force_ker
         const int w0 = start[S], w1 = start[S + 1];
         if (w0 >= t1) break;
         if (w1 == w0) continue;
-        const int cnt = G.count[S];
+        // the launch covers the entries [lo, hi) of the row: all of them, or (slab decomposition) the interior prefix in one
+        // launch and the rest in another
+        const int lo_e = G.count_lo ? G.count_lo[S] : 0, hi_e = G.count[S];
+        const int cnt = hi_e - lo_e;
         // entry range of this block inside the row (multiples of 4: one entry per warp and pass); both neighbours of a cut use
         // the same formula, so the shares tile the row exactly
         const int e_begin = (t0 <= w0) ? 0 : (int)(((long long)(t0 - w0) * cnt / (w1 - w0)) & ~3ll);
         const int e_end = (t1 >= w1) ? cnt : (int)(((long long)(t1 - w0) * cnt / (w1 - w0)) & ~3ll);
-        if (e_begin < e_end) tile_chunk<FORM, SW, GEO>(T, S, e_begin, e_end, fbuf, sh);
+        if (e_begin < e_end) tile_chunk<FORM, SW, GEO>(T, S, lo_e + e_begin, lo_e + e_end, fbuf, sh);
     }
 }
 

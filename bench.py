@@ -329,6 +329,7 @@ def multi_gpu_records(lib, rank, world, local):
     nst = ctx.counter("nstlist")
     ctx.set_option("phase_timing", 1)
     ctx.step(200)
+    phase_run_ms = ctx.counter("last_step_ms") / 200
     phases = {k: ctx.counter("phase_ms." + k) / 200 for k in ("rebuild", "force", "integrate", "halo")}
     owned = sharding_gather([ctx.counter("owned_beads")], local)
     all_phases = sharding_gather([phases[k] for k in ("rebuild", "force", "integrate", "halo")], local).reshape(world, 4)
@@ -337,7 +338,9 @@ def multi_gpu_records(lib, rank, world, local):
         sN = 600 / dev
         out["c5"] = {"workload": "C5: C2 compacted state tiled 8 x 8, 1 043 200 beads, %d slabs along y" % world, "md_steps_per_s": sN,
                      "ns_per_day": ns_per_day(600, spec.dt, dev), "md_steps_per_s_one_gpu": one, "strong_scaling_efficiency": sN / one / world,
-                     "nstlist": nst, "phase_ms_per_step_rank0": phases, "halo_message_bytes": ctx.counter("halo_message_bytes"),
+                     "nstlist": nst, "phase_ms_per_step_rank0": phases, "phase_run_ms_per_step_rank0": phase_run_ms,
+                     "phase_note": "phases are CUDA-event intervals on rank 0's compute stream in a separate 200-step run; 'halo' is the stall at the "
+                                   "join with the side stream that carries the halo positions, 'force' includes the interior launch that overlaps them", "halo_message_bytes": ctx.counter("halo_message_bytes"),
                      "halo": "peer-memory push (CUDA IPC over NVLink)" if ctx.counter("halo_push") else "nccl send/recv",
                      "pair_kernel": "tiles" if ctx.counter("tiled.1") else "rows", "owned_beads_per_rank": [int(v) for v in owned],
                      "phase_ms_per_step_by_rank": {k: [round(float(v), 4) for v in all_phases[:, i]] for i, k in enumerate(("rebuild", "force", "integrate", "halo"))},

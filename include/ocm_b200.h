@@ -240,10 +240,15 @@ int  ocm_get_roles(ocm_context*, unsigned char* role);
 
 /* tunables (set_option / get_option):
  *   "skin_nm" (Verlet buffer), "nstlist" (0 = adaptive), "threads_per_bead" (0 = auto, 4/8/16/32),
- *   "beads_per_block" (rows per force block, 0 = auto ~ sqrt(rows)/12), "row_staging" (bulk-copy row staging, off),
+ *   "beads_per_block" (rows per force block, 0 = auto ~ sqrt(rows)/12),
+ *   "pair_kernel" (-1 = by size (default): cluster-pair tile lists for pair lists of >= 131 072 beads, Verlet rows below;
+ *                  1 = tiles wherever possible (periodic or virtual box, single system, >= 1024 beads in the list); 0 = rows),
+ *   "tile_blocks" (blocks of the persistent tile force launch per list, 0 = one wave),
+ *   "replica_kernel" (1 = whole-step persistent kernel for small unlimited-boundary systems / replica batches; 0 default),
  *   "pdl" (programmatic dependent launch of the per-step kernels: 0 off, 1, 2; no gain inside CUDA graphs),
  *   "phase_timing" (CUDA events between the phases of a step; counters "phase_ms.rebuild|force|integrate|halo"),
- *   slab contexts: "halo_capacity", "halo_push" (1 = per-step halo over NVLink peer memory, 0 = ncclSend/ncclRecv). */
+ *   slab contexts: "halo_capacity", "halo_push" (1 = per-step halo over NVLink peer memory, 0 = ncclSend/ncclRecv),
+ *                  "halo_overlap" (1 default: interior tile entries run while the halo positions travel on a side stream). */
 int ocm_context_set_option(ocm_context*, const char* key, double value);
 int ocm_context_get_option(ocm_context*, const char* key, double* value);
 

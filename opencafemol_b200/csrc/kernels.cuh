@@ -137,7 +137,7 @@ struct DAListDev {
 
 struct WorkSeg {
     int block_begin, nblocks, kind, id, tpb, chunk;  // pair segments: tpb threads per bead, chunk beads per block
-    int staged;                                       // rows staged in shared memory by bulk async copies (tpb == 32)
+    int staged;                                       // unused (the bulk-copy row staging experiment of round 1 was removed)
 };
 
 struct StepParams {
@@ -201,30 +201,6 @@ __device__ __forceinline__ float fast_rsqrt(float x) {
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
-}
-
-// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP): a whole Verlet row global -> shared -------
-__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
-    unsigned int done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
 }
 
 // programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
@@ -820,79 +796,6 @@ __device__ __forceinline__ void tz_pair_inner(const float4 c, float r2, float dx
     fx = fmaf(fr, dx, fx); fy = fmaf(fr, dy, fy); fz = fmaf(fr, dz, fz);
 }
 
-// T = 32 path with the row staged in shared memory: one lane issues a 1-D bulk async copy (TMA engine) of the
-// NEXT bead's whole row while the warp works on the current one, so the L2 latency of the row stream never
-// sits on the critical path; inside a row, four gathers + four table look-ups are in flight per lane.
-template <bool PER, bool SW>
-__device__ __forceinline__ void pair_tz_rows_staged(const PairListDev& L, int k_lo, int k_hi, const StepParams& P,
-                                                    unsigned long long* __restrict__ fbuf, const float4* tab,
-                                                    unsigned int* rowbuf, unsigned long long* bars) {
-    constexpr int G = kBlock / 32;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint4* __restrict__ spos = L.spos;
-    const int nt = L.ntypes, stride = L.stride;
-    const float rc2 = L.rc2, rsw = L.rsw, inv_sw = L.inv_sw, rsw2 = rsw * rsw;
-    const float kin = L.k_in;
-    unsigned int* buf = rowbuf + (size_t)warp * 2 * stride;
-    unsigned long long* bar = bars + warp * 2;
-    int k = k_lo + warp;
-    if (k >= k_hi) return;
-    int n_cur = L.nbr_count[k];
-    int n_next = (k + G < k_hi) ? L.nbr_count[k + G] : 0;
-    if (lane == 0) {
-        const unsigned int bytes = (unsigned int)((n_cur + 31) & ~31) << 2;
-        if (bytes) { mbar_expect_tx(&bar[0], bytes); bulk_copy_g2s(buf, L.nbr + (size_t)k * stride, bytes, &bar[0]); }
-    }
-    for (int it = 0; k < k_hi; k += G, it++) {
-        const int b = it & 1;
-        const int n = n_cur;
-        __syncwarp();  // every lane is done reading buffer b^1 (previous bead)
-        if (lane == 0 && k + G < k_hi) {
-            const unsigned int bytes = (unsigned int)((n_next + 31) & ~31) << 2;
-            if (bytes) { mbar_expect_tx(&bar[b ^ 1], bytes); bulk_copy_g2s(buf + (size_t)(b ^ 1) * stride, L.nbr + (size_t)(k + G) * stride, bytes, &bar[b ^ 1]); }
-        }
-        n_cur = n_next;
-        n_next = (k + 2 * G < k_hi) ? L.nbr_count[k + 2 * G] : 0;
-        const uint4 pi = spos[k];
-        const int trow = (int)(pi.w >> 24) * nt;
-        float fx = 0.f, fy = 0.f, fz = 0.f;
-        if (n > 0) {
-            // buffer b completes its (it>>1)-th phase
-            mbar_wait(&bar[b], (unsigned int)(it >> 1) & 1u);
-            const unsigned int* row = buf + (size_t)b * stride;
-            const unsigned int self = (unsigned int)k | (pi.w & 0xFF000000u);  // rows are padded to 32 with the self entry (r2 = 0)
-            for (int t0 = 0; t0 < n; t0 += 128) {
-                unsigned int e[4];
-                uint4 pj[4];
-                float4 c[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) e[u] = (t0 + u * 32 < n) ? row[t0 + u * 32 + lane] : self;
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    pj[u] = __ldg(&spos[(int)(e[u] & 0xFFFFFFu)]);
-                    c[u] = tab[trow + (int)(e[u] >> 24)];
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (t0 + u * 32 >= n) break;  // warp-uniform
-                    float dx, dy, dz;
-                    delta<PER>(pi, pj[u], P.fscale, dx, dy, dz);
-                    const float r2 = norm2(dx, dy, dz);
-                    const bool in = (r2 < rc2) && (r2 > 0.f);
-                    tz_pair<SW>(c[u], r2, in, dx, dy, dz, kin, rsw, rsw2, inv_sw, fx, fy, fz);
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            fx += __shfl_xor_sync(0xffffffffu, fx, o);
-            fy += __shfl_xor_sync(0xffffffffu, fy, o);
-            fz += __shfl_xor_sync(0xffffffffu, fz, o);
-        }
-        if (lane == 0) add_force_fixed(fbuf, P.n, (int)(pi.w & 0xFFFFFFu), fx, fy, fz);
-    }
-}
-
 // T = 32 path, rows streamed from global memory with register double-buffering: the next four row entries
 // (and the first four of the next bead's row) are requested before the current four pairs are evaluated, so the
 // row stream's L2 latency overlaps arithmetic; four gathers + four table look-ups are in flight per lane.
@@ -978,23 +881,6 @@ __device__ __forceinline__ void pair_tz_rows_warp(const PairListDev& L, int k_lo
         n_in = n_in_next;
         row = row_next;
     }
-}
-
-template <bool PER>
-__device__ __forceinline__ void pair_tz_block_staged(const PairListDev& L, int blk, int chunk, const StepParams& P,
-                                                     unsigned long long* __restrict__ fbuf, float* smem) {
-    // dynamic shared memory: [barriers: 2 per warp][coefficient table nt^2 float4][row buffers: 2 x stride per warp]
-    const int nt2 = L.ntypes * L.ntypes;
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);
-    float4* sF = reinterpret_cast<float4*>(smem + 2 * 2 * (kBlock / 32));
-    unsigned int* rowbuf = reinterpret_cast<unsigned int*>(sF + nt2);
-    if (threadIdx.x < 2 * (kBlock / 32)) mbar_init(&bars[threadIdx.x], 1);
-    for (int k = threadIdx.x; k < nt2; k += kBlock) sF[k] = L.tabF[k];
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    const int k_lo = blk * chunk, k_hi = min(list_rows(L), k_lo + chunk);
-    if (L.has_switch) pair_tz_rows_staged<PER, true>(L, k_lo, k_hi, P, fbuf, sF, rowbuf, bars);
-    else pair_tz_rows_staged<PER, false>(L, k_lo, k_hi, P, fbuf, sF, rowbuf, bars);
 }
 
 template <bool PER, int T>
@@ -1462,7 +1348,6 @@ __global__ void __launch_bounds__(kBlock, OCM_FORCE_MINBLOCKS) force_kernel(cons
     const int blk = blockIdx.x - sg.block_begin;
     if (sg.kind == SEG_PAIR_TZ) {
         const PairListDev& L = lists[sg.id];
-        if (sg.staged) { pair_tz_block_staged<PER>(L, blk, sg.chunk, P, fbuf, smem); return; }
         // (under a slab decomposition the grid covers L.row_capacity rows, the rows in use at the last sizing pass plus
         // head-room; build_list_kernel raises the overflow flag, i.e. a re-sizing pass, if more rows ever exist)
         switch (sg.tpb) {

@@ -57,7 +57,10 @@ struct DevBuf {
         n = count;
         if (count) CUDA_TRY(cudaMalloc(&p, count * sizeof(T)));
     }
-    void zero(cudaStream_t s = 0) { if (n) CUDA_TRY(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    // synchronous (the engine's kernels run on a non-blocking stream, which does not order with the legacy stream: an
+    // asynchronous memset there could race with them); zero_async takes the stream that will use the buffer
+    void zero() { if (n) CUDA_TRY(cudaMemset(p, 0, n * sizeof(T))); }
+    void zero_async(cudaStream_t s) { if (n) CUDA_TRY(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
     void upload(const std::vector<T>& h) {
         alloc(h.size());
         if (n) CUDA_TRY(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
@@ -243,7 +246,6 @@ struct ocm_context {
     int nst = 10;
     int tpb_opt = 0;         // 0 = auto
     int chunk_opt = 0;       // beads per block of the pair kernels, 0 = auto
-    int staging_opt = 0;     // stage Verlet rows in shared memory with bulk async copies
     bool lists_ready = false, positions_set = false, lists_current = false;
     bool last_disp2_ok = false;  // every window of the last batch ended with all beads inside their Verlet buffer
     std::map<int, cudaGraphExec_t> graphs;
@@ -728,14 +730,10 @@ static void build_segments(ocm_context* c) {
         // overflow flag in build_list_kernel and the lists are sized again)
         int nb = ((c->dd ? std::min(L.np, (int)(1.25 * rows) + chunk) : L.np) + chunk - 1) / chunk;
         L.dev.row_capacity = c->dd ? std::min(L.np, nb * chunk) : L.np;
-        // T = 32 two-zone lists stage their rows in shared memory (bulk async copies) when two rows per warp fit
         const size_t tab_bytes = (size_t)L.ntypes * L.ntypes * 16;
-        const size_t staged_bytes = 64 + tab_bytes + (size_t)(kBlock / 32) * 2 * L.stride * sizeof(unsigned int);
-        const int staged = (c->staging_opt && !c->dd && L.form == SEG_PAIR_TZ && L.tpb == 32 && L.dev.smem_tab && staged_bytes <= 56 * 1024) ? 1 : 0;
-        c->segs.push_back({blk, nb, L.form, (int)l, L.tpb, chunk, staged});
+        c->segs.push_back({blk, nb, L.form, (int)l, L.tpb, chunk, 0});
         blk += nb;
-        if (staged) smem = std::max(smem, staged_bytes);
-        else if (L.dev.smem_tab) smem = std::max(smem, tab_bytes);
+        if (L.dev.smem_tab) smem = std::max(smem, tab_bytes);
     }
     for (int k = 0; k < B_NUM_KINDS; k++) {
         if (c->bonded_h[k].n == 0) continue;
@@ -1520,6 +1518,7 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
     cudaStream_t s = c->stream;
     const size_t xb = (size_t)3 * c->n * sizeof(double), vb = (size_t)c->n * sizeof(float4);
     int64_t done = 0;
+    int replays = 0;   // consecutive rollbacks of the same batch
     if (c->nstlist_fixed > 0) c->nst = c->nstlist_fixed;
     CUDA_TRY(cudaEventRecord(c->ev0, s));
     while (done < nsteps) {
@@ -1557,6 +1556,8 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
             CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, (size_t)3 * c->n * sizeof(unsigned long long), s));
             canon_kernel<<<nblk(c->n, 256), 256, 0, s>>>(c->P, c->x.p, c->posq.p);
             c->n_rollbacks += 1;
+            // (a batch that keeps failing must not spin: the retries of ensure_lists_current are bounded the same way)
+            if (++replays > 8) throw std::runtime_error("a batch of steps keeps being rolled back (list overflow or Verlet-buffer violation)");
             if (c->dd) {
                 CUDA_TRY(cudaMemcpyAsync(c->dd->role.p, c->dd->role_bak.p, (size_t)c->n, cudaMemcpyDeviceToDevice, s));
                 if (fl[FLAG_DD_OVERFLOW]) dd_alloc(c, std::max(2 * c->dd->cap, (int)(1.5 * fl[FLAG_DD_MAXSEND])));
@@ -1570,7 +1571,9 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
                 canon_kernel<<<nblk(c->n, 256), 256, 0, s>>>(c->P, c->x.p, c->posq.p);
                 size_lists(c, 1.25);
             }
-            if (fl[FLAG_OVERFLOW] || fl[FLAG_DA_OVERFLOW] || fl[FLAG_DD_OVERFLOW]) size_lists(c, 1.5);
+            // the counting pass of size_lists sees the restored positions, not the step that overflowed: from the second replay on
+            // grow beyond what it asks for
+            if (fl[FLAG_OVERFLOW] || fl[FLAG_DA_OVERFLOW] || fl[FLAG_DD_OVERFLOW]) size_lists(c, replays > 1 ? 1.5 + 0.5 * replays : 1.5);
             if (fl[FLAG_VIOLATION]) {
                 if (c->nst <= 1) throw std::runtime_error("a particle crosses the Verlet buffer within one step; increase skin_nm or reduce the time step");
                 c->nst = quantise_nst(std::max(1.0, c->nst * 0.6));
@@ -1579,6 +1582,7 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
         }
         c->n_launches += launches; c->n_windows += windows; c->n_rebuilds += windows;
         done += batch;
+        replays = 0;
         {
             float d2max;
             std::memcpy(&d2max, &fl[FLAG_MAXDISP], sizeof(float));
@@ -2060,8 +2064,9 @@ int ocm_context_set_option(ocm_context* c, const char* key, double value) {
         c->tpb_opt = t;
         if (c->lists_ready) { build_segments(c); upload_lists(c); c->lists_current = false; }
     } else if (k == "row_staging") {
-        c->staging_opt = value != 0 ? 1 : 0;
-        if (c->lists_ready) { build_segments(c); upload_lists(c); c->lists_current = false; }
+        // (round-1 experiment: Verlet rows staged in shared memory by bulk async copies.  It never paid, and its mbarrier phase
+        // bookkeeping was wrong for beads without neighbours; removed in round 2)
+        if (value != 0) return fail("row_staging: the bulk-copy row staging path has been removed");
     } else if (k == "pair_kernel") {
         // 1: cluster-pair tile lists where the system allows them; 0: per-bead Verlet rows; -1 (default): tiles for the lists of
         // at least kTileAutoBeads beads (measured on B200: rows 38.6 us vs tiles 48 us per force launch at 16 300 beads, where one wave
@@ -2098,7 +2103,7 @@ int ocm_context_get_option(ocm_context* c, const char* key, double* value) {
     else if (k == "nstlist") *value = c->nstlist_fixed;
     else if (k == "threads_per_bead") *value = c->tpb_opt;
     else if (k == "beads_per_block") *value = c->chunk_opt;
-    else if (k == "row_staging") *value = c->staging_opt;
+    else if (k == "row_staging") *value = 0;
     else if (k == "halo_capacity") *value = c->dd ? c->dd->cap : 0;
     else if (k == "pair_kernel") *value = c->tile_opt;
     else if (k == "replica_kernel") *value = (c->rep_ok && c->rep_opt) ? 1 : 0;

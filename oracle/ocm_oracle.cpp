@@ -125,6 +125,20 @@ struct ocm_context {
     int dd_rank = 0, dd_world = 1, dd_axis = -1;
     double dd_halo = 0;
     double vbox[3] = {0, 0, 0};  // the engine's virtual box of an unlimited-boundary system (canonical predicate only)
+    // the CPU arm of bench.py (oracle_step on large systems): Verlet half lists with a skin, shared by the pair terms of equal
+    // topology, rebuilt when a bead has moved more than half the skin; per-thread force slabs kept between calls
+    struct VerletGroup {
+        std::vector<int> terms;            // pair terms (same participants, exclusions, classes) evaluated over this list
+        double rlist = 0;
+        std::vector<int> off, nbr;         // CSR half list: partners j of participant bead i (global indices)
+        std::vector<int> beads;            // row -> bead
+    };
+    std::vector<VerletGroup> vgroups;
+    std::vector<Vec3> vl_xref;
+    std::vector<std::vector<Vec3>> vl_F;   // [thread][bead]
+    bool vl_valid = false, vl_enabled = true;
+    double vl_skin = 0.3;
+    long long vl_builds = 0;
 };
 
 struct ocm_comm { int world; };
@@ -1203,6 +1217,8 @@ void oracle_context_destroy(ocm_context* c) { delete c; }
 int oracle_context_set_option(ocm_context* c, const char* key, double v) {
     if (!c) return fail("null context");
     if (!strcmp(key, "brute_force")) { c->force_brute = v != 0; return 0; }
+    if (!strcmp(key, "cpu_verlet")) { c->vl_enabled = v != 0; c->vl_valid = false; return 0; }       // Verlet lists in oracle_step (default on)
+    if (!strcmp(key, "cpu_skin_nm")) { if (v > 0) c->vl_skin = v; c->vl_valid = false; return 0; }
     if (!strcmp(key, "slab_halo_nm")) { c->dd_halo = v; return 0; }
     if (!strcmp(key, "virtual_box_x")) { c->vbox[0] = v; return 0; }
     if (!strcmp(key, "virtual_box_y")) { c->vbox[1] = v; return 0; }
@@ -1217,6 +1233,7 @@ int oracle_context_set_option(ocm_context* c, const char* key, double v) {
 }
 int oracle_context_get_option(ocm_context* c, const char* key, double* v) {
     if (!c || !v) return fail("null argument");
+    if (!strcmp(key, "cpu_verlet_builds")) { *v = (double)c->vl_builds; return 0; }
     if (!strcmp(key, "threads")) {
 #ifdef _OPENMP
         *v = omp_get_max_threads();
@@ -1253,14 +1270,144 @@ int oracle_set_velocities_to_temperature(ocm_context* c, double T, uint64_t seed
 }
 
 // SURVEY.md B.1 (OpenMM LangevinIntegrator, leap-frog)
+// ---- Verlet-list force evaluation for oracle_step on large systems (the CPU arm of bench.py) -------------------
+// Same pair set as the cell-list path (every pair inside the cutoff is in the list and is tested against the cutoff),
+// so the same forces up to the order of double-precision additions.
+static bool verlet_applicable(const ocm_context& c) {
+    if (!c.vl_enabled || c.force_brute || c.sys.pairs.empty()) return false;
+    size_t big = 0;
+    for (const auto& t : c.sys.pairs) big = std::max(big, t.part.size());
+    return big >= 1500;
+}
+
+static void verlet_build(ocm_context& c) {
+    c.vgroups.clear();
+    // group the pair terms by topology
+    for (int ti = 0; ti < (int)c.sys.pairs.size(); ti++) {
+        const PairTerm& t = c.sys.pairs[ti];
+        bool placed = false;
+        for (auto& g : c.vgroups) {
+            const PairTerm& o = c.sys.pairs[g.terms[0]];
+            if (o.periodic == t.periodic && o.part == t.part && o.excl == t.excl && o.cls == t.cls && o.allow == t.allow && o.nper == t.nper) {
+                g.terms.push_back(ti); placed = true; break;
+            }
+        }
+        if (!placed) { ocm_context::VerletGroup g; g.terms.push_back(ti); c.vgroups.push_back(std::move(g)); }
+    }
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    for (auto& g : c.vgroups) {
+        const PairTerm& t0 = c.sys.pairs[g.terms[0]];
+        double rc = 0;
+        for (int ti : g.terms) rc = std::max(rc, effective_rc(c.sys.pairs[ti]));
+        g.rlist = rc + c.vl_skin;
+        if (t0.periodic) for (int k = 0; k < 3; k++) g.rlist = std::min(g.rlist, 0.4999 * c.sys.box[k]);
+        std::vector<std::vector<std::pair<int, int>>> found(nthreads);
+        for_each_pair(c, t0, g.rlist, true, [&](int i, int j, Vec3, double) {
+            if (!pair_allowed(t0, i, j)) return;
+            int tid = 0;
+#ifdef _OPENMP
+            tid = omp_get_thread_num();
+#endif
+            found[tid].emplace_back(i, j);
+        });
+        std::vector<int> row_of(c.sys.n, -1);
+        g.beads.assign(t0.part.begin(), t0.part.end());
+        for (size_t a = 0; a < g.beads.size(); a++) row_of[g.beads[a]] = (int)a;
+        g.off.assign(g.beads.size() + 1, 0);
+        for (auto& v : found) for (auto& pr : v) g.off[row_of[pr.first] + 1]++;
+        for (size_t a = 0; a < g.beads.size(); a++) g.off[a + 1] += g.off[a];
+        g.nbr.resize(g.off.back());
+        std::vector<int> cur(g.off.begin(), g.off.end() - 1);
+        for (auto& v : found) for (auto& pr : v) g.nbr[cur[row_of[pr.first]]++] = pr.second;
+    }
+    c.vl_xref = c.x;
+    c.vl_valid = true;
+    c.vl_builds++;
+    if ((int)c.vl_F.size() != nthreads || (c.vl_F.size() && (int)c.vl_F[0].size() != c.sys.n)) c.vl_F.assign(nthreads, std::vector<Vec3>(c.sys.n, Vec3{0, 0, 0}));
+}
+
+static void compute_forces_verlet(ocm_context& c, std::vector<Vec3>* F) {
+    const int n = c.sys.n;
+    // rebuild when a bead has moved more than half the skin since the lists were made
+    bool stale = !c.vl_valid;
+    if (!stale) {
+        const double lim = 0.25 * c.vl_skin * c.vl_skin;
+        int moved = 0;
+#pragma omp parallel for reduction(| : moved)
+        for (int i = 0; i < n; i++) { const Vec3 d = c.x[i] - c.vl_xref[i]; if (dot(d, d) > lim) moved |= 1; }
+        stale = moved != 0;
+    }
+    if (stale) verlet_build(c);
+    F->assign(n, Vec3{0, 0, 0});
+    for (const auto& t : c.sys.bonded) eval_bonded(c, t, F, nullptr);
+    for (const auto& t : c.sys.das) eval_da(c, t, F, nullptr);
+    const int nthreads = (int)c.vl_F.size();
+#pragma omp parallel
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        std::vector<Vec3>& Fl = c.vl_F[tid];
+        for (auto& g : c.vgroups) {
+            const PairTerm& t0 = c.sys.pairs[g.terms[0]];
+            const bool per = t0.periodic != 0;
+            const double* box = c.sys.box;
+            const double ibx = per ? 1.0 / box[0] : 0, iby = per ? 1.0 / box[1] : 0, ibz = per ? 1.0 / box[2] : 0;
+            double rc2max = 0;
+            for (int ti : g.terms) rc2max = std::max(rc2max, c.sys.pairs[ti].rc * c.sys.pairs[ti].rc);
+#pragma omp for schedule(dynamic, 32) nowait
+            for (int a = 0; a < (int)g.beads.size(); a++) {
+                const int i = g.beads[a];
+                const Vec3 xi = c.x[i];
+                Vec3 fi{0, 0, 0};
+                for (int q = g.off[a]; q < g.off[a + 1]; q++) {
+                    const int j = g.nbr[q];
+                    Vec3 d = xi - c.x[j];
+                    if (per) { d.x -= box[0] * std::nearbyint(d.x * ibx); d.y -= box[1] * std::nearbyint(d.y * iby); d.z -= box[2] * std::nearbyint(d.z * ibz); }
+                    const double r2 = dot(d, d);
+                    if (!(r2 < rc2max)) continue;
+                    const double r = std::sqrt(r2);
+                    double dEsum = 0;
+                    for (int ti : g.terms) {
+                        const PairTerm& t = c.sys.pairs[ti];
+                        if (!(r < t.rc)) continue;
+                        double E, dE;
+                        pair_energy(t, i, j, r, &E, &dE);
+                        dEsum += dE;
+                    }
+                    const Vec3 f = d * (-dEsum / r);
+                    fi = fi + f;
+                    Fl[j] = Fl[j] - f;
+                }
+                Fl[i] = Fl[i] + fi;
+            }
+        }
+#pragma omp barrier
+        // reduce the per-thread slabs in parallel over the beads, and clear them for the next call
+#pragma omp for schedule(static)
+        for (int i = 0; i < n; i++) {
+            Vec3 s = (*F)[i];
+            for (int k = 0; k < nthreads; k++) { s = s + c.vl_F[k][i]; c.vl_F[k][i] = Vec3{0, 0, 0}; }
+            (*F)[i] = s;
+        }
+    }
+}
+
 int oracle_step(ocm_context* c, int64_t nsteps) {
     if (!c) return fail("null context");
     const double a = std::exp(-c->gamma * c->dt);
     const double b = c->gamma == 0 ? c->dt : (1.0 - a) / c->gamma;
     const double cc = std::sqrt(kBoltz * c->T * (1.0 - a * a));
     std::vector<Vec3> F;
+    const bool verlet = verlet_applicable(*c);
+    c->vl_valid = false;  // (positions may have been set since the last call)
     for (int64_t s = 0; s < nsteps; s++) {
-        compute(*c, &F, nullptr, 0xFFFFFFFFu);
+        if (verlet) compute_forces_verlet(*c, &F);
+        else compute(*c, &F, nullptr, 0xFFFFFFFFu);
         for (int i = 0; i < c->sys.n; i++) {
             double m = c->sys.mass[i];
             if (!(m > 0)) continue;

@@ -374,3 +374,22 @@ def test_committed_c2_state_is_a_valid_compacted_condensate(oracle):
     assert two.positions.shape == (32600, 3) and np.allclose(two.box, spec.box * np.array([2, 1, 1]))
     f2 = ti.make_context(oracle, two).get_state(forces=True)["forces"]
     assert np.abs(f2 - np.concatenate([f1, f1])).max() < 1e-7 * max(1.0, np.abs(f1).max())
+
+
+def test_cpu_arm_verlet_lists_reproduce_the_cell_list_path(oracle):
+    """oracle_step on large systems walks Verlet half lists with a skin (the CPU arm of bench.py); same pair set as the per-step
+    cell list, so the same trajectory up to the order of double-precision additions, across several list rebuilds"""
+    from opencafemol_b200 import synth, toml_input as ti
+
+    spec = synth.hps_slab(n_chains=12)
+    out = []
+    for verlet in (0, 1):
+        ctx = ti.make_context(oracle, spec)
+        ctx.set_option("cpu_verlet", verlet)
+        ctx.set_option("cpu_skin_nm", 0.05)   # a thin skin: several rebuilds within the run
+        ctx.step(40)
+        out.append(ctx.get_state(positions=True, velocities=True))
+        if verlet:
+            assert ctx.get_option("cpu_verlet_builds") >= 3
+    assert np.abs(out[0]["positions"] - out[1]["positions"]).max() < 1e-10
+    assert np.abs(out[0]["velocities"] - out[1]["velocities"]).max() < 1e-9

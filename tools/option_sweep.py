@@ -2,14 +2,14 @@
 """A/B engine tunables on one equilibrated state (one GPU, one gpurun call).
 
     python tools/option_sweep.py [--chains 100] [--tile 1x1] [--equil 6000] [--steps 4000] \
-        skin_nm=0.3,0.4,0.5 row_staging=0,1 beads_per_block=0,8,16
+        skin_nm=0.3,0.4,0.5 beads_per_block=0,8,16
 
 The workload (synth.hps_slab: C2 with the defaults, --tile 8x8 --chains 6400 = C5 on one GPU) is equilibrated once with
 the default options; every combination of the listed option values then starts from that same state (positions and
 velocities through the C ABI, same integrator seed), runs --steps MD steps twice (the first run settles the adaptive
 rebuild interval) and prints one JSON line: MD steps/s from the device-timed second run, the per-kernel times of
 ocm_profile_kernel, the rebuild interval and the list size.  Options are the context tunables of include/ocm_b200.h
-("skin_nm", "nstlist", "threads_per_bead", "beads_per_block", "row_staging", "pdl", ...).
+("skin_nm", "nstlist", "threads_per_bead", "beads_per_block", "pair_kernel", "tile_blocks", "pdl", ...).
 """
 import argparse
 import itertools

@@ -348,6 +348,28 @@ def multi_gpu_records(lib, rank, world, local):
     dist.barrier()
     ctx.close()
     comm.close()
+    # ---- C4: the fixed ensemble of 512 SH3 replicas sharded 512 / N per rank (no collective on the data path) ----
+    import sys as _sys
+
+    from opencafemol_b200 import sharding
+    _sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import load_golden_spec
+
+    sh3 = load_golden_spec("sh3")
+    one = None
+    if rank == 0:
+        c1 = toml_input.make_context(lib, sh3, device=local, replicas=512)
+        one = 512 * 2000 / timed_steps(c1, 500, 2000, local, 1)
+        c1.close()
+    dist.barrier()
+    first, per = sharding.replica_shard(512, world, rank)
+    ctx = toml_input.make_context(lib, sh3, device=local, seed=sh3.seed + first, replicas=per)
+    dev = timed_steps(ctx, 500, 2000, local, world)
+    if rank == 0:
+        out["c4"] = {"workload": "C4: 512 SH3 replicas, %d per GPU, no collective per step" % per, "replica_steps_per_s": 512 * 2000 / dev,
+                     "replica_steps_per_s_one_gpu": one, "strong_scaling_efficiency": 512 * 2000 / dev / one / world}
+    dist.barrier()
+    ctx.close()
     return out
 
 

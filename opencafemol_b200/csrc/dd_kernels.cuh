@@ -86,8 +86,9 @@ __global__ void dd_install_kernel(DDGeom G, StepParams P, int cap, DDMsg M, doub
 }
 
 // new roles of every bead this rank has current state for (owned so far, or just received)
+// ... and the compact list of the beads present here (owned + halo): integrate_kernel runs over it instead of over the system
 __global__ void dd_assign_kernel(int n, DDGeom G, const uint4* __restrict__ posq, unsigned char* __restrict__ role,
-                                 unsigned char* __restrict__ known) {
+                                 unsigned char* __restrict__ known, int* __restrict__ present, int* __restrict__ n_present) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned char r = 0;
@@ -97,6 +98,7 @@ __global__ void dd_assign_kernel(int n, DDGeom G, const uint4* __restrict__ posq
     }
     role[i] = r;
     known[i] = 0;
+    if (r) present[atomicAdd(n_present, 1)] = i;
 }
 
 // phase B: per-step halo lists of the owned beads (indices only)
@@ -119,8 +121,9 @@ __global__ void dd_steplist_kernel(int n, DDGeom G, int cap, const unsigned char
 }
 
 // every bonded term with an owned bead must have all its beads on this rank
+// ... and the terms with an owned bead are compacted into terms[] (the bonded blocks of force_kernel run over that list)
 __global__ void dd_check_bonded_kernel(const BondedDev* __restrict__ bonded, int kind, const unsigned char* __restrict__ role,
-                                       int* __restrict__ flags) {
+                                       int* __restrict__ flags, int* __restrict__ terms, int* __restrict__ count, int capacity) {
     const BondedDev& B = bonded[kind];
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= B.n) return;
@@ -128,6 +131,10 @@ __global__ void dd_check_bonded_kernel(const BondedDev* __restrict__ bonded, int
     bool mine = false, all = true;
     for (int q = 0; q < nb; q++) { const unsigned char r = role[B.idx[nb * m + q]]; mine = mine || r == 1; all = all && r != 0; }
     if (mine && !all) flags[FLAG_DD_REACH] = 1;
+    if (mine) {
+        const int p = atomicAdd(count, 1);
+        if (p < capacity) terms[p] = m; else flags[FLAG_OVERFLOW] = 1;   // more terms than the force launch covers: re-size
+    }
 }
 
 // per MD step: positions of the halo-list beads, both directions in one launch

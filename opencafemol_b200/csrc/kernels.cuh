@@ -112,6 +112,10 @@ struct BondedDev {
     const double* par;    // npar * n
     const int* meta;      // group | periodic<<8 | table<<16
     const double* tabs;   // 24 doubles per table
+    // slab decomposition: the terms with an owned bead on this rank, compacted at every list rebuild (dd_check_bonded_kernel);
+    // null otherwise
+    const int* dd_terms;
+    const int* dd_count;
 };
 
 // donor x acceptor terms (3SPN.2 base pairing / cross stacking, PDNS): per-term tables + one Verlet list of
@@ -155,6 +159,8 @@ struct StepParams {
     const double* origin;       // [3*nrep] or null (single system, origin 0)
     const uint2* rep_seed;      // [nrep] or null
     const unsigned char* role;  // slab decomposition: 0 = not on this rank, 1 = owned, 2 = halo; null = single domain
+    const int* present;         // slab decomposition: the beads present on this rank (owned + halo), compacted at every rebuild
+    const int* n_present;
     int pdl_early;              // programmatic dependent launch: release the successor's launch at block start
 };
 
@@ -1366,16 +1372,11 @@ __global__ void __launch_bounds__(kBlock, OCM_FORCE_MINBLOCKS) force_kernel(cons
         }
     } else {
         const BondedDev& B = bonded[sg.id];
-        const int m = blk * kBlock + threadIdx.x;
+        int m = blk * kBlock + threadIdx.x;
+        // slab decomposition: a term is evaluated by every rank that owns one of its beads (the forces on the other beads
+        // are discarded with the accumulator); those terms were compacted at the last rebuild
+        if (B.dd_terms) m = (m < *B.dd_count) ? B.dd_terms[m] : B.n;
         if (m < B.n) {
-            if (P.role) {
-                // slab decomposition: a term is evaluated by every rank that owns one of its beads (the forces on the
-                // other beads are discarded with the accumulator); all its beads must be present here
-                const int nb = bonded_nbody_dev(sg.id);
-                bool mine = false;
-                for (int q = 0; q < nb; q++) mine = mine || P.role[B.idx[nb * m + q]] == 1;
-                if (!mine) return;
-            }
             int g;
             bonded_term(sg.id, B, m, P, x, fbuf, &g);
         }
@@ -1430,7 +1431,13 @@ __global__ void integrate_kernel(StepParams P, double* __restrict__ x, float4* _
                                  int step_offset, int window, int last_in_window, int* __restrict__ flags) {
     if (P.pdl_early) pdl_trigger();
     pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // slab decomposition: one thread per bead PRESENT on this rank (compacted at the last rebuild), not per bead of the system
+    if (P.present) {
+        const int np = *P.n_present;
+        if (i == 0 && np > (int)(gridDim.x * blockDim.x)) flags[FLAG_OVERFLOW] = 1;   // more beads than the launch covers: re-size
+        i = (i < np) ? P.present[i] : P.n;
+    }
     const unsigned long long step = *step_base + (unsigned long long)step_offset;
     float d2 = 0.f;
     // slab decomposition: beads that are not on this rank cost one byte; halo beads only have their accumulator cleared
@@ -1541,7 +1548,8 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(const WorkSeg* __restric
         int g = -1;
         if (sg.kind == SEG_BONDED) {
             const BondedDev& B = bonded[sg.id];
-            const int m = blk * kBlock + threadIdx.x;
+            int m = blk * kBlock + threadIdx.x;
+            if (B.dd_terms) m = (m < *B.dd_count) ? B.dd_terms[m] : B.n;
             // slab decomposition: the rank owning the first bead of a term reports its energy
             if (m < B.n && (!P.role || P.role[B.idx[bonded_nbody_dev(sg.id) * m]] == 1)) E = bonded_term(sg.id, B, m, P, x, nullptr, &g);
         } else {

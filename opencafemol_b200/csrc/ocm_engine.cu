@@ -129,6 +129,12 @@ struct DDState {
     DevBuf<double> s_send[2], s_recv[2];          // per-step positions
     DevBuf<double> gx; DevBuf<float> gv; DevBuf<long long> gf;  // state gather
     std::vector<int> rows_est;                    // per pair list: rows in use at the last sizing pass
+    // compact work lists of this rank, rebuilt with the pair lists: beads present (owned + halo), bonded terms with an owned bead
+    DevBuf<int> present, counts;                  // counts: [0] beads present, [1 + kind] bonded terms
+    DevBuf<int> bterms[B_NUM_KINDS];
+    int present_est = 0, bterm_est[B_NUM_KINDS] = {0};
+    int integrate_cover(int n) const { return present_est > 0 ? std::min(n, (int)(1.3 * present_est) + 1024) : n; }
+    int bonded_cover(int kind, int nterms) const { return bterm_est[kind] > 0 ? std::min(nterms, (int)(1.3 * bterm_est[kind]) + 1024) : nterms; }
     double n_exchanges = 0;
     // per-step halo over peer memory (dd_push_kernel): [4 flags x 128 B][side 0/1][parity 0/1][cap x 3 doubles]
     DevBuf<char> push;
@@ -737,7 +743,7 @@ static void build_segments(ocm_context* c) {
     }
     for (int k = 0; k < B_NUM_KINDS; k++) {
         if (c->bonded_h[k].n == 0) continue;
-        int nb = (c->bonded_h[k].n + kBlock - 1) / kBlock;
+        int nb = ((c->dd ? c->dd->bonded_cover(k, c->bonded_h[k].n) : c->bonded_h[k].n) + kBlock - 1) / kBlock;
         c->segs.push_back({blk, nb, SEG_BONDED, k, 0, 0, 0});
         blk += nb;
     }
@@ -784,9 +790,14 @@ static void compile_bonded(ocm_context* c) {
         }
         BondedDev& B = c->bonded_h[k];
         B.n = (int)(idx.size() / nbody); B.npar = npar;
+        B.dd_terms = nullptr; B.dd_count = nullptr;
         if (B.n) {
             c->b_idx[k].upload(idx); c->b_par[k].upload(par); c->b_meta[k].upload(meta);
             B.idx = c->b_idx[k].p; B.par = c->b_par[k].p; B.meta = c->b_meta[k].p;
+            if (c->dd) {
+                c->dd->bterms[k].alloc(B.n);
+                B.dd_terms = c->dd->bterms[k].p; B.dd_count = c->dd->counts.p + 1 + k;
+            }
         }
     }
     c->b_tabs.upload(tabs);
@@ -991,6 +1002,8 @@ static void update_params(ocm_context* c) {
     P.origin = c->nrep > 1 ? c->origin.p : nullptr;
     P.rep_seed = c->nrep > 1 ? c->d_rep_seed.p : nullptr;
     P.role = c->dd ? c->dd->role.p : nullptr;
+    P.present = c->dd ? c->dd->present.p : nullptr;
+    P.n_present = c->dd ? c->dd->counts.p : nullptr;
     if (c->dd) dd_configure(c);
 }
 
@@ -1069,7 +1082,8 @@ static void dd_exchange_rebuild(ocm_context* c, cudaStream_t s) {
     d.comm->ring_exchange(d.rank, d.a_send[0].p, d.a_send[1].p, d.a_recv[0].p, d.a_recv[1].p, d.bytes_a(), s);
     dd_install_kernel<<<nblk(cap, 256), 256, 0, s>>>(d.G, c->P, cap, rlo, c->x.p, c->v.p, c->posq.p, d.known.p);
     dd_install_kernel<<<nblk(cap, 256), 256, 0, s>>>(d.G, c->P, cap, rhi, c->x.p, c->v.p, c->posq.p, d.known.p);
-    dd_assign_kernel<<<nblk(n, 256), 256, 0, s>>>(n, d.G, c->posq.p, d.role.p, d.known.p);
+    CUDA_TRY(cudaMemsetAsync(d.counts.p, 0, (1 + B_NUM_KINDS) * sizeof(int), s));
+    dd_assign_kernel<<<nblk(n, 256), 256, 0, s>>>(n, d.G, c->posq.p, d.role.p, d.known.p, d.present.p, d.counts.p);
     CUDA_TRY(cudaMemsetAsync(d.b_send[0].p, 0, 16, s));
     CUDA_TRY(cudaMemsetAsync(d.b_send[1].p, 0, 16, s));
     dd_steplist_kernel<<<nblk(n, 256), 256, 0, s>>>(n, d.G, cap, d.role.p, c->posq.p, reinterpret_cast<int*>(d.b_send[0].p),
@@ -1077,7 +1091,9 @@ static void dd_exchange_rebuild(ocm_context* c, cudaStream_t s) {
                                                     reinterpret_cast<int*>(d.b_send[1].p + 16), c->flags.p);
     d.comm->ring_exchange(d.rank, d.b_send[0].p, d.b_send[1].p, d.b_recv[0].p, d.b_recv[1].p, d.bytes_b(), s);
     for (int k = 0; k < B_NUM_KINDS; k++)
-        if (c->bonded_h[k].n > 0) dd_check_bonded_kernel<<<nblk(c->bonded_h[k].n, 256), 256, 0, s>>>(c->d_bonded.p, k, d.role.p, c->flags.p);
+        if (c->bonded_h[k].n > 0)
+            dd_check_bonded_kernel<<<nblk(c->bonded_h[k].n, 256), 256, 0, s>>>(c->d_bonded.p, k, d.role.p, c->flags.p, d.bterms[k].p, d.counts.p + 1 + k,
+                                                                                 nblk(d.bonded_cover(k, c->bonded_h[k].n), kBlock) * kBlock);
     c->n_launches += 5; d.n_exchanges += 2;
 }
 
@@ -1284,6 +1300,12 @@ static void size_lists(ocm_context* c, double growth) {
             dd_alloc(c, std::max(2 * d.cap, (int)(1.5 * fl[FLAG_DD_MAXSEND])));
         }
         d.rows_est.assign(c->lists.size(), 0);
+        // how many beads / bonded terms this rank works on: the integrate and bonded launches cover 1.3 x that
+        // (more than that at a later rebuild raises the overflow flag: sized again)
+        int h[1 + B_NUM_KINDS];
+        CUDA_TRY(cudaMemcpy(h, d.counts.p, sizeof(h), cudaMemcpyDeviceToHost));
+        d.present_est = (int)(h[0] * std::max(1.0, growth / 1.25));
+        for (int k = 0; k < B_NUM_KINDS; k++) d.bterm_est[k] = (int)(h[1 + k] * std::max(1.0, growth / 1.25));
     }
     std::vector<int> fl(FLAG_COUNT, 0);
     // one counting pass per list: FLAG_MAXDISP+1 receives the largest neighbour count of that list
@@ -1417,7 +1439,7 @@ static void enqueue_window(ocm_context* c, cudaStream_t s, int nst) {
         } else enqueue_forces(c, s, 0);
         interior_done = false;
         phase_mark(c, s, 1);
-        launch_chained(c, integrate_kernel, nblk(c->n, 128), 128, 0, s, c->P, c->x.p, c->v.p, c->fbuf.p, c->posq.p, c->d_lists.p, (int)c->lists.size(), c->xref.p,
+        launch_chained(c, integrate_kernel, nblk(c->dd ? c->dd->integrate_cover(c->n) : c->n, 128), 128, 0, s, c->P, c->x.p, c->v.p, c->fbuf.p, c->posq.p, c->d_lists.p, (int)c->lists.size(), c->xref.p,
                        c->step_base.p, k, nst, k == nst - 1 ? 1 : 0, c->flags.p);
         phase_mark(c, s, 2);
         // the next window starts with a full halo refresh, so the last step of a window ships nothing
@@ -1830,6 +1852,7 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
         c->dd->comm = comm->impl; c->dd->rank = dd_rank; c->dd->world = comm->impl->world; c->dd->axis = dd_axis;
         c->dd->role.alloc(sys->n); c->dd->role_bak.alloc(sys->n); c->dd->role_tmp.alloc(sys->n); c->dd->known.alloc(sys->n);
         c->dd->role.zero(); c->dd->role_bak.zero(); c->dd->role_tmp.zero(); c->dd->known.zero();
+        c->dd->present.alloc(sys->n); c->dd->counts.alloc(1 + B_NUM_KINDS); c->dd->counts.zero();
         if (auto* lc = dynamic_cast<LocalComm*>(comm->impl)) lc->attach(dd_rank, device);
     }
     if (nrep == 1) c->sys = *sys;

@@ -228,7 +228,9 @@ def timed_steps(ctx, warm, steps, local, world):
         dist.barrier()
     torch.cuda.synchronize()
     ctx.step(steps)
-    return sharding.max_over_ranks([ctx.counter("last_step_ms") * 1e-3], device=f"cuda:{local}")[0]
+    dev = ctx.counter("last_step_ms") * 1e-3
+    # (world == 1: a single-rank measurement, possibly made by rank 0 alone inside a multi-rank run: no collective)
+    return sharding.max_over_ranks([dev], device=f"cuda:{local}")[0] if world > 1 else dev
 
 
 def single_gpu_records(lib, local):

@@ -1,0 +1,11 @@
+"""C5 (the compacted C2 state tiled 8 x 8, 1 043 200 beads) for profilers: a few dozen MD steps across one list rebuild."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from opencafemol_b200 import synth, toml_input as ti  # noqa: E402
+from opencafemol_b200.capi import product_library  # noqa: E402
+
+ctx = ti.make_context(product_library(), synth.c2_equilibrated(tile=(8, 8)))
+ctx.step(30)
+print("ms/step", ctx.counter("last_step_ms") / 30)

@@ -20,9 +20,14 @@ import re
 import subprocess
 
 
-def load(report):
+def load(report, kernel_re=None):
     out = subprocess.run(["ncu", "-i", report, "--page", "source", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
+    # a report may hold several launches: one section per launch, each starting with its "Kernel Name" line
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] or [0]
+    pick = next((i for i in starts if re.search(kernel_re, rows[i][1])), starts[0]) if kernel_re else starts[0]
+    end = next((i for i in starts if i > pick), len(rows))
+    rows = rows[pick:end]
     h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     kernel = next((r[1] for r in rows[:h] if r and r[0] == "Kernel Name"), "?")
     hdr = rows[h]
@@ -36,8 +41,9 @@ def main():
     ap.add_argument("report")
     ap.add_argument("--top", type=int, default=25)
     ap.add_argument("--dump", default=None, help="A:B = print the SASS of instruction indices [A, B)")
+    ap.add_argument("--kernel", default=None, help="regular expression: the first captured launch whose kernel name matches")
     a = ap.parse_args()
-    kernel, hdr, ix, data = load(a.report)
+    kernel, hdr, ix, data = load(a.report, a.kernel)
     ex = [int(r[ix["Instructions Executed"]] or 0) for r in data]
     sm = [int(r[ix["# Samples"]] or 0) for r in data]
     tot, stot = sum(ex), max(sum(sm), 1)

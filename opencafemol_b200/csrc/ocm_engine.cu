@@ -218,10 +218,7 @@ struct ocm_context {
     int rep_opt = 0;                        // option "replica_kernel": 1 = use it where possible, 0 (default) = general path
     RepParams rep{};
     size_t rep_smem = 0;
-    std::vector<std::unique_ptr<DevBuf<ushort2>>> rep_ij;
-    std::vector<std::unique_ptr<DevBuf<float4>>> rep_coef;
-    DevBuf<int> rep_b_idx[B_NUM_KINDS], rep_b_meta[B_NUM_KINDS];
-    DevBuf<double> rep_b_par[B_NUM_KINDS];
+    std::vector<std::unique_ptr<DevBuf<unsigned char>>> rep_blobs;   // its static tables (compile_replica_tables)
     double n_rep_launches = 0;
     int tile_opt = -1;                      // option "pair_kernel": 1 = cluster-pair tiles where possible, 0 = Verlet rows, -1 = by size
     int tile_debug = 0;
@@ -806,15 +803,27 @@ static void compile_bonded(ocm_context* c) {
 }
 
 // ---- whole-step persistent kernel: static tables of one replica ------------------------------------------
+template <typename T>
+static const T* rep_upload(ocm_context* c, const std::vector<T>& v) {
+    if (v.empty()) return nullptr;
+    c->rep_blobs.emplace_back(new DevBuf<unsigned char>());
+    c->rep_blobs.back()->alloc(v.size() * sizeof(T));
+    CUDA_TRY(cudaMemcpy(c->rep_blobs.back()->p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return reinterpret_cast<const T*>(c->rep_blobs.back()->p);
+}
+
 static void compile_replica_tables(ocm_context* c) {
     c->rep_ok = false;
+    c->rep_blobs.clear();
     const ocm_system& S1 = c->nrep > 1 ? c->sys1 : c->sys;
     const int nper = c->nper;
     if (c->dd || (c->sys.has_box && !c->vbox) || !S1.das.empty() || nper > 256 || nper < 2) return;
     if ((int)c->lists.size() > kRepMaxLists) return;
+    for (const auto& t : S1.bonded) if (t.kind == B_3SPN2_STACK && t.n() > 0) return;
     RepParams& R = c->rep;
     R = RepParams{};
     R.nper = nper; R.nrep = c->nrep; R.nlists = 0;
+    std::vector<RepTask> tasks;
     for (auto& Lp : c->lists) {
         PairListHost& L = *Lp;
         if (L.np == 0) continue;
@@ -822,8 +831,8 @@ static void compile_replica_tables(ocm_context* c) {
         const PairTerm& t0 = S1.pairs[L.terms[0]];
         const PairTerm* rep = nullptr; const PairTerm* att = nullptr;
         if (nm == 2) { rep = &S1.pairs[L.terms[0]]; att = &S1.pairs[L.terms[1]]; if (rep->kind != P_LJREP) std::swap(rep, att); }
-        std::vector<ushort2> ij;
-        std::vector<float4> coef;
+        // full table: coefficients of every interacting pair from both sides, zero elsewhere
+        std::vector<float4> coef((size_t)nper * nper, make_float4(0.f, 0.f, 0.f, 0.f));
         size_t e = 0;  // exclusions are sorted (i < j): walk them alongside the pair loop
         for (size_t a = 0; a < t0.part.size(); a++)
             for (size_t b = a + 1; b < t0.part.size(); b++) {
@@ -841,58 +850,85 @@ static void compile_replica_tables(ocm_context* c) {
                     if (t0.kind == P_LJATT) cf = make_float4((float)(12.0 * z.c12o), (float)(6.0 * z.c6o), (float)z.a2, 1.f);
                     else cf = make_float4((float)(12.0 * z.c12i), (float)(6.0 * z.c6i), std::isfinite(z.a2) ? (float)z.a2 : INFINITY, 0.f);
                 }
-                ij.push_back(make_ushort2((unsigned short)i, (unsigned short)j));
-                coef.push_back(cf);
+                coef[(size_t)i * nper + j] = cf; coef[(size_t)j * nper + i] = cf;
             }
-        RepList& Q = R.lists[R.nlists++];
-        Q.npairs = (int)ij.size(); Q.form = L.form; Q.has_switch = L.dev.has_switch;
-        Q.rc2 = L.dev.rc2; Q.k_in = L.dev.k_in; Q.rsw = L.dev.rsw; Q.inv_sw = L.dev.inv_sw; Q.inv_debye = L.dev.inv_debye;
-        if (ij.empty()) { ij.push_back(make_ushort2(0, 0)); coef.push_back(make_float4(0, 0, 0, 0)); }
-        c->rep_ij.emplace_back(new DevBuf<ushort2>()); c->rep_ij.back()->upload(ij);
-        c->rep_coef.emplace_back(new DevBuf<float4>()); c->rep_coef.back()->upload(coef);
-        Q.ij = c->rep_ij.back()->p; Q.coef = c->rep_coef.back()->p;
+        const int l = R.nlists++;
+        RepList& Q = R.lists[l];
+        Q.form = L.form; Q.has_switch = L.dev.has_switch;
+        Q.rc2 = L.dev.rc2; Q.rl2 = (float)std::pow(std::sqrt((double)L.dev.rc2) + (double)kRepSkin, 2); Q.k_in = L.dev.k_in; Q.rsw = L.dev.rsw; Q.inv_sw = L.dev.inv_sw; Q.inv_debye = L.dev.inv_debye;
+        Q.coef = rep_upload(c, coef);
+        for (int i0 = 0; i0 < nper; i0 += 8) tasks.push_back({kRepTaskPair + l, i0});
     }
-    // bonded tables of one replica (local bead indices); a single system uses the engine's own tables
-    if (c->nrep == 1) for (int k = 0; k < B_NUM_KINDS; k++) R.bonded[k] = c->bonded_h[k];
-    else {
-        // (table ids must match the replicated compile: tables are appended per BondedTerm in system order, once per term)
-        for (int k = 0; k < B_NUM_KINDS; k++) {
-            std::vector<int> idx, meta;
-            std::vector<double> par;
-            int npar = 0;
-            for (size_t ti = 0; ti < S1.bonded.size(); ti++) {
-                const BondedTerm& t = S1.bonded[ti];
-                if (t.kind != k) continue;
-                npar = t.npar;
-                // the table id the replicated compile gave this term: count the flexible-local terms of kinds <= k before it
-                int tab_id = 0;
-                if (k == B_FLEX_ANGLE || k == B_FLEX_DIHEDRAL) {
-                    tab_id = 1;
-                    for (int kk = 0; kk <= k; kk++)
-                        for (size_t tj = 0; tj < S1.bonded.size(); tj++) {
-                            const BondedTerm& u = S1.bonded[tj];
-                            if (u.kind != kk || !(kk == B_FLEX_ANGLE || kk == B_FLEX_DIHEDRAL)) continue;
-                            if (kk == k && tj >= ti) break;
-                            tab_id++;
-                        }
+    // bonded terms of one replica, kind by kind: local bead indices, FP32 parameters, own table numbering
+    std::vector<float> tabs(24, 0.f);
+    std::vector<std::vector<unsigned short>> slots_of_bead(nper);
+    int nslots = 0;
+    for (int k = 0; k < 9; k++) {
+        std::vector<unsigned short> idx, tab;
+        std::vector<float> par;
+        std::vector<double> r0;
+        int npar = 0;
+        const int nbody = bonded_nbody(k);
+        for (const auto& t : S1.bonded) {
+            if (t.kind != k || t.n() == 0) continue;
+            if (t.periodic) return;
+            if (npar && npar != t.npar) return;
+            npar = t.npar;
+            int tab_id = 0;
+            if (k == B_FLEX_ANGLE || k == B_FLEX_DIHEDRAL) {
+                tab_id = (int)(tabs.size() / 24);
+                if (tab_id >= 65536) return;
+                for (int q = 0; q < 24; q++) tabs.push_back((float)t.tab[q]);
+            }
+            for (int v : t.idx) idx.push_back((unsigned short)v);
+            for (double v : t.p) par.push_back((float)v);
+            for (int64_t m = 0; m < t.n(); m++) {
+                tab.push_back((unsigned short)tab_id);
+                if (k == B_HARMONIC_BOND) r0.push_back(t.p[(size_t)m * t.npar + 0]);
+                else if (k == B_GAUSSIAN_BOND) r0.push_back(t.p[(size_t)m * t.npar + 1]);
+                else if (k == B_3SPN2_BOND) r0.push_back(t.p[(size_t)m * t.npar + 2]);
+            }
+        }
+        RepBonded& B = R.bonded[k];
+        B = RepBonded{};
+        B.n = (int)(idx.size() / nbody); B.npar = npar; B.slot0 = nslots;
+        if (npar > 5) return;
+        if (B.n) {
+            B.idx = rep_upload(c, idx); B.par = rep_upload(c, par);
+            B.r0 = rep_upload(c, r0);
+            B.tab = (k == B_FLEX_ANGLE || k == B_FLEX_DIHEDRAL) ? rep_upload(c, tab) : nullptr;
+            for (int m = 0; m < B.n; m++)
+                for (int b = 0; b < nbody; b++) {
+                    const int slot = nslots + b * B.n + m;
+                    if (slot >= 65536) return;
+                    slots_of_bead[idx[(size_t)m * nbody + b]].push_back((unsigned short)slot);
                 }
-                idx.insert(idx.end(), t.idx.begin(), t.idx.end());
-                par.insert(par.end(), t.p.begin(), t.p.end());
-                for (int64_t m = 0; m < t.n(); m++) meta.push_back(t.group | (t.periodic << 8) | (tab_id << 16));
-            }
-            BondedDev& B = R.bonded[k];
-            B = BondedDev{};
-            B.n = (int)(idx.size() / bonded_nbody(k)); B.npar = npar;
-            if (B.n) {
-                c->rep_b_idx[k].upload(idx); c->rep_b_par[k].upload(par); c->rep_b_meta[k].upload(meta);
-                B.idx = c->rep_b_idx[k].p; B.par = c->rep_b_par[k].p; B.meta = c->rep_b_meta[k].p;
-            }
-            B.tabs = c->b_tabs.p;
+            nslots += nbody * B.n;
         }
     }
+    // warp tasks, long ones first (pair gathers are already in): dihedrals, angles, noise, bonds
+    const int order[9] = {8, 6, 7, 5, 4, 2, 1, 3, 0};
+    for (int q = 0; q < 4; q++)
+        for (int m0 = 0; m0 < R.bonded[order[q]].n; m0 += 32) tasks.push_back({order[q], m0});
+    for (int i0 = 0; i0 < nper; i0 += 32) tasks.push_back({kRepTaskNoise, i0});
+    for (int q = 4; q < 9; q++)
+        for (int m0 = 0; m0 < R.bonded[order[q]].n; m0 += 32) tasks.push_back({order[q], m0});
+    std::vector<int> csr_off(nper + 1, 0);
+    std::vector<unsigned short> csr_slot;
+    for (int i = 0; i < nper; i++) {
+        csr_off[i] = (int)csr_slot.size();
+        csr_slot.insert(csr_slot.end(), slots_of_bead[i].begin(), slots_of_bead[i].end());
+    }
+    csr_off[nper] = (int)csr_slot.size();
+    if (csr_slot.empty()) csr_slot.push_back(0);
+    R.nslots = nslots; R.ntasks = (int)tasks.size(); R.ncsr = (int)csr_slot.size();
+    R.tabs = rep_upload(c, tabs); R.tasks = rep_upload(c, tasks);
+    R.csr_off = rep_upload(c, csr_off); R.csr_slot = rep_upload(c, csr_slot);
     R.rep_seed = c->nrep > 1 ? c->d_rep_seed.p : nullptr;
-    c->rep_smem = (size_t)nper * (3 * 8 + 16 + 16);
+    c->rep_smem = rep_smem_bytes(nper, R.nlists, nslots, R.ncsr);
+    if (c->rep_smem > 96 * 1024) return;   // (scratch slots of a few thousand terms: beyond that the general path)
     CUDA_TRY(cudaFuncSetAttribute(replica_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(c->rep_smem, 1024)));
+    CUDA_TRY(cudaFuncSetAttribute(replica_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     c->rep_ok = true;
 }
 
@@ -1513,7 +1549,7 @@ static void do_steps_replica_kernel(ocm_context* c, int64_t nsteps) {
     // (launches of at most 65 536 steps: a block holds its replica for the whole launch)
     for (int64_t done = 0; done < nsteps;) {
         const int chunk = (int)std::min<int64_t>(65536, nsteps - done);
-        replica_step_kernel<<<c->nrep, kRepBlock, c->rep_smem, s>>>(R, c->x.p, c->v.p, c->fbuf.p, c->n, (unsigned long long)(c->step + done), chunk, c->flags.p);
+        replica_step_kernel<<<c->nrep, kRepBlock, c->rep_smem, s>>>(R, c->x.p, c->v.p, (unsigned long long)(c->step + done), chunk, c->flags.p);
         c->n_launches += 1; c->n_rep_launches += 1;
         done += chunk;
     }

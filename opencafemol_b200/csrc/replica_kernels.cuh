@@ -1,47 +1,82 @@
 // replica_kernels.cuh — whole-step persistent kernel for small systems (configs C1 and C4: an SH3 domain of 56 beads,
 // alone or as an ensemble of independent replicas).
 //
-// One thread block owns one replica for a whole launch of `nsteps` MD steps: positions, velocities and the fixed-point force
-// accumulator live in shared memory, every non-excluded bead pair of the replica is visited each step from a static pair
-// table (no neighbour list: 1 540 pairs for 56 beads), the bonded terms are the same device functions as in force_kernel
-// (double precision), the Langevin update draws the same Philox4x32-10 numbers as integrate_kernel.  Only __syncthreads
-// separates the phases of a step: no grid synchronisation, no global counters, no per-step kernel launches.
+// One thread block owns one replica for a whole launch of `nsteps` MD steps.  Positions, velocities, the noise of the
+// step and every force contribution live in shared memory; two __syncthreads per step are the only synchronisation: no
+// grid synchronisation, no global counters, no per-step kernel launches, and NO ATOMICS:
+//   phase 1  the warps of the block share a static list of warp tasks —
+//              pair task    8 beads x 4 lanes: each bead gathers its force from its partners, every pair seen from both
+//                           sides instead of being added atomically.  Partners come from a per-bead Verlet list in shared
+//                           memory (4 interleaved sub-lists per bead, one per lane, one byte per entry), rebuilt by the
+//                           same task from a scan of all beads when any bead has moved half the skin since the last
+//                           build; coefficients from a full n x n table (zero for excluded / non-interacting pairs);
+//              bonded task  32 terms of one kind in FP32 (replica_math.hpp: differences and stiff bond lengths in double,
+//                           everything after that in single precision); each term writes the force on each of its beads
+//                           into its own scratch slot;
+//              noise task   Philox4x32-10 + Box-Muller for 32 beads (the same streams as integrate_kernel);
+//   phase 2  one thread per (bead, component): sum of the bead's scratch slots in a fixed order (static CSR), pair force,
+//            Langevin leap-frog update, master position in double, FP32 pair-kernel position for the next step.
+// Sums run in a fixed order, so a run is bit-reproducible.
 //
-// MEASURED (B200, round 2) and therefore OFF by default (option replica_kernel = 1 turns it on): one SH3 replica steps at
-// 75 k steps/s here against 118 k steps/s through the general path (2 launches per step); 512 replicas 17.2 M against 19.3 M
-// replica-steps/s.  A step of one replica costs ~11 k double-precision warp instructions in its ~480 bonded terms, and one
-// SM issues 0.5 of those per clock: 11 us per step on one SM, where the general path spreads the same terms over 4 SMs.
-// So these small systems are bound by FP64 throughput of the bonded terms, not by launches; a version spreading one replica
-// over a cluster of 8 CTAs (DSMEM) measured 59 k steps/s and was removed.  The lever that remains is FP32 bonded arithmetic.
+// Why this shape (measured on B200, round 2).  The first version of this kernel kept the double-precision bonded terms
+// of force_kernel and accumulated with 64-bit fixed-point atomics: 75 k steps/s for one SH3 replica against 118 k through
+// the general path (2 launches per step), 17.2 M against 19.3 M replica-steps/s for 512 replicas.  A step of one replica
+// cost ~11 k FP64 warp instructions in its ~480 bonded terms, and shared-memory atomics cost 2 cycles per LANE
+// (64-bit ones are a compare-and-swap loop).  Hence FP32 bonded arithmetic and gather instead of scatter.
 //
 // What it stands for on the reference side: Simulator::run's integrator->step(save_step) (src/Simulator.cpp:55-60) for the
 // small AICG2+ samples (sample/toml_input/sh3_AICG2+.toml); OpenMM launches 10-20 kernels per step for such a system.
 #pragma once
 #include "kernels.cuh"
+#include "replica_math.hpp"
 
 namespace ocm {
 
 constexpr int kRepMaxLists = 6;
 constexpr int kRepBlock = 256;
+constexpr int kRepNbMax = 16;        // entries per (bead, lane) sub-list of the in-kernel Verlet lists; overflow = scan every step
+constexpr float kRepSkin = 0.2f;     // nm
+constexpr int kRepTaskPair = 100;    // RepTask::kind: 0..8 = bonded kind, 100 + l = pair list l, 200 = noise
+constexpr int kRepTaskNoise = 200;
 
-// static pair table of one pair list of ONE replica: every participant pair that is neither excluded nor forbidden by the
-// interaction classes, with its coefficients (two-zone 12-6: the entry of PairListDev::tabF; screened Coulomb: K q_i q_j)
+// one pair list of ONE replica: full coefficient table (two-zone 12-6: the entry of PairListDev::tabF; screened
+// Coulomb: K q_i q_j); zero rows / entries for beads that do not take part, excluded pairs and the diagonal
 struct RepList {
-    int npairs, form, has_switch, pad;
-    float rc2, k_in, rsw, inv_sw, inv_debye;
-    const ushort2* ij;     // local bead indices, i < j
-    const float4* coef;
+    int form, has_switch;
+    float rc2, rl2, k_in, rsw, inv_sw, inv_debye;   // rl2 = (cutoff + kRepSkin)^2
+    const float4* coef;    // [nper * nper]
 };
+
+struct RepBonded {
+    int n, npar, slot0, pad;        // terms, parameters per term, first scratch slot: slot(m, body) = slot0 + body * n + m
+    const unsigned short* idx;      // nbody * n local bead indices
+    const float* par;               // npar * n
+    const double* r0;               // kinds 0, 1, 3: equilibrium length (r - r0 is taken in double), else null
+    const unsigned short* tab;      // table index per term (kinds 5 and 8), else null
+};
+
+struct RepTask { int kind, m0; };
 
 struct RepParams {
-    int nper, nrep, nlists, periodic_unused;
+    int nper, nrep, nlists, ntasks, nslots, ncsr;
     RepList lists[kRepMaxLists];
-    BondedDev bonded[10];  // local bead indices (B_NUM_KINDS entries)
+    RepBonded bonded[9];
+    const float* tabs;              // 24 floats per table
+    const RepTask* tasks;
+    const int* csr_off;             // [nper + 1]
+    const unsigned short* csr_slot; // scratch slots of each bead, ordered by (kind, term, body)
     double dt;
-    float a, b, c;         // Langevin coefficients (StepParams)
+    float a, b, c;                  // Langevin coefficients (StepParams)
     unsigned int seed_lo, seed_hi;
-    const uint2* rep_seed; // per-replica noise keys or null
+    const uint2* rep_seed;          // per-replica noise keys or null
 };
+
+// dynamic shared memory of one block: xf, vs (float4), xs (double 3n), origin (double 3), fpair, noise, xref (float 3n each),
+// scratch (float 3 nslots), csr (ushort), Verlet sub-list counts and entries (bytes)
+__host__ __device__ inline size_t rep_smem_bytes(int nper, int nlists, int nslots, int ncsr) {
+    return (size_t)nper * (16 + 16 + 24 + 12 * (size_t)nlists + 12 + 12) + 24 + 12 * (size_t)nslots + 2 * (size_t)((ncsr + 1) & ~1)
+           + (size_t)nlists * nper * 4 * (1 + kRepNbMax);
+}
 
 // two-zone 12-6 force over r (tz_pair of kernels.cuh, one pair, no votes)
 __device__ __forceinline__ float rep_pair_tz(const RepList& L, const float4 c, float r2) {
@@ -62,95 +97,201 @@ __device__ __forceinline__ float rep_pair_tz(const RepList& L, const float4 c, f
     return fr;
 }
 
-// Forces are accumulated with fire-and-forget 64-bit integer atomics on the engine's global accumulator (L2): 64-bit adds
-// on SHARED memory compile to a compare-and-swap spin loop (ATOMS.CAST.SPIN), which under ~40 contributions per address
-// and step made the step 4 x slower than the arithmetic.
+__device__ __forceinline__ float rep_pair_force(const RepList& L, const float4 c, float r2) {
+    if (L.form == SEG_PAIR_DH) {
+        const float ir = fast_rsqrt(r2), r = r2 * ir;
+        return c.x * __expf(-r * L.inv_debye) * (ir + L.inv_debye) * ir * ir;
+    }
+    return rep_pair_tz(L, c, r2);
+}
+
+__device__ __forceinline__ repmath::V3<float> rep_diff(const double* __restrict__ xs, int i, int j) {
+    return {(float)(xs[3 * i] - xs[3 * j]), (float)(xs[3 * i + 1] - xs[3 * j + 1]), (float)(xs[3 * i + 2] - xs[3 * j + 2])};
+}
+__device__ __forceinline__ void rep_put(float* __restrict__ scratch, int nslots, int slot, const repmath::V3<float>& f) {
+    scratch[slot] = f.x; scratch[nslots + slot] = f.y; scratch[2 * nslots + slot] = f.z;
+}
+
+// 32 terms of bonded kind KIND (compile-time: the switch in repmath::eval folds away)
+template <int KIND>
+__device__ __forceinline__ void rep_bonded_task(const RepParams& R, int m, const double* __restrict__ xs, float* __restrict__ scratch) {
+    using namespace repmath;
+    const RepBonded& B = R.bonded[KIND];
+    if (m >= B.n) return;
+    float p[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) p[k] = (k < B.npar) ? __ldg(&B.par[(size_t)m * B.npar + k]) : 0.f;
+    const float* tab = (KIND == 5 || KIND == 8) ? R.tabs + 24 * (int)__ldg(&B.tab[m]) : R.tabs;
+    const int ns = R.nslots, s0 = B.slot0 + m;
+    if (KIND <= 3) {
+        const int i = __ldg(&B.idx[2 * m]), j = __ldg(&B.idx[2 * m + 1]);
+        const double dx = xs[3 * i] - xs[3 * j], dy = xs[3 * i + 1] - xs[3 * j + 1], dz = xs[3 * i + 2] - xs[3 * j + 2];
+        const V3<float> d = {(float)dx, (float)dy, (float)dz};
+        float r, dq = 0.f;
+        if (KIND == 0 || KIND == 1 || KIND == 3) {
+            const double rd = sqrt(dx * dx + dy * dy + dz * dz);
+            r = (float)rd; dq = (float)(rd - __ldg(&B.r0[m]));
+        } else r = sqrtf(dot(d, d));
+        V3<float> fi;
+        bond<float>(KIND, p, tab, d, r, dq, fi);
+        rep_put(scratch, ns, s0, fi);
+        rep_put(scratch, ns, s0 + B.n, {-fi.x, -fi.y, -fi.z});
+    } else if (KIND <= 5) {
+        const int i = __ldg(&B.idx[3 * m]), j = __ldg(&B.idx[3 * m + 1]), k = __ldg(&B.idx[3 * m + 2]);
+        V3<float> fi, fk;
+        angle<float>(KIND, p, tab, rep_diff(xs, i, j), rep_diff(xs, k, j), fi, fk);
+        rep_put(scratch, ns, s0, fi);
+        rep_put(scratch, ns, s0 + B.n, {-fi.x - fk.x, -fi.y - fk.y, -fi.z - fk.z});
+        rep_put(scratch, ns, s0 + 2 * B.n, fk);
+    } else {
+        const int i = __ldg(&B.idx[4 * m]), j = __ldg(&B.idx[4 * m + 1]), k = __ldg(&B.idx[4 * m + 2]), l = __ldg(&B.idx[4 * m + 3]);
+        V3<float> f1, f2, f3, f4;
+        dihedral<float>(KIND, p, tab, rep_diff(xs, i, j), rep_diff(xs, j, k), rep_diff(xs, l, k), f1, f2, f3, f4);
+        rep_put(scratch, ns, s0, f1);
+        rep_put(scratch, ns, s0 + B.n, f2);
+        rep_put(scratch, ns, s0 + 2 * B.n, f3);
+        rep_put(scratch, ns, s0 + 3 * B.n, f4);
+    }
+}
+
 __global__ void __launch_bounds__(kRepBlock) replica_step_kernel(const __grid_constant__ RepParams R, double* __restrict__ x_g, float4* __restrict__ v_g,
-                                                                 unsigned long long* __restrict__ fbuf, int n_total, unsigned long long step0, int nsteps,
-                                                                 int* __restrict__ flags) {
+                                                                 unsigned long long step0, int nsteps, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char rep_smem[];
-    const int n = R.nper, rep = blockIdx.x, tid = threadIdx.x;
-    double* xs = reinterpret_cast<double*>(rep_smem);                              // [3n] master positions
-    float4* vs = reinterpret_cast<float4*>(xs + 3 * n);                             // [n] velocities, w = 1/m
-    float4* xf = vs + n;                                                            // [n] FP32 offsets from the replica's origin
-    unsigned long long* fb = fbuf + (size_t)rep * n;                                // this replica's slice: fb[q * n_total + i]
-    __shared__ double origin[3];
+    const int n = R.nper, rep = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4* xf = reinterpret_cast<float4*>(rep_smem);              // [n] FP32 offsets from the replica's origin
+    float4* vs = xf + n;                                           // [n] velocities, w = 1/m
+    double* xs = reinterpret_cast<double*>(vs + n);                // [3n] master positions
+    double* origin = xs + 3 * n;                                   // [3]
+    float* fpair = reinterpret_cast<float*>(origin + 3);           // [nlists][3][n] pair forces
+    float* noise = fpair + 3 * n * R.nlists;                       // [3][n] unit normals of the step
+    float* xref = noise + 3 * n;                                   // [3][n] xf when the Verlet lists were built
+    float* scratch = xref + 3 * n;                                 // [3][nslots] bonded force contributions
+    unsigned short* csr = reinterpret_cast<unsigned short*>(scratch + 3 * R.nslots);   // [ncsr] scratch slots bead by bead
+    unsigned char* nbcnt = reinterpret_cast<unsigned char*>(csr + ((R.ncsr + 1) & ~1));   // [nlists][n][4] sub-list lengths
+    unsigned char* nb = nbcnt + R.nlists * n * 4;                  // [nlists][n][4][kRepNbMax] partners
+    __shared__ int rebuild[2];   // [step parity]: scan all pairs and rebuild the Verlet lists in this step
+    __shared__ int nb_overflow;  // a sub-list overflowed: scan in every step from now on
     __shared__ int bad;
     for (int k = tid; k < 3 * n; k += kRepBlock) xs[k] = x_g[(size_t)3 * n * rep + k];
     for (int i = tid; i < n; i += kRepBlock) vs[i] = v_g[(size_t)n * rep + i];
-    if (tid == 0) bad = 0;
+    for (int k = tid; k < R.ncsr; k += kRepBlock) csr[k] = R.csr_slot[k];
+    if (tid == 0) { bad = 0; rebuild[0] = 1; rebuild[1] = 0; nb_overflow = 0; }
+    const float disp_max = 0.5f * kRepSkin * 0.57735f;   // per component: |d| <= sqrt(3) max_q |d_q|
     const uint2 key = R.rep_seed ? R.rep_seed[rep] : make_uint2(R.seed_lo, R.seed_hi);
-    // the bonded device functions read a StepParams: n is the stride of the accumulator, the box is unused (unlimited boundary)
-    StepParams P{};
-    P.n = n_total; P.periodic = 0;
-    for (int k = 0; k < 3; k++) { P.box[k] = 1.0; P.inv_box[k] = 1.0; }
-    P.role = nullptr;
     __syncthreads();
     for (int s = 0; s < nsteps; s++) {
-        // ---- FP32 pair-kernel positions relative to the replica's centroid (refreshed every 256 steps) ----
+        // ---- FP32 pair-kernel positions relative to the replica's centroid (moved every 256 steps) ----
         if ((s & 255) == 0) {
             if (tid < 3) {
                 double c = 0;
                 for (int i = 0; i < n; i++) c += xs[3 * i + tid];
                 origin[tid] = c / n;
             }
+            if (tid == 0) rebuild[s & 1] = 1;   // (the reference positions of the lists are in the old frame)
+            __syncthreads();
+            for (int i = tid; i < n; i += kRepBlock)
+                xf[i] = make_float4((float)(xs[3 * i] - origin[0]), (float)(xs[3 * i + 1] - origin[1]), (float)(xs[3 * i + 2] - origin[2]), 0.f);
             __syncthreads();
         }
-        for (int i = tid; i < n; i += kRepBlock)
-            xf[i] = make_float4((float)(xs[3 * i] - origin[0]), (float)(xs[3 * i + 1] - origin[1]), (float)(xs[3 * i + 2] - origin[2]), 0.f);
-        __syncthreads();
-        // ---- pair terms: the static table of every list ----
-        for (int l = 0; l < R.nlists; l++) {
-            const RepList& L = R.lists[l];
-            for (int p = tid; p < L.npairs; p += kRepBlock) {
-                const ushort2 ij = __ldg(&L.ij[p]);
-                const float4 pi = xf[ij.x], pj = xf[ij.y];
-                const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
-                const float r2 = norm2(dx, dy, dz);
-                if (!(r2 < L.rc2)) continue;
-                const float4 c = __ldg(&L.coef[p]);
-                float fr;
-                if (L.form == SEG_PAIR_DH) {
-                    const float ir = fast_rsqrt(r2), r = r2 * ir;
-                    fr = c.x * __expf(-r * L.inv_debye) * (ir + L.inv_debye) * ir * ir;
-                } else fr = rep_pair_tz(L, c, r2);
-                const float fx = fr * dx, fy = fr * dy, fz = fr * dz;
-                const long long qx = (long long)(fx * 4294967296.0f), qy = (long long)(fy * 4294967296.0f), qz = (long long)(fz * 4294967296.0f);
-                atomicAdd(&fb[ij.x], (unsigned long long)qx); atomicAdd(&fb[n_total + ij.x], (unsigned long long)qy); atomicAdd(&fb[2 * (size_t)n_total + ij.x], (unsigned long long)qz);
-                atomicAdd(&fb[ij.y], (unsigned long long)(-qx)); atomicAdd(&fb[n_total + ij.y], (unsigned long long)(-qy)); atomicAdd(&fb[2 * (size_t)n_total + ij.y], (unsigned long long)(-qz));
-            }
-        }
-        // ---- bonded terms (double precision on the master positions) ----
-#pragma unroll 1
-        for (int kind = 0; kind < 10; kind++) {
-            const BondedDev& B = R.bonded[kind];
-            for (int m = tid; m < B.n; m += kRepBlock) { int g; bonded_term(kind, B, m, P, xs, fb, &g); }
-        }
-        __threadfence();   // the atomics of this block are performed at L2 before anybody reads the sums
-        __syncthreads();
-        // ---- leap-frog Langevin update (integrate_kernel, same noise stream) ----
         const unsigned long long step = step0 + (unsigned long long)s;
-        for (int i = tid; i < n; i += kRepBlock) {
-            const float inv32 = 2.3283064365386963e-10f;
-            const float fx = (float)(long long)__ldcg(&fb[i]) * inv32, fy = (float)(long long)__ldcg(&fb[n_total + i]) * inv32,
-                        fz = (float)(long long)__ldcg(&fb[2 * (size_t)n_total + i]) * inv32;
-            __stcg(&fb[i], 0ull); __stcg(&fb[n_total + i], 0ull); __stcg(&fb[2 * (size_t)n_total + i], 0ull);
-            float4 vi = vs[i];
-            const float im = vi.w;
-            if (im > 0.f) {
-                float g0, g1, g2;
-                normals3(philox4x32_10(make_uint4((unsigned int)i, (unsigned int)step, (unsigned int)(step >> 32), 0u), key), g0, g1, g2);
-                const float cs = R.c * sqrtf(im), bm = R.b * im;
-                vi.x = R.a * vi.x + bm * fx + cs * g0;
-                vi.y = R.a * vi.y + bm * fy + cs * g1;
-                vi.z = R.a * vi.z + bm * fz + cs * g2;
-                vs[i] = vi;
-                const double px = xs[3 * i] + (double)vi.x * R.dt, py = xs[3 * i + 1] + (double)vi.y * R.dt, pz = xs[3 * i + 2] + (double)vi.z * R.dt;
-                xs[3 * i] = px; xs[3 * i + 1] = py; xs[3 * i + 2] = pz;
-                if (!(px == px) || !(py == py) || !(pz == pz) || !(fx == fx)) bad = 1;
+        const bool scan = rebuild[s & 1] != 0;   // (written before the last barrier; cleared after the next one)
+        // ---- phase 1: warp tasks ----
+        for (int t = warp; t < R.ntasks; t += kRepBlock / 32) {
+            const RepTask task = R.tasks[t];
+            if (task.kind >= kRepTaskNoise) {
+                const int i = task.m0 + lane;
+                if (i < n) {
+                    float g0, g1, g2;
+                    normals3(philox4x32_10(make_uint4((unsigned int)i, (unsigned int)step, (unsigned int)(step >> 32), 0u), key), g0, g1, g2);
+                    noise[i] = g0; noise[n + i] = g1; noise[2 * n + i] = g2;
+                }
+            } else if (task.kind >= kRepTaskPair) {
+                const int l = task.kind - kRepTaskPair;
+                const RepList& L = R.lists[l];
+                const int i = task.m0 + (lane >> 2), sub = lane & 3;
+                float fx = 0.f, fy = 0.f, fz = 0.f;
+                if (i < n) {
+                    const float4 pi = xf[i];
+                    const float4* __restrict__ crow = L.coef + (size_t)i * n;
+                    unsigned char* my_nb = nb + ((size_t)(l * n + i) * 4 + sub) * kRepNbMax;
+                    if (scan) {
+                        // all beads: forces inside the cutoff, partners inside cutoff + skin into this lane's sub-list
+                        int cnt = 0;
+                        for (int j = sub; j < n; j += 4) {
+                            const float4 pj = xf[j];
+                            const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
+                            const float r2 = norm2(dx, dy, dz);
+                            if (r2 < L.rl2 && j != i) {
+                                const float4 c = __ldg(&crow[j]);
+                                if (c.x == 0.f && c.y == 0.f) continue;   // excluded, not interacting
+                                if (cnt < kRepNbMax) my_nb[cnt] = (unsigned char)j; else nb_overflow = 1;
+                                cnt++;
+                                if (r2 < L.rc2) {
+                                    const float fr = rep_pair_force(L, c, r2);
+                                    fx = fmaf(fr, dx, fx); fy = fmaf(fr, dy, fy); fz = fmaf(fr, dz, fz);
+                                }
+                            }
+                        }
+                        nbcnt[(l * n + i) * 4 + sub] = (unsigned char)min(cnt, kRepNbMax);
+                        if (sub == 0 && l == 0) { xref[i] = pi.x; xref[n + i] = pi.y; xref[2 * n + i] = pi.z; }
+                    } else {
+                        const int cnt = nbcnt[(l * n + i) * 4 + sub];
+                        for (int k = 0; k < cnt; k++) {
+                            const int j = my_nb[k];
+                            const float4 pj = xf[j];
+                            const float4 c = __ldg(&crow[j]);
+                            const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
+                            const float r2 = norm2(dx, dy, dz);
+                            if (r2 < L.rc2) {
+                                const float fr = rep_pair_force(L, c, r2);
+                                fx = fmaf(fr, dx, fx); fy = fmaf(fr, dy, fy); fz = fmaf(fr, dz, fz);
+                            }
+                        }
+                    }
+                }
+                fx += __shfl_xor_sync(0xffffffffu, fx, 1); fy += __shfl_xor_sync(0xffffffffu, fy, 1); fz += __shfl_xor_sync(0xffffffffu, fz, 1);
+                fx += __shfl_xor_sync(0xffffffffu, fx, 2); fy += __shfl_xor_sync(0xffffffffu, fy, 2); fz += __shfl_xor_sync(0xffffffffu, fz, 2);
+                if (i < n && sub == 0) { float* fp = fpair + 3 * n * l; fp[i] = fx; fp[n + i] = fy; fp[2 * n + i] = fz; }
+            } else {
+                const int m = task.m0 + lane;
+                switch (task.kind) {
+                    case 0: rep_bonded_task<0>(R, m, xs, scratch); break;
+                    case 1: rep_bonded_task<1>(R, m, xs, scratch); break;
+                    case 2: rep_bonded_task<2>(R, m, xs, scratch); break;
+                    case 3: rep_bonded_task<3>(R, m, xs, scratch); break;
+                    case 4: rep_bonded_task<4>(R, m, xs, scratch); break;
+                    case 5: rep_bonded_task<5>(R, m, xs, scratch); break;
+                    case 6: rep_bonded_task<6>(R, m, xs, scratch); break;
+                    case 7: rep_bonded_task<7>(R, m, xs, scratch); break;
+                    default: rep_bonded_task<8>(R, m, xs, scratch);
+                }
             }
         }
-        __threadfence();   // the cleared accumulator is visible before the next step's atomics
+        __syncthreads();
+        if (tid == 0) rebuild[s & 1] = 0;
+        if (tid == 1 && nb_overflow) rebuild[(s + 1) & 1] = 1;
+        // ---- phase 2: one thread per (component, bead): fixed-order force sum, leap-frog Langevin update ----
+        for (int t = tid; t < 3 * n; t += kRepBlock) {
+            const int q = t / n, i = t - q * n;
+            float f = 0.f;
+            for (int l = 0; l < R.nlists; l++) f += fpair[3 * n * l + t];
+            const float* __restrict__ sc = scratch + q * R.nslots;
+            const int c0 = __ldg(&R.csr_off[i]), c1 = __ldg(&R.csr_off[i + 1]);
+#pragma unroll 4
+            for (int e = c0; e < c1; e++) f += sc[csr[e]];
+            float* vp = reinterpret_cast<float*>(vs + i);
+            const float im = vp[3];
+            if (im > 0.f) {
+                const float vq = R.a * vp[q] + (R.b * im) * f + (R.c * sqrtf(im)) * noise[t];
+                vp[q] = vq;
+                const double px = xs[3 * i + q] + (double)vq * R.dt;
+                xs[3 * i + q] = px;
+                const float xq = (float)(px - origin[q]);
+                reinterpret_cast<float*>(xf + i)[q] = xq;
+                if (fabsf(xq - xref[t]) > disp_max) rebuild[(s + 1) & 1] = 1;
+                if (!(px == px) || !(f == f)) bad = 1;
+            }
+        }
         __syncthreads();
         if (bad) break;  // (block-uniform: read after the barrier)
     }

@@ -244,7 +244,8 @@ int  ocm_get_roles(ocm_context*, unsigned char* role);
  *   "pair_kernel" (-1 = by size (default): cluster-pair tile lists for pair lists of >= 131 072 beads, Verlet rows below;
  *                  1 = tiles wherever possible (periodic or virtual box, single system, >= 1024 beads in the list); 0 = rows),
  *   "tile_blocks" (blocks of the persistent tile force launch per list, 0 = one wave),
- *   "replica_kernel" (1 = whole-step persistent kernel for small unlimited-boundary systems / replica batches; 0 default),
+ *   "replica_kernel" (1 (default) = whole-step persistent kernel, one thread block per replica, for unlimited-boundary systems of
+ *                  <= 256 beads without donor-acceptor terms, alone or as a replica batch; 0 = general path),
  *   "pdl" (programmatic dependent launch of the per-step kernels: 0 off, 1, 2; no gain inside CUDA graphs),
  *   "phase_timing" (CUDA events between the phases of a step; counters "phase_ms.rebuild|force|integrate|halo"),
  *   slab contexts: "halo_capacity", "halo_push" (1 = per-step halo over NVLink peer memory, 0 = ncclSend/ncclRecv),

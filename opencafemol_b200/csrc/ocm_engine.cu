@@ -215,7 +215,8 @@ struct ocm_context {
     // whole-step persistent kernel for small unlimited-boundary systems and replica ensembles (replica_kernels.cuh)
     ocm_system sys1;                        // the system of ONE replica (replica batches keep it beside the replicated tables)
     bool rep_ok = false;
-    int rep_opt = 0;                        // option "replica_kernel": 1 = use it where possible, 0 (default) = general path
+    int rep_block = 256;                    // threads per block of the replica kernel (compile_replica_tables)
+    int rep_opt = 1;                        // option "replica_kernel": 1 (default) = use it where possible, 0 = general path
     RepParams rep{};
     size_t rep_smem = 0;
     std::vector<std::unique_ptr<DevBuf<unsigned char>>> rep_blobs;   // its static tables (compile_replica_tables)
@@ -861,18 +862,15 @@ static void compile_replica_tables(ocm_context* c) {
     }
     // bonded terms of one replica, kind by kind: local bead indices, FP32 parameters, own table numbering
     std::vector<float> tabs(24, 0.f);
-    std::vector<std::vector<unsigned short>> slots_of_bead(nper);
-    int nslots = 0;
+    std::vector<RepTerm> rec[9];
+    std::vector<int> nslot_of_bead(nper, 0);
     for (int k = 0; k < 9; k++) {
-        std::vector<unsigned short> idx, tab;
-        std::vector<float> par;
-        std::vector<double> r0;
         int npar = 0;
         const int nbody = bonded_nbody(k);
         for (const auto& t : S1.bonded) {
             if (t.kind != k || t.n() == 0) continue;
             if (t.periodic) return;
-            if (npar && npar != t.npar) return;
+            if ((npar && npar != t.npar) || t.npar > 5) return;
             npar = t.npar;
             int tab_id = 0;
             if (k == B_FLEX_ANGLE || k == B_FLEX_DIHEDRAL) {
@@ -880,55 +878,55 @@ static void compile_replica_tables(ocm_context* c) {
                 if (tab_id >= 65536) return;
                 for (int q = 0; q < 24; q++) tabs.push_back((float)t.tab[q]);
             }
-            for (int v : t.idx) idx.push_back((unsigned short)v);
-            for (double v : t.p) par.push_back((float)v);
             for (int64_t m = 0; m < t.n(); m++) {
-                tab.push_back((unsigned short)tab_id);
-                if (k == B_HARMONIC_BOND) r0.push_back(t.p[(size_t)m * t.npar + 0]);
-                else if (k == B_GAUSSIAN_BOND) r0.push_back(t.p[(size_t)m * t.npar + 1]);
-                else if (k == B_3SPN2_BOND) r0.push_back(t.p[(size_t)m * t.npar + 2]);
+                RepTerm r{};
+                for (int b = 0; b < nbody; b++) { r.idx[b] = (unsigned short)t.idx[(size_t)m * nbody + b]; nslot_of_bead[r.idx[b]]++; }
+                r.tab = (unsigned short)tab_id;
+                for (int q = 0; q < t.npar; q++) r.p[q] = (float)t.p[(size_t)m * t.npar + q];
+                if (k == B_HARMONIC_BOND) r.r0 = t.p[(size_t)m * t.npar + 0];
+                else if (k == B_GAUSSIAN_BOND) r.r0 = t.p[(size_t)m * t.npar + 1];
+                else if (k == B_3SPN2_BOND) r.r0 = t.p[(size_t)m * t.npar + 2];
+                rec[k].push_back(r);
             }
         }
-        RepBonded& B = R.bonded[k];
-        B = RepBonded{};
-        B.n = (int)(idx.size() / nbody); B.npar = npar; B.slot0 = nslots;
-        if (npar > 5) return;
-        if (B.n) {
-            B.idx = rep_upload(c, idx); B.par = rep_upload(c, par);
-            B.r0 = rep_upload(c, r0);
-            B.tab = (k == B_FLEX_ANGLE || k == B_FLEX_DIHEDRAL) ? rep_upload(c, tab) : nullptr;
-            for (int m = 0; m < B.n; m++)
-                for (int b = 0; b < nbody; b++) {
-                    const int slot = nslots + b * B.n + m;
-                    if (slot >= 65536) return;
-                    slots_of_bead[idx[(size_t)m * nbody + b]].push_back((unsigned short)slot);
-                }
-            nslots += nbody * B.n;
+        R.bonded[k] = RepBonded{};
+        R.bonded[k].n = (int)rec[k].size(); R.bonded[k].npar = npar;
+        for (int m0 = 0; m0 < (int)rec[k].size(); m0 += 32) tasks.push_back({k, m0});
+    }
+    // scratch slots: contribution number p to bead i (in (kind, term, body) order) lives in slot p * nper + i
+    const int nslots = nper * std::max(1, *std::max_element(nslot_of_bead.begin(), nslot_of_bead.end()));
+    if (nslots >= 65536) return;
+    {
+        std::vector<int> fill(nper, 0);
+        for (int k = 0; k < 9; k++) {
+            const int nbody = bonded_nbody(k);
+            for (auto& r : rec[k])
+                for (int b = 0; b < nbody; b++) r.slot[b] = (unsigned short)(fill[r.idx[b]]++ * nper + r.idx[b]);
+            if (!rec[k].empty()) R.bonded[k].rec = reinterpret_cast<const uint4*>(rep_upload(c, rec[k]));
         }
     }
-    // warp tasks, long ones first (pair gathers are already in): dihedrals, angles, noise, bonds
-    const int order[9] = {8, 6, 7, 5, 4, 2, 1, 3, 0};
-    for (int q = 0; q < 4; q++)
-        for (int m0 = 0; m0 < R.bonded[order[q]].n; m0 += 32) tasks.push_back({order[q], m0});
     for (int i0 = 0; i0 < nper; i0 += 32) tasks.push_back({kRepTaskNoise, i0});
-    for (int q = 4; q < 9; q++)
-        for (int m0 = 0; m0 < R.bonded[order[q]].n; m0 += 32) tasks.push_back({order[q], m0});
-    std::vector<int> csr_off(nper + 1, 0);
-    std::vector<unsigned short> csr_slot;
-    for (int i = 0; i < nper; i++) {
-        csr_off[i] = (int)csr_slot.size();
-        csr_slot.insert(csr_slot.end(), slots_of_bead[i].begin(), slots_of_bead[i].end());
-    }
-    csr_off[nper] = (int)csr_slot.size();
-    if (csr_slot.empty()) csr_slot.push_back(0);
-    R.nslots = nslots; R.ntasks = (int)tasks.size(); R.ncsr = (int)csr_slot.size();
+    // Threads per block: a block is one replica.  An ensemble that fills the GPU runs 256-thread blocks (several per SM);
+    // a few replicas get up to 1024 threads each, so that every warp has one task and a step is as short as its longest task.
+    c->rep_block = c->nrep > 296 ? 256 : (c->nrep > 148 ? 512 : 1024);
+    while (c->rep_block > 256 && c->rep_block / 32 >= 2 * (int)tasks.size()) c->rep_block /= 2;
+    // warp w runs tasks w, w + nwarps, ... of this list: longest first (estimated warp instructions per task, from the SASS of the
+    // kinds: FLD 380, gaussian / cosine dihedral 340, FLA 260, a walk over a bead group's Verlet lists 250, harmonic angle 200,
+    // noise 170, bonds 140-160, 12-10 contact 110)
+    auto cost = [](int kind) {
+        static const int bonded_cost[9] = {140, 160, 110, 150, 200, 260, 340, 340, 380};
+        return kind >= kRepTaskNoise ? 170 : (kind >= kRepTaskPair ? 250 : bonded_cost[kind]);
+    };
+    std::stable_sort(tasks.begin(), tasks.end(), [&](const RepTask& a, const RepTask& b) { return cost(a.kind) > cost(b.kind); });
+    R.nslots = nslots; R.ntasks = (int)tasks.size();
     R.tabs = rep_upload(c, tabs); R.tasks = rep_upload(c, tasks);
-    R.csr_off = rep_upload(c, csr_off); R.csr_slot = rep_upload(c, csr_slot);
+    R.nslot_of_bead = rep_upload(c, nslot_of_bead);
     R.rep_seed = c->nrep > 1 ? c->d_rep_seed.p : nullptr;
-    c->rep_smem = rep_smem_bytes(nper, R.nlists, nslots, R.ncsr);
+    c->rep_smem = rep_smem_bytes(nper, R.nlists, nslots);
     if (c->rep_smem > 96 * 1024) return;   // (scratch slots of a few thousand terms: beyond that the general path)
-    CUDA_TRY(cudaFuncSetAttribute(replica_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(c->rep_smem, 1024)));
-    CUDA_TRY(cudaFuncSetAttribute(replica_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    auto* kern = c->rep_block == 256 ? replica_step_kernel<256> : (c->rep_block == 512 ? replica_step_kernel<512> : replica_step_kernel<1024>);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(c->rep_smem, 1024)));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     c->rep_ok = true;
 }
 
@@ -1549,7 +1547,8 @@ static void do_steps_replica_kernel(ocm_context* c, int64_t nsteps) {
     // (launches of at most 65 536 steps: a block holds its replica for the whole launch)
     for (int64_t done = 0; done < nsteps;) {
         const int chunk = (int)std::min<int64_t>(65536, nsteps - done);
-        replica_step_kernel<<<c->nrep, kRepBlock, c->rep_smem, s>>>(R, c->x.p, c->v.p, (unsigned long long)(c->step + done), chunk, c->flags.p);
+        auto* kern = c->rep_block == 256 ? replica_step_kernel<256> : (c->rep_block == 512 ? replica_step_kernel<512> : replica_step_kernel<1024>);
+        kern<<<c->nrep, c->rep_block, c->rep_smem, s>>>(R, c->x.p, c->v.p, (unsigned long long)(c->step + done), chunk, c->flags.p);
         c->n_launches += 1; c->n_rep_launches += 1;
         done += chunk;
     }
@@ -2134,9 +2133,9 @@ int ocm_context_set_option(ocm_context* c, const char* key, double value) {
         c->lists_ready = false; c->lists_current = false;
         drop_graphs(c);
     } else if (k == "replica_kernel") {
-        // 1: small unlimited-boundary systems and replica ensembles step in the whole-step persistent kernel; 0 (default: it measured
-        // slower, see replica_kernels.cuh): general path
-        c->rep_opt = (int)value;
+        // 1 (default): small unlimited-boundary systems and replica ensembles step in the whole-step persistent kernel (measured on
+        // B200: 2 x the general path for one SH3 replica, 4 x for 512, see replica_kernels.cuh); 0: general path
+        c->rep_opt = value != 0 ? 1 : 0;
     } else if (k == "tile_debug") {
         // timing experiments only (wrong forces): see TileLaunch::debug; 4 = evaluate the list without its switching function
         c->tile_debug = (int)value;

@@ -4,7 +4,8 @@
 // One thread block owns one replica for a whole launch of `nsteps` MD steps.  Positions, velocities, the noise of the
 // step and every force contribution live in shared memory; two __syncthreads per step are the only synchronisation: no
 // grid synchronisation, no global counters, no per-step kernel launches, and NO ATOMICS:
-//   phase 1  the warps of the block share a static list of warp tasks —
+//   phase 1  warp w runs the warp tasks w, w + nwarps, ... of a static list sorted longest first (drawing tasks from a shared
+//            atomic counter instead measured 6 % slower for 512 replicas: with 4 blocks per SM the other blocks fill the gaps) —
 //              pair task    8 beads x 4 lanes: each bead gathers its force from its partners, every pair seen from both
 //                           sides instead of being added atomically.  Partners come from a per-bead Verlet list in shared
 //                           memory (4 interleaved sub-lists per bead, one per lane, one byte per entry), rebuilt by the
@@ -12,9 +13,10 @@
 //                           build; coefficients from a full n x n table (zero for excluded / non-interacting pairs);
 //              bonded task  32 terms of one kind in FP32 (replica_math.hpp: differences and stiff bond lengths in double,
 //                           everything after that in single precision); each term writes the force on each of its beads
-//                           into its own scratch slot;
+//                           into its own scratch slot (slot = position in the bead's list * n + bead: beads that are
+//                           neighbours along the chain are neighbours in memory, writes and reads without bank conflicts);
 //              noise task   Philox4x32-10 + Box-Muller for 32 beads (the same streams as integrate_kernel);
-//   phase 2  one thread per (bead, component): sum of the bead's scratch slots in a fixed order (static CSR), pair force,
+//   phase 2  one thread per (bead, component): sum of the bead's scratch slots in a fixed order, pair force,
 //            Langevin leap-frog update, master position in double, FP32 pair-kernel position for the next step.
 // Sums run in a fixed order, so a run is bit-reproducible.
 //
@@ -33,7 +35,8 @@
 namespace ocm {
 
 constexpr int kRepMaxLists = 6;
-constexpr int kRepBlock = 256;
+constexpr int kRepBlockMax = 1024;   // threads per block: 256 for ensembles that fill the GPU, up to 1024 for a few replicas
+constexpr int kRepMaxWarps = kRepBlockMax / 32;
 constexpr int kRepNbMax = 16;        // entries per (bead, lane) sub-list of the in-kernel Verlet lists; overflow = scan every step
 constexpr float kRepSkin = 0.2f;     // nm
 constexpr int kRepTaskPair = 100;    // RepTask::kind: 0..8 = bonded kind, 100 + l = pair list l, 200 = noise
@@ -47,35 +50,39 @@ struct RepList {
     const float4* coef;    // [nper * nper]
 };
 
+// one bonded term: 48 bytes, fetched with three 16-byte loads
+struct RepTerm {
+    unsigned short idx[4];          // local bead indices (nbody used)
+    unsigned short slot[4];         // scratch slot of the force on each of them
+    float p[5];
+    unsigned short tab, pad;        // table index (kinds 5 and 8)
+    double r0;                      // kinds 0, 1, 3: equilibrium length (r - r0 is taken in double)
+};
+static_assert(sizeof(RepTerm) == 48, "RepTerm layout");
 struct RepBonded {
-    int n, npar, slot0, pad;        // terms, parameters per term, first scratch slot: slot(m, body) = slot0 + body * n + m
-    const unsigned short* idx;      // nbody * n local bead indices
-    const float* par;               // npar * n
-    const double* r0;               // kinds 0, 1, 3: equilibrium length (r - r0 is taken in double), else null
-    const unsigned short* tab;      // table index per term (kinds 5 and 8), else null
+    int n, npar;                    // terms, parameters per term
+    const uint4* rec;               // [3 n] RepTerm records
 };
 
 struct RepTask { int kind, m0; };
 
 struct RepParams {
-    int nper, nrep, nlists, ntasks, nslots, ncsr;
+    int nper, nrep, nlists, ntasks, nslots;   // nslots = nper * (largest number of bonded contributions to one bead)
     RepList lists[kRepMaxLists];
     RepBonded bonded[9];
     const float* tabs;              // 24 floats per table
-    const RepTask* tasks;
-    const int* csr_off;             // [nper + 1]
-    const unsigned short* csr_slot; // scratch slots of each bead, ordered by (kind, term, body)
+    const RepTask* tasks;           // longest first; warp w runs tasks w, w + nwarps, ...
+    const int* nslot_of_bead;       // [nper] bonded contributions to each bead: its slots are p * nper + bead, p < that number
     double dt;
     float a, b, c;                  // Langevin coefficients (StepParams)
     unsigned int seed_lo, seed_hi;
     const uint2* rep_seed;          // per-replica noise keys or null
 };
 
-// dynamic shared memory of one block: xf, vs (float4), xs (double 3n), origin (double 3), fpair, noise, xref (float 3n each),
-// scratch (float 3 nslots), csr (ushort), Verlet sub-list counts and entries (bytes)
-__host__ __device__ inline size_t rep_smem_bytes(int nper, int nlists, int nslots, int ncsr) {
-    return (size_t)nper * (16 + 16 + 24 + 12 * (size_t)nlists + 12 + 12) + 24 + 12 * (size_t)nslots + 2 * (size_t)((ncsr + 1) & ~1)
-           + (size_t)nlists * nper * 4 * (1 + kRepNbMax);
+// dynamic shared memory of one block: xf, vs (float4 n), scratch (float 3 nslots), xs (double 3n), origin (double 3), fpair,
+// noise, xref (float 3n each), Verlet sub-list counts and entries (bytes)
+__host__ __device__ inline size_t rep_smem_bytes(int nper, int nlists, int nslots) {
+    return (size_t)nper * (16 + 16 + 24 + 12 * (size_t)nlists + 12 + 12) + 24 + 12 * (size_t)nslots + (size_t)nlists * nper * 4 * (1 + kRepNbMax);
 }
 
 // two-zone 12-6 force over r (tz_pair of kernels.cuh, one pair, no votes)
@@ -118,67 +125,70 @@ __device__ __forceinline__ void rep_bonded_task(const RepParams& R, int m, const
     using namespace repmath;
     const RepBonded& B = R.bonded[KIND];
     if (m >= B.n) return;
-    float p[5];
-#pragma unroll
-    for (int k = 0; k < 5; k++) p[k] = (k < B.npar) ? __ldg(&B.par[(size_t)m * B.npar + k]) : 0.f;
-    const float* tab = (KIND == 5 || KIND == 8) ? R.tabs + 24 * (int)__ldg(&B.tab[m]) : R.tabs;
-    const int ns = R.nslots, s0 = B.slot0 + m;
+    union { uint4 q[3]; RepTerm t; } u;
+    u.q[0] = __ldg(&B.rec[3 * m]); u.q[1] = __ldg(&B.rec[3 * m + 1]); u.q[2] = __ldg(&B.rec[3 * m + 2]);
+    const float* p = u.t.p;
+    const float* tab = R.tabs + 24 * (int)u.t.tab;
+    const int ns = R.nslots;
     if (KIND <= 3) {
-        const int i = __ldg(&B.idx[2 * m]), j = __ldg(&B.idx[2 * m + 1]);
+        const int i = u.t.idx[0], j = u.t.idx[1];
         const double dx = xs[3 * i] - xs[3 * j], dy = xs[3 * i + 1] - xs[3 * j + 1], dz = xs[3 * i + 2] - xs[3 * j + 2];
         const V3<float> d = {(float)dx, (float)dy, (float)dz};
         float r, dq = 0.f;
         if (KIND == 0 || KIND == 1 || KIND == 3) {
             const double rd = sqrt(dx * dx + dy * dy + dz * dz);
-            r = (float)rd; dq = (float)(rd - __ldg(&B.r0[m]));
+            r = (float)rd; dq = (float)(rd - u.t.r0);
         } else r = sqrtf(dot(d, d));
         V3<float> fi;
         bond<float>(KIND, p, tab, d, r, dq, fi);
-        rep_put(scratch, ns, s0, fi);
-        rep_put(scratch, ns, s0 + B.n, {-fi.x, -fi.y, -fi.z});
+        rep_put(scratch, ns, u.t.slot[0], fi);
+        rep_put(scratch, ns, u.t.slot[1], {-fi.x, -fi.y, -fi.z});
     } else if (KIND <= 5) {
-        const int i = __ldg(&B.idx[3 * m]), j = __ldg(&B.idx[3 * m + 1]), k = __ldg(&B.idx[3 * m + 2]);
+        const int i = u.t.idx[0], j = u.t.idx[1], k = u.t.idx[2];
         V3<float> fi, fk;
         angle<float>(KIND, p, tab, rep_diff(xs, i, j), rep_diff(xs, k, j), fi, fk);
-        rep_put(scratch, ns, s0, fi);
-        rep_put(scratch, ns, s0 + B.n, {-fi.x - fk.x, -fi.y - fk.y, -fi.z - fk.z});
-        rep_put(scratch, ns, s0 + 2 * B.n, fk);
+        rep_put(scratch, ns, u.t.slot[0], fi);
+        rep_put(scratch, ns, u.t.slot[1], {-fi.x - fk.x, -fi.y - fk.y, -fi.z - fk.z});
+        rep_put(scratch, ns, u.t.slot[2], fk);
     } else {
-        const int i = __ldg(&B.idx[4 * m]), j = __ldg(&B.idx[4 * m + 1]), k = __ldg(&B.idx[4 * m + 2]), l = __ldg(&B.idx[4 * m + 3]);
+        const int i = u.t.idx[0], j = u.t.idx[1], k = u.t.idx[2], l = u.t.idx[3];
         V3<float> f1, f2, f3, f4;
         dihedral<float>(KIND, p, tab, rep_diff(xs, i, j), rep_diff(xs, j, k), rep_diff(xs, l, k), f1, f2, f3, f4);
-        rep_put(scratch, ns, s0, f1);
-        rep_put(scratch, ns, s0 + B.n, f2);
-        rep_put(scratch, ns, s0 + 2 * B.n, f3);
-        rep_put(scratch, ns, s0 + 3 * B.n, f4);
+        rep_put(scratch, ns, u.t.slot[0], f1);
+        rep_put(scratch, ns, u.t.slot[1], f2);
+        rep_put(scratch, ns, u.t.slot[2], f3);
+        rep_put(scratch, ns, u.t.slot[3], f4);
     }
 }
 
-__global__ void __launch_bounds__(kRepBlock) replica_step_kernel(const __grid_constant__ RepParams R, double* __restrict__ x_g, float4* __restrict__ v_g,
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 5 : (NT == 512 ? 2 : 1)) replica_step_kernel(const __grid_constant__ RepParams R, double* __restrict__ x_g, float4* __restrict__ v_g,
                                                                  unsigned long long step0, int nsteps, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char rep_smem[];
-    const int n = R.nper, rep = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = R.nper, rep = blockIdx.x, tid = threadIdx.x, lane = tid & 31, nthr = NT;
     float4* xf = reinterpret_cast<float4*>(rep_smem);              // [n] FP32 offsets from the replica's origin
     float4* vs = xf + n;                                           // [n] velocities, w = 1/m
-    double* xs = reinterpret_cast<double*>(vs + n);                // [3n] master positions
+    float* scratch = reinterpret_cast<float*>(vs + n);             // [3][nslots] bonded force contributions, 16-byte aligned
+    double* xs = reinterpret_cast<double*>(scratch + 3 * R.nslots);   // [3n] master positions
     double* origin = xs + 3 * n;                                   // [3]
     float* fpair = reinterpret_cast<float*>(origin + 3);           // [nlists][3][n] pair forces
     float* noise = fpair + 3 * n * R.nlists;                       // [3][n] unit normals of the step
     float* xref = noise + 3 * n;                                   // [3][n] xf when the Verlet lists were built
-    float* scratch = xref + 3 * n;                                 // [3][nslots] bonded force contributions
-    unsigned short* csr = reinterpret_cast<unsigned short*>(scratch + 3 * R.nslots);   // [ncsr] scratch slots bead by bead
-    unsigned char* nbcnt = reinterpret_cast<unsigned char*>(csr + ((R.ncsr + 1) & ~1));   // [nlists][n][4] sub-list lengths
+    unsigned char* nbcnt = reinterpret_cast<unsigned char*>(xref + 3 * n);   // [nlists][n][4] sub-list lengths
     unsigned char* nb = nbcnt + R.nlists * n * 4;                  // [nlists][n][4][kRepNbMax] partners
     __shared__ int rebuild[2];   // [step parity]: scan all pairs and rebuild the Verlet lists in this step
     __shared__ int nb_overflow;  // a sub-list overflowed: scan in every step from now on
     __shared__ int bad;
-    for (int k = tid; k < 3 * n; k += kRepBlock) xs[k] = x_g[(size_t)3 * n * rep + k];
-    for (int i = tid; i < n; i += kRepBlock) vs[i] = v_g[(size_t)n * rep + i];
-    for (int k = tid; k < R.ncsr; k += kRepBlock) csr[k] = R.csr_slot[k];
+    for (int k = tid; k < 3 * n; k += nthr) xs[k] = x_g[(size_t)3 * n * rep + k];
+    for (int i = tid; i < n; i += nthr) vs[i] = v_g[(size_t)n * rep + i];
     if (tid == 0) { bad = 0; rebuild[0] = 1; rebuild[1] = 0; nb_overflow = 0; }
     const float disp_max = 0.5f * kRepSkin * 0.57735f;   // per component: |d| <= sqrt(3) max_q |d_q|
     const uint2 key = R.rep_seed ? R.rep_seed[rep] : make_uint2(R.seed_lo, R.seed_hi);
     __syncthreads();
+    // constants of this thread's first (component, bead) item of phase 2
+    const int q0 = (tid >= n) + (tid >= 2 * n), i0 = min(tid - q0 * n, n - 1);
+    const int cnt0 = __ldg(&R.nslot_of_bead[i0]);
+    const float im0 = vs[i0].w, bm0 = R.b * im0, cs0 = R.c * sqrtf(fmaxf(im0, 0.f));
     for (int s = 0; s < nsteps; s++) {
         // ---- FP32 pair-kernel positions relative to the replica's centroid (moved every 256 steps) ----
         if ((s & 255) == 0) {
@@ -189,14 +199,14 @@ __global__ void __launch_bounds__(kRepBlock) replica_step_kernel(const __grid_co
             }
             if (tid == 0) rebuild[s & 1] = 1;   // (the reference positions of the lists are in the old frame)
             __syncthreads();
-            for (int i = tid; i < n; i += kRepBlock)
+            for (int i = tid; i < n; i += nthr)
                 xf[i] = make_float4((float)(xs[3 * i] - origin[0]), (float)(xs[3 * i + 1] - origin[1]), (float)(xs[3 * i + 2] - origin[2]), 0.f);
             __syncthreads();
         }
         const unsigned long long step = step0 + (unsigned long long)s;
         const bool scan = rebuild[s & 1] != 0;   // (written before the last barrier; cleared after the next one)
         // ---- phase 1: warp tasks ----
-        for (int t = warp; t < R.ntasks; t += kRepBlock / 32) {
+        for (int t = tid >> 5; t < R.ntasks; t += NT / 32) {
             const RepTask task = R.tasks[t];
             if (task.kind >= kRepTaskNoise) {
                 const int i = task.m0 + lane;
@@ -271,18 +281,23 @@ __global__ void __launch_bounds__(kRepBlock) replica_step_kernel(const __grid_co
         if (tid == 0) rebuild[s & 1] = 0;
         if (tid == 1 && nb_overflow) rebuild[(s + 1) & 1] = 1;
         // ---- phase 2: one thread per (component, bead): fixed-order force sum, leap-frog Langevin update ----
-        for (int t = tid; t < 3 * n; t += kRepBlock) {
-            const int q = t / n, i = t - q * n;
+        for (int t = tid; t < 3 * n; t += nthr) {
+            const bool first = t == tid;   // (the first item of a thread: its constants were prepared before the step loop)
+            const int q = first ? q0 : t / n, i = t - q * n;
+            const int cnt = first ? cnt0 : __ldg(&R.nslot_of_bead[i]);
             float f = 0.f;
             for (int l = 0; l < R.nlists; l++) f += fpair[3 * n * l + t];
-            const float* __restrict__ sc = scratch + q * R.nslots;
-            const int c0 = __ldg(&R.csr_off[i]), c1 = __ldg(&R.csr_off[i + 1]);
-#pragma unroll 4
-            for (int e = c0; e < c1; e++) f += sc[csr[e]];
+            const float* __restrict__ sc = scratch + q * R.nslots + i;
+            float f1 = 0.f, f2 = 0.f, f3 = 0.f;
+            int e = 0;
+            for (; e + 4 <= cnt; e += 4) { f += sc[e * n]; f1 += sc[(e + 1) * n]; f2 += sc[(e + 2) * n]; f3 += sc[(e + 3) * n]; }
+            for (; e < cnt; e++) f += sc[e * n];
+            f = (f + f1) + (f2 + f3);
             float* vp = reinterpret_cast<float*>(vs + i);
             const float im = vp[3];
             if (im > 0.f) {
-                const float vq = R.a * vp[q] + (R.b * im) * f + (R.c * sqrtf(im)) * noise[t];
+                const float bm = first ? bm0 : R.b * im, cs = first ? cs0 : R.c * sqrtf(im);
+                const float vq = R.a * vp[q] + bm * f + cs * noise[t];
                 vp[q] = vq;
                 const double px = xs[3 * i + q] + (double)vq * R.dt;
                 xs[3 * i + q] = px;
@@ -295,8 +310,8 @@ __global__ void __launch_bounds__(kRepBlock) replica_step_kernel(const __grid_co
         __syncthreads();
         if (bad) break;  // (block-uniform: read after the barrier)
     }
-    for (int k = tid; k < 3 * n; k += kRepBlock) x_g[(size_t)3 * n * rep + k] = xs[k];
-    for (int i = tid; i < n; i += kRepBlock) v_g[(size_t)n * rep + i] = vs[i];
+    for (int k = tid; k < 3 * n; k += nthr) x_g[(size_t)3 * n * rep + k] = xs[k];
+    for (int i = tid; i < n; i += nthr) v_g[(size_t)n * rep + i] = vs[i];
     if (tid == 0 && bad) flags[FLAG_NAN] = 1;
 }
 

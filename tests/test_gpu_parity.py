@@ -229,9 +229,9 @@ def test_replica_batch_large(engine):
 
 @pytest.mark.parametrize("replicas", [None, 5])
 def test_whole_step_replica_kernel_option(engine, oracle, replicas):
-    """option replica_kernel = 1: the whole MD step of a small system in one persistent kernel, one block per replica
-    (replica_kernels.cuh; off by default because it measured slower).  Same noise streams, so it tracks the oracle like the
-    general path, step by step and across launches."""
+    """option replica_kernel = 1 (the default): the whole MD step of a small system in one persistent kernel, one block per
+    replica (replica_kernels.cuh).  Same noise streams, so it tracks the oracle like the general path, step by step and across
+    launches."""
     spec = load_golden_spec("sh3")
     ctx, ora = ti.make_context(engine, spec, replicas=replicas), ti.make_context(oracle, spec, replicas=replicas)
     ctx.set_option("replica_kernel", 1)
@@ -416,8 +416,8 @@ def test_options_and_counters(engine):
         ctx.set_option("no_such_option", 1)
 
 
-def test_every_bonded_kind_and_interaction_groups(engine, oracle):
-    """Random small system exercising all nine bonded kinds, EXV with interaction groups, 3SPN.2 EXV."""
+def all_kinds_contexts(engine, oracle):
+    """Random small system exercising all nine bonded kinds, EXV with interaction groups, 3SPN.2 EXV: (engine, oracle) contexts."""
     from opencafemol_b200 import tables
     rng = np.random.default_rng(5)
     n = 40
@@ -460,12 +460,63 @@ def test_every_bonded_kind_and_interaction_groups(engine, oracle):
         c = Context(s, 300.0, 0.2, 0.002, seed=11)
         c.set_positions(pos)
         ctxs.append(c)
-    ctx, ora = ctxs
+    return ctxs
 
-    class Spec:
-        group_ids = {str(g): g for g in range(11)}
-    check_state(ctx, ora, Spec)
+
+class AllKindsSpec:
+    group_ids = {str(g): g for g in range(11)}
+
+
+def test_every_bonded_kind_and_interaction_groups(engine, oracle):
+    ctx, ora = all_kinds_contexts(engine, oracle)
+    check_state(ctx, ora, AllKindsSpec)
     check_sets(ctx, ora)
+
+
+def test_whole_step_replica_kernel_all_kinds(engine, oracle):
+    """The whole-step replica kernel (default for small unlimited-boundary systems) on every bonded kind it restates in FP32
+    (replica_math.hpp) and on two pair lists with interaction groups, against the oracle under the same noise, and against
+    the general path (option replica_kernel = 0)."""
+    ctx, ora = all_kinds_contexts(engine, oracle)
+    gen, _ = all_kinds_contexts(engine, oracle)
+    assert ctx.get_option("replica_kernel") == 1
+    gen.set_option("replica_kernel", 0)
+    for c in (ctx, ora, gen):
+        c.set_velocities_to_temperature(300.0, 3)
+    ctx.step(1); ora.step(1); gen.step(1)
+    a, b, g = (c.get_state(positions=True, velocities=True) for c in (ctx, ora, gen))
+    # one step from identical states under identical noise: the velocity difference is dt/m times the force difference
+    assert np.abs(a["velocities"] - b["velocities"]).max() < 2e-6
+    assert np.abs(g["velocities"] - b["velocities"]).max() < 2e-6
+    ctx.step(29); ora.step(29); gen.step(29)
+    a, b, g = (c.get_state(positions=True, velocities=True) for c in (ctx, ora, gen))
+    assert ctx.counter("replica_kernel_launches") == 2 and gen.counter("replica_kernel_launches") == 0
+    assert np.abs(a["positions"] - b["positions"]).max() < 2e-5
+    assert np.abs(g["positions"] - b["positions"]).max() < 2e-5
+    check_state(ctx, ora, AllKindsSpec, ftol=5e-3, etol=5e-3)   # (own states: differ by the accumulated FP32 drift)
+
+
+def test_whole_step_replica_kernel_is_reproducible_and_rebuilds_its_lists(engine, oracle):
+    """Two runs of the replica kernel give the same bits (fixed summation order, no atomics on data), and a run long enough for
+    beads to cross the kernel's Verlet skin (in-kernel list rebuilds) still tracks a run that scans all pairs every step
+    (skin 0: option replica_kernel = 0 is the general path with its own lists)."""
+    spec = load_golden_spec("sh3")
+    a, b = ti.make_context(engine, spec, replicas=3), ti.make_context(engine, spec, replicas=3)
+    for c in (a, b):
+        c.step(1500); c.step(2500)   # (the same calls: a launch re-centres its FP32 frame at its first step)
+    xa, xb = a.get_state(positions=True)["positions"], b.get_state(positions=True)["positions"]
+    assert np.array_equal(xa, xb)
+    # forces at the end state against the oracle (the kernel's own lists played no part in them) and energies finite
+    ora = ti.make_context(oracle, spec, replicas=3)
+    ora.set_positions(xa)
+    fa, fb = a.get_state(forces=True)["forces"], ora.get_state(forces=True)["forces"]
+    assert force_error(fa, fb).max() < FORCE_TOL
+    # the general path from the same start, same noise: chaotic divergence over 4000 steps is bounded by the thermal scale, but
+    # the first 200 steps must agree closely
+    c, d = ti.make_context(engine, spec, replicas=3), ti.make_context(engine, spec, replicas=3)
+    d.set_option("replica_kernel", 0)
+    c.step(200); d.step(200)
+    assert np.abs(c.get_state(positions=True)["positions"] - d.get_state(positions=True)["positions"]).max() < 1e-4
 
 
 def test_c3_nucleosome_grid(engine, oracle):

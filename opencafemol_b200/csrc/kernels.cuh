@@ -500,8 +500,11 @@ __global__ void rank_fill_kernel(const PairListDev* lists, int li, const uint4* 
 //   B : r^2 < zone_c2   switching region / cutoff shell
 //   C : the rest of the skin                                      (warp-uniform vote skips everything)
 // count_only: just record the neighbour count (used to size the list).  zoned == 0: no shared memory, one zone.
-template <bool PER>
-__global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P, int* __restrict__ flags, int count_only, int zoned) {
+// DH / CLS: compile-time copies of L.form == SEG_PAIR_DH and L.cls != null.  The candidate loop is the cost of a rebuild (C2: 63
+// groups of 32 candidates per bead): everything it needs from the list descriptor is hoisted into registers before it, and the
+// per-zone counts are kept per lane and summed once (ncu, round 2: 195 -> ~70 warp instructions per candidate group).
+template <bool PER, bool DH, bool CLS>
+__global__ void __launch_bounds__(256) build_list_kernel(const PairListDev* lists, int li, StepParams P, int* __restrict__ flags, int count_only, int zoned) {
     extern __shared__ __align__(16) unsigned int bl_smem[];
     const PairListDev& L = lists[li];
     const int lane = threadIdx.x & 31;
@@ -510,7 +513,10 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
     if (w >= list_rows(L)) return;
     const GridDev& g = *L.grid;
     const uint4* __restrict__ spos = L.spos;
-    const bool dh = L.form == SEG_PAIR_DH;
+    const int* __restrict__ excl_idx = L.excl_idx;
+    const signed char* __restrict__ cls = L.cls;
+    const int* __restrict__ sslots = L.sorted_slots;
+    const int* __restrict__ bor = L.bead_of_rank;
     const int a = L.sorted_slots[w];
     if (L.role && L.role[L.part[a]] != 1) {
         // halo bead: present as a partner only, its own row stays empty (its owner computes its forces)
@@ -524,7 +530,7 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
     const int ci = cig - cell_base;
     const int cx = ci % ncx, cy = (ci / ncx) % ncy, cz = ci / (ncx * ncy);
     const int e0 = L.excl_off[a], e1 = L.excl_off[a + 1];
-    const unsigned int my_allow = L.cls ? L.allow[(int)L.cls[a]] : 0xffffffffu;
+    const unsigned int my_allow = CLS ? L.allow[(int)L.cls[a]] : 0xffffffffu;
     const float rl2 = L.rlist2, za2 = L.zone_a2, zb2 = L.zone_b2, zc2 = L.zone_c2;
     const int stride = L.stride;
     unsigned int* row = L.nbr + (size_t)w * stride;
@@ -533,6 +539,8 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
     unsigned int* s_row = bl_smem + (size_t)wib * stride;
     unsigned char* s_zone = reinterpret_cast<unsigned char*>(bl_smem + (size_t)wpb * stride) + (size_t)wib * stride;
     int count = 0, cz0 = 0, cz1 = 0, cz2 = 0;
+    int n0 = 0, n1 = 0, n2 = 0;   // this lane's accepted entries per zone
+    const unsigned int lt = (1u << lane) - 1u;
 
     int nz, ny, z0, y0;
     if (PER) { nz = min(5, ncz); z0 = (ncz >= 5) ? cz - 2 : 0; ny = min(5, ncy); y0 = (ncy >= 5) ? cy - 2 : 0; }
@@ -594,8 +602,41 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
         }
     }
     // the first four exclusions of this bead live in registers
-    const int ex0 = (e0 < e1) ? L.excl_idx[e0] : -1, ex1 = (e0 + 1 < e1) ? L.excl_idx[e0 + 1] : -1;
-    const int ex2 = (e0 + 2 < e1) ? L.excl_idx[e0 + 2] : -1, ex3 = (e0 + 3 < e1) ? L.excl_idx[e0 + 3] : -1;
+    const int ex0 = (e0 < e1) ? excl_idx[e0] : -1, ex1 = (e0 + 1 < e1) ? excl_idx[e0 + 1] : -1;
+    const int ex2 = (e0 + 2 < e1) ? excl_idx[e0 + 2] : -1, ex3 = (e0 + 3 < e1) ? excl_idx[e0 + 3] : -1;
+    const bool more_excl = e0 + 4 < e1;
+
+    // one group of 32 candidates: lane's candidate k (rank in the cell-sorted order) with its position pj; ke = end of the run
+    auto group = [&](const int k, const uint4 pj, const int ke) {
+        bool ok = false;
+        unsigned int entry = 0;
+        int zone = 3;
+        if (k < ke && k != w) {
+            float dx, dy, dz;
+            delta<PER>(pi, pj, P.fscale, dx, dy, dz);
+            const float r2 = norm2(dx, dy, dz);
+            if (r2 < rl2) {
+                ok = true;
+                if (CLS) ok = (my_allow >> (int)cls[sslots[k]]) & 1u;
+                const int j = DH ? bor[k] : (int)(pj.w & 0xFFFFFFu);
+                ok = ok && j != ex0 && j != ex1 && j != ex2 && j != ex3;
+                if (more_excl) for (int e = e0 + 4; ok && e < e1; e++) ok = excl_idx[e] != j;
+                entry = DH ? (unsigned int)k : ((unsigned int)k | (pj.w & 0xFF000000u));
+                zone = (r2 < za2) ? 0 : (r2 < zb2) ? 1 : (r2 < zc2) ? 2 : 3;
+            }
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, ok);
+        if (m == 0u) return;
+        if (!count_only) {
+            const int pos = count + __popc(m & lt);
+            if (ok && pos < stride) {
+                if (stage) { s_row[pos] = entry; s_zone[pos] = (unsigned char)zone; }
+                else row[pos] = entry;
+            }
+            if (ok) { n0 += (zone == 0); n1 += (zone == 1); n2 += (zone == 2); }
+        }
+        count += __popc(m);
+    };
 
     for (int r = 0; r < 2 * nrows; r++) {
         const int kb = __shfl_sync(0xffffffffu, (r & 1) ? kb1 : kb0, r >> 1);
@@ -604,47 +645,17 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
             // two 32-candidate groups per iteration: both position loads are in flight together
             const int ka = k0 + lane, kbb = k0 + 32 + lane;
             uint4 pja = make_uint4(0, 0, 0, 0), pjb = make_uint4(0, 0, 0, 0);
-            if (ka < ke) pja = spos[ka];
-            if (kbb < ke) pjb = spos[kbb];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int k = h ? kbb : ka;
-                const uint4 pj = h ? pjb : pja;
-                if (h && k0 + 32 >= ke) break;  // warp-uniform
-                bool ok = false;
-                unsigned int entry = 0;
-                int zone = 3;
-                if (k < ke && k != w) {
-                    float dx, dy, dz;
-                    delta<PER>(pi, pj, P.fscale, dx, dy, dz);
-                    const float r2 = norm2(dx, dy, dz);
-                    if (r2 < rl2) {
-                        ok = true;
-                        if (L.cls) ok = (my_allow >> (int)L.cls[L.sorted_slots[k]]) & 1u;
-                        const int j = dh ? L.bead_of_rank[k] : (int)(pj.w & 0xFFFFFFu);
-                        ok = ok && j != ex0 && j != ex1 && j != ex2 && j != ex3;
-                        for (int e = e0 + 4; ok && e < e1; e++) ok = L.excl_idx[e] != j;
-                        entry = dh ? (unsigned int)k : ((unsigned int)k | (pj.w & 0xFF000000u));
-                        zone = (r2 < za2) ? 0 : (r2 < zb2) ? 1 : (r2 < zc2) ? 2 : 3;
-                    }
-                }
-                const unsigned int m = __ballot_sync(0xffffffffu, ok);
-                if (m == 0u) continue;
-                if (!count_only) {
-                    const int pos = count + __popc(m & ((1u << lane) - 1u));
-                    if (ok && pos < stride) {
-                        if (stage) { s_row[pos] = entry; s_zone[pos] = (unsigned char)zone; }
-                        else row[pos] = entry;
-                    }
-                    if (stage) {
-                        cz0 += __popc(__ballot_sync(0xffffffffu, ok && zone == 0));
-                        cz1 += __popc(__ballot_sync(0xffffffffu, ok && zone == 1));
-                        cz2 += __popc(__ballot_sync(0xffffffffu, ok && zone == 2));
-                    }
-                }
-                count += __popc(m);
-            }
+            if (ka < ke) pja = __ldg(&spos[ka]);
+            if (kbb < ke) pjb = __ldg(&spos[kbb]);
+            group(ka, pja, ke);
+            if (k0 + 32 < ke) group(kbb, pjb, ke);   // warp-uniform
         }
+    }
+    if (stage) {
+        for (int o = 16; o > 0; o >>= 1) {
+            n0 += __shfl_xor_sync(0xffffffffu, n0, o); n1 += __shfl_xor_sync(0xffffffffu, n1, o); n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        }
+        cz0 = n0; cz1 = n1; cz2 = n2;
     }
     if (count_only) {
         if (lane == 0) { L.nbr_count[w] = count; atomicMax(&flags[FLAG_MAXDISP + 1], count); }
@@ -664,7 +675,6 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
             const bool live = t < count;
             const unsigned int e = live ? s_row[t] : 0u;
             const int z = live ? (int)s_zone[t] : -1;
-            const unsigned int lt = (1u << lane) - 1u;
             const unsigned int m0 = __ballot_sync(0xffffffffu, z == 0), m1 = __ballot_sync(0xffffffffu, z == 1);
             const unsigned int m2 = __ballot_sync(0xffffffffu, z == 2), m3 = __ballot_sync(0xffffffffu, z == 3);
             if (z == 0) row[off0 + __popc(m0 & lt)] = e;
@@ -677,7 +687,7 @@ __global__ void build_list_kernel(const PairListDev* lists, int li, StepParams P
     // pad the row to a multiple of 32 with the self entry (distance 0, never interacts): the T = 32 force paths
     // read whole 32-entry groups
     const int pad = count + lane;
-    if (pad < ((count + 31) & ~31) && pad < stride) row[pad] = dh ? (unsigned int)w : ((unsigned int)w | (pi.w & 0xFF000000u));
+    if (pad < ((count + 31) & ~31) && pad < stride) row[pad] = DH ? (unsigned int)w : ((unsigned int)w | (pi.w & 0xFF000000u));
     if (lane == 0) { L.nbr_count[w] = count; L.nbr_inner[w] = n_inner; }
 }
 

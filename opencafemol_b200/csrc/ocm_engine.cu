@@ -1173,14 +1173,23 @@ static void read_flags(ocm_context* c, int* fl) {
 }
 
 // the list-build launch: rows are staged in shared memory (8 warps x stride x 5 bytes) to be written out in zone order
+typedef void (*BuildListKernel)(const PairListDev*, int, StepParams, int*, int, int);
+static BuildListKernel build_list_variant(bool per, bool dh, bool cls) {
+    static const BuildListKernel tab[8] = {
+        build_list_kernel<false, false, false>, build_list_kernel<false, false, true>, build_list_kernel<false, true, false>,
+        build_list_kernel<false, true, true>,   build_list_kernel<true, false, false>, build_list_kernel<true, false, true>,
+        build_list_kernel<true, true, false>,   build_list_kernel<true, true, true>};
+    return tab[(per ? 4 : 0) + (dh ? 2 : 0) + (cls ? 1 : 0)];
+}
+
 static void launch_build(ocm_context* c, PairListHost& L, int li, cudaStream_t s, bool count_only) {
     const size_t bytes = (size_t)8 * L.stride * 5 + 16;
     const int zoned = (!count_only && L.stride > 0 && bytes <= 160 * 1024) ? 1 : 0;
     const size_t smem = zoned ? bytes : 0;
     // one warp per row; under a slab decomposition only the rows the force launch covers (more rows than that: overflow flag)
     const int rows = (c->dd && !count_only && L.dev.row_capacity > 0) ? L.dev.row_capacity : L.np;
-    if (c->periodic) build_list_kernel<true><<<nblk(rows * 32, 256), 256, smem, s>>>(c->d_lists.p, li, c->P, c->flags.p, count_only ? 1 : 0, zoned);
-    else build_list_kernel<false><<<nblk(rows * 32, 256), 256, smem, s>>>(c->d_lists.p, li, c->P, c->flags.p, count_only ? 1 : 0, zoned);
+    auto* kern = build_list_variant(c->periodic, L.form == SEG_PAIR_DH, L.dev.cls != nullptr);
+    kern<<<nblk(rows * 32, 256), 256, smem, s>>>(c->d_lists.p, li, c->P, c->flags.p, count_only ? 1 : 0, zoned);
 }
 
 // sort the beads of one list into cells and build its pair list (Verlet rows or cluster-pair tiles)
@@ -1934,8 +1943,8 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
     CUDA_TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
-    CUDA_TRY(cudaFuncSetAttribute(build_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 16));
-    CUDA_TRY(cudaFuncSetAttribute(build_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 16));
+    for (int v = 0; v < 8; v++)
+        CUDA_TRY(cudaFuncSetAttribute(build_list_variant(v & 4, v & 2, v & 1), cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 16));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_obs, cudaEventDisableTiming));
     for (int b = 0; b < 2; b++) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_obs_done[b], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_in_free, cudaEventDisableTiming));

@@ -1485,13 +1485,14 @@ __global__ void integrate_kernel(StepParams P, double* __restrict__ x, float4* _
             }
             q.w = 0;
             posq[i] = q;
-            // refresh the cell-sorted copies the pair kernels read (w keeps bead | type)
+            // refresh the cell-sorted copies the pair kernels read; w (bead | type, or the mixing parameter of a tile list) is not
+            // touched: an 8-byte and a 4-byte store instead of a load - modify - store of 16 bytes (one dependent L2 round trip less)
             for (int l = 0; l < nlists; l++) {
                 const int k = lists[l].rank_of_bead[i];
                 if (k >= 0) {
                     uint4* sp = lists[l].spos + k;
-                    q.w = sp->w;
-                    *sp = q;
+                    *reinterpret_cast<uint2*>(sp) = make_uint2(q.x, q.y);
+                    sp->z = q.z;
                 }
             }
             const float ex = (float)(px - xref[3 * i]), ey = (float)(py - xref[3 * i + 1]), ez = (float)(pz - xref[3 * i + 2]);

@@ -179,6 +179,15 @@ int ocm_system_add_lj_repulsive(ocm_system*, int group, double rc, const double*
  * interaction groups) */
 int ocm_system_add_wca(ocm_system*, int group, double rc, const double* eps, const double* sigma,
                        const ocm_pair_topology* topo);
+/* Attractive wells of the lipid model: E = -e for r < b, -e f((r - b) / w) for b <= r < b + w, 0 beyond; b = 2^(1/6) s;
+ * e GEOMETRIC mean, s and w (omega) arithmetic means; pairs beyond rc contribute nothing (the reference's cutoffs, below,
+ * are handed over as they are: Trigonometric's lies inside b + w for unequal sigmas, and the energy jumps there as in OpenMM).
+ *   iSoLF:          f(u) = cos^2(pi u / 2)       iSoLFAttractiveForceFieldGenerator.cpp:41-50, cutoff :129-134
+ *   Trigonometric:  f(u) = 1 + 2 u^3 - 3 u^2     TrigonometricForceFieldGenerator.cpp:43-53, cutoff :119-123 */
+int ocm_system_add_isolf_attractive(ocm_system*, int group, double rc, const double* eps, const double* sigma,
+                                    const double* omega, const ocm_pair_topology* topo);
+int ocm_system_add_trigonometric(ocm_system*, int group, double rc, const double* eps, const double* sigma,
+                                 const double* omega, const ocm_pair_topology* topo);
 /* E = e (step(r - 2^(1/6) s) 4((s/r)^12-(s/r)^6) - step(2^(1/6) s - r)), OpenMM switching
  * function on [r_switch, rc]             LennardJonesAttractiveForceFieldGenerator.cpp:38-123 */
 int ocm_system_add_lj_attractive(ocm_system*, int group, double rc, double r_switch,

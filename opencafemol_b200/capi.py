@@ -162,6 +162,8 @@ class Library:
         ),
         "system_add_lj_repulsive": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _f64p, _f64p, C.POINTER(PairTopologyStruct)]),
         "system_add_wca": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _f64p, _f64p, C.POINTER(PairTopologyStruct)]),
+        "system_add_isolf_attractive": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _f64p, _f64p, _f64p, C.POINTER(PairTopologyStruct)]),
+        "system_add_trigonometric": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _f64p, _f64p, _f64p, C.POINTER(PairTopologyStruct)]),
         "system_add_lj_attractive": (
             C.c_int,
             [C.c_void_p, C.c_int, C.c_double, C.c_double, _f64p, _f64p, C.POINTER(PairTopologyStruct)],
@@ -421,6 +423,18 @@ class System:
         e, sg = self._per_bead(eps), self._per_bead(sigma)
         self.lib.check(self.lib.fn["system_add_wca"](self.handle, int(group), float(rc), _p(e, _f64p), _p(sg, _f64p), C.byref(s)))
         self.pair_terms.append("WeeksChandlerAndersen")
+
+    def add_isolf_attractive(self, group, rc, eps, sigma, omega, topo: PairTopology):
+        s, keep = topo.to_struct()
+        e, sg, om = self._per_bead(eps), self._per_bead(sigma), self._per_bead(omega)
+        self.lib.check(self.lib.fn["system_add_isolf_attractive"](self.handle, int(group), float(rc), _p(e, _f64p), _p(sg, _f64p), _p(om, _f64p), C.byref(s)))
+        self.pair_terms.append("iSoLFAttractive")
+
+    def add_trigonometric(self, group, rc, eps, sigma, omega, topo: PairTopology):
+        s, keep = topo.to_struct()
+        e, sg, om = self._per_bead(eps), self._per_bead(sigma), self._per_bead(omega)
+        self.lib.check(self.lib.fn["system_add_trigonometric"](self.handle, int(group), float(rc), _p(e, _f64p), _p(sg, _f64p), _p(om, _f64p), C.byref(s)))
+        self.pair_terms.append("Trigonometric")
 
     def add_lj_attractive(self, group, rc, r_switch, eps, sigma, topo: PairTopology):
         s, keep = topo.to_struct()

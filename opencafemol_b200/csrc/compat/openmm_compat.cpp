@@ -149,6 +149,12 @@ const char* kLJAttractive =                                                   //
 const char* kWCA =                                                            // WeeksChandlerAndersenForceFieldGenerator.cpp:34-41
     "step(sigma*2^(1/6)-r)*(4*eps*(sigma_r_12-sigma_r_6)+eps);sigma_r_12=sigma_r_6^2;sigma_r_6=sigma_r^6;sigma_r=sigma/r;"
     "eps=sqrt(eps1*eps2);sigma=(sigma1+sigma2)*0.5";
+const char* kISoLFAttractive =                                                // iSoLFAttractiveForceFieldGenerator.cpp:41-50
+    "-eps*(step(base-r)+step(r-base)*step(base+omega-r)*cos(0.5*pi*(r-base)/omega)^2);base=sigma*2^(1/6);sigma=(sigma1+sigma2)*0.5;"
+    "eps=sqrt(eps1*eps2);omega=(omega1+omega2)*0.5;pi=3.1415926535897932385";
+const char* kTrigonometric =                                                  // TrigonometricForceFieldGenerator.cpp:43-53
+    "-epsilon*(step(threthold+omega-r)+step(r-threthold)*step(threthold+omega-r)*(2*r_th_omeg^3-3*r_th_omeg^2));r_th_omeg=(r-threthold)/omega;"
+    "threthold=sigma*2^(1/6);epsilon=(epsilon1*epsilon2)^(1/2);sigma=(sigma1+sigma2)*0.5;omega=(omega1+omega2)*0.5";
 const char* kUniformWCA =                                                     // UniformWeeksChandlerAndersenForceFieldGenerator.cpp:138-143
     "4*eps*(sigma_r_12-sigma_r_6+0.25);sigma_r_12=sigma_r_6^2;sigma_r_6=sigma_r^6;sigma_r=sigma/r";
 const char* kUniformLJAttractive =                                            // UniformLennardJonesAttractiveForceFieldGenerator.cpp:145-152
@@ -467,6 +473,14 @@ class SystemCompiler {
         } else if (nz.expr == kWCA) {
             expect_names(nz.params, {"sigma", "eps"}, "WCA");
             check(ocm_system_add_wca(out_, g, f.cutoff_, column(f.rows_, 1).data(), column(f.rows_, 0).data(), &pt.t), "WCA");
+        } else if (nz.expr == kISoLFAttractive) {
+            expect_names(nz.params, {"sigma", "eps", "omega"}, "iSoLFAttractive");
+            check(ocm_system_add_isolf_attractive(out_, g, f.cutoff_, column(f.rows_, 1).data(), column(f.rows_, 0).data(), column(f.rows_, 2).data(), &pt.t),
+                  "iSoLFAttractive");
+        } else if (nz.expr == kTrigonometric) {
+            expect_names(nz.params, {"epsilon", "sigma", "omega"}, "Trigonometric");
+            check(ocm_system_add_trigonometric(out_, g, f.cutoff_, column(f.rows_, 0).data(), column(f.rows_, 1).data(), column(f.rows_, 2).data(), &pt.t),
+                  "Trigonometric");
         } else if (nz.expr == kUniformWCA || nz.expr == kUniformLJAttractive) {
             // one sigma / epsilon for every member of the interaction groups (one Force per residue-name pair): hand the
             // engine per-bead arrays that carry the parameter on the members and NaN elsewhere

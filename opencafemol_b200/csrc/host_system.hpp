@@ -35,13 +35,13 @@ struct BondedTerm {
     int64_t n() const { return (int64_t)idx.size() / nbody; }
 };
 
-enum PairKind : int { P_EXV = 0, P_DH, P_LJREP, P_LJATT, P_3SPN2EXV, P_WCA };
+enum PairKind : int { P_EXV = 0, P_DH, P_LJREP, P_LJATT, P_3SPN2EXV, P_WCA, P_ISOLF, P_TRIG };
 
 struct PairTerm {
     int kind, group, periodic;
     double rc, rsw;
     double g0, g1, g2;
-    std::vector<double> p0, p1;             // per bead, NaN = non participant
+    std::vector<double> p0, p1, p2;         // per bead, NaN = non participant (p2: attractive wells only)
     std::vector<int32_t> part;              // ascending participants
     std::vector<std::pair<int32_t, int32_t>> excl;  // sorted unique (i<j)
     std::vector<int32_t> cls;               // interaction class per bead (-1 none)
@@ -129,7 +129,7 @@ inline int add_bonded(ocm_system* s, int kind, int group, int periodic, int64_t 
 // Beads with identical membership over all sets share a class; a class pair interacts if some
 // group has one class in set1 and the other in set2 (CustomNonbondedForce::addInteractionGroup).
 inline int add_pair(ocm_system* s, int kind, int group, double rc, double rsw, double g0, double g1, double g2,
-                    const double* p0, const double* p1, const ocm_pair_topology* topo, const char* what) {
+                    const double* p0, const double* p1, const ocm_pair_topology* topo, const char* what, const double* p2 = nullptr) {
     if (!s) return fail("null system");
     if (group < 0 || group > 31) return fail("force group must be in 0..31");
     if (!topo || !p0) return fail(std::string(what) + ": null argument");
@@ -146,8 +146,9 @@ inline int add_pair(ocm_system* s, int kind, int group, double rc, double rsw, d
     const int n = s->n;
     t.p0.assign(p0, p0 + n);
     if (p1) t.p1.assign(p1, p1 + n); else t.p1 = t.p0;
+    if (p2) t.p2.assign(p2, p2 + n); else t.p2 = t.p0;
     for (int i = 0; i < n; i++)
-        if (std::isnan(t.p0[i]) != std::isnan(t.p1[i]))
+        if (std::isnan(t.p0[i]) != std::isnan(t.p1[i]) || std::isnan(t.p0[i]) != std::isnan(t.p2[i]))
             return fail(std::string(what) + ": incomplete parameter set for a particle");
     if (topo->n_excl < 0 || (topo->n_excl > 0 && !topo->excl_ij)) return fail(std::string(what) + ": bad exclusion list");
     if (check_indices(s, topo->excl_ij, topo->n_excl * 2, what)) return 1;

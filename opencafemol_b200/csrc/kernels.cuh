@@ -23,7 +23,7 @@ constexpr int kBlock = 128;            // threads per block of the force kernel
 constexpr double kFixScale = 4294967296.0;  // force accumulator: 64-bit fixed point, 2^32 per kJ/mol/nm
 constexpr int kMaxMembers = 4;
 
-enum SegKind : int { SEG_PAIR_TZ = 0, SEG_PAIR_DH = 1, SEG_BONDED = 2, SEG_DA = 3 };
+enum SegKind : int { SEG_PAIR_TZ = 0, SEG_PAIR_DH = 1, SEG_BONDED = 2, SEG_DA = 3, SEG_PAIR_WELL = 4 };
 enum FlagSlot : int { FLAG_VIOLATION = 0, FLAG_OVERFLOW = 1, FLAG_TICKET = 2, FLAG_NAN = 3, FLAG_MAXDISP = 4, FLAG_DA_OVERFLOW = 6,
                        // slab decomposition: halo message overflow, a bonded term reaching beyond the halo, largest message (entries)
                        FLAG_DD_OVERFLOW = 7, FLAG_DD_REACH = 8, FLAG_DD_MAXSEND = 9,
@@ -967,6 +967,60 @@ __device__ __forceinline__ void pair_dh_block(const PairListDev& L, int blk, int
     }
 }
 
+// attractive wells (iSoLFAttractiveForceFieldGenerator.cpp:41-50, TrigonometricForceFieldGenerator.cpp:43-53):
+//   E = -eps for r < base, -eps f(u) for 0 <= u = (r - base) / omega < 1, 0 beyond;  f = cos^2(pi u / 2) or 1 + 2 u^3 - 3 u^2.
+// The force acts in the shell only.  Per type pair {base, 1 / omega, amp, shape}:
+//   dE/dr = amp sin(pi u), amp = eps pi / (2 omega)   (shape 0)     dE/dr = amp u (1 - u), amp = 6 eps / omega   (shape 1)
+__device__ __forceinline__ float well_dedr(const float4 c, float r) {
+    const float u = (r - c.x) * c.y;
+    if (!(u > 0.f && u < 1.f)) return 0.f;
+    return c.w == 0.f ? c.z * sinpif(u) : c.z * u * (1.f - u);
+}
+template <bool PER, int T>
+__device__ __forceinline__ void pair_well_block(const PairListDev& L, int blk, int chunk, const StepParams& P,
+                                                unsigned long long* __restrict__ fbuf) {
+    constexpr int G = kBlock / T;
+    const int g = threadIdx.x / T, s = threadIdx.x % T;
+    const uint4* __restrict__ spos = L.spos;
+    const float4* __restrict__ tab = L.tabF;
+    const float rc2 = L.rc2;
+    const int nt = L.ntypes;
+    const int k_lo = blk * chunk, k_hi = min(list_rows(L), k_lo + chunk);
+    for (int base = k_lo; base < k_hi; base += G) {
+        const int k = base + g;
+        const bool active = k < k_hi;
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        unsigned int wi = 0;
+        if (active) {
+            const uint4 pi = spos[k];
+            wi = pi.w;
+            const int trow = (int)(wi >> 24) * nt;
+            const int n = L.nbr_count[k];
+            const unsigned int* __restrict__ row = L.nbr + (size_t)k * L.stride;
+#pragma unroll 2
+            for (int t = s; t < n; t += T) {
+                const unsigned int e = __ldg(&row[t]);
+                const uint4 pj = __ldg(&spos[(int)(e & 0xFFFFFFu)]);
+                float dx, dy, dz;
+                delta<PER>(pi, pj, P.fscale, dx, dy, dz);
+                const float r2 = norm2(dx, dy, dz);
+                if (r2 < rc2 && r2 > 0.f) {
+                    const float ir = fast_rsqrt(r2);
+                    const float fr = -well_dedr(__ldg(&tab[trow + (int)(e >> 24)]), r2 * ir) * ir;
+                    fx = fmaf(fr, dx, fx); fy = fmaf(fr, dy, fy); fz = fmaf(fr, dz, fz);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = T / 2; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        if (active && s == 0) add_force_fixed(fbuf, P.n, (int)(wi & 0xFFFFFFu), fx, fy, fz);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // bonded terms (double precision on the master positions; one thread per term)
 struct D3 { double x, y, z; };
@@ -1380,6 +1434,14 @@ __global__ void __launch_bounds__(kBlock, OCM_FORCE_MINBLOCKS) force_kernel(cons
             case 16: pair_dh_block<PER, 16>(L, blk, sg.chunk, P, fbuf); break;
             default: pair_dh_block<PER, 32>(L, blk, sg.chunk, P, fbuf);
         }
+    } else if (sg.kind == SEG_PAIR_WELL) {
+        const PairListDev& L = lists[sg.id];
+        switch (sg.tpb) {
+            case 4: pair_well_block<PER, 4>(L, blk, sg.chunk, P, fbuf); break;
+            case 8: pair_well_block<PER, 8>(L, blk, sg.chunk, P, fbuf); break;
+            case 16: pair_well_block<PER, 16>(L, blk, sg.chunk, P, fbuf); break;
+            default: pair_well_block<PER, 32>(L, blk, sg.chunk, P, fbuf);
+        }
     } else {
         const BondedDev& B = bonded[sg.id];
         int m = blk * kBlock + threadIdx.x;
@@ -1614,6 +1676,18 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(const WorkSeg* __restric
                     const float ir = rsqrtf(r2), r = r2 * ir;
                     Em[0] += (double)(__uint_as_float(pi.w) * __uint_as_float(pj.w) * (__expf(-r * L.inv_debye) * ir - L.dh_cc));
                 }
+            } else if (sg.kind == SEG_PAIR_WELL) {
+                if (r2 < L.rc2 && r2 > 0.f) {
+                    // {base, 1 / omega, amp, shape}: eps = amp (2 / pi) omega (shape 0), amp omega / 6 (shape 1)
+                    const float4 c = L.tabF[ti];
+                    const double u = ((double)sqrtf(r2) - (double)c.x) * (double)c.y;
+                    const double eps = (c.w == 0.f) ? (double)c.z * 0.63661977236758134 / (double)c.y : (double)c.z / (6.0 * (double)c.y);
+                    if (u < 0.0) Em[0] -= eps;
+                    else if (u < 1.0) {
+                        const double cs = cospi(0.5 * u);
+                        Em[0] -= eps * ((c.w == 0.f) ? cs * cs : 1.0 + u * u * (2.0 * u - 3.0));
+                    }
+                }
             } else {
                 for (int m = 0; m < L.nmem; m++) {
                     if (!(r2 < L.mem_rc2[m])) continue;
@@ -1633,7 +1707,7 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(const WorkSeg* __restric
         if (P.nrep > 1) {
             // this bead's share goes to its replica's slots (full list: each pair is seen twice)
             const int rep = L.bead_of_rank[k] / P.nper;
-            const int nmm = (sg.kind == SEG_PAIR_DH) ? 1 : L.nmem;
+            const int nmm = (sg.kind == SEG_PAIR_TZ) ? L.nmem : 1;
             for (int m = 0; m < nmm; m++) {
                 if (Em[m] != 0.0) atomicAdd(&egroup[rep * 40 + L.mem_group[m]], 0.5 * Em[m]);
                 Em[m] = Ekeep[m];
@@ -1641,7 +1715,7 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(const WorkSeg* __restric
         }
     }
     if (P.nrep > 1) return;
-    const int nm = (sg.kind == SEG_PAIR_DH) ? 1 : L.nmem;
+    const int nm = (sg.kind == SEG_PAIR_TZ) ? L.nmem : 1;
     for (int m = 0; m < nm; m++) block_add(0.5 * Em[m], &egroup[L.mem_group[m]]);  // full list: each pair twice
 }
 

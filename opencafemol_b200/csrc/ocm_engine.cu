@@ -71,7 +71,7 @@ const double kBoltz = 8.31446261815324e-3;  // kJ/mol/K
 
 struct PairListHost {
     std::vector<int> terms;  // member pair terms (indices into sys.pairs)
-    int form = 0;            // SEG_PAIR_TZ / SEG_PAIR_DH
+    int form = 0;            // SEG_PAIR_TZ / SEG_PAIR_DH / SEG_PAIR_WELL
     int np = 0, ntypes = 0, stride = 0, tpb = 8;
     double rc_list = 0;      // largest effective cutoff of the members
     std::vector<double> rc_eff;  // per member
@@ -357,7 +357,7 @@ static void plan_lists(ocm_context* c) {
         if (target < 0) {
             c->lists.emplace_back(new PairListHost());
             target = (int)c->lists.size() - 1;
-            c->lists[target]->form = (pt.kind == P_DH) ? SEG_PAIR_DH : SEG_PAIR_TZ;
+            c->lists[target]->form = (pt.kind == P_DH) ? SEG_PAIR_DH : ((pt.kind == P_ISOLF || pt.kind == P_TRIG) ? SEG_PAIR_WELL : SEG_PAIR_TZ);
         }
         c->term_list[t] = target;
         c->term_member[t] = (int)c->lists[target]->terms.size();
@@ -396,7 +396,7 @@ static uint64_t hilbert_index(uint32_t x, uint32_t y, uint32_t z, int bits) {
 //   3SPN2ExcludedVolume eps (q^6 - 2 q^3) + eps inside sigma    a = sigma/2,  b = sqrt(12 eps_i) (product), alpha 1, beta 1, qz 1
 static void compile_tile_tables(ocm_context* c, PairListHost& L) {
     // (small lists -- a few hundred charged beads -- stay Verlet rows inside the fused launch: a tile launch of their own costs more)
-    L.tile_ok = c->periodic && c->nrep == 1 && L.np >= 1024;
+    L.tile_ok = c->periodic && c->nrep == 1 && L.np >= 1024 && L.form != SEG_PAIR_WELL;   // (wells: Verlet rows only)
     L.tile_auto = L.np >= kTileAutoBeads;
     if (!L.tile_ok) return;
     const auto& pairs = c->sys.pairs;
@@ -467,7 +467,7 @@ static void compile_list(ocm_context* c, PairListHost& L) {
     for (int a = 0; a < L.np && L.form != SEG_PAIR_DH; a++) {
         int i = t0.part[a];
         std::vector<double> key;
-        for (int m = 0; m < nm; m++) { key.push_back(pairs[L.terms[m]].p0[i]); key.push_back(pairs[L.terms[m]].p1[i]); }
+        for (int m = 0; m < nm; m++) { key.push_back(pairs[L.terms[m]].p0[i]); key.push_back(pairs[L.terms[m]].p1[i]); key.push_back(pairs[L.terms[m]].p2[i]); }
         auto it = ids.find(key);
         if (it == ids.end()) {
             if (ids.size() >= 255) throw std::runtime_error("pair term with more than 255 distinct per-bead parameter sets is not supported");
@@ -525,6 +525,23 @@ static void compile_list(ocm_context* c, PairListHost& L) {
         L.qscaled.upload(qs);
         D.qscaled = L.qscaled.p;
         D.inv_debye = (float)(1.0 / t0.g1); D.dh_cc = (float)t0.g2;
+        D.mem_group[0] = t0.group; D.mem_rc2[0] = D.rc2;
+    } else if (L.form == SEG_PAIR_WELL) {
+        // attractive wells: per type pair {base = 2^(1/6) sigma_ij, 1 / omega_ij, amp, shape} (well_dedr in kernels.cuh);
+        // p0 = eps (geometric mean), p1 = sigma, p2 = omega (arithmetic means)
+        if (nm != 1) throw std::runtime_error("internal: unsupported pair-list fusion");
+        std::vector<float4> tf(nt2, make_float4(0, 0, 0, 0));
+        const double pi = 3.1415926535897932385;
+        for (int a = 0; a < nt && !rep_bead.empty(); a++)
+            for (int b = 0; b < nt; b++) {
+                const int i = rep_bead[a], j = rep_bead[b];
+                const double ep = std::sqrt(t0.p0[i] * t0.p0[j]), sg = 0.5 * (t0.p1[i] + t0.p1[j]), om = 0.5 * (t0.p2[i] + t0.p2[j]);
+                if (!(om > 0)) throw std::runtime_error("attractive well: omega must be positive");
+                const double amp = (t0.kind == P_ISOLF) ? ep * pi / (2.0 * om) : 6.0 * ep / om;
+                tf[a * nt + b] = make_float4((float)(sg * std::pow(2.0, 1.0 / 6.0)), (float)(1.0 / om), (float)amp, t0.kind == P_ISOLF ? 0.f : 1.f);
+            }
+        L.tabF.upload(tf);
+        D.k_in = 1.f;
         D.mem_group[0] = t0.group; D.mem_rc2[0] = D.rc2;
     } else {
         // force table: {12 c12, 6 c6, a2, w}; zone factor = r^2 < a2 ? k_in : k_out + k_w w
@@ -829,6 +846,7 @@ static void compile_replica_tables(ocm_context* c) {
     R = RepParams{};
     R.nper = nper; R.nrep = c->nrep; R.nlists = 0;
     std::vector<RepTask> tasks;
+    for (auto& Lp : c->lists) if (Lp->form == SEG_PAIR_WELL) return;
     for (auto& Lp : c->lists) {
         PairListHost& L = *Lp;
         if (L.np == 0) continue;
@@ -1862,6 +1880,19 @@ int ocm_system_add_lj_repulsive(ocm_system* s, int g, double rc, const double* e
     if (!sigma) return fail("lj_repulsive: null sigma");
     return add_pair(s, P_LJREP, g, rc, rc, 0, 0, 0, eps, sigma, topo, "lj_repulsive");
 }
+static int add_well(ocm_system* s, int kind, int g, double rc, const double* eps, const double* sigma, const double* omega,
+                    const ocm_pair_topology* topo, const char* what) {
+    if (!eps || !sigma || !omega) return fail(std::string(what) + ": null parameter array");
+    return add_pair(s, kind, g, rc, rc, 0, 0, 0, eps, sigma, topo, what, omega);
+}
+int ocm_system_add_isolf_attractive(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const double* omega,
+                                    const ocm_pair_topology* topo) {
+    return add_well(s, P_ISOLF, g, rc, eps, sigma, omega, topo, "isolf_attractive");
+}
+int ocm_system_add_trigonometric(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const double* omega,
+                                 const ocm_pair_topology* topo) {
+    return add_well(s, P_TRIG, g, rc, eps, sigma, omega, topo, "trigonometric");
+}
 int ocm_system_add_wca(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
     if (!sigma) return fail("wca: null sigma");
     return add_pair(s, P_WCA, g, rc, rc, 0, 0, 0, eps, sigma, topo, "wca");
@@ -1930,10 +1961,12 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
         }
         for (const auto& t : sys->pairs) {
             PairTerm u = t;
-            u.p0.clear(); u.p1.clear(); u.part.clear(); u.excl.clear(); u.cls.clear();
+            u.p0.clear(); u.p1.clear(); u.p2.clear(); u.part.clear(); u.excl.clear(); u.cls.clear();
             for (int r = 0; r < nrep; r++) {
                 u.p0.insert(u.p0.end(), t.p0.begin(), t.p0.end());
                 u.p1.insert(u.p1.end(), t.p1.begin(), t.p1.end());
+                u.p2.insert(u.p2.end(), t.p2.begin(), t.p2.end());
+            u.p2.insert(u.p2.end(), t.p2.begin(), t.p2.end());
                 u.cls.insert(u.cls.end(), t.cls.begin(), t.cls.end());
                 for (int32_t v : t.part) u.part.push_back(v + r * np);
                 for (auto& e : t.excl) u.excl.emplace_back(e.first + r * np, e.second + r * np);

@@ -830,6 +830,29 @@ def _read_global(spec, gf, topo, periodic, attr):
         mx, sm = _two_largest(sig[has], strict=False)
         rc = (mx + sm) * 0.5 * 2.0 ** (1.0 / 6.0)
         spec.add_term(Term("wca", "WeeksChandlerAndersen", dict(rc=rc, eps=eps, sigma=sig, topo=topo_for(has))))
+    elif pot in ("iSoLFAttractive", "Trigonometric"):
+        # read_toml_isolf_attractive_ff_generator (ReadTOMLForceFieldGenerator.cpp:1434-1492) /
+        # read_toml_trigonometric_ff_generator (:2246-2303); cutoffs of the generators
+        # (iSoLFAttractiveForceFieldGenerator.cpp:129-134: mean of the two largest sigmas * 2^(1/6) + mean of the two largest
+        # omegas; TrigonometricForceFieldGenerator.cpp:119-123: mean of the two largest sigma + omega), "<=" trackers
+        who = "read_toml_isolf_attractive_ff_generator" if pot == "iSoLFAttractive" else "read_toml_trigonometric_ff_generator"
+        eps, sig, om = np.full(n, np.nan), np.full(n, np.nan), np.full(n, np.nan)
+        for p in params:
+            i = _param(p, env, "index") + _param(p, env, "offset", 0)
+            if i >= n:
+                raise RuntimeError(f"[error] {who} : index {i} exceeds the system's largest index {n - 1}.")
+            sig[i] = _param(p, env, "sigma") * NM_PER_ANGSTROM
+            eps[i] = _param(p, env, "epsilon") * KJ_PER_KCAL
+            om[i] = _param(p, env, "omega") * NM_PER_ANGSTROM
+        has = ~np.isnan(sig)
+        if pot == "iSoLFAttractive":
+            ms, ss = _two_largest(sig[has], strict=False)
+            mo, so = _two_largest(om[has], strict=False)
+            rc = (ms + ss) * 0.5 * 2.0 ** (1.0 / 6.0) + (mo + so) * 0.5
+            spec.add_term(Term("isolf_attractive", pot, dict(rc=rc, eps=eps, sigma=sig, omega=om, topo=topo_for(has))))
+        else:
+            mr, sr = _two_largest((sig + om)[has], strict=False)
+            spec.add_term(Term("trigonometric", pot, dict(rc=(mr + sr) * 0.5, eps=eps, sigma=sig, omega=om, topo=topo_for(has))))
     else:
         raise NotImplementedError(f"global force field {pot} is not in scope yet")
 

@@ -68,14 +68,14 @@ struct BondedTerm {
     int64_t n() const { return (int64_t)idx.size() / nbody; }
 };
 
-enum PairKind { P_EXV, P_DH, P_LJREP, P_LJATT, P_3SPN2EXV, P_WCA };
+enum PairKind { P_EXV, P_DH, P_LJREP, P_LJATT, P_3SPN2EXV, P_WCA, P_ISOLF, P_TRIG };
 
 struct PairTerm {
     PairKind kind;
     int group, periodic;
     double rc, rsw;
     double g0, g1, g2;            // global parameters (meaning depends on kind)
-    std::vector<double> p0, p1;   // per-bead parameters (NaN = not a participant)
+    std::vector<double> p0, p1, p2;   // per-bead parameters (NaN = not a participant); p2: attractive wells only
     std::vector<int32_t> part;    // participants, ascending
     std::vector<std::vector<int32_t>> excl;  // per bead, sorted partner list
     std::vector<int32_t> cls;     // interaction class per bead (-1 none)
@@ -401,6 +401,33 @@ inline void pair_energy(const PairTerm& t, int i, int j, double r, double* E, do
                 *E = ep * (s12 - 2.0 * s6) + ep;
                 *dEdr = ep * (-12.0 * s12 + 12.0 * s6) / r;
             } else { *E = 0; *dEdr = 0; }
+        } break;
+        case P_ISOLF: {  // iSoLFAttractiveForceFieldGenerator.cpp:41-50; p0 = eps (geometric), p1 = sigma, p2 = omega (arithmetic)
+            const double PI = 3.1415926535897932385;
+            double ep = std::sqrt(t.p0[i] * t.p0[j]), base = 0.5 * (t.p1[i] + t.p1[j]) * kTwoSixth, om = 0.5 * (t.p2[i] + t.p2[j]);
+            // -eps (step(base - r) + step(r - base) step(base + omega - r) cos(0.5 pi (r - base) / omega)^2), step(0) = 1
+            double e = 0, de = 0;
+            if (base - r >= 0.0) e -= ep;
+            if (r - base >= 0.0 && base + om - r >= 0.0) {
+                double a = 0.5 * PI * (r - base) / om, cs = std::cos(a);
+                e -= ep * cs * cs;
+                de += ep * 2.0 * cs * std::sin(a) * 0.5 * PI / om;
+            }
+            *E = e; *dEdr = de;
+        } break;
+        case P_TRIG: {  // TrigonometricForceFieldGenerator.cpp:43-53; p0 = epsilon (geometric), p1 = sigma, p2 = omega (arithmetic)
+            double ep = std::sqrt(t.p0[i] * t.p0[j]), th = 0.5 * (t.p1[i] + t.p1[j]) * kTwoSixth, om = 0.5 * (t.p2[i] + t.p2[j]);
+            // -epsilon (step(th + omega - r) + step(r - th) step(th + omega - r) (2 u^3 - 3 u^2)), u = (r - th) / omega
+            double e = 0, de = 0;
+            if (th + om - r >= 0.0) {
+                e -= ep;
+                if (r - th >= 0.0) {
+                    double u = (r - th) / om;
+                    e -= ep * (2.0 * u * u * u - 3.0 * u * u);
+                    de -= ep * (6.0 * u * u - 6.0 * u) / om;
+                }
+            }
+            *E = e; *dEdr = de;
         } break;
     }
 }
@@ -882,7 +909,7 @@ int add_bonded(ocm_system* s, BondedKind kind, int group, int periodic, int nbod
 }
 
 int add_pair(ocm_system* s, PairKind kind, int group, double rc, double rsw, double g0, double g1, double g2,
-             const double* p0, const double* p1, const ocm_pair_topology* topo, const char* what) {
+             const double* p0, const double* p1, const ocm_pair_topology* topo, const char* what, const double* p2 = nullptr) {
     if (!s) return fail("null system");
     if (group < 0 || group > 31) return fail("force group must be in 0..31");
     if (!topo) return fail("null topology");
@@ -896,6 +923,7 @@ int add_pair(ocm_system* s, PairKind kind, int group, double rc, double rsw, dou
     int n = s->n;
     t.p0.assign(p0, p0 + n);
     if (p1) t.p1.assign(p1, p1 + n); else t.p1 = t.p0;  // single-parameter kinds
+    if (p2) t.p2.assign(p2, p2 + n); else t.p2 = t.p0;
     for (int i = 0; i < n; i++) {
         bool has0 = !std::isnan(t.p0[i]), has1 = !std::isnan(t.p1[i]);
         if (has0 != has1) return fail(std::string(what) + ": incomplete parameter set for a particle");
@@ -1094,6 +1122,16 @@ int oracle_system_add_debye_huckel(ocm_system* s, int g, double K, double debye,
 int oracle_system_add_lj_repulsive(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
     return add_pair(s, P_LJREP, g, rc, rc, 0, 0, 0, eps, sigma, topo, "lj_repulsive");
 }
+int oracle_system_add_isolf_attractive(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const double* omega,
+                                       const ocm_pair_topology* topo) {
+    if (!eps || !sigma || !omega) return fail("isolf_attractive: null parameter array");
+    return add_pair(s, P_ISOLF, g, rc, rc, 0, 0, 0, eps, sigma, topo, "isolf_attractive", omega);
+}
+int oracle_system_add_trigonometric(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const double* omega,
+                                    const ocm_pair_topology* topo) {
+    if (!eps || !sigma || !omega) return fail("trigonometric: null parameter array");
+    return add_pair(s, P_TRIG, g, rc, rc, 0, 0, 0, eps, sigma, topo, "trigonometric", omega);
+}
 int oracle_system_add_wca(ocm_system* s, int g, double rc, const double* eps, const double* sigma, const ocm_pair_topology* topo) {
     return add_pair(s, P_WCA, g, rc, rc, 0, 0, 0, eps, sigma, topo, "wca");
 }
@@ -1139,11 +1177,12 @@ int oracle_context_create_batch(const ocm_system* sys, int32_t nrep, double T, d
     }
     for (const auto& t : sys->pairs) {
         PairTerm u = t;
-        u.p0.clear(); u.p1.clear(); u.part.clear(); u.excl.clear(); u.cls.clear();
+        u.p0.clear(); u.p1.clear(); u.p2.clear(); u.part.clear(); u.excl.clear(); u.cls.clear();
         u.nper = np;
         for (int r = 0; r < nrep; r++) {
             u.p0.insert(u.p0.end(), t.p0.begin(), t.p0.end());
             u.p1.insert(u.p1.end(), t.p1.begin(), t.p1.end());
+            u.p2.insert(u.p2.end(), t.p2.begin(), t.p2.end());
             u.cls.insert(u.cls.end(), t.cls.begin(), t.cls.end());
             for (int32_t v : t.part) u.part.push_back(v + r * np);
             for (const auto& e : t.excl) {

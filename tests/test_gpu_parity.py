@@ -581,6 +581,45 @@ def test_wca_random(engine, oracle, periodic):
     check_sets(ctx, ora)
 
 
+@pytest.mark.parametrize("periodic", [False, True])
+@pytest.mark.parametrize("kind", ["isolf_attractive", "trigonometric"])
+def test_attractive_wells_random(engine, oracle, kind, periodic):
+    """iSoLFAttractive / Trigonometric (the attractive wells of the lipid model): a pair form of their own (Verlet rows,
+    well_dedr in kernels.cuh) against the oracle, which is pinned to the reference's expression strings by the membrane fixture.
+    Unequal sigmas and omegas; for Trigonometric the generator's cutoff lies inside the widest well."""
+    rng = np.random.default_rng(33)
+    n = 600
+    box = np.array([6.0, 5.5, 6.5]) if periodic else None
+    g = np.stack(np.meshgrid(np.arange(8), np.arange(8), np.arange(10), indexing="ij"), -1).reshape(-1, 3)[:n]
+    pos = g * 0.62 + rng.uniform(-0.12, 0.12, (n, 3)) + 0.3
+    eps, sig, om = rng.choice([0.5, 0.9, 1.7], n), rng.choice([0.5, 0.56, 0.7], n), rng.choice([0.3, 0.45, 0.6], n)
+    for a in (eps, sig, om):
+        a[::13] = np.nan
+    has = ~np.isnan(sig)
+    s2, o2, r2 = np.sort(sig[has])[-2:], np.sort(om[has])[-2:], np.sort((sig + om)[has])[-2:]
+    rc = s2.sum() * 0.5 * 2.0 ** (1.0 / 6.0) + o2.sum() * 0.5 if kind == "isolf_attractive" else r2.sum() * 0.5
+    excl = np.array([[i, i + 1] for i in range(0, n - 1, 3) if has[i] and has[i + 1]], np.int32)
+    part = np.nonzero(has)[0]
+
+    def make(lib):
+        s = System(lib, np.full(n, 100.0), box)
+        getattr(s, "add_" + kind)(0, rc, eps, sig, om, PairTopology(excl=excl, igroups=[(part, part)], periodic=periodic))
+        s.add_harmonic_bond(1, np.array([[i, i + 1] for i in range(0, n - 1, 2)]), np.full(n // 2, 0.62), np.full(n // 2, 500.0), periodic=periodic)
+        c = Context(s, 300.0, 0.2, 0.002, seed=5)
+        c.set_positions(pos)
+        c.set_velocities_to_temperature(300.0, 3)
+        return c
+
+    ctx, ora = make(engine), make(oracle)
+    a, b = ctx.get_state(forces=True, energy=True), ora.get_state(forces=True, energy=True)
+    assert force_error(a["forces"], b["forces"]).max() < FORCE_TOL
+    assert a["energy_by_group"][0] == pytest.approx(b["energy_by_group"][0], rel=ENERGY_TOL)
+    assert b["energy_by_group"][0] < 0
+    check_sets(ctx, ora)
+    ctx.step(20); ora.step(20)
+    assert np.abs(ctx.get_state(positions=True)["positions"] - ora.get_state(positions=True)["positions"]).max() < 2e-5
+
+
 def test_capped_go_contact(engine, oracle):
     """Go contacts with the linear short-range cap (CappedGoContactForceFieldGenerator): both branches, against the oracle"""
     rng = np.random.default_rng(8)

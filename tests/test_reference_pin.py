@@ -28,9 +28,11 @@ from opencafemol_b200 import toml_input as ti
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import ref_binding as rb  # noqa: E402
 
-CASES = ["sh3", "dna_3spn2", "nucleosome", "fus10"]
+# "membrane": the POPC sample in the NVT ensemble with a Trigonometric term added (tests/golden/make_ref_membrane.py)
+CASES = ["sh3", "dna_3spn2", "nucleosome", "fus10", "membrane"]
 REF_SAMPLES = "/root/reference/sample/toml_input"
-PAIR_KINDS = ("excluded_volume", "debye_huckel", "lj_repulsive", "lj_attractive", "3spn2_excluded_volume")
+PAIR_KINDS = ("excluded_volume", "debye_huckel", "lj_repulsive", "lj_attractive", "3spn2_excluded_volume", "wca", "isolf_attractive",
+              "trigonometric")
 DA_KINDS = ("3spn2_base_pair", "3spn2_cross_stacking", "pdns")
 
 
@@ -87,7 +89,7 @@ def test_oracle_matches_reference_fus100_full_size(oracle):
         assert st["energy_by_group"][spec.group_ids[name]] == pytest.approx(ref, rel=1e-10, abs=1e-7)
 
 
-@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "nucleosome"])
+@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "nucleosome", "membrane"])
 def test_oracle_trajectory_matches_reference_run(oracle, name):
     """20 leap-frog Langevin steps of the reference's LangevinIntegrator semantics with the shared Philox noise."""
     gold = load_ref(name)
@@ -283,7 +285,7 @@ def test_engine_matches_reference_vectors(engine, name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["sh3", "dna_3spn2"])
+@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "membrane"])
 def test_engine_trajectory_tracks_reference_run(engine, name):
     """FP32 pair arithmetic and FP32 velocities against the reference's double-precision run, same noise"""
     gold = load_ref(name)

@@ -250,6 +250,14 @@ def single_gpu_records(lib, local):
                  "kernel_ms": {k: ctx.profile_kernel(k, 5) for k in ("force", "integrate", "rebuild")}}
     hbm = spec.mass.size * BYTES_PER_BEAD_INTEGRATE / (out["c5"]["kernel_ms"]["integrate"] * 1e-3) / 1e9
     peaks, how = measured_peaks()
+    # FP32 line of the tile force launches (Ashbaugh-Hatch tile list + the Coulomb rows of the fused launch), algorithmic flops
+    n_ah5, n_dh5 = ctx.num_neighbor_pairs(1), ctx.num_neighbor_pairs(2)
+    flop5 = n_ah5 * FLOP_PER_AH_PAIR + n_dh5 * FLOP_PER_DH_PAIR
+    peak32 = lib.measure_fp32_peak(local)
+    out["c5"]["roofline"] = {"bound": "fp32", "kernel": "tile_force_kernel + force_kernel (all force launches of a step)",
+                             "achieved": flop5 / (out["c5"]["kernel_ms"]["force"] * 1e-3) / 1e12, "peak": peak32, "unit": "TFLOP/s",
+                             "frac": flop5 / (out["c5"]["kernel_ms"]["force"] * 1e-3) / 1e12 / peak32 if peak32 else None,
+                             "in_cutoff_pairs": {"ashbaugh_hatch": n_ah5, "debye_huckel": n_dh5}}
     out["c5"]["roofline_hbm"] = {"bound": "hbm", "kernel": "integrate_kernel", "achieved": hbm, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                  "frac": hbm / peaks.get("hbm_gbs", 1.0), "peak_source": how}
     ctx.close()
@@ -261,11 +269,12 @@ def single_gpu_records(lib, local):
     ctx = toml_input.make_context(lib, sh3, device=local, replicas=512)
     dev = timed_steps(ctx, 500, 2000, local, 1)
     out["c4"] = {"workload": "C4: 512 replicas of the SH3 AICG2+ sample (56 beads each) in one context", "replica_steps_per_s": 512 * 2000 / dev,
-                 "md_steps_per_s": 2000 / dev}
+                 "md_steps_per_s": 2000 / dev, "kernel": "replica_step_kernel (one thread block per replica)" if ctx.get_option("replica_kernel") else "general path"}
     ctx.close()
     ctx = toml_input.make_context(lib, sh3, device=local)
     dev = timed_steps(ctx, 500, 5000, local, 1)
-    out["c1"] = {"workload": "C1: sample/toml_input/sh3_AICG2+.toml (56 beads)", "md_steps_per_s": 5000 / dev, "ns_per_day": ns_per_day(5000, sh3.dt, dev)}
+    out["c1"] = {"workload": "C1: sample/toml_input/sh3_AICG2+.toml (56 beads)", "md_steps_per_s": 5000 / dev, "ns_per_day": ns_per_day(5000, sh3.dt, dev),
+                 "kernel": "replica_step_kernel (one thread block per replica)" if ctx.get_option("replica_kernel") else "general path"}
     # end to end with the sample's own save_step = 100: every frame downloads positions + energies (what its observers ask for),
     # the download of frame k overlapping the steps of frame k + 1
     import torch

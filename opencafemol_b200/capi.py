@@ -654,6 +654,12 @@ class Context:
         self.lib.check(self.lib.fn["get_neighbor_pairs"](self.handle, int(term), _p(ij, _i32p), ij.shape[0], C.byref(n)))
         return ij[: n.value]
 
+    def num_neighbor_pairs(self, term):
+        """number of in-cutoff pairs of pair term `term` (the counting pass of neighbor_pairs, nothing is copied)"""
+        n = C.c_int64()
+        self.lib.check(self.lib.fn["get_neighbor_pairs"](self.handle, int(term), None, 0, C.byref(n)))
+        return int(n.value)
+
     def num_da_terms(self):
         return int(self.lib.fn["num_da_terms"](self.handle))
 

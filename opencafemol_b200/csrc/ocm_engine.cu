@@ -916,7 +916,7 @@ static void compile_replica_tables(ocm_context* c) {
         for (int m0 = 0; m0 < (int)rec[k].size(); m0 += 32) tasks.push_back({k, m0});
     }
     // scratch slots: contribution number p to bead i (in (kind, term, body) order) lives in slot p * nper + i
-    const int nslots = nper * std::max(1, *std::max_element(nslot_of_bead.begin(), nslot_of_bead.end()));
+    const int nslots = nper * ((std::max(1, *std::max_element(nslot_of_bead.begin(), nslot_of_bead.end())) + 7) & ~7);
     if (nslots >= 65536) return;
     {
         std::vector<int> fill(nper, 0);
@@ -942,6 +942,8 @@ static void compile_replica_tables(ocm_context* c) {
     std::stable_sort(tasks.begin(), tasks.end(), [&](const RepTask& a, const RepTask& b) { return cost(a.kind) > cost(b.kind); });
     R.nslots = nslots; R.ntasks = (int)tasks.size();
     R.tabs = rep_upload(c, tabs); R.tasks = rep_upload(c, tasks);
+    // (phase 2 sums a bead's slots eight at a time: counts rounded up, the padding slots hold zeros)
+    for (int& v : nslot_of_bead) v = (v + 7) & ~7;
     R.nslot_of_bead = rep_upload(c, nslot_of_bead);
     R.rep_seed = c->nrep > 1 ? c->d_rep_seed.p : nullptr;
     c->rep_smem = rep_smem_bytes(nper, R.nlists, nslots);

@@ -67,12 +67,12 @@ struct RepBonded {
 struct RepTask { int kind, m0; };
 
 struct RepParams {
-    int nper, nrep, nlists, ntasks, nslots;   // nslots = nper * (largest number of bonded contributions to one bead)
+    int nper, nrep, nlists, ntasks, nslots;   // nslots = nper * (largest number of bonded contributions to one bead, rounded up to 8)
     RepList lists[kRepMaxLists];
     RepBonded bonded[9];
     const float* tabs;              // 24 floats per table
     const RepTask* tasks;           // longest first; warp w runs tasks w, w + nwarps, ...
-    const int* nslot_of_bead;       // [nper] bonded contributions to each bead: its slots are p * nper + bead, p < that number
+    const int* nslot_of_bead;       // [nper] bonded contributions to each bead rounded up to 8: its slots are p * nper + bead, p < that
     double dt;
     float a, b, c;                  // Langevin coefficients (StepParams)
     unsigned int seed_lo, seed_hi;
@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 5 : (NT == 512 ? 2 : 1)) repli
     __shared__ int bad;
     for (int k = tid; k < 3 * n; k += nthr) xs[k] = x_g[(size_t)3 * n * rep + k];
     for (int i = tid; i < n; i += nthr) vs[i] = v_g[(size_t)n * rep + i];
+    for (int k = tid; k < 3 * R.nslots; k += nthr) scratch[k] = 0.f;   // (the padding slots of every bead stay zero)
     if (tid == 0) { bad = 0; rebuild[0] = 1; rebuild[1] = 0; nb_overflow = 0; }
     const float disp_max = 0.5f * kRepSkin * 0.57735f;   // per component: |d| <= sqrt(3) max_q |d_q|
     const uint2 key = R.rep_seed ? R.rep_seed[rep] : make_uint2(R.seed_lo, R.seed_hi);
@@ -281,24 +282,22 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 5 : (NT == 512 ? 2 : 1)) repli
         if (tid == 0) rebuild[s & 1] = 0;
         if (tid == 1 && nb_overflow) rebuild[(s + 1) & 1] = 1;
         // ---- phase 2: one thread per (component, bead): fixed-order force sum, leap-frog Langevin update ----
-        for (int t = tid; t < 3 * n; t += nthr) {
-            const bool first = t == tid;   // (the first item of a thread: its constants were prepared before the step loop)
-            const int q = first ? q0 : t / n, i = t - q * n;
-            const int cnt = first ? cnt0 : __ldg(&R.nslot_of_bead[i]);
-            float f = 0.f;
+        auto item = [&](const int t, const int q, const int i, const int cnt8, const float im, const float bm, const float cs) {
+            float f = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+#pragma unroll 1
             for (int l = 0; l < R.nlists; l++) f += fpair[3 * n * l + t];
+            // the bead's scratch slots p * n + i, p < cnt8: its contributions, padded with zero slots to a multiple of 8
             const float* __restrict__ sc = scratch + q * R.nslots + i;
-            float f1 = 0.f, f2 = 0.f, f3 = 0.f;
-            int e = 0;
-            for (; e + 4 <= cnt; e += 4) { f += sc[e * n]; f1 += sc[(e + 1) * n]; f2 += sc[(e + 2) * n]; f3 += sc[(e + 3) * n]; }
-            for (; e < cnt; e++) f += sc[e * n];
+#pragma unroll 1
+            for (int e = 0; e < cnt8; e += 8, sc += 8 * n) {
+                f += sc[0]; f1 += sc[n]; f2 += sc[2 * n]; f3 += sc[3 * n];
+                f += sc[4 * n]; f1 += sc[5 * n]; f2 += sc[6 * n]; f3 += sc[7 * n];
+            }
             f = (f + f1) + (f2 + f3);
-            float* vp = reinterpret_cast<float*>(vs + i);
-            const float im = vp[3];
             if (im > 0.f) {
-                const float bm = first ? bm0 : R.b * im, cs = first ? cs0 : R.c * sqrtf(im);
-                const float vq = R.a * vp[q] + bm * f + cs * noise[t];
-                vp[q] = vq;
+                float* vp = reinterpret_cast<float*>(vs + i) + q;
+                const float vq = R.a * *vp + bm * f + cs * noise[t];
+                *vp = vq;
                 const double px = xs[3 * i + q] + (double)vq * R.dt;
                 xs[3 * i + q] = px;
                 const float xq = (float)(px - origin[q]);
@@ -306,6 +305,12 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 5 : (NT == 512 ? 2 : 1)) repli
                 if (fabsf(xq - xref[t]) > disp_max) rebuild[(s + 1) & 1] = 1;
                 if (!(px == px) || !(f == f)) bad = 1;
             }
+        };
+        if (tid < 3 * n) item(tid, q0, i0, cnt0, im0, bm0, cs0);
+        for (int t = tid + nthr; t < 3 * n; t += nthr) {   // (more than nthr / 3 beads)
+            const int q = t / n, i = t - q * n;
+            const float im = vs[i].w;
+            item(t, q, i, __ldg(&R.nslot_of_bead[i]), im, R.b * im, R.c * sqrtf(fmaxf(im, 0.f)));
         }
         __syncthreads();
         if (bad) break;  // (block-uniform: read after the barrier)

@@ -300,6 +300,33 @@ int ocm_set_state_async(ocm_context*, const double* xyz_nm, const double* vel_nm
 int ocm_minimize(ocm_context*, double tolerance_kj_mol_nm, int max_iterations, int* iterations,
                  double* final_energy);
 
+/* Monte Carlo barostats: OpenMM::MonteCarloAnisotropicBarostat (MonteCarloAnisotropicBarostatGenerator.cpp:9-17,
+ * ensemble "NPT", ReadTOMLInput.cpp:88-109) and OpenMM::MonteCarloMembraneBarostat
+ * (MonteCarloMembraneBarostatGenerator.cpp:6-14, ensemble "NPgammaT", ReadTOMLInput.cpp:110-169), added to the System by
+ * SystemGenerator.cpp:89-108.  OpenMM 8.0.0 semantics restated: before the MD step at which the barostat's call counter
+ * reaches `frequency`, one trial changes the box volume by a uniform random amount along one axis (membrane barostat: X and Y
+ * together in the isotropic mode, Z compensating in the constant-volume mode), every molecule (the connected components of
+ * the bonded terms) is translated rigidly so that its centre, wrapped into the box, scales with the box, and the trial is
+ * accepted with the Metropolis rule on
+ *   w = dE + P dV - gamma dA - N_mol kT ln(V'/V)      (P in bar, gamma in bar nm; 1 bar = N_A 1e-25 kJ/mol/nm^3);
+ * the step size of an axis is tuned every 10 trials to keep the acceptance between 25 % and 75 %.  The energy evaluations,
+ * the molecule scaling and the restore of a rejected trial run on the device; the decision is one host read of two energies.
+ * kind OCM_BAROSTAT_ANISOTROPIC: pressure3_bar = {Px, Py, Pz}, mode3 = {scaleX, scaleY, scaleZ} (0/1), surface tension
+ * ignored.  kind OCM_BAROSTAT_MEMBRANE: pressure3_bar[0] = P, mode3 = {xymode (0 isotropic, 1 anisotropic), zmode (0 free,
+ * 1 fixed, 2 constant volume), 0}.  OpenMM draws from SFMT with a seed of its own; here the stream is SplitMix64 of
+ * `seed`, restated in the oracle, so that engine and oracle take the same decisions.  kind OCM_BAROSTAT_NONE removes it.
+ * Periodic single-system contexts only (no replica batch, no slab decomposition). */
+enum { OCM_BAROSTAT_NONE = 0, OCM_BAROSTAT_ANISOTROPIC = 1, OCM_BAROSTAT_MEMBRANE = 2 };
+int ocm_context_set_barostat(ocm_context*, int kind, const double* pressure3_bar, double surface_tension_bar_nm,
+                             double temperature_K, const int32_t* mode3, int32_t frequency, uint64_t seed);
+/* State::getPeriodicBoxVectors (Observer.cpp:193): the current box edges in nm (zeros without a box).
+ * ocm_set_box = Context::setPeriodicBoxVectors: positions are kept, cell grids and lists are laid out again. */
+int ocm_get_box(ocm_context*, double* box3_nm);
+int ocm_set_box(ocm_context*, const double* box3_nm);
+/* barostat bookkeeping: out12 = {trials, accepted, last axis, last dV, last E before, last E after, last w, last accepted (0/1),
+ * volume step of X, Y, Z, number of molecules} */
+int ocm_get_barostat_info(ocm_context*, double* out12);
+
 /* Context::getState (Observer.cpp:34,107,113,340,344).  Any output pointer may be NULL.
  * pos/vel/force: 3*N doubles; epot: sum over groups in group_mask; ekin: leap-frog kinetic
  * energy shifted by dt/2 as OpenMM reports it; epot_by_group: 32 doubles (all groups). */

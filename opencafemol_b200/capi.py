@@ -219,6 +219,10 @@ class Library:
         "step": (C.c_int, [C.c_void_p, C.c_int64]),
         "current_step": (C.c_int64, [C.c_void_p]),
         "minimize": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+        "context_set_barostat": (C.c_int, [C.c_void_p, C.c_int, _f64p, C.c_double, C.c_double, _i32p, C.c_int32, C.c_uint64]),
+        "get_box": (C.c_int, [C.c_void_p, _f64p]),
+        "set_box": (C.c_int, [C.c_void_p, _f64p]),
+        "get_barostat_info": (C.c_int, [C.c_void_p, _f64p]),
         "get_state": (C.c_int, [C.c_void_p, C.c_uint32, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]),
         "get_state_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
         "get_state_end": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]),
@@ -562,6 +566,40 @@ class Context:
         it, e = C.c_int(), C.c_double()
         self.lib.check(self.lib.fn["minimize"](self.handle, float(tolerance), int(max_iterations), C.byref(it), C.byref(e)))
         return it.value, e.value
+
+    # ---- Monte Carlo barostats (OpenMM::MonteCarloAnisotropicBarostat / MonteCarloMembraneBarostat) ----
+    def set_anisotropic_barostat(self, pressure_bar, temperature, scale_axis=(True, True, True), frequency=25, seed=0):
+        """ensemble "NPT" of the reference's input (ReadTOMLInput.cpp:88-109)"""
+        p = _f64(np.broadcast_to(np.asarray(pressure_bar, dtype=np.float64), (3,)).copy())
+        m = _i32([1 if a else 0 for a in scale_axis])
+        self.lib.check(self.lib.fn["context_set_barostat"](self.handle, 1, _p(p, _f64p), 0.0, float(temperature), _p(m, _i32p),
+                                                           int(frequency), int(seed)))
+
+    def set_membrane_barostat(self, pressure_bar, surface_tension_bar_nm, temperature, xymode="Isotropic", zmode="Free", frequency=25, seed=0):
+        """ensemble "NPgammaT" of the reference's input (ReadTOMLInput.cpp:110-169)"""
+        p = _f64([float(pressure_bar), 0.0, 0.0])
+        m = _i32([{"Isotropic": 0, "Anisotropic": 1}[xymode], {"Free": 0, "Fixed": 1, "ConstantVolume": 2}[zmode], 0])
+        self.lib.check(self.lib.fn["context_set_barostat"](self.handle, 2, _p(p, _f64p), float(surface_tension_bar_nm), float(temperature),
+                                                           _p(m, _i32p), int(frequency), int(seed)))
+
+    def remove_barostat(self):
+        p = _f64([0.0, 0.0, 0.0]); m = _i32([0, 0, 0])
+        self.lib.check(self.lib.fn["context_set_barostat"](self.handle, 0, _p(p, _f64p), 0.0, 0.0, _p(m, _i32p), 0, 0))
+
+    def box(self):
+        b = np.zeros(3)
+        self.lib.check(self.lib.fn["get_box"](self.handle, _p(b, _f64p)))
+        return b
+
+    def set_box(self, box_nm):
+        b = _f64(box_nm)
+        self.lib.check(self.lib.fn["set_box"](self.handle, _p(b, _f64p)))
+
+    def barostat_info(self):
+        o = np.zeros(12)
+        self.lib.check(self.lib.fn["get_barostat_info"](self.handle, _p(o, _f64p)))
+        return {"trials": int(o[0]), "accepted": int(o[1]), "axis": int(o[2]), "dV": o[3], "e_before": o[4], "e_after": o[5], "w": o[6],
+                "last_accepted": bool(o[7]), "volume_step": o[8:11].copy(), "molecules": int(o[11])}
 
     @property
     def current_step(self):

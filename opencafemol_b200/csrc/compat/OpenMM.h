@@ -260,7 +260,7 @@ class CustomHbondForce : public CustomForceBase {
 };
 
 // Recorded so that the reference's generators compile and run; a Context refuses a System that contains one
-// (restraints, pulling, barostats are outside the hot-path scope).
+// (restraints and pulling are outside the hot-path scope).
 class CustomExternalForce : public CustomForceBase {
   public:
     explicit CustomExternalForce(const std::string& energy) : CustomForceBase(energy) {}
@@ -279,15 +279,54 @@ class CustomCentroidBondForce : public CustomForceBase {
     int ng_;
     std::vector<std::pair<std::vector<int>, std::vector<double>>> groups_;
 };
+// Monte Carlo barostats (MonteCarloAnisotropicBarostatGenerator.cpp:9-17, MonteCarloMembraneBarostatGenerator.cpp:6-14): the
+// parameters are handed to ocm_context_set_barostat when the Context is created; the trials run inside ocm_step.
 class MonteCarloAnisotropicBarostat : public Force {
   public:
-    MonteCarloAnisotropicBarostat(const Vec3&, double, bool = true, bool = true, bool = true, int = 25) {}
+    MonteCarloAnisotropicBarostat(const Vec3& defaultPressure, double defaultTemperature, bool scaleX = true, bool scaleY = true, bool scaleZ = true,
+                                  int frequency = 25)
+        : pressure_(defaultPressure), temperature_(defaultTemperature), frequency_(frequency) { scale_[0] = scaleX; scale_[1] = scaleY; scale_[2] = scaleZ; }
+    const Vec3& getDefaultPressure() const { return pressure_; }
+    double getDefaultTemperature() const { return temperature_; }
+    bool getScaleX() const { return scale_[0]; }
+    bool getScaleY() const { return scale_[1]; }
+    bool getScaleZ() const { return scale_[2]; }
+    int getFrequency() const { return frequency_; }
+    void setFrequency(int f) { frequency_ = f; }
+    int getRandomNumberSeed() const { return seed_; }
+    void setRandomNumberSeed(int seed) { seed_ = seed; }
+    bool usesPeriodicBoundaryConditions() const override { return true; }
+
+  private:
+    Vec3 pressure_;
+    double temperature_;
+    bool scale_[3];
+    int frequency_, seed_ = 0;
 };
 class MonteCarloMembraneBarostat : public Force {
   public:
     enum XYMode { XYIsotropic = 0, XYAnisotropic = 1 };
     enum ZMode { ZFree = 0, ZFixed = 1, ConstantVolume = 2 };
-    MonteCarloMembraneBarostat(double, double, double, XYMode, ZMode, int = 25) {}
+    MonteCarloMembraneBarostat(double defaultPressure, double defaultSurfaceTension, double defaultTemperature, XYMode xymode, ZMode zmode,
+                               int frequency = 25)
+        : pressure_(defaultPressure), tension_(defaultSurfaceTension), temperature_(defaultTemperature), xymode_(xymode), zmode_(zmode),
+          frequency_(frequency) {}
+    double getDefaultPressure() const { return pressure_; }
+    double getDefaultSurfaceTension() const { return tension_; }
+    double getDefaultTemperature() const { return temperature_; }
+    XYMode getXYMode() const { return xymode_; }
+    ZMode getZMode() const { return zmode_; }
+    int getFrequency() const { return frequency_; }
+    void setFrequency(int f) { frequency_ = f; }
+    int getRandomNumberSeed() const { return seed_; }
+    void setRandomNumberSeed(int seed) { seed_ = seed; }
+    bool usesPeriodicBoundaryConditions() const override { return true; }
+
+  private:
+    double pressure_, tension_, temperature_;
+    XYMode xymode_;
+    ZMode zmode_;
+    int frequency_, seed_ = 0;
 };
 
 // ---- system ------------------------------------------------------------------------------------------------

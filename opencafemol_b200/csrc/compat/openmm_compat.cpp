@@ -300,7 +300,8 @@ class SystemCompiler {
         } else if (auto* p = dynamic_cast<const CustomHbondForce*>(&f)) {
             add_hbond(*p, g);
         } else if (dynamic_cast<const MonteCarloAnisotropicBarostat*>(&f) || dynamic_cast<const MonteCarloMembraneBarostat*>(&f)) {
-            throw OpenMMException("B200 engine: Monte Carlo barostats are outside the hot-path scope (NVT only)");
+            // not a term of the system tables: Context::create hands it to ocm_context_set_barostat
+            if (!sys_.has_box_) throw OpenMMException("barostat should be used with periodic boundary condition.");
         } else if (auto* p = dynamic_cast<const CustomForceBase*>(&f)) {
             unsupported("external / centroid", *p);
         } else {
@@ -574,6 +575,24 @@ void Context::create(const std::map<std::string, std::string>& props) {
     const int rc = ocm_context_create(sys, li->getTemperature(), li->getFriction(), li->getStepSize(), seed, device, &h_);
     ocm_system_destroy(sys);
     check(rc, "ocm_context_create");
+    // barostats (SystemGenerator.cpp:89-108).  OpenMM draws their random stream from a seed of its own (0 = from the clock); a
+    // zero seed here follows the integrator's, so that a run with a fixed integrator seed is reproducible.
+    for (int k = 0; k < sys_->getNumForces(); k++) {
+        const Force& f = sys_->getForce(k);
+        if (auto* b = dynamic_cast<const MonteCarloAnisotropicBarostat*>(&f)) {
+            const double P[3] = {b->getDefaultPressure()[0], b->getDefaultPressure()[1], b->getDefaultPressure()[2]};
+            const std::int32_t mode[3] = {b->getScaleX() ? 1 : 0, b->getScaleY() ? 1 : 0, b->getScaleZ() ? 1 : 0};
+            const std::uint64_t bs = b->getRandomNumberSeed() ? (std::uint64_t)(std::int64_t)b->getRandomNumberSeed() : seed;
+            check(ocm_context_set_barostat(h_, OCM_BAROSTAT_ANISOTROPIC, P, 0.0, b->getDefaultTemperature(), mode, b->getFrequency(), bs),
+                  "MonteCarloAnisotropicBarostat");
+        } else if (auto* b = dynamic_cast<const MonteCarloMembraneBarostat*>(&f)) {
+            const double P[3] = {b->getDefaultPressure(), 0.0, 0.0};
+            const std::int32_t mode[3] = {(std::int32_t)b->getXYMode(), (std::int32_t)b->getZMode(), 0};
+            const std::uint64_t bs = b->getRandomNumberSeed() ? (std::uint64_t)(std::int64_t)b->getRandomNumberSeed() : seed;
+            check(ocm_context_set_barostat(h_, OCM_BAROSTAT_MEMBRANE, P, b->getDefaultSurfaceTension(), b->getDefaultTemperature(), mode,
+                                           b->getFrequency(), bs), "MonteCarloMembraneBarostat");
+        }
+    }
     integ_->ctx_ = this;
 }
 void Context::setPositions(const std::vector<Vec3>& p) {
@@ -603,6 +622,12 @@ State Context::getState(int types, bool enforcePeriodicBox, int groups) const {
     s.types_ = types;
     s.time_ = getTime();
     sys_->getDefaultPeriodicBoxVectors(s.box_[0], s.box_[1], s.box_[2]);
+    if (sys_->usesPeriodicBoundaryConditions()) {
+        // (a Monte Carlo barostat changes the box of the Context, not the System's default)
+        double b[3] = {0, 0, 0};
+        check(ocm_get_box(h_, b), "getState");
+        if (b[0] > 0) { s.box_[0] = Vec3(b[0], 0, 0); s.box_[1] = Vec3(0, b[1], 0); s.box_[2] = Vec3(0, 0, b[2]); }
+    }
     const int n = sys_->getNumParticles();
     if (types & State::Forces) s.frc_.resize(n);
     if ((types & State::Forces) && (unsigned)groups != 0xFFFFFFFFu) throw OpenMMException("B200 engine: forces restricted to a force-group mask are not supported");

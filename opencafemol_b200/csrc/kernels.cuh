@@ -246,6 +246,30 @@ __global__ void canon_kernel(StepParams P, const double* __restrict__ x, uint4* 
     posq[i] = q;
 }
 
+// Monte Carlo barostat trial (OpenMM ApplyMonteCarloBarostatKernel::scaleCoordinates as MonteCarloAnisotropicBarostat /
+// MonteCarloMembraneBarostat call it): every molecule moves rigidly so that its centre (plain mean of its beads), wrapped
+// into the old box, is multiplied by the length scale of each axis.  One thread per molecule, beads in ascending order
+// (the oracle adds in the same order).
+__global__ void scale_molecules_kernel(int nmol, const int* __restrict__ mol_start, const int* __restrict__ mol_bead, double* __restrict__ x,
+                                       double bx, double by, double bz, double sx, double sy, double sz) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmol) return;
+    const int lo = mol_start[m], hi = mol_start[m + 1];
+    double cx = 0, cy = 0, cz = 0;
+    for (int k = lo; k < hi; k++) {
+        const int i = mol_bead[k];
+        cx += x[3 * i]; cy += x[3 * i + 1]; cz += x[3 * i + 2];
+    }
+    const double cnt = (double)(hi - lo);
+    cx /= cnt; cy /= cnt; cz /= cnt;
+    const double wx = cx - floor(cx / bx) * bx, wy = cy - floor(cy / by) * by, wz = cz - floor(cz / bz) * bz;
+    const double dx = wx * sx - cx, dy = wy * sy - cy, dz = wz * sz - cz;
+    for (int k = lo; k < hi; k++) {
+        const int i = mol_bead[k];
+        x[3 * i] += dx; x[3 * i + 1] += dy; x[3 * i + 2] += dz;
+    }
+}
+
 // replica batch: move every replica's local frame to its current centroid (one warp per replica).  Forces are
 // translation invariant, so this only keeps the FP32 offsets small and the shared cell grid compact.
 __global__ void recentre_kernel(StepParams P, const double* __restrict__ x, double* __restrict__ origin) {

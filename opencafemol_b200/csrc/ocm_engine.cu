@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -46,15 +47,19 @@ thread_local std::string g_err;
 template <class T>
 struct DevBuf {
     T* p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap = 0;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; cap = 0; }
+    // (contents are undefined afterwards.  An allocation that still fits is kept: a Monte Carlo barostat lays the cell grids out
+    // again at every trial.  cudaFree waits for the device; the kept buffer does the same, so that a host copy into it cannot
+    // overtake a kernel that still reads the old contents)
     void alloc(size_t count) {
+        if (p && count && count <= cap && 2 * count >= cap) { CUDA_TRY(cudaDeviceSynchronize()); n = count; return; }
         release();
-        n = count;
+        n = count; cap = count;
         if (count) CUDA_TRY(cudaMalloc(&p, count * sizeof(T)));
     }
     // synchronous (the engine's kernels run on a non-blocking stream, which does not order with the legacy stream: an
@@ -256,6 +261,23 @@ struct ocm_context {
     // counters
     double n_rebuilds = 0, n_rollbacks = 0, n_launches = 0, n_windows = 0, last_step_ms = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // Monte Carlo barostat (ocm_context_set_barostat)
+    struct Barostat {
+        int kind = 0;                        // OCM_BAROSTAT_*
+        double pressure[3] = {0, 0, 0};      // bar
+        double tension = 0, T = 0;           // bar nm, K
+        int mode[3] = {0, 0, 0};             // anisotropic: scale X, Y, Z; membrane: xymode, zmode
+        int frequency = 25;
+        uint64_t rng = 0;                    // SplitMix64 state
+        double volume_scale[3] = {0, 0, 0};  // trial step of each axis (nm^3)
+        int attempted[3] = {0, 0, 0}, accepted[3] = {0, 0, 0};
+        int64_t until_trial = 0;             // MD steps that may still run before the next trial
+        double n_trials = 0, n_accepted = 0;
+        double last[6] = {-1, 0, 0, 0, 0, 0};  // axis, dV, E before, E after, w, accepted
+        int nmol = 0;
+        DevBuf<int> mol_start, mol_bead;
+        DevBuf<double> xsave;
+    } baro;
 
     ~ocm_context() {
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
@@ -1632,8 +1654,9 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
         const int nst = c->nst;
         while (done + batch < nsteps && windows < 16) {
             int w = (int)std::min<int64_t>(nst, nsteps - done - batch);
-            if (c->dd || c->phase_timing) {
-                // slab decomposition: direct launches (the exchanges are host-ordered across ranks); also when phases are timed
+            if (c->dd || c->phase_timing || c->baro.kind) {
+                // slab decomposition: direct launches (the exchanges are host-ordered across ranks); also when phases are timed,
+                // and under a Monte Carlo barostat (the box, a kernel argument, changes every few steps)
                 const double l0 = c->n_launches, r0 = c->n_rebuilds;
                 enqueue_window(c, s, w);
                 c->n_launches = l0; c->n_rebuilds = r0;
@@ -1726,6 +1749,161 @@ static void compute_forces_into_fbuf(ocm_context* c) {
     ensure_lists_current(c);
     CUDA_TRY(cudaMemsetAsync(c->fbuf.p, 0, (size_t)3 * c->n * sizeof(unsigned long long), c->stream));
     enqueue_forces(c, c->stream);
+}
+
+// ---- Monte Carlo barostat -----------------------------------------------------------------------------------
+// Context::setPeriodicBoxVectors: everything laid out in the box (fixed-point positions, cell grids, tile tables, list
+// capacities) is derived again at the next list build; positions are kept.
+static void apply_box(ocm_context* c, const double* nb) {
+    if (!c->periodic || c->vbox) throw std::runtime_error("set_box: the context has no periodic box");
+    for (int k = 0; k < 3; k++) if (!(nb[k] > 0) || !std::isfinite(nb[k])) throw std::runtime_error("set_box: box edge must be positive");
+    double rmax = c->da_rcmax;
+    for (auto& L : c->lists) if (L->np) rmax = std::max(rmax, L->rc_list);
+    double skin = c->skin;
+    for (int k = 0; k < 3; k++) {
+        if (2.0 * rmax > nb[k]) throw std::runtime_error("The periodic box size has decreased to less than twice the nonbonded cutoff.");
+        if (rmax + skin > 0.5 * nb[k]) skin = std::max(0.0, 0.5 * nb[k] - rmax) * 0.999;
+    }
+    c->skin = skin;
+    for (int k = 0; k < 3; k++) c->sys.box[k] = nb[k];
+    update_params(c);
+    if (c->positions_set) canon_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->P, c->x.p, c->posq.p);
+    if (c->lists_ready) {
+        // the capacities found by the last sizing pass stay (a barostat trial changes an edge by a per cent or so; a list that
+        // outgrows its rows raises the overflow flag and is sized again): only the cell grids and what is derived from the box
+        bool tiled = false;
+        for (auto& L : c->lists) { configure_grid(c, *L); tiled = tiled || L->tiled; }
+        if (tiled) build_segments(c);   // (the tile launch records hold the box)
+        upload_lists(c);
+    }
+    c->lists_current = false;
+    drop_graphs(c);
+}
+
+static double potential_energy(ocm_context* c) {
+    cudaStream_t s = c->stream;
+    ensure_lists_current(c);
+    CUDA_TRY(cudaMemsetAsync(c->egroup.p, 0, 40 * sizeof(double), s));
+    enqueue_energies(c, s);
+    double he[40];
+    CUDA_TRY(cudaMemcpyAsync(he, c->egroup.p, sizeof(he), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    double e = 0;
+    for (int g = 0; g < 32; g++) e += he[g];
+    return e;
+}
+
+// OpenMM's getMolecules(): connected components of the graph whose edges are the bonded terms' consecutive bodies
+static void barostat_molecules(ocm_context* c) {
+    const int n = c->n;
+    std::vector<int> parent(n);
+    for (int i = 0; i < n; i++) parent[i] = i;
+    auto find = [&](int i) { while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; } return i; };
+    for (const auto& t : c->sys.bonded)
+        for (int64_t m = 0; m < t.n(); m++)
+            for (int b = 1; b < t.nbody; b++) {
+                int ra = find(t.idx[(size_t)m * t.nbody + b - 1]), rb = find(t.idx[(size_t)m * t.nbody + b]);
+                if (ra != rb) parent[std::max(ra, rb)] = std::min(ra, rb);
+            }
+    // molecules in the order of their first bead, beads ascending
+    std::vector<int> id(n, -1), count;
+    for (int i = 0; i < n; i++) { int r = find(i); if (id[r] < 0) { id[r] = (int)count.size(); count.push_back(0); } count[id[r]]++; }
+    std::vector<int> start(count.size() + 1, 0), bead(n);
+    for (size_t m = 0; m < count.size(); m++) start[m + 1] = start[m] + count[m];
+    std::vector<int> cur(start.begin(), start.end() - 1);
+    for (int i = 0; i < n; i++) bead[cur[id[find(i)]]++] = i;
+    c->baro.nmol = (int)count.size();
+    c->baro.mol_start.upload(start);
+    c->baro.mol_bead.upload(bead);
+    c->baro.xsave.alloc((size_t)3 * n);
+}
+
+static inline double baro_uniform(ocm_context::Barostat& B) {
+    uint64_t z = (B.rng += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// one trial (MonteCarloAnisotropicBarostatImpl / MonteCarloMembraneBarostatImpl::updateContextState of OpenMM 8.0)
+static void barostat_trial(ocm_context* c) {
+    auto& B = c->baro;
+    cudaStream_t s = c->stream;
+    const double kBar = 6.02214076e23 * 1e-25;  // bar -> kJ/mol/nm^3
+    const double e0 = potential_energy(c);
+    int axis = 0;
+    for (;;) {
+        const double rnd = baro_uniform(B) * 3.0;
+        if (B.kind == OCM_BAROSTAT_ANISOTROPIC) {
+            if (rnd < 1.0) { if (B.mode[0]) { axis = 0; break; } }
+            else if (rnd < 2.0) { if (B.mode[1]) { axis = 1; break; } }
+            else if (B.mode[2]) { axis = 2; break; }
+        } else {
+            if (rnd < 1.0) { axis = 0; break; }
+            else if (rnd < 2.0) { if (B.mode[0] == 1) { axis = 1; break; } }
+            else if (B.mode[1] == 0) { axis = 2; break; }
+        }
+    }
+    double box[3] = {c->sys.box[0], c->sys.box[1], c->sys.box[2]};
+    const double volume = box[0] * box[1] * box[2];
+    double dV = B.volume_scale[axis] * 2.0 * (baro_uniform(B) - 0.5);
+    double new_volume = volume + dV;
+    double scale[3] = {1.0, 1.0, 1.0};
+    if (B.kind == OCM_BAROSTAT_MEMBRANE && B.mode[0] == 0 && axis == 0) scale[0] = scale[1] = std::sqrt(new_volume / volume);
+    else scale[axis] = new_volume / volume;
+    if (B.kind == OCM_BAROSTAT_MEMBRANE && B.mode[1] == 2 && axis != 2) {
+        scale[2] = 1.0 / (scale[0] * scale[1]);
+        new_volume = volume; dV = 0.0;
+    }
+    const double nb[3] = {box[0] * scale[0], box[1] * scale[1], box[2] * scale[2]};
+    const double dA = nb[0] * nb[1] - box[0] * box[1];
+    const double skin0 = c->skin;
+    CUDA_TRY(cudaMemcpyAsync(B.xsave.p, c->x.p, (size_t)3 * c->n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    scale_molecules_kernel<<<nblk(B.nmol, 128), 128, 0, s>>>(B.nmol, B.mol_start.p, B.mol_bead.p, c->x.p, box[0], box[1], box[2], scale[0], scale[1], scale[2]);
+    apply_box(c, nb);
+    const double e1 = potential_energy(c);
+    const double kT = kBoltz * B.T;
+    const double pressure = (B.kind == OCM_BAROSTAT_ANISOTROPIC ? B.pressure[axis] : B.pressure[0]) * kBar;
+    const double tension = (B.kind == OCM_BAROSTAT_MEMBRANE ? B.tension : 0.0) * kBar;
+    const double w = e1 - e0 + pressure * dV - tension * dA - B.nmol * kT * std::log(new_volume / volume);
+    bool accept = true;
+    if (w > 0 && baro_uniform(B) > std::exp(-w / kT)) {
+        accept = false;
+        CUDA_TRY(cudaMemcpyAsync(c->x.p, B.xsave.p, (size_t)3 * c->n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        c->skin = skin0;
+        apply_box(c, box);
+    } else B.accepted[axis]++;
+    B.attempted[axis]++;
+    if (B.attempted[axis] >= 10) {
+        if (B.accepted[axis] < 0.25 * B.attempted[axis]) { B.volume_scale[axis] /= 1.1; B.attempted[axis] = 0; B.accepted[axis] = 0; }
+        else if (B.accepted[axis] > 0.75 * B.attempted[axis]) {
+            B.volume_scale[axis] = std::min(B.volume_scale[axis] * 1.1, volume * 0.3);
+            B.attempted[axis] = 0; B.accepted[axis] = 0;
+        }
+    }
+    B.n_trials += 1; B.n_accepted += accept ? 1 : 0;
+    B.last[0] = axis; B.last[1] = dV; B.last[2] = e0; B.last[3] = e1; B.last[4] = w; B.last[5] = accept ? 1 : 0;
+}
+
+// ocm_step under a barostat: OpenMM calls the barostat before every MD step; at the call where its counter reaches `frequency`
+// it makes a trial, i.e. before MD steps frequency, 2 frequency, ... (counted from 1) of the context
+static void do_steps_barostat(ocm_context* c, int64_t nsteps) {
+    auto& B = c->baro;
+    double ms = 0;
+    while (nsteps > 0) {
+        if (B.until_trial == 0) {
+            const auto t0 = std::chrono::steady_clock::now();
+            barostat_trial(c);
+            ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            B.until_trial = B.frequency;
+        }
+        const int64_t k = std::min(nsteps, B.until_trial);
+        do_steps(c, k);
+        ms += c->last_step_ms;
+        B.until_trial -= k; nsteps -= k;
+    }
+    c->last_step_ms = ms;
 }
 
 // Context::getState under a slab decomposition: every rank contributes what it owns, the sums over ranks (exact for
@@ -2268,11 +2446,67 @@ int ocm_step(ocm_context* c, int64_t nsteps) {
     if (nsteps < 0) return fail("step: negative step count");
     OCM_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
-    do_steps(c, nsteps);
+    if (c->baro.kind && c->baro.frequency > 0) do_steps_barostat(c, nsteps);
+    else do_steps(c, nsteps);
     return 0;
     OCM_GUARD_END
 }
 int64_t ocm_current_step(const ocm_context* c) { return c ? c->step : -1; }
+
+int ocm_context_set_barostat(ocm_context* c, int kind, const double* pressure3, double tension, double T, const int32_t* mode3, int32_t frequency,
+                             uint64_t seed) {
+    if (!c) return fail("null context");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    auto& B = c->baro;
+    if (kind == OCM_BAROSTAT_NONE) { B.kind = 0; return 0; }
+    if (kind != OCM_BAROSTAT_ANISOTROPIC && kind != OCM_BAROSTAT_MEMBRANE) return fail("set_barostat: unknown kind");
+    if (!pressure3 || !mode3) return fail("set_barostat: null argument");
+    if (!c->periodic || c->vbox) return fail("barostat should be used with periodic boundary condition.");
+    if (c->dd) return fail("set_barostat: not available under slab decomposition");
+    if (c->nrep > 1) return fail("set_barostat: not available for replica batches");
+    if (frequency < 0) return fail("set_barostat: negative frequency");
+    if (!(T > 0)) return fail("set_barostat: temperature must be positive");
+    if (kind == OCM_BAROSTAT_ANISOTROPIC && !mode3[0] && !mode3[1] && !mode3[2]) frequency = 0;  // (OpenMM: nothing to scale, never a trial)
+    if (kind == OCM_BAROSTAT_MEMBRANE && (mode3[0] < 0 || mode3[0] > 1 || mode3[1] < 0 || mode3[1] > 2)) return fail("set_barostat: unknown xymode / zmode");
+    B.kind = kind;
+    for (int k = 0; k < 3; k++) { B.pressure[k] = pressure3[kind == OCM_BAROSTAT_MEMBRANE ? 0 : k]; B.mode[k] = mode3[k]; }
+    B.tension = tension; B.T = T; B.frequency = frequency; B.rng = seed;
+    const double volume = c->sys.box[0] * c->sys.box[1] * c->sys.box[2];
+    for (int k = 0; k < 3; k++) { B.volume_scale[k] = 0.01 * volume; B.attempted[k] = 0; B.accepted[k] = 0; }
+    B.until_trial = std::max(0, frequency - 1);
+    B.n_trials = 0; B.n_accepted = 0; B.last[0] = -1;
+    barostat_molecules(c);
+    return 0;
+    OCM_GUARD_END
+}
+
+int ocm_get_box(ocm_context* c, double* box3) {
+    if (!c || !box3) return fail("null argument");
+    for (int k = 0; k < 3; k++) box3[k] = (c->periodic && !c->vbox) ? c->sys.box[k] : 0.0;
+    return 0;
+}
+
+int ocm_set_box(ocm_context* c, const double* box3) {
+    if (!c || !box3) return fail("null argument");
+    OCM_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->dd) return fail("set_box: not available under slab decomposition");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    apply_box(c, box3);
+    return 0;
+    OCM_GUARD_END
+}
+
+int ocm_get_barostat_info(ocm_context* c, double* out) {
+    if (!c || !out) return fail("null argument");
+    const auto& B = c->baro;
+    out[0] = B.n_trials; out[1] = B.n_accepted;
+    for (int k = 0; k < 6; k++) out[2 + k] = B.last[k];
+    for (int k = 0; k < 3; k++) out[8 + k] = B.volume_scale[k];
+    out[11] = B.nmol;
+    return 0;
+}
 
 int ocm_minimize(ocm_context* c, double tolerance, int max_iterations, int* iterations, double* final_energy) {
     if (!c) return fail("null context");

@@ -132,6 +132,7 @@ class SystemSpec:
     output: dict = field(default_factory=dict)
     platform: dict = field(default_factory=dict)
     state: str = ""  # provenance of positions/velocities when they are not the input file's (synth.c2_equilibrated)
+    ensemble: dict | None = None  # None = NVT; {"type": "NPT" | "NPgammaT", ...} = a Monte Carlo barostat (apply_ensemble)
 
     def add_term(self, term: Term):
         """SystemGenerator::add_ff_generator group rule (src/SystemGenerator.cpp:4-32): the group id is
@@ -378,12 +379,30 @@ def read_toml(path_or_dict, base_dir=None) -> SystemSpec:
         lo, up = np.array(shape["lower"], float), np.array(shape["upper"], float)
         box = (up - lo) * NM_PER_ANGSTROM
     attr = systems[0]["attributes"]
-    if "ensemble" in attr and attr["ensemble"].get("type", "NVT") != "NVT":
-        raise NotImplementedError("only the NVT ensemble is in scope (barostats: SURVEY.md §2.2 out of scope)")
     temperature = float(attr["temperature"])
+    ensemble = None
+    if "ensemble" in attr and attr["ensemble"]["type"] != "NVT":
+        # ReadTOMLInput.cpp:77-175: NPT = MonteCarloAnisotropicBarostat, NPgammaT = MonteCarloMembraneBarostat (the generator does
+        # not hand the input's frequency to the membrane barostat: MonteCarloMembraneBarostatGenerator.cpp:8-12, OpenMM's default 25)
+        ens = attr["ensemble"]
+        if not periodic:
+            raise RuntimeError("barostat should be used with periodic boundary condition.")
+        if ens["type"] == "NPT":
+            ensemble = {"type": "NPT", "pressure": [float(v) for v in ens["pressure"]], "scale_axis": [bool(v) for v in ens["scale_axis"]],
+                        "frequency": int(ens.get("frequency", 25))}
+        elif ens["type"] in ("NPgammaT", "NPγT"):
+            if ens["xymode"] not in ("Isotropic", "Anisotropic"):
+                raise RuntimeError("[error] unknown xymode " + ens["xymode"] + " was specified.")
+            if ens["zmode"] not in ("Free", "Fixed", "ConstantVolume"):
+                raise RuntimeError("[error] unknown zmode " + ens["xymode"] + " was specified.")
+            ensemble = {"type": "NPgammaT", "pressure": float(ens["pressure"]), "surface_tension": float(ens["surface_tension"]),
+                        "xymode": ens["xymode"], "zmode": ens["zmode"], "frequency": 25}
+        else:
+            raise RuntimeError("[error] unknown ensemble type " + ens["type"] + " was specified.")
 
     spec = SystemSpec(mass=mass, box=box, positions=pos, velocities=vel, names=names, groups=groups)
     spec.periodic = periodic
+    spec.ensemble = ensemble
     spec.temperature = temperature
     spec.delta_t_raw = float(sim["delta_t"])
     spec.dt = spec.delta_t_raw * CAFETIME
@@ -866,6 +885,19 @@ def build_system(lib: Library, spec: SystemSpec) -> System:
     return sysm
 
 
+def apply_ensemble(ctx: Context, spec: SystemSpec, seed=None):
+    """SystemGenerator.cpp:89-108: the barostat of the input's ensemble, if any (its random stream is seeded with the integrator
+    seed; OpenMM seeds its own from the clock)"""
+    ens = spec.ensemble
+    if not ens:
+        return
+    sd = spec.seed if seed is None else seed
+    if ens["type"] == "NPT":
+        ctx.set_anisotropic_barostat(ens["pressure"], spec.temperature, ens["scale_axis"], ens["frequency"], sd)
+    else:
+        ctx.set_membrane_barostat(ens["pressure"], ens["surface_tension"], spec.temperature, ens["xymode"], ens["zmode"], ens["frequency"], sd)
+
+
 def make_context(lib: Library, spec: SystemSpec, device=0, seed=None, replicas=None, comm=None, rank=0, axis=1) -> Context:
     """Simulator ctor + initialize + set_velocity (src/Simulator.cpp:4-47, ReadTOMLInput.cpp:1094-1121).
     replicas = R builds a replica ensemble (config C4): R copies of the system in one context, replica r with the
@@ -880,6 +912,7 @@ def make_context(lib: Library, spec: SystemSpec, device=0, seed=None, replicas=N
             ctx.set_velocities(spec.velocities)
         else:
             ctx.set_velocities_to_temperature(spec.temperature, spec.vel_seed)
+        apply_ensemble(ctx, spec, base_seed)
     else:
         ctx = Context(sysm, spec.temperature, spec.friction, spec.dt, device=device,
                       replica_seeds=[base_seed + r for r in range(replicas)])
@@ -918,6 +951,7 @@ def spec_to_dict(spec: SystemSpec) -> dict:
         "temperature": spec.temperature, "friction": spec.friction, "dt": spec.dt, "seed": spec.seed,
         "vel_seed": spec.vel_seed, "total_step": spec.total_step, "save_step": spec.save_step,
         "delta_t_raw": spec.delta_t_raw, "energy_minimization": spec.energy_minimization, "periodic": spec.periodic,
+        "ensemble": spec.ensemble,
         "terms": [{"kind": t.kind, "name": t.name, "group": t.group, "args": {k: conv(v) for k, v in t.args.items()}}
                   for t in spec.terms],
     }
@@ -943,6 +977,7 @@ def spec_from_dict(d: dict) -> SystemSpec:
               "energy_minimization", "periodic"):
         setattr(spec, k, d[k])
     spec.group_ids = dict(d["group_ids"])
+    spec.ensemble = d.get("ensemble")
     for t in d["terms"]:
         spec.terms.append(Term(t["kind"], t["name"], {k: conv(v) for k, v in t["args"].items()}, t["group"]))
     return spec

@@ -139,6 +139,13 @@ struct ocm_context {
     bool vl_valid = false, vl_enabled = true;
     double vl_skin = 0.3;
     long long vl_builds = 0;
+    // Monte Carlo barostat (oracle_context_set_barostat)
+    int baro_kind = 0, baro_mode[3] = {0, 0, 0}, baro_freq = 0, baro_attempted[3] = {0, 0, 0}, baro_accepted[3] = {0, 0, 0};
+    double baro_pressure[3] = {0, 0, 0}, baro_tension = 0, baro_T = 0, baro_vscale[3] = {0, 0, 0};
+    uint64_t baro_rng = 0;
+    int64_t baro_calls = 0;               // updateContextState calls since the last trial
+    double baro_trials = 0, baro_accepts = 0, baro_last[6] = {-1, 0, 0, 0, 0, 0};
+    std::vector<std::vector<int>> molecules;
 };
 
 struct ocm_comm { int world; };
@@ -1436,6 +1443,161 @@ static void compute_forces_verlet(ocm_context& c, std::vector<Vec3>* F) {
     }
 }
 
+// ---- Monte Carlo barostats -------------------------------------------------------------------------------------
+// OpenMM 8.0.0 is not under /root/reference (external dependency, CI pins 8.0.0); this restates the published
+// algorithm of MonteCarloAnisotropicBarostatImpl / MonteCarloMembraneBarostatImpl::updateContextState and of
+// ReferenceMonteCarloBarostat::applyBarostat as the reference's generators configure them
+// (MonteCarloAnisotropicBarostatGenerator.cpp:9-17, MonteCarloMembraneBarostatGenerator.cpp:6-14, SystemGenerator.cpp:89-108).
+// PARITY UNPINNED for this part: nothing in /root/reference holds a barostat trajectory, and OpenMM's SFMT stream is replaced
+// by SplitMix64 (the engine draws the same stream, so the two take the same decisions).
+namespace {
+double baro_uniform(ocm_context& c) {
+    c.baro_rng += 0x9E3779B97F4A7C15ull;
+    uint64_t z = c.baro_rng;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) / 9007199254740992.0;
+}
+double total_potential(ocm_context& c) {
+    double Eg[32];
+    compute(c, nullptr, Eg, 0xFFFFFFFFu);
+    double e = 0;
+    for (int g = 0; g < 32; g++) e += Eg[g];
+    return e;
+}
+// molecules = sets of beads connected through bonded terms (ContextImpl::getMolecules over getBondedParticles)
+void find_molecules(ocm_context& c) {
+    const int n = c.sys.n;
+    std::vector<std::vector<int>> adj(n);
+    for (const auto& t : c.sys.bonded)
+        for (int64_t m = 0; m < t.n(); m++)
+            for (int b = 0; b + 1 < t.nbody; b++) {
+                const int i = t.idx[m * t.nbody + b], j = t.idx[m * t.nbody + b + 1];
+                adj[i].push_back(j); adj[j].push_back(i);
+            }
+    std::vector<int> mol(n, -1);
+    c.molecules.clear();
+    for (int i = 0; i < n; i++) {
+        if (mol[i] >= 0) continue;
+        const int id = (int)c.molecules.size();
+        std::vector<int> stack(1, i), members;
+        mol[i] = id;
+        while (!stack.empty()) {
+            const int a = stack.back(); stack.pop_back();
+            members.push_back(a);
+            for (int b : adj[a]) if (mol[b] < 0) { mol[b] = id; stack.push_back(b); }
+        }
+        std::sort(members.begin(), members.end());
+        c.molecules.push_back(members);
+    }
+}
+void barostat_trial(ocm_context& c) {
+    const double bar = 6.02214076e23 * 1e-25;  // kJ/mol/nm^3 per bar
+    const double E_before = total_potential(c);
+    const bool membrane = c.baro_kind == 2;
+    int axis = -1;
+    while (axis < 0) {
+        const double r = 3.0 * baro_uniform(c);
+        const int pick = r < 1.0 ? 0 : (r < 2.0 ? 1 : 2);
+        bool allowed;
+        if (!membrane) allowed = c.baro_mode[pick] != 0;
+        else allowed = pick == 0 || (pick == 1 && c.baro_mode[0] == 1) || (pick == 2 && c.baro_mode[1] == 0);
+        if (allowed) axis = pick;
+    }
+    const double old_box[3] = {c.sys.box[0], c.sys.box[1], c.sys.box[2]};
+    const double V = old_box[0] * old_box[1] * old_box[2];
+    double dV = c.baro_vscale[axis] * 2 * (baro_uniform(c) - 0.5);
+    double Vn = V + dV;
+    double ls[3] = {1, 1, 1};
+    if (membrane && c.baro_mode[0] == 0 && axis == 0) ls[0] = ls[1] = std::sqrt(Vn / V);
+    else ls[axis] = Vn / V;
+    if (membrane && c.baro_mode[1] == 2) { ls[2] = 1.0 / (ls[0] * ls[1]); Vn = V; dV = 0; }
+    const std::vector<Vec3> saved = c.x;
+    for (const auto& mol : c.molecules) {
+        Vec3 ctr = {0, 0, 0};
+        for (int i : mol) ctr = ctr + c.x[i];
+        const double cnt = (double)mol.size();
+        ctr = {ctr.x / cnt, ctr.y / cnt, ctr.z / cnt};
+        const Vec3 wr = {ctr.x - std::floor(ctr.x / old_box[0]) * old_box[0], ctr.y - std::floor(ctr.y / old_box[1]) * old_box[1],
+                         ctr.z - std::floor(ctr.z / old_box[2]) * old_box[2]};
+        const Vec3 shift = {wr.x * ls[0] - ctr.x, wr.y * ls[1] - ctr.y, wr.z * ls[2] - ctr.z};
+        for (int i : mol) c.x[i] = c.x[i] + shift;
+    }
+    for (int k = 0; k < 3; k++) c.sys.box[k] = old_box[k] * ls[k];
+    const double dA = c.sys.box[0] * c.sys.box[1] - old_box[0] * old_box[1];
+    const double E_after = total_potential(c);
+    const double kT = kBoltz * c.baro_T;
+    const double P = (membrane ? c.baro_pressure[0] : c.baro_pressure[axis]) * bar;
+    const double gam = membrane ? c.baro_tension * bar : 0.0;
+    const double w = E_after - E_before + P * dV - gam * dA - (double)c.molecules.size() * kT * std::log(Vn / V);
+    bool ok = true;
+    if (w > 0 && baro_uniform(c) > std::exp(-w / kT)) {
+        ok = false;
+        c.x = saved;
+        for (int k = 0; k < 3; k++) c.sys.box[k] = old_box[k];
+    }
+    c.baro_attempted[axis]++;
+    if (ok) c.baro_accepted[axis]++;
+    if (c.baro_attempted[axis] >= 10) {
+        if (c.baro_accepted[axis] < 0.25 * c.baro_attempted[axis]) {
+            c.baro_vscale[axis] /= 1.1;
+            c.baro_attempted[axis] = c.baro_accepted[axis] = 0;
+        } else if (c.baro_accepted[axis] > 0.75 * c.baro_attempted[axis]) {
+            c.baro_vscale[axis] = std::min(c.baro_vscale[axis] * 1.1, V * 0.3);
+            c.baro_attempted[axis] = c.baro_accepted[axis] = 0;
+        }
+    }
+    c.baro_trials += 1; c.baro_accepts += ok ? 1 : 0;
+    c.baro_last[0] = axis; c.baro_last[1] = dV; c.baro_last[2] = E_before; c.baro_last[3] = E_after; c.baro_last[4] = w; c.baro_last[5] = ok ? 1 : 0;
+    c.vl_valid = false;
+}
+}  // namespace
+
+int oracle_context_set_barostat(ocm_context* c, int kind, const double* pressure3, double tension, double T, const int32_t* mode3, int32_t frequency,
+                                uint64_t seed) {
+    if (!c) return fail("null context");
+    if (kind == 0) { c->baro_kind = 0; return 0; }
+    if (kind != 1 && kind != 2) return fail("set_barostat: unknown kind");
+    if (!pressure3 || !mode3) return fail("set_barostat: null argument");
+    if (!c->sys.has_box) return fail("barostat should be used with periodic boundary condition.");
+    if (c->nrep > 1 || c->dd_world > 1) return fail("set_barostat: single periodic systems only");
+    if (frequency < 0) return fail("set_barostat: negative frequency");
+    if (!(T > 0)) return fail("set_barostat: temperature must be positive");
+    if (kind == 1 && !mode3[0] && !mode3[1] && !mode3[2]) frequency = 0;
+    if (kind == 2 && (mode3[0] < 0 || mode3[0] > 1 || mode3[1] < 0 || mode3[1] > 2)) return fail("set_barostat: unknown xymode / zmode");
+    c->baro_kind = kind; c->baro_freq = frequency; c->baro_T = T; c->baro_tension = tension; c->baro_rng = seed; c->baro_calls = 0;
+    const double V = c->sys.box[0] * c->sys.box[1] * c->sys.box[2];
+    for (int k = 0; k < 3; k++) {
+        c->baro_pressure[k] = pressure3[kind == 2 ? 0 : k]; c->baro_mode[k] = mode3[k];
+        c->baro_vscale[k] = 0.01 * V; c->baro_attempted[k] = c->baro_accepted[k] = 0;
+    }
+    c->baro_trials = c->baro_accepts = 0; c->baro_last[0] = -1;
+    find_molecules(*c);
+    return 0;
+}
+int oracle_get_box(ocm_context* c, double* box3) {
+    if (!c || !box3) return fail("null argument");
+    for (int k = 0; k < 3; k++) box3[k] = c->sys.has_box ? c->sys.box[k] : 0.0;
+    return 0;
+}
+int oracle_set_box(ocm_context* c, const double* box3) {
+    if (!c || !box3) return fail("null argument");
+    if (!c->sys.has_box) return fail("set_box: the context has no periodic box");
+    for (int k = 0; k < 3; k++) if (!(box3[k] > 0)) return fail("set_box: box edge must be positive");
+    for (int k = 0; k < 3; k++) c->sys.box[k] = box3[k];
+    c->vl_valid = false;
+    return 0;
+}
+int oracle_get_barostat_info(ocm_context* c, double* out) {
+    if (!c || !out) return fail("null argument");
+    out[0] = c->baro_trials; out[1] = c->baro_accepts;
+    for (int k = 0; k < 6; k++) out[2 + k] = c->baro_last[k];
+    for (int k = 0; k < 3; k++) out[8 + k] = c->baro_vscale[k];
+    out[11] = (double)c->molecules.size();
+    return 0;
+}
+
 int oracle_step(ocm_context* c, int64_t nsteps) {
     if (!c) return fail("null context");
     const double a = std::exp(-c->gamma * c->dt);
@@ -1445,6 +1607,8 @@ int oracle_step(ocm_context* c, int64_t nsteps) {
     const bool verlet = verlet_applicable(*c);
     c->vl_valid = false;  // (positions may have been set since the last call)
     for (int64_t s = 0; s < nsteps; s++) {
+        // ContextImpl::updateContextState before every step: the barostat counts the calls and makes a trial at every frequency-th
+        if (c->baro_kind && c->baro_freq > 0 && ++c->baro_calls >= c->baro_freq) { c->baro_calls = 0; barostat_trial(*c); }
         if (verlet) compute_forces_verlet(*c, &F);
         else compute(*c, &F, nullptr, 0xFFFFFFFFu);
         for (int i = 0; i < c->sys.n; i++) {

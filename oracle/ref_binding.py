@@ -47,6 +47,8 @@ class RefLibrary:
         L.ref_get_state.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_potential_energy.argtypes = [C.c_void_p, C.c_uint, C.POINTER(C.c_double), C.c_void_p]
         L.ref_step.argtypes = [C.c_void_p, C.c_int]
+        if hasattr(L, "ref_get_box"):
+            L.ref_get_box.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_minimize.argtypes = [C.c_void_p, C.c_double, C.c_int]
         L.ref_integrator.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ref_toml_to_json.argtypes = [C.c_char_p, C.c_char_p, C.c_long]
@@ -156,6 +158,11 @@ class RefSystem:
 
     def step(self, n):
         self.L.check(self.L.lib.ref_step(self.h, int(n)))
+
+    def box(self):
+        b = np.empty(3)
+        self.L.check(self.L.lib.ref_get_box(self.h, b.ctypes.data))
+        return b
 
     def minimize(self, tolerance=10.0, max_iterations=0):
         self.L.check(self.L.lib.ref_minimize(self.h, float(tolerance), int(max_iterations)))

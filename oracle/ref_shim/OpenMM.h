@@ -114,6 +114,8 @@ class Force {
     virtual double evaluate(const lite::EvalContext& ec, std::vector<Vec3>* forces) const = 0;
     // openmm-lite: everything the reference handed to this Force, as one JSON object
     virtual void describe(lite::Describer& out) const = 0;
+    // openmm-lite: ForceImpl::getBondedParticles (the edges ContextImpl::getMolecules joins into molecules)
+    virtual void bondedParticles(std::vector<std::pair<int, int>>&) const {}
 
   private:
     int group_ = 0;
@@ -127,6 +129,7 @@ class HarmonicBondForce : public Force {
     bool usesPeriodicBoundaryConditions() const override { return periodic_; }
     double evaluate(const lite::EvalContext&, std::vector<Vec3>*) const override;
     void describe(lite::Describer&) const override;
+    void bondedParticles(std::vector<std::pair<int, int>>& out) const override { for (auto& b : bonds_) out.emplace_back(b.p1, b.p2); }
 
   private:
     struct Bond { int p1, p2; double length, k; };
@@ -142,6 +145,9 @@ class HarmonicAngleForce : public Force {
     bool usesPeriodicBoundaryConditions() const override { return periodic_; }
     double evaluate(const lite::EvalContext&, std::vector<Vec3>*) const override;
     void describe(lite::Describer&) const override;
+    void bondedParticles(std::vector<std::pair<int, int>>& out) const override {
+        for (auto& a : angles_) { out.emplace_back(a.p1, a.p2); out.emplace_back(a.p2, a.p3); }
+    }
 
   private:
     struct Angle { int p1, p2, p3; double angle, k; };
@@ -176,6 +182,7 @@ class CustomBondForce : public CustomForceBase {
     bool usesPeriodicBoundaryConditions() const override { return periodic_; }
     double evaluate(const lite::EvalContext&, std::vector<Vec3>*) const override;
     void describe(lite::Describer&) const override;
+    void bondedParticles(std::vector<std::pair<int, int>>& out) const override { for (auto& b : bonds_) out.emplace_back(b.p1, b.p2); }
 
   private:
     struct Bond { int p1, p2; std::vector<double> params; };
@@ -194,6 +201,9 @@ class CustomTorsionForce : public CustomForceBase {
     bool usesPeriodicBoundaryConditions() const override { return periodic_; }
     double evaluate(const lite::EvalContext&, std::vector<Vec3>*) const override;
     void describe(lite::Describer&) const override;
+    void bondedParticles(std::vector<std::pair<int, int>>& out) const override {
+        for (auto& t : torsions_) for (int k = 1; k < 4; k++) out.emplace_back(t.p[k - 1], t.p[k]);
+    }
 
   private:
     struct Torsion { int p[4]; std::vector<double> params; };
@@ -212,6 +222,9 @@ class CustomCompoundBondForce : public CustomForceBase {
     bool usesPeriodicBoundaryConditions() const override { return periodic_; }
     double evaluate(const lite::EvalContext&, std::vector<Vec3>*) const override;
     void describe(lite::Describer&) const override;
+    void bondedParticles(std::vector<std::pair<int, int>>& out) const override {
+        for (auto& b : bonds_) for (std::size_t k = 1; k < b.p.size(); k++) out.emplace_back(b.p[k - 1], b.p[k]);
+    }
 
   private:
     struct Bond { std::vector<int> p; std::vector<double> params; };
@@ -317,7 +330,8 @@ class CustomHbondForce : public CustomForceBase {
     double cutoff_ = 1.0;
 };
 
-// barostats: recorded only (the hot path in scope is NVT); a Context that contains one refuses to step
+// barostats: the trial moves run inside LangevinIntegrator::step (Context::updateContextState; OpenMM 8.0 algorithm restated,
+// random stream = SplitMix64 of the integrator seed as in the engine and the oracle)
 class MonteCarloAnisotropicBarostat : public Force {
   public:
     MonteCarloAnisotropicBarostat(const Vec3& pressure, double temperature, bool scaleX = true, bool scaleY = true,
@@ -327,6 +341,7 @@ class MonteCarloAnisotropicBarostat : public Force {
     void describe(lite::Describer&) const override;
 
   private:
+    friend class Context;
     Vec3 p_;
     double t_;
     bool sx_, sy_, sz_;
@@ -344,6 +359,7 @@ class MonteCarloMembraneBarostat : public Force {
     void describe(lite::Describer&) const override;
 
   private:
+    friend class Context;
     double p_, g_, t_;
     XYMode xy_;
     ZMode z_;
@@ -480,9 +496,18 @@ class Context {
     Vec3 box_[3];
     double time_ = 0;
     std::int64_t steps_ = 0;
-    bool has_barostat_ = false;
     bool moved_from_ = false;
     void init();
+    // Monte Carlo barostat state (one barostat per System)
+    struct Baro {
+        int kind = 0, mode[3] = {0, 0, 0}, freq = 0, calls = 0, attempted[3] = {0, 0, 0}, accepted[3] = {0, 0, 0};
+        double pressure[3] = {0, 0, 0}, tension = 0, T = 0, vscale[3] = {0, 0, 0};
+        std::uint64_t rng = 0;
+        bool seeded = false;
+        std::vector<std::vector<int>> molecules;
+    } baro_;
+    void updateContextState(std::uint64_t integrator_seed);
+    void barostatTrial();
 };
 
 // L-BFGS on the potential energy until the RMS force drops below `tolerance` (kJ/mol/nm)

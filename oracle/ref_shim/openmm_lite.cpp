@@ -1119,7 +1119,7 @@ Context::Context(const System& s, Integrator& i, Platform& p) : sys_(s), integ_(
 Context::Context(const System& s, Integrator& i, Platform& p, const std::map<std::string, std::string>&) : sys_(s), integ_(i), platform_(&p) { init(); }
 Context::Context(Context&& o)
     : sys_(o.sys_), integ_(o.integ_), platform_(o.platform_), pos_(std::move(o.pos_)), vel_(std::move(o.vel_)), time_(o.time_),
-      steps_(o.steps_), has_barostat_(o.has_barostat_) {
+      steps_(o.steps_), baro_(std::move(o.baro_)) {
     for (int c = 0; c < 3; c++) box_[c] = o.box_[c];
     o.moved_from_ = true;
     integ_.ctx_ = this;
@@ -1139,9 +1139,108 @@ void Context::init() {
     sys_.getDefaultPeriodicBoxVectors(box_[0], box_[1], box_[2]);
     for (int k = 0; k < sys_.getNumForces(); k++) {
         const Force* f = &sys_.getForce(k);
-        if (dynamic_cast<const MonteCarloAnisotropicBarostat*>(f) || dynamic_cast<const MonteCarloMembraneBarostat*>(f)) has_barostat_ = true;
+        if (auto* b = dynamic_cast<const MonteCarloAnisotropicBarostat*>(f)) {
+            baro_.kind = 1; baro_.freq = b->freq_; baro_.T = b->t_;
+            for (int c = 0; c < 3; c++) baro_.pressure[c] = b->p_[c];
+            baro_.mode[0] = b->sx_; baro_.mode[1] = b->sy_; baro_.mode[2] = b->sz_;
+            if (!b->sx_ && !b->sy_ && !b->sz_) baro_.freq = 0;
+        } else if (auto* m = dynamic_cast<const MonteCarloMembraneBarostat*>(f)) {
+            baro_.kind = 2; baro_.freq = m->freq_; baro_.T = m->t_; baro_.pressure[0] = m->p_; baro_.tension = m->g_;
+            baro_.mode[0] = (int)m->xy_; baro_.mode[1] = (int)m->z_;
+        }
+    }
+    if (baro_.kind) {
+        if (!sys_.hasBox()) throw OpenMMException("barostat should be used with periodic boundary condition.");
+        const double V = box_[0][0] * box_[1][1] * box_[2][2];
+        for (int c = 0; c < 3; c++) baro_.vscale[c] = 0.01 * V;
+        // molecules: connected components over every Force's bonded particles, in the order of their first particle
+        std::vector<std::pair<int, int>> edges;
+        for (int k = 0; k < sys_.getNumForces(); k++) sys_.getForce(k).bondedParticles(edges);
+        std::vector<int> label(n);
+        for (int i = 0; i < n; i++) label[i] = i;
+        for (bool changed = true; changed;) {
+            changed = false;
+            for (auto& e : edges) {
+                const int lo = std::min(label[e.first], label[e.second]);
+                if (label[e.first] != lo || label[e.second] != lo) { label[e.first] = label[e.second] = lo; changed = true; }
+            }
+        }
+        std::map<int, int> index;
+        for (int i = 0; i < n; i++) {
+            auto it = index.find(label[i]);
+            if (it == index.end()) { it = index.emplace(label[i], (int)baro_.molecules.size()).first; baro_.molecules.emplace_back(); }
+            baro_.molecules[it->second].push_back(i);
+        }
     }
     g_most_recent = this;
+}
+
+// ContextImpl::updateContextState as the barostats implement it (OpenMM 8.0 MonteCarloAnisotropicBarostatImpl /
+// MonteCarloMembraneBarostatImpl): a trial at every frequency-th call, before that step is integrated
+static double lite_uniform(std::uint64_t& state) {
+    state += 0x9E3779B97F4A7C15ull;
+    std::uint64_t z = state;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+void Context::updateContextState(std::uint64_t integrator_seed) {
+    if (!baro_.kind || baro_.freq <= 0) return;
+    if (!baro_.seeded) { baro_.rng = integrator_seed; baro_.seeded = true; }
+    if (++baro_.calls < baro_.freq) return;
+    baro_.calls = 0;
+    barostatTrial();
+}
+void Context::barostatTrial() {
+    Baro& B = baro_;
+    const double bar = 6.02214076e23 * 1e-25;
+    const double E0 = computeForcesAndEnergy(0xFFFFFFFF, nullptr);
+    int axis;
+    for (;;) {
+        const double rnd = lite_uniform(B.rng) * 3.0;
+        if (rnd < 1.0) { if (B.kind == 2 || B.mode[0]) { axis = 0; break; } }
+        else if (rnd < 2.0) { if (B.kind == 2 ? B.mode[0] == 1 : B.mode[1] != 0) { axis = 1; break; } }
+        else if (B.kind == 2 ? B.mode[1] == 0 : B.mode[2] != 0) { axis = 2; break; }
+    }
+    const Vec3 old_box[3] = {box_[0], box_[1], box_[2]};
+    const double volume = box_[0][0] * box_[1][1] * box_[2][2];
+    double deltaVolume = B.vscale[axis] * 2 * (lite_uniform(B.rng) - 0.5);
+    double newVolume = volume + deltaVolume;
+    double scale[3] = {1.0, 1.0, 1.0};
+    if (B.kind == 2 && B.mode[0] == 0 && axis == 0) scale[0] = scale[1] = std::sqrt(newVolume / volume);
+    else scale[axis] = newVolume / volume;
+    if (B.kind == 2 && B.mode[1] == 2) { scale[2] = 1.0 / (scale[0] * scale[1]); newVolume = volume; deltaVolume = 0; }
+    const std::vector<Vec3> saved = pos_;
+    for (const auto& mol : B.molecules) {
+        Vec3 centre;
+        for (int i : mol) centre += pos_[i];
+        centre = centre / (double)mol.size();
+        Vec3 wrapped = centre;
+        for (int c = 0; c < 3; c++) wrapped[c] -= std::floor(centre[c] / box_[c][c]) * box_[c][c];
+        Vec3 shift;
+        for (int c = 0; c < 3; c++) shift[c] = wrapped[c] * scale[c] - centre[c];
+        for (int i : mol) pos_[i] += shift;
+    }
+    for (int c = 0; c < 3; c++) box_[c] = old_box[c] * scale[c];
+    const double deltaArea = box_[0][0] * box_[1][1] - old_box[0][0] * old_box[1][1];
+    const double E1 = computeForcesAndEnergy(0xFFFFFFFF, nullptr);
+    const double kT = kBoltz * B.T;
+    const double pressure = (B.kind == 2 ? B.pressure[0] : B.pressure[axis]) * bar;
+    const double tension = (B.kind == 2 ? B.tension : 0.0) * bar;
+    const double w = E1 - E0 + pressure * deltaVolume - tension * deltaArea - (double)B.molecules.size() * kT * std::log(newVolume / volume);
+    if (w > 0 && lite_uniform(B.rng) > std::exp(-w / kT)) {
+        pos_ = saved;
+        for (int c = 0; c < 3; c++) box_[c] = old_box[c];
+    } else B.accepted[axis]++;
+    B.attempted[axis]++;
+    if (B.attempted[axis] >= 10) {
+        if (B.accepted[axis] < 0.25 * B.attempted[axis]) { B.vscale[axis] /= 1.1; B.attempted[axis] = B.accepted[axis] = 0; }
+        else if (B.accepted[axis] > 0.75 * B.attempted[axis]) {
+            B.vscale[axis] = std::min(B.vscale[axis] * 1.1, volume * 0.3);
+            B.attempted[axis] = B.accepted[axis] = 0;
+        }
+    }
 }
 void Context::setPositions(const std::vector<Vec3>& p) {
     if ((int)p.size() != sys_.getNumParticles()) throw OpenMMException("Called setPositions() on a Context with the wrong number of positions");
@@ -1218,13 +1317,13 @@ LangevinIntegrator::LangevinIntegrator(double T, double friction, double dt) : T
 void LangevinIntegrator::step(int steps) {
     if (!ctx_) throw OpenMMException("This Integrator is not bound to a context!");
     Context& c = *ctx_;
-    if (c.has_barostat_) throw OpenMMException("openmm-lite: Monte Carlo barostats are recorded but not simulated");
     const double a = std::exp(-gamma_ * dt_);
     const double b = gamma_ == 0 ? dt_ : (1.0 - a) / gamma_;
     const double cc = std::sqrt(kBoltz * T_ * (1.0 - a * a));
     std::vector<Vec3> F;
     const int n = c.sys_.getNumParticles();
     for (int s = 0; s < steps; s++) {
+        c.updateContextState((std::uint64_t)(std::int64_t)seed_);
         c.computeForcesAndEnergy(0xFFFFFFFF, &F);
         for (int i = 0; i < n; i++) {
             const double m = c.sys_.getParticleMass(i);

@@ -189,6 +189,15 @@ int ref_potential_energy(void* hv, unsigned groups, double* epot, double* frc) {
     });
 }
 
+// State::getPeriodicBoxVectors (cuboid: the three diagonal entries)
+int ref_get_box(void* hv, double* box3) {
+    return guarded([&] {
+        OpenMM::Vec3 a, b, c;
+        static_cast<RefHandle*>(hv)->ctx->getState(0).getPeriodicBoxVectors(a, b, c);
+        box3[0] = a[0]; box3[1] = b[1]; box3[2] = c[2];
+    });
+}
+
 int ref_step(void* hv, int nsteps) {
     return guarded([&] { static_cast<RefHandle*>(hv)->ctx->getIntegrator().step(nsteps); });
 }

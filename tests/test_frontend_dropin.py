@@ -77,7 +77,7 @@ needs_frontend = pytest.mark.skipif(not os.path.exists(BIN), reason="bin/open_ca
 
 
 @needs_frontend
-@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "fus10", "wcamix", "dna_localize", "membrane"])
+@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "fus10", "wcamix", "dna_localize", "membrane", "membrane_npt", "membrane_npgt"])
 def test_frontend_translates_every_force_then_fails_loudly_without_gpu(built, tmp_path, name):
     """without a device the run must stop at ocm_context_create, i.e. after the reference's reader and generators ran
     and every OpenMM::Force they produced was recognised and translated into the C ABI (host code)"""
@@ -95,19 +95,24 @@ REF_POPC = "/root/reference/sample/toml_input/POPC_flat_membrane_128.toml"
 
 @needs_frontend
 @pytest.mark.skipif(not os.path.exists(REF_POPC), reason="reference tree not mounted")
-def test_frontend_refuses_out_of_scope_potentials_loudly(built, tmp_path):
-    """the lipid-membrane sample as shipped runs in the NPT ensemble: the Monte Carlo barostat is outside the
-    hot-path scope, and the host layer says so and stops; no CPU fallback, no silent skip.  (Its potentials, iSoLFAttractive
-    included, are in scope: the same sample in the NVT ensemble is the `membrane` case of the file tests.)  A System with a
-    pair expression outside the catalogue is refused by name."""
+def test_frontend_accepts_the_lipid_sample_as_shipped(built, tmp_path):
+    """the lipid-membrane sample as shipped runs in the NPT ensemble: since round 2 the Monte Carlo barostat is part of the
+    engine (ocm_context_set_barostat), so the host layer translates the whole System and, without a device, stops where every
+    other input stops: at ocm_context_create.  No CPU fallback, no silent skip."""
     import shutil
 
+    from opencafemol_b200.capi import product_library
+
+    if product_library().device_count() > 0:
+        pytest.skip("a GPU is visible")
     shutil.copy(REF_POPC, tmp_path / "popc.toml")
     os.makedirs(tmp_path / "output", exist_ok=True)
     r = subprocess.run([BIN, "popc.toml"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
     out = r.stdout + r.stderr
     assert r.returncode == 1
-    assert "Monte Carlo barostats are outside the hot-path scope" in out
+    assert "barostat is MonteCarloAnisotropicBarostat" in out
+    assert "outside the hot-path scope" not in out
+    assert "ocm_context_create" in out and "no CUDA device available" in out
 
 
 HOSTLAYER_ON_ORACLE = os.path.join(ROOT, "oracle", "_ref", "open_cafemol_hostlayer_oracle")
@@ -115,7 +120,7 @@ HOSTLAYER_ON_ORACLE = os.path.join(ROOT, "oracle", "_ref", "open_cafemol_hostlay
 
 @pytest.mark.skipif(not os.path.exists(HOSTLAYER_ON_ORACLE), reason="oracle/_ref is built where the reference tree is mounted")
 @pytest.mark.parametrize("name,periodic", [("sh3", False), ("dna_3spn2", False), ("fus10", True), ("wcamix", False), ("dna_localize", False),
-                                           ("membrane", True)])
+                                           ("membrane", True), ("membrane_npt", True), ("membrane_npgt", True)])
 def test_host_layer_on_oracle_backend_reproduces_reference_files(tmp_path, name, periodic):
     """CPU-only check of the product's host layer (compat/OpenMM.h -> C ABI): the reference's front end drives it with
     the double-precision ORACLE behind the C ABI (oracle/Makefile renames ocm_* to oracle_* for this test binary only).
@@ -170,7 +175,7 @@ def test_toml11_stand_in_compiles_with_the_reference_reader():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,periodic", [("sh3", False), ("dna_3spn2", False), ("fus10", True), ("wcamix", False), ("dna_localize", False),
-                                           ("membrane", True)])
+                                           ("membrane", True), ("membrane_npt", True), ("membrane_npgt", True)])
 def test_frontend_writes_the_reference_files(engine, tmp_path, name, periodic):
     if not os.path.exists(BIN):
         pytest.skip("bin/open_cafemol_b200 missing: it is built by __graft_entry__.build() where the reference tree is mounted and travels with the snapshot")

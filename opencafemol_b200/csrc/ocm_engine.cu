@@ -222,6 +222,8 @@ struct ocm_context {
     bool rep_ok = false;
     int rep_block = 256;                    // threads per block of the replica kernel (compile_replica_tables)
     int rep_opt = 1;                        // option "replica_kernel": 1 (default) = use it where possible, 0 = general path
+    int rep_block_opt = 0;                  // option "replica_block": threads per block (256 / 512 / 1024), 0 = by ensemble size
+    int rep_carveout_opt = -1;              // option "replica_carveout": shared-memory carve-out in per cent, -1 = what the resident blocks need
     RepParams rep{};
     size_t rep_smem = 0;
     std::vector<std::unique_ptr<DevBuf<unsigned char>>> rep_blobs;   // its static tables (compile_replica_tables)
@@ -954,6 +956,7 @@ static void compile_replica_tables(ocm_context* c) {
     // a few replicas get up to 1024 threads each, so that every warp has one task and a step is as short as its longest task.
     c->rep_block = c->nrep > 296 ? 256 : (c->nrep > 148 ? 512 : 1024);
     while (c->rep_block > 256 && c->rep_block / 32 >= 2 * (int)tasks.size()) c->rep_block /= 2;
+    if (c->rep_block_opt == 256 || c->rep_block_opt == 512 || c->rep_block_opt == 1024) c->rep_block = c->rep_block_opt;
     // warp w runs tasks w, w + nwarps, ... of this list: longest first (estimated warp instructions per task, from the SASS of the
     // kinds: FLD 380, gaussian / cosine dihedral 340, FLA 260, a walk over a bead group's Verlet lists 250, harmonic angle 200,
     // noise 170, bonds 140-160, 12-10 contact 110)
@@ -972,7 +975,20 @@ static void compile_replica_tables(ocm_context* c) {
     if (c->rep_smem > 96 * 1024) return;   // (scratch slots of a few thousand terms: beyond that the general path)
     auto* kern = c->rep_block == 256 ? replica_step_kernel<256> : (c->rep_block == 512 ? replica_step_kernel<512> : replica_step_kernel<1024>);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(c->rep_smem, 1024)));
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    // Shared memory of the blocks that can be resident on one SM, and no more: what is left of the 256 KB stays L1, where the
+    // read-only tables of the kernel live (coefficient table n x n x 16 B, term records 48 B each).  With the largest carve-out the
+    // L1 is 28 KB and those loads come from L2.
+    {
+        const int per_sm_limit = c->rep_block == 256 ? 5 : (c->rep_block == 512 ? 2 : 1);
+        const int resident = std::max(1, std::min(per_sm_limit, (c->nrep + 147) / 148));
+        cudaFuncAttributes fa{};
+        CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+        // (per block: dynamic + static shared memory + 1 KB the system reserves)
+        int pct = (int)std::ceil(100.0 * (double)resident * (double)(c->rep_smem + fa.sharedSizeBytes + 1024) / (228.0 * 1024.0)) + 1;
+        pct = std::max(0, std::min(100, pct));
+        if (c->rep_carveout_opt >= 0) pct = std::min(100, c->rep_carveout_opt);
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     c->rep_ok = true;
 }
 
@@ -2370,6 +2386,9 @@ int ocm_context_set_option(ocm_context* c, const char* key, double value) {
         // 1 (default): small unlimited-boundary systems and replica ensembles step in the whole-step persistent kernel (measured on
         // B200: 2 x the general path for one SH3 replica, 4 x for 512, see replica_kernels.cuh); 0: general path
         c->rep_opt = value != 0 ? 1 : 0;
+    } else if (k == "replica_block" || k == "replica_carveout") {
+        if (k == "replica_block") c->rep_block_opt = (int)value; else c->rep_carveout_opt = (int)value;
+        compile_replica_tables(c);
     } else if (k == "tile_debug") {
         // timing experiments only (wrong forces): see TileLaunch::debug; 4 = evaluate the list without its switching function
         c->tile_debug = (int)value;

@@ -258,6 +258,7 @@ struct ocm_context {
     int tpb_opt = 0;         // 0 = auto
     int chunk_opt = 0;       // beads per block of the pair kernels, 0 = auto
     bool lists_ready = false, positions_set = false, lists_current = false;
+    bool lists_fresh = false;    // lists_current because the lists were built at exactly the present positions (ensure_lists_current)
     bool last_disp2_ok = false;  // every window of the last batch ended with all beads inside their Verlet buffer
     std::map<int, cudaGraphExec_t> graphs;
     // counters
@@ -303,6 +304,7 @@ struct ocm_context {
 namespace ocm {
 
 static const int kTileAutoBeads = 131072;
+static const int kIntegrateEarlyBeads = 262144;   // below: integrate_kernel<true> (loads hoisted: latency-bound sizes)
 static const int kNstChoices[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 56, 64, 80, 100};
 
 static void dd_configure(ocm_context* c);
@@ -1489,7 +1491,7 @@ static void ensure_lists_current(ocm_context* c) {
         enqueue_rebuild(c, c->stream, false);
         int fl[FLAG_COUNT];
         read_flags(c, fl);
-        if (!fl[FLAG_OVERFLOW] && !fl[FLAG_DA_OVERFLOW] && !fl[FLAG_DD_OVERFLOW] && !fl[FLAG_VBOX]) { c->lists_current = true; return; }
+        if (!fl[FLAG_OVERFLOW] && !fl[FLAG_DA_OVERFLOW] && !fl[FLAG_DD_OVERFLOW] && !fl[FLAG_VBOX]) { c->lists_current = true; c->lists_fresh = true; return; }
         if (fl[FLAG_VBOX]) {
             // unlimited boundary: the beads left the range of the virtual box; lay it out again around them
             std::vector<double> hx((size_t)3 * c->n);
@@ -1533,9 +1535,10 @@ static void phase_collect(ocm_context* c) {
 }
 
 // one window: rebuild, then nst x [forces, integrate (+ halo positions to the neighbouring slabs)]
-static void enqueue_window(ocm_context* c, cudaStream_t s, int nst) {
+static void enqueue_window(ocm_context* c, cudaStream_t s, int nst, bool lists_are_fresh = false) {
     phase_mark(c, s, -1);
-    enqueue_rebuild(c, s, false);
+    // (a Monte Carlo barostat trial has just built the lists at these very positions for its energy evaluation)
+    if (!lists_are_fresh) enqueue_rebuild(c, s, false);
     phase_mark(c, s, 0);
     // slab decomposition with split tile lists and the peer-memory halo: the halo positions of a step travel on the side stream
     // while the interior tile entries (owned beads only) are already evaluated on the compute stream
@@ -1550,7 +1553,7 @@ static void enqueue_window(ocm_context* c, cudaStream_t s, int nst) {
         } else enqueue_forces(c, s, 0);
         interior_done = false;
         phase_mark(c, s, 1);
-        launch_chained(c, integrate_kernel, nblk(c->dd ? c->dd->integrate_cover(c->n) : c->n, 128), 128, 0, s, c->P, c->x.p, c->v.p, c->fbuf.p, c->posq.p, c->d_lists.p, (int)c->lists.size(), c->xref.p,
+        launch_chained(c, c->n < kIntegrateEarlyBeads ? integrate_kernel<true> : integrate_kernel<false>, nblk(c->dd ? c->dd->integrate_cover(c->n) : c->n, 128), 128, 0, s, c->P, c->x.p, c->v.p, c->fbuf.p, c->posq.p, c->d_lists.p, (int)c->lists.size(), c->xref.p,
                        c->step_base.p, k, nst, k == nst - 1 ? 1 : 0, c->flags.p);
         phase_mark(c, s, 2);
         // the next window starts with a full halo refresh, so the last step of a window ships nothing
@@ -1674,7 +1677,10 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
                 // slab decomposition: direct launches (the exchanges are host-ordered across ranks); also when phases are timed,
                 // and under a Monte Carlo barostat (the box, a kernel argument, changes every few steps)
                 const double l0 = c->n_launches, r0 = c->n_rebuilds;
-                enqueue_window(c, s, w);
+                // the first window after an accepted barostat trial starts on the lists of the trial's energy evaluation
+                const bool fresh = c->baro.kind && !c->dd && windows == 0 && replays == 0 && c->lists_current && c->lists_fresh;
+                enqueue_window(c, s, w, fresh);
+                c->lists_current = false; c->lists_fresh = false;
                 c->n_launches = l0; c->n_rebuilds = r0;
             } else CUDA_TRY(cudaGraphLaunch(window_graph(c, w), s));
             launches += launches_per_window(c, w);
@@ -1746,6 +1752,7 @@ static void do_steps(ocm_context* c, int64_t nsteps) {
     // from the list's reference positions (the cell-sorted positions are refreshed by every step): the observer can evaluate
     // energies and forces on them without a list build.  (Slab decomposition: halos are only complete right after a rebuild.)
     c->lists_current = !c->dd && c->nrep == 1 && c->last_disp2_ok;
+    c->lists_fresh = false;
 }
 
 // per-group energies of every term at the current positions (lists must be current), added into egroup
@@ -2944,7 +2951,7 @@ int ocm_profile_kernel(ocm_context* c, const char* which, int reps, double* avg_
             else if (w == "rebuild") enqueue_rebuild(c, s, false);
             else if (w == "integrate") {
                 // dt = 0 copy of the parameters would change the physics; instead integrate a scratch copy
-                integrate_kernel<<<nblk(c->n, 128), 128, 0, s>>>(c->P, c->xbak.p, c->vbak.p, c->fbuf.p, c->posq.p, c->d_lists.p, (int)c->lists.size(), c->xref.p,
+                (c->n < kIntegrateEarlyBeads ? integrate_kernel<true> : integrate_kernel<false>)<<<nblk(c->n, 128), 128, 0, s>>>(c->P, c->xbak.p, c->vbak.p, c->fbuf.p, c->posq.p, c->d_lists.p, (int)c->lists.size(), c->xref.p,
                                                                  c->step_base.p, 0, 1, 0, c->flags.p);
             } else throw std::runtime_error("profile_kernel: unknown kernel " + w);
         }

@@ -9,3 +9,9 @@ from opencafemol_b200.capi import product_library  # noqa: E402
 ctx = ti.make_context(product_library(), synth.c2_equilibrated(tile=(8, 8)))
 ctx.step(30)
 print("ms/step", ctx.counter("last_step_ms") / 30)
+if len(sys.argv) > 1:   # python tools/c5_profile_run.py time: a timed run and the per-kernel figures of bench.py's c5 record
+    ctx.step(200)
+    ctx.step(400)
+    print("ms/step", ctx.counter("last_step_ms") / 400, "nstlist", ctx.counter("nstlist"))
+    for k in ("force", "integrate", "rebuild"):
+        print(k, "ms", ctx.profile_kernel(k, 20))

@@ -198,6 +198,33 @@ int ocm_system_add_lj_attractive(ocm_system*, int group, double rc, double r_swi
 int ocm_system_add_3spn2_excluded_volume(ocm_system*, int group, double rc, const double* eps,
                                          const double* sigma, const ocm_pair_topology* topo);
 
+/* ---- external terms (one bead each, "CustomExternalForce"; absolute, unwrapped coordinates) ------------------------
+ * The reference reaches these through [[forcefields.external]] (ReadTOMLInput.cpp:763-870). */
+/* E = k (|x - x0| - v0)^2 (no factor 1/2).  The generator's periodic branch assigns to a shadowed local, so the plain
+ * distance is what runs in either boundary; restated as it runs.
+ *                                         PositionRestraintForceFieldGenerator.cpp:6-36 */
+int ocm_system_add_position_restraint(ocm_system*, int group, int64_t n, const int32_t* index, const double* pos3,
+                                      const double* k, const double* v0);
+/* E = -f . x (a constant force f on the bead)     PullingForceFieldGenerator.cpp:3-22 */
+int ocm_system_add_pulling(ocm_system*, int group, int64_t n, const int32_t* index, const double* force3);
+/* E = eps sum_axes ((radius / (x - lower))^12 + (radius / (upper - x))^12); unlimited boundary only (the generator
+ * throws under a periodic one)                    EXVRectangularBoxForceFieldGenerator.cpp:7-56 */
+int ocm_system_add_exv_rectangular_box(ocm_system*, int group, double eps, const double* lower3, const double* upper3,
+                                       int64_t n, const int32_t* index, const double* radius);
+/* E = k (dr - v0)^2, dr = |x - h|, h = (axis . x) axis + shift: the distance from the line through `shift` along the unit
+ * vector `axis` (shift orthogonal to axis); periodic = 1: minimum image of x - h (OpenMM periodicdistance)
+ *                                         CylindricalRestraintForceFieldGenerator.cpp:4-47 */
+int ocm_system_add_cylindrical_restraint(ocm_system*, int group, int periodic, int64_t n, const int32_t* index,
+                                         const double* axis3, const double* shift3, const double* k, const double* v0);
+/* E = 1/2 k (|c1 - c2| - v0)^2, c1, c2 the mass-weighted centres of two bead groups ("CustomCentroidBondForce" with its
+ * default weights); periodic = 1: minimum image of c1 - c2     HarmonicCoMPullingForceFieldGenerator.cpp:3-20 */
+int ocm_system_add_harmonic_com_pulling(ocm_system*, int group, int periodic, double k, double v0, int64_t n1,
+                                        const int32_t* group1, int64_t n2, const int32_t* group2);
+/* Go-type 12-10 contact between every donor bead and every acceptor bead closer than the cutoff (one bead per donor and
+ * per acceptor: topo->donors / acceptors carry d1 / a1 and -1, -1):  E = k (5 (r0/r)^12 - 6 (r0/r)^10), r = |a1 - d1|,
+ * discontinuous at the cutoff as in OpenMM      CombinatorialGoContactForceFieldGenerator.cpp:3-43 */
+int ocm_system_add_combinatorial_go_contact(ocm_system*, int group, const ocm_da_topology* topo, double k, double r0);
+
 /* ---- context (replaces OpenMM::Context + LangevinIntegrator) -------------------------------
  * Simulator.cpp:14-17 (Context), IntegratorGenerator.cpp:5-14 (LangevinIntegrator(T, gamma, dt),
  * setRandomNumberSeed).  The system is compiled into device-resident term tables; the system

@@ -188,6 +188,15 @@ class Library:
             C.c_int,
             [C.c_void_p, C.c_int, C.POINTER(DATopologyStruct), _f64p, _f64p, _f64p, _f64p, C.c_double, C.c_double],
         ),
+        "system_add_position_restraint": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _f64p, _f64p, _f64p]),
+        "system_add_pulling": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _f64p]),
+        "system_add_exv_rectangular_box": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _f64p, _f64p, C.c_int64, _i32p, _f64p]),
+        "system_add_cylindrical_restraint": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _f64p, _f64p, _f64p, _f64p]),
+        "system_add_harmonic_com_pulling": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int64, _i32p, C.c_int64, _i32p],
+        ),
+        "system_add_combinatorial_go_contact": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DATopologyStruct), C.c_double, C.c_double]),
         "num_da_terms": (C.c_int, [C.c_void_p]),
         "get_da_pairs": (C.c_int, [C.c_void_p, C.c_int, _i32p, C.c_int64, _i64p]),
         "context_create": (
@@ -393,6 +402,45 @@ class System:
     def add_pdns(self, group, topo, k, r0, theta0, phi0, sigma, delta):
         nd = np.asarray(topo.donors).reshape(-1, 3).shape[0]
         self._da("system_add_pdns", group, topo, [k, r0, theta0, phi0], nd, (sigma, delta))
+
+    def add_combinatorial_go_contact(self, group, topo, k, r0):
+        self._da("system_add_combinatorial_go_contact", group, topo, [], 0, (k, r0))
+
+    # ---- external (one bead each) and centre-of-mass terms ------------------------------------
+    def _rows(self, a, n, width, what):
+        a = _f64(a).reshape(-1)
+        assert a.size == n * width, f"{what}: expected {n} x {width} values, got {a.size}"
+        return a
+
+    def add_position_restraint(self, group, index, position, k, v0):
+        idx = _i32(index).reshape(-1)
+        n = idx.size
+        pos, k, v0 = self._rows(position, n, 3, "position"), self._rows(k, n, 1, "k"), self._rows(v0, n, 1, "v0")
+        self.lib.check(self.lib.fn["system_add_position_restraint"](self.handle, int(group), n, _p(idx, _i32p), _p(pos, _f64p), _p(k, _f64p), _p(v0, _f64p)))
+
+    def add_pulling(self, group, index, force):
+        idx = _i32(index).reshape(-1)
+        f = self._rows(force, idx.size, 3, "force")
+        self.lib.check(self.lib.fn["system_add_pulling"](self.handle, int(group), idx.size, _p(idx, _i32p), _p(f, _f64p)))
+
+    def add_exv_rectangular_box(self, group, eps, lower, upper, index, radius):
+        idx = _i32(index).reshape(-1)
+        lo, hi, r = self._rows(lower, 1, 3, "lower"), self._rows(upper, 1, 3, "upper"), self._rows(radius, idx.size, 1, "radius")
+        self.lib.check(self.lib.fn["system_add_exv_rectangular_box"](self.handle, int(group), float(eps), _p(lo, _f64p), _p(hi, _f64p), idx.size,
+                                                                      _p(idx, _i32p), _p(r, _f64p)))
+
+    def add_cylindrical_restraint(self, group, index, axis, shift, k, v0, periodic=False):
+        idx = _i32(index).reshape(-1)
+        n = idx.size
+        ax, sh = self._rows(axis, n, 3, "axis"), self._rows(shift, n, 3, "shift")
+        k, v0 = self._rows(k, n, 1, "k"), self._rows(v0, n, 1, "v0")
+        self.lib.check(self.lib.fn["system_add_cylindrical_restraint"](self.handle, int(group), int(bool(periodic)), n, _p(idx, _i32p), _p(ax, _f64p),
+                                                                        _p(sh, _f64p), _p(k, _f64p), _p(v0, _f64p)))
+
+    def add_harmonic_com_pulling(self, group, k, v0, group1, group2, periodic=False):
+        g1, g2 = _i32(group1).reshape(-1), _i32(group2).reshape(-1)
+        self.lib.check(self.lib.fn["system_add_harmonic_com_pulling"](self.handle, int(group), int(bool(periodic)), float(k), float(v0), g1.size,
+                                                                       _p(g1, _i32p), g2.size, _p(g2, _i32p)))
 
     # ---- pair -------------------------------------------------------------------------------
     def _per_bead(self, a):

@@ -259,8 +259,8 @@ class CustomHbondForce : public CustomForceBase {
     double cutoff_ = 1.0;
 };
 
-// Recorded so that the reference's generators compile and run; a Context refuses a System that contains one
-// (restraints and pulling are outside the hot-path scope).
+// One-bead external terms and the centroid spring (PositionRestraint, Pulling, EXVRectangularBox, CylindricalRestraint,
+// HarmonicCoMPulling generators): translated like every other Custom*Force, by their expression.
 class CustomExternalForce : public CustomForceBase {
   public:
     explicit CustomExternalForce(const std::string& energy) : CustomForceBase(energy) {}
@@ -274,8 +274,10 @@ class CustomCentroidBondForce : public CustomForceBase {
     int addGroup(const std::vector<int>& particles, const std::vector<double>& weights = {}) { groups_.emplace_back(particles, weights); return (int)groups_.size() - 1; }
     int addBond(const std::vector<int>& groups, const std::vector<double>& params = {}) { return add_row(groups, params, "CustomCentroidBondForce"); }
     void setUsesPeriodicBoundaryConditions(bool p) { periodic_ = p; }
+    bool usesPeriodicBoundaryConditions() const override { return periodic_; }
 
   private:
+    friend class b200::SystemCompiler;
     int ng_;
     std::vector<std::pair<std::vector<int>, std::vector<double>>> groups_;
 };

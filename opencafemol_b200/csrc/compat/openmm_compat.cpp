@@ -196,6 +196,19 @@ const char* kPDNS =                                                           //
     "K=pi/(2*delta);phi=angle(d2,a1,a2);theta=acos(cost1lim);cost1lim=min(max(cost1,-0.99999),0.99999);"
     "cost1=sin(t1)*sin(t2)*cos(phi1)-cos(t1)*cos(t2);t1=angle(d1,d3,a1);t2=angle(d3,a1,d2);phi1=dihedral(d1,d3,a1,d2);pi=3.1415926535897932385";
 
+// one-bead external terms, the centroid spring and the combinatorial contact
+const char* kPositionRestraint = "k*(((x-x0)^2+(y-y0)^2+(z-z0)^2)^(1/2)-v0)^2";  // PositionRestraintForceFieldGenerator.cpp:8-10
+const char* kPulling = "-kx*x-ky*y-kz*z";                                        // PullingForceFieldGenerator.cpp:5-7
+const char* kRectangularBox =                                                   // EXVRectangularBoxForceFieldGenerator.cpp:33-38
+    "epsilon*((radius/(x-x_lower))^12+(radius/(x_upper-x))^12+(radius/(y-y_lower))^12+(radius/(y_upper-y))^12+(radius/(z-z_lower))^12+"
+    "(radius/(z_upper-z))^12)";
+const char* kCylindricalRestraint =                                             // CylindricalRestraintForceFieldGenerator.cpp:10-17
+    "k*(dr-v0)^2;dr=((x-xh)^2+(y-yh)^2+(z-zh)^2)^(1/2);xh=ra_r*xa+x0;yh=ra_r*ya+y0;zh=ra_r*za+z0;ra_r=xa*x+ya*y+za*z";
+const char* kCylindricalRestraintPeriodic =                                     // CylindricalRestraintForceFieldGenerator.cpp:19-26
+    "k*(dr-v0)^2;dr=periodicdistance(x,y,z,xh,yh,zh);xh=ra_r*xa+x0;yh=ra_r*ya+y0;zh=ra_r*za+z0;ra_r=xa*x+ya*y+za*z";
+const char* kHarmonicCoMPulling = "0.5*k*(distance(g1,g2)-v0)^2";                // HarmonicCoMPullingForceFieldGenerator.cpp:5-7
+const char* kCombinatorialGoContact = "k*(5*(r0/distance(a1,d1))^12-6*(r0/distance(a1,d1))^10)";  // CombinatorialGoContact...cpp:5-10
+
 }  // namespace
 
 class SystemCompiler {
@@ -302,8 +315,12 @@ class SystemCompiler {
         } else if (dynamic_cast<const MonteCarloAnisotropicBarostat*>(&f) || dynamic_cast<const MonteCarloMembraneBarostat*>(&f)) {
             // not a term of the system tables: Context::create hands it to ocm_context_set_barostat
             if (!sys_.has_box_) throw OpenMMException("barostat should be used with periodic boundary condition.");
+        } else if (auto* p = dynamic_cast<const CustomExternalForce*>(&f)) {
+            add_external(*p, g);
+        } else if (auto* p = dynamic_cast<const CustomCentroidBondForce*>(&f)) {
+            add_centroid(*p, g);
         } else if (auto* p = dynamic_cast<const CustomForceBase*>(&f)) {
-            unsupported("external / centroid", *p);
+            unsupported("Custom force", *p);
         } else {
             throw OpenMMException("B200 engine: unknown Force class");
         }
@@ -508,6 +525,56 @@ class SystemCompiler {
         }
     }
 
+    // rows of `width` doubles starting at parameter column `col`
+    static std::vector<double> columns(const std::vector<CustomForceBase::Row>& rows, int col, int width) {
+        std::vector<double> out;
+        out.reserve(rows.size() * width);
+        for (auto& r : rows) for (int k = 0; k < width; k++) out.push_back(r.v[col + k]);
+        return out;
+    }
+
+    void add_external(const CustomExternalForce& f, int g) {
+        const Norm nz = normalise(f);
+        const auto idx = indices(f.rows_, 1);
+        const std::int64_t n = (std::int64_t)f.rows_.size();
+        if (nz.expr == kPositionRestraint) {
+            expect_names(nz.params, {"x0", "y0", "z0", "k", "v0"}, "PositionRestraint");
+            check(ocm_system_add_position_restraint(out_, g, n, idx.data(), columns(f.rows_, 0, 3).data(), column(f.rows_, 3).data(), column(f.rows_, 4).data()),
+                  "PositionRestraint");
+        } else if (nz.expr == kPulling) {
+            expect_names(nz.params, {"kx", "ky", "kz"}, "Pulling");
+            check(ocm_system_add_pulling(out_, g, n, idx.data(), columns(f.rows_, 0, 3).data()), "Pulling");
+        } else if (nz.expr == kRectangularBox) {
+            expect_names(nz.params, {"radius"}, "EXVRectangularBox");
+            const double lo[3] = {global_value(f, nz, "x_lower"), global_value(f, nz, "y_lower"), global_value(f, nz, "z_lower")};
+            const double hi[3] = {global_value(f, nz, "x_upper"), global_value(f, nz, "y_upper"), global_value(f, nz, "z_upper")};
+            check(ocm_system_add_exv_rectangular_box(out_, g, global_value(f, nz, "epsilon"), lo, hi, n, idx.data(), column(f.rows_, 0).data()), "EXVRectangularBox");
+        } else if (nz.expr == kCylindricalRestraint || nz.expr == kCylindricalRestraintPeriodic) {
+            expect_names(nz.params, {"xa", "ya", "za", "x0", "y0", "z0", "k", "v0"}, "CylindricalRestraint");
+            check(ocm_system_add_cylindrical_restraint(out_, g, nz.expr == kCylindricalRestraintPeriodic, n, idx.data(), columns(f.rows_, 0, 3).data(),
+                                                       columns(f.rows_, 3, 3).data(), column(f.rows_, 6).data(), column(f.rows_, 7).data()), "CylindricalRestraint");
+        } else {
+            unsupported("CustomExternalForce", f);
+        }
+    }
+
+    void add_centroid(const CustomCentroidBondForce& f, int g) {
+        const Norm nz = normalise(f);
+        if (nz.expr != kHarmonicCoMPulling || f.ng_ != 2) unsupported("CustomCentroidBondForce", f);
+        const double k = global_value(f, nz, "k"), v0 = global_value(f, nz, "v0");
+        for (auto& grp : f.groups_)
+            if (!grp.second.empty()) throw OpenMMException("B200 engine: CustomCentroidBondForce groups with explicit weights are not supported (the reference uses the masses)");
+        for (auto& r : f.rows_) {
+            if (r.p.size() != 2 || r.p[0] < 0 || r.p[1] < 0 || r.p[0] >= (int)f.groups_.size() || r.p[1] >= (int)f.groups_.size())
+                throw OpenMMException("CustomCentroidBondForce: group index out of range");
+            const std::vector<int>& a = f.groups_[r.p[0]].first;
+            const std::vector<int>& b = f.groups_[r.p[1]].first;
+            std::vector<std::int32_t> g1(a.begin(), a.end()), g2(b.begin(), b.end());
+            check(ocm_system_add_harmonic_com_pulling(out_, g, f.periodic_, k, v0, (std::int64_t)g1.size(), g1.data(), (std::int64_t)g2.size(), g2.data()),
+                  "HarmonicCoMPulling");
+        }
+    }
+
     void add_hbond(const CustomHbondForce& f, int g) {
         const Norm nz = normalise(f, &f.aparams_);
         if (f.method_ == CustomHbondForce::NoCutoff) throw OpenMMException("B200 engine: CustomHbondForce needs a cutoff method (the reference always sets one)");
@@ -531,6 +598,8 @@ class SystemCompiler {
             expect_names(nz.params, {"sigma", "delta", "k", "r0", "theta0", "phi0"}, "PDNS");
             check(ocm_system_add_pdns(out_, g, &t, column(f.rows_, 2).data(), column(f.rows_, 3).data(), column(f.rows_, 4).data(), column(f.rows_, 5).data(),
                                       uniform(f.rows_, 0, "PDNS sigma"), uniform(f.rows_, 1, "PDNS delta")), "PDNS");
+        } else if (nz.expr == kCombinatorialGoContact) {
+            check(ocm_system_add_combinatorial_go_contact(out_, g, &t, global_value(f, nz, "k"), global_value(f, nz, "r0")), "CombinatorialGoContact");
         } else {
             unsupported("CustomHbondForce", f);
         }

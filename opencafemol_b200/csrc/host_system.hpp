@@ -18,10 +18,18 @@ namespace ocm {
 enum BondedKind : int {
     B_HARMONIC_BOND = 0, B_GAUSSIAN_BOND, B_GO_CONTACT, B_3SPN2_BOND,
     B_HARMONIC_ANGLE, B_FLEX_ANGLE, B_GAUSSIAN_DIHEDRAL, B_COSINE_DIHEDRAL, B_FLEX_DIHEDRAL, B_3SPN2_STACK,
+    B_EXTERNAL,   // one-bead external terms; p[0] selects the form (ExternalForm), kExternalNpar parameters per term
     B_NUM_KINDS
 };
 
+// forms of B_EXTERNAL and their parameter rows (p[0] = form):
+//   X_POSITION_RESTRAINT  x0 y0 z0 k v0          X_PULLING  fx fy fz
+//   X_RECTANGULAR_BOX     eps lo[3] hi[3] radius X_CYLINDRICAL_RESTRAINT  axis[3] shift[3] k v0
+enum ExternalForm : int { X_POSITION_RESTRAINT = 0, X_PULLING, X_RECTANGULAR_BOX, X_CYLINDRICAL_RESTRAINT };
+constexpr int kExternalNpar = 10;
+
 inline int bonded_nbody(int kind) {
+    if (kind == B_EXTERNAL) return 1;
     if (kind <= B_3SPN2_BOND) return 2;
     if (kind <= B_FLEX_ANGLE || kind == B_3SPN2_STACK) return 3;
     return 4;
@@ -50,17 +58,24 @@ struct PairTerm {
 };
 
 // donor x acceptor ("CustomHbondForce"-like) term
-enum DAKind : int { DA_BASE_PAIR = 0, DA_CROSS_STACK = 1, DA_PDNS = 2 };
+enum DAKind : int { DA_BASE_PAIR = 0, DA_CROSS_STACK = 1, DA_PDNS = 2, DA_COMB_GO = 3 };
 
 struct DATerm {
     int kind, group, periodic, npar;
     double cutoff;
     double g0, g1, g2;                  // BP: alpha, K_BP; CS: K_BP, K_CS, alpha; PDNS: sigma, delta
     std::vector<int32_t> donors, acceptors;  // 3 per entry, -1 = unused
-    std::vector<double> p;              // npar per donor (BP, PDNS) or per acceptor (CS)
+    std::vector<double> p;              // npar per donor (BP, PDNS) or per acceptor (CS); none for DA_COMB_GO (g0 = k, g1 = r0)
     std::vector<uint64_t> excl;         // sorted keys donor * n_acceptors + acceptor
     int64_t nd() const { return (int64_t)donors.size() / 3; }
     int64_t na() const { return (int64_t)acceptors.size() / 3; }
+};
+
+// harmonic spring between the mass-weighted centres of two bead groups ("CustomCentroidBondForce")
+struct ComTerm {
+    int group, periodic;
+    double k, v0;
+    std::vector<int32_t> g1, g2;
 };
 
 }  // namespace ocm
@@ -73,6 +88,7 @@ struct ocm_system {
     std::vector<ocm::BondedTerm> bonded;
     std::vector<ocm::PairTerm> pairs;
     std::vector<ocm::DATerm> das;
+    std::vector<ocm::ComTerm> coms;
 };
 
 namespace ocm {
@@ -232,8 +248,8 @@ inline int add_da(ocm_system* s, int kind, int group, const ocm_da_topology* top
     t.donors.assign(topo->donors, topo->donors + 3 * topo->n_donors);
     t.acceptors.assign(topo->acceptors, topo->acceptors + 3 * topo->n_acceptors);
     // which slots the expression of each kind reads (d1,d2,d3 / a1,a2,a3); d1 and a1 always (cutoff)
-    static const bool need_d[3][3] = {{true, true, false}, {true, true, false}, {true, true, true}};
-    static const bool need_a[3][3] = {{true, true, false}, {true, true, true}, {true, true, false}};
+    static const bool need_d[4][3] = {{true, true, false}, {true, true, false}, {true, true, true}, {true, false, false}};
+    static const bool need_a[4][3] = {{true, true, false}, {true, true, true}, {true, true, false}, {true, false, false}};
     for (int64_t d = 0; d < topo->n_donors; d++)
         for (int q = 0; q < 3; q++) {
             int32_t v = t.donors[3 * d + q];

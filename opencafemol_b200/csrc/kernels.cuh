@@ -139,6 +139,15 @@ struct DAListDev {
     uint2* entries;                    // x = term << 24 | donor, y = acceptor
 };
 
+// spring between the mass-weighted centres of two bead groups: idx / w hold group 1 then group 2, w = mass / group mass
+struct ComDev {
+    int group, periodic, n1, n2, begin, pad;
+    double k, v0;
+    const int* idx;
+    const double* w;
+};
+constexpr int kComBlock = 256;
+
 struct WorkSeg {
     int block_begin, nblocks, kind, id, tpb, chunk;  // pair segments: tpb threads per bead, chunk beads per block
     int staged;                                       // unused (the bulk-copy row staging experiment of round 1 was removed)
@@ -171,7 +180,7 @@ __device__ __forceinline__ int list_nkeys(const PairListDev& L) { return L.grid-
 __device__ __forceinline__ int list_rows(const PairListDev& L) { return L.role ? L.cell_start[list_nkeys(L)] : L.np; }
 // rows of owned beads (they come first when halo_split is set)
 __device__ __forceinline__ int list_rows_owned(const PairListDev& L) { return L.halo_split ? L.cell_start[L.grid->ncell * L.nrep] : list_rows(L); }
-__device__ __forceinline__ int bonded_nbody_dev(int kind) { return kind <= 3 ? 2 : ((kind <= 5 || kind == 9) ? 3 : 4); }
+__device__ __forceinline__ int bonded_nbody_dev(int kind) { return kind == 10 ? 1 : (kind <= 3 ? 2 : ((kind <= 5 || kind == 9) ? 3 : 4)); }
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int to_fix(double x, double inv_l) {
@@ -1138,6 +1147,18 @@ __device__ __forceinline__ double da_eval(const DATermDev& T, int d, int a, cons
     const int a1 = T.acceptors[3 * a], a2 = T.acceptors[3 * a + 1], a3 = T.acceptors[3 * a + 2];
     D3 fd1 = {0, 0, 0}, fd2 = {0, 0, 0}, fd3 = {0, 0, 0}, fa1 = {0, 0, 0}, fa2 = {0, 0, 0}, fa3 = {0, 0, 0};
     double E;
+    if (T.kind == 3) {
+        // combinatorial Go contact, one bead per donor / acceptor; g0 = k, g1 = r0     CombinatorialGoContact...cpp:5-10
+        const D3 rv = d3sub(x, a1, d1, per, P);                 // a1 - d1
+        const double r2 = d3dot(rv, rv), s2 = T.g1 * T.g1 / r2, s4 = s2 * s2, s10 = s4 * s4 * s2, s12 = s10 * s2;
+        E = T.g0 * (5.0 * s12 - 6.0 * s10);
+        if (fbuf) {
+            const double sr = T.g0 * 60.0 * (s10 - s12) / r2;   // (dE/dr) / r
+            add_force_fixed_d(fbuf, P.n, a1, -sr * rv.x, -sr * rv.y, -sr * rv.z);
+            add_force_fixed_d(fbuf, P.n, d1, sr * rv.x, sr * rv.y, sr * rv.z);
+        }
+        return E;
+    }
     if (T.kind == 0) {
         // 3SPN.2 base pair, per-donor eps, r0, theta0_1, theta0_2, phi0; g0 = alpha, g1 = K_BP
         // ThreeSPN2BasePairForceFieldGenerator.cpp:8-26
@@ -1339,6 +1360,61 @@ __device__ __forceinline__ void bonded_eval(int kind, const double* __restrict__
     }
 }
 
+// one-bead external terms on the absolute (unwrapped) master position; p[0] = form, rows as in host_system.hpp
+__device__ __forceinline__ double external_term(const double* __restrict__ p, int i, bool per, const StepParams& P,
+                                                const double* __restrict__ x, unsigned long long* __restrict__ fbuf) {
+    const double px = x[3 * i], py = x[3 * i + 1], pz = x[3 * i + 2];
+    const int form = (int)p[0];
+    double E, gx, gy, gz;  // energy and its gradient
+    if (form == 0) {
+        // PositionRestraint: k (|x - x0| - v0)^2     PositionRestraintForceFieldGenerator.cpp:8-10 (the periodic string is
+        // never used, :12-17)
+        const double dx = px - p[1], dy = py - p[2], dz = pz - p[3];
+        const double r = sqrt(dx * dx + dy * dy + dz * dz), d = r - p[5];
+        E = p[4] * d * d;
+        const double s = (r > 0.0) ? 2.0 * p[4] * d / r : 0.0;
+        gx = s * dx; gy = s * dy; gz = s * dz;
+    } else if (form == 1) {
+        // Pulling: -kx x - ky y - kz z               PullingForceFieldGenerator.cpp:5-7
+        E = -(p[1] * px + p[2] * py + p[3] * pz);
+        gx = -p[1]; gy = -p[2]; gz = -p[3];
+    } else if (form == 2) {
+        // EXVRectangularBox: eps sum (radius / (x - lo))^12 + (radius / (hi - x))^12     EXVRectangularBox...cpp:33-38
+        const double eps = p[1], rad = p[8];   // row: eps lo[3] hi[3] radius
+        const double q[3] = {px, py, pz};
+        double g[3];
+        E = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const double il = 1.0 / (q[a] - p[2 + a]), iu = 1.0 / (p[5 + a] - q[a]);
+            const double sl = rad * il, su = rad * iu;
+            const double sl2 = sl * sl, su2 = su * su, sl6 = sl2 * sl2 * sl2, su6 = su2 * su2 * su2;
+            const double el = sl6 * sl6, eu = su6 * su6;
+            E += eps * (el + eu);
+            g[a] = 12.0 * eps * (eu * iu - el * il);
+        }
+        gx = g[0]; gy = g[1]; gz = g[2];
+    } else {
+        // CylindricalRestraint: k (dr - v0)^2, dr = |x - h|, h = (axis . x) axis + shift     Cylindrical...cpp:10-26
+        // x - h = (1 - a a^T) x - shift; its derivative with respect to x is the (symmetric) matrix 1 - a a^T
+        const double ax = p[1], ay = p[2], az = p[3];
+        const double ra = ax * px + ay * py + az * pz;
+        double dx = px - (ra * ax + p[4]), dy = py - (ra * ay + p[5]), dz = pz - (ra * az + p[6]);
+        if (per) {
+            dx -= P.box[0] * rint(dx * P.inv_box[0]);
+            dy -= P.box[1] * rint(dy * P.inv_box[1]);
+            dz -= P.box[2] * rint(dz * P.inv_box[2]);
+        }
+        const double r = sqrt(dx * dx + dy * dy + dz * dz), d = r - p[8];
+        E = p[7] * d * d;
+        const double s = (r > 0.0) ? 2.0 * p[7] * d / r : 0.0;
+        const double da = ax * dx + ay * dy + az * dz;
+        gx = s * (dx - da * ax); gy = s * (dy - da * ay); gz = s * (dz - da * az);
+    }
+    if (fbuf) add_force_fixed_d(fbuf, P.n, i, -gx, -gy, -gz);
+    return E;
+}
+
 // computes one bonded term; accumulates forces (fbuf != null) and returns the energy
 __device__ __forceinline__ double bonded_term(int kind, const BondedDev& B, int m, const StepParams& P,
                                               const double* __restrict__ x, unsigned long long* __restrict__ fbuf, int* group) {
@@ -1370,6 +1446,7 @@ __device__ __forceinline__ double bonded_term(int kind, const BondedDev& B, int 
         }
         return E;
     }
+    if (kind == 10) return external_term(p, B.idx[m], per, P, x, fbuf);
     if (kind <= 3) {
         const int i = B.idx[2 * m], j = B.idx[2 * m + 1];
         const D3 d = d3sub(x, i, j, per, P);
@@ -1476,6 +1553,51 @@ __global__ void __launch_bounds__(kBlock, OCM_FORCE_MINBLOCKS) force_kernel(cons
             int g;
             bonded_term(sg.id, B, m, P, x, fbuf, &g);
         }
+    }
+}
+
+// HarmonicCoMPulling (HarmonicCoMPullingForceFieldGenerator.cpp:5-18): E = 1/2 k (|c1 - c2| - v0)^2.  One block per term: both
+// centres are reduced in a fixed order (lane strides, xor tree, warp partials summed 0..7), so the result does not depend on
+// the schedule; every bead then takes its mass share of the spring force.  egroup != null: the energy only.
+__global__ void __launch_bounds__(kComBlock) com_kernel(const ComDev* __restrict__ terms, StepParams P, const double* __restrict__ x,
+                                                         unsigned long long* __restrict__ fbuf, double* __restrict__ egroup) {
+    const ComDev T = terms[blockIdx.x];
+    __shared__ double part[6][kComBlock / 32];
+    double c1x = 0, c1y = 0, c1z = 0, c2x = 0, c2y = 0, c2z = 0;
+    const int nt = T.n1 + T.n2;
+    for (int m = threadIdx.x; m < nt; m += kComBlock) {
+        const int i = T.idx[m];
+        const double w = T.w[m], wx = w * x[3 * i], wy = w * x[3 * i + 1], wz = w * x[3 * i + 2];
+        if (m < T.n1) { c1x += wx; c1y += wy; c1z += wz; } else { c2x += wx; c2y += wy; c2z += wz; }
+    }
+    double v[6] = {c1x, c1y, c1z, c2x, c2y, c2z};
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+        if ((threadIdx.x & 31) == 0) part[q][threadIdx.x >> 5] = v[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        double s = 0;
+        for (int wv = 0; wv < kComBlock / 32; wv++) s += part[q][wv];
+        v[q] = s;
+    }
+    double dx = v[0] - v[3], dy = v[1] - v[4], dz = v[2] - v[5];
+    if (T.periodic) {
+        dx -= P.box[0] * rint(dx * P.inv_box[0]);
+        dy -= P.box[1] * rint(dy * P.inv_box[1]);
+        dz -= P.box[2] * rint(dz * P.inv_box[2]);
+    }
+    const double r = sqrt(dx * dx + dy * dy + dz * dz), d = r - T.v0;
+    if (egroup) {
+        if (threadIdx.x == 0) atomicAdd(&egroup[T.group], 0.5 * T.k * d * d);
+        return;
+    }
+    const double s = (r > 0.0) ? T.k * d / r : 0.0;   // (dE/dr) / r
+    for (int m = threadIdx.x; m < nt; m += kComBlock) {
+        const double f = (m < T.n1 ? -s : s) * T.w[m];
+        add_force_fixed_d(fbuf, P.n, T.idx[m], f * dx, f * dy, f * dz);
     }
 }
 
@@ -1687,7 +1809,7 @@ __global__ void __launch_bounds__(kBlock) energy_kernel(const WorkSeg* __restric
             // replica batch: energies are kept per replica (40 slots each); bonded terms never span replicas
             if (g >= 0 && sg.kind == SEG_BONDED) {
                 const BondedDev& B = bonded[sg.id];
-                const int nbody = (sg.id <= 3) ? 2 : ((sg.id <= 5 || sg.id == 9) ? 3 : 4);
+                const int nbody = bonded_nbody_dev(sg.id);
                 const int rep = B.idx[nbody * (blk * kBlock + threadIdx.x)] / P.nper;
                 atomicAdd(&egroup[rep * 40 + g], E);
             }

@@ -192,6 +192,10 @@ struct ocm_context {
     std::vector<std::unique_ptr<PairListHost>> lists;
     std::vector<int> term_list, term_member;  // pair term -> (list, member)
     DevBuf<PairListDev> d_lists;
+    int n_coms = 0;                         // centre-of-mass pulling terms (com_kernel: one block each)
+    DevBuf<ComDev> d_coms;
+    DevBuf<int> com_idx;
+    DevBuf<double> com_w;
     BondedDev bonded_h[B_NUM_KINDS]{};
     DevBuf<int> b_idx[B_NUM_KINDS], b_meta[B_NUM_KINDS];
     DevBuf<double> b_par[B_NUM_KINDS], b_tabs;
@@ -850,6 +854,28 @@ static void compile_bonded(ocm_context* c) {
     c->d_bonded.upload(std::vector<BondedDev>(c->bonded_h, c->bonded_h + B_NUM_KINDS));
 }
 
+static void compile_coms(ocm_context* c) {
+    c->n_coms = (int)c->sys.coms.size();
+    if (!c->n_coms) return;
+    std::vector<int> idx;
+    std::vector<double> w;
+    std::vector<ComDev> terms;
+    for (const auto& t : c->sys.coms) {
+        ComDev D{};
+        D.group = t.group; D.periodic = t.periodic; D.n1 = (int)t.g1.size(); D.n2 = (int)t.g2.size(); D.begin = (int)idx.size();
+        D.k = t.k; D.v0 = t.v0;
+        for (const auto* grp : {&t.g1, &t.g2}) {
+            double M = 0;
+            for (int32_t i : *grp) M += c->sys.mass[i];
+            for (int32_t i : *grp) { idx.push_back(i); w.push_back(c->sys.mass[i] / M); }
+        }
+        terms.push_back(D);
+    }
+    c->com_idx.upload(idx); c->com_w.upload(w);
+    for (auto& D : terms) { D.idx = c->com_idx.p + D.begin; D.w = c->com_w.p + D.begin; }
+    c->d_coms.upload(terms);
+}
+
 // ---- whole-step persistent kernel: static tables of one replica ------------------------------------------
 template <typename T>
 static const T* rep_upload(ocm_context* c, const std::vector<T>& v) {
@@ -867,7 +893,8 @@ static void compile_replica_tables(ocm_context* c) {
     const int nper = c->nper;
     if (c->dd || (c->sys.has_box && !c->vbox) || !S1.das.empty() || nper > 256 || nper < 2) return;
     if ((int)c->lists.size() > kRepMaxLists) return;
-    for (const auto& t : S1.bonded) if (t.kind == B_3SPN2_STACK && t.n() > 0) return;
+    for (const auto& t : S1.bonded) if (t.kind >= B_3SPN2_STACK && t.n() > 0) return;   // (base stacking, external terms)
+    if (!S1.coms.empty()) return;
     RepParams& R = c->rep;
     R = RepParams{};
     R.nper = nper; R.nrep = c->nrep; R.nlists = 0;
@@ -1350,7 +1377,7 @@ static void launch_tile(ocm_context* c, PairListHost& L, const TileLaunch& T, in
 // phase 0: all forces.  Slab decomposition with split tile lists: phase 1 = the interior tile entries only (owned beads on
 // both sides: they can run while the step's halo positions are still travelling), phase 2 = everything else.
 static void enqueue_forces(ocm_context* c, cudaStream_t s, int phase = 0) {
-    if (c->total_blocks == 0 && c->tile_blocks == 0) return;
+    if (c->total_blocks == 0 && c->tile_blocks == 0 && c->n_coms == 0) return;
     if (phase == 1) {
         for (auto& Lp : c->lists)
             if (Lp->tiled && Lp->np && Lp->tile_nblocks_in > 0) launch_tile(c, *Lp, Lp->launch_in, Lp->tile_nblocks_in, s);
@@ -1381,6 +1408,10 @@ static void enqueue_forces(ocm_context* c, cudaStream_t s, int phase = 0) {
         c->n_launches += 1;
     }
     if (fork) CUDA_TRY(cudaStreamWaitEvent(s, c->ev_join, 0));
+    if (c->n_coms > 0) {
+        com_kernel<<<c->n_coms, kComBlock, 0, s>>>(c->d_coms.p, c->P, c->x.p, c->fbuf.p, nullptr);
+        c->n_launches += 1;
+    }
 }
 
 // size (or re-size) the Verlet rows from a counting pass at the current positions
@@ -1766,6 +1797,7 @@ static void enqueue_energies(ocm_context* c, cudaStream_t s) {
         if (L.np == 0 || !L.tiled) continue;
         tile_energy_kernel<true><<<L.dev.row_capacity / 64, kBlock, 0, s>>>(c->d_lists.p, (int)l, c->P, c->egroup.p);
     }
+    if (c->n_coms > 0) com_kernel<<<c->n_coms, kComBlock, 0, s>>>(c->d_coms.p, c->P, c->x.p, nullptr, c->egroup.p);
 }
 
 static void compute_forces_into_fbuf(ocm_context* c) {
@@ -2066,6 +2098,61 @@ int ocm_system_add_3spn2_cross_stacking(ocm_system* s, int g, const ocm_da_topol
                                         const double* t03, const double* t0CS, double K_BP, double K_CS, double alpha) {
     return add_da(s, DA_CROSS_STACK, g, topo, false, {eps, r0, t03, t0CS}, K_BP, K_CS, alpha, "3spn2_cross_stacking");
 }
+static int add_external(ocm_system* s, int form, int g, int per, int64_t n, const int32_t* index, const std::vector<std::pair<const double*, int>>& cols,
+                        const std::vector<double>& globals, const char* what) {
+    // one row of kExternalNpar doubles per term: form, the globals, then the per-term columns (pointer, width)
+    if (n < 0 || (n > 0 && !index)) return fail(std::string(what) + ": bad arguments");
+    for (auto& cw : cols) if (n > 0 && !cw.first) return fail(std::string(what) + ": null parameter array");
+    std::vector<std::vector<double>> col(kExternalNpar, std::vector<double>((size_t)n, 0.0));
+    std::fill(col[0].begin(), col[0].end(), (double)form);
+    int q = 1;
+    for (double v : globals) { std::fill(col[q].begin(), col[q].end(), v); q++; }
+    for (auto& cw : cols)
+        for (int w = 0; w < cw.second; w++, q++)
+            for (int64_t m = 0; m < n; m++) col[q][m] = cw.first[(size_t)m * cw.second + w];
+    std::vector<const double*> ptr;
+    for (auto& v : col) ptr.push_back(n > 0 ? v.data() : reinterpret_cast<const double*>(&q));
+    return add_bonded(s, B_EXTERNAL, g, per, n, index, ptr, what);
+}
+int ocm_system_add_position_restraint(ocm_system* s, int g, int64_t n, const int32_t* index, const double* pos3, const double* k, const double* v0) {
+    return add_external(s, X_POSITION_RESTRAINT, g, 0, n, index, {{pos3, 3}, {k, 1}, {v0, 1}}, {}, "position_restraint");
+}
+int ocm_system_add_pulling(ocm_system* s, int g, int64_t n, const int32_t* index, const double* force3) {
+    return add_external(s, X_PULLING, g, 0, n, index, {{force3, 3}}, {}, "pulling");
+}
+int ocm_system_add_exv_rectangular_box(ocm_system* s, int g, double eps, const double* lower3, const double* upper3, int64_t n, const int32_t* index,
+                                       const double* radius) {
+    if (!s || !lower3 || !upper3) return fail("exv_rectangular_box: null argument");
+    if (s->has_box) return fail("exv_rectangular_box: RectangularBox interaction does not work under periodic boundary condition");
+    for (int a = 0; a < 3; a++) if (!(upper3[a] > lower3[a])) return fail("exv_rectangular_box: the upper edge must be larger than the lower edge");
+    return add_external(s, X_RECTANGULAR_BOX, g, 0, n, index, {{radius, 1}},
+                        {eps, lower3[0], lower3[1], lower3[2], upper3[0], upper3[1], upper3[2]}, "exv_rectangular_box");
+}
+int ocm_system_add_cylindrical_restraint(ocm_system* s, int g, int per, int64_t n, const int32_t* index, const double* axis3, const double* shift3,
+                                         const double* k, const double* v0) {
+    return add_external(s, X_CYLINDRICAL_RESTRAINT, g, per, n, index, {{axis3, 3}, {shift3, 3}, {k, 1}, {v0, 1}}, {}, "cylindrical_restraint");
+}
+int ocm_system_add_harmonic_com_pulling(ocm_system* s, int g, int per, double k, double v0, int64_t n1, const int32_t* g1, int64_t n2, const int32_t* g2) {
+    if (!s) return fail("null system");
+    if (g < 0 || g > 31) return fail("force group must be in 0..31");
+    if (n1 <= 0 || n2 <= 0 || !g1 || !g2) return fail("harmonic_com_pulling: both bead groups must be non-empty");
+    if (per && !s->has_box) return fail("harmonic_com_pulling: periodic term without a box");
+    if (check_indices(s, g1, n1, "harmonic_com_pulling") || check_indices(s, g2, n2, "harmonic_com_pulling")) return 1;
+    ComTerm t;
+    t.group = g; t.periodic = per ? 1 : 0; t.k = k; t.v0 = v0;
+    t.g1.assign(g1, g1 + n1); t.g2.assign(g2, g2 + n2);
+    for (const auto* grp : {&t.g1, &t.g2}) {
+        double M = 0;
+        for (int32_t i : *grp) M += s->mass[i];
+        if (!(M > 0)) return fail("harmonic_com_pulling: a bead group has no mass");
+    }
+    s->coms.push_back(std::move(t));
+    return 0;
+}
+int ocm_system_add_combinatorial_go_contact(ocm_system* s, int g, const ocm_da_topology* topo, double k, double r0) {
+    if (!(r0 > 0)) return fail("combinatorial_go_contact: r0 must be positive");
+    return add_da(s, DA_COMB_GO, g, topo, true, {}, k, r0, 0, "combinatorial_go_contact");
+}
 int ocm_system_add_pdns(ocm_system* s, int g, const ocm_da_topology* topo, const double* k, const double* r0, const double* theta0,
                         const double* phi0, double sigma, double delta) {
     if (!(sigma > 0) || !(delta > 0)) return fail("pdns: sigma and delta must be positive");
@@ -2117,11 +2204,13 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
     if (nrep < 1) return fail("context_create_batch: at least one replica");
     if (nrep > 1 && sys->has_box) return fail("context_create_batch: replica batches need an unlimited boundary (no box)");
     if (nrep > 1 && !sys->das.empty()) return fail("context_create_batch: donor-acceptor terms are not supported in replica batches yet");
+    if (nrep > 1 && !sys->coms.empty()) return fail("context_create_batch: centre-of-mass pulling terms are not supported in replica batches");
     if ((int64_t)sys->n * nrep >= (1 << 24)) return fail("context_create: at most 16,777,215 particles are supported");
     if (comm) {
         if (!comm->impl) return fail("context_create_slab: communicator is closed");
         if (!sys->has_box) return fail("context_create_slab: a slab decomposition needs a periodic box");
         if (!sys->das.empty()) return fail("context_create_slab: donor-acceptor terms are not supported under a slab decomposition");
+        if (!sys->coms.empty()) return fail("context_create_slab: centre-of-mass pulling terms are not supported under a slab decomposition");
         if (dd_axis < 0 || dd_axis > 2) return fail("context_create_slab: axis must be 0, 1 or 2");
         if (dd_rank < 0 || dd_rank >= comm->impl->world) return fail("context_create_slab: rank out of range");
         if (comm->rank >= 0 && comm->rank != dd_rank) return fail("context_create_slab: the communicator belongs to another rank");
@@ -2169,7 +2258,6 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
                 u.p0.insert(u.p0.end(), t.p0.begin(), t.p0.end());
                 u.p1.insert(u.p1.end(), t.p1.begin(), t.p1.end());
                 u.p2.insert(u.p2.end(), t.p2.begin(), t.p2.end());
-            u.p2.insert(u.p2.end(), t.p2.begin(), t.p2.end());
                 u.cls.insert(u.cls.end(), t.cls.begin(), t.cls.end());
                 for (int32_t v : t.part) u.part.push_back(v + r * np);
                 for (auto& e : t.excl) u.excl.emplace_back(e.first + r * np, e.second + r * np);
@@ -2229,6 +2317,7 @@ static int create_context(const ocm_system* sys, int nrep, double T, double gamm
             for (int k = 0; k < 3; k++)
                 if (L->rc_list + c->skin > 0.5 * c->sys.box[k]) c->skin = std::max(0.0, 0.5 * c->sys.box[k] - L->rc_list) * 0.999;
     compile_bonded(c);
+    compile_coms(c);
     update_params(c);
     compile_replica_tables(c);
     c->nst = initial_nst(c);

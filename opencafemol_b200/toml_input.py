@@ -422,8 +422,69 @@ def read_toml(path_or_dict, base_dir=None) -> SystemSpec:
     topo.make_molecule("bond")
     for gf in ff.get("global", []):
         _read_global(spec, gf, topo, periodic, attr)
+    for xf in ff.get("external", []):
+        _read_external(spec, xf, topo, periodic)
     spec.topology = topo
     return spec
+
+
+def _read_external(spec, xf, topo, periodic):
+    """[[forcefields.external]] (src/input/ReadTOMLInput.cpp:763-870 and the readers of
+    ReadTOMLForceFieldGenerator.cpp:2496-2790); unit handling as the readers do it, quirks included."""
+    inter = xf["interaction"]
+    env = xf.get("env")
+    n = topo.size()
+    if inter == "CoMPullingForce":
+        if xf["potential"] != "Harmonic":
+            raise RuntimeError(f"[error] invalid potential {xf['potential']} found.")
+        for p in xf["parameters"]:
+            # read_toml_harmonic_com_pulling_ff_generator (:2622-2659): k and v0 are handed over unconverted (SURVEY.md C.11)
+            g1, g2 = p["indices_pair"]
+            spec.add_term(Term("harmonic_com_pulling", "HamonicCoMPulling",
+                               dict(k=float(_param(p, env, "k")), v0=float(_param(p, env, "v0")), group1=list(g1), group2=list(g2), periodic=periodic)))
+    elif inter == "PullingForce":
+        # read_toml_pulling_ff_generator (:2506-2548): kcal/(mol A) -> kJ/(mol nm)
+        idx = [_index(p, env, "read_toml_pulling_ff_generator", n) for p in xf["parameters"]]
+        f = [[c * KJ_PER_KCAL * 10.0 for c in _param(p, env, "force")] for p in xf["parameters"]]
+        spec.add_term(Term("pulling", "Pulling", dict(index=idx, force=f)))
+    elif inter == "PositionRestraint":
+        if xf["potential"] != "Harmonic":
+            raise RuntimeError(f"[error] invalid potential {xf['potential']} found.")
+        # read_toml_position_restraint_ff_generator (:2559-2611)
+        prm = xf["parameters"]
+        idx = [_index(p, env, "read_toml_position_restraint_ff_generator", n) for p in prm]
+        pos = [[c * NM_PER_ANGSTROM for c in _param(p, env, "position")] for p in prm]
+        k = [_param(p, env, "k") * KJ_PER_KCAL * 100.0 for p in prm]
+        v0 = [_param(p, env, "v0") * NM_PER_ANGSTROM for p in prm]
+        spec.add_term(Term("position_restraint", "PositionRestraint", dict(index=idx, position=pos, k=k, v0=v0)))
+    elif inter == "CylindricalRestraint":
+        if xf["potential"] != "Harmonic":
+            raise RuntimeError(f"[error] invalid potential {xf['potential']} found.")
+        # read_toml_cylindrical_restraint_ff_generator (:2720-2775) and the generator's constructor (…Generator.hpp:20-51):
+        # the axis is normalised, the shift made orthogonal to it
+        prm = xf["parameters"]
+        idx = [_index(p, env, "read_toml_position_restraint_ff_generator", n) for p in prm]
+        axis = np.array([[c * NM_PER_ANGSTROM for c in _param(p, env, "axis")] for p in prm], float).reshape(-1, 3)
+        shift = np.array([[c * NM_PER_ANGSTROM for c in _param(p, env, "shift")] for p in prm], float).reshape(-1, 3)
+        axis = axis / np.sqrt((axis * axis).sum(1))[:, None]
+        shift = shift - (axis * shift).sum(1)[:, None] * axis
+        k = [_param(p, env, "k") * KJ_PER_KCAL * 100.0 for p in prm]
+        v0 = [_param(p, env, "v0") * NM_PER_ANGSTROM for p in prm]
+        spec.add_term(Term("cylindrical_restraint", "CylinderRestraint", dict(index=idx, axis=axis, shift=shift, k=k, v0=v0, periodic=periodic)))
+    elif inter == "RectangularBox":
+        if xf["potential"] != "ExcludedVolumeWall":
+            raise RuntimeError(f"[error] invalid potential {xf['potential']} found.")
+        if periodic:
+            raise RuntimeError("[error] read_toml_rectangular_box_ff_generator : RectangularBox interaction does not work under "
+                               "periodic boundary condition. Use unlimited boundary.")
+        # read_toml_exv_rectangular_box_ff_generator (:2665-2710): epsilon is handed over unconverted (SURVEY.md C.11)
+        prm = xf["parameters"]
+        lo = [c * NM_PER_ANGSTROM for c in _param(xf["box"], env, "lower")]
+        hi = [c * NM_PER_ANGSTROM for c in _param(xf["box"], env, "upper")]
+        idx = [_param(p, env, "index") + _param(p, env, "offset", 0) for p in prm]
+        rad = [_param(p, env, "radius") * NM_PER_ANGSTROM for p in prm]
+        spec.add_term(Term("exv_rectangular_box", "EXVRectangularBox", dict(eps=float(_param(xf, env, "epsilon")), lower=lo, upper=hi, index=idx, radius=rad)))
+    # (any other interaction name is skipped without a message, as ReadTOMLInput.cpp:767-868 does)
 
 
 def _read_local(spec, lf, topo, periodic):
@@ -764,6 +825,8 @@ def _read_global(spec, gf, topo, periodic, attr):
         return _base_pair(spec, gf, topo, periodic, pot)
     if pot == "PDNS":
         return _pdns(spec, gf, periodic)
+    if pot == "CombinatorialGoContact":
+        return _combinatorial_go(spec, gf, topo, periodic)
     env = gf.get("env")
     n = topo.size()
     params = gf.get("parameters", [])
@@ -874,6 +937,27 @@ def _read_global(spec, gf, topo, periodic, attr):
             spec.add_term(Term("trigonometric", pot, dict(rc=(mr + sr) * 0.5, eps=eps, sigma=sig, omega=om, topo=topo_for(has))))
     else:
         raise NotImplementedError(f"global force field {pot} is not in scope yet")
+
+
+def _combinatorial_go(spec, gf, topo, periodic):
+    """read_toml_combinatorial_go_contact_ff_generators (ReadTOMLForceFieldGenerator.cpp:2307-2402), one term per
+    parameter row.  As the reference runs it: the `offset` is computed and then dropped (the un-offset index
+    lists reach the generator, :2336-2339), and the ignore list, pairs of PARTICLE indices, is handed to
+    CustomHbondForce::addExclusion, which takes (donor number, acceptor number) (CombinatorialGoContact...cpp:37-41); pairs that
+    are not valid numbers there make OpenMM (and this engine) refuse the system."""
+    env = gf.get("env")
+    cutoff_ratio = float(gf.get("cutoff", 1.8))
+    excl = np.zeros((0, 2), np.int32)
+    if "ignore" in gf:
+        excl, _ = _read_ignore(gf, topo)
+    for p in gf["parameters"]:
+        first, second = _param(p, env, "indices_pair")
+        k = _param(p, env, "k") * KJ_PER_KCAL
+        r0 = _param(p, env, "v0") * NM_PER_ANGSTROM
+        don = np.full((len(first), 3), -1, np.int32); don[:, 0] = first
+        acc = np.full((len(second), 3), -1, np.int32); acc[:, 0] = second
+        da = DATopology(don, acc, r0 * cutoff_ratio, np.asarray(excl, np.int32).reshape(-1, 2), periodic)
+        spec.add_term(Term("combinatorial_go_contact", "CombinatorialGoContact", dict(topo=da, k=k, r0=r0)))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -53,8 +53,10 @@ inline Vec3 cross(Vec3 a, Vec3 b) {
 
 enum BondedKind {
     B_HARMONIC_BOND, B_GAUSSIAN_BOND, B_GO_CONTACT, B_3SPN2_BOND,
-    B_HARMONIC_ANGLE, B_FLEX_ANGLE, B_GAUSSIAN_DIHEDRAL, B_COSINE_DIHEDRAL, B_FLEX_DIHEDRAL, B_3SPN2_STACK
+    B_HARMONIC_ANGLE, B_FLEX_ANGLE, B_GAUSSIAN_DIHEDRAL, B_COSINE_DIHEDRAL, B_FLEX_DIHEDRAL, B_3SPN2_STACK,
+    B_EXTERNAL  // one-bead "CustomExternalForce" terms, p[0] = form (ExternalForm)
 };
+enum ExternalForm { X_POSITION_RESTRAINT, X_PULLING, X_RECTANGULAR_BOX, X_CYLINDRICAL_RESTRAINT };
 
 struct BondedTerm {
     BondedKind kind;
@@ -85,7 +87,7 @@ struct PairTerm {
 };
 
 // donor x acceptor ("CustomHbondForce"-like) term, SURVEY.md B.5
-enum DAKind { DA_BASE_PAIR, DA_CROSS_STACK, DA_PDNS };
+enum DAKind { DA_BASE_PAIR, DA_CROSS_STACK, DA_PDNS, DA_COMB_GO };
 struct DATerm {
     DAKind kind;
     int group, periodic;
@@ -99,6 +101,13 @@ struct DATerm {
     int64_t na() const { return (int64_t)acceptors.size() / 3; }
 };
 
+// spring between the mass-weighted centres of two bead groups ("CustomCentroidBondForce", default weights)
+struct ComTerm {
+    int group, periodic;
+    double k, v0;
+    std::vector<int32_t> g1, g2;
+};
+
 }  // namespace
 
 struct ocm_system {
@@ -109,6 +118,7 @@ struct ocm_system {
     std::vector<BondedTerm> bonded;
     std::vector<PairTerm> pairs;
     std::vector<DATerm> das;
+    std::vector<ComTerm> coms;
 };
 
 struct ocm_context {
@@ -277,9 +287,11 @@ inline void dihedral_like(const BondedTerm& t, int64_t m, double phi, double* E,
 }
 
 void eval_base_stacking(const ocm_context& c, const BondedTerm& t, std::vector<Vec3>* F, double* Egroup);
+void eval_external(const ocm_context& c, const BondedTerm& t, std::vector<Vec3>* F, double* Egroup);
 
 void eval_bonded(const ocm_context& c, const BondedTerm& t, std::vector<Vec3>* F, double* Egroup) {
     if (t.kind == B_3SPN2_STACK) { eval_base_stacking(c, t, F, Egroup); return; }
+    if (t.kind == B_EXTERNAL) { eval_external(c, t, F, Egroup); return; }
     const double* box = c.sys.box;
     double Esum = 0;
     for (int64_t m = 0; m < t.n(); m++) {
@@ -658,6 +670,28 @@ void eval_pair(const ocm_context& c, const PairTerm& t, std::vector<Vec3>* F, do
 
 void eval_da(const ocm_context& c, const DATerm& t, std::vector<Vec3>* F, double* Egroup);
 
+// HarmonicCoMPullingForceFieldGenerator.cpp:5-18: "0.5 * k * (distance(g1, g2) - v0)^2" between the centres of two groups,
+// weights = masses (CustomCentroidBondForce::addGroup without weights); every bead takes its mass share of the force
+void eval_com(const ocm_context& c, const ComTerm& t, std::vector<Vec3>* F, double* Egroup) {
+    Vec3 cen[2];
+    double M[2];
+    const std::vector<int32_t>* grp[2] = {&t.g1, &t.g2};
+    for (int q = 0; q < 2; q++) {
+        M[q] = 0; cen[q] = Vec3{0, 0, 0};
+        for (int32_t i : *grp[q]) { M[q] += c.sys.mass[i]; cen[q] = cen[q] + c.x[i] * c.sys.mass[i]; }
+        cen[q] = cen[q] * (1.0 / M[q]);
+    }
+    Vec3 d = cen[0] - cen[1];
+    if (t.periodic) d = min_image(d, c.sys.box);
+    const double r = std::sqrt(dot(d, d)), dl = r - t.v0;
+    if (Egroup) Egroup[t.group] += 0.5 * t.k * dl * dl;
+    if (F && r > 0.0) {
+        const Vec3 f = d * (-t.k * dl / r);   // force on centre 1
+        for (int32_t i : t.g1) (*F)[i] = (*F)[i] + f * (c.sys.mass[i] / M[0]);
+        for (int32_t i : t.g2) (*F)[i] = (*F)[i] - f * (c.sys.mass[i] / M[1]);
+    }
+}
+
 void compute(const ocm_context& c, std::vector<Vec3>* F, double* Egroup, uint32_t mask) {
     if (F) F->assign(c.sys.n, Vec3{0, 0, 0});
     if (Egroup) std::fill(Egroup, Egroup + 32, 0.0);
@@ -667,6 +701,8 @@ void compute(const ocm_context& c, std::vector<Vec3>* F, double* Egroup, uint32_
         if (mask >> t.group & 1) eval_pair(c, t, F, Egroup);
     for (const auto& t : c.sys.das)
         if (mask >> t.group & 1) eval_da(c, t, F, Egroup);
+    for (const auto& t : c.sys.coms)
+        if (mask >> t.group & 1) eval_com(c, t, F, Egroup);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -795,11 +831,59 @@ void eval_base_stacking(const ocm_context& c, const BondedTerm& t, std::vector<V
     if (Egroup) Egroup[t.group] += Esum;
 }
 
+// One-bead external terms: the reference's expression strings restated literally on dual numbers seeded with the bead's own
+// coordinates (absolute, unwrapped, as CustomExternalForce sees them on the Reference platform).
+inline Dual dpow12(const Dual& a) { Dual a2 = a * a, a4 = a2 * a2; return a4 * a4 * a4; }
+void eval_external(const ocm_context& c, const BondedTerm& t, std::vector<Vec3>* F, double* Egroup) {
+    double Esum = 0;
+    for (int64_t m = 0; m < t.n(); m++) {
+        const double* p = &t.p[m * t.npar];
+        DAGeom g{&c, false, {t.idx[m], -1, -1, -1, -1, -1}};
+        const DVec x = g.pos(0);
+        Dual E = dconst(0.0);
+        switch ((int)p[0]) {
+            case X_POSITION_RESTRAINT:  // "k * (((x-x0)^2 + (y-y0)^2 + (z-z0)^2)^(1/2) - v0)^2", p = x0 y0 z0 k v0
+                                        // PositionRestraintForceFieldGenerator.cpp:8-10 (the periodic string of :12-17 is dead code)
+                E = p[4] * dsq(dsqrt(dsq(x.x - p[1]) + dsq(x.y - p[2]) + dsq(x.z - p[3])) - p[5]);
+                break;
+            case X_PULLING:  // "-kx * x - ky * y - kz * z"     PullingForceFieldGenerator.cpp:5-7
+                E = -(p[1] * x.x) - p[2] * x.y - p[3] * x.z;
+                break;
+            case X_RECTANGULAR_BOX: {  // "epsilon * ((radius/(x-x_lower))^12 + (radius/(x_upper-x))^12 + ...)", p = eps lo[3] hi[3] radius
+                                       // EXVRectangularBoxForceFieldGenerator.cpp:33-38
+                const Dual q[3] = {x.x, x.y, x.z};
+                for (int a = 0; a < 3; a++)
+                    E = E + dpow12(dconst(p[8]) / (q[a] - p[2 + a])) + dpow12(dconst(p[8]) / (p[5 + a] - q[a]));
+                E = p[1] * E;
+            } break;
+            default: {  // "k * (dr - v0)^2; dr = |x - h| or periodicdistance(x, h); h = ra_r * axis + shift; ra_r = axis . x",
+                        // p = axis[3] shift[3] k v0     CylindricalRestraintForceFieldGenerator.cpp:10-26
+                const Dual ra = p[1] * x.x + p[2] * x.y + p[3] * x.z;
+                DVec d{x.x - (ra * p[1] + p[4]), x.y - (ra * p[2] + p[5]), x.z - (ra * p[3] + p[6])};
+                if (t.periodic) {
+                    const Vec3 mi = min_image(Vec3{d.x.v, d.y.v, d.z.v}, c.sys.box);
+                    d.x.v = mi.x; d.y.v = mi.y; d.z.v = mi.z;
+                }
+                E = p[7] * dsq(dsqrt(ddot(d, d)) - p[8]);
+            }
+        }
+        Esum += E.v;
+        if (F) scatter_dual(E, g.bead, 1, F);
+    }
+    if (Egroup) Egroup[t.group] += Esum;
+}
+
 // slots: 0,1,2 = d1,d2,d3 ; 3,4,5 = a1,a2,a3
 Dual da_energy(const ocm_context& c, const DATerm& t, int64_t d, int64_t a) {
     DAGeom g{&c, t.periodic != 0, {t.donors[3 * d], t.donors[3 * d + 1], t.donors[3 * d + 2],
                                   t.acceptors[3 * a], t.acceptors[3 * a + 1], t.acceptors[3 * a + 2]}};
     enum { d1 = 0, d2 = 1, d3 = 2, a1 = 3, a2 = 4, a3 = 5 };
+    if (t.kind == DA_COMB_GO) {
+        // "k * (5 * (r0 / distance(a1, d1))^12 - 6 * (r0 / distance(a1, d1))^10)", k = g0, r0 = g1
+        // CombinatorialGoContactForceFieldGenerator.cpp:5-10
+        const Dual s = dconst(t.g1) / g.distance(a1, d1), s2 = s * s, s4 = s2 * s2, s10 = s4 * s4 * s2;
+        return t.g0 * (5.0 * (s10 * s2) - 6.0 * s10);
+    }
     if (t.kind == DA_BASE_PAIR) {
         // ThreeSPN2BasePairForceFieldGenerator.cpp:8-26; per-donor eps, r0, t01, t02, phi0; alpha = g0, K = g1
         const double* p = &t.p[d * t.npar];
@@ -1093,6 +1177,58 @@ static int add_da(ocm_system* s, DAKind kind, int group, const ocm_da_topology* 
     s->das.push_back(std::move(t));
     return 0;
 }
+static int add_external(ocm_system* s, int form, int g, int per, int64_t n, const int32_t* index, const std::vector<std::pair<const double*, int>>& cols,
+                        const std::vector<double>& globals, const char* what) {
+    // rows of 10 doubles: form, the globals, then the per-term columns (pointer, width); same layout as the engine's
+    const int npar = 10;
+    if (n < 0 || (n > 0 && !index)) return fail(std::string(what) + ": bad arguments");
+    std::vector<std::vector<double>> col(npar, std::vector<double>((size_t)std::max<int64_t>(n, 1), 0.0));
+    std::fill(col[0].begin(), col[0].end(), (double)form);
+    int q = 1;
+    for (double v : globals) { std::fill(col[q].begin(), col[q].end(), v); q++; }
+    for (auto& cw : cols) {
+        if (n > 0 && !cw.first) return fail(std::string(what) + ": null parameter array");
+        for (int w = 0; w < cw.second; w++, q++)
+            for (int64_t m = 0; m < n; m++) col[q][m] = cw.first[(size_t)m * cw.second + w];
+    }
+    std::vector<const double*> ptr;
+    for (auto& v : col) ptr.push_back(v.data());
+    return add_bonded(s, B_EXTERNAL, g, per, 1, n, index, npar, ptr, what);
+}
+int oracle_system_add_position_restraint(ocm_system* s, int g, int64_t n, const int32_t* index, const double* pos3, const double* k, const double* v0) {
+    return add_external(s, X_POSITION_RESTRAINT, g, 0, n, index, {{pos3, 3}, {k, 1}, {v0, 1}}, {}, "position_restraint");
+}
+int oracle_system_add_pulling(ocm_system* s, int g, int64_t n, const int32_t* index, const double* force3) {
+    return add_external(s, X_PULLING, g, 0, n, index, {{force3, 3}}, {}, "pulling");
+}
+int oracle_system_add_exv_rectangular_box(ocm_system* s, int g, double eps, const double* lower3, const double* upper3, int64_t n, const int32_t* index,
+                                          const double* radius) {
+    if (!s || !lower3 || !upper3) return fail("exv_rectangular_box: null argument");
+    if (s->has_box) return fail("exv_rectangular_box: RectangularBox interaction does not work under periodic boundary condition");
+    for (int a = 0; a < 3; a++) if (!(upper3[a] > lower3[a])) return fail("exv_rectangular_box: the upper edge must be larger than the lower edge");
+    return add_external(s, X_RECTANGULAR_BOX, g, 0, n, index, {{radius, 1}},
+                        {eps, lower3[0], lower3[1], lower3[2], upper3[0], upper3[1], upper3[2]}, "exv_rectangular_box");
+}
+int oracle_system_add_cylindrical_restraint(ocm_system* s, int g, int per, int64_t n, const int32_t* index, const double* axis3, const double* shift3,
+                                            const double* k, const double* v0) {
+    return add_external(s, X_CYLINDRICAL_RESTRAINT, g, per, n, index, {{axis3, 3}, {shift3, 3}, {k, 1}, {v0, 1}}, {}, "cylindrical_restraint");
+}
+int oracle_system_add_harmonic_com_pulling(ocm_system* s, int g, int per, double k, double v0, int64_t n1, const int32_t* g1, int64_t n2, const int32_t* g2) {
+    if (!s) return fail("null system");
+    if (g < 0 || g > 31) return fail("force group must be in 0..31");
+    if (n1 <= 0 || n2 <= 0 || !g1 || !g2) return fail("harmonic_com_pulling: both bead groups must be non-empty");
+    if (per && !s->has_box) return fail("harmonic_com_pulling: periodic term without a box");
+    if (check_idx(s, g1, n1, "harmonic_com_pulling") || check_idx(s, g2, n2, "harmonic_com_pulling")) return 1;
+    ComTerm t;
+    t.group = g; t.periodic = per ? 1 : 0; t.k = k; t.v0 = v0;
+    t.g1.assign(g1, g1 + n1); t.g2.assign(g2, g2 + n2);
+    s->coms.push_back(std::move(t));
+    return 0;
+}
+int oracle_system_add_combinatorial_go_contact(ocm_system* s, int g, const ocm_da_topology* topo, double k, double r0) {
+    if (!(r0 > 0)) return fail("combinatorial_go_contact: r0 must be positive");
+    return add_da(s, DA_COMB_GO, g, topo, 0, true, {}, k, r0, 0, "combinatorial_go_contact");
+}
 int oracle_system_add_3spn2_base_pair(ocm_system* s, int g, const ocm_da_topology* topo, const double* eps, const double* r0,
                                       const double* t01, const double* t02, const double* phi0, double alpha, double K_BP) {
     return add_da(s, DA_BASE_PAIR, g, topo, 5, true, {eps, r0, t01, t02, phi0}, alpha, K_BP, 0, "3spn2_base_pair");
@@ -1168,6 +1304,7 @@ int oracle_context_create_batch(const ocm_system* sys, int32_t nrep, double T, d
     if (!sys || !out || !seeds || nrep < 1) return fail("context_create_batch: bad arguments");
     if (sys->has_box) return fail("context_create_batch: replica batches need an unlimited boundary (no box)");
     if (!sys->das.empty()) return fail("context_create_batch: donor-acceptor terms are not supported in replica batches yet");
+    if (!sys->coms.empty()) return fail("context_create_batch: centre-of-mass pulling terms are not supported in replica batches");
     auto* c = new ocm_context();
     const int np = sys->n;
     ocm_system& S = c->sys;
@@ -1390,6 +1527,7 @@ static void compute_forces_verlet(ocm_context& c, std::vector<Vec3>* F) {
     F->assign(n, Vec3{0, 0, 0});
     for (const auto& t : c.sys.bonded) eval_bonded(c, t, F, nullptr);
     for (const auto& t : c.sys.das) eval_da(c, t, F, nullptr);
+    for (const auto& t : c.sys.coms) eval_com(c, t, F, nullptr);
     const int nthreads = (int)c.vl_F.size();
 #pragma omp parallel
     {

@@ -70,6 +70,7 @@ struct EvalContext {
     const std::vector<Vec3>* pos;
     double box[3];
     bool has_box;
+    const System* sys = nullptr;   // (particle masses: the default weights of CustomCentroidBondForce groups)
 };
 
 static inline Vec3 min_image(Vec3 d, const EvalContext& ec, bool periodic) {
@@ -755,9 +756,53 @@ void CustomCompoundBondForce::describe(Describer& d) const {
 int CustomCentroidBondForce::addPerBondParameter(const std::string& n) { params_.push_back(n); return (int)params_.size() - 1; }
 int CustomCentroidBondForce::addGroup(const std::vector<int>& particles, const std::vector<double>& weights) { groups_.push_back({particles, weights}); return (int)groups_.size() - 1; }
 int CustomCentroidBondForce::addBond(const std::vector<int>& groups, const std::vector<double>& params) { bonds_.push_back({groups, params}); return (int)bonds_.size() - 1; }
-double CustomCentroidBondForce::evaluate(const EvalContext&, std::vector<Vec3>*) const {
+// OpenMM: the position of a group is the weighted mean of its particles, weights = the given ones or, when none are given, the
+// particle masses; the expression sees the groups as g1, g2, ... and the force on a group centre is shared out by weight.
+double CustomCentroidBondForce::evaluate(const EvalContext& ec, std::vector<Vec3>* F) const {
     if (bonds_.empty()) return 0.0;
-    throw OpenMMException("openmm-lite: CustomCentroidBondForce is recorded but not evaluated (out of the hot-path scope)");
+    if (ng_ > 6) throw OpenMMException("openmm-lite: CustomCentroidBondForce with more than 6 groups per bond");
+    if (!prog_) {
+        const int ng = ng_;
+        lite::Compiler c(expr_, [this](const std::string& n) -> VarRef {
+            const int k = index_of(params_, n);
+            if (k >= 0) return passive(k);
+            return find_in(globals_, n);
+        }, [ng](const std::string& n) { return (n.size() == 2 && n[0] == 'g' && n[1] >= '1' && n[1] < '1' + ng) ? n[1] - '1' : -1; }, fn_lookup(functions_));
+        prog_ = c.compile();
+        prog_->periodic = periodic_;
+    }
+    const auto& x = *ec.pos;
+    auto weights = [&](const Group& g) {
+        std::vector<double> w = g.w;
+        if (w.empty()) for (int i : g.p) w.push_back(ec.sys->getParticleMass(i));
+        if (w.size() != g.p.size()) throw OpenMMException("CustomCentroidBondForce: wrong number of weights");
+        double tot = 0;
+        for (double v : w) tot += v;
+        for (double& v : w) v /= tot;
+        return w;
+    };
+    double E = 0;
+    const int nd = 3 * ng_;
+    for (auto& b : bonds_) {
+        DVec gp[6];
+        std::vector<std::vector<double>> w;
+        for (int s = 0; s < ng_; s++) {
+            const Group& g = groups_.at(b.g[s]);
+            w.push_back(weights(g));
+            Vec3 cen;
+            for (std::size_t k = 0; k < g.p.size(); k++) cen += x[g.p[k]] * w[s][k];
+            gp[s] = seed_position(cen, s, nd);
+        }
+        const Dual e = lite::run(*prog_, b.params.data(), nullptr, gp, ec, nd);
+        E += e.v;
+        if (F)
+            for (int s = 0; s < ng_; s++) {
+                const Group& g = groups_.at(b.g[s]);
+                for (std::size_t k = 0; k < g.p.size(); k++)
+                    for (int c = 0; c < 3; c++) (*F)[g.p[k]][c] -= e.d[3 * s + c] * w[s][k];
+            }
+    }
+    return E;
 }
 void CustomCentroidBondForce::describe(Describer& d) const {
     describe_common(d, "CustomCentroidBondForce");
@@ -1268,6 +1313,7 @@ double Context::computeForcesAndEnergy(int groups, std::vector<Vec3>* forces) co
     EvalContext ec;
     ec.pos = &pos_;
     ec.has_box = sys_.hasBox();
+    ec.sys = &sys_;
     for (int c = 0; c < 3; c++) ec.box[c] = box_[c][c];
     if (forces) forces->assign(pos_.size(), Vec3());
     double E = 0;

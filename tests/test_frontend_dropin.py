@@ -77,7 +77,8 @@ needs_frontend = pytest.mark.skipif(not os.path.exists(BIN), reason="bin/open_ca
 
 
 @needs_frontend
-@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "fus10", "wcamix", "dna_localize", "membrane", "membrane_npt", "membrane_npgt"])
+@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "fus10", "wcamix", "dna_localize", "membrane", "membrane_npt", "membrane_npgt", "external",
+                                  "external_pbc"])
 def test_frontend_translates_every_force_then_fails_loudly_without_gpu(built, tmp_path, name):
     """without a device the run must stop at ocm_context_create, i.e. after the reference's reader and generators ran
     and every OpenMM::Force they produced was recognised and translated into the C ABI (host code)"""
@@ -120,7 +121,8 @@ HOSTLAYER_ON_ORACLE = os.path.join(ROOT, "oracle", "_ref", "open_cafemol_hostlay
 
 @pytest.mark.skipif(not os.path.exists(HOSTLAYER_ON_ORACLE), reason="oracle/_ref is built where the reference tree is mounted")
 @pytest.mark.parametrize("name,periodic", [("sh3", False), ("dna_3spn2", False), ("fus10", True), ("wcamix", False), ("dna_localize", False),
-                                           ("membrane", True), ("membrane_npt", True), ("membrane_npgt", True)])
+                                           ("membrane", True), ("membrane_npt", True), ("membrane_npgt", True), ("external", False),
+                                           ("external_pbc", True)])
 def test_host_layer_on_oracle_backend_reproduces_reference_files(tmp_path, name, periodic):
     """CPU-only check of the product's host layer (compat/OpenMM.h -> C ABI): the reference's front end drives it with
     the double-precision ORACLE behind the C ABI (oracle/Makefile renames ocm_* to oracle_* for this test binary only).
@@ -175,7 +177,8 @@ def test_toml11_stand_in_compiles_with_the_reference_reader():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,periodic", [("sh3", False), ("dna_3spn2", False), ("fus10", True), ("wcamix", False), ("dna_localize", False),
-                                           ("membrane", True), ("membrane_npt", True), ("membrane_npgt", True)])
+                                           ("membrane", True), ("membrane_npt", True), ("membrane_npgt", True), ("external", False),
+                                           ("external_pbc", True)])
 def test_frontend_writes_the_reference_files(engine, tmp_path, name, periodic):
     if not os.path.exists(BIN):
         pytest.skip("bin/open_cafemol_b200 missing: it is built by __graft_entry__.build() where the reference tree is mounted and travels with the snapshot")

@@ -647,3 +647,82 @@ def test_capped_go_contact(engine, oracle):
     assert force_error(a["forces"], b["forces"]).max() < FORCE_TOL
     for g in (0, 1):
         assert a["energy_by_group"][g] == pytest.approx(b["energy_by_group"][g], rel=ENERGY_TOL)
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+@pytest.mark.parametrize("form", ["position_restraint", "pulling", "exv_rectangular_box", "cylindrical_restraint", "harmonic_com_pulling",
+                                  "combinatorial_go_contact"])
+def test_external_terms_random(engine, oracle, form, periodic):
+    """The reference's external generators (PositionRestraint, Pulling, EXVRectangularBox, CylindricalRestraint, HarmonicCoMPulling)
+    and CombinatorialGoContact on random chains, both boundaries: forces and group energies at 1e-5 against the oracle's dual-number
+    restatement of the reference's expression strings, then a short trajectory (the terms live in the captured step graph) and the
+    combination sets of the contact term."""
+    from test_oracle_kat import external_terms
+    if periodic and form == "exv_rectangular_box":
+        pytest.skip("the generator throws under a periodic boundary")
+    n = 24
+    box = np.array([3.4, 3.1, 3.6]) if periodic else None
+    masses = np.random.default_rng(5).uniform(20.0, 120.0, n)
+    for seed in range(3):
+        ctxs = []
+        for lib in (engine, oracle):
+            rng = np.random.default_rng(300 + seed)
+            s = System(lib, masses, box)
+            pos = external_terms(s, rng, n, form, periodic)
+            # a chain of harmonic bonds keeps the beads together during the trajectory part
+            ij = np.array([[i, i + 1] for i in range(n - 1)], np.int32)
+            s.add_harmonic_bond(0, ij, np.full(n - 1, 0.38), np.full(n - 1, 2000.0), periodic)
+            c = Context(s, 300.0, 0.2, 0.002, seed=3)
+            c.set_positions(pos)
+            c.set_velocities_to_temperature(300.0, 17)
+            ctxs.append(c)
+        ctx, ora = ctxs
+
+        class Spec:
+            group_ids = {"bond": 0, "term": 2, "term_b": 3}
+        a, _ = check_state(ctx, ora, Spec)
+        assert abs(a["energy_by_group"][2]) > 1e-6, "vacuous check: the term has no energy"
+        if form == "combinatorial_go_contact":
+            pa, pb = ctx.da_pairs(0), ora.da_pairs(0)
+            assert len(pa) > 0 and np.array_equal(pa, pb)
+        ctx.step(25); ora.step(25)
+        pa, pb = ctx.get_state(positions=True)["positions"], ora.get_state(positions=True)["positions"]
+        assert np.abs(pa - pb).max() < 5e-5, f"{form} seed {seed}: trajectories deviate by {np.abs(pa - pb).max():.3e} nm after 25 steps"
+        check_state(ctx, ora, Spec, ftol=2e-3, etol=2e-3)
+
+
+def test_external_terms_refused_where_unsupported(engine):
+    """centre-of-mass springs couple beads of different slabs / replicas: refused loudly instead of being dropped"""
+    s = System(engine, np.full(8, 50.0), None)
+    s.add_harmonic_com_pulling(0, 10.0, 0.5, [0, 1, 2], [5, 6, 7])
+    with pytest.raises(RuntimeError, match="centre-of-mass"):
+        Context(s, 300.0, 0.2, 0.002, replica_seeds=[1, 2, 3])
+
+
+def test_external_terms_in_a_replica_batch_take_the_general_path(engine, oracle):
+    """one-bead external terms are not part of the whole-step replica kernel: a batch that has them must run (correctly) on the
+    general path"""
+    from test_oracle_kat import external_terms
+    n, R = 12, 4
+    ctxs = []
+    for lib in (engine, oracle):
+        rng = np.random.default_rng(77)
+        s = System(lib, np.full(n, 60.0), None)
+        pos = external_terms(s, rng, n, "position_restraint")
+        ij = np.array([[i, i + 1] for i in range(n - 1)], np.int32)
+        s.add_harmonic_bond(0, ij, np.full(n - 1, 0.38), np.full(n - 1, 2000.0))
+        c = Context(s, 300.0, 0.2, 0.002, replica_seeds=[11 + r for r in range(R)])
+        c.set_positions(np.tile(pos, (R, 1)))
+        c.set_velocities_to_temperature(300.0, 5)
+        ctxs.append(c)
+    ctx, ora = ctxs
+    assert ctx.get_option("replica_kernel") == 0
+
+    class Spec:
+        group_ids = {"bond": 0, "term": 2}
+    check_state(ctx, ora, Spec)
+    ctx.step(20); ora.step(20)
+    pa, pb = ctx.get_state(positions=True)["positions"], ora.get_state(positions=True)["positions"]
+    assert np.abs(pa - pb).max() < 5e-5
+    ea, eb = ctx.replica_energies(), ora.replica_energies()
+    assert np.allclose(ea["potential_energy"], eb["potential_energy"], rtol=2e-3, atol=1e-3)

@@ -44,9 +44,9 @@ def test_sh3_exclusion_counts():
     assert exv.args["rc"] == pytest.approx((0.2348 + 0.2265) * 2.0, abs=1e-9)
 
 
-def _fd_check(lib, build, n, box=None, seed=0, h=1e-6, tol=2e-6):
+def _fd_check(lib, build, n, box=None, seed=0, h=1e-6, tol=2e-6, masses=None):
     rng = np.random.default_rng(seed)
-    sysm = System(lib, np.full(n, 50.0), box)
+    sysm = System(lib, np.full(n, 50.0) if masses is None else masses, box)
     pos = build(sysm, rng)
     ctx = Context(sysm, 300.0, 0.2, 0.001, 1)
     ctx.set_positions(pos)
@@ -116,6 +116,63 @@ def test_bonded_finite_difference(oracle, kind, periodic):
         return _chain(n, rng)
 
     _fd_check(oracle, build, n, box, seed=BONDED.index(kind))
+
+
+def external_terms(s, rng, n, form, periodic=False):
+    """One external / centre-of-mass / combinatorial term of the given form on an n-bead chain (shared by the oracle's
+    finite-difference test and the GPU parity test); returns the positions."""
+    from opencafemol_b200.capi import DATopology
+    pos = _chain(n, rng)
+    idx = np.arange(n)
+    if form == "position_restraint":
+        s.add_position_restraint(2, idx, pos + rng.normal(scale=0.3, size=(n, 3)), rng.uniform(10, 100, n), rng.uniform(0.0, 0.4, n))
+    elif form == "pulling":
+        s.add_pulling(2, idx[::2], rng.normal(scale=20.0, size=(len(idx[::2]), 3)))
+    elif form == "exv_rectangular_box":
+        s.add_exv_rectangular_box(2, 0.6, pos.min(0) - 0.35, pos.max(0) + 0.3, idx, rng.uniform(0.2, 0.3, n))
+    elif form == "cylindrical_restraint":
+        axis = rng.normal(size=(n, 3)); axis /= np.linalg.norm(axis, axis=1)[:, None]
+        shift = rng.normal(scale=2.0, size=(n, 3)); shift -= (shift * axis).sum(1)[:, None] * axis
+        s.add_cylindrical_restraint(2, idx, axis, shift, rng.uniform(10, 100, n), rng.uniform(0.0, 0.5, n), periodic)
+    elif form == "harmonic_com_pulling":
+        s.add_harmonic_com_pulling(2, 350.0, 0.25, idx[: n // 2], idx[n // 2:], periodic)
+        s.add_harmonic_com_pulling(3, 120.0, 1.5, idx[1::3], idx[::3], periodic)   # (interleaved groups)
+    else:
+        don = np.full((n // 2, 3), -1); don[:, 0] = idx[: n // 2]
+        acc = np.full((n - n // 2, 3), -1); acc[:, 0] = idx[n // 2:]
+        s.add_combinatorial_go_contact(2, DATopology(don, acc, 0.9, np.array([[0, 0], [1, 2]]), periodic), 1.3, 0.45)
+    return pos
+
+
+EXTERNAL = ["position_restraint", "pulling", "exv_rectangular_box", "cylindrical_restraint", "harmonic_com_pulling",
+            "combinatorial_go_contact"]
+
+
+@pytest.mark.parametrize("form", EXTERNAL)
+@pytest.mark.parametrize("periodic", [False, True])
+def test_external_finite_difference(oracle, form, periodic):
+    """The reference's external generators (PositionRestraint, Pulling, EXVRectangularBox, CylindricalRestraint,
+    HarmonicCoMPulling) and CombinatorialGoContact: F = -dE/dx of the oracle's restatement."""
+    if periodic and form == "exv_rectangular_box":
+        pytest.skip("the generator throws under a periodic boundary")
+    n = 8
+    box = np.array([2.5, 2.2, 2.0]) if periodic else None
+    masses = np.random.default_rng(5).uniform(20.0, 120.0, n)
+
+    def build(s, rng):
+        return external_terms(s, rng, n, form, periodic)
+
+    _fd_check(oracle, build, n, box, seed=EXTERNAL.index(form), masses=masses)
+
+
+def test_external_argument_checks(oracle):
+    s = System(oracle, np.full(4, 50.0), np.array([3.0, 3.0, 3.0]))
+    with pytest.raises(RuntimeError, match="periodic"):
+        s.add_exv_rectangular_box(0, 0.5, np.zeros(3), np.ones(3), [0], [0.2])
+    with pytest.raises(RuntimeError, match="out of range"):
+        s.add_pulling(0, [7], np.ones((1, 3)))
+    with pytest.raises(RuntimeError, match="non-empty"):
+        s.add_harmonic_com_pulling(0, 1.0, 0.0, [], [1])
 
 
 @pytest.mark.parametrize("periodic", [False, True])

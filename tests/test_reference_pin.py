@@ -29,11 +29,13 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import ref_binding as rb  # noqa: E402
 
 # "membrane": the POPC sample in the NVT ensemble with a Trigonometric term added (tests/golden/make_ref_membrane.py)
-CASES = ["sh3", "dna_3spn2", "nucleosome", "fus10", "membrane"]
+# "external" / "external_pbc": the SH3 sample and 10 FUS chains with the external generators (PositionRestraint, Pulling,
+# EXVRectangularBox, CylindricalRestraint, HarmonicCoMPulling) and a CombinatorialGoContact added (tests/golden/make_ref_external.py)
+CASES = ["sh3", "dna_3spn2", "nucleosome", "fus10", "membrane", "external", "external_pbc"]
 REF_SAMPLES = "/root/reference/sample/toml_input"
 PAIR_KINDS = ("excluded_volume", "debye_huckel", "lj_repulsive", "lj_attractive", "3spn2_excluded_volume", "wca", "isolf_attractive",
               "trigonometric")
-DA_KINDS = ("3spn2_base_pair", "3spn2_cross_stacking", "pdns")
+DA_KINDS = ("3spn2_base_pair", "3spn2_cross_stacking", "pdns", "combinatorial_go_contact")
 
 
 def load_ref(name):
@@ -89,7 +91,7 @@ def test_oracle_matches_reference_fus100_full_size(oracle):
         assert st["energy_by_group"][spec.group_ids[name]] == pytest.approx(ref, rel=1e-10, abs=1e-7)
 
 
-@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "nucleosome", "membrane"])
+@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "nucleosome", "membrane", "external", "external_pbc"])
 def test_oracle_trajectory_matches_reference_run(oracle, name):
     """20 leap-frog Langevin steps of the reference's LangevinIntegrator semantics with the shared Philox noise."""
     gold = load_ref(name)
@@ -285,7 +287,7 @@ def test_engine_matches_reference_vectors(engine, name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "membrane"])
+@pytest.mark.parametrize("name", ["sh3", "dna_3spn2", "membrane", "external", "external_pbc"])
 def test_engine_trajectory_tracks_reference_run(engine, name):
     """FP32 pair arithmetic and FP32 velocities against the reference's double-precision run, same noise"""
     gold = load_ref(name)

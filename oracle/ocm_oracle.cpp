@@ -5,11 +5,17 @@
 // Appendix A/B).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load this library; the product (libocm_b200.so) never does.
 //
-// PARITY STATUS: "parity unpinned" by the reference's own tests — test/test_read_toml_ff_generator.cpp
-// holds no numeric assertion and OpenMM (where the arithmetic lives, pinned 8.0.0 by
-// .github/workflows/main.yml:25) is absent from /root/reference and cannot be built offline.
-// The oracle is instead pinned by (i) the closed-form known answers of the reference's own sample
-// inputs (tests/test_oracle_kat.py) and (ii) finite differences F = -dE/dx.
+// PARITY STATUS: pinned by the reference compiled here.  The reference's own tests
+// (test/test_read_toml_ff_generator.cpp) hold no numeric assertion and OpenMM (where the arithmetic lives,
+// pinned 8.0.0 by .github/workflows/main.yml:25) is absent from /root/reference and cannot be built
+// offline, so the pin is oracle/_ref: every reference source compiled unmodified (oracle/Makefile, target
+// `ref`) against the stand-in OpenMM of oracle/ref_shim, whose Custom*Force classes evaluate the reference's
+// own energy-expression strings with forward-mode differentiation.  tests/golden/make_ref_*.py (committed)
+// generate tests/golden/ref_*.json.gz from it; tests/test_reference_pin.py holds this file to those vectors
+// (energies 1e-10, forces 1e-9, 20-step trajectories 1e-8).  Beside that: (i) the closed-form known answers
+// of the reference's sample inputs (tests/test_oracle_kat.py), (ii) finite differences
+// F = -dE/dx of every term kind.  Unpinned against OpenMM itself: the Monte Carlo barostat's acceptance rule
+// and OpenMM's integrator internals are restated from its published source.
 //
 // It exports the same C ABI as include/ocm_b200.h with the prefix `oracle_` instead of `ocm_`.
 // Each potential cites the reference file:line whose expression string it restates.

@@ -124,6 +124,11 @@ def external_terms(s, rng, n, form, periodic=False):
     from opencafemol_b200.capi import DATopology
     pos = _chain(n, rng)
     idx = np.arange(n)
+    if form == "combinatorial_go_contact":
+        # a random walk can bring a donor and an acceptor almost on top of each other; (r0/r)^12 then exceeds every force a run
+        # would see (and the range of the engine's fixed-point accumulators, 2e9 kJ/mol/nm): draw again until none is closer than 0.3 nm
+        while np.linalg.norm(pos[: n // 2, None, :] - pos[None, n // 2:, :], axis=2).min() < 0.3:
+            pos = _chain(n, rng)
     if form == "position_restraint":
         s.add_position_restraint(2, idx, pos + rng.normal(scale=0.3, size=(n, 3)), rng.uniform(10, 100, n), rng.uniform(0.0, 0.4, n))
     elif form == "pulling":

@@ -571,7 +571,7 @@ void for_each_pair(const ocm_context& c, const PairTerm& t, double rc, bool para
         }
     }
     if (brute) {
-#pragma omp parallel for schedule(dynamic, 8) if (parallel)
+#pragma omp parallel for schedule(static, 8) if (parallel)   // (static: which thread sums what does not depend on timing)
         for (int a = 0; a < np; a++) {
             int i = t.part[a];
             for (int b = a + 1; b < np; b++) {
@@ -609,7 +609,7 @@ void for_each_pair(const ocm_context& c, const PairTerm& t, double rc, bool para
         ids[slot] = t.part[a];
         xs[slot] = xw[a];
     }
-#pragma omp parallel for schedule(dynamic, 4) if (parallel)
+#pragma omp parallel for schedule(static, 4) if (parallel)
     for (int64_t cidx = 0; cidx < ncell; cidx++) {
         int cx = cidx % nc[0], cy = (cidx / nc[0]) % nc[1], cz = cidx / ((int64_t)nc[0] * nc[1]);
         for (int dz = -1; dz <= 1; dz++)
@@ -1549,7 +1549,7 @@ static void compute_forces_verlet(ocm_context& c, std::vector<Vec3>* F) {
             const double ibx = per ? 1.0 / box[0] : 0, iby = per ? 1.0 / box[1] : 0, ibz = per ? 1.0 / box[2] : 0;
             double rc2max = 0;
             for (int ti : g.terms) rc2max = std::max(rc2max, c.sys.pairs[ti].rc * c.sys.pairs[ti].rc);
-#pragma omp for schedule(dynamic, 32) nowait
+#pragma omp for schedule(static, 32) nowait   // (round-robin chunks: balanced, and reproducible for a given thread count)
             for (int a = 0; a < (int)g.beads.size(); a++) {
                 const int i = g.beads[a];
                 const Vec3 xi = c.x[i];

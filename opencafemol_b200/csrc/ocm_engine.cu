@@ -78,6 +78,7 @@ struct PairListHost {
     std::vector<int> terms;  // member pair terms (indices into sys.pairs)
     int form = 0;            // SEG_PAIR_TZ / SEG_PAIR_DH / SEG_PAIR_WELL
     int np = 0, ntypes = 0, stride = 0, tpb = 8;
+    int row_len32 = 0;                      // longest row (with head-room) rounded to 32: what pick_tpb looks at; stride is rounded to 128
     double rc_list = 0;      // largest effective cutoff of the members
     std::vector<double> rc_eff;  // per member
     // device storage
@@ -723,7 +724,7 @@ static int pick_tpb(const ocm_context* c, const PairListHost& L) {
     if (c->tpb_opt == 4 || c->tpb_opt == 8 || c->tpb_opt == 16 || c->tpb_opt == 32) return c->tpb_opt;
     // one warp per bead unless the rows are too short to keep 32 lanes busy
     int t = 32;
-    if (L.stride > 0) while (t > 4 && L.stride < 4 * t) t >>= 1;
+    if (L.row_len32 > 0) while (t > 4 && L.row_len32 < 4 * t) t >>= 1;
     return t;
 }
 
@@ -1103,7 +1104,7 @@ static bool vbox_layout(ocm_context* c, const double* xyz, bool force) {
     c->n_vbox_resize++;
     update_params(c);
     c->lists_ready = false; c->lists_current = false;
-    for (auto& L : c->lists) L->stride = 0;
+    for (auto& L : c->lists) { L->stride = 0; L->row_len32 = 0; }
     drop_graphs(c);
     return true;
 }
@@ -1478,10 +1479,15 @@ static void size_lists(ocm_context* c, double growth) {
             if (cap > L.tl_mask_cap) { L.tl_mask_cap = cap; L.tl_masks.alloc((size_t)cap * 8); }
             L.dev.tl_stride = L.tl_stride; L.dev.tl_entries = L.tl_entries.p; L.dev.tl_masks = L.tl_masks.p; L.dev.tl_mask_cap = L.tl_mask_cap;
             L.stride = std::max(L.stride, 32);  // (rows are not built; a non-zero stride marks the list as sized)
+            L.row_len32 = std::max(L.row_len32, 32);
             continue;
         }
         int want = (int)(maxn * growth) + 16;
         want = (want + 31) / 32 * 32;
+        L.row_len32 = std::max(L.row_len32, want);
+        // rows are padded with self entries to whole 128-entry groups (the T = 32 force path reads four 32-entry groups per
+        // iteration without testing where the row ends)
+        want = (want + 127) / 128 * 128;
         if (want > L.stride) {
             L.stride = want;
             L.nbr.alloc((size_t)std::max(L.np, 1) * L.stride);
@@ -2433,7 +2439,7 @@ int ocm_context_set_option(ocm_context* c, const char* key, double value) {
         c->skin = value;
         update_params(c);
         c->lists_ready = false; c->lists_current = false;
-        for (auto& L : c->lists) L->stride = 0;
+        for (auto& L : c->lists) { L->stride = 0; L->row_len32 = 0; }
         drop_graphs(c);
         if (c->nstlist_fixed <= 0) c->nst = initial_nst(c);
     } else if (k == "pdl") {

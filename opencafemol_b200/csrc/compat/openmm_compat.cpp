@@ -117,97 +117,115 @@ void replace_all(std::string& s, const std::string& from, const std::string& to)
     if (from.empty()) return;
     for (std::size_t p = s.find(from); p != std::string::npos; p = s.find(from, p + to.size())) s.replace(p, from.size(), to);
 }
+// Canonical form under which an energy expression is looked up: white space removed, trailing ';' dropped, and the auxiliary
+// definitions that follow the main expression ("energy; a = ...; b = ...") sorted, since Lepton does not care about their order.
+// An upstream edit that only re-indents or re-orders the definitions of a generator's string still finds its catalogue entry.
+std::string canonical(const std::string& expr) {
+    const std::string s = strip_ws(expr);
+    std::vector<std::string> parts;
+    std::size_t b = 0;
+    for (std::size_t p = s.find(';'); ; p = s.find(';', b)) {
+        parts.push_back(s.substr(b, p == std::string::npos ? std::string::npos : p - b));
+        if (p == std::string::npos) break;
+        b = p + 1;
+    }
+    parts.erase(std::remove_if(parts.begin() + 1, parts.end(), [](const std::string& t) { return t.empty(); }), parts.end());
+    std::sort(parts.begin() + 1, parts.end());
+    std::string o = parts[0];
+    for (std::size_t k = 1; k < parts.size(); k++) o += ";" + parts[k];
+    return o;
+}
 
 // expressions emitted by the reference's generators, normalised
-const char* kGoContact = "k*(5*(r0/r)^12-6*(r0/r)^10)";                       // GoContactForceFieldGenerator.cpp:5-18
-const char* kCappedGoContact =                                                // CappedGoContactForceFieldGenerator.cpp:5-9
+const std::string kGoContact = canonical("k*(5*(r0/r)^12-6*(r0/r)^10)");                       // GoContactForceFieldGenerator.cpp:5-18
+const std::string kCappedGoContact = canonical(  // CappedGoContactForceFieldGenerator.cpp:5-9
     "cap_val*cap_formula+(1-cap_val)*lj_formula;cap_formula=k*slope/roverdist+k*intercept;lj_formula=k*(5*roverdist^12-6*roverdist^10);"
-    "cap_val=step(cap-1/roverdist);roverdist=r0/r";
-const char* kGaussianBond = "k*exp(-(r-v0)^2/(2*sigma^2))";                   // GaussianBondForceFieldGenerator.cpp:5-21
-const char* k3SPN2Bond = "k2*(r-v0)^2+100.0*k4*(r-v0)^4";                     // ThreeSPN2BondForceFieldGenerator.cpp:5-20
-const char* kFLA =                                                            // FlexibleLocalAngleForceFieldGenerator.cpp:21-27
+    "cap_val=step(cap-1/roverdist);roverdist=r0/r");
+const std::string kGaussianBond = canonical("k*exp(-(r-v0)^2/(2*sigma^2))");                   // GaussianBondForceFieldGenerator.cpp:5-21
+const std::string k3SPN2Bond = canonical("k2*(r-v0)^2+100.0*k4*(r-v0)^4");                     // ThreeSPN2BondForceFieldGenerator.cpp:5-20
+const std::string kFLA = canonical(  // FlexibleLocalAngleForceFieldGenerator.cpp:21-27
     "k*(spline(theta)-min_energy+(step(min_theta-theta)*(30*(min_theta-theta)+min_theta_y))+(step(theta-max_theta)*(30*(theta-max_theta)+max_theta_y)));"
-    "theta=angle(p1,p2,p3)";
-const char* kBaseStacking =                                                   // ThreeSPN2BaseStackingForceFieldGenerator.cpp:6-22
+    "theta=angle(p1,p2,p3)");
+const std::string kBaseStacking = canonical(  // ThreeSPN2BaseStackingForceFieldGenerator.cpp:6-22
     "rep+f2*attr;rep=epsilon*(1-exp(-alpha*(dr)))^2*step(-dr);attr=epsilon*(1-exp(-alpha*(dr)))^2*step(dr)-epsilon;dr=distance(p2,p3)-r0;"
     "f2=max(f*rect2,rect1);rect1=step(dt+pi/2)*step(pi/2-dt);rect2=step(dt+pi)*step(pi-dt);f=1-cos(dt)^2;dt=K_BS*(angle(p1,p2,p3)-t0);"
-    "pi=3.1415926535897932385";
-const char* kGaussianDihedral =                                               // GaussianDihedralForceFieldGenerator.cpp:5-13
-    "k*exp(-(dt_periodic)^2/(2*sigma^2));dt_periodic=dt-floor((dt+pi)/(2*pi))*(2*pi);dt=theta-theta0;pi=3.1415926535897932385";
-const char* kCosineDihedral = "k_periodic*(1-cos(n0*(theta-t0)))";            // CosineDihedralForceFieldGenerator.cpp:7
-const char* kFLD =                                                            // FlexibleLocalDihedralForceFieldGenerator.cpp:28-37
-    "k*(c-min_energy+kcos1*cos(theta)+ksin1*sin(theta)+kcos2*cos(2*theta)+ksin2*sin(2*theta)+kcos3*cos(3*theta)+ksin3*sin(3*theta))";
-const char* kExcludedVolume =                                                 // ExcludedVolumeForceFieldGenerator.cpp:25-27
-    "epsilon*(sigma_sum)^12*((1/r)^12-cutoff_correction);sigma_sum=sigma1+sigma2";
-const char* kDebyeHuckel = "q1*q2*inv_4_pi_eps0_epsk*(exp(-r/debye_length)/r-cutoff_correction)";  // DebyeHuckelForceFieldGenerator.cpp:54-57
-const char* kLJRepulsive =                                                    // LennardJonesRepulsiveForceFieldGenerator.cpp:35-43
+    "pi=3.1415926535897932385");
+const std::string kGaussianDihedral = canonical(  // GaussianDihedralForceFieldGenerator.cpp:5-13
+    "k*exp(-(dt_periodic)^2/(2*sigma^2));dt_periodic=dt-floor((dt+pi)/(2*pi))*(2*pi);dt=theta-theta0;pi=3.1415926535897932385");
+const std::string kCosineDihedral = canonical("k_periodic*(1-cos(n0*(theta-t0)))");            // CosineDihedralForceFieldGenerator.cpp:7
+const std::string kFLD = canonical(  // FlexibleLocalDihedralForceFieldGenerator.cpp:28-37
+    "k*(c-min_energy+kcos1*cos(theta)+ksin1*sin(theta)+kcos2*cos(2*theta)+ksin2*sin(2*theta)+kcos3*cos(3*theta)+ksin3*sin(3*theta))");
+const std::string kExcludedVolume = canonical(  // ExcludedVolumeForceFieldGenerator.cpp:25-27
+    "epsilon*(sigma_sum)^12*((1/r)^12-cutoff_correction);sigma_sum=sigma1+sigma2");
+const std::string kDebyeHuckel = canonical("q1*q2*inv_4_pi_eps0_epsk*(exp(-r/debye_length)/r-cutoff_correction)");  // DebyeHuckelForceFieldGenerator.cpp:54-57
+const std::string kLJRepulsive = canonical(  // LennardJonesRepulsiveForceFieldGenerator.cpp:35-43
     "step(threthold-r)*epsilon*(4*(sigma_r_12-sigma_r_6)+1);sigma_r_12=sigma_r_6^2;sigma_r_6=sigma_r^6;sigma_r=sigma/r;threthold=sigma*2^(1/6);"
-    "sigma=(sigma1+sigma2)*0.5;epsilon=(epsilon1+epsilon2)*0.5";
-const char* kLJAttractive =                                                   // LennardJonesAttractiveForceFieldGenerator.cpp:40-50
+    "sigma=(sigma1+sigma2)*0.5;epsilon=(epsilon1+epsilon2)*0.5");
+const std::string kLJAttractive = canonical(  // LennardJonesAttractiveForceFieldGenerator.cpp:40-50
     "epsilon*(step(r-threthold)*4*(sigma_r_12-sigma_r_6)-step(threthold-r));sigma_r_12=sigma_r_6^2;sigma_r_6=sigma_r^6;sigma_r=sigma/r;"
-    "threthold=sigma*2^(1/6);sigma=(sigma1+sigma2)*0.5;epsilon=(epsilon1+epsilon2)*0.5";
-const char* kWCA =                                                            // WeeksChandlerAndersenForceFieldGenerator.cpp:34-41
+    "threthold=sigma*2^(1/6);sigma=(sigma1+sigma2)*0.5;epsilon=(epsilon1+epsilon2)*0.5");
+const std::string kWCA = canonical(  // WeeksChandlerAndersenForceFieldGenerator.cpp:34-41
     "step(sigma*2^(1/6)-r)*(4*eps*(sigma_r_12-sigma_r_6)+eps);sigma_r_12=sigma_r_6^2;sigma_r_6=sigma_r^6;sigma_r=sigma/r;"
-    "eps=sqrt(eps1*eps2);sigma=(sigma1+sigma2)*0.5";
-const char* kISoLFAttractive =                                                // iSoLFAttractiveForceFieldGenerator.cpp:41-50
+    "eps=sqrt(eps1*eps2);sigma=(sigma1+sigma2)*0.5");
+const std::string kISoLFAttractive = canonical(  // iSoLFAttractiveForceFieldGenerator.cpp:41-50
     "-eps*(step(base-r)+step(r-base)*step(base+omega-r)*cos(0.5*pi*(r-base)/omega)^2);base=sigma*2^(1/6);sigma=(sigma1+sigma2)*0.5;"
-    "eps=sqrt(eps1*eps2);omega=(omega1+omega2)*0.5;pi=3.1415926535897932385";
-const char* kTrigonometric =                                                  // TrigonometricForceFieldGenerator.cpp:43-53
+    "eps=sqrt(eps1*eps2);omega=(omega1+omega2)*0.5;pi=3.1415926535897932385");
+const std::string kTrigonometric = canonical(  // TrigonometricForceFieldGenerator.cpp:43-53
     "-epsilon*(step(threthold+omega-r)+step(r-threthold)*step(threthold+omega-r)*(2*r_th_omeg^3-3*r_th_omeg^2));r_th_omeg=(r-threthold)/omega;"
-    "threthold=sigma*2^(1/6);epsilon=(epsilon1*epsilon2)^(1/2);sigma=(sigma1+sigma2)*0.5;omega=(omega1+omega2)*0.5";
-const char* kUniformWCA =                                                     // UniformWeeksChandlerAndersenForceFieldGenerator.cpp:138-143
-    "4*eps*(sigma_r_12-sigma_r_6+0.25);sigma_r_12=sigma_r_6^2;sigma_r_6=sigma_r^6;sigma_r=sigma/r";
-const char* kUniformLJAttractive =                                            // UniformLennardJonesAttractiveForceFieldGenerator.cpp:145-152
+    "threthold=sigma*2^(1/6);epsilon=(epsilon1*epsilon2)^(1/2);sigma=(sigma1+sigma2)*0.5;omega=(omega1+omega2)*0.5");
+const std::string kUniformWCA = canonical(  // UniformWeeksChandlerAndersenForceFieldGenerator.cpp:138-143
+    "4*eps*(sigma_r_12-sigma_r_6+0.25);sigma_r_12=sigma_r_6^2;sigma_r_6=sigma_r^6;sigma_r=sigma/r");
+const std::string kUniformLJAttractive = canonical(  // UniformLennardJonesAttractiveForceFieldGenerator.cpp:145-152
     "epsilon*(step(r-threthold)*4*(sigma_r_12-sigma_r_6)-step(threthold-r));sigma_r_12=sigma_r_6^2;sigma_r_6=sigma_r^6;sigma_r=sigma/r;"
-    "threthold=sigma*2^(1/6)";
-const char* k3SPN2ExcludedVolume =                                            // ThreeSPN2ExcludedVolumeForceFieldGenerator.cpp:21-26
-    "step(sigma-r)*(epsilon*((sigma/r)^12-2*(sigma/r)^6)+epsilon);epsilon=sqrt(epsilon1*epsilon2);sigma=0.5*(sigma1+sigma2)";
-const char* kBasePair =                                                       // ThreeSPN2BasePairForceFieldGenerator.cpp:8-26
+    "threthold=sigma*2^(1/6)");
+const std::string k3SPN2ExcludedVolume = canonical(  // ThreeSPN2ExcludedVolumeForceFieldGenerator.cpp:21-26
+    "step(sigma-r)*(epsilon*((sigma/r)^12-2*(sigma/r)^6)+epsilon);epsilon=sqrt(epsilon1*epsilon2);sigma=0.5*(sigma1+sigma2)");
+const std::string kBasePair = canonical(  // ThreeSPN2BasePairForceFieldGenerator.cpp:8-26
     "rep+1/2*(1+cos(dphi))*fdt1*fdt2*attr;rep=epsilon*(1-exp(-alpha_BP*dr))^2*(1-step(dr));attr=epsilon*(1-exp(-alpha_BP*dr))^2*step(dr)-epsilon;"
     "fdt1=max(f1*rect0t1,rect1t1);fdt2=max(f2*rect0t2,rect1t2);rect1t1=step(pi/2+dt1)*step(pi/2-dt1);rect1t2=step(pi/2+dt2)*step(pi/2-dt2);"
     "rect0t1=step(pi+dt1)*step(pi-dt1);rect0t2=step(pi+dt2)*step(pi-dt2);f1=1-cos(dt1)^2;f2=1-cos(dt2)^2;dphi=dihedral(d2,d1,a1,a2)-phi0;"
-    "dr=distance(d1,a1)-r0;dt1=K_BP*(angle(d2,d1,a1)-t01);dt2=K_BP*(angle(a2,a1,d1)-t02);pi=3.1415926535897932385";
-const char* kCrossStacking =                                                  // ThreeSPN2CrossStackingForceFieldGenerator.cpp:8-31
+    "dr=distance(d1,a1)-r0;dt1=K_BP*(angle(d2,d1,a1)-t01);dt2=K_BP*(angle(a2,a1,d1)-t02);pi=3.1415926535897932385");
+const std::string kCrossStacking = canonical(  // ThreeSPN2CrossStackingForceFieldGenerator.cpp:8-31
     "fdt3*fdtCS*attr/2;attr=epsilon*(1-exp(-alpha_CS*dr))^2*step(dr)-epsilon;fdt3=max(f1*rect0t3,rect1t3);fdtCS=max(f2*rect0tCS,rect1tCS);"
     "rect0t3=step(pi+dt3)*step(pi-dt3);rect0tCS=step(pi+dtCS)*step(pi-dtCS);rect1t3=step(pi/2+dt3)*step(pi/2-dt3);"
     "rect1tCS=step(pi/2+dtCS)*step(pi/2-dtCS);f1=1-cos(dt3)^2;f2=1-cos(dtCS)^2;dr=distance(d1,a3)-r0;dt3=K_BP*(t3-t03);dtCS=K_CS*(tCS-t0CS);"
     "tCS=angle(d2,d1,a3);t3=acos(cost3lim);cost3lim=min(max(cost3,-0.99),0.99);cost3=sin(t1)*sin(t2)*cos(phi)-cos(t1)*cos(t2);"
-    "t1=angle(d2,d1,a1);t2=angle(d1,a1,a2);phi=dihedral(d2,d1,a1,a2);pi=3.1415926535897932385";
+    "t1=angle(d2,d1,a1);t2=angle(d1,a1,a2);phi=dihedral(d2,d1,a1,a2);pi=3.1415926535897932385");
 // the *Local variants: the same energies over an explicit list of (donor, acceptor) nucleotide pairs, as compound bonds
-const char* kBasePairLocal =                                                  // ThreeSPN2BasePairLocalForceFieldGenerator.cpp:6-25
+const std::string kBasePairLocal = canonical(  // ThreeSPN2BasePairLocalForceFieldGenerator.cpp:6-25
     "rep+1/2*(1+cos(dphi))*fdt1*fdt2*attr;rep=epsilon*(1-exp(-alpha_BP*dr))^2*(1-step(dr));attr=epsilon*(1-exp(-alpha_BP*dr))^2*step(dr)-epsilon;"
     "fdt1=max(f1*rect0t1,rect1t1);fdt2=max(f2*rect0t2,rect1t2);rect1t1=step(pi/2+dt1)*step(pi/2-dt1);rect1t2=step(pi/2+dt2)*step(pi/2-dt2);"
     "rect0t1=step(pi+dt1)*step(pi-dt1);rect0t2=step(pi+dt2)*step(pi-dt2);f1=1-cos(dt1)^2;f2=1-cos(dt2)^2;dphi=dihedral(p1,p2,p3,p4)-phi0;"
-    "dr=distance(p2,p3)-r0;dt1=K_BP*(angle(p1,p2,p3)-t01);dt2=K_BP*(angle(p4,p3,p2)-t02);pi=3.1415926535897932385";
-const char* kCrossStackingLocal =                                             // ThreeSPN2CrossStackingLocalForceFieldGenerator.cpp:6-30
+    "dr=distance(p2,p3)-r0;dt1=K_BP*(angle(p1,p2,p3)-t01);dt2=K_BP*(angle(p4,p3,p2)-t02);pi=3.1415926535897932385");
+const std::string kCrossStackingLocal = canonical(  // ThreeSPN2CrossStackingLocalForceFieldGenerator.cpp:6-30
     "fdt3*fdtCS*attr/2;attr=epsilon*(1-exp(-alpha_CS*dr))^2*step(dr)-epsilon;fdt3=max(f1*rect0t3,rect1t3);fdtCS=max(f2*rect0tCS,rect1tCS);"
     "rect0t3=step(pi+dt3)*step(pi-dt3);rect0tCS=step(pi+dtCS)*step(pi-dtCS);rect1t3=step(pi/2+dt3)*step(pi/2-dt3);"
     "rect1tCS=step(pi/2+dtCS)*step(pi/2-dtCS);f1=1-cos(dt3)^2;f2=1-cos(dtCS)^2;dr=distance(p2,p6)-r0;dt3=K_BP*(t3-t03);dtCS=K_CS*(tCS-t0CS);"
     "tCS=angle(p1,p2,p6);t3=acos(cost3lim);cost3lim=min(max(cost3,-0.99),0.99);cost3=sin(t1)*sin(t2)*cos(phi)-cos(t1)*cos(t2);"
-    "t1=angle(p1,p2,p3);t2=angle(p2,p3,p4);phi=dihedral(p1,p2,p3,p4);pi=3.1415926535897932385";
+    "t1=angle(p1,p2,p3);t2=angle(p2,p3,p4);phi=dihedral(p1,p2,p3,p4);pi=3.1415926535897932385");
 // Range inside which the *Local pairs are evaluated.  The compound bonds have no cutoff, but their energy beyond
 // r0 + 1.9 nm is below eps * 2 exp(-alpha * 1.9 nm) < 1e-15 kJ/mol (alpha >= 20 / nm): nothing is lost at double precision.
 constexpr double kLocalPairRange = 2.5;
 
-const char* kPDNS =                                                           // ProteinDNANonSpecificForceFieldGenerator.cpp:60-83
+const std::string kPDNS = canonical(  // ProteinDNANonSpecificForceFieldGenerator.cpp:60-83
     "-k*f_r*g_theta*g_phi;f_r=exp(-dr^2/(2*sigma*sigma));g_theta=max(g1*rect0t,rect1t);g_phi=max(g2*rect0p,rect1p);"
     "rect0t=step(pi+dtheta)*step(pi-dtheta);rect1t=step(pi/2+dtheta)*step(pi/2-dtheta);rect0p=step(pi+dphi)*step(pi-dphi);"
     "rect1p=step(pi/2+dphi)*step(pi/2-dphi);g1=1-cos(dtheta)^2;g2=1-cos(dphi)^2;dr=distance(d2,a1)-r0;dtheta=K*(theta-theta0);dphi=K*(phi-phi0);"
     "K=pi/(2*delta);phi=angle(d2,a1,a2);theta=acos(cost1lim);cost1lim=min(max(cost1,-0.99999),0.99999);"
-    "cost1=sin(t1)*sin(t2)*cos(phi1)-cos(t1)*cos(t2);t1=angle(d1,d3,a1);t2=angle(d3,a1,d2);phi1=dihedral(d1,d3,a1,d2);pi=3.1415926535897932385";
+    "cost1=sin(t1)*sin(t2)*cos(phi1)-cos(t1)*cos(t2);t1=angle(d1,d3,a1);t2=angle(d3,a1,d2);phi1=dihedral(d1,d3,a1,d2);pi=3.1415926535897932385");
 
 // one-bead external terms, the centroid spring and the combinatorial contact
-const char* kPositionRestraint = "k*(((x-x0)^2+(y-y0)^2+(z-z0)^2)^(1/2)-v0)^2";  // PositionRestraintForceFieldGenerator.cpp:8-10
-const char* kPulling = "-kx*x-ky*y-kz*z";                                        // PullingForceFieldGenerator.cpp:5-7
-const char* kRectangularBox =                                                   // EXVRectangularBoxForceFieldGenerator.cpp:33-38
+const std::string kPositionRestraint = canonical("k*(((x-x0)^2+(y-y0)^2+(z-z0)^2)^(1/2)-v0)^2");  // PositionRestraintForceFieldGenerator.cpp:8-10
+const std::string kPulling = canonical("-kx*x-ky*y-kz*z");                                        // PullingForceFieldGenerator.cpp:5-7
+const std::string kRectangularBox = canonical(  // EXVRectangularBoxForceFieldGenerator.cpp:33-38
     "epsilon*((radius/(x-x_lower))^12+(radius/(x_upper-x))^12+(radius/(y-y_lower))^12+(radius/(y_upper-y))^12+(radius/(z-z_lower))^12+"
-    "(radius/(z_upper-z))^12)";
-const char* kCylindricalRestraint =                                             // CylindricalRestraintForceFieldGenerator.cpp:10-17
-    "k*(dr-v0)^2;dr=((x-xh)^2+(y-yh)^2+(z-zh)^2)^(1/2);xh=ra_r*xa+x0;yh=ra_r*ya+y0;zh=ra_r*za+z0;ra_r=xa*x+ya*y+za*z";
-const char* kCylindricalRestraintPeriodic =                                     // CylindricalRestraintForceFieldGenerator.cpp:19-26
-    "k*(dr-v0)^2;dr=periodicdistance(x,y,z,xh,yh,zh);xh=ra_r*xa+x0;yh=ra_r*ya+y0;zh=ra_r*za+z0;ra_r=xa*x+ya*y+za*z";
-const char* kHarmonicCoMPulling = "0.5*k*(distance(g1,g2)-v0)^2";                // HarmonicCoMPullingForceFieldGenerator.cpp:5-7
-const char* kCombinatorialGoContact = "k*(5*(r0/distance(a1,d1))^12-6*(r0/distance(a1,d1))^10)";  // CombinatorialGoContact...cpp:5-10
+    "(radius/(z_upper-z))^12)");
+const std::string kCylindricalRestraint = canonical(  // CylindricalRestraintForceFieldGenerator.cpp:10-17
+    "k*(dr-v0)^2;dr=((x-xh)^2+(y-yh)^2+(z-zh)^2)^(1/2);xh=ra_r*xa+x0;yh=ra_r*ya+y0;zh=ra_r*za+z0;ra_r=xa*x+ya*y+za*z");
+const std::string kCylindricalRestraintPeriodic = canonical(  // CylindricalRestraintForceFieldGenerator.cpp:19-26
+    "k*(dr-v0)^2;dr=periodicdistance(x,y,z,xh,yh,zh);xh=ra_r*xa+x0;yh=ra_r*ya+y0;zh=ra_r*za+z0;ra_r=xa*x+ya*y+za*z");
+const std::string kHarmonicCoMPulling = canonical("0.5*k*(distance(g1,g2)-v0)^2");                // HarmonicCoMPullingForceFieldGenerator.cpp:5-7
+const std::string kCombinatorialGoContact = canonical("k*(5*(r0/distance(a1,d1))^12-6*(r0/distance(a1,d1))^10)");  // CombinatorialGoContact...cpp:5-10
 
 }  // namespace
 
@@ -253,8 +271,9 @@ class SystemCompiler {
         const std::size_t us = prefix.rfind('_');
         prefix = us == std::string::npos ? std::string() : prefix.substr(0, us + 1);
         auto strip = [&](const std::string& s) { return (!prefix.empty() && s.compare(0, prefix.size(), prefix) == 0) ? s.substr(prefix.size()) : s; };
-        nz.expr = strip_ws(f.expr_);
+        nz.expr = f.expr_;
         replace_all(nz.expr, prefix, "");
+        nz.expr = canonical(nz.expr);
         for (auto& p : f.params_) nz.params.push_back(strip(p));
         if (aparams) for (auto& p : *aparams) nz.aparams.push_back(strip(p));
         for (auto& g : f.globals_) nz.globals.push_back(strip(g.first));

@@ -73,6 +73,20 @@ def test_host_layer_is_built(built):
     assert os.path.exists(COMPAT_SO), "libocm_openmm_compat.so missing: __graft_entry__.build() must produce it"
 
 
+def test_host_layer_recognises_expressions_in_canonical_form(built, tmp_path):
+    """tests/c/compat_expressions.cpp: a generator's expression is found whatever the order and spacing of its auxiliary
+    definitions; a changed energy (or an expression that is not the reference's) is refused with an exception"""
+    libdir = os.path.dirname(COMPAT_SO)
+    exe = tmp_path / "compat_expressions"
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "opencafemol_b200", "csrc", "compat"),
+           os.path.join(ROOT, "tests", "c", "compat_expressions.cpp"), "-o", str(exe), "-L", libdir, "-locm_openmm_compat", "-locm_b200",
+           "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 needs_frontend = pytest.mark.skipif(not os.path.exists(BIN), reason="bin/open_cafemol_b200 is built where the reference tree is mounted")
 
 

@@ -457,3 +457,40 @@ def test_cpu_arm_verlet_lists_reproduce_the_cell_list_path(oracle):
             assert ctx.get_option("cpu_verlet_builds") >= 3
     assert np.abs(out[0]["positions"] - out[1]["positions"]).max() < 1e-10
     assert np.abs(out[0]["velocities"] - out[1]["velocities"]).max() < 1e-9
+
+
+def test_external_terms_closed_form_statistics(oracle):
+    """Physics known answers for two external generators through the whole Langevin path (sign and scale of the forces):
+    a bead in the PositionRestraint well k |x - x0|^2 holds 3/2 kT of potential energy on average (equipartition), and a bead
+    under a constant Pulling force f drifts with the terminal velocity f / (m gamma)."""
+    kT = 8.31446261815324e-3 * 300.0
+    n = 64   # independent beads = independent samples
+    s = System(oracle, np.full(n, 40.0), None)
+    x0 = np.random.default_rng(1).normal(scale=3.0, size=(n, 3))
+    s.add_position_restraint(0, np.arange(n), x0, np.full(n, 25.0), np.zeros(n))
+    c = Context(s, 300.0, 2.0, 0.01, seed=11)
+    c.set_positions(x0 + 0.05)
+    c.set_velocities_to_temperature(300.0, 5)
+    c.step(2000)
+    e = []
+    for _ in range(150):
+        c.step(40)
+        e.append(c.get_state(energy=True)["potential_energy"] / n)
+    e = np.array(e)
+    assert e.mean() == pytest.approx(1.5 * kT, rel=0.06), (e.mean(), 1.5 * kT)
+
+    m, gamma, f = 40.0, 2.0, np.array([30.0, -12.0, 0.0])
+    s = System(oracle, np.full(n, m), None)
+    s.add_pulling(0, np.arange(n), np.tile(f, (n, 1)))
+    c = Context(s, 300.0, gamma, 0.01, seed=12)
+    c.set_positions(np.zeros((n, 3)))
+    c.set_velocities_to_temperature(300.0, 6)
+    c.step(1000)                     # several 1 / gamma: the drift has reached its terminal value
+    a = c.get_state(positions=True)["positions"].mean(0)
+    c.step(4000)
+    b = c.get_state(positions=True)["positions"].mean(0)
+    v = (b - a) / (4000 * 0.01)
+    vt = f / (m * gamma)
+    # thermal spread of the mean displacement over 40 ps: sqrt(2 D t / n), D = kT / (m gamma)
+    tol = 4.0 * np.sqrt(2.0 * kT / (m * gamma) * 40.0 / n) / 40.0
+    assert np.all(np.abs(v - vt) < tol + 0.02 * np.abs(vt)), (v, vt, tol)

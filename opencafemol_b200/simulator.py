@@ -1,5 +1,5 @@
-"""The reference's run loop and observers on the C ABI, in Python: `python -m opencafemol_b200 input.toml` runs a TOML input
-end to end on the B200 engine and writes the files the reference writes (.ene, _position.dcd / _velocity.dcd or .pdb), without
+"""The reference's run loop and observers on the C ABI, in Python: `python -m opencafemol_b200 input.toml | input.inp` runs a TOML or
+GENESIS input end to end on the B200 engine and writes the files the reference writes (.ene, _position.dcd / _velocity.dcd or .pdb), without
 the reference tree (the drop-in build `bin/open_cafemol_b200` compiles the reference's own front end and needs it).
 
 What is restated here, with the reference file:line it follows:
@@ -145,6 +145,14 @@ class Simulator:
         else:
             raise RuntimeError("[error] output file format `" + str(fmt) + "` is not supported.")
         self.observers.append(EnergyObserver(prefix, spec.group_ids))
+        if "initial_pdb" in out:
+            # GENESIS path: the input structure goes to `pdbfile` before the run (src/input/ReadGenesisInput.cpp:404-435)
+            ip = out["initial_pdb"]
+            with open(os.path.join(workdir, ip["file"]), "w") as fh:
+                fh.write("MODEL     0\n")
+                for i, p in enumerate(spec.positions * ANGSTROM_PER_NM):
+                    fh.write("ATOM  %5d %s %s     1    %8.3f%8.3f%8.3f  1.00  0.00\n" % (i + 1, ip["atom_names"][i], ip["res_names"][i], p[0], p[1], p[2]))
+                fh.write("ENDMDL\n")
         # Simulator ctor + initialize + set_velocity (make_context); the minimiser runs between positions and velocities in the
         # reference, which is the same thing: it does not touch velocities
         self.ctx = ti.make_context(lib, spec, device=device)
@@ -173,12 +181,20 @@ class Simulator:
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     if len(argv) != 1 or argv[0] in ("-h", "--help"):
-        print("usage: python -m opencafemol_b200 <input.toml>", file=sys.stderr)
+        print("usage: python -m opencafemol_b200 <input.toml> or <input.inp>", file=sys.stderr)
         return 2
     from .capi import product_library
 
     lib = product_library()   # raises when the CUDA extension is missing; ocm_context_create refuses to run without a GPU
-    spec = ti.read_toml(argv[0])
+    if argv[0].endswith(".toml"):
+        spec = ti.read_toml(argv[0])
+    elif argv[0].endswith(".inp"):
+        from .genesis_input import read_genesis
+
+        spec = read_genesis(argv[0])
+    else:
+        print("usage: python -m opencafemol_b200 <input.toml> or <input.inp>", file=sys.stderr)
+        return 2
     device = int(spec.platform.get("properties", {}).get("DeviceIndex", 0)) if isinstance(spec.platform, dict) else 0
     sim = Simulator(lib, spec, workdir=".", device=device)
     print(f"system of {spec.mass.size} beads, {sim.total_step} steps, a frame every {sim.save_step}", file=sys.stderr)

@@ -879,7 +879,9 @@ def _read_global(spec, gf, topo, periodic, attr):
         )
     elif pot in ("LennardJonesRepulsive", "LennardJonesAttractive"):
         if "table" in gf:
-            raise NotImplementedError("UniformLennardJonesAttractive is not in scope yet")
+            if pot != "LennardJonesAttractive":
+                raise RuntimeError(f"[error] invalid potential {pot} with a parameter table found.")
+            return _uniform_pair(spec, gf, topo, periodic, "lj_attractive")
         ratio = float(_param(gf, env, "cutoff", 2.5))
         eps = np.full(n, np.nan)
         sig = np.full(n, np.nan)
@@ -897,9 +899,9 @@ def _read_global(spec, gf, topo, periodic, attr):
     elif pot == "WCA":
         # read_toml_weeks_chandler_andersen_ff_generator (ReadTOMLForceFieldGenerator.cpp:1238-1293) and the generator's
         # cutoff (WeeksChandlerAndersenForceFieldGenerator.cpp:49-96): (max + 2nd max sigma)/2 * 2^(1/6), "<=" updates.
-        # The name-pair table form (UniformWeeksChandlerAndersen) is served through the C++ host layer only.
+        # The name-pair table form (UniformWeeksChandlerAndersen): _uniform_pair.
         if "table" in gf:
-            raise NotImplementedError("UniformWeeksChandlerAndersen (table form): use the C++ host layer")
+            return _uniform_pair(spec, gf, topo, periodic, "wca")
         eps = np.full(n, np.nan)
         sig = np.full(n, np.nan)
         for p in params:
@@ -937,6 +939,80 @@ def _read_global(spec, gf, topo, periodic, attr):
             spec.add_term(Term("trigonometric", pot, dict(rc=(mr + sr) * 0.5, eps=eps, sigma=sig, omega=om, topo=topo_for(has))))
     else:
         raise NotImplementedError(f"global force field {pot} is not in scope yet")
+
+
+def _uniform_groups(former, latter, ignore_group_pairs, group_vec):
+    """interaction groups of the uniform (name-pair table) pair potentials: the constructor of
+    UniformWeeksChandlerAndersenForceFieldGenerator.cpp:9-131 (UniformLennardJonesAttractive...cpp has the same code)"""
+    if not ignore_group_pairs:
+        return [(sorted(set(former)), sorted(set(latter)))]
+    related = sorted({g for pr in ignore_group_pairs for g in pr})
+
+    def split(members):
+        by_group, others = {g: set() for g in related}, set()
+        for i in members:
+            g = group_vec[i]
+            if g is not None and g in by_group:
+                by_group[g].add(i)
+            else:
+                others.add(i)
+        return by_group, others
+
+    fmap, fothers = split(former)
+    lmap, lothers = split(latter)
+    out = []
+    if fothers:
+        for g in related:
+            if lmap[g]:
+                out.append((sorted(fothers), sorted(lmap[g])))
+        if lothers:
+            out.append((sorted(fothers), sorted(lothers)))
+    pairs = {tuple(pr) for pr in ignore_group_pairs}
+    for g1 in related:
+        if not fmap[g1]:
+            continue
+        if lothers:
+            out.append((sorted(fmap[g1]), sorted(lothers)))
+        for g2 in related:
+            if (g1, g2) not in pairs and lmap[g2]:
+                out.append((sorted(fmap[g1]), sorted(lmap[g2])))
+    return out
+
+
+def _uniform_pair(spec, gf, topo, periodic, kind):
+    """WCA / LennardJonesAttractive with a residue-name pair table: one uniform Force per table entry, acting between the beads
+    named `first` and the beads named `second` (ReadTOMLInput.cpp:437-499 and :548-610; readers ReadTOMLForceFieldGenerator.cpp:1306-1358
+    and :1508-1562).  All entries share one generator name, hence one force group, whatever order the reference's (unordered) table
+    is walked in; an entry without beads on either side is skipped."""
+    env = gf.get("env")
+    n = topo.size()
+    excl, gpairs = _read_ignore(gf, topo) if "ignore" in gf else (np.zeros((0, 2), np.int32), [])
+    who = ("read_toml_uniform_weeks_chandler_andersen_ff_generator" if kind == "wca"
+           else "read_toml_uniform_lennard_jones_attractive_ff_generator")
+    named = [(p["name"], _index(p, env, who, n)) for p in gf["parameters"]]
+    seen = set()
+    for first, sub in gf["table"].items():
+        for second, tab in sub.items():
+            if (first, second) in seen:
+                raise RuntimeError(f"[error] parameter table for {first}-{second} is defined in dupulicate.")
+            sigma = float(_either(tab, "sigma", "σ")) * NM_PER_ANGSTROM
+            eps = float(_either(tab, "epsilon", "ε")) * KJ_PER_KCAL
+            former = [i for nm, i in named if nm == first]
+            latter = [i for nm, i in named if nm == second]
+            if not former or not latter:
+                continue
+            seen.add((first, second))
+            ig = _uniform_groups(former, latter, gpairs, spec.groups)
+            sg, ep = np.full(n, np.nan), np.full(n, np.nan)
+            for a, b in ig:
+                for i in list(a) + list(b):
+                    sg[i], ep[i] = sigma, eps
+            tp = PairTopology(excl=excl, igroups=ig, periodic=periodic)
+            if kind == "wca":
+                spec.add_term(Term("wca", "UniformWeeksChadlerAndersen", dict(rc=sigma * 2.0 ** (1.0 / 6.0), eps=ep, sigma=sg, topo=tp)))
+            else:
+                rc = sigma * float(_param(gf, env, "cutoff", 2.5))
+                spec.add_term(Term("lj_attractive", "UniformLennardJonesAttractive", dict(rc=rc, r_switch=0.9 * rc, eps=ep, sigma=sg, topo=tp)))
 
 
 def _combinatorial_go(spec, gf, topo, periodic):

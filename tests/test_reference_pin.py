@@ -78,6 +78,38 @@ def test_oracle_matches_reference_vectors(oracle, name):
     assert spec.temperature == integ["temperature"] and spec.seed == integ["seed"]
 
 
+def test_oracle_matches_reference_vectors_name_pair_tables(oracle):
+    """"wcamix" (tests/golden/make_ref_golden.py: per-particle WCA, the name-pair table forms UniformWeeksChandlerAndersen and
+    UniformLennardJonesAttractive, capped Go contacts): this repository's reader on the input the reference ran, the oracle against the
+    reference's energies and forces"""
+    gold = load_ref("wcamix")
+    with gzip.open(os.path.join(GOLDEN, "ref_wcamix_run.toml.gz"), "rt") as fh:
+        spec = ti.read_toml(tomllib.loads(fh.read()))
+    assert spec.group_ids == gold["group_map"]
+    ctx = ti.make_context(oracle, spec)
+    ctx.set_positions(np.array(gold["positions"]))
+    st = ctx.get_state(forces=True, energy=True)
+    for k, g in spec.group_ids.items():
+        assert st["energy_by_group"][g] == pytest.approx(gold["energy_by_group_kj"][k], rel=1e-10, abs=1e-9), k
+    assert force_error(st["forces"], np.array(gold["forces"])).max() < 1e-9
+    # the digest of the Forces the reference built: one CustomNonbondedForce per table entry, same cutoffs and interaction groups
+    ref_nb = [f for f in gold["force_digest"] if f["class"] == "CustomNonbondedForce"]
+    mine_nb = [t for t in spec.terms if t.kind in PAIR_KINDS]
+    assert len(ref_nb) == len(mine_nb) == 7
+
+    def key(cut, groups):
+        return (round(cut, 9), tuple(sorted(groups)))
+    ref_keys = sorted(key(r["cutoff"], [(a, b, sha) for a, b, sha in r["interaction_groups"]]) for r in ref_nb)
+    mine_keys = []
+    for t in mine_nb:
+        groups = []
+        for a, b in t.args["topo"].igroups:
+            a, b = sorted(map(int, a)), sorted(map(int, b))
+            groups.append((len(a), len(b), hashlib.sha1(np.asarray(a + b, np.int32).tobytes()).hexdigest()))
+        mine_keys.append(key(t.args["rc"], groups))
+    assert sorted(mine_keys) == ref_keys   # (the reference walks its table in unordered_map order: compare as sets)
+
+
 def test_oracle_matches_reference_fus100_full_size(oracle):
     """sample/toml_input/FUS_100_HPS.toml at full size (16 300 beads, config C2's sample): the oracle against the reference's own
     energies and forces at relaxed coordinates (tests/golden/make_ref_fus100.py)."""

@@ -611,6 +611,10 @@ def _read_local(spec, lf, topo, periodic):
             )
     elif inter == "3SPN2BaseStacking" and pot in ("3SPN2", "3SPN2C"):
         _base_stacking(spec, lf, params, env, topo, periodic, pot)
+    elif inter == "3SPN2BasePairLocal" and pot in ("3SPN2", "3SPN2C"):
+        _base_pair_local(spec, lf, params, env, topo, periodic, pot)
+    elif inter == "3SPN2CrossStackingLocal" and pot in ("3SPN2", "3SPN2C"):
+        _cross_stacking_local(spec, lf, params, env, topo, periodic, pot)
     else:
         raise NotImplementedError(f"local force field {inter}/{pot} is not in scope yet")
 
@@ -742,6 +746,98 @@ def _cross_stacking(spec, gf, topo, periodic, pot):
             spec.add_term(Term("3spn2_cross_stacking", f"{pot}CrossStacking ({first}-{second})",
                                dict(topo=t, eps=[m["epsilon_CS"][k] for k in acc_kind], r0=[m["r0_CS"][k] for k in acc_kind],
                                     theta0_3=[m["theta3_0"][first + second]] * len(acc), theta0_CS=[m["theta_CS_0"][k] for k in acc_kind],
+                                    K_BP=sc["K_BP"], K_CS=sc["K_CS"], alpha=sc["alpha_CS"])))
+
+
+# The *Local forms: the same energies over an explicit list of nucleotide pairs (CustomCompoundBondForce in the reference, no
+# cutoff).  On the C ABI they are donor x acceptor terms in which entry i contributes donor i and acceptor i and every other
+# combination is excluded, evaluated inside LOCAL_PAIR_RANGE (beyond r0 + 1.9 nm the energy is below eps 2 exp(-alpha 1.9 nm)
+# < 1e-15 kJ/mol): the mapping the C++ host layer uses (openmm_compat.cpp, kLocalPairRange).
+LOCAL_PAIR_RANGE = 2.5
+
+
+def _local_da_topology(donors, acceptors, periodic):
+    m = len(donors)
+    excl = np.array([[d, a] for d in range(m) for a in range(m) if a != d], np.int32).reshape(-1, 2)
+    return DATopology(donors=np.array(donors, np.int32).reshape(-1, 3), acceptors=np.array(acceptors, np.int32).reshape(-1, 3),
+                      cutoff=LOCAL_PAIR_RANGE, excl=excl, periodic=periodic)
+
+
+def _reserve_group(spec, name):
+    """a generator without entries still takes its force-group number (SystemGenerator::add_ff_generator is unconditional)"""
+    spec.group_ids.setdefault(name, len(spec.group_ids))
+
+
+def _base_pair_local(spec, lf, params, env, topo, periodic, pot):
+    """read_toml_3spn2_base_pair_local_ff_generator x {A-T, G-C} (ReadTOMLForceFieldGenerator.cpp:1565-1643, ReadTOMLInput.cpp:313-353)
+    and ThreeSPN2BasePairLocalForceFieldGenerator.cpp: particles (p1, p2, p3, p4) = (sugar, base, paired base, its sugar)"""
+    tab = tables_3spn2()["ThreeSPN2BasePairPotentialParameter" if pot == "3SPN2" else "ThreeSPN2CBasePairPotentialParameter"]
+    m, sc = tab["maps"], tab["scalars"]
+    for b0, b1 in (("A", "T"), ("G", "C")):
+        quads = []
+        for p in params:
+            pair = p["nucleotide_pair"]
+            if len(pair) != 2:
+                raise RuntimeError("[error] invalid toml array size.The array size of nucleotide_pair must be 2.")
+            s0, s1 = pair[0]["Base"], pair[1]["Base"]
+            if s0 == b0 and s1 == b1:
+                quads.append([_param(pair[0], env, "S"), _param(pair[0], env, "B"), _param(pair[1], env, "B"), _param(pair[1], env, "S")])
+            elif s0 == b1 and s1 == b0:
+                quads.append([_param(pair[1], env, "S"), _param(pair[1], env, "B"), _param(pair[0], env, "B"), _param(pair[0], env, "S")])
+        if "topology" in lf:
+            topo.add_edges(quads, lf["topology"])
+        name, kind, nd = f"{pot}BasePairLocal ({b0}-{b1})", b0 + b1, len(quads)
+        if not quads:
+            _reserve_group(spec, name)
+            continue
+        t = _local_da_topology([[q[1], q[0], -1] for q in quads], [[q[2], q[3], -1] for q in quads], periodic)
+        spec.add_term(Term("3spn2_base_pair", name,
+                           dict(topo=t, eps=np.full(nd, m["epsilon_BP"][kind]), r0=np.full(nd, m["r0"][kind]),
+                                theta0_1=np.full(nd, m["theta0_1"][kind]), theta0_2=np.full(nd, m["theta0_2"][kind]),
+                                phi0=np.full(nd, m["phi0"][kind]), alpha=sc["alpha_BP"], K_BP=sc["K_BP"])))
+
+
+def _cross_stacking_local(spec, lf, params, env, topo, periodic, pot):
+    """read_toml_3spn2_cross_stacking_local_ff_generator x {A-T, T-A, G-C, C-G} x {sense, antisense}
+    (ReadTOMLForceFieldGenerator.cpp:1774-1901, ReadTOMLInput.cpp:355-410) and ThreeSPN2CrossStackingLocalForceFieldGenerator.cpp:
+    particles (p1..p6) = (sugar, base, paired base, its sugar, neighbouring base, cross base); nucleotide_group = [reference,
+    base-pairing, neighbouring, cross-stacking nucleotide]"""
+    tab = tables_3spn2()["ThreeSPN2CrossStackingPotentialParameter" if pot == "3SPN2" else "ThreeSPN2CCrossStackingPotentialParameter"]
+    m, sc = tab["maps"], tab["scalars"]
+
+    def six(g, order):
+        a, b, c, d, e, f = order   # nucleotide numbers giving S, B, B, S, B, B
+        return [_param(g[a], env, "S"), _param(g[b], env, "B"), _param(g[c], env, "B"), _param(g[d], env, "S"), _param(g[e], env, "B"),
+                _param(g[f], env, "B")]
+
+    for first, second in (("A", "T"), ("T", "A"), ("G", "C"), ("C", "G")):
+        for strand_kind in ("sense", "antisense"):
+            rows, kinds = [], []
+            for p in params:
+                g = p["nucleotide_group"]
+                if len(g) != 4:
+                    raise RuntimeError("[error] invalid toml array size.The array size of nucleotide_group must be 4.")
+                b_0, b_p, b_n, b_c = (x["Base"] for x in g)
+                if strand_kind == "sense":
+                    if b_0 == first and b_p == second:
+                        rows.append(six(g, (0, 0, 1, 1, 2, 3))); kinds.append(b_0 + b_c + "5")
+                    if b_c == first and b_n == second:
+                        rows.append(six(g, (3, 3, 2, 2, 1, 0))); kinds.append(b_c + b_0 + "5")
+                else:
+                    if b_0 == first and b_p == second:
+                        rows.append(six(g, (1, 1, 0, 0, 3, 2))); kinds.append(b_p + b_n + "3")
+                    if b_c == first and b_n == second:
+                        rows.append(six(g, (2, 2, 3, 3, 0, 1))); kinds.append(b_n + b_p + "3")
+            if "topology" in lf:
+                topo.add_edges(rows, lf["topology"])
+            name = f"{pot}CrossStackingLocal ({first}-{second})"
+            if not rows:
+                _reserve_group(spec, name)
+                continue
+            t = _local_da_topology([[r[1], r[0], -1] for r in rows], [[r[2], r[3], r[5]] for r in rows], periodic)
+            spec.add_term(Term("3spn2_cross_stacking", name,
+                               dict(topo=t, eps=[m["epsilon_CS"][k] for k in kinds], r0=[m["r0_CS"][k] for k in kinds],
+                                    theta0_3=[m["theta3_0"][first + second]] * len(rows), theta0_CS=[m["theta_CS_0"][k] for k in kinds],
                                     K_BP=sc["K_BP"], K_CS=sc["K_CS"], alpha=sc["alpha_CS"])))
 
 

@@ -110,6 +110,23 @@ def test_oracle_matches_reference_vectors_name_pair_tables(oracle):
     assert sorted(mine_keys) == ref_keys   # (the reference walks its table in unordered_map order: compare as sets)
 
 
+def test_oracle_matches_reference_vectors_local_dna_terms(oracle):
+    """"dna_localize" (sample/toml_input/dna_3SPN2_localize.toml: 3SPN2BasePairLocal / 3SPN2CrossStackingLocal, explicit nucleotide pairs):
+    this repository's reader on the input the reference ran, the oracle against the reference's energies and forces"""
+    gold = load_ref("dna_localize")
+    with gzip.open(os.path.join(GOLDEN, "ref_dna_localize_run.toml.gz"), "rt") as fh:
+        spec = ti.read_toml(tomllib.loads(fh.read()))
+    assert spec.group_ids == gold["group_map"]
+    ctx = ti.make_context(oracle, spec)
+    ctx.set_positions(np.array(gold["positions"]))
+    st = ctx.get_state(forces=True, energy=True)
+    escale = max(max(abs(v) for v in gold["energy_by_group_kj"].values()), 1.0)
+    for k, g in spec.group_ids.items():
+        ref = gold["energy_by_group_kj"][k]
+        assert abs(st["energy_by_group"][g] - ref) <= 1e-10 * max(abs(ref), 1e-3 * escale), (k, st["energy_by_group"][g], ref)
+    assert force_error(st["forces"], np.array(gold["forces"])).max() < 1e-9
+
+
 def test_oracle_matches_reference_fus100_full_size(oracle):
     """sample/toml_input/FUS_100_HPS.toml at full size (16 300 beads, config C2's sample): the oracle against the reference's own
     energies and forces at relaxed coordinates (tests/golden/make_ref_fus100.py)."""

@@ -616,7 +616,7 @@ def _read_local(spec, lf, topo, periodic):
     elif inter == "3SPN2CrossStackingLocal" and pot in ("3SPN2", "3SPN2C"):
         _cross_stacking_local(spec, lf, params, env, topo, periodic, pot)
     else:
-        raise NotImplementedError(f"local force field {inter}/{pot} is not in scope yet")
+        raise RuntimeError(f"[error] invalid local force field: interaction {inter} with potential {pot} is none of the reference's (ReadTOMLInput.cpp:125-420)")
 
 
 _T3 = None
@@ -1034,7 +1034,7 @@ def _read_global(spec, gf, topo, periodic, attr):
             mr, sr = _two_largest((sig + om)[has], strict=False)
             spec.add_term(Term("trigonometric", pot, dict(rc=(mr + sr) * 0.5, eps=eps, sigma=sig, omega=om, topo=topo_for(has))))
     else:
-        raise NotImplementedError(f"global force field {pot} is not in scope yet")
+        raise RuntimeError(f"[error] invalid global force field: potential {pot} is none of the reference's (ReadTOMLInput.cpp:422-760)")
 
 
 def _uniform_groups(former, latter, ignore_group_pairs, group_vec):
